@@ -1,0 +1,155 @@
+/*
+ * hp3d_oracle.h -- CPU restatement ("oracle") of hp3D's element-local hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+ *
+ * Pinning status: the reference (Fortran 90 + PETSc/MUMPS) cannot be built in this image (no
+ * Fortran compiler), and its test-suite holds no numeric golden vectors for this path.  The oracle is
+ * pinned on the reference's own *analytic* known-answer tests instead (tests/test_oracle_*.py):
+ *   - integer encodings: trunk/test/decode.F90, encod_decod.F90, ij_to_packed.F90 (exact);
+ *   - trunk/test/poly_pois.F90:101  (u=xyz reproduced to 1e-15 through elem + stc + solve);
+ *   - trunk/test/poly_maxw.F90:101  (polynomial E reproduced to 1e-14, complex);
+ *   - BLAS3 `elem_opt` == scalar-loop `elem_*` twins, exact-sequence identities.
+ * DPG element matrices, Cholesky condensation and p>=3 are "parity unpinned" by the reference's own
+ * tests; the oracle adds the self-consistency pins listed above.
+ *
+ * Every function cites the reference file:line (relative to /root/reference/trunk) it follows.
+ * All matrices are column-major (Fortran order); complex = interleaved (re,im) = complex(8).
+ */
+#ifndef HP3D_ORACLE_H
+#define HP3D_ORACLE_H
+#include <complex.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef double _Complex zdouble;
+
+#define ORC_MAXP 9                 /* highest order incl. enrichment (Gauss table has <=10 points) */
+#define ORC_MAXN (ORC_MAXP + 1)
+#define ORC_MAXBRICK_H ((ORC_MAXP + 1) * (ORC_MAXP + 1) * (ORC_MAXP + 1))
+#define ORC_MAXBRICK_E (3 * ORC_MAXP * (ORC_MAXP + 1) * (ORC_MAXP + 1))
+
+/* ---- integer encodings: src/utility/decod.F90:21, encod.F90:21, decode.F90:19, ij_to_packed.F90:15 */
+void orc_decod(int nick, int mod, int n, int *narray);
+void orc_encod(const int *narray, int mod, int n, int *nick);
+void orc_decode(int nick, int *j1, int *j2);
+void orc_decode2(int nick, int *j1, int *j2);
+void orc_ddecode(int nick, int *j1, int *j2, int *j3);
+int orc_ij_upper_to_packed(int i, int j);
+int orc_ij_lower_to_packed(int i, int j, int n);
+
+/* ---- limits (src/modules/parameters.F90:17 MAXP, parametersDPG.F90:14 MAXPP=MAXP+1) */
+void orc_set_maxp(int maxp);
+int orc_get_maxp(void);
+
+/* ---- 1-D polynomials: src/element/shape_1/Polynomials.F90:34,109,455,497 */
+void orc_poly_legendre(double x, double t, int nord, double *P /*0..nord*/);
+void orc_poly_ilegendre(double x, double t, int nord, int idec, double *L /*[2..nord]*/,
+                        double *P /*[1..nord-1]*/, double *R /*[1..nord-1]*/);
+
+/* ---- Gauss rule on [0,1]: src/element/quadrature/gauss_quadrature.F90:518-651,749-750 */
+void orc_gauss1(int n, double *xi /*n*/, double *w /*n*/);
+
+/* ---- hexahedron shape functions: src/element/shape_1/Hexahedron.F90:33,240,468,634 */
+int orc_shape3DH_hexa(const double xi[3], const int nord[19], const int norie[12], const int norif[6],
+                      double *shapH, double *gradH /*(3,n)*/);
+int orc_shape3DE_hexa(const double xi[3], const int nord[19], const int norie[12], const int norif[6],
+                      double *shapE /*(3,n)*/, double *curlE /*(3,n)*/);
+int orc_shape3DV_hexa(const double xi[3], const int nord[19], const int norif[6], double *shapV /*(3,n)*/,
+                      double *divV);
+int orc_shape3DQ_hexa(const double xi[3], const int nord[19], double *shapQ);
+/* broken (enriched test) functions: src/element/shape_1/broken/BrokenHexahedron.F90:31,139,286,422 */
+int orc_shape1HH(double xi, int nord, double *shapH, double *gradH);
+int orc_shape1QQ(double xi, int nord, double *shapQ);
+int orc_shape3HH_hexa(const double xi[3], int nordM, double *shapH, double *gradH);
+int orc_shape3EE_hexa(const double xi[3], int nordM, double *shapE, double *curlE);
+int orc_shape3VV_hexa(const double xi[3], int nordM, double *shapV, double *divV);
+int orc_shape3QQ_hexa(const double xi[3], int nordM, double *shapQ);
+
+/* ---- dof counts: src/modules/element_data.F90:808 (ndof_nod), src/element/util/celndof.F90:24 */
+void orc_ndof_nod_quad(int nord, int *h, int *e, int *v, int *q);
+void orc_ndof_nod_hexa(int nord, int *h, int *e, int *v, int *q);
+void orc_celndof_hexa(const int nord[19], int *h, int *e, int *v, int *q);
+void orc_compute_enriched_order_hexa(int nordP, int norder[19]); /* MAXWELL/ULTRAWEAK_DPG/elem/elem.F90:147 */
+
+/* ---- quadrature: src/element/quadrature/set_3D_int.F90:47,112,155 ; set_2D_int.F90:121,177 ;
+ *      src/datstrs/find_order.F90:68 (find_order_loc) */
+void orc_find_order_loc_hexa(const int norder[19], const int norif[6], int nloc[19]);
+int orc_set_3D_int_hexa(const int norder[19], const int norif[6], int integration, int maxp,
+                        double *xiloc /*(3,nint)*/, double *waloc);
+int orc_set_2D_int_quad(const int nordf[5], int norif, int integration, int maxp, double *tloc /*(2,nint)*/,
+                        double *wtloc);
+
+/* ---- geometry: src/element/util/geom.F90:30, geom3D.F90:30,149 ; element_data.F90:554,616,750 */
+void orc_geom(const double dxdxi[9], double dxidx[9], double *rjac, int *iflag);
+void orc_geom3D(const double *xnod, const double *shapH, const double *gradH, int nrdofH, double x[3],
+                double dxdxi[9], double dxidx[9], double *rjac, int *iflag);
+void orc_bgeom3D(const double *xnod, const double *shapH, const double *gradH, int nrdofH,
+                 const double dxidt[6], int nsign, double x[3], double dxdxi[9], double dxidx[9], double *rjac,
+                 double dxdt[6], double rn[3], double *bjac);
+void orc_face_param_hexa(int iface, const double t[2], double xi[3], double dxidt[6]);
+int orc_nsign_param_hexa(int iface);
+void orc_face_order_hexa(int iface, const int norder[19], int nordf[5]);
+
+/* ---- dense kernels (BLAS/LAPACK subset the path calls; see dense.c).  If orc_dense_use_blas() finds
+ *      an OpenBLAS it forwards to it, else runs the built-in textbook loops. */
+int orc_dense_use_blas(const char *libpath); /* returns 1 if loaded */
+void orc_dense_set_threads(int n);
+
+/* ---- problem parameters shared by the element routines */
+typedef struct {
+  int nord_add;       /* parametersDPG.F90 NORD_ADD (enrichment dp)                 */
+  int test_norm;      /* MAXWELL/UW commonParam: 1=GRAPH_NORM (adjoint graph), 2=MATH_NORM, 3=GRAPH_DIAG */
+  double alpha_norm;  /* ALPHA_NORM                                                  */
+  double omega, eps, mu, sigma;
+  zdouble eps_tensor[9]; /* get_permittivity (column-major 3x3); identity by default */
+  int source;         /* 0: none, 1: manufactured "sin" (isol=1), 2: polynomial (isol=2), 9: table */
+  int icomp_exact;    /* ICOMP_EXACT (1..3) for Maxwell manufactured solutions       */
+  const void *source_table; /* optional per-quadrature-point source values (source==9) */
+} orc_params;
+void orc_params_default(orc_params *p);
+
+/* ---- element routines (BLAS3 formulation).  Outputs are dense column-major blocks sized exactly.
+ *  POISSON/GALERKIN/elem_opt.F90:22 */
+int orc_elem_poisson_galerkin(const int norder[19], const int norie[12], const int norif[6], const double *xnod,
+                              const orc_params *prm, double *Aloc /*(n,n)*/, double *Bloc /*n*/, int *n);
+/*  POISSON/PRIMAL_DPG/elem_opt.F90:32 : trial = [H1 (nH) | H(div) trace (nVi)] */
+int orc_elem_poisson_primal_dpg(const int norder[19], const int norie[12], const int norif[6],
+                                const double *xnod, const orc_params *prm, double *Aloc /*(nt,nt)*/,
+                                double *Bloc /*nt*/, int *nH, int *nVi);
+/*  MAXWELL/GALERKIN/elem_opt.F90:22 */
+int orc_elem_maxwell_galerkin(const int norder[19], const int norie[12], const int norif[6], const double *xnod,
+                              const orc_params *prm, zdouble *Aloc, zdouble *Bloc, int *n);
+/*  MAXWELL/ULTRAWEAK_DPG/elem/elem_opt.F90:25 : trial = [2*nEi trace | 6*nQ field]; also returns
+ *  the enriched stiffness/Gram when the pointers are non-NULL (for kernel-level parity tests).   */
+int orc_elem_maxwell_uw_dpg(const int norder[19], const int norie[12], const int norif[6], const double *xnod,
+                            const orc_params *prm, zdouble *Aloc /*(nt,nt)*/, zdouble *Bloc /*nt*/, int *nEi,
+                            int *nQ, zdouble *gram_out /*(nTest,nTest) upper*/,
+                            zdouble *stiff_out /*(nTest,nt+1)*/);
+
+/* ---- static condensation: src/modules/stc.F90:338 (herm), :443 (gen).  A is (ni+nb)^2 with the
+ *  interface dofs first; on exit Aii/Bi hold the condensed system, ASchur=(nb,ni), BSchur=nb. */
+int orc_stc_fwd_real(int herm, int ni, int nb, double *Aii, double *Abi, double *Aib, double *Abb, double *Bi,
+                     double *Bb);
+int orc_stc_fwd_cplx(int herm, int ni, int nb, zdouble *Aii, zdouble *Abi, zdouble *Aib, zdouble *Abb,
+                     zdouble *Bi, zdouble *Bb);
+
+/* ---- whole unit of work (elem + stc_fwd_wrapper) for one element; problem_kind as in include/hp3d_gpu.h */
+int orc_condensed_element(int problem_kind, const int norder[19], const int norie[12], const int norif[6],
+                          const double *xnod, const orc_params *prm, void *Aii, void *Bi, void *ASchur,
+                          void *BSchur, int *ni, int *nb);
+/* interface/bubble permutation of the full local matrix (stc.F90:226-261): perm[k] = local dof index */
+int orc_stc_partition(int problem_kind, const int norder[19], int *perm, int *ni, int *nb);
+
+/* OpenMP element loop shaped like par_mumps_sc.F90:318-357 (used for the CPU baseline) */
+int orc_condensed_batch(int problem_kind, int nel, const int *norder, const int *norie, const int *norif,
+                        const double *xnod, int xnod_stride, const orc_params *prm, void *Aii, void *Bi,
+                        void *ASchur, void *BSchur, long sAii, long sBi, long sAS, long sBS, int *info,
+                        int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,274 @@
+"""ctypes front-end of the CPU oracle (oracle/libhp3d_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product package (hp3d_b200) never imports this module.
+"""
+import ctypes as C
+import glob
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+POIS_GAL, POIS_PDPG, MAXW_GAL, MAXW_UW = 1, 2, 3, 4
+
+
+class Params(C.Structure):
+    _fields_ = [("nord_add", C.c_int), ("test_norm", C.c_int), ("alpha_norm", C.c_double),
+                ("omega", C.c_double), ("eps", C.c_double), ("mu", C.c_double), ("sigma", C.c_double),
+                ("eps_tensor", C.c_double * 18), ("source", C.c_int), ("icomp_exact", C.c_int),
+                ("source_table", C.c_void_p)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libhp3d_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("shape.c", "quad_geom.c", "dense.c", "elem.c", "hp3d_oracle.h", "dense.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libhp3d_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def find_openblas():
+    """The OpenBLAS bundled with scipy in this image (LP64, symbols prefixed scipy_)."""
+    try:
+        import scipy
+        cands = glob.glob(os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs", "libscipy_openblas*.so"))
+        cands = [c for c in cands if "64_" not in os.path.basename(c)]
+        return cands[0] if cands else None
+    except Exception:
+        return None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.orc_dense_use_blas.argtypes = [C.c_char_p]
+        L.orc_dense_use_blas.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def use_blas(on=True, threads=1):
+    L = lib()
+    if not on:
+        L.orc_dense_use_blas(None)
+        return False
+    path = find_openblas()
+    ok = bool(path) and bool(L.orc_dense_use_blas(path.encode()))
+    if ok:
+        L.orc_dense_set_threads(int(threads))
+    return ok
+
+
+def _ip(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _i(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _d(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def default_params(**kw):
+    p = Params()
+    lib().orc_params_default(C.byref(p))
+    for k, v in kw.items():
+        if k == "eps_tensor":
+            t = np.asarray(v, dtype=np.complex128).reshape(3, 3).T.copy().view(np.float64).ravel()  # column-major
+            for i in range(18):
+                p.eps_tensor[i] = t[i]
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def set_maxp(maxp):
+    lib().orc_set_maxp(int(maxp))
+
+
+def uniform_order(p):
+    """norder(19) of an isotropic order-p hexa (find_order.F90:41-58 layout)."""
+    return np.array([p] * 12 + [11 * p] * 6 + [111 * p], dtype=np.int32)
+
+
+def celndof(norder):
+    h, e, v, q = (C.c_int() for _ in range(4))
+    lib().orc_celndof_hexa(_i(_ip(norder)), C.byref(h), C.byref(e), C.byref(v), C.byref(q))
+    return h.value, e.value, v.value, q.value
+
+
+def ndof_mdl(nord):
+    h, e, v, q = (C.c_int() for _ in range(4))
+    lib().orc_ndof_nod_hexa(int(nord), C.byref(h), C.byref(e), C.byref(v), C.byref(q))
+    return h.value, e.value, v.value, q.value
+
+
+def gauss1(n):
+    x = np.zeros(n)
+    w = np.zeros(n)
+    lib().orc_gauss1(n, _d(x), _d(w))
+    return x, w
+
+
+def shape3DH(xi, norder, norie, norif):
+    nH = celndof(norder)[0]
+    s = np.zeros(nH)
+    g = np.zeros((nH, 3))
+    xi = np.ascontiguousarray(xi, dtype=np.float64)
+    n = lib().orc_shape3DH_hexa(_d(xi), _i(_ip(norder)), _i(_ip(norie)), _i(_ip(norif)), _d(s), _d(g))
+    assert n == nH
+    return s, g
+
+
+def shape3DE(xi, norder, norie, norif):
+    nE = celndof(norder)[1]
+    s = np.zeros((nE, 3))
+    c = np.zeros((nE, 3))
+    xi = np.ascontiguousarray(xi, dtype=np.float64)
+    n = lib().orc_shape3DE_hexa(_d(xi), _i(_ip(norder)), _i(_ip(norie)), _i(_ip(norif)), _d(s), _d(c))
+    assert n == nE
+    return s, c
+
+
+def shape3DV(xi, norder, norif):
+    nV = celndof(norder)[2]
+    s = np.zeros((nV, 3))
+    d = np.zeros(nV)
+    xi = np.ascontiguousarray(xi, dtype=np.float64)
+    n = lib().orc_shape3DV_hexa(_d(xi), _i(_ip(norder)), _i(_ip(norif)), _d(s), _d(d))
+    assert n == nV
+    return s, d
+
+
+def shape3DQ(xi, norder):
+    nQ = celndof(norder)[3]
+    s = np.zeros(nQ)
+    xi = np.ascontiguousarray(xi, dtype=np.float64)
+    n = lib().orc_shape3DQ_hexa(_d(xi), _i(_ip(norder)), _d(s))
+    assert n == nQ
+    return s
+
+
+def shape3HH(xi, nordM):
+    n = int(np.prod([d + 1 for d in divmod(nordM // 10, 10)] + [nordM % 10 + 1]))
+    s = np.zeros(n)
+    g = np.zeros((n, 3))
+    xi = np.ascontiguousarray(xi, dtype=np.float64)
+    m = lib().orc_shape3HH_hexa(_d(xi), int(nordM), _d(s), _d(g))
+    assert m == n
+    return s, g
+
+
+def shape3EE(xi, nordM):
+    px, py, pz = nordM // 100, (nordM // 10) % 10, nordM % 10
+    n = px * (py + 1) * (pz + 1) + (px + 1) * py * (pz + 1) + (px + 1) * (py + 1) * pz
+    s = np.zeros((n, 3))
+    c = np.zeros((n, 3))
+    xi = np.ascontiguousarray(xi, dtype=np.float64)
+    m = lib().orc_shape3EE_hexa(_d(xi), int(nordM), _d(s), _d(c))
+    assert m == n
+    return s, c
+
+
+def quad3(norder, norif, integration, maxp):
+    xi = np.zeros((1000, 3))
+    w = np.zeros(1000)
+    n = lib().orc_set_3D_int_hexa(_i(_ip(norder)), _i(_ip(norif)), int(integration), int(maxp), _d(xi), _d(w))
+    return xi[:n].copy(), w[:n].copy()
+
+
+def stc_partition(kind, norder):
+    perm = np.zeros(8192, dtype=np.int32)
+    ni, nb = C.c_int(), C.c_int()
+    r = lib().orc_stc_partition(int(kind), _i(_ip(norder)), _i(perm), C.byref(ni), C.byref(nb))
+    assert r == 0
+    return perm[: ni.value + nb.value].copy(), ni.value, nb.value
+
+
+def elem(kind, norder, norie, norif, xnod, prm, want_dpg=False):
+    """Full (uncondensed) local matrix/load of one element, reference dof ordering. xnod: (nrdofH,3)."""
+    L = lib()
+    norder, norie, norif = _ip(norder), _ip(norie), _ip(norif)
+    xnod = np.ascontiguousarray(xnod, dtype=np.float64)
+    nH, nE, nV, nQ = celndof(norder)
+    bH, bE, bV, bQ = ndof_mdl(int(norder[18]))
+    a1, a2 = C.c_int(), C.c_int()
+    if kind == POIS_GAL:
+        n = nH
+        A = np.zeros((n, n), order="F"); b = np.zeros(n)
+        r = L.orc_elem_poisson_galerkin(_i(norder), _i(norie), _i(norif), _d(xnod), C.byref(prm), _d(A), _d(b), C.byref(a1))
+    elif kind == POIS_PDPG:
+        n = nH + nV - bV
+        A = np.zeros((n, n), order="F"); b = np.zeros(n)
+        r = L.orc_elem_poisson_primal_dpg(_i(norder), _i(norie), _i(norif), _d(xnod), C.byref(prm), _d(A), _d(b), C.byref(a1), C.byref(a2))
+    elif kind == MAXW_GAL:
+        n = nE
+        A = np.zeros((n, n), order="F", dtype=np.complex128); b = np.zeros(n, dtype=np.complex128)
+        r = L.orc_elem_maxwell_galerkin(_i(norder), _i(norie), _i(norif), _d(xnod), C.byref(prm), _d(A), _d(b), C.byref(a1))
+    elif kind == MAXW_UW:
+        n = 2 * (nE - bE) + 6 * nQ
+        A = np.zeros((n, n), order="F", dtype=np.complex128); b = np.zeros(n, dtype=np.complex128)
+        gram = stiff = None
+        gp = sp = None
+        if want_dpg:
+            dp = prm.nord_add
+            nEE = celndof(enriched_order(int(norder[18]) + dp * 111))[1]
+            gram = np.zeros((2 * nEE, 2 * nEE), order="F", dtype=np.complex128)
+            stiff = np.zeros((2 * nEE, n + 1), order="F", dtype=np.complex128)
+            gp, sp = _d(gram), _d(stiff)
+        r = L.orc_elem_maxwell_uw_dpg(_i(norder), _i(norie), _i(norif), _d(xnod), C.byref(prm), _d(A), _d(b), C.byref(a1), C.byref(a2), gp, sp)
+        if want_dpg:
+            assert r == 0
+            return A, b, gram, stiff
+    else:
+        raise ValueError(kind)
+    assert r == 0, r
+    return A, b
+
+
+def enriched_order(nordP):
+    no = np.zeros(19, dtype=np.int32)
+    lib().orc_compute_enriched_order_hexa(int(nordP), _i(no))
+    return no
+
+
+def condensed(kind, norder, norie, norif, xnod, prm):
+    """elem + stc_fwd_wrapper for one element -> Aii, Bi, ASchur, BSchur."""
+    L = lib()
+    norder, norie, norif = _ip(norder), _ip(norie), _ip(norif)
+    xnod = np.ascontiguousarray(xnod, dtype=np.float64)
+    _, ni, nb = stc_partition(kind, norder)
+    dt = np.complex128 if kind >= 3 else np.float64
+    Aii = np.zeros((ni, ni), order="F", dtype=dt); Bi = np.zeros(ni, dtype=dt)
+    AS = np.zeros((nb, ni), order="F", dtype=dt); BS = np.zeros(nb, dtype=dt)
+    a, b = C.c_int(), C.c_int()
+    r = L.orc_condensed_element(int(kind), _i(norder), _i(norie), _i(norif), _d(xnod), C.byref(prm), _d(Aii), _d(Bi), _d(AS), _d(BS), C.byref(a), C.byref(b))
+    assert r == 0, r
+    return Aii, Bi, AS, BS
+
+
+def condensed_batch(kind, norder, norie, norif, xnod, prm, nthreads=1):
+    """OpenMP element loop (par_mumps_sc.F90:318-357 shape).  norder (nel,19), xnod (nel,nrdofH,3)."""
+    L = lib()
+    norder, norie, norif = _ip(norder), _ip(norie), _ip(norif)
+    xnod = np.ascontiguousarray(xnod, dtype=np.float64)
+    nel = norder.shape[0]
+    _, ni, nb = stc_partition(kind, norder[0])
+    dt = np.complex128 if kind >= 3 else np.float64
+    Aii = np.zeros((nel, ni, ni), dtype=dt); Bi = np.zeros((nel, ni), dtype=dt)
+    AS = np.zeros((nel, ni, nb), dtype=dt); BS = np.zeros((nel, nb), dtype=dt)
+    info = np.zeros(nel, dtype=np.int32)
+    L.orc_condensed_batch.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_long, C.c_long,
+                                      C.c_void_p, C.c_int]
+    bad = L.orc_condensed_batch(int(kind), nel, _d(norder), _d(norie), _d(norif), _d(xnod), int(xnod[0].size), C.byref(prm),
+                                _d(Aii), _d(Bi), _d(AS), _d(BS), ni * ni, ni, ni * nb, nb, _d(info), int(nthreads))
+    # per-element blocks are column-major: expose them as (nel, rows, cols)
+    return (np.transpose(Aii, (0, 2, 1)), Bi, np.transpose(AS.reshape(nel, ni, nb), (0, 2, 1)), BS, info, bad)
