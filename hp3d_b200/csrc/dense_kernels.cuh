@@ -1,0 +1,250 @@
+// dense_kernels.cuh -- batched FP64 dense kernels for the DPG normal equations and the element-local
+// static condensation (north-star subsystem 3), hand-written for sm_100a.
+//
+// Replaces, for a whole batch of elements at once, the LAPACK/BLAS calls of
+//   problems/MAXWELL/ULTRAWEAK_DPG/elem/elem_opt.F90:841 (ZPOTRF), :852 (ZTRTRS), :862 (ZHERK)
+//   problems/POISSON/PRIMAL_DPG/elem_opt.F90:417 (DPFTRF), :424 (DTFSM), :430 (DSYRK)
+//   src/modules/stc.F90:355-414 (?TRTTF/?PFTRF/?PFTRS/?GEMM)
+//
+// Layout: every matrix is ROW-major with the contraction index contiguous, complex matrices are PLANAR
+// (a real plane and an imaginary plane `im_off` doubles apart) so that each complex product is four real
+// DMMA (mma.sync.m8n8k4.f64) tile products.  All extents are padded to multiples of TILE=64.
+// The only product form needed anywhere on the path is   C(i,j) = Cin(i,j) + alpha * sum_k A(i,k) conj(B(j,k))
+// (Cholesky panel update, triangular solve by the inverted diagonal block, HERK, Schur update), so there
+// is ONE tensor-core kernel (gemm_nc) plus a small in-shared-memory factor/invert kernel for 64x64 tiles.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hp3d {
+
+constexpr int TILE = 64;      // block size of the factorizations == CTA tile edge
+constexpr int KC = 16;        // k-chunk per pipeline stage
+constexpr int LDS_K = KC + 4; // padded smem row (20 doubles: rows 160 B apart -> conflict-free 8-byte fragment loads)
+constexpr int GEMM_THREADS = 128;
+
+struct MatRef {
+  double *re;          // real plane, already offset to the (0,0) entry of the sub-block addressed by this launch
+  long long im_off;    // imaginary plane = re + im_off (ignored for real problems)
+  long long batch;     // stride between consecutive elements of the batch (doubles)
+  int ld;              // row stride (doubles)
+};
+
+struct GemmArgs {
+  MatRef A, B, Cin, Cout;
+  int K;          // contraction length (multiple of KC)
+  int lower_only; // skip tiles strictly above the block diagonal (blockIdx.y > blockIdx.x + diag_shift)
+  int diag_shift;
+  int use_cin;    // 0: C = alpha*S ; 1: C = Cin + alpha*S
+  double alpha;
+};
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double dneg(double x) { return __longlong_as_double(__double_as_longlong(x) ^ 0x8000000000000000ULL); }
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// One 64x64 output tile per CTA, 4 warps (2x2), each warp a 32x32 sub-tile = 4x4 DMMA tiles.
+// grid = (row tiles, col tiles, batch)
+template <bool CPLX>
+__global__ void __launch_bounds__(GEMM_THREADS, CPLX ? 2 : 3) gemm_nc_kernel(const GemmArgs g) {
+  const int ti = blockIdx.x, tj = blockIdx.y, e = blockIdx.z;
+  if (g.lower_only && tj > ti + g.diag_shift) return;
+  constexpr int NP = CPLX ? 2 : 1;
+  extern __shared__ __align__(16) double smem[];
+  // smem: [stage 2][operand 2][plane NP][TILE][LDS_K]
+  auto sm = [&](int stage, int op, int pl) { return smem + (size_t)((stage * 2 + op) * NP + pl) * TILE * LDS_K; };
+
+  const double *Ag = g.A.re + (long long)e * g.A.batch + (long long)ti * TILE * g.A.ld;
+  const double *Bg = g.B.re + (long long)e * g.B.batch + (long long)tj * TILE * g.B.ld;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp >> 1, wn = warp & 1, gq = lane >> 2, tq = lane & 3;
+
+  double cr[4][4][2], ci[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) { cr[a][b][0] = cr[a][b][1] = 0.0; ci[a][b][0] = ci[a][b][1] = 0.0; }
+
+  auto load_stage = [&](int stage, int k0) {
+    // each plane of each operand: 64 rows x 16 doubles = 64 x 8 chunks of 16 B
+#pragma unroll
+    for (int it = 0; it < (TILE * (KC / 2)) / GEMM_THREADS; it++) {
+      int c = tid + it * GEMM_THREADS;
+      int row = c >> 3, ch = c & 7;
+#pragma unroll
+      for (int pl = 0; pl < NP; pl++) {
+        cp_async16(sm(stage, 0, pl) + row * LDS_K + ch * 2, Ag + (pl ? g.A.im_off : 0) + (long long)row * g.A.ld + k0 + ch * 2);
+        cp_async16(sm(stage, 1, pl) + row * LDS_K + ch * 2, Bg + (pl ? g.B.im_off : 0) + (long long)row * g.B.ld + k0 + ch * 2);
+      }
+    }
+    cp_async_commit();
+  };
+
+  const int nk = g.K / KC;
+  if (nk > 0) load_stage(0, 0);
+  for (int kc = 0; kc < nk; kc++) {
+    const int st = kc & 1;
+    if (kc + 1 < nk) { load_stage(st ^ 1, (kc + 1) * KC); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const double *Ar = sm(st, 0, 0) + (32 * wm + gq) * LDS_K + tq;
+    const double *Br = sm(st, 1, 0) + (32 * wn + gq) * LDS_K + tq;
+    const double *Ai = CPLX ? sm(st, 0, 1) + (32 * wm + gq) * LDS_K + tq : nullptr;
+    const double *Bi = CPLX ? sm(st, 1, 1) + (32 * wn + gq) * LDS_K + tq : nullptr;
+#pragma unroll
+    for (int k4 = 0; k4 < KC / 4; k4++) {
+      double ar[4], ai[4], br[4], bi[4];
+#pragma unroll
+      for (int m = 0; m < 4; m++) {
+        ar[m] = Ar[m * 8 * LDS_K + k4 * 4];
+        br[m] = Br[m * 8 * LDS_K + k4 * 4];
+        if (CPLX) { ai[m] = Ai[m * 8 * LDS_K + k4 * 4]; bi[m] = Bi[m * 8 * LDS_K + k4 * 4]; }
+      }
+#pragma unroll
+      for (int m = 0; m < 4; m++)
+#pragma unroll
+        for (int n = 0; n < 4; n++) {
+          dmma884(cr[m][n][0], cr[m][n][1], ar[m], br[n]);
+          if (CPLX) {
+            dmma884(cr[m][n][0], cr[m][n][1], ai[m], bi[n]);   // + Ai*Bi   (conj(B) flips the sign of Bi)
+            dmma884(ci[m][n][0], ci[m][n][1], ai[m], br[n]);   // + Ai*Br
+            dmma884(ci[m][n][0], ci[m][n][1], dneg(ar[m]), bi[n]); // - Ar*Bi
+          }
+        }
+    }
+    __syncthreads();
+  }
+
+  // epilogue: C = [Cin] + alpha*S ; each thread owns (row = 32wm+8m+gq, cols 32wn+8n+2tq, +1)
+  const long long crow0 = (long long)ti * TILE, ccol0 = (long long)tj * TILE;
+  double *Co = g.Cout.re + (long long)e * g.Cout.batch;
+  const double *Cn = g.use_cin ? g.Cin.re + (long long)e * g.Cin.batch : nullptr;
+#pragma unroll
+  for (int m = 0; m < 4; m++)
+#pragma unroll
+    for (int n = 0; n < 4; n++) {
+      long long r = crow0 + 32 * wm + 8 * m + gq, c = ccol0 + 32 * wn + 8 * n + 2 * tq;
+      double2 vr = make_double2(g.alpha * cr[m][n][0], g.alpha * cr[m][n][1]);
+      double2 vi = make_double2(g.alpha * ci[m][n][0], g.alpha * ci[m][n][1]);
+      if (g.use_cin) {
+        double2 o = *reinterpret_cast<const double2 *>(Cn + r * g.Cin.ld + c);
+        vr.x += o.x; vr.y += o.y;
+        if (CPLX) { double2 oi = *reinterpret_cast<const double2 *>(Cn + g.Cin.im_off + r * g.Cin.ld + c); vi.x += oi.x; vi.y += oi.y; }
+      }
+      *reinterpret_cast<double2 *>(Co + r * g.Cout.ld + c) = vr;
+      if (CPLX) *reinterpret_cast<double2 *>(Co + g.Cout.im_off + r * g.Cout.ld + c) = vi;
+    }
+}
+
+constexpr size_t potrf_smem_bytes() { return (size_t)4 * TILE * (TILE + 1) * sizeof(double); }
+template <bool CPLX> constexpr size_t gemm_smem_bytes() { return (size_t)2 * 2 * (CPLX ? 2 : 1) * TILE * LDS_K * sizeof(double); }
+
+// ---------------------------------------------------------------------------------------------------
+// potrf_inv_tile: factor the Hermitian positive definite 64x64 diagonal tile (lower, L L^H), write L back
+// (upper part zeroed), and write Linv = L^-1 and LinvH = L^-H (both row-major planar 64x64) for the
+// "triangular solve = GEMM with the inverted block" steps.  One CTA (256 threads) per element.
+// info[e] = first non-positive pivot (1-based, offset by `col0`) like LAPACK ?POTRF, 0 if ok.
+template <bool CPLX>
+__global__ void __launch_bounds__(256) potrf_inv_tile_kernel(MatRef D, MatRef Linv, MatRef LinvH, int *info, int info_stride, int col0) {
+  constexpr int N = TILE, LD = TILE + 1;
+  extern __shared__ __align__(16) double smem[];  // 4 planes of N*LD doubles (133 KB: opt-in dynamic smem)
+  double *sr = smem, *si = smem + N * LD, *xr = smem + 2 * N * LD, *xi = smem + 3 * N * LD;
+  __shared__ int bad;
+  const int e = blockIdx.x, tid = threadIdx.x;
+  double *Dg = D.re + (long long)e * D.batch;
+  if (tid == 0) bad = 0;
+  for (int idx = tid; idx < N * N; idx += blockDim.x) {
+    int r = idx / N, c = idx % N;
+    sr[r * LD + c] = Dg[(long long)r * D.ld + c];
+    if (CPLX) si[r * LD + c] = Dg[D.im_off + (long long)r * D.ld + c];
+  }
+  __syncthreads();
+  // right-looking Cholesky on the lower triangle
+  for (int k = 0; k < N; k++) {
+    double d = sr[k * LD + k];
+    if (!(d > 0.0)) { if (tid == 0 && bad == 0) bad = k + 1; d = 1.0; }
+    double rs = 1.0 / sqrt(d);
+    __syncthreads();
+    if (tid >= k && tid < N) { // scale column k (entry (tid,k)); the diagonal becomes sqrt(d)
+      if (tid == k) { sr[k * LD + k] = sqrt(d); if (CPLX) si[k * LD + k] = 0.0; }
+      else { sr[tid * LD + k] *= rs; if (CPLX) si[tid * LD + k] *= rs; }
+    }
+    __syncthreads();
+    const int rem = N - k - 1;
+    for (int idx = tid; idx < rem * rem; idx += blockDim.x) {
+      int r = k + 1 + idx / rem, c = k + 1 + idx % rem;
+      if (c > r) continue;
+      double ar = sr[r * LD + k], br = sr[c * LD + k];
+      if (CPLX) {
+        double ai = si[r * LD + k], bi = si[c * LD + k];
+        sr[r * LD + c] -= ar * br + ai * bi;   // a * conj(b)
+        si[r * LD + c] -= ai * br - ar * bi;
+      } else sr[r * LD + c] -= ar * br;
+    }
+    __syncthreads();
+  }
+  // X = L^-1 by forward substitution, one column per thread
+  if (tid < N) {
+    const int j = tid;
+    for (int i = 0; i < N; i++) {
+      if (i < j) { xr[i * LD + j] = 0.0; if (CPLX) xi[i * LD + j] = 0.0; continue; }
+      double accr = (i == j) ? 1.0 : 0.0, acci = 0.0;
+      for (int k = j; k < i; k++) {
+        double lr = sr[i * LD + k], xr_ = xr[k * LD + j];
+        if (CPLX) { double li = si[i * LD + k], xi_ = xi[k * LD + j]; accr -= lr * xr_ - li * xi_; acci -= lr * xi_ + li * xr_; }
+        else accr -= lr * xr_;
+      }
+      double dinv = 1.0 / sr[i * LD + i];
+      xr[i * LD + j] = accr * dinv;
+      if (CPLX) xi[i * LD + j] = acci * dinv;
+    }
+  }
+  __syncthreads();
+  double *Xg = Linv.re + (long long)e * Linv.batch, *XHg = LinvH.re + (long long)e * LinvH.batch;
+  for (int idx = tid; idx < N * N; idx += blockDim.x) {
+    int r = idx / N, c = idx % N;
+    bool low = c <= r;
+    Dg[(long long)r * D.ld + c] = low ? sr[r * LD + c] : 0.0;
+    Xg[(long long)r * Linv.ld + c] = xr[r * LD + c];
+    XHg[(long long)r * LinvH.ld + c] = xr[c * LD + r];
+    if (CPLX) {
+      Dg[D.im_off + (long long)r * D.ld + c] = low ? si[r * LD + c] : 0.0;
+      Xg[Linv.im_off + (long long)r * Linv.ld + c] = xi[r * LD + c];
+      XHg[LinvH.im_off + (long long)r * LinvH.ld + c] = -xi[c * LD + r];
+    }
+  }
+  if (tid == 0 && bad && info && info[(long long)e * info_stride] == 0) info[(long long)e * info_stride] = col0 + bad;
+}
+
+// Out(j,i) = conj(In(i,j)) for an R x C (row-major planar) block; grid = (C/32, R/32, batch), block (32,8)
+template <bool CPLX>
+__global__ void conj_transpose_kernel(MatRef In, MatRef Out, int R, int Cn) {
+  __shared__ double tr[32][33], tim[32][33];
+  const int e = blockIdx.z, bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  const double *I = In.re + (long long)e * In.batch;
+  double *O = Out.re + (long long)e * Out.batch;
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    int r = by + y, c = bx + threadIdx.x;
+    if (r < R && c < Cn) { tr[y][threadIdx.x] = I[(long long)r * In.ld + c]; if (CPLX) tim[y][threadIdx.x] = I[In.im_off + (long long)r * In.ld + c]; }
+  }
+  __syncthreads();
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    int r = bx + y, c = by + threadIdx.x; // output row = input col
+    if (r < Cn && c < R) { O[(long long)r * Out.ld + c] = tr[threadIdx.x][y]; if (CPLX) O[Out.im_off + (long long)r * Out.ld + c] = -tim[threadIdx.x][y]; }
+  }
+}
+
+// unit diagonal on the padded rows [n0, n1) of a square row-major planar matrix (keeps the factorization regular)
+__global__ void pad_diag_kernel(double *A, long long batch_stride, int ld, int n0, int n1) {
+  int i = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n1) A[(long long)blockIdx.y * batch_stride + (long long)i * ld + i] = 1.0;
+}
+
+}  // namespace hp3d

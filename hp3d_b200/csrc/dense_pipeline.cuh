@@ -1,0 +1,145 @@
+// dense_pipeline.cuh -- host-side orchestration of the batched dense phase for one batch of elements:
+//   (DPG only)  G = L L^H  (left-looking blocked Cholesky),  B~^H = B^H L^-H  (rows appended below G, so the
+//               triangular solve rides in the same panel update),  A = B~^H (B~^H)^H   (HERK)
+//   (all)       static condensation of the bubble block:  A_bb = L L^H,  Y~ = A_ib L^-H,
+//               A_ii -= Y~ Y~^H,  ASchur^H = Y~ L^-1   (reference: src/modules/stc.F90:338-414)
+// Internal trial ordering is [bubble dofs | interface dofs | load], each padded to a multiple of 64; the
+// signed permutation back to the reference dof ordering happens in the output kernel (formats.cuh).
+#pragma once
+#include "dense_kernels.cuh"
+#include <cstdio>
+
+namespace hp3d {
+
+inline int pad64(int n) { return (n + TILE - 1) / TILE * TILE; }
+
+struct DenseDims {
+  bool cplx = true;
+  bool dpg = true;     // true: Gram + enriched stiffness present; false: A is given directly
+  int n = 0;           // test dofs (rows of the Gram)
+  int nb = 0, ni = 0;  // bubble / interface trial dofs
+  int np = 0, nbp = 0, nip = 0;  // padded: np=pad64(n), nbp=pad64(nb), nip=pad64(ni+1)
+  __host__ __device__ int M() const { return nbp + nip; }
+  __host__ __device__ int R() const { return np + nbp + nip; }
+  void finish() { np = dpg ? pad64(n) : 0; nbp = pad64(nb); nip = pad64(ni + 1); }
+  // doubles per element
+  __host__ __device__ size_t planes() const { return cplx ? 2 : 1; }
+  __host__ __device__ size_t w_plane() const { return (size_t)R() * np; }
+  __host__ __device__ size_t a_plane() const { return (size_t)M() * M(); }
+  __host__ __device__ size_t lh_plane() const { return (size_t)nbp * nbp; }
+  __host__ __device__ size_t linv_plane() const { return (size_t)TILE * TILE; }
+  __host__ __device__ int nsteps_stc() const { return nbp / TILE; }
+};
+
+struct DenseBuffers {
+  double *W = nullptr;      // [batch][planes][R][np]     Gram (lower) on top of B^H
+  double *Am = nullptr;     // [batch][planes][M][M]      A = B~^H B~ (lower), then L / Y~ / Schur / Z in place
+  double *LH = nullptr;     // [batch][planes][nbp][nbp]  L^H of the bubble block (for the backward solve)
+  double *Linv = nullptr;   // [batch][planes][64][64]    scratch for the Gram factorization steps
+  double *LinvH = nullptr;
+  double *LinvS = nullptr;  // [batch][nsteps][planes][64][64]  kept for the stc backward solve
+  double *LinvSH = nullptr;
+  int *info = nullptr;      // [batch]
+};
+
+template <bool CPLX>
+static void launch_gemm(const GemmArgs &g, int mt, int nt, int batch, cudaStream_t st) {
+  if (mt <= 0 || nt <= 0 || batch <= 0) return;
+  dim3 grid(mt, nt, batch);
+  gemm_nc_kernel<CPLX><<<grid, GEMM_THREADS, gemm_smem_bytes<CPLX>(), st>>>(g);
+}
+
+template <bool CPLX> static cudaError_t dense_configure() {
+  cudaError_t e = cudaFuncSetAttribute(gemm_nc_kernel<CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<CPLX>());
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(potrf_inv_tile_kernel<CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem_bytes());
+}
+
+// Left-looking blocked Cholesky of the leading `ncol` columns of a lower-trapezoidal row-major matrix with
+// `nrow` rows (rows >= ncol are "appended right-hand sides": they come out as X L^-H).
+// If LinvKeep != nullptr the inverted diagonal blocks are stored per step (stride keep_step doubles).
+template <bool CPLX>
+static void chol_trapezoid(double *Mbase, long long plane, long long batch_stride, int ld, int nrow, int ncol, int batch,
+                           double *Linv, double *LinvH, long long linv_batch, long long linv_step, int *info, cudaStream_t st) {
+  const int nt_r = nrow / TILE, nt_c = ncol / TILE;
+  const long long lp = (long long)TILE * TILE;
+  for (int j = 0; j < nt_c; j++) {
+    MatRef Dj{Mbase + (long long)j * TILE * ld + (long long)j * TILE, plane, batch_stride, ld};
+    if (j > 0) {  // panel update: rows j.. , block column j :  W(i,j) -= sum_{k<j} L(i,k) L(j,k)^H
+      GemmArgs g{};
+      g.A = MatRef{Mbase + (long long)j * TILE * ld, plane, batch_stride, ld};
+      g.B = MatRef{Mbase + (long long)j * TILE * ld, plane, batch_stride, ld};
+      g.Cin = Dj; g.Cout = Dj;
+      g.K = j * TILE; g.lower_only = 0; g.diag_shift = 0; g.use_cin = 1; g.alpha = -1.0;
+      launch_gemm<CPLX>(g, nt_r - j, 1, batch, st);
+    }
+    MatRef Li{Linv + j * linv_step, lp, linv_batch, TILE}, LiH{LinvH + j * linv_step, lp, linv_batch, TILE};
+    potrf_inv_tile_kernel<CPLX><<<batch, 256, potrf_smem_bytes(), st>>>(Dj, Li, LiH, info, 1, j * TILE);
+    if (nt_r - j - 1 > 0) {  // rows below the diagonal block:  L(i,j) = P(i,j) * Linv_jj^H
+      GemmArgs g{};
+      MatRef Pj{Mbase + (long long)(j + 1) * TILE * ld + (long long)j * TILE, plane, batch_stride, ld};
+      g.A = Pj; g.B = Li; g.Cin = Pj; g.Cout = Pj;
+      g.K = TILE; g.use_cin = 0; g.alpha = 1.0;
+      launch_gemm<CPLX>(g, nt_r - j - 1, 1, batch, st);
+    }
+  }
+}
+
+// The whole dense phase for `batch` elements whose W (DPG) or Am (Galerkin) buffers have been filled.
+template <bool CPLX>
+static void dense_phase(const DenseDims &d, const DenseBuffers &b, int batch, cudaStream_t st) {
+  const long long P = CPLX ? 2 : 1;
+  const long long lp = (long long)TILE * TILE;
+  const int M = d.M();
+  if (d.dpg) {
+    const long long wpl = (long long)d.w_plane();
+    chol_trapezoid<CPLX>(b.W, wpl, P * wpl, d.np, d.R(), d.np, batch, b.Linv, b.LinvH, P * lp, 0, b.info, st);
+    // A = B~^H (B~^H)^H  (lower tiles only)
+    GemmArgs g{};
+    MatRef Bt{b.W + (long long)d.np * d.np, wpl, P * wpl, d.np};
+    g.A = Bt; g.B = Bt;
+    g.Cout = MatRef{b.Am, (long long)d.a_plane(), P * (long long)d.a_plane(), M}; g.Cin = g.Cout;
+    g.K = d.np; g.lower_only = 1; g.diag_shift = 0; g.use_cin = 0; g.alpha = 1.0;
+    launch_gemm<CPLX>(g, M / TILE, M / TILE, batch, st);
+  }
+  if (d.nb == 0) return;
+  const long long apl = (long long)d.a_plane(), ab = P * apl;
+  if (d.nbp > d.nb) {  // padded bubble rows: unit diagonal keeps the factorization regular
+    dim3 grid((d.nbp - d.nb + 63) / 64, batch);
+    pad_diag_kernel<<<grid, 64, 0, st>>>(b.Am, ab, M, d.nb, d.nbp);
+  }
+  const int ns = d.nsteps_stc();
+  // A_bb = L L^H ; rows below become Y~ = A_ib L^-H (and the load row y_b^H)
+  chol_trapezoid<CPLX>(b.Am, apl, ab, M, M, d.nbp, batch, b.LinvS, b.LinvSH, (long long)ns * P * lp, P * lp, b.info, st);
+  {  // Schur complement: S = A_ii - Y~ Y~^H (lower tiles)
+    GemmArgs g{};
+    MatRef Y{b.Am + (long long)d.nbp * M, apl, ab, M};
+    MatRef S{b.Am + (long long)d.nbp * M + d.nbp, apl, ab, M};
+    g.A = Y; g.B = Y; g.Cin = S; g.Cout = S;
+    g.K = d.nbp; g.lower_only = 1; g.use_cin = 1; g.alpha = -1.0;
+    launch_gemm<CPLX>(g, d.nip / TILE, d.nip / TILE, batch, st);
+  }
+  {  // LH = L^H (upper, row-major) for the backward solve
+    MatRef In{b.Am, apl, ab, M}, Out{b.LH, (long long)d.lh_plane(), P * (long long)d.lh_plane(), d.nbp};
+    dim3 grid(d.nbp / 32, d.nbp / 32, batch), blk(32, 8);
+    conj_transpose_kernel<CPLX><<<grid, blk, 0, st>>>(In, Out, d.nbp, d.nbp);
+  }
+  // Z = Y~ L^-1  (ASchur^H), block columns from last to first, in place
+  for (int j = ns - 1; j >= 0; j--) {
+    MatRef Zj{b.Am + (long long)d.nbp * M + (long long)j * TILE, apl, ab, M};
+    if (j < ns - 1) {
+      GemmArgs g{};
+      g.A = MatRef{b.Am + (long long)d.nbp * M + (long long)(j + 1) * TILE, apl, ab, M};
+      g.B = MatRef{b.LH + (long long)j * TILE * d.nbp + (long long)(j + 1) * TILE, (long long)d.lh_plane(), P * (long long)d.lh_plane(), d.nbp};
+      g.Cin = Zj; g.Cout = Zj;
+      g.K = d.nbp - (j + 1) * TILE; g.use_cin = 1; g.alpha = -1.0;
+      launch_gemm<CPLX>(g, d.nip / TILE, 1, batch, st);
+    }
+    GemmArgs g{};
+    g.A = Zj; g.B = MatRef{b.LinvSH + (long long)j * P * lp, lp, (long long)ns * P * lp, TILE};
+    g.Cin = Zj; g.Cout = Zj; g.K = TILE; g.use_cin = 0; g.alpha = 1.0;
+    launch_gemm<CPLX>(g, d.nip / TILE, 1, batch, st);
+  }
+}
+
+}  // namespace hp3d

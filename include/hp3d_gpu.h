@@ -1,0 +1,122 @@
+/*
+ * hp3d_gpu.h -- C ABI of the B200 element engine: the drop-in boundary for hp3D's element-local hot path.
+ *
+ * What it replaces (paths relative to the reference's trunk/):
+ *   subroutine elem(Mdle, Itest,Itrial)          problems/<PROB>/elem.F90:20  (fills ALOC/BLOC, src/modules/assembly.F90:36-37)
+ *   subroutine stc_fwd_wrapper(Iel,Mdle)         src/modules/stc.F90:182      (condenses ALOC/BLOC, stores CLOC(Iel)%ASchur/BSchur)
+ * for ALL elements of a subdomain at once (the !$OMP DO element loop of src/solver/par_mumps/par_mumps_sc.F90:347-357
+ * becomes "one batched call, then copy-out inside the unchanged loop").  Everything above that boundary
+ * (celem_systemI constraints/compression, LCON, MUMPS) and below it on the host (find_order, find_orient,
+ * nodcor: the per-element descriptors) stays in the Fortran code.  INTEGRATION.md shows the ISO_C_BINDING stub.
+ *
+ * Conventions: plain C, no C++/torch types.  All matrices are column-major; complex values are interleaved
+ * (re,im) doubles == Fortran complex(8) (HP3D_COMPLEX=1, src/common/hp3d/typedefs.h:2-6).  Device, not host,
+ * pointers are never exposed except through the *_dev entry points.  Every function returns 0 on success or a
+ * negative HP3D_E* code; per-element LAPACK-style info (0 ok, >0 first non-positive pivot, -1 negative
+ * Jacobian) is returned in `info[]` so the Fortran shim can print + stop like the reference does
+ * (stc.F90:371-374, elem_opt.F90:846-849, geom3D.F90:92-109).
+ */
+#ifndef HP3D_GPU_H
+#define HP3D_GPU_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HP3D_OK 0
+#define HP3D_EINVAL (-1)     /* bad argument / unsupported configuration                       */
+#define HP3D_ENODEV (-2)     /* no CUDA device / CUDA runtime error (see hp3d_gpu_last_error)  */
+#define HP3D_ENOMEM (-3)
+#define HP3D_ENOPLAN (-4)
+
+/* problem_kind: which `elem` plugin of the reference is being replaced */
+#define HP3D_POIS_GAL 1  /* problems/POISSON/GALERKIN/elem_opt.F90:22      real,    stc LU       */
+#define HP3D_POIS_PDPG 2 /* problems/POISSON/PRIMAL_DPG/elem_opt.F90:32    real,    stc Cholesky */
+#define HP3D_MAXW_GAL 3  /* problems/MAXWELL/GALERKIN/elem_opt.F90:22      complex, stc LU       */
+#define HP3D_MAXW_UW 4   /* problems/MAXWELL/ULTRAWEAK_DPG/elem/elem_opt.F90:25  complex, stc Cholesky */
+
+/* element types (src/modules/node_types.F90): only the brick is implemented in this round */
+#define HP3D_MDLB 1
+
+/* test norms of the ultraweak Maxwell problem (problems/MAXWELL/ULTRAWEAK_DPG/modules/commonParam.F90) */
+#define HP3D_GRAPH_NORM 1
+#define HP3D_MATH_NORM 2
+#define HP3D_GRAPH_DIAG 3
+
+/* source term ("getf" user callback of the reference) */
+#define HP3D_SRC_ZERO 0
+#define HP3D_SRC_SIN 1   /* manufactured sin solution, common/mfd_solutions.F90:80-100 (isol=1)          */
+#define HP3D_SRC_TABLE 9 /* caller-supplied values at the quadrature points (see hp3d_gpu_quad_points) */
+
+typedef struct hp3d_params {
+  int nord_add;          /* parametersDPG NORD_ADD (enrichment dp); ignored by Galerkin problems       */
+  int maxp;              /* parameters MAXP (src/modules/parameters.F90:17); MAXPP = maxp+1            */
+  int test_norm;         /* HP3D_GRAPH_NORM ...                                                        */
+  double alpha_norm;     /* ALPHA_NORM                                                                 */
+  double omega, eps, mu, sigma; /* OMEGA, EPSILON, MU, SIGMA                                           */
+  double eps_tensor[18]; /* get_permittivity: 3x3 complex, column-major, interleaved (identity default)*/
+  int source;            /* HP3D_SRC_*                                                                 */
+  int icomp_exact;       /* ICOMP_EXACT 1..3 (Maxwell manufactured solutions)                          */
+  int store_schur;       /* STORE_STC: also return ASchur/BSchur (stc.F90:273-277)                     */
+} hp3d_params;
+
+void hp3d_gpu_params_default(hp3d_params *p);
+
+/* Select the device, create streams / workspaces lazily.  complex_mode mirrors HP3D_COMPLEX. */
+int hp3d_gpu_init(int device);
+int hp3d_gpu_finalize(void);
+const char *hp3d_gpu_last_error(void);
+
+/* Fix the problem + its parameters; returns a plan handle >= 0.  Plans are cheap; tables for each
+ * (order, orientation) signature met later are built on first use and cached inside the plan. */
+int hp3d_gpu_plan(int problem_kind, const hp3d_params *prm);
+int hp3d_gpu_plan_destroy(int plan);
+
+/* Sizes for one element signature: ni/nb as stc_get_nrdof (stc.F90:94), nint = # volume quadrature points,
+ * nrdofH = # geometry dofs (columns of xnod actually read). */
+int hp3d_gpu_sizes(int plan, const int *norder /*19*/, int *ni, int *nb, int *nint, int *nrdofH);
+
+/* The batched unit of work.  For e = 0..nel-1 (elements may differ in order and orientation; they are grouped
+ * by signature internally):
+ *   etype[e]             element type (HP3D_MDLB)
+ *   norder[19*e..]       find_order            (src/datstrs/find_order.F90:5)
+ *   norient_edge[12*e..] , norient_face[6*e..]  find_orient (find_orient.F90:8)
+ *   xnod[xnod_ld*e..]    nodcor: geometry dofs, (3, nrdofH) column-major (src/constrs/nodcor.F90:19)
+ *   source_qp            HP3D_SRC_TABLE only: per element nint values (real problems) or 3*nint complex
+ * Outputs, element e at offset e*stride (strides in SCALARS of the problem's value type; pass the sizes of the
+ * largest element), each block column-major with its own exact leading dimension:
+ *   Aii (ni x ni), Bi (ni)              condensed system  == ALOC/BLOC after stc_fwd_wrapper
+ *   ASchur (nb x ni), BSchur (nb)       == CLOC(iel)%ASchur / %BSchur          (may be NULL if !store_schur)
+ *   ni_out[e], nb_out[e], info[e]
+ */
+int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, const int *norient_edge,
+                        const int *norient_face, const double *xnod, int xnod_ld, const void *source_qp,
+                        void *Aii, long long sAii, void *Bi, long long sBi, void *ASchur, long long sAS,
+                        void *BSchur, long long sBS, int *ni_out, int *nb_out, int *info);
+
+/* Physical coordinates of the volume quadrature points (3, nint) per element, for callers that evaluate
+ * their own getf() on the host and pass the values back through source_qp. */
+int hp3d_gpu_quad_points(int plan, int nel, const int *etype, const int *norder, const int *norient_edge,
+                         const int *norient_face, const double *xnod, int xnod_ld, double *xq, long long sxq);
+
+/* Back-substitution of the bubble dofs after the global solve (stc_bwd, src/modules/stc.F90:661-677):
+ *   xb = BSchur - ASchur * xi      for a batch of elements with identical (ni, nb). */
+int hp3d_gpu_stc_bwd_batch(int complex_mode, int nel, int ni, int nb, const void *ASchur, long long sAS,
+                           const void *BSchur, long long sBS, const void *xi, long long sxi, void *xb, long long sxb);
+
+/* Throughput driver used by bench.py: runs the hot path `reps` times over `nel` resident elements (inputs
+ * already in HBM, outputs left in HBM), reporting device time from CUDA events on the launching streams.
+ * If host_io != 0 the same work is timed end to end from pinned host descriptors to pinned host results. */
+int hp3d_gpu_bench(int plan, int nel, const int *norder, const int *norient_edge, const int *norient_face,
+                   const double *xnod, int xnod_ld, int reps, int host_io, double *ms_total, double *ms_dense,
+                   long long *launches, long long *h2d_bytes, long long *d2h_bytes);
+
+/* Test hook: run only the dense phase (DPG normal equations + static condensation) on caller-provided
+ * Gram / enriched stiffness matrices.  G: (n x n) Hermitian, upper triangle read; Bm: n x (nb+ni+1), columns
+ * ordered [bubble | interface | load].  cplx selects real(8)/complex(8). */
+int hp3d_gpu_dense_debug(int cplx, int nel, int n, int nb, int ni, const void *G, const void *Bm, void *Aii,
+                         void *Bi, void *ASchur, void *BSchur, int *info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
