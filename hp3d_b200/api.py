@@ -1,0 +1,195 @@
+"""Host-side mirror of the reference interface for the element-local hot path, on top of the C ABI.
+
+The reference computes one element at a time:
+    call elem(Mdle, Itest,Itrial)         problems/<PROB>/elem.F90:20        -> ALOC/BLOC  (src/modules/assembly.F90:36-37)
+    call stc_fwd_wrapper(Iel,Mdle)        src/modules/stc.F90:182            -> condensed ALOC/BLOC + CLOC(Iel)%ASchur/BSchur
+inside the OpenMP element loop of par_mumps_sc (src/solver/par_mumps/par_mumps_sc.F90:347-357).  Here the same two
+steps run for all elements of a subdomain in one call (`ElemEngine.elem_stc_batch`), and `stc_bwd_batch` mirrors
+stc_bwd (stc.F90:661-677).  Argument names follow the reference (norder, norient_edge, norient_face, xnod).
+
+Everything numeric happens in hp3d_b200/libhp3d_gpu.so (CUDA, sm_100a).  There is no CPU fallback: without the
+library or without a GPU these calls raise.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+POIS_GAL, POIS_PDPG, MAXW_GAL, MAXW_UW = 1, 2, 3, 4
+GRAPH_NORM, MATH_NORM, GRAPH_DIAG = 1, 2, 3
+SRC_ZERO, SRC_SIN, SRC_TABLE = 0, 1, 9
+MDLB = 1
+
+
+def _ptr(a, t=C.c_void_p):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def pinned_empty(shape, dtype):
+    """Page-locked host array (hp3d_gpu_host_alloc) so that result copies are asynchronous DMA transfers."""
+    L = _lib.lib()
+    L.hp3d_gpu_host_alloc.restype = C.c_void_p
+    L.hp3d_gpu_host_alloc.argtypes = [C.c_longlong]
+    L.hp3d_gpu_host_free.argtypes = [C.c_void_p]
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape))
+    p = L.hp3d_gpu_host_alloc(max(n * dt.itemsize, 8))
+    if not p:
+        raise MemoryError("hp3d_gpu_host_alloc failed")
+    buf = (C.c_char * (n * dt.itemsize)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+    arr.flags.writeable = True
+    return _Pinned(arr, p)
+
+
+class _Pinned:
+    """Owner of a pinned allocation; `.a` is the numpy view."""
+
+    def __init__(self, arr, ptr):
+        self.a, self._ptr = arr, ptr
+
+    def free(self):
+        if self._ptr:
+            _lib.lib().hp3d_gpu_host_free(C.c_void_p(self._ptr))
+            self._ptr = None
+            self.a = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class ElemEngine:
+    """One plan = one problem (`elem` plugin of the reference) with fixed parameters."""
+
+    _initialised = None
+
+    def __init__(self, kind, device=0, **params):
+        self.L = _lib.lib()
+        L = self.L
+        if ElemEngine._initialised != device:
+            _lib.check(L.hp3d_gpu_init(int(device)))
+            ElemEngine._initialised = device
+        prm = _lib.Params()
+        L.hp3d_gpu_params_default(C.byref(prm))
+        for k, v in params.items():
+            if not hasattr(prm, k):
+                raise TypeError(f"unknown parameter {k}")
+            setattr(prm, k, v)
+        self.kind, self.prm = kind, prm
+        self.complex = kind >= MAXW_GAL
+        self.dtype = np.complex128 if self.complex else np.float64
+        self.plan = L.hp3d_gpu_plan(int(kind), C.byref(prm))
+        if self.plan < 0:
+            _lib.check(self.plan)
+
+    def close(self):
+        if self.plan is not None and self.plan >= 0:
+            self.L.hp3d_gpu_plan_destroy(self.plan)
+            self.plan = None
+
+    def sizes(self, norder):
+        """(ni, nb, nint, nrdofH) for one element order vector, as stc_get_nrdof (stc.F90:94) / set_3D_int / celndof."""
+        norder = _i32(norder)
+        v = [C.c_int() for _ in range(4)]
+        _lib.check(self.L.hp3d_gpu_sizes(self.plan, _ptr(norder), *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    def quad_points(self, norder, norient_edge, norient_face, xnod):
+        norder, noe, nof = _i32(norder).reshape(-1, 19), _i32(norient_edge).reshape(-1, 12), _i32(norient_face).reshape(-1, 6)
+        xnod = np.ascontiguousarray(xnod, dtype=np.float64)
+        nel = norder.shape[0]
+        nint = max(self.sizes(norder[e])[2] for e in range(nel))
+        xq = np.zeros((nel, nint, 3))
+        _lib.check(self.L.hp3d_gpu_quad_points(self.plan, nel, None, _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod),
+                                               int(xnod[0].size), _ptr(xq), C.c_longlong(nint * 3)))
+        return xq
+
+    def elem_stc_batch(self, norder, norient_edge, norient_face, xnod, source_qp=None, out=None):
+        """elem + stc_fwd_wrapper for nel elements.
+
+        norder (nel,19), norient_edge (nel,12), norient_face (nel,6): find_order / find_orient output;
+        xnod (nel, nrdofH_max, 3): nodcor output (geometry dofs; row k = coordinates of dof k).
+        Returns dict(Aii (nel,ni,ni) [Fortran order per element: Aii[e].T is the column-major block], Bi, ASchur, BSchur,
+        ni, nb, info).  All elements are padded to the largest ni/nb of the batch.
+        """
+        L = self.L
+        norder, noe, nof = _i32(norder).reshape(-1, 19), _i32(norient_edge).reshape(-1, 12), _i32(norient_face).reshape(-1, 6)
+        xnod = np.ascontiguousarray(xnod, dtype=np.float64)
+        nel = norder.shape[0]
+        assert xnod.shape[0] == nel
+        sz = {}
+        for e in range(nel):
+            k = norder[e].tobytes()
+            if k not in sz:
+                sz[k] = self.sizes(norder[e])
+        ni = max(s[0] for s in sz.values())
+        nb = max(s[1] for s in sz.values())
+        if out is None:
+            out = dict(Aii=np.zeros((nel, ni * ni), self.dtype), Bi=np.zeros((nel, ni), self.dtype),
+                       ASchur=np.zeros((nel, max(nb * ni, 1)), self.dtype), BSchur=np.zeros((nel, max(nb, 1)), self.dtype))
+        Aii, Bi, AS, BS = out["Aii"], out["Bi"], out["ASchur"], out["BSchur"]
+        nio = np.zeros(nel, np.int32); nbo = np.zeros(nel, np.int32); info = np.zeros(nel, np.int32)
+        src_ld = 0
+        if source_qp is not None:
+            source_qp = np.ascontiguousarray(source_qp)
+            src_ld = source_qp[0].size * (2 if np.iscomplexobj(source_qp) else 1)
+        L.hp3d_gpu_elem_batch.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                          C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
+                                          C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = L.hp3d_gpu_elem_batch(self.plan, nel, None, _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(xnod[0].size),
+                                   _ptr(source_qp), src_ld, _ptr(Aii), Aii[0].size, _ptr(Bi), Bi[0].size, _ptr(AS), AS[0].size,
+                                   _ptr(BS), BS[0].size, _ptr(nio), _ptr(nbo), _ptr(info))
+        _lib.check(rc)
+        return dict(Aii=Aii, Bi=Bi, ASchur=AS, BSchur=BS, ni=nio, nb=nbo, info=info)
+
+    @staticmethod
+    def unpack(res, e):
+        """Element e of an elem_stc_batch result as (Aii (ni,ni), Bi (ni), ASchur (nb,ni), BSchur (nb)) numpy arrays."""
+        ni, nb = int(res["ni"][e]), int(res["nb"][e])
+        Aii = res["Aii"][e][: ni * ni].reshape(ni, ni).T
+        AS = res["ASchur"][e][: nb * ni].reshape(ni, nb).T
+        return Aii, res["Bi"][e][:ni], AS, res["BSchur"][e][:nb]
+
+    def stc_bwd_batch(self, ASchur, BSchur, xi):
+        """xb = BSchur - ASchur xi (stc_bwd, stc.F90:661-677).  ASchur (nel,nb,ni) logical, passed column-major per element."""
+        nel, nb, ni = ASchur.shape
+        A = np.ascontiguousarray(np.transpose(ASchur, (0, 2, 1)), dtype=self.dtype)   # per element column-major
+        B = np.ascontiguousarray(BSchur, dtype=self.dtype); x = np.ascontiguousarray(xi, dtype=self.dtype)
+        xb = np.zeros((nel, nb), self.dtype)
+        ll = C.c_longlong
+        self.L.hp3d_gpu_stc_bwd_batch.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, ll, C.c_void_p, ll, C.c_void_p, ll, C.c_void_p, ll]
+        _lib.check(self.L.hp3d_gpu_stc_bwd_batch(int(self.complex), nel, ni, nb, _ptr(A), nb * ni, _ptr(B), nb, _ptr(x), ni, _ptr(xb), nb))
+        return xb
+
+    def integrate_debug(self, norder, norient_edge, norient_face, xnod, source_qp=None):
+        """Raw dense-phase input of one element (test hook): returns (W (planes,R,np), dims dict)."""
+        norder, noe, nof = _i32(norder), _i32(norient_edge), _i32(norient_face)
+        xnod = np.ascontiguousarray(xnod, dtype=np.float64)
+        dims = np.zeros(8, np.int32)
+        f = self.L.hp3d_gpu_integrate_debug
+        f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
+        _lib.check(f(self.plan, _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), _ptr(source_qp), None, 0, _ptr(dims)))
+        np_, nbp, nip, n, nb, ni, R, P = [int(v) for v in dims]
+        ld = np_ if np_ else R
+        W = np.zeros((P, R, ld))
+        _lib.check(f(self.plan, _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), _ptr(source_qp), _ptr(W), W.size, _ptr(dims)))
+        return W, dict(np=np_, nbp=nbp, nip=nip, n=n, nb=nb, ni=ni, R=R, planes=P)
+
+    def bench(self, norder, norient_edge, norient_face, xnod, reps=1, max_chunk=0):
+        """Device-resident throughput run (hp3d_gpu_bench): returns dict(ms_total, ms_integ, ms_dense, launches)."""
+        norder, noe, nof = _i32(norder).reshape(-1, 19), _i32(norient_edge).reshape(-1, 12), _i32(norient_face).reshape(-1, 6)
+        xnod = np.ascontiguousarray(xnod, dtype=np.float64)
+        nel = norder.shape[0]
+        t = [C.c_double() for _ in range(3)]
+        ln = C.c_longlong()
+        _lib.check(self.L.hp3d_gpu_bench(self.plan, nel, _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(xnod[0].size), int(reps),
+                                         int(max_chunk), C.byref(t[0]), C.byref(t[1]), C.byref(t[2]), C.byref(ln)))
+        return dict(ms_total=t[0].value, ms_integ=t[1].value, ms_dense=t[2].value, launches=ln.value)

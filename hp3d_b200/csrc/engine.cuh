@@ -1,9 +1,14 @@
-// engine.cuh -- batch engine behind the C ABI: workspaces, the per-batch pipeline, debug drivers.
+// engine.cuh -- batch engine behind the C ABI: per-signature device programs, workspaces, the per-chunk pipeline
+//   descriptors -> geometry/weight fields -> sum-factorised integration -> dense phase -> condensed outputs.
 #pragma once
 #include "dense_pipeline.cuh"
 #include "formats.cuh"
+#include "forms.hpp"
+#include "integ_kernels.cuh"
 
 #include <complex>
+#include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -15,6 +20,16 @@ namespace hp3d {
     if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); return -2; } \
   } while (0)
 
+static long long g_launches = 0;  // kernels launched by this library (reported by hp3d_gpu_bench)
+
+template <class T> static int dev_upload(const std::vector<T> &h, T **d, std::string &err) {
+  *d = nullptr;
+  if (h.empty()) return 0;
+  HP3D_CK(cudaMalloc((void **)d, sizeof(T) * h.size()));
+  HP3D_CK(cudaMemcpy(*d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 struct DenseWorkspace {
   DenseDims d;
   DenseBuffers b;
@@ -22,6 +37,10 @@ struct DenseWorkspace {
   void release() {
     cudaFree(b.W); cudaFree(b.Am); cudaFree(b.LH); cudaFree(b.Linv); cudaFree(b.LinvH); cudaFree(b.LinvS); cudaFree(b.LinvSH); cudaFree(b.info);
     b = DenseBuffers{}; cap = 0;
+  }
+  static size_t bytes_per_element(const DenseDims &d) {
+    const size_t P = d.planes(), lp = d.linv_plane(), ns = d.nsteps_stc() ? d.nsteps_stc() : 1;
+    return sizeof(double) * P * ((d.dpg ? d.w_plane() : 0) + d.a_plane() + (d.lh_plane() ? d.lh_plane() : 1) + 2 * lp + 2 * lp * ns) + sizeof(int);
   }
   int reserve(const DenseDims &dims, int batch, std::string &err) {
     release();
@@ -41,7 +60,193 @@ struct DenseWorkspace {
   }
 };
 
-struct Plan;  // defined in plan.cuh
+// ------------------------------------------------------------------------------------------------
+// One element signature compiled and resident on the device.
+struct Signature {
+  SigHost h;
+  double *d_tab = nullptr, *d_wq = nullptr, *d_CW = nullptr, *d_ones = nullptr;
+  int *d_hdof = nullptr, *d_maps = nullptr, *d_crow = nullptr, *d_iota = nullptr;
+  FamilyDesc *d_fam = nullptr; TermDesc *d_term = nullptr; SlotDesc *d_slot = nullptr; BlockDesc *d_block = nullptr; WorkItem *d_work = nullptr;
+  DenseWorkspace ws;
+  double *d_WF = nullptr, *d_xnod = nullptr, *d_src = nullptr;         // per-chunk inputs / fields
+  struct OutStage { double *Aii = nullptr, *Bi = nullptr, *AS = nullptr, *BS = nullptr; int *info = nullptr; };
+  OutStage out[2];   // per-chunk outputs (device staging), double-buffered so D2H of chunk k overlaps chunk k+1
+  double *h_xnod = nullptr, *h_src = nullptr;  // pinned host staging of the chunk inputs [2][cap]
+  int cap = 0;
+  ~Signature() {
+    cudaFree(d_tab); cudaFree(d_wq); cudaFree(d_CW); cudaFree(d_ones); cudaFree(d_hdof); cudaFree(d_maps); cudaFree(d_crow); cudaFree(d_iota);
+    cudaFree(d_fam); cudaFree(d_term); cudaFree(d_slot); cudaFree(d_block); cudaFree(d_work);
+    free_chunk();
+  }
+  void free_chunk() {
+    ws.release();
+    cudaFree(d_WF); cudaFree(d_xnod); cudaFree(d_src);
+    for (int i = 0; i < 2; i++) { cudaFree(out[i].Aii); cudaFree(out[i].Bi); cudaFree(out[i].AS); cudaFree(out[i].BS); cudaFree(out[i].info); out[i] = OutStage(); }
+    cudaFreeHost(h_xnod); cudaFreeHost(h_src);
+    d_WF = d_xnod = d_src = nullptr; h_xnod = h_src = nullptr; cap = 0;
+  }
+  int ns() const { return h.cplx ? 2 : 1; }
+  size_t src_doubles() const { return (size_t)h.nint * (h.cplx ? 6 : 1); }
+  size_t bytes_per_element() const {
+    const size_t NS = ns();
+    return DenseWorkspace::bytes_per_element(h.dims) +
+           sizeof(double) * ((size_t)NFIELD * h.nint + 3 * (size_t)h.nH + src_doubles() +
+                             2 * NS * ((size_t)h.ni * h.ni + h.ni + (size_t)h.nb * h.ni + h.nb + 2));
+  }
+  int upload(std::string &err) {
+    if (dev_upload(h.tab, &d_tab, err) || dev_upload(h.wq, &d_wq, err) || dev_upload(h.hdof, &d_hdof, err) || dev_upload(h.maps, &d_maps, err) ||
+        dev_upload(h.fam, &d_fam, err) || dev_upload(h.term, &d_term, err) || dev_upload(h.slot, &d_slot, err) ||
+        dev_upload(h.block, &d_block, err) || dev_upload(h.work, &d_work, err) || dev_upload(h.crow, &d_crow, err) || dev_upload(h.CW, &d_CW, err))
+      return -2;
+    const int n = std::max(h.ni, h.nb) + 1;
+    std::vector<int> iota(n);
+    std::vector<double> ones(n, 1.0);
+    for (int i = 0; i < n; i++) iota[i] = i;
+    if (dev_upload(iota, &d_iota, err) || dev_upload(ones, &d_ones, err)) return -2;
+    return 0;
+  }
+  int reserve(int batch, std::string &err) {
+    if (batch <= cap) return 0;
+    free_chunk();
+    if (int rc = ws.reserve(h.dims, batch, err)) return rc;
+    const size_t NS = ns();
+    HP3D_CK(cudaMalloc(&d_WF, sizeof(double) * NFIELD * h.nint * batch));
+    HP3D_CK(cudaMalloc(&d_xnod, sizeof(double) * 3 * h.nH * batch));
+    HP3D_CK(cudaMalloc(&d_src, sizeof(double) * src_doubles() * batch));
+    for (int i = 0; i < 2; i++) {
+      HP3D_CK(cudaMalloc(&out[i].Aii, sizeof(double) * NS * (size_t)h.ni * h.ni * batch));
+      HP3D_CK(cudaMalloc(&out[i].Bi, sizeof(double) * NS * h.ni * batch));
+      HP3D_CK(cudaMalloc(&out[i].AS, sizeof(double) * NS * ((size_t)h.nb * h.ni + 1) * batch));
+      HP3D_CK(cudaMalloc(&out[i].BS, sizeof(double) * NS * (h.nb + 1) * batch));
+      HP3D_CK(cudaMalloc(&out[i].info, sizeof(int) * batch));
+    }
+    HP3D_CK(cudaMallocHost(&h_xnod, sizeof(double) * 2 * 3 * h.nH * batch));
+    HP3D_CK(cudaMallocHost(&h_src, sizeof(double) * 2 * src_doubles() * batch));
+    cap = batch;
+    return 0;
+  }
+};
+
+template <int NMAX> static cudaError_t tp3_configure() {
+  return cudaFuncSetAttribute(tp3_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+static void launch_tp3(const Signature &S, const Tp3Args &A, int nel, cudaStream_t st) {
+  dim3 grid((unsigned)S.h.work.size(), nel);
+  const int off = (int)S.h.smem_u_off;
+  switch (S.h.nmax) {
+    case 4: tp3_kernel<4><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, off); break;
+    case 6: tp3_kernel<6><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, off); break;
+    case 8: tp3_kernel<8><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, off); break;
+    default: tp3_kernel<10><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, off); break;
+  }
+  g_launches++;
+}
+
+struct StageEvents { cudaEvent_t e[4]; bool on = false; };  // start, after integration, after dense, after scatter
+
+// Integration of `nel` resident elements (d_xnod/d_src filled) into the dense phase's input buffers.
+static void run_integration(Signature &S, const GeomParams &gp, int nel, const double *d_xnod, const double *d_src, cudaStream_t st) {
+  const SigHost &h = S.h;
+  const DenseDims &d = h.dims;
+  const long long P = h.cplx ? 2 : 1;
+  SigTables sg;
+  sg.tab = S.d_tab; sg.wq = S.d_wq; sg.hdof = S.d_hdof; sg.nH = h.nH; sg.nint = h.nint;
+  for (int i = 0; i < 3; i++) sg.nq[i] = h.nq[i];
+  cudaMemsetAsync(S.ws.b.info, 0, sizeof(int) * nel, st);
+  const long long npts = (long long)nel * h.nint;
+  geom_fields_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(sg, gp, nel, d_xnod, 3LL * h.nH, d_src, S.d_WF, S.ws.b.info);
+  g_launches++;
+  Tp3Args A;
+  A.tab = S.d_tab; A.fam = S.d_fam; A.term = S.d_term; A.slot = S.d_slot; A.block = S.d_block; A.work = S.d_work; A.maps = S.d_maps;
+  A.WF = S.d_WF; A.nint = h.nint;
+  for (int i = 0; i < 3; i++) A.nq[i] = h.nq[i];
+  A.mat[0] = MatTarget{S.ws.b.W, P * (long long)d.w_plane(), (long long)d.w_plane(), d.np};
+  A.mat[1] = MatTarget{S.ws.b.Am, P * (long long)d.a_plane(), (long long)d.a_plane(), d.M()};
+  if (d.dpg) {
+    cudaMemsetAsync(S.ws.b.W, 0, sizeof(double) * P * d.w_plane() * nel, st);
+    if (d.np > d.n) { dim3 g((d.np - d.n + 63) / 64, nel); unit_diag_kernel<<<g, 64, 0, st>>>(A.mat[0], d.n, d.np); g_launches++; }
+  } else {
+    cudaMemsetAsync(S.ws.b.Am, 0, sizeof(double) * P * d.a_plane() * nel, st);
+  }
+  launch_tp3(S, A, nel, st);
+  if (!h.crow.empty()) {
+    dim3 g((d.np + 255) / 256, (unsigned)h.crow.size(), nel);
+    const_rows_kernel<<<g, 256, 0, st>>>(S.d_CW, S.d_crow, d.np, A.mat[0]);
+    g_launches++;
+  }
+}
+
+static long long dense_phase_launches(const DenseDims &d) {  // mirrors the launch structure of dense_phase()
+  long long n = 0;
+  auto chol = [&](int nt_r, int nt_c) { for (int j = 0; j < nt_c; j++) { if (j > 0) n++; n++; if (nt_r - j - 1 > 0) n++; } };
+  if (d.dpg) { chol(d.R() / TILE, d.np / TILE); n++; }
+  if (d.nb == 0) return n;
+  if (d.nbp > d.nb) n++;
+  chol(d.M() / TILE, d.nbp / TILE);
+  n += 2;
+  const int ns = d.nsteps_stc();
+  for (int j = ns - 1; j >= 0; j--) { if (j < ns - 1) n++; n++; }
+  return n;
+}
+
+template <bool CPLX>
+static void run_dense_and_scatter(Signature &S, int nel, bool want_schur, const Signature::OutStage &o, cudaStream_t st, StageEvents *ev) {
+  const SigHost &h = S.h;
+  const DenseDims &d = h.dims;
+  dense_phase<CPLX>(d, S.ws.b, nel, st);
+  g_launches += dense_phase_launches(d);
+  if (ev && ev->on) cudaEventRecord(ev->e[2], st);
+  OutMaps mp{S.d_iota, S.d_iota, S.d_ones, S.d_ones, 0, 0, 0, 0};
+  dim3 blk(16, 16), g1((h.ni + 15) / 16, (h.ni + 15) / 16, nel);
+  scatter_condensed_kernel<CPLX><<<g1, blk, 0, st>>>(d, S.ws.b.Am, mp, o.Aii, o.Bi, (long long)h.ni * h.ni, (long long)h.ni);
+  g_launches++;
+  if (h.nb > 0 && want_schur) {
+    dim3 g2((h.nb + 15) / 16, (h.ni + 15) / 16, nel);
+    scatter_schur_kernel<CPLX><<<g2, blk, 0, st>>>(d, S.ws.b.Am, mp, o.AS, o.BS, (long long)h.nb * h.ni, (long long)h.nb);
+    g_launches++;
+  }
+  cudaMemcpyAsync(o.info, S.ws.b.info, sizeof(int) * nel, cudaMemcpyDeviceToDevice, st);
+}
+
+static void run_chunk(Signature &S, const GeomParams &gp, int nel, const double *d_xnod, const double *d_src, bool want_schur, int obuf,
+                      cudaStream_t st, StageEvents *ev = nullptr) {
+  if (ev && ev->on) cudaEventRecord(ev->e[0], st);
+  run_integration(S, gp, nel, d_xnod, d_src, st);
+  if (ev && ev->on) cudaEventRecord(ev->e[1], st);
+  if (S.h.cplx) run_dense_and_scatter<true>(S, nel, want_schur, S.out[obuf], st, ev);
+  else run_dense_and_scatter<false>(S, nel, want_schur, S.out[obuf], st, ev);
+  if (ev && ev->on) cudaEventRecord(ev->e[3], st);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct Plan {
+  FormParams fp;
+  int store_schur = 1;
+  std::map<std::string, std::unique_ptr<Signature>> sigs;
+  GeomParams geom() const {
+    GeomParams g; g.kind = fp.kind; g.source = fp.source; g.icomp = fp.icomp; g.omega = fp.omega; g.eps = fp.eps; g.mu = fp.mu; g.sigma = fp.sigma;
+    return g;
+  }
+  static std::string key(const int *norder, const int *norie, const int *norif) {
+    std::string k((const char *)norder, 19 * sizeof(int));
+    k.append((const char *)norie, 12 * sizeof(int));
+    k.append((const char *)norif, 6 * sizeof(int));
+    return k;
+  }
+  // find or compile; device upload only when `device` is set
+  Signature *get(const int *norder, const int *norie, const int *norif, bool device, std::string &err) {
+    const std::string k = key(norder, norie, norif);
+    auto it = sigs.find(k);
+    if (it == sigs.end()) {
+      std::unique_ptr<Signature> s(new Signature());
+      if (!compile_signature(fp, norder, norie, norif, s->h)) { err = s->h.err; return nullptr; }
+      it = sigs.emplace(k, std::move(s)).first;
+    }
+    Signature *s = it->second.get();
+    if (device && !s->d_tab) { if (s->upload(err)) return nullptr; }
+    return s;
+  }
+};
 
 // ------------------------------------------------------------------------------------------------
 // Test hook: dense phase only, host matrices in / host matrices out (identity dof maps).
@@ -117,10 +322,5 @@ int dense_debug_run(int nel, int n, int nb, int ni, const void *Gv, const void *
   ws.release();
   return 0;
 }
-
-struct Plan {
-  int kind = 0;
-  virtual ~Plan() {}
-};
 
 }  // namespace hp3d

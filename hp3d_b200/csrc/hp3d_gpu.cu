@@ -15,6 +15,7 @@ std::mutex g_mu;
 std::string g_err;
 int g_device = -1;
 std::vector<Plan *> g_plans;
+cudaStream_t g_compute = nullptr, g_copy = nullptr;
 
 int fail(int code, const char *fmt, ...) {
   char buf[512];
@@ -30,6 +31,44 @@ int fail(int code, const char *fmt, ...) {
     cudaError_t e_ = (x);                                                               \
     if (e_ != cudaSuccess) return fail(HP3D_ENODEV, "%s: %s", #x, cudaGetErrorString(e_)); \
   } while (0)
+
+Plan *plan_of(int id) { return (id >= 0 && id < (int)g_plans.size()) ? g_plans[id] : nullptr; }
+
+// largest chunk (elements) of this signature that fits in the free device memory
+int chunk_capacity(const Signature &S, int want) {
+  size_t fre = 0, tot = 0;
+  cudaMemGetInfo(&fre, &tot);
+  // memory already held by this signature's chunk buffers is reusable
+  size_t have = (size_t)S.cap * S.bytes_per_element();
+  double budget = 0.80 * (double)(fre + have);
+  long long cap = (long long)(budget / (double)S.bytes_per_element());
+  if (cap > 1024) cap = 1024;
+  if (cap > want) cap = want;
+  return (int)cap;
+}
+// xb = BSchur - ASchur * xi, one warp per (row, element)
+template <bool CPLX>
+__global__ void stc_bwd_kernel(int ni, int nb, const double *AS, long long sAS, const double *BS, long long sBS, const double *xi,
+                               long long sxi, double *xb, long long sxb) {
+  constexpr int NS = CPLX ? 2 : 1;
+  const int e = blockIdx.y, r = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+  if (r >= nb) return;
+  const double *A = AS + (long long)e * sAS * NS, *x = xi + (long long)e * sxi * NS;
+  double sr = 0, si = 0;
+  for (int c = lane; c < ni; c += 32) {
+    const double *a = A + ((long long)r + (long long)nb * c) * NS;
+    if (CPLX) { sr += a[0] * x[2 * c] - a[1] * x[2 * c + 1]; si += a[0] * x[2 * c + 1] + a[1] * x[2 * c]; }
+    else sr += a[0] * x[c];
+  }
+  for (int o = 16; o; o >>= 1) { sr += __shfl_xor_sync(0xffffffffu, sr, o); if (CPLX) si += __shfl_xor_sync(0xffffffffu, si, o); }
+  if (lane == 0) {
+    const double *b = BS + (long long)e * sBS * NS + (long long)r * NS;
+    double *o = xb + (long long)e * sxb * NS + (long long)r * NS;
+    o[0] = b[0] - sr;
+    if (CPLX) o[1] = b[1] - si;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -56,6 +95,9 @@ int hp3d_gpu_init(int device) {
   if (prop.major < 10) return fail(HP3D_ENODEV, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
   CUDA_TRY(dense_configure<true>());
   CUDA_TRY(dense_configure<false>());
+  CUDA_TRY(tp3_configure<4>()); CUDA_TRY(tp3_configure<6>()); CUDA_TRY(tp3_configure<8>()); CUDA_TRY(tp3_configure<10>());
+  if (!g_compute) CUDA_TRY(cudaStreamCreateWithFlags(&g_compute, cudaStreamNonBlocking));
+  if (!g_copy) CUDA_TRY(cudaStreamCreateWithFlags(&g_copy, cudaStreamNonBlocking));
   g_device = device;
   return HP3D_OK;
 }
@@ -64,7 +106,357 @@ int hp3d_gpu_finalize(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   for (Plan *p : g_plans) delete p;
   g_plans.clear();
+  if (g_compute) { cudaStreamDestroy(g_compute); g_compute = nullptr; }
+  if (g_copy) { cudaStreamDestroy(g_copy); g_copy = nullptr; }
   g_device = -1;
+  return HP3D_OK;
+}
+
+int hp3d_gpu_plan(int problem_kind, const hp3d_params *prm) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!prm) return fail(HP3D_EINVAL, "null params");
+  if (problem_kind < HP3D_POIS_GAL || problem_kind > HP3D_MAXW_UW) return fail(HP3D_EINVAL, "unknown problem kind %d", problem_kind);
+  if (problem_kind == HP3D_MAXW_GAL) return fail(HP3D_EINVAL, "MAXW_GAL (pivoted-LU condensation) is not implemented on the GPU yet");
+  // constant isotropic permittivity only (the reference's default get_permittivity is the identity,
+  // problems/MAXWELL/ULTRAWEAK_DPG/common/commonRoutines.F90:126-150)
+  for (int j = 0; j < 3; j++)
+    for (int i = 0; i < 3; i++) {
+      double re = prm->eps_tensor[2 * (i + 3 * j)], im = prm->eps_tensor[2 * (i + 3 * j) + 1];
+      if (re != (i == j ? 1.0 : 0.0) || im != 0.0) return fail(HP3D_EINVAL, "only the identity permittivity tensor is supported (scale with eps)");
+    }
+  if (prm->maxp < 1 || prm->maxp > 9) return fail(HP3D_EINVAL, "maxp out of range");
+  if (prm->icomp_exact < 1 || prm->icomp_exact > 3) return fail(HP3D_EINVAL, "icomp_exact out of range");
+  Plan *p = new Plan();
+  p->fp.kind = problem_kind; p->fp.nord_add = prm->nord_add; p->fp.maxp = prm->maxp; p->fp.test_norm = prm->test_norm;
+  p->fp.alpha_norm = prm->alpha_norm; p->fp.omega = prm->omega; p->fp.eps = prm->eps; p->fp.mu = prm->mu; p->fp.sigma = prm->sigma;
+  p->fp.source = prm->source; p->fp.icomp = prm->icomp_exact - 1;
+  p->store_schur = prm->store_schur;
+  for (size_t i = 0; i < g_plans.size(); i++)
+    if (!g_plans[i]) { g_plans[i] = p; return (int)i; }
+  g_plans.push_back(p);
+  return (int)g_plans.size() - 1;
+}
+
+int hp3d_gpu_plan_destroy(int plan) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Plan *p = plan_of(plan);
+  if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
+  delete p;
+  g_plans[plan] = nullptr;
+  return HP3D_OK;
+}
+
+int hp3d_gpu_sizes(int plan, const int *norder, int *ni, int *nb, int *nint, int *nrdofH) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Plan *p = plan_of(plan);
+  if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
+  const int z12[12] = {0}, z6[6] = {0};
+  std::string err;
+  Signature *s = p->get(norder, z12, z6, false, err);
+  if (!s) return fail(HP3D_EINVAL, "%s", err.c_str());
+  if (ni) *ni = s->h.ni;
+  if (nb) *nb = s->h.nb;
+  if (nint) *nint = s->h.nint;
+  if (nrdofH) *nrdofH = s->h.nH;
+  return HP3D_OK;
+}
+
+int hp3d_gpu_dof_map(int space, const int *norder, const int *norie, const int *norif, int cap, int *fam, int *idx, int *sgn) {
+  std::vector<TensorDof> d;
+  switch (space) {
+    case 0: d = hexa_dofs_H1(norder, norie, norif); break;
+    case 1: d = hexa_dofs_Hcurl(norder, norie, norif); break;
+    case 2: d = hexa_dofs_Hdiv(norder, norif); break;
+    case 3: d = hexa_dofs_L2(norder); break;
+    default: return fail(HP3D_EINVAL, "unknown space %d", space);
+  }
+  const int n = (int)d.size();
+  if (!fam && !idx && !sgn) return n;
+  if (cap < n) return fail(HP3D_EINVAL, "dof_map: capacity %d < %d", cap, n);
+  for (int k = 0; k < n; k++) {
+    if (fam) fam[k] = d[k].fam;
+    if (sgn) sgn[k] = d[k].sgn;
+    if (idx) for (int a = 0; a < 3; a++) idx[3 * k + a] = d[k].idx[a];
+  }
+  return n;
+}
+
+int hp3d_gpu_tables_1d(int p, int nq, double *x, double *w, double *H, double *dH, double *Q) {
+  if (p < 1 || p > MAXN1D - 1 || nq < 1 || nq > MAXN1D) return fail(HP3D_EINVAL, "tables_1d: p=%d nq=%d out of range", p, nq);
+  Tables1D t = make_tables(p, nq);
+  if (x) memcpy(x, t.x.data(), sizeof(double) * nq);
+  if (w) memcpy(w, t.w.data(), sizeof(double) * nq);
+  if (H) memcpy(H, t.H.data(), sizeof(double) * (p + 1) * nq);
+  if (dH) memcpy(dH, t.dH.data(), sizeof(double) * (p + 1) * nq);
+  if (Q) memcpy(Q, t.Q.data(), sizeof(double) * p * nq);
+  return HP3D_OK;
+}
+
+void *hp3d_gpu_host_alloc(long long bytes) {
+  void *p = nullptr;
+  if (bytes <= 0 || cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+void hp3d_gpu_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------------------------------------
+int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif,
+                        const double *xnod, int xnod_ld, const void *source_qp, long long source_ld, void *Aii, long long sAii,
+                        void *Bi, long long sBi, void *ASchur, long long sAS, void *BSchur, long long sBS, int *ni_out, int *nb_out,
+                        int *info) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
+  Plan *p = plan_of(plan);
+  if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
+  if (nel < 0 || !norder || !norie || !norif || !xnod || !Aii || !Bi) return fail(HP3D_EINVAL, "null argument");
+  if (p->fp.source == HP3D_SRC_TABLE && !source_qp) return fail(HP3D_EINVAL, "source == HP3D_SRC_TABLE needs source_qp");
+  const bool want_schur = p->store_schur && ASchur && BSchur;
+  // ---- group by signature
+  std::map<std::string, std::vector<int>> groups;
+  for (int e = 0; e < nel; e++) {
+    if (etype && etype[e] != HP3D_MDLB) return fail(HP3D_EINVAL, "element %d: only bricks (HP3D_MDLB) are implemented", e);
+    groups[Plan::key(norder + 19 * e, norie + 12 * e, norif + 6 * e)].push_back(e);
+  }
+  const GeomParams gp = p->geom();
+  std::string err;
+  cudaEvent_t evCompute[2], evCopy[2], evH2D[2];
+  for (int i = 0; i < 2; i++) {
+    CUDA_TRY(cudaEventCreateWithFlags(&evCompute[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&evCopy[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&evH2D[i], cudaEventDisableTiming));
+  }
+  int rc = HP3D_OK;
+  std::vector<int> hinfo;
+  for (auto &g : groups) {
+    const std::vector<int> &el = g.second;
+    const int e0 = el[0];
+    Signature *S = p->get(norder + 19 * e0, norie + 12 * e0, norif + 6 * e0, true, err);
+    if (!S) { rc = fail(HP3D_EINVAL, "element %d: %s", e0, err.c_str()); break; }
+    if (xnod_ld < 3 * S->h.nH) { rc = fail(HP3D_EINVAL, "xnod_ld=%d < 3*nrdofH=%d", xnod_ld, 3 * S->h.nH); break; }
+    const int cap = chunk_capacity(*S, (int)el.size());
+    if (cap < 1) { rc = fail(HP3D_ENOMEM, "not enough device memory for one element (%zu bytes)", S->bytes_per_element()); break; }
+    if (S->reserve(cap, err)) { rc = fail(HP3D_ENOMEM, "%s", err.c_str()); break; }
+    const SigHost &h = S->h;
+    const size_t NS = S->ns(), es = sizeof(double) * NS;
+    const size_t nx = 3 * (size_t)h.nH, nsrc = S->src_doubles();
+    const size_t bA = (size_t)h.ni * h.ni, bB = h.ni, bAS = (size_t)h.nb * h.ni, bBS = h.nb;
+    hinfo.resize(2 * (size_t)S->cap);
+    int nchunk = 0;
+    for (size_t c0 = 0; c0 < el.size(); c0 += S->cap, nchunk++) {
+      const int n = (int)std::min(el.size() - c0, (size_t)S->cap), buf = nchunk & 1;
+      // the pinned input staging of this buffer must have been consumed by the H2D of chunk nchunk-2
+      if (nchunk >= 2) cudaEventSynchronize(evH2D[buf]);
+      double *hx = S->h_xnod + (size_t)buf * nx * S->cap, *hs = S->h_src + (size_t)buf * nsrc * S->cap;
+      for (int i = 0; i < n; i++) {
+        const int e = el[c0 + i];
+        memcpy(hx + (size_t)i * nx, xnod + (size_t)e * xnod_ld, sizeof(double) * nx);
+        if (gp.source == HP3D_SRC_TABLE) memcpy(hs + (size_t)i * nsrc, (const double *)source_qp + (size_t)e * source_ld, sizeof(double) * nsrc);
+      }
+      // the device inputs are single-buffered: stream order on g_compute protects them
+      cudaMemcpyAsync(S->d_xnod, hx, sizeof(double) * nx * n, cudaMemcpyHostToDevice, g_compute);
+      if (gp.source == HP3D_SRC_TABLE) cudaMemcpyAsync(S->d_src, hs, sizeof(double) * nsrc * n, cudaMemcpyHostToDevice, g_compute);
+      cudaEventRecord(evH2D[buf], g_compute);
+      if (nchunk >= 2) cudaStreamWaitEvent(g_compute, evCopy[buf], 0);  // output stage `buf` drained by the copy stream
+      run_chunk(*S, gp, n, S->d_xnod, S->d_src, want_schur, buf, g_compute);
+      cudaEventRecord(evCompute[buf], g_compute);
+      cudaStreamWaitEvent(g_copy, evCompute[buf], 0);
+      // D2H straight into the caller's arrays; runs of consecutive elements with dense strides are merged
+      const Signature::OutStage &o = S->out[buf];
+      for (int i = 0; i < n;) {
+        int j = i + 1;
+        while (j < n && el[c0 + j] == el[c0 + j - 1] + 1) j++;
+        const int e = el[c0 + i], run = j - i;
+        auto copy = [&](void *dst, long long stride, const double *src, size_t blk) {
+          if (blk == 0) return;
+          if ((size_t)stride == blk)
+            cudaMemcpyAsync((char *)dst + es * stride * e, src + NS * blk * i, es * blk * run, cudaMemcpyDeviceToHost, g_copy);
+          else
+            cudaMemcpy2DAsync((char *)dst + es * stride * e, es * stride, src + NS * blk * i, es * blk, es * blk, run, cudaMemcpyDeviceToHost, g_copy);
+        };
+        copy(Aii, sAii, o.Aii, bA);
+        copy(Bi, sBi, o.Bi, bB);
+        if (want_schur) { copy(ASchur, sAS, o.AS, bAS); copy(BSchur, sBS, o.BS, bBS); }
+        i = j;
+      }
+      cudaMemcpyAsync(hinfo.data() + (size_t)buf * S->cap, o.info, sizeof(int) * n, cudaMemcpyDeviceToHost, g_copy);
+      cudaEventRecord(evCopy[buf], g_copy);
+      // info needs the host: it is tiny, so wait for the previous chunk's copy here (keeps one chunk in flight)
+      if (nchunk >= 1) {
+        const int pb = buf ^ 1;
+        cudaEventSynchronize(evCopy[pb]);
+        const size_t pc0 = c0 - S->cap;
+        const int pn = (int)std::min(el.size() - pc0, (size_t)S->cap);
+        for (int i = 0; i < pn; i++) { const int e = el[pc0 + i]; if (info) info[e] = hinfo[(size_t)pb * S->cap + i]; }
+      }
+    }
+    {  // drain the last chunk
+      const int lb = (nchunk - 1) & 1;
+      cudaEventSynchronize(evCopy[lb]);
+      const size_t pc0 = (size_t)(nchunk - 1) * S->cap;
+      const int pn = (int)(el.size() - pc0);
+      for (int i = 0; i < pn; i++) { const int e = el[pc0 + i]; if (info) info[e] = hinfo[(size_t)lb * S->cap + i]; }
+    }
+    for (int e : el) { if (ni_out) ni_out[e] = h.ni; if (nb_out) nb_out[e] = h.nb; }
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) { rc = fail(HP3D_ENODEV, "CUDA error in elem_batch: %s", cudaGetErrorString(ce)); break; }
+  }
+  cudaStreamSynchronize(g_compute);
+  cudaStreamSynchronize(g_copy);
+  for (int i = 0; i < 2; i++) { cudaEventDestroy(evCompute[i]); cudaEventDestroy(evCopy[i]); cudaEventDestroy(evH2D[i]); }
+  if (rc == HP3D_OK) {
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) rc = fail(HP3D_ENODEV, "CUDA error in elem_batch: %s", cudaGetErrorString(ce));
+  }
+  return rc;
+}
+
+int hp3d_gpu_quad_points(int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif,
+                         const double *xnod, int xnod_ld, double *xq, long long sxq) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
+  Plan *p = plan_of(plan);
+  if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
+  GeomParams gp = p->geom();
+  gp.source = HP3D_SRC_ZERO;
+  std::string err;
+  std::vector<double> f;
+  for (int e = 0; e < nel; e++) {  // not a hot path: one element at a time
+    if (etype && etype[e] != HP3D_MDLB) return fail(HP3D_EINVAL, "element %d: only bricks are implemented", e);
+    Signature *S = p->get(norder + 19 * e, norie + 12 * e, norif + 6 * e, true, err);
+    if (!S) return fail(HP3D_EINVAL, "element %d: %s", e, err.c_str());
+    if (S->cap < 1 && S->reserve(1, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());
+    const SigHost &h = S->h;
+    CUDA_TRY(cudaMemcpyAsync(S->d_xnod, xnod + (size_t)e * xnod_ld, sizeof(double) * 3 * h.nH, cudaMemcpyHostToDevice, g_compute));
+    SigTables sg;
+    sg.tab = S->d_tab; sg.wq = S->d_wq; sg.hdof = S->d_hdof; sg.nH = h.nH; sg.nint = h.nint;
+    for (int i = 0; i < 3; i++) sg.nq[i] = h.nq[i];
+    geom_fields_kernel<<<(h.nint + 127) / 128, 128, 0, g_compute>>>(sg, gp, 1, S->d_xnod, 3LL * h.nH, nullptr, S->d_WF, S->ws.b.info);
+    f.resize(3 * (size_t)h.nint);
+    CUDA_TRY(cudaMemcpyAsync(f.data(), S->d_WF + (size_t)F_X * h.nint, sizeof(double) * 3 * h.nint, cudaMemcpyDeviceToHost, g_compute));
+    CUDA_TRY(cudaStreamSynchronize(g_compute));
+    for (int q = 0; q < h.nint; q++)
+      for (int c = 0; c < 3; c++) xq[(size_t)e * sxq + 3 * q + c] = f[(size_t)c * h.nint + q];
+  }
+  return HP3D_OK;
+}
+
+int hp3d_gpu_stc_bwd_batch(int cplx, int nel, int ni, int nb, const void *ASchur, long long sAS, const void *BSchur, long long sBS,
+                           const void *xi, long long sxi, void *xb, long long sxb) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
+  if (nel <= 0 || ni <= 0 || nb <= 0) return fail(HP3D_EINVAL, "bad sizes");
+  const size_t es = sizeof(double) * (cplx ? 2 : 1);
+  double *dA, *dB, *dx, *dy;
+  // element e of each host array sits at e*stride; copy the used extents as 2-D blocks
+  CUDA_TRY(cudaMalloc(&dA, es * (size_t)nb * ni * nel)); CUDA_TRY(cudaMalloc(&dB, es * (size_t)nb * nel));
+  CUDA_TRY(cudaMalloc(&dx, es * (size_t)ni * nel)); CUDA_TRY(cudaMalloc(&dy, es * (size_t)nb * nel));
+  CUDA_TRY(cudaMemcpy2D(dA, es * nb * ni, ASchur, es * sAS, es * nb * ni, nel, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy2D(dB, es * nb, BSchur, es * sBS, es * nb, nel, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy2D(dx, es * ni, xi, es * sxi, es * ni, nel, cudaMemcpyHostToDevice));
+  dim3 grid((nb + 7) / 8, nel);
+  if (cplx) stc_bwd_kernel<true><<<grid, 256>>>(ni, nb, dA, (long long)nb * ni, dB, nb, dx, ni, dy, nb);
+  else stc_bwd_kernel<false><<<grid, 256>>>(ni, nb, dA, (long long)nb * ni, dB, nb, dx, ni, dy, nb);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy2D(xb, es * sxb, dy, es * nb, es * nb, nel, cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dB); cudaFree(dx); cudaFree(dy);
+  return HP3D_OK;
+}
+
+int hp3d_gpu_bench(int plan, int nel, const int *norder, const int *norie, const int *norif, const double *xnod, int xnod_ld, int reps,
+                   int max_chunk, double *ms_total, double *ms_integ, double *ms_dense, long long *launches) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
+  Plan *p = plan_of(plan);
+  if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
+  if (nel <= 0 || reps <= 0) return fail(HP3D_EINVAL, "bad sizes");
+  if (p->fp.source == HP3D_SRC_TABLE) return fail(HP3D_EINVAL, "bench: table sources are not supported");
+  std::map<std::string, std::vector<int>> groups;
+  for (int e = 0; e < nel; e++) groups[Plan::key(norder + 19 * e, norie + 12 * e, norif + 6 * e)].push_back(e);
+  const GeomParams gp = p->geom();
+  std::string err;
+  struct Grp { Signature *S; double *dx; int n; };
+  std::vector<Grp> gs;
+  for (auto &g : groups) {
+    const int e0 = g.second[0];
+    Signature *S = p->get(norder + 19 * e0, norie + 12 * e0, norif + 6 * e0, true, err);
+    if (!S) return fail(HP3D_EINVAL, "%s", err.c_str());
+    int want = (int)g.second.size();
+    if (max_chunk > 0 && want > max_chunk) want = max_chunk;
+    const int cap = chunk_capacity(*S, want);
+    if (cap < 1) return fail(HP3D_ENOMEM, "not enough device memory");
+    if (S->reserve(cap, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());
+    const size_t nx = 3 * (size_t)S->h.nH;
+    std::vector<double> hx(nx * g.second.size());
+    for (size_t i = 0; i < g.second.size(); i++) memcpy(hx.data() + i * nx, xnod + (size_t)g.second[i] * xnod_ld, sizeof(double) * nx);
+    double *dx;
+    CUDA_TRY(cudaMalloc(&dx, sizeof(double) * hx.size()));
+    CUDA_TRY(cudaMemcpy(dx, hx.data(), sizeof(double) * hx.size(), cudaMemcpyHostToDevice));
+    gs.push_back(Grp{S, dx, (int)g.second.size()});
+  }
+  std::vector<StageEvents> evs;
+  cudaEvent_t t0, t1;
+  CUDA_TRY(cudaEventCreate(&t0)); CUDA_TRY(cudaEventCreate(&t1));
+  const long long l0 = g_launches;
+  CUDA_TRY(cudaStreamSynchronize(g_compute));
+  CUDA_TRY(cudaEventRecord(t0, g_compute));
+  for (int r = 0; r < reps; r++)
+    for (Grp &g : gs)
+      for (int c0 = 0, k = 0; c0 < g.n; c0 += g.S->cap, k++) {
+        const int n = std::min(g.n - c0, g.S->cap);
+        StageEvents ev;
+        ev.on = true;
+        for (int i = 0; i < 4; i++) cudaEventCreate(&ev.e[i]);
+        run_chunk(*g.S, gp, n, g.dx + (size_t)c0 * 3 * g.S->h.nH, nullptr, p->store_schur != 0, k & 1, g_compute, &ev);
+        evs.push_back(ev);
+      }
+  CUDA_TRY(cudaEventRecord(t1, g_compute));
+  CUDA_TRY(cudaStreamSynchronize(g_compute));
+  CUDA_TRY(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, t0, t1);
+  double mi = 0, md = 0;
+  for (StageEvents &ev : evs) {
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, ev.e[0], ev.e[1]);
+    cudaEventElapsedTime(&b, ev.e[1], ev.e[2]);
+    mi += a; md += b;
+    for (int i = 0; i < 4; i++) cudaEventDestroy(ev.e[i]);
+  }
+  if (ms_total) *ms_total = ms;
+  if (ms_integ) *ms_integ = mi;
+  if (ms_dense) *ms_dense = md;
+  if (launches) *launches = g_launches - l0;
+  cudaEventDestroy(t0); cudaEventDestroy(t1);
+  for (Grp &g : gs) cudaFree(g.dx);
+  return HP3D_OK;
+}
+
+int hp3d_gpu_integrate_debug(int plan, const int *norder, const int *norie, const int *norif, const double *xnod, const void *source_qp,
+                             double *W, long long cap_doubles, int *dims) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
+  Plan *p = plan_of(plan);
+  if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
+  std::string err;
+  Signature *S = p->get(norder, norie, norif, true, err);
+  if (!S) return fail(HP3D_EINVAL, "%s", err.c_str());
+  if (S->cap < 1 && S->reserve(1, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());
+  const SigHost &h = S->h;
+  const DenseDims &d = h.dims;
+  const size_t P = d.planes();
+  const size_t need = P * (d.dpg ? d.w_plane() : d.a_plane());
+  if (dims) { dims[0] = d.np; dims[1] = d.nbp; dims[2] = d.nip; dims[3] = d.n; dims[4] = d.nb; dims[5] = d.ni; dims[6] = d.dpg ? d.R() : d.M(); dims[7] = (int)P; }
+  if (!W) return HP3D_OK;
+  if ((size_t)cap_doubles < need) return fail(HP3D_EINVAL, "integrate_debug: need %zu doubles", need);
+  CUDA_TRY(cudaMemcpyAsync(S->d_xnod, xnod, sizeof(double) * 3 * h.nH, cudaMemcpyHostToDevice, g_compute));
+  if (p->fp.source == HP3D_SRC_TABLE) {
+    if (!source_qp) return fail(HP3D_EINVAL, "source table missing");
+    CUDA_TRY(cudaMemcpyAsync(S->d_src, source_qp, sizeof(double) * S->src_doubles(), cudaMemcpyHostToDevice, g_compute));
+  }
+  run_integration(*S, p->geom(), 1, S->d_xnod, S->d_src, g_compute);
+  CUDA_TRY(cudaMemcpyAsync(W, d.dpg ? S->ws.b.W : S->ws.b.Am, sizeof(double) * need, cudaMemcpyDeviceToHost, g_compute));
+  CUDA_TRY(cudaStreamSynchronize(g_compute));
+  CUDA_TRY(cudaGetLastError());
   return HP3D_OK;
 }
 

@@ -1,0 +1,320 @@
+// integ_kernels.cuh -- batched, sum-factorised FP64 element integration for hexahedra (north-star subsystem 2).
+//
+// What it replaces in the reference (paths relative to trunk/):
+//   * the quadrature-point loop of every elem_opt: shape3DH + geom3D (src/element/util/geom3D.F90:30-110,
+//     geom.F90:30-113), Piola maps (e.g. problems/MAXWELL/ULTRAWEAK_DPG/elem/elem_opt.F90:236-325), user source getf;
+//   * the BLAS3 integration calls that follow it (MAXWELL/ULTRAWEAK_DPG/elem/elem_opt.F90:339-470,
+//     POISSON/PRIMAL_DPG/elem_opt.F90:219-269, POISSON/GALERKIN/elem_opt.F90:110-137, MAXWELL/GALERKIN/elem_opt.F90:120-149)
+//   by the sum-factorised evaluation the reference itself uses in its fast path
+//   (problems/LASER/UW_COUPLED/elem/elem_maxwell_fi_hexa.F90:534-1690): every integral is
+//        M[(iA,jA,kA),(iB,jB,kB)] = sum_q  XA[iA][qx] XB[iB][qx] * YA[jA][qy] YB[jB][qy] * ZA[kA][qz] ZB[kB][qz] * F(q)
+//   with 1-D tables X,Y,Z (values or derivatives of the H / Q bases, tables.hpp) and a per-point weight field F(q)
+//   built from the Jacobian (metric tensors w*det*J^-1 J^-T, w/det*J^T J, w*J^-1, w*J/det) and material constants.
+//
+// Kernels:
+//   geom_fields_kernel : one thread per (element, quadrature point): x, J, J^-1, det from the geometry dofs
+//                        (tensor-product H1 functions), then all weight fields + source terms -> WF[e][field][q].
+//   tp3_kernel         : one CTA per (element, block, iA, jA): x- and y-contractions into shared memory, z-contraction
+//                        in registers, result written straight into the dense phase's buffers (W or Am).
+//   const_rows_kernel  : copies the element-independent rows (trace pairings, see forms.hpp) into W.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hp3d {
+
+constexpr int MAXQ = 10;           // points / functions per axis (Gauss table limit of the reference)
+constexpr int TABSZ = MAXQ * MAXQ; // one 1-D table
+enum TabType { T_H = 0, T_DH = 1, T_Q = 2, T_ONE = 3 };
+
+// weight fields per quadrature point
+enum Field {
+  F_D = 0,     // 6: w*det*(J^-1 J^-T), symmetric (00,11,22,01,02,12)     (H1 gradients / H(curl) values)
+  F_C = 6,     // 6: w/det*(J^T J), symmetric                             (H(curl) curls)
+  F_W = 12,    // w
+  F_WDET = 13, // w*det
+  F_WJI = 14,  // 9: w*dxi_a/dx_c  at [14+3a+c]
+  F_WJD = 23,  // 9: w*dx_c/dxi_b/det at [23+3c+b]
+  F_SRC = 32,  // 6: source terms (real problems: [32] = w*det*f ; Maxwell: re/im of w*det*(J^-1 zJ)_a at [32+2a], [33+2a])
+  F_X = 38,    // 3: physical coordinates
+  NFIELD = 41
+};
+__host__ __device__ inline int sym_idx(int a, int b) { return a == b ? a : (a + b + 2); }  // 01->3, 02->4, 12->5
+
+struct GeomParams {
+  int kind;            // HP3D_* problem kind
+  int source;          // HP3D_SRC_*
+  int icomp;           // 0-based component of the manufactured Maxwell solution
+  double omega, eps, mu, sigma;
+};
+
+struct SigTables {               // element-signature tables, device memory
+  const double *tab;             // [3 axes][4 types][TABSZ] ; entry [i*nq + q]
+  const double *wq;              // [3][MAXQ] 1-D weights
+  const int *hdof;               // [nH] geometry dofs: idx0 | idx1<<8 | idx2<<16 | (sign<0)<<24
+  int nq[3];
+  int nH;
+  int nint;
+};
+
+__device__ __forceinline__ void dev_sincos(double x, double &s, double &c) { sincos(x, &s, &c); }
+
+// manufactured "sin" solutions of the reference's problem directories (isol = 1):
+//   POISSON: u = sin(pi x) sin(pi y) sin(pi z), f = -Laplace u          (problems/POISSON/*/common/exact.F90, getf.F90)
+//   MAXWELL: E = p e_ic, p = (1+i) sin(w x) sin(w y) sin(w z)            (MAXWELL/ULTRAWEAK_DPG/common/mfd_solutions.F90:80-100)
+__device__ inline void sin_potential_hess(double a, const double x[3], double &p, double h[9]) {
+  double s[3], c[3];
+  for (int i = 0; i < 3; i++) dev_sincos(a * x[i], s[i], c[i]);
+  const double a2 = a * a;
+  p = s[0] * s[1] * s[2];
+  h[0] = h[4] = h[8] = -a2 * p;
+  h[1] = h[3] = a2 * c[0] * c[1] * s[2];
+  h[2] = h[6] = a2 * c[0] * c[2] * s[1];
+  h[5] = h[7] = a2 * c[1] * c[2] * s[0];
+}
+
+// grid: ceil(nel*nint/128) x 1, block 128
+__global__ void __launch_bounds__(128) geom_fields_kernel(SigTables sg, GeomParams gp, int nel, const double *__restrict__ xnod,
+                                                          long long xnod_ld, const double *__restrict__ src_tab, double *__restrict__ WF,
+                                                          int *__restrict__ info) {
+  __shared__ double sH[3][TABSZ], sdH[3][TABSZ];
+  for (int i = threadIdx.x; i < 3 * TABSZ; i += blockDim.x) {
+    int ax = i / TABSZ, r = i % TABSZ;
+    sH[ax][r] = sg.tab[(ax * 4 + T_H) * TABSZ + r];
+    sdH[ax][r] = sg.tab[(ax * 4 + T_DH) * TABSZ + r];
+  }
+  __syncthreads();
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)nel * sg.nint) return;
+  const int e = (int)(gid / sg.nint), q = (int)(gid % sg.nint);
+  const int qx = q % sg.nq[0], qy = (q / sg.nq[0]) % sg.nq[1], qz = q / (sg.nq[0] * sg.nq[1]);
+  const double *xn = xnod + (long long)e * xnod_ld;
+  double x[3] = {0, 0, 0}, J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // J[c + 3*d] = dx_c/dxi_d  (column-major like dxdxi)
+  for (int k = 0; k < sg.nH; k++) {
+    const int d = sg.hdof[k];
+    const int i0 = d & 255, i1 = (d >> 8) & 255, i2 = (d >> 16) & 255;
+    const double sgn = (d >> 24) ? -1.0 : 1.0;
+    const double h0 = sH[0][i0 * sg.nq[0] + qx], h1 = sH[1][i1 * sg.nq[1] + qy], h2 = sH[2][i2 * sg.nq[2] + qz];
+    const double g0 = sdH[0][i0 * sg.nq[0] + qx], g1 = sdH[1][i1 * sg.nq[1] + qy], g2 = sdH[2][i2 * sg.nq[2] + qz];
+    const double v = sgn * h0 * h1 * h2, d0 = sgn * g0 * h1 * h2, d1 = sgn * h0 * g1 * h2, d2 = sgn * h0 * h1 * g2;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const double xc = xn[3 * k + c];
+      x[c] += xc * v;
+      J[c] += xc * d0; J[c + 3] += xc * d1; J[c + 6] += xc * d2;
+    }
+  }
+  // determinant (Sarrus) and inverse by cofactors, as src/element/util/geom.F90:57-113
+  const double det = J[0] * J[4] * J[8] + J[1] * J[5] * J[6] + J[2] * J[3] * J[7] - J[2] * J[4] * J[6] - J[0] * J[5] * J[7] - J[1] * J[3] * J[8];
+  if (!(det > 0.0)) info[e] = -1;
+  double Ji[9];  // Ji[a + 3*c] = dxi_a/dx_c
+  Ji[0] = (J[4] * J[8] - J[5] * J[7]) / det;
+  Ji[1] = (-J[1] * J[8] + J[2] * J[7]) / det;
+  Ji[2] = (J[1] * J[5] - J[2] * J[4]) / det;
+  Ji[3] = (J[5] * J[6] - J[3] * J[8]) / det;
+  Ji[4] = (J[0] * J[8] - J[2] * J[6]) / det;
+  Ji[5] = (-J[0] * J[5] + J[2] * J[3]) / det;
+  Ji[6] = (J[3] * J[7] - J[4] * J[6]) / det;
+  Ji[7] = (-J[0] * J[7] + J[1] * J[6]) / det;
+  Ji[8] = (J[0] * J[4] - J[1] * J[3]) / det;
+  const double w = sg.wq[qx] * sg.wq[MAXQ + qy] * sg.wq[2 * MAXQ + qz];
+  double *F = WF + (long long)e * NFIELD * sg.nint + q;
+  const long long fs = sg.nint;
+  const double wd = w * det, wod = w / det;
+  for (int a = 0; a < 3; a++)
+    for (int b = a; b < 3; b++) {
+      double dd = 0, cc = 0;
+      for (int c = 0; c < 3; c++) { dd += Ji[a + 3 * c] * Ji[b + 3 * c]; cc += J[c + 3 * a] * J[c + 3 * b]; }
+      F[(F_D + sym_idx(a, b)) * fs] = wd * dd;
+      F[(F_C + sym_idx(a, b)) * fs] = wod * cc;
+    }
+  F[F_W * fs] = w;
+  F[F_WDET * fs] = wd;
+  for (int a = 0; a < 3; a++)
+    for (int c = 0; c < 3; c++) {
+      F[(F_WJI + 3 * a + c) * fs] = w * Ji[a + 3 * c];
+      F[(F_WJD + 3 * c + a) * fs] = wod * J[c + 3 * a];
+    }
+  for (int c = 0; c < 3; c++) F[(F_X + c) * fs] = x[c];
+  // ---- source term
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  if (gp.kind == 1 || gp.kind == 2) {  // Poisson: f(x)
+    double f = 0.0;
+    if (gp.source == 9) f = src_tab[(long long)e * sg.nint + q];
+    else if (gp.source == 1) { double p, h[9]; sin_potential_hess(3.14159265358979323846, x, p, h); f = -(h[0] + h[4] + h[8]); }
+    s[0] = wd * f;
+  } else {  // Maxwell: complex vector zJ(x)
+    double jr[3] = {0, 0, 0}, ji[3] = {0, 0, 0};
+    if (gp.source == 9) {
+      const double *t = src_tab + ((long long)e * sg.nint + q) * 6;
+      for (int c = 0; c < 3; c++) { jr[c] = t[2 * c]; ji[c] = t[2 * c + 1]; }
+    } else if (gp.source == 1) {
+      double p, h[9], cc[3];
+      sin_potential_hess(gp.omega, x, p, h);      // real profile; amplitude (1+i) applied below
+      const int ic = gp.icomp;
+      for (int c = 0; c < 3; c++) cc[c] = h[c + 3 * ic];
+      cc[ic] -= h[0] + h[4] + h[8];               // curl curl (p e_ic) = grad(d_ic p) - Laplace(p) e_ic
+      if (gp.kind == 4) {
+        // J = curl H - i w eps E, H = curl E / (-i w mu)  (MAXWELL/ULTRAWEAK_DPG/getf.F90)  => J = (i/(w mu)) cc(1+i) - i w eps p(1+i) e_ic
+        const double a = 1.0 / (gp.omega * gp.mu), b = gp.omega * gp.eps;
+        for (int c = 0; c < 3; c++) { jr[c] = -a * cc[c]; ji[c] = a * cc[c]; }   // i*(1+i) = -1 + i
+        jr[ic] += b * p; ji[ic] -= b * p;                                           // -i*(1+i) = 1 - i
+      } else {
+        // -i w J = curl(1/mu curl E) - (w^2 eps - i w sigma) E   (MAXWELL/GALERKIN/common/getf.F90:50-73)
+        // store g = -i w J directly (the load vector is -i w (J,F))
+        const double zr = gp.omega * gp.omega * gp.eps, zi = -gp.omega * gp.sigma;  // zb = zr + i zi
+        for (int c = 0; c < 3; c++) { jr[c] = cc[c] / gp.mu; ji[c] = cc[c] / gp.mu; }
+        // zb*(1+i)*p = (zr - zi) + i (zr + zi)
+        jr[ic] -= (zr - zi) * p; ji[ic] -= (zr + zi) * p;
+      }
+    }
+    for (int a = 0; a < 3; a++) {
+      double gr = 0, gi = 0;
+      for (int c = 0; c < 3; c++) { gr += Ji[a + 3 * c] * jr[c]; gi += Ji[a + 3 * c] * ji[c]; }
+      s[2 * a] = wd * gr; s[2 * a + 1] = wd * gi;
+    }
+  }
+  for (int i = 0; i < 6; i++) F[(F_SRC + i) * fs] = s[i];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+struct FamilyDesc { int n[3]; int tab[3]; };             // grid extents and base table type per axis
+struct TermDesc { int dA, dB, field, slot; double coef; };  // derivative axis of the A / B factor (-1: none)
+struct SlotDesc { int zA, zB; double c[2]; };            // z-axis table types; contribution to the two output channels
+struct ChannelDesc {
+  int mat;        // 0: W, 1: Am ; -1: unused
+  int plane;      // 0 real, 1 imaginary
+  int row0, col0; // affine target (row = row0 + lA) unless a map is given
+  int rowmap, colmap;  // offsets into the map pool or -1.  map entry m: 0 skip, else target = |m|-1, sign = sgn(m)
+};
+struct BlockDesc { int famA, famB, t0, nt, s0, ns; ChannelDesc ch[2]; };
+struct WorkItem { short block, iA, jA, pad; };
+
+struct MatTarget { double *base; long long batch, plane; int ld; };
+
+struct Tp3Args {
+  const double *tab;            // signature tables [3][4][TABSZ]
+  const FamilyDesc *fam;
+  const TermDesc *term;
+  const SlotDesc *slot;
+  const BlockDesc *block;
+  const WorkItem *work;
+  const int *maps;
+  const double *WF;             // [nel][NFIELD][nint]
+  int nq[3];
+  int nint;
+  MatTarget mat[2];
+};
+
+// dynamic smem: tables 12*TABSZ | T1 [nBx*nqy*nqz] | U [ns][nqz][nBx*nBy]   (sized by the host for the signature)
+template <int NMAX>
+__global__ void __launch_bounds__(384) tp3_kernel(Tp3Args A, int smem_u_off) {
+  extern __shared__ __align__(16) double sm[];
+  double *sTab = sm, *sT1 = sm + 12 * TABSZ, *sU = sm + smem_u_off;
+  const int e = blockIdx.y;
+  const WorkItem wi = A.work[blockIdx.x];
+  const BlockDesc &B = A.block[wi.block];
+  const FamilyDesc fa = A.fam[B.famA], fb = A.fam[B.famB];
+  const int iA = wi.iA, jA = wi.jA;
+  const int nqx = A.nq[0], nqy = A.nq[1], nqz = A.nq[2];
+  const int nBx = fb.n[0], nBy = fb.n[1], nBz = fb.n[2], nAz = fa.n[2];
+  const int nij = nBx * nBy;
+  for (int i = threadIdx.x; i < 12 * TABSZ; i += blockDim.x) sTab[i] = A.tab[i];
+  for (int i = threadIdx.x; i < B.ns * nqz * nij; i += blockDim.x) sU[i] = 0.0;
+  __syncthreads();
+  const double *WFe = A.WF + (long long)e * NFIELD * A.nint;
+  auto tabp = [&](int axis, int type) { return sTab + (axis * 4 + type) * TABSZ; };
+  // ---- stage 1: x and y contractions, term by term, accumulated per slot
+  for (int t = 0; t < B.nt; t++) {
+    const TermDesc T = A.term[B.t0 + t];
+    const double *XA = tabp(0, T.dA == 0 ? T_DH : fa.tab[0]) + iA * nqx;
+    const double *XB = tabp(0, T.dB == 0 ? T_DH : fb.tab[0]);
+    const double *YA = tabp(1, T.dA == 1 ? T_DH : fa.tab[1]) + jA * nqy;
+    const double *YB = tabp(1, T.dB == 1 ? T_DH : fb.tab[1]);
+    const double *Fq = WFe + (long long)T.field * A.nint;
+    for (int o = threadIdx.x; o < nBx * nqy * nqz; o += blockDim.x) {
+      const int iB = o % nBx, qyz = o / nBx;
+      const double *f = Fq + qyz * nqx;
+      double s = 0.0;
+      for (int qx = 0; qx < nqx; qx++) s += XA[qx] * XB[iB * nqx + qx] * f[qx];
+      sT1[o] = s * T.coef;   // [qyz][iB]
+    }
+    __syncthreads();
+    double *U = sU + T.slot * nqz * nij;
+    for (int o = threadIdx.x; o < nij * nqz; o += blockDim.x) {
+      const int ij = o % nij, qz = o / nij, iB = ij % nBx, jB = ij / nBx;
+      double s = 0.0;
+      for (int qy = 0; qy < nqy; qy++) s += YA[qy] * YB[jB * nqy + qy] * sT1[(qz * nqy + qy) * nBx + iB];
+      U[qz * nij + ij] += s;
+    }
+    __syncthreads();
+  }
+  // ---- stage 2: z contraction; thread item = (kA, iB, jB), registers over kB
+  const ChannelDesc c0 = B.ch[0], c1 = B.ch[1];
+  const int lA0 = iA + fa.n[0] * jA, strideA = fa.n[0] * fa.n[1];
+  for (int it = threadIdx.x; it < nAz * nij; it += blockDim.x) {
+    const int ij = it % nij, kA = it / nij;
+    double acc0[NMAX], acc1[NMAX];
+#pragma unroll
+    for (int k = 0; k < NMAX; k++) { acc0[k] = 0.0; acc1[k] = 0.0; }
+    for (int s = 0; s < B.ns; s++) {
+      const SlotDesc S = A.slot[B.s0 + s];
+      const double *ZA = tabp(2, S.zA) + kA * nqz;
+      const double *ZB = tabp(2, S.zB);
+      const double *U = sU + s * nqz * nij + ij;
+      double v[NMAX];
+#pragma unroll
+      for (int qz = 0; qz < NMAX; qz++) v[qz] = (qz < nqz) ? ZA[qz] * U[qz * nij] : 0.0;
+#pragma unroll
+      for (int kB = 0; kB < NMAX; kB++) {
+        if (kB < nBz) {
+          double d = 0.0;
+#pragma unroll
+          for (int qz = 0; qz < NMAX; qz++)
+            if (qz < nqz) d += v[qz] * ZB[kB * nqz + qz];
+          acc0[kB] += S.c[0] * d;
+          acc1[kB] += S.c[1] * d;
+        }
+      }
+    }
+    // write out
+    const int lA = lA0 + strideA * kA;
+#pragma unroll
+    for (int ch = 0; ch < 2; ch++) {
+      const ChannelDesc C = ch ? c1 : c0;
+      if (C.mat < 0) continue;
+      long long row; double sg = 1.0;
+      if (C.rowmap >= 0) { int m = A.maps[C.rowmap + lA]; if (m == 0) continue; row = (m < 0 ? -m : m) - 1; if (m < 0) sg = -1.0; }
+      else row = C.row0 + lA;
+      const MatTarget M = A.mat[C.mat];
+      double *dst = M.base + (long long)e * M.batch + (long long)C.plane * M.plane + row * M.ld;
+#pragma unroll
+      for (int kB = 0; kB < NMAX; kB++) {
+        if (kB < nBz) {
+          const int lB = ij + nij * kB;
+          long long col; double sc = sg;
+          if (C.colmap >= 0) { int m = A.maps[C.colmap + lB]; if (m == 0) continue; col = (m < 0 ? -m : m) - 1; if (m < 0) sc = -sc; }
+          else col = C.col0 + lB;
+          dst[col] = sc * (ch ? acc1[kB] : acc0[kB]);
+        }
+      }
+    }
+  }
+}
+
+// Element-independent rows of W (trace pairings): W[e][plane 0][crow[r]][0..ncol) = CW[r][0..ncol)
+// grid (ceil(ncol/256), nrows, nel)
+__global__ void const_rows_kernel(const double *__restrict__ CW, const int *__restrict__ crow, int ncol, MatTarget M) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncol) return;
+  const int r = blockIdx.y, e = blockIdx.z;
+  M.base[(long long)e * M.batch + (long long)crow[r] * M.ld + c] = CW[(long long)r * ncol + c];
+}
+
+// unit diagonal on rows [n0,n1) of the real plane (keeps padded Gram rows regular); grid (ceil((n1-n0)/64), nel)
+__global__ void unit_diag_kernel(MatTarget M, int n0, int n1) {
+  const int i = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n1) M.base[(long long)blockIdx.y * M.batch + (long long)i * M.ld + i] = 1.0;
+}
+
+}  // namespace hp3d

@@ -81,7 +81,8 @@ int hp3d_gpu_sizes(int plan, const int *norder /*19*/, int *ni, int *nb, int *ni
  *   norder[19*e..]       find_order            (src/datstrs/find_order.F90:5)
  *   norient_edge[12*e..] , norient_face[6*e..]  find_orient (find_orient.F90:8)
  *   xnod[xnod_ld*e..]    nodcor: geometry dofs, (3, nrdofH) column-major (src/constrs/nodcor.F90:19)
- *   source_qp            HP3D_SRC_TABLE only: per element nint values (real problems) or 3*nint complex
+ *   source_qp            HP3D_SRC_TABLE only: element e at source_qp + e*source_ld doubles: nint values f(x_q)
+ *                        (real problems) or 3*nint complex values J(x_q) (Maxwell), quadrature order of set_3D_int
  * Outputs, element e at offset e*stride (strides in SCALARS of the problem's value type; pass the sizes of the
  * largest element), each block column-major with its own exact leading dimension:
  *   Aii (ni x ni), Bi (ni)              condensed system  == ALOC/BLOC after stc_fwd_wrapper
@@ -90,8 +91,8 @@ int hp3d_gpu_sizes(int plan, const int *norder /*19*/, int *ni, int *nb, int *ni
  */
 int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, const int *norient_edge,
                         const int *norient_face, const double *xnod, int xnod_ld, const void *source_qp,
-                        void *Aii, long long sAii, void *Bi, long long sBi, void *ASchur, long long sAS,
-                        void *BSchur, long long sBS, int *ni_out, int *nb_out, int *info);
+                        long long source_ld, void *Aii, long long sAii, void *Bi, long long sBi, void *ASchur,
+                        long long sAS, void *BSchur, long long sBS, int *ni_out, int *nb_out, int *info);
 
 /* Physical coordinates of the volume quadrature points (3, nint) per element, for callers that evaluate
  * their own getf() on the host and pass the values back through source_qp. */
@@ -103,12 +104,34 @@ int hp3d_gpu_quad_points(int plan, int nel, const int *etype, const int *norder,
 int hp3d_gpu_stc_bwd_batch(int complex_mode, int nel, int ni, int nb, const void *ASchur, long long sAS,
                            const void *BSchur, long long sBS, const void *xi, long long sxi, void *xb, long long sxb);
 
-/* Throughput driver used by bench.py: runs the hot path `reps` times over `nel` resident elements (inputs
- * already in HBM, outputs left in HBM), reporting device time from CUDA events on the launching streams.
- * If host_io != 0 the same work is timed end to end from pinned host descriptors to pinned host results. */
+/* Throughput driver used by bench.py: runs the hot path `reps` times over `nel` RESIDENT elements (geometry dofs
+ * already in HBM, condensed outputs left in HBM), timed with CUDA events on the launching stream.
+ *   ms_total   device time of all reps;  ms_integ / ms_dense: the part spent in integration / in the dense phase
+ *   launches   kernels launched inside the timed region
+ * (The end-to-end number with host buffers is measured by calling hp3d_gpu_elem_batch itself.) */
 int hp3d_gpu_bench(int plan, int nel, const int *norder, const int *norient_edge, const int *norient_face,
-                   const double *xnod, int xnod_ld, int reps, int host_io, double *ms_total, double *ms_dense,
-                   long long *launches, long long *h2d_bytes, long long *d2h_bytes);
+                   const double *xnod, int xnod_ld, int reps, int max_chunk, double *ms_total, double *ms_integ,
+                   double *ms_dense, long long *launches);
+
+/* Page-locked host memory for the caller's result arrays (so that the D2H copies of hp3d_gpu_elem_batch are
+ * asynchronous DMA transfers that overlap the next chunk's kernels).  Pageable buffers work too, only slower. */
+void *hp3d_gpu_host_alloc(long long bytes);
+void hp3d_gpu_host_free(void *p);
+
+/* ---- host-only introspection (no GPU needed): the signed tensor-product description of the shape functions.
+ * space: 0 H1, 1 H(curl), 2 H(div), 3 L2.  For dof k (reference order, src/element/shape_1/Hexahedron.F90):
+ *   fam[k] vector direction (0..2, -1 scalar), idx[3k..3k+2] 1-D table index per axis, sgn[k] = +-1.
+ * Returns the number of dofs (or a negative error); arrays may be NULL to query the count. */
+int hp3d_gpu_dof_map(int space, const int *norder, const int *norient_edge, const int *norient_face, int cap, int *fam,
+                     int *idx, int *sgn);
+/* 1-D Gauss rule on [0,1] (nq points) and the tables H[(p+1) x nq], dH[(p+1) x nq], Q[p x nq] evaluated at it */
+int hp3d_gpu_tables_1d(int p, int nq, double *x, double *w, double *H, double *dH, double *Q);
+
+/* Test hook: integrate ONE element of a DPG plan and return the dense phase's raw input buffer W
+ * (planes x R x np doubles, row-major, see hp3d_b200/csrc/dense_pipeline.cuh) with dims[8] =
+ * {np, nbp, nip, n, nb, ni, R, planes}.  For non-DPG plans the buffer is Am (planes x M x M), dims[0] = 0. */
+int hp3d_gpu_integrate_debug(int plan, const int *norder, const int *norient_edge, const int *norient_face,
+                             const double *xnod, const void *source_qp, double *W, long long cap_doubles, int *dims);
 
 /* Test hook: run only the dense phase (DPG normal equations + static condensation) on caller-provided
  * Gram / enriched stiffness matrices.  G: (n x n) Hermitian, upper triangle read; Bm: n x (nb+ni+1), columns

@@ -1,0 +1,143 @@
+"""GPU parity tests proper: the CUDA path through the C ABI against the CPU oracle on the same seeded inputs.
+
+Tolerances (north_star): element and condensed matrices within 1e-12 relative Frobenius error.  The Schur
+back-substitution factors ASchur = A_bb^-1 A_bi are a *solution* of a linear system, so their forward error scales with
+cond(A_bb); they are checked by residual (||A_bb ASchur - A_bi|| / ||A_bi|| via the oracle's own uncondensed matrix)
+and by a conditioning-scaled forward bound.
+"""
+import numpy as np
+import pytest
+
+from tests.util import hexa_xnod, random_signature, uniform_order
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def _engine(kind, **kw):
+    from hp3d_b200.api import ElemEngine
+    return ElemEngine(kind, **kw)
+
+
+def _oracle_params(oracle, **kw):
+    return oracle.default_params(**kw)
+
+
+@pytest.mark.parametrize("p,curved", [(1, 0.0), (2, 0.0), (2, 0.03), (3, 0.02)])
+def test_uw_maxwell_integration_vs_oracle(oracle, gpu, p, curved):
+    """Gram matrix and enriched stiffness of ultraweak Maxwell straight out of the integration kernels
+    (MAXWELL/ULTRAWEAK_DPG/elem/elem_opt.F90:236-768) vs the oracle's BLAS3 restatement."""
+    oracle.set_maxp(6)
+    rng = np.random.default_rng(100 + p)
+    norder, _, _ = random_signature(rng, uniform=True)
+    norder = uniform_order(p)
+    norie = rng.integers(0, 2, 12).astype(np.int32); norif = rng.integers(0, 8, 6).astype(np.int32)
+    nH = oracle.celndof(norder)[0]
+    X = hexa_xnod(nH, h=0.5, jitter=0.15, curved=curved, rng=rng)
+    om = 2 * np.pi
+    prm = _oracle_params(oracle, omega=om)
+    A, b, G, S = oracle.elem(oracle.MAXW_UW, norder, norie, norif, X, prm, want_dpg=True)
+    eng = _engine(4, omega=om)
+    W, d = eng.integrate_debug(norder, norie, norif, X)
+    n, nb, ni, np_, nbp = d["n"], d["nb"], d["ni"], d["np"], d["nbp"]
+    nEE = n // 2
+    Wc = W[0] + 1j * W[1]
+    Gi = np.tril(Wc[:n, :n]); Gi = Gi + np.tril(Gi, -1).conj().T
+    perm = np.empty(n, int); perm[0::2] = np.arange(nEE); perm[1::2] = nEE + np.arange(nEE)
+    Gg = Gi[np.ix_(perm, perm)]
+    Gu = np.triu(G); Go = Gu + np.triu(Gu, 1).conj().T
+    assert relerr(Gg, Go) < 1e-13
+    rows = np.r_[np_ + nbp + np.arange(ni), np_ + np.arange(nb), np_ + nbp + ni]
+    Bg = Wc[rows][:, :n].conj().T[perm]
+    assert relerr(Bg[:, :ni], S[:, :ni]) < 1e-13          # trace pairings
+    assert relerr(Bg[:, ni:ni + nb], S[:, ni:ni + nb]) < 1e-13
+    assert relerr(Bg[:, -1], S[:, -1]) < 1e-13            # load
+    eng.close()
+
+
+CASES = [
+    # kind, p, nel, tolerances on (Aii, Bi)
+    (1, 1, 3), (1, 2, 3), (1, 3, 4), (1, 4, 2),
+    (2, 1, 3), (2, 2, 3), (2, 3, 2), (2, 4, 2),
+    (4, 1, 3), (4, 2, 3), (4, 3, 2),
+]
+
+
+@pytest.mark.parametrize("kind,p,nel", CASES)
+def test_condensed_vs_oracle(oracle, gpu, kind, p, nel):
+    """elem + stc_fwd_wrapper through hp3d_gpu_elem_batch vs the oracle, uniform order p, random orientations,
+    jittered + slightly curved geometry, several elements per call."""
+    oracle.set_maxp(6)
+    oracle.use_blas(True)
+    rng = np.random.default_rng(1000 * kind + p)
+    norder = np.tile(uniform_order(p), (nel, 1))
+    norie = rng.integers(0, 2, (nel, 12)).astype(np.int32); norif = rng.integers(0, 8, (nel, 6)).astype(np.int32)
+    norie[0] = 0; norif[0] = 0
+    nH = oracle.celndof(norder[0])[0]
+    X = np.stack([hexa_xnod(nH, h=0.5, origin=(0.1 * e, 0.2, 0.3), jitter=0.15, curved=0.01 if p > 1 else 0.0, rng=rng) for e in range(nel)])
+    om = 2 * np.pi if kind == 4 else 1.0
+    prm = _oracle_params(oracle, omega=om)
+    eng = _engine(kind, omega=om)
+    res = eng.elem_stc_batch(norder, norie, norif, X)
+    assert (res["info"] == 0).all()
+    for e in range(nel):
+        Aii, Bi, AS, BS = eng.unpack(res, e)
+        rA, rB, rAS, rBS = oracle.condensed(kind, norder[e], norie[e], norif[e], X[e], prm)
+        assert Aii.shape == rA.shape and AS.shape == rAS.shape
+        assert relerr(Aii, rA) < 1e-12, (e, relerr(Aii, rA))
+        assert relerr(Bi, rB) < 1e-12, (e, relerr(Bi, rB))
+        if AS.size:
+            # residual check of the stored factors against the oracle's uncondensed element matrix
+            Afull, bfull = oracle.elem(kind, norder[e], norie[e], norif[e], X[e], prm)
+            perm, ni, nb = oracle.stc_partition(kind, norder[e])
+            Ap = Afull[np.ix_(perm, perm)]; bp = bfull[perm]
+            Abb, Abi = Ap[ni:, ni:], Ap[ni:, :ni]
+            assert relerr(Abb @ AS, Abi) < 1e-12
+            assert relerr(Abb @ BS, bp[ni:]) < 1e-12
+            cond = np.linalg.cond(Abb)
+            assert relerr(AS, rAS) < 1e-15 * cond * 50 + 1e-12
+            assert relerr(BS, rBS) < 1e-15 * cond * 50 + 1e-12
+    eng.close()
+
+
+def test_mixed_signatures_one_call(oracle, gpu):
+    """Elements of different order and orientation in one batch (grouped by signature internally)."""
+    oracle.set_maxp(6)
+    rng = np.random.default_rng(7)
+    sigs = [random_signature(rng, pmax=3) for _ in range(3)] + [(uniform_order(2), np.zeros(12, np.int32), np.zeros(6, np.int32))]
+    order = [0, 3, 1, 0, 2, 3, 1]
+    nel = len(order)
+    norder = np.stack([sigs[i][0] for i in order]); norie = np.stack([sigs[i][1] for i in order]); norif = np.stack([sigs[i][2] for i in order])
+    nHmax = max(oracle.celndof(s[0])[0] for s in sigs)
+    X = np.zeros((nel, nHmax, 3))
+    for e in range(nel):
+        nH = oracle.celndof(norder[e])[0]
+        X[e, :nH] = hexa_xnod(nH, h=0.4, jitter=0.1, rng=rng)
+    for kind in (1, 2, 4):
+        om = 2 * np.pi if kind == 4 else 1.0
+        prm = _oracle_params(oracle, omega=om)
+        eng = _engine(kind, omega=om)
+        res = eng.elem_stc_batch(norder, norie, norif, X)
+        assert (res["info"] == 0).all()
+        for e in range(nel):
+            nH = oracle.celndof(norder[e])[0]
+            Aii, Bi, AS, BS = eng.unpack(res, e)
+            rA, rB, rAS, rBS = oracle.condensed(kind, norder[e], norie[e], norif[e], X[e, :nH], prm)
+            assert Aii.shape == rA.shape
+            assert relerr(Aii, rA) < 1e-12, (kind, e, relerr(Aii, rA))
+            assert relerr(Bi, rB) < 1e-12, (kind, e)
+        eng.close()
+
+
+def test_negative_jacobian_flag(gpu):
+    """geom3D.F90:92-109: a negative Jacobian is reported per element (info = -1) instead of stopping."""
+    eng = _engine(1)
+    norder = uniform_order(2)[None]
+    X = hexa_xnod(27)[None].copy()
+    X[0, :8, 0] *= -1.0   # mirror -> negative determinant
+    res = eng.elem_stc_batch(norder, np.zeros((1, 12), np.int32), np.zeros((1, 6), np.int32), X)
+    assert res["info"][0] == -1
+    eng.close()
