@@ -1,0 +1,258 @@
+#!/usr/bin/env python
+"""Benchmark of the element-local hot path: condensed element matrices per second (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--elements B] [--p 5] [--kind 4]
+
+Workload (config[3] of BASELINE.json, the configuration the metric is quoted on): ultraweak DPG Maxwell, hexahedra of
+order p=5, enrichment dp=1, complex FP64, perturbed (jittered) cube mesh so no two elements are congruent; one "step" =
+one pass of the hot path (descriptors -> integration -> DPG normal equations -> static condensation) over a batch of B
+elements per GPU.  Elements are block-partitioned over the ranks (hp3D's ZOLTAN_LB=0 split); there is no collective on
+the path, so scaling is "weak" (fixed B per GPU).
+
+  value     whole-job elements/s with the geometry dofs already resident in HBM (device time, CUDA events on the
+            launching stream inside the library, max over ranks)
+  e2e       the same metric through the C-ABI call hp3d_gpu_elem_batch with HOST buffers: H2D of the geometry dofs and
+            D2H of Aii, Bi, ASchur, BSchur inside the timed region
+  roofline  FP64 tensor (DMMA) roofline of the dense phase: algorithmic flops / time of the dense phase
+  cpu_baseline  the CPU oracle (restatement of the reference's elem_opt + stc_fwd_herm, OpenMP over elements like
+            par_mumps_sc.F90:347, single-threaded OpenBLAS per element) on the host's cores, bounded sample
+
+--impl reference times that CPU path alone (the reference is Fortran + PETSc/MUMPS and cannot be built in this image).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DMMA_PEAK_TFLOPS = 37.05   # measured on this pool's B200: raw mma.sync m16n8k16.f64 loop (profiles/r01_dmma_probe.jsonl);
+                           # cuBLAS DGEMM 8192^3 reaches 35.5, ZGEMM 4096^3 36.8 (profiles/r01_fp64_peak.json)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for i, nm in enumerate(names):
+                if f[5 + i].lower().startswith("active"):
+                    reasons.add(nm)
+        # "under load" = samples drawing real power
+        load = [s for s, p in zip(sm, pw) if p > 300] or sm
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+def cpu_reference_rate(kind, p, nsample, threads, omega):
+    """Elements/s of the CPU restatement (oracle) on `threads` host threads over `nsample` elements of the same workload."""
+    from oracle import oracle as O
+    from hp3d_b200 import synth
+    O.set_maxp(6)
+    blas = O.use_blas(True, threads=1)
+    norder, noe, nof, xnod = synth.cube_mesh(nsample, p)
+    prm = O.default_params(omega=omega)
+    t0 = time.perf_counter()
+    out = O.condensed_batch(kind, norder, noe, nof, xnod, prm, nthreads=threads)
+    dt = time.perf_counter() - t0
+    assert out[-1] == 0
+    return nsample / dt, dt, blas
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    nsample = args.cpu_sample or max(2 * cores, 8)
+    omega = 2 * np.pi
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_rate(args.kind, args.p, max(cores, 1), cores, omega)
+    t_tot, n_tot = 0.0, 0
+    for _ in range(args.steps):
+        r, dt, blas = cpu_reference_rate(args.kind, args.p, nsample, cores, omega)
+        t_tot += dt; n_tot += nsample
+    val = n_tot / t_tot
+    sample = f"{nsample} elements/step of the same perturbed-cube workload, {cores} OpenMP threads over elements, single-threaded {'OpenBLAS' if blas else 'built-in loops'} per element"
+    print(json.dumps({
+        "impl": "reference", "metric": "condensed element matrices/sec", "value": val, "unit": "elements/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "c128" if args.kind >= 3 else "f64", "data": "synthetic",
+        "config": workload_config(args, nsample),
+        "cpu_baseline": {"value": val, "unit": "elements/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, B):
+    names = {1: "Poisson Galerkin", 2: "Poisson primal DPG (dp=1)", 3: "Maxwell Galerkin", 4: "Maxwell ultraweak DPG (dp=1, adjoint-graph norm)"}
+    return {"workload": f"{names[args.kind]}, hexa p={args.p}, complex FP64, perturbed cube mesh (jitter 0.15h, seed 12345)" if args.kind >= 3
+            else f"{names[args.kind]}, hexa p={args.p}, real FP64, perturbed cube mesh (jitter 0.15h, seed 12345)",
+            "elements_per_gpu_per_step": B, "partition": "contiguous blocks of the element list per rank (ZOLTAN_LB=0)",
+            "l2": "per-step working set (>100 MB per element at p=5) far exceeds the 126 MB L2; no flush needed"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--elements", type=int, default=256, help="elements per GPU per step")
+    ap.add_argument("--e2e-elements", type=int, default=128)
+    ap.add_argument("--p", type=int, default=5)
+    ap.add_argument("--kind", type=int, default=4)
+    ap.add_argument("--cpu-sample", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from hp3d_b200 import synth
+    from hp3d_b200.api import ElemEngine, pinned_empty
+    omega = 2 * np.pi if args.kind == 4 else 1.0
+    eng = ElemEngine(args.kind, device=local, omega=omega)
+    B = args.elements
+    norder, noe, nof, xnod = synth.cube_mesh(B, args.p, first=rank * B, total=world * B)
+    ntest, ntrial, ni, nb = synth.problem_sizes(args.kind, args.p)
+    F_dense = synth.dense_flops(args.kind, ntest, ntrial, ni, nb)
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up (also builds the signature tables and allocates the workspaces)
+    for _ in range(max(args.warmup, 3)):
+        eng.bench(norder, noe, nof, xnod, reps=1)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    r = eng.bench(norder, noe, nof, xnod, reps=args.steps)   # K steps, CUDA events on the launching stream around them
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = r["ms_total"]
+    ms_dense, ms_integ = r["ms_dense"], r["ms_integ"]
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms, ms_dense, ms_integ], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_dense, ms_integ = [float(v) for v in t.tolist()]
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end to end through hp3d_gpu_elem_batch with pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        Be = min(args.e2e_elements, B)
+        dt = eng.dtype
+        bufs = [pinned_empty((Be, ni * ni), dt), pinned_empty((Be, ni), dt), pinned_empty((Be, max(nb * ni, 1)), dt), pinned_empty((Be, max(nb, 1)), dt)]
+        out = dict(Aii=bufs[0].a, Bi=bufs[1].a, ASchur=bufs[2].a, BSchur=bufs[3].a)
+        xs = pinned_empty(xnod[:Be].shape, np.float64)
+        xs.a[...] = xnod[:Be]
+        for _ in range(2):
+            eng.elem_stc_batch(norder[:Be], noe[:Be], nof[:Be], xs.a, out=out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = eng.elem_stc_batch(norder[:Be], noe[:Be], nof[:Be], xs.a, out=out)   # returns after the last D2H completed
+        te = time.perf_counter() - t0
+        barrier()
+        assert (res["info"] == 0).all()
+        if dist is not None:
+            import torch
+            t = torch.tensor([te], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            te = float(t.item())
+        es = 16 if args.kind >= 3 else 8
+        e2e = {"value": world * Be * args.steps / te, "unit": "elements/s", "elements_per_gpu_per_step": Be,
+               "h2d_bytes_per_step": int(xs.a.nbytes), "d2h_bytes_per_step": int(Be * (es * (ni * ni + ni + nb * ni + nb) + 4)),
+               "timer": "host wall clock around the synchronous C-ABI calls (they return after the last D2H)"}
+        for b in bufs + [xs]:
+            b.free()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    achieved = F_dense * B * args.steps / (ms_dense * 1e-3) / 1e12
+    out = {
+        "metric": "condensed element matrices/sec", "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "c128" if args.kind >= 3 else "f64", "data": "synthetic", "config": workload_config(args, B),
+        "gpu_launches": int(r["launches"]), "clocks": clocks, "e2e": e2e,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / DMMA_PEAK_TFLOPS,
+                     "traffic": None, "kernel": "gemm_nc_kernel<complex> (all launches of the dense phase: Cholesky panels, solves, HERK, Schur)",
+                     "flops_per_element": F_dense, "ms_dense_per_step": ms_dense / args.steps, "ms_integration_per_step": ms_integ / args.steps,
+                     "peak_source": "own probe: raw FP64 DMMA loop on this pool's B200 (profiles/r01_dmma_probe.jsonl); MEASURED_PEAKS.json has no FP64 entry",
+                     "whole_step_frac": F_dense * B * args.steps / (ms * 1e-3) / 1e12 / DMMA_PEAK_TFLOPS},
+    }
+    if not args.no_cpu:
+        cores = host_cores()
+        ns = args.cpu_sample or max(2 * cores, 8)
+        v, dtc, blas = cpu_reference_rate(args.kind, args.p, ns, cores, omega)
+        out["cpu_baseline"] = {"value": v, "unit": "elements/s", "cores": cores, "kind": "port",
+                               "sample": f"{ns} elements of the same workload in {dtc:.1f} s; OpenMP over elements ({cores} threads), single-threaded {'OpenBLAS' if blas else 'built-in loops'} per element"}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -16,6 +16,7 @@ std::string g_err;
 int g_device = -1;
 std::vector<Plan *> g_plans;
 cudaStream_t g_compute = nullptr, g_copy = nullptr;
+int g_max_chunk = 0;
 
 int fail(int code, const char *fmt, ...) {
   char buf[512];
@@ -137,6 +138,13 @@ int hp3d_gpu_plan(int problem_kind, const hp3d_params *prm) {
   return (int)g_plans.size() - 1;
 }
 
+int hp3d_gpu_set_chunk(int max_elements) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (max_elements < 0) return fail(HP3D_EINVAL, "negative chunk size");
+  g_max_chunk = max_elements;
+  return HP3D_OK;
+}
+
 int hp3d_gpu_plan_destroy(int plan) {
   std::lock_guard<std::mutex> lk(g_mu);
   Plan *p = plan_of(plan);
@@ -233,7 +241,10 @@ int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, 
     Signature *S = p->get(norder + 19 * e0, norie + 12 * e0, norif + 6 * e0, true, err);
     if (!S) { rc = fail(HP3D_EINVAL, "element %d: %s", e0, err.c_str()); break; }
     if (xnod_ld < 3 * S->h.nH) { rc = fail(HP3D_EINVAL, "xnod_ld=%d < 3*nrdofH=%d", xnod_ld, 3 * S->h.nH); break; }
-    const int cap = chunk_capacity(*S, (int)el.size());
+    int want = (int)el.size();
+    if (g_max_chunk > 0) want = std::min(want, g_max_chunk);
+    else if (want >= 128) want = std::max(32, (want + 3) / 4);   // >= 4 chunks: D2H of chunk k overlaps chunk k+1
+    const int cap = chunk_capacity(*S, want);
     if (cap < 1) { rc = fail(HP3D_ENOMEM, "not enough device memory for one element (%zu bytes)", S->bytes_per_element()); break; }
     if (S->reserve(cap, err)) { rc = fail(HP3D_ENOMEM, "%s", err.c_str()); break; }
     const SigHost &h = S->h;
@@ -242,8 +253,9 @@ int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, 
     const size_t bA = (size_t)h.ni * h.ni, bB = h.ni, bAS = (size_t)h.nb * h.ni, bBS = h.nb;
     hinfo.resize(2 * (size_t)S->cap);
     int nchunk = 0;
-    for (size_t c0 = 0; c0 < el.size(); c0 += S->cap, nchunk++) {
-      const int n = (int)std::min(el.size() - c0, (size_t)S->cap), buf = nchunk & 1;
+    const int chunk = cap;
+    for (size_t c0 = 0; c0 < el.size(); c0 += chunk, nchunk++) {
+      const int n = (int)std::min(el.size() - c0, (size_t)chunk), buf = nchunk & 1;
       // the pinned input staging of this buffer must have been consumed by the H2D of chunk nchunk-2
       if (nchunk >= 2) cudaEventSynchronize(evH2D[buf]);
       double *hx = S->h_xnod + (size_t)buf * nx * S->cap, *hs = S->h_src + (size_t)buf * nsrc * S->cap;
@@ -284,15 +296,15 @@ int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, 
       if (nchunk >= 1) {
         const int pb = buf ^ 1;
         cudaEventSynchronize(evCopy[pb]);
-        const size_t pc0 = c0 - S->cap;
-        const int pn = (int)std::min(el.size() - pc0, (size_t)S->cap);
+        const size_t pc0 = c0 - chunk;
+        const int pn = chunk;
         for (int i = 0; i < pn; i++) { const int e = el[pc0 + i]; if (info) info[e] = hinfo[(size_t)pb * S->cap + i]; }
       }
     }
     {  // drain the last chunk
       const int lb = (nchunk - 1) & 1;
       cudaEventSynchronize(evCopy[lb]);
-      const size_t pc0 = (size_t)(nchunk - 1) * S->cap;
+      const size_t pc0 = (size_t)(nchunk - 1) * chunk;
       const int pn = (int)(el.size() - pc0);
       for (int i = 0; i < pn; i++) { const int e = el[pc0 + i]; if (info) info[e] = hinfo[(size_t)lb * S->cap + i]; }
     }
@@ -374,7 +386,7 @@ int hp3d_gpu_bench(int plan, int nel, const int *norder, const int *norie, const
   for (int e = 0; e < nel; e++) groups[Plan::key(norder + 19 * e, norie + 12 * e, norif + 6 * e)].push_back(e);
   const GeomParams gp = p->geom();
   std::string err;
-  struct Grp { Signature *S; double *dx; int n; };
+  struct Grp { Signature *S; double *dx; int n, chunk; };
   std::vector<Grp> gs;
   for (auto &g : groups) {
     const int e0 = g.second[0];
@@ -391,7 +403,7 @@ int hp3d_gpu_bench(int plan, int nel, const int *norder, const int *norie, const
     double *dx;
     CUDA_TRY(cudaMalloc(&dx, sizeof(double) * hx.size()));
     CUDA_TRY(cudaMemcpy(dx, hx.data(), sizeof(double) * hx.size(), cudaMemcpyHostToDevice));
-    gs.push_back(Grp{S, dx, (int)g.second.size()});
+    gs.push_back(Grp{S, dx, (int)g.second.size(), cap});
   }
   std::vector<StageEvents> evs;
   cudaEvent_t t0, t1;
@@ -401,8 +413,8 @@ int hp3d_gpu_bench(int plan, int nel, const int *norder, const int *norie, const
   CUDA_TRY(cudaEventRecord(t0, g_compute));
   for (int r = 0; r < reps; r++)
     for (Grp &g : gs)
-      for (int c0 = 0, k = 0; c0 < g.n; c0 += g.S->cap, k++) {
-        const int n = std::min(g.n - c0, g.S->cap);
+      for (int c0 = 0, k = 0; c0 < g.n; c0 += g.chunk, k++) {
+        const int n = std::min(g.n - c0, g.chunk);
         StageEvents ev;
         ev.on = true;
         for (int i = 0; i < 4; i++) cudaEventCreate(&ev.e[i]);

@@ -94,6 +94,10 @@ int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, 
                         long long source_ld, void *Aii, long long sAii, void *Bi, long long sBi, void *ASchur,
                         long long sAS, void *BSchur, long long sBS, int *ni_out, int *nb_out, int *info);
 
+/* Upper bound on the number of elements processed per internal chunk by hp3d_gpu_elem_batch (0 = automatic: as many
+ * as fit in device memory, but at least four chunks for large groups so that result copies overlap compute). */
+int hp3d_gpu_set_chunk(int max_elements);
+
 /* Physical coordinates of the volume quadrature points (3, nint) per element, for callers that evaluate
  * their own getf() on the host and pass the values back through source_qp. */
 int hp3d_gpu_quad_points(int plan, int nel, const int *etype, const int *norder, const int *norient_edge,

@@ -141,3 +141,51 @@ def test_negative_jacobian_flag(gpu):
     res = eng.elem_stc_batch(norder, np.zeros((1, 12), np.int32), np.zeros((1, 6), np.int32), X)
     assert res["info"][0] == -1
     eng.close()
+
+
+def test_full_size_p5_uw_maxwell(oracle, gpu):
+    """BASELINE.json configs[3] at full size (p=5, dp=1: 1764 test / 1350 trial dofs, ni=600, nb=750), two elements of the
+    bench workload, against the oracle; plus the size-independent properties used when the oracle is too slow."""
+    from hp3d_b200 import synth
+    oracle.set_maxp(6)
+    oracle.use_blas(True)
+    nel = 2
+    norder, noe, nof, xnod = synth.cube_mesh(nel, 5, first=3)
+    om = 2 * np.pi
+    eng = _engine(4, omega=om)
+    res = eng.elem_stc_batch(norder, noe, nof, xnod)
+    assert (res["info"] == 0).all() and (res["ni"] == 600).all() and (res["nb"] == 750).all()
+    prm = _oracle_params(oracle, omega=om)
+    for e in range(nel):
+        Aii, Bi, AS, BS = eng.unpack(res, e)
+        rA, rB, rAS, rBS = oracle.condensed(4, norder[e], noe[e], nof[e], xnod[e], prm)
+        assert relerr(Aii, rA) < 1e-12, relerr(Aii, rA)
+        assert relerr(Bi, rB) < 1e-12, relerr(Bi, rB)
+        assert relerr(Aii, Aii.conj().T) < 1e-14            # Hermitian (ZHERK + mirror, elem_opt.F90:862-869)
+        assert relerr(AS, rAS) < 1e-9 and relerr(BS, rBS) < 1e-9
+    eng.close()
+
+
+def test_properties_at_full_size(gpu):
+    """Size-independent properties on a larger p=5 batch (no oracle): results do not depend on the batch composition or
+    chunking, translation of an element leaves its matrix unchanged and only rephases nothing for a zero source, and the
+    condensed matrix is Hermitian positive semi-definite (it is a Schur complement of B^H G^-1 B)."""
+    from hp3d_b200 import synth
+    nel = 6
+    norder, noe, nof, xnod = synth.cube_mesh(nel, 5)
+    eng = _engine(4, omega=2 * np.pi, source=0)
+    a = eng.elem_stc_batch(norder, noe, nof, xnod)
+    gpu.hp3d_gpu_set_chunk(2)
+    b = eng.elem_stc_batch(norder[::-1].copy(), noe, nof, xnod[::-1].copy())
+    gpu.hp3d_gpu_set_chunk(0)
+    for e in range(nel):
+        A1 = eng.unpack(a, e)[0]; A2 = eng.unpack(b, nel - 1 - e)[0]
+        assert np.array_equal(A1, A2)                       # bitwise: same kernels, same data, different batch slot
+        assert np.abs(eng.unpack(a, e)[1]).max() == 0.0    # zero source -> zero load
+    xs = xnod.copy(); xs[:, :8, :] += np.array([0.25, -0.5, 1.0])
+    c = eng.elem_stc_batch(norder, noe, nof, xs)
+    for e in range(nel):
+        assert relerr(eng.unpack(c, e)[0], eng.unpack(a, e)[0]) < 1e-11
+    w = np.linalg.eigvalsh(eng.unpack(a, 0)[0])
+    assert w.min() > -1e-10 * w.max()
+    eng.close()

@@ -58,6 +58,15 @@ template<int MODE> __global__ void __launch_bounds__(256) rate(double*out,int it
       if(MODE==1){ double aa[2]={a[i&7],a[(i+1)&7]}; mma1684(acc[i],aa,b[i&3]); }
       if(MODE==2){ double aa[4]={a[i&7],a[(i+1)&7],a[(i+2)&7],a[(i+3)&7]}; double bb[2]={b[i&3],b[(i+1)&3]}; mma1688(acc[i],aa,bb); }
       if(MODE==3){ mma16816(acc[i],a,b); }
+      if(MODE==5){ // mixed: one m8n8k4 DMMA (512 flop/warp) + 2 DFMA per lane (128 flop/warp): do the pipes overlap?
+        mma884(acc[i][0],acc[i][1],a[i&7],b[i&3]);
+        acc[i][2]=fma(acc[i][2],a[2],b[2]); acc[i][3]=fma(acc[i][3],a[3],b[3]);
+      }
+      if(MODE==6){ // mixed 1:1 flops: one m8n8k4 DMMA (512) + 8 DFMA per lane (512)
+        mma884(acc[i][0],acc[i][1],a[i&7],b[i&3]);
+        #pragma unroll
+        for(int j=0;j<4;j++){ acc[(i+1)&7][2]=fma(acc[(i+1)&7][2],a[j],b[j]); acc[(i+2)&7][3]=fma(acc[(i+2)&7][3],a[j+4],b[j]); }
+      }
       if(MODE==4){ // plain DFMA: 32 independent chains
         #pragma unroll
         for(int j=0;j<4;j++) acc[i][j]=fma(acc[i][j],a[j],b[j]);
@@ -98,6 +107,7 @@ int main(){
     run_rate<0>("dmma_m8n8k4",2.0*8*8*4,c); run_rate<1>("dmma_m16n8k4",2.0*16*8*4,c);
     run_rate<2>("dmma_m16n8k8",2.0*16*8*8,c); run_rate<3>("dmma_m16n8k16",2.0*16*8*16,c);
     run_rate<4>("dfma",2.0*32*4,c);
+    run_rate<5>("mixed_dmma512_dfma128",512.0+128.0,c); run_rate<6>("mixed_dmma512_dfma512",512.0+512.0,c);
   }
   return 0;
 }

@@ -1,0 +1,32 @@
+"""Generate the golden fixtures under tests/golden/ from the CPU oracle (the reference itself cannot be built here:
+no Fortran compiler).  Each fixture holds the inputs the reference's `elem` would see for one or two
+elements and the condensed outputs.  Run:  python tools/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+from tests.util import hexa_xnod, random_signature, uniform_order  # noqa: E402
+
+O.set_maxp(6)
+O.use_blas(False)   # built-in loops: no dependence on the BLAS build
+CASES = [(1, 2, 11), (1, 3, 12), (2, 2, 21), (2, 3, 22), (3, 2, 31), (4, 1, 41), (4, 2, 42)]
+for kind, p, seed in CASES:
+    rng = np.random.default_rng(seed)
+    nel = 2
+    norder = np.tile(uniform_order(p), (nel, 1))
+    norie = rng.integers(0, 2, (nel, 12)).astype(np.int32)
+    norif = rng.integers(0, 8, (nel, 6)).astype(np.int32)
+    nH = O.celndof(norder[0])[0]
+    xnod = np.stack([hexa_xnod(nH, h=0.5, origin=(0.2, 0.1 * e, 0.3), jitter=0.15, curved=0.01, rng=rng) for e in range(nel)])
+    omega = 2 * np.pi if kind == 4 else (np.pi if kind == 3 else 1.0)
+    prm = O.default_params(omega=omega)
+    out = [O.condensed(kind, norder[e], norie[e], norif[e], xnod[e], prm) for e in range(nel)]
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"cond_kind{kind}_p{p}.npz"), kind=kind, p=p, omega=omega, norder=norder,
+                        norie=norie, norif=norif, xnod=xnod, Aii=np.array([o[0] for o in out]), Bi=np.array([o[1] for o in out]),
+                        ASchur=np.array([o[2] for o in out]), BSchur=np.array([o[3] for o in out]))
+    print(kind, p, out[0][0].shape, out[0][2].shape)
