@@ -180,21 +180,26 @@ def main():
 
     # ---- warm-up (also builds the signature tables and allocates the workspaces)
     for _ in range(max(args.warmup, 3)):
-        eng.bench(norder, noe, nof, xnod, reps=1)
+        eng.bench(norder, noe, nof, xnod, reps=1, lanes=2)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
-    r = eng.bench(norder, noe, nof, xnod, reps=args.steps)   # K steps, CUDA events on the launching stream around them
+    # K steps; each step = the B elements as two half-batches on two streams (the way hp3d_gpu_elem_batch runs chunks);
+    # CUDA events on the launching stream bracket the K steps (the second stream is fenced inside that interval)
+    r = eng.bench(norder, noe, nof, xnod, reps=args.steps, lanes=2)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = r["ms_total"]
-    ms_dense, ms_integ = r["ms_dense"], r["ms_integ"]
+    # stage breakdown (integration / dense phase) from a single-stream pass of the same K steps: stage events are only
+    # meaningful when nothing overlaps
+    r1 = eng.bench(norder, noe, nof, xnod, reps=args.steps, lanes=1)
+    ms_dense, ms_integ, ms_single = r1["ms_dense"], r1["ms_integ"], r1["ms_total"]
     if dist is not None:
         import torch
-        t = torch.tensor([ms, ms_dense, ms_integ], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, ms_dense, ms_integ, ms_single], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_dense, ms_integ = [float(v) for v in t.tolist()]
+        ms, ms_dense, ms_integ, ms_single = [float(v) for v in t.tolist()]
     value = world * B * args.steps / (ms * 1e-3)
 
     # ---- end to end through hp3d_gpu_elem_batch with pinned host buffers
@@ -240,6 +245,8 @@ def main():
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / DMMA_PEAK_TFLOPS,
                      "traffic": None, "kernel": "gemm_nc_kernel<complex> (all launches of the dense phase: Cholesky panels, solves, HERK, Schur)",
                      "flops_per_element": F_dense, "ms_dense_per_step": ms_dense / args.steps, "ms_integration_per_step": ms_integ / args.steps,
+                     "ms_per_step_single_stream": ms_single / args.steps,
+                     "timing": "achieved = algorithmic dense flops / CUDA-event time of the dense phase in a single-stream pass of the same K steps; whole_step_frac uses the two-stream step time that `value` reports",
                      "peak_source": "own probe: raw FP64 DMMA loop on this pool's B200 (profiles/r01_dmma_probe.jsonl); MEASURED_PEAKS.json has no FP64 entry",
                      "whole_step_frac": F_dense * B * args.steps / (ms * 1e-3) / 1e12 / DMMA_PEAK_TFLOPS},
     }

@@ -183,7 +183,7 @@ class ElemEngine:
         _lib.check(f(self.plan, _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), _ptr(source_qp), _ptr(W), W.size, _ptr(dims)))
         return W, dict(np=np_, nbp=nbp, nip=nip, n=n, nb=nb, ni=ni, R=R, planes=P)
 
-    def bench(self, norder, norient_edge, norient_face, xnod, reps=1, max_chunk=0):
+    def bench(self, norder, norient_edge, norient_face, xnod, reps=1, max_chunk=0, lanes=2):
         """Device-resident throughput run (hp3d_gpu_bench): returns dict(ms_total, ms_integ, ms_dense, launches)."""
         norder, noe, nof = _i32(norder).reshape(-1, 19), _i32(norient_edge).reshape(-1, 12), _i32(norient_face).reshape(-1, 6)
         xnod = np.ascontiguousarray(xnod, dtype=np.float64)
@@ -191,5 +191,5 @@ class ElemEngine:
         t = [C.c_double() for _ in range(3)]
         ln = C.c_longlong()
         _lib.check(self.L.hp3d_gpu_bench(self.plan, nel, _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(xnod[0].size), int(reps),
-                                         int(max_chunk), C.byref(t[0]), C.byref(t[1]), C.byref(t[2]), C.byref(ln)))
+                                         int(max_chunk), int(lanes), C.byref(t[0]), C.byref(t[1]), C.byref(t[2]), C.byref(ln)))
         return dict(ms_total=t[0].value, ms_integ=t[1].value, ms_dense=t[2].value, launches=ln.value)

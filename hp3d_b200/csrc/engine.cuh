@@ -67,27 +67,38 @@ struct Signature {
   double *d_tab = nullptr, *d_wq = nullptr, *d_CW = nullptr, *d_ones = nullptr;
   int *d_hdof = nullptr, *d_maps = nullptr, *d_crow = nullptr, *d_iota = nullptr;
   FamilyDesc *d_fam = nullptr; TermDesc *d_term = nullptr; SlotDesc *d_slot = nullptr; BlockDesc *d_block = nullptr; WorkItem *d_work = nullptr;
-  DenseWorkspace ws;
-  double *d_WF = nullptr, *d_xnod = nullptr, *d_src = nullptr;         // per-chunk inputs / fields
-  struct OutStage { double *Aii = nullptr, *Bi = nullptr, *AS = nullptr, *BS = nullptr; int *info = nullptr; };
-  OutStage out[2];   // per-chunk outputs (device staging), double-buffered so D2H of chunk k overlaps chunk k+1
-  double *h_xnod = nullptr, *h_src = nullptr;  // pinned host staging of the chunk inputs [2][cap]
-  int cap = 0;
+  // A lane = one complete set of per-chunk buffers.  Two lanes run on two streams so that the latency-bound steps of one
+  // chunk (64x64 tile factorizations, launch tails) overlap the GEMMs of the other, and D2H of a finished chunk
+  // overlaps compute.
+  struct Lane {
+    DenseWorkspace ws;
+    double *d_WF = nullptr, *d_xnod = nullptr, *d_src = nullptr;         // chunk inputs / weight fields
+    struct Out { double *Aii = nullptr, *Bi = nullptr, *AS = nullptr, *BS = nullptr; int *info = nullptr, *h_info = nullptr; };  // h_info: pinned
+    Out out[2];   // chunk outputs (device staging), double-buffered: the D2H of one chunk overlaps the lane's next chunk
+    double *h_xnod = nullptr, *h_src = nullptr;                          // pinned host staging of the chunk inputs
+    void release() {
+      ws.release();
+      cudaFree(d_WF); cudaFree(d_xnod); cudaFree(d_src);
+      for (int i = 0; i < 2; i++) { cudaFree(out[i].Aii); cudaFree(out[i].Bi); cudaFree(out[i].AS); cudaFree(out[i].BS); cudaFree(out[i].info); cudaFreeHost(out[i].h_info); out[i] = Out(); }
+      cudaFreeHost(h_xnod); cudaFreeHost(h_src);
+      d_WF = d_xnod = d_src = nullptr; h_xnod = h_src = nullptr;
+    }
+  };
+  static constexpr int NLANE = 2;
+  Lane lane[NLANE];
+  int cap = 0;   // elements per lane
   ~Signature() {
     cudaFree(d_tab); cudaFree(d_wq); cudaFree(d_CW); cudaFree(d_ones); cudaFree(d_hdof); cudaFree(d_maps); cudaFree(d_crow); cudaFree(d_iota);
     cudaFree(d_fam); cudaFree(d_term); cudaFree(d_slot); cudaFree(d_block); cudaFree(d_work);
     free_chunk();
   }
   void free_chunk() {
-    ws.release();
-    cudaFree(d_WF); cudaFree(d_xnod); cudaFree(d_src);
-    for (int i = 0; i < 2; i++) { cudaFree(out[i].Aii); cudaFree(out[i].Bi); cudaFree(out[i].AS); cudaFree(out[i].BS); cudaFree(out[i].info); out[i] = OutStage(); }
-    cudaFreeHost(h_xnod); cudaFreeHost(h_src);
-    d_WF = d_xnod = d_src = nullptr; h_xnod = h_src = nullptr; cap = 0;
+    for (int i = 0; i < NLANE; i++) lane[i].release();
+    cap = 0;
   }
   int ns() const { return h.cplx ? 2 : 1; }
   size_t src_doubles() const { return (size_t)h.nint * (h.cplx ? 6 : 1); }
-  size_t bytes_per_element() const {
+  size_t bytes_per_element() const {   // device bytes per element of ONE lane
     const size_t NS = ns();
     return DenseWorkspace::bytes_per_element(h.dims) +
            sizeof(double) * ((size_t)NFIELD * h.nint + 3 * (size_t)h.nH + src_doubles() +
@@ -108,20 +119,24 @@ struct Signature {
   int reserve(int batch, std::string &err) {
     if (batch <= cap) return 0;
     free_chunk();
-    if (int rc = ws.reserve(h.dims, batch, err)) return rc;
     const size_t NS = ns();
-    HP3D_CK(cudaMalloc(&d_WF, sizeof(double) * NFIELD * h.nint * batch));
-    HP3D_CK(cudaMalloc(&d_xnod, sizeof(double) * 3 * h.nH * batch));
-    HP3D_CK(cudaMalloc(&d_src, sizeof(double) * src_doubles() * batch));
-    for (int i = 0; i < 2; i++) {
-      HP3D_CK(cudaMalloc(&out[i].Aii, sizeof(double) * NS * (size_t)h.ni * h.ni * batch));
-      HP3D_CK(cudaMalloc(&out[i].Bi, sizeof(double) * NS * h.ni * batch));
-      HP3D_CK(cudaMalloc(&out[i].AS, sizeof(double) * NS * ((size_t)h.nb * h.ni + 1) * batch));
-      HP3D_CK(cudaMalloc(&out[i].BS, sizeof(double) * NS * (h.nb + 1) * batch));
-      HP3D_CK(cudaMalloc(&out[i].info, sizeof(int) * batch));
+    for (int i = 0; i < NLANE; i++) {
+      Lane &L = lane[i];
+      if (int rc = L.ws.reserve(h.dims, batch, err)) return rc;
+      HP3D_CK(cudaMalloc(&L.d_WF, sizeof(double) * NFIELD * h.nint * batch));
+      HP3D_CK(cudaMalloc(&L.d_xnod, sizeof(double) * 3 * h.nH * batch));
+      HP3D_CK(cudaMalloc(&L.d_src, sizeof(double) * src_doubles() * batch));
+      for (int o = 0; o < 2; o++) {
+        HP3D_CK(cudaMalloc(&L.out[o].Aii, sizeof(double) * NS * (size_t)h.ni * h.ni * batch));
+        HP3D_CK(cudaMalloc(&L.out[o].Bi, sizeof(double) * NS * h.ni * batch));
+        HP3D_CK(cudaMalloc(&L.out[o].AS, sizeof(double) * NS * ((size_t)h.nb * h.ni + 1) * batch));
+        HP3D_CK(cudaMalloc(&L.out[o].BS, sizeof(double) * NS * (h.nb + 1) * batch));
+        HP3D_CK(cudaMalloc(&L.out[o].info, sizeof(int) * batch));
+        HP3D_CK(cudaMallocHost(&L.out[o].h_info, sizeof(int) * batch));
+      }
+      HP3D_CK(cudaMallocHost(&L.h_xnod, sizeof(double) * 3 * h.nH * batch));
+      HP3D_CK(cudaMallocHost(&L.h_src, sizeof(double) * src_doubles() * batch));
     }
-    HP3D_CK(cudaMallocHost(&h_xnod, sizeof(double) * 2 * 3 * h.nH * batch));
-    HP3D_CK(cudaMallocHost(&h_src, sizeof(double) * 2 * src_doubles() * batch));
     cap = batch;
     return 0;
   }
@@ -145,28 +160,28 @@ static void launch_tp3(const Signature &S, const Tp3Args &A, int nel, cudaStream
 struct StageEvents { cudaEvent_t e[4]; bool on = false; };  // start, after integration, after dense, after scatter
 
 // Integration of `nel` resident elements (d_xnod/d_src filled) into the dense phase's input buffers.
-static void run_integration(Signature &S, const GeomParams &gp, int nel, const double *d_xnod, const double *d_src, cudaStream_t st) {
+static void run_integration(Signature &S, Signature::Lane &L, const GeomParams &gp, int nel, const double *d_xnod, const double *d_src, cudaStream_t st) {
   const SigHost &h = S.h;
   const DenseDims &d = h.dims;
   const long long P = h.cplx ? 2 : 1;
   SigTables sg;
   sg.tab = S.d_tab; sg.wq = S.d_wq; sg.hdof = S.d_hdof; sg.nH = h.nH; sg.nint = h.nint;
   for (int i = 0; i < 3; i++) sg.nq[i] = h.nq[i];
-  cudaMemsetAsync(S.ws.b.info, 0, sizeof(int) * nel, st);
+  cudaMemsetAsync(L.ws.b.info, 0, sizeof(int) * nel, st);
   const long long npts = (long long)nel * h.nint;
-  geom_fields_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(sg, gp, nel, d_xnod, 3LL * h.nH, d_src, S.d_WF, S.ws.b.info);
+  geom_fields_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(sg, gp, nel, d_xnod, 3LL * h.nH, d_src, L.d_WF, L.ws.b.info);
   g_launches++;
   Tp3Args A;
   A.tab = S.d_tab; A.fam = S.d_fam; A.term = S.d_term; A.slot = S.d_slot; A.block = S.d_block; A.work = S.d_work; A.maps = S.d_maps;
-  A.WF = S.d_WF; A.nint = h.nint;
+  A.WF = L.d_WF; A.nint = h.nint;
   for (int i = 0; i < 3; i++) A.nq[i] = h.nq[i];
-  A.mat[0] = MatTarget{S.ws.b.W, P * (long long)d.w_plane(), (long long)d.w_plane(), d.np};
-  A.mat[1] = MatTarget{S.ws.b.Am, P * (long long)d.a_plane(), (long long)d.a_plane(), d.M()};
+  A.mat[0] = MatTarget{L.ws.b.W, P * (long long)d.w_plane(), (long long)d.w_plane(), d.np};
+  A.mat[1] = MatTarget{L.ws.b.Am, P * (long long)d.a_plane(), (long long)d.a_plane(), d.M()};
   if (d.dpg) {
-    cudaMemsetAsync(S.ws.b.W, 0, sizeof(double) * P * d.w_plane() * nel, st);
+    cudaMemsetAsync(L.ws.b.W, 0, sizeof(double) * P * d.w_plane() * nel, st);
     if (d.np > d.n) { dim3 g((d.np - d.n + 63) / 64, nel); unit_diag_kernel<<<g, 64, 0, st>>>(A.mat[0], d.n, d.np); g_launches++; }
   } else {
-    cudaMemsetAsync(S.ws.b.Am, 0, sizeof(double) * P * d.a_plane() * nel, st);
+    cudaMemsetAsync(L.ws.b.Am, 0, sizeof(double) * P * d.a_plane() * nel, st);
   }
   launch_tp3(S, A, nel, st);
   if (!h.crow.empty()) {
@@ -190,31 +205,31 @@ static long long dense_phase_launches(const DenseDims &d) {  // mirrors the laun
 }
 
 template <bool CPLX>
-static void run_dense_and_scatter(Signature &S, int nel, bool want_schur, const Signature::OutStage &o, cudaStream_t st, StageEvents *ev) {
+static void run_dense_and_scatter(Signature &S, Signature::Lane &L, const Signature::Lane::Out &o, int nel, bool want_schur, cudaStream_t st, StageEvents *ev) {
   const SigHost &h = S.h;
   const DenseDims &d = h.dims;
-  dense_phase<CPLX>(d, S.ws.b, nel, st);
+  dense_phase<CPLX>(d, L.ws.b, nel, st);
   g_launches += dense_phase_launches(d);
   if (ev && ev->on) cudaEventRecord(ev->e[2], st);
   OutMaps mp{S.d_iota, S.d_iota, S.d_ones, S.d_ones, 0, 0, 0, 0};
   dim3 blk(16, 16), g1((h.ni + 15) / 16, (h.ni + 15) / 16, nel);
-  scatter_condensed_kernel<CPLX><<<g1, blk, 0, st>>>(d, S.ws.b.Am, mp, o.Aii, o.Bi, (long long)h.ni * h.ni, (long long)h.ni);
+  scatter_condensed_kernel<CPLX><<<g1, blk, 0, st>>>(d, L.ws.b.Am, mp, o.Aii, o.Bi, (long long)h.ni * h.ni, (long long)h.ni);
   g_launches++;
   if (h.nb > 0 && want_schur) {
     dim3 g2((h.nb + 15) / 16, (h.ni + 15) / 16, nel);
-    scatter_schur_kernel<CPLX><<<g2, blk, 0, st>>>(d, S.ws.b.Am, mp, o.AS, o.BS, (long long)h.nb * h.ni, (long long)h.nb);
+    scatter_schur_kernel<CPLX><<<g2, blk, 0, st>>>(d, L.ws.b.Am, mp, o.AS, o.BS, (long long)h.nb * h.ni, (long long)h.nb);
     g_launches++;
   }
-  cudaMemcpyAsync(o.info, S.ws.b.info, sizeof(int) * nel, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(o.info, L.ws.b.info, sizeof(int) * nel, cudaMemcpyDeviceToDevice, st);
 }
 
-static void run_chunk(Signature &S, const GeomParams &gp, int nel, const double *d_xnod, const double *d_src, bool want_schur, int obuf,
+static void run_chunk(Signature &S, Signature::Lane &L, int ob, const GeomParams &gp, int nel, const double *d_xnod, const double *d_src, bool want_schur,
                       cudaStream_t st, StageEvents *ev = nullptr) {
   if (ev && ev->on) cudaEventRecord(ev->e[0], st);
-  run_integration(S, gp, nel, d_xnod, d_src, st);
+  run_integration(S, L, gp, nel, d_xnod, d_src, st);
   if (ev && ev->on) cudaEventRecord(ev->e[1], st);
-  if (S.h.cplx) run_dense_and_scatter<true>(S, nel, want_schur, S.out[obuf], st, ev);
-  else run_dense_and_scatter<false>(S, nel, want_schur, S.out[obuf], st, ev);
+  if (S.h.cplx) run_dense_and_scatter<true>(S, L, L.out[ob], nel, want_schur, st, ev);
+  else run_dense_and_scatter<false>(S, L, L.out[ob], nel, want_schur, st, ev);
   if (ev && ev->on) cudaEventRecord(ev->e[3], st);
 }
 

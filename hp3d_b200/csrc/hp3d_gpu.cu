@@ -3,6 +3,8 @@
 #include "engine.cuh"
 
 #include <cstdarg>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -15,7 +17,8 @@ std::mutex g_mu;
 std::string g_err;
 int g_device = -1;
 std::vector<Plan *> g_plans;
-cudaStream_t g_compute = nullptr, g_copy = nullptr;
+cudaStream_t g_lane_stream[2] = {nullptr, nullptr}, g_copy = nullptr;
+#define g_compute g_lane_stream[0]
 int g_max_chunk = 0;
 
 int fail(int code, const char *fmt, ...) {
@@ -39,10 +42,10 @@ Plan *plan_of(int id) { return (id >= 0 && id < (int)g_plans.size()) ? g_plans[i
 int chunk_capacity(const Signature &S, int want) {
   size_t fre = 0, tot = 0;
   cudaMemGetInfo(&fre, &tot);
-  // memory already held by this signature's chunk buffers is reusable
-  size_t have = (size_t)S.cap * S.bytes_per_element();
+  // memory already held by this signature's chunk buffers is reusable; two lanes share the budget
+  size_t have = (size_t)Signature::NLANE * S.cap * S.bytes_per_element();
   double budget = 0.80 * (double)(fre + have);
-  long long cap = (long long)(budget / (double)S.bytes_per_element());
+  long long cap = (long long)(budget / (double)(Signature::NLANE * S.bytes_per_element()));
   if (cap > 1024) cap = 1024;
   if (cap > want) cap = want;
   return (int)cap;
@@ -97,7 +100,8 @@ int hp3d_gpu_init(int device) {
   CUDA_TRY(dense_configure<true>());
   CUDA_TRY(dense_configure<false>());
   CUDA_TRY(tp3_configure<4>()); CUDA_TRY(tp3_configure<6>()); CUDA_TRY(tp3_configure<8>()); CUDA_TRY(tp3_configure<10>());
-  if (!g_compute) CUDA_TRY(cudaStreamCreateWithFlags(&g_compute, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++)
+    if (!g_lane_stream[i]) CUDA_TRY(cudaStreamCreateWithFlags(&g_lane_stream[i], cudaStreamNonBlocking));
   if (!g_copy) CUDA_TRY(cudaStreamCreateWithFlags(&g_copy, cudaStreamNonBlocking));
   g_device = device;
   return HP3D_OK;
@@ -107,7 +111,8 @@ int hp3d_gpu_finalize(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   for (Plan *p : g_plans) delete p;
   g_plans.clear();
-  if (g_compute) { cudaStreamDestroy(g_compute); g_compute = nullptr; }
+  for (int i = 0; i < 2; i++)
+    if (g_lane_stream[i]) { cudaStreamDestroy(g_lane_stream[i]); g_lane_stream[i] = nullptr; }
   if (g_copy) { cudaStreamDestroy(g_copy); g_copy = nullptr; }
   g_device = -1;
   return HP3D_OK;
@@ -227,14 +232,14 @@ int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, 
   }
   const GeomParams gp = p->geom();
   std::string err;
-  cudaEvent_t evCompute[2], evCopy[2], evH2D[2];
-  for (int i = 0; i < 2; i++) {
+  // slot = (lane, output buffer): chunk k runs on lane k&1 and writes output buffer (k>>1)&1 of that lane
+  cudaEvent_t evCompute[4], evCopy[4], evH2D[2];
+  for (int i = 0; i < 4; i++) {
     CUDA_TRY(cudaEventCreateWithFlags(&evCompute[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&evCopy[i], cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&evH2D[i], cudaEventDisableTiming));
   }
+  for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&evH2D[i], cudaEventDisableTiming));
   int rc = HP3D_OK;
-  std::vector<int> hinfo;
   for (auto &g : groups) {
     const std::vector<int> &el = g.second;
     const int e0 = el[0];
@@ -243,7 +248,7 @@ int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, 
     if (xnod_ld < 3 * S->h.nH) { rc = fail(HP3D_EINVAL, "xnod_ld=%d < 3*nrdofH=%d", xnod_ld, 3 * S->h.nH); break; }
     int want = (int)el.size();
     if (g_max_chunk > 0) want = std::min(want, g_max_chunk);
-    else if (want >= 128) want = std::max(32, (want + 3) / 4);   // >= 4 chunks: D2H of chunk k overlaps chunk k+1
+    else if (want >= 64) want = std::max(16, (want + 7) / 8);   // >= 8 chunks: copies of finished chunks overlap compute
     const int cap = chunk_capacity(*S, want);
     if (cap < 1) { rc = fail(HP3D_ENOMEM, "not enough device memory for one element (%zu bytes)", S->bytes_per_element()); break; }
     if (S->reserve(cap, err)) { rc = fail(HP3D_ENOMEM, "%s", err.c_str()); break; }
@@ -251,29 +256,40 @@ int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, 
     const size_t NS = S->ns(), es = sizeof(double) * NS;
     const size_t nx = 3 * (size_t)h.nH, nsrc = S->src_doubles();
     const size_t bA = (size_t)h.ni * h.ni, bB = h.ni, bAS = (size_t)h.nb * h.ni, bBS = h.nb;
-    hinfo.resize(2 * (size_t)S->cap);
-    int nchunk = 0;
     const int chunk = cap;
+    int nchunk = 0;
+    auto collect_info = [&](int k) {   // host side of chunk k: wait for its D2H, publish info[]
+      const int slot = (k & 1) * 2 + ((k >> 1) & 1);
+      cudaEventSynchronize(evCopy[slot]);
+      const size_t pc0 = (size_t)k * chunk;
+      const int pn = (int)std::min(el.size() - pc0, (size_t)chunk);
+      const int *hi = S->lane[k & 1].out[(k >> 1) & 1].h_info;
+      for (int i = 0; i < pn; i++) { const int e = el[pc0 + i]; if (info) info[e] = hi[i]; }
+    };
     for (size_t c0 = 0; c0 < el.size(); c0 += chunk, nchunk++) {
-      const int n = (int)std::min(el.size() - c0, (size_t)chunk), buf = nchunk & 1;
-      // the pinned input staging of this buffer must have been consumed by the H2D of chunk nchunk-2
-      if (nchunk >= 2) cudaEventSynchronize(evH2D[buf]);
-      double *hx = S->h_xnod + (size_t)buf * nx * S->cap, *hs = S->h_src + (size_t)buf * nsrc * S->cap;
+      const int n = (int)std::min(el.size() - c0, (size_t)chunk), ln = nchunk & 1, ob = (nchunk >> 1) & 1, slot = ln * 2 + ob;
+      Signature::Lane &L = S->lane[ln];
+      cudaStream_t st = g_lane_stream[ln];
+      const bool trace = getenv("HP3D_TRACE") != nullptr;
+      auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+      const double tA = now();
+      if (nchunk >= 4) collect_info(nchunk - 4);              // this slot's previous results are on the host
+      const double tB = now();
+      if (nchunk >= 2) cudaEventSynchronize(evH2D[ln]);        // the lane's pinned input staging has been consumed
+      const double tC = now();
       for (int i = 0; i < n; i++) {
         const int e = el[c0 + i];
-        memcpy(hx + (size_t)i * nx, xnod + (size_t)e * xnod_ld, sizeof(double) * nx);
-        if (gp.source == HP3D_SRC_TABLE) memcpy(hs + (size_t)i * nsrc, (const double *)source_qp + (size_t)e * source_ld, sizeof(double) * nsrc);
+        memcpy(L.h_xnod + (size_t)i * nx, xnod + (size_t)e * xnod_ld, sizeof(double) * nx);
+        if (gp.source == HP3D_SRC_TABLE) memcpy(L.h_src + (size_t)i * nsrc, (const double *)source_qp + (size_t)e * source_ld, sizeof(double) * nsrc);
       }
-      // the device inputs are single-buffered: stream order on g_compute protects them
-      cudaMemcpyAsync(S->d_xnod, hx, sizeof(double) * nx * n, cudaMemcpyHostToDevice, g_compute);
-      if (gp.source == HP3D_SRC_TABLE) cudaMemcpyAsync(S->d_src, hs, sizeof(double) * nsrc * n, cudaMemcpyHostToDevice, g_compute);
-      cudaEventRecord(evH2D[buf], g_compute);
-      if (nchunk >= 2) cudaStreamWaitEvent(g_compute, evCopy[buf], 0);  // output stage `buf` drained by the copy stream
-      run_chunk(*S, gp, n, S->d_xnod, S->d_src, want_schur, buf, g_compute);
-      cudaEventRecord(evCompute[buf], g_compute);
-      cudaStreamWaitEvent(g_copy, evCompute[buf], 0);
+      cudaMemcpyAsync(L.d_xnod, L.h_xnod, sizeof(double) * nx * n, cudaMemcpyHostToDevice, st);
+      if (gp.source == HP3D_SRC_TABLE) cudaMemcpyAsync(L.d_src, L.h_src, sizeof(double) * nsrc * n, cudaMemcpyHostToDevice, st);
+      cudaEventRecord(evH2D[ln], st);
+      run_chunk(*S, L, ob, gp, n, L.d_xnod, L.d_src, want_schur, st);
+      cudaEventRecord(evCompute[slot], st);
+      cudaStreamWaitEvent(g_copy, evCompute[slot], 0);
       // D2H straight into the caller's arrays; runs of consecutive elements with dense strides are merged
-      const Signature::OutStage &o = S->out[buf];
+      const Signature::Lane::Out &o = L.out[ob];
       for (int i = 0; i < n;) {
         int j = i + 1;
         while (j < n && el[c0 + j] == el[c0 + j - 1] + 1) j++;
@@ -290,31 +306,20 @@ int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, 
         if (want_schur) { copy(ASchur, sAS, o.AS, bAS); copy(BSchur, sBS, o.BS, bBS); }
         i = j;
       }
-      cudaMemcpyAsync(hinfo.data() + (size_t)buf * S->cap, o.info, sizeof(int) * n, cudaMemcpyDeviceToHost, g_copy);
-      cudaEventRecord(evCopy[buf], g_copy);
-      // info needs the host: it is tiny, so wait for the previous chunk's copy here (keeps one chunk in flight)
-      if (nchunk >= 1) {
-        const int pb = buf ^ 1;
-        cudaEventSynchronize(evCopy[pb]);
-        const size_t pc0 = c0 - chunk;
-        const int pn = chunk;
-        for (int i = 0; i < pn; i++) { const int e = el[pc0 + i]; if (info) info[e] = hinfo[(size_t)pb * S->cap + i]; }
-      }
+      cudaMemcpyAsync(o.h_info, o.info, sizeof(int) * n, cudaMemcpyDeviceToHost, g_copy);   // pinned: stays asynchronous
+      cudaEventRecord(evCopy[slot], g_copy);
+      if (trace) fprintf(stderr, "[hp3d trace] chunk %d lane %d: t=%.1f wait_copy %.1f wait_h2d %.1f enqueue %.1f ms\n", nchunk, ln, tA, tB - tA, tC - tB, now() - tC);
     }
-    {  // drain the last chunk
-      const int lb = (nchunk - 1) & 1;
-      cudaEventSynchronize(evCopy[lb]);
-      const size_t pc0 = (size_t)(nchunk - 1) * chunk;
-      const int pn = (int)(el.size() - pc0);
-      for (int i = 0; i < pn; i++) { const int e = el[pc0 + i]; if (info) info[e] = hinfo[(size_t)lb * S->cap + i]; }
-    }
+    for (int k = std::max(0, nchunk - 4); k < nchunk; k++) collect_info(k);
     for (int e : el) { if (ni_out) ni_out[e] = h.ni; if (nb_out) nb_out[e] = h.nb; }
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) { rc = fail(HP3D_ENODEV, "CUDA error in elem_batch: %s", cudaGetErrorString(ce)); break; }
   }
-  cudaStreamSynchronize(g_compute);
+  cudaStreamSynchronize(g_lane_stream[0]);
+  cudaStreamSynchronize(g_lane_stream[1]);
   cudaStreamSynchronize(g_copy);
-  for (int i = 0; i < 2; i++) { cudaEventDestroy(evCompute[i]); cudaEventDestroy(evCopy[i]); cudaEventDestroy(evH2D[i]); }
+  for (int i = 0; i < 4; i++) { cudaEventDestroy(evCompute[i]); cudaEventDestroy(evCopy[i]); }
+  for (int i = 0; i < 2; i++) cudaEventDestroy(evH2D[i]);
   if (rc == HP3D_OK) {
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) rc = fail(HP3D_ENODEV, "CUDA error in elem_batch: %s", cudaGetErrorString(ce));
@@ -338,13 +343,14 @@ int hp3d_gpu_quad_points(int plan, int nel, const int *etype, const int *norder,
     if (!S) return fail(HP3D_EINVAL, "element %d: %s", e, err.c_str());
     if (S->cap < 1 && S->reserve(1, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());
     const SigHost &h = S->h;
-    CUDA_TRY(cudaMemcpyAsync(S->d_xnod, xnod + (size_t)e * xnod_ld, sizeof(double) * 3 * h.nH, cudaMemcpyHostToDevice, g_compute));
+    Signature::Lane &L = S->lane[0];
+    CUDA_TRY(cudaMemcpyAsync(L.d_xnod, xnod + (size_t)e * xnod_ld, sizeof(double) * 3 * h.nH, cudaMemcpyHostToDevice, g_compute));
     SigTables sg;
     sg.tab = S->d_tab; sg.wq = S->d_wq; sg.hdof = S->d_hdof; sg.nH = h.nH; sg.nint = h.nint;
     for (int i = 0; i < 3; i++) sg.nq[i] = h.nq[i];
-    geom_fields_kernel<<<(h.nint + 127) / 128, 128, 0, g_compute>>>(sg, gp, 1, S->d_xnod, 3LL * h.nH, nullptr, S->d_WF, S->ws.b.info);
+    geom_fields_kernel<<<(h.nint + 127) / 128, 128, 0, g_compute>>>(sg, gp, 1, L.d_xnod, 3LL * h.nH, nullptr, L.d_WF, L.ws.b.info);
     f.resize(3 * (size_t)h.nint);
-    CUDA_TRY(cudaMemcpyAsync(f.data(), S->d_WF + (size_t)F_X * h.nint, sizeof(double) * 3 * h.nint, cudaMemcpyDeviceToHost, g_compute));
+    CUDA_TRY(cudaMemcpyAsync(f.data(), L.d_WF + (size_t)F_X * h.nint, sizeof(double) * 3 * h.nint, cudaMemcpyDeviceToHost, g_compute));
     CUDA_TRY(cudaStreamSynchronize(g_compute));
     for (int q = 0; q < h.nint; q++)
       for (int c = 0; c < 3; c++) xq[(size_t)e * sxq + 3 * q + c] = f[(size_t)c * h.nint + q];
@@ -375,12 +381,12 @@ int hp3d_gpu_stc_bwd_batch(int cplx, int nel, int ni, int nb, const void *ASchur
 }
 
 int hp3d_gpu_bench(int plan, int nel, const int *norder, const int *norie, const int *norif, const double *xnod, int xnod_ld, int reps,
-                   int max_chunk, double *ms_total, double *ms_integ, double *ms_dense, long long *launches) {
+                   int max_chunk, int lanes, double *ms_total, double *ms_integ, double *ms_dense, long long *launches) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
   Plan *p = plan_of(plan);
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
-  if (nel <= 0 || reps <= 0) return fail(HP3D_EINVAL, "bad sizes");
+  if (nel <= 0 || reps <= 0 || lanes < 1 || lanes > 2) return fail(HP3D_EINVAL, "bad sizes");
   if (p->fp.source == HP3D_SRC_TABLE) return fail(HP3D_EINVAL, "bench: table sources are not supported");
   std::map<std::string, std::vector<int>> groups;
   for (int e = 0; e < nel; e++) groups[Plan::key(norder + 19 * e, norie + 12 * e, norif + 6 * e)].push_back(e);
@@ -393,6 +399,7 @@ int hp3d_gpu_bench(int plan, int nel, const int *norder, const int *norie, const
     Signature *S = p->get(norder + 19 * e0, norie + 12 * e0, norif + 6 * e0, true, err);
     if (!S) return fail(HP3D_EINVAL, "%s", err.c_str());
     int want = (int)g.second.size();
+    if (lanes == 2) want = (want + 1) / 2;
     if (max_chunk > 0 && want > max_chunk) want = max_chunk;
     const int cap = chunk_capacity(*S, want);
     if (cap < 1) return fail(HP3D_ENOMEM, "not enough device memory");
@@ -406,23 +413,28 @@ int hp3d_gpu_bench(int plan, int nel, const int *norder, const int *norie, const
     gs.push_back(Grp{S, dx, (int)g.second.size(), cap});
   }
   std::vector<StageEvents> evs;
-  cudaEvent_t t0, t1;
-  CUDA_TRY(cudaEventCreate(&t0)); CUDA_TRY(cudaEventCreate(&t1));
+  cudaEvent_t t0, t1, tj;
+  CUDA_TRY(cudaEventCreate(&t0)); CUDA_TRY(cudaEventCreate(&t1)); CUDA_TRY(cudaEventCreateWithFlags(&tj, cudaEventDisableTiming));
   const long long l0 = g_launches;
-  CUDA_TRY(cudaStreamSynchronize(g_compute));
-  CUDA_TRY(cudaEventRecord(t0, g_compute));
+  CUDA_TRY(cudaStreamSynchronize(g_lane_stream[0]));
+  CUDA_TRY(cudaStreamSynchronize(g_lane_stream[1]));
+  CUDA_TRY(cudaEventRecord(t0, g_lane_stream[0]));
+  if (lanes == 2) CUDA_TRY(cudaStreamWaitEvent(g_lane_stream[1], t0, 0));   // lane 1 starts inside the timed region
+  int k = 0;
   for (int r = 0; r < reps; r++)
     for (Grp &g : gs)
-      for (int c0 = 0, k = 0; c0 < g.n; c0 += g.chunk, k++) {
-        const int n = std::min(g.n - c0, g.chunk);
+      for (int c0 = 0; c0 < g.n; c0 += g.chunk, k++) {
+        const int n = std::min(g.n - c0, g.chunk), ln = lanes == 2 ? (k & 1) : 0;
         StageEvents ev;
-        ev.on = true;
-        for (int i = 0; i < 4; i++) cudaEventCreate(&ev.e[i]);
-        run_chunk(*g.S, gp, n, g.dx + (size_t)c0 * 3 * g.S->h.nH, nullptr, p->store_schur != 0, k & 1, g_compute, &ev);
-        evs.push_back(ev);
+        ev.on = (lanes == 1);
+        if (ev.on) for (int i = 0; i < 4; i++) cudaEventCreate(&ev.e[i]);
+        run_chunk(*g.S, g.S->lane[ln], 0, gp, n, g.dx + (size_t)c0 * 3 * g.S->h.nH, nullptr, p->store_schur != 0, g_lane_stream[ln], &ev);
+        if (ev.on) evs.push_back(ev);
       }
-  CUDA_TRY(cudaEventRecord(t1, g_compute));
-  CUDA_TRY(cudaStreamSynchronize(g_compute));
+  if (lanes == 2) { CUDA_TRY(cudaEventRecord(tj, g_lane_stream[1])); CUDA_TRY(cudaStreamWaitEvent(g_lane_stream[0], tj, 0)); }
+  CUDA_TRY(cudaEventRecord(t1, g_lane_stream[0]));
+  CUDA_TRY(cudaStreamSynchronize(g_lane_stream[0]));
+  CUDA_TRY(cudaStreamSynchronize(g_lane_stream[1]));
   CUDA_TRY(cudaGetLastError());
   float ms = 0;
   cudaEventElapsedTime(&ms, t0, t1);
@@ -438,7 +450,7 @@ int hp3d_gpu_bench(int plan, int nel, const int *norder, const int *norie, const
   if (ms_integ) *ms_integ = mi;
   if (ms_dense) *ms_dense = md;
   if (launches) *launches = g_launches - l0;
-  cudaEventDestroy(t0); cudaEventDestroy(t1);
+  cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(tj);
   for (Grp &g : gs) cudaFree(g.dx);
   return HP3D_OK;
 }
@@ -460,13 +472,14 @@ int hp3d_gpu_integrate_debug(int plan, const int *norder, const int *norie, cons
   if (dims) { dims[0] = d.np; dims[1] = d.nbp; dims[2] = d.nip; dims[3] = d.n; dims[4] = d.nb; dims[5] = d.ni; dims[6] = d.dpg ? d.R() : d.M(); dims[7] = (int)P; }
   if (!W) return HP3D_OK;
   if ((size_t)cap_doubles < need) return fail(HP3D_EINVAL, "integrate_debug: need %zu doubles", need);
-  CUDA_TRY(cudaMemcpyAsync(S->d_xnod, xnod, sizeof(double) * 3 * h.nH, cudaMemcpyHostToDevice, g_compute));
+  Signature::Lane &L = S->lane[0];
+  CUDA_TRY(cudaMemcpyAsync(L.d_xnod, xnod, sizeof(double) * 3 * h.nH, cudaMemcpyHostToDevice, g_compute));
   if (p->fp.source == HP3D_SRC_TABLE) {
     if (!source_qp) return fail(HP3D_EINVAL, "source table missing");
-    CUDA_TRY(cudaMemcpyAsync(S->d_src, source_qp, sizeof(double) * S->src_doubles(), cudaMemcpyHostToDevice, g_compute));
+    CUDA_TRY(cudaMemcpyAsync(L.d_src, source_qp, sizeof(double) * S->src_doubles(), cudaMemcpyHostToDevice, g_compute));
   }
-  run_integration(*S, p->geom(), 1, S->d_xnod, S->d_src, g_compute);
-  CUDA_TRY(cudaMemcpyAsync(W, d.dpg ? S->ws.b.W : S->ws.b.Am, sizeof(double) * need, cudaMemcpyDeviceToHost, g_compute));
+  run_integration(*S, L, p->geom(), 1, L.d_xnod, L.d_src, g_compute);
+  CUDA_TRY(cudaMemcpyAsync(W, d.dpg ? L.ws.b.W : L.ws.b.Am, sizeof(double) * need, cudaMemcpyDeviceToHost, g_compute));
   CUDA_TRY(cudaStreamSynchronize(g_compute));
   CUDA_TRY(cudaGetLastError());
   return HP3D_OK;

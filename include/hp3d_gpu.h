@@ -110,12 +110,14 @@ int hp3d_gpu_stc_bwd_batch(int complex_mode, int nel, int ni, int nb, const void
 
 /* Throughput driver used by bench.py: runs the hot path `reps` times over `nel` RESIDENT elements (geometry dofs
  * already in HBM, condensed outputs left in HBM), timed with CUDA events on the launching stream.
+ *   lanes      1: chunks run back to back on one stream (stage times ms_integ / ms_dense are then meaningful);
+ *              2: chunks alternate between two buffer sets on two streams, as hp3d_gpu_elem_batch runs them
  *   ms_total   device time of all reps;  ms_integ / ms_dense: the part spent in integration / in the dense phase
  *   launches   kernels launched inside the timed region
  * (The end-to-end number with host buffers is measured by calling hp3d_gpu_elem_batch itself.) */
 int hp3d_gpu_bench(int plan, int nel, const int *norder, const int *norient_edge, const int *norient_face,
-                   const double *xnod, int xnod_ld, int reps, int max_chunk, double *ms_total, double *ms_integ,
-                   double *ms_dense, long long *launches);
+                   const double *xnod, int xnod_ld, int reps, int max_chunk, int lanes, double *ms_total,
+                   double *ms_integ, double *ms_dense, long long *launches);
 
 /* Page-locked host memory for the caller's result arrays (so that the D2H copies of hp3d_gpu_elem_batch are
  * asynchronous DMA transfers that overlap the next chunk's kernels).  Pageable buffers work too, only slower. */
