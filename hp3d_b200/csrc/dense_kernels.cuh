@@ -248,3 +248,136 @@ __global__ void pad_diag_kernel(double *A, long long batch_stride, int ld, int n
 }
 
 }  // namespace hp3d
+
+namespace hp3d {
+
+// ---------------------------------------------------------------------------------------------------
+// stc_gen_kernel: static condensation with a PIVOTED LU of the bubble block, for element matrices that are not
+// Hermitian positive definite (complex-symmetric Maxwell Galerkin: HERM_STC = .false.).  Mirrors
+// stc_fwd_gen (src/modules/stc.F90:443-507: ?GETRF, 2 x ?GETRS, 2 x ?GEMM) as one Gaussian elimination of the full
+// element matrix [A_bb A_bi b_b ; A_ib A_ii b_i] with partial pivoting restricted to the bubble rows: after nb steps the
+// interface rows hold the Schur complement and the condensed load, and a back substitution on the bubble rows gives
+// ASchur = A_bb^-1 A_bi, BSchur = A_bb^-1 b_b.  One CTA per element, matrix in global memory (L2-resident), planar.
+// Layout of Am: [M][M] row-major, bubbles at rows/cols [0,nb), interface at [nbp, nbp+ni), load COLUMN nbp+ni.
+// Outputs are written directly in the caller's layout (column-major, interleaved complex).
+template <bool CPLX>
+__global__ void __launch_bounds__(512) stc_gen_kernel(int nb, int nbp, int ni, int M, double *Am, long long a_plane, long long a_batch,
+                                                      double *Aii, double *Bi, double *AS, double *BS, long long sA, long long sB,
+                                                      long long sAS, long long sBS, int want_schur, int *info) {
+  constexpr int NS = CPLX ? 2 : 1;
+  extern __shared__ __align__(16) double sh[];   // pivot row: [2][M]
+  __shared__ double red_v[16];
+  __shared__ int red_i[16];
+  __shared__ int s_piv;
+  __shared__ double s_pr, s_pi;
+  const int e = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  double *Ar = Am + (long long)e * a_batch, *Ai = Ar + a_plane;
+  const int ncol = nbp + ni + 1;          // columns in use (load column last)
+  double *pr = sh, *pi = sh + M;
+  int bad = 0;
+  for (int k = 0; k < nb; k++) {
+    // ---- pivot search over bubble rows k..nb-1 of column k
+    double best = -1.0; int bi = k;
+    for (int i = k + tid; i < nb; i += nt) {
+      double vr = Ar[(long long)i * M + k], vi = CPLX ? Ai[(long long)i * M + k] : 0.0;
+      double v = vr * vr + vi * vi;
+      if (v > best) { best = v; bi = i; }
+    }
+    for (int o = 16; o; o >>= 1) {
+      double ov = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { red_v[warp] = best; red_i[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      double b = red_v[0]; int p = red_i[0];
+      for (int w = 1; w < nw; w++) if (red_v[w] > b || (red_v[w] == b && red_i[w] < p)) { b = red_v[w]; p = red_i[w]; }
+      s_piv = p;
+      if (!(b > 0.0)) { if (!bad) bad = k + 1; }
+    }
+    __syncthreads();
+    const int p = s_piv;
+    // ---- swap rows k <-> p (columns >= k), keep the pivot row in shared memory
+    for (int j = k + tid; j < ncol; j += nt) {
+      if (j >= nb && j < nbp) continue;
+      double ar = Ar[(long long)p * M + j], ai = CPLX ? Ai[(long long)p * M + j] : 0.0;
+      if (p != k) {
+        Ar[(long long)p * M + j] = Ar[(long long)k * M + j];
+        Ar[(long long)k * M + j] = ar;
+        if (CPLX) { Ai[(long long)p * M + j] = Ai[(long long)k * M + j]; Ai[(long long)k * M + j] = ai; }
+      }
+      pr[j] = ar; if (CPLX) pi[j] = ai;
+    }
+    __syncthreads();
+    // 1 / pivot
+    double dr = pr[k], di = CPLX ? pi[k] : 0.0, dn = dr * dr + di * di;
+    if (!(dn > 0.0)) { dr = 1.0; di = 0.0; dn = 1.0; }
+    const double ir = dr / dn, ii = -di / dn;
+    // ---- eliminate column k from every row below (bubble rows k+1..nb-1 and interface rows nbp..nbp+ni-1)
+    const int nrows = (nb - k - 1) + ni;
+    for (int r = warp; r < nrows; r += nw) {
+      const int i = (r < nb - k - 1) ? k + 1 + r : nbp + (r - (nb - k - 1));
+      double *rr = Ar + (long long)i * M, *ri = Ai + (long long)i * M;
+      const double ar = rr[k], ai = CPLX ? ri[k] : 0.0;
+      const double lr = ar * ir - ai * ii, li = ar * ii + ai * ir;   // l = a(i,k) / pivot
+      if (lr == 0.0 && li == 0.0) continue;
+      for (int j = k + 1 + lane; j < ncol; j += 32) {
+        if (j >= nb && j < nbp) continue;
+        if (CPLX) {
+          rr[j] -= lr * pr[j] - li * pi[j];
+          ri[j] -= lr * pi[j] + li * pr[j];
+        } else rr[j] -= lr * pr[j];
+      }
+    }
+    __syncthreads();
+  }
+  // ---- condensed system straight from the interface rows
+  double *oA = Aii + (long long)e * sA * NS, *oB = Bi + (long long)e * sB * NS;
+  for (int idx = tid; idx < ni * ni; idx += nt) {
+    const int r = idx % ni, c = idx / ni;   // column-major output
+    oA[(long long)idx * NS] = Ar[(long long)(nbp + r) * M + nbp + c];
+    if (CPLX) oA[(long long)idx * NS + 1] = Ai[(long long)(nbp + r) * M + nbp + c];
+  }
+  for (int r = tid; r < ni; r += nt) {
+    oB[(long long)r * NS] = Ar[(long long)(nbp + r) * M + nbp + ni];
+    if (CPLX) oB[(long long)r * NS + 1] = Ai[(long long)(nbp + r) * M + nbp + ni];
+  }
+  if (tid == 0 && bad && info[e] == 0) info[e] = bad;
+  if (!want_schur || nb == 0) return;
+  // ---- back substitution on the bubble rows: X = U_bb^-1 [U_bi | y_b], in place in columns [nbp, ncol)
+  for (int k = nb - 1; k >= 0; k--) {
+    __syncthreads();
+    double dr = Ar[(long long)k * M + k], di = CPLX ? Ai[(long long)k * M + k] : 0.0, dn = dr * dr + di * di;
+    if (!(dn > 0.0)) { dr = 1.0; di = 0.0; dn = 1.0; }
+    const double ir = dr / dn, ii = -di / dn;
+    for (int j = nbp + tid; j < ncol; j += nt) {
+      const double ar = Ar[(long long)k * M + j], ai = CPLX ? Ai[(long long)k * M + j] : 0.0;
+      const double xr = ar * ir - ai * ii, xi = ar * ii + ai * ir;
+      Ar[(long long)k * M + j] = xr; pr[j] = xr;
+      if (CPLX) { Ai[(long long)k * M + j] = xi; pi[j] = xi; }
+    }
+    __syncthreads();
+    for (int i = warp; i < k; i += nw) {
+      double *rr = Ar + (long long)i * M, *ri = Ai + (long long)i * M;
+      const double ur = rr[k], ui = CPLX ? ri[k] : 0.0;
+      if (ur == 0.0 && ui == 0.0) continue;
+      for (int j = nbp + lane; j < ncol; j += 32) {
+        if (CPLX) { rr[j] -= ur * pr[j] - ui * pi[j]; ri[j] -= ur * pi[j] + ui * pr[j]; }
+        else rr[j] -= ur * pr[j];
+      }
+    }
+  }
+  __syncthreads();
+  double *oS = AS + (long long)e * sAS * NS, *oT = BS + (long long)e * sBS * NS;
+  for (int idx = tid; idx < nb * ni; idx += nt) {
+    const int b = idx % nb, c = idx / nb;
+    oS[(long long)idx * NS] = Ar[(long long)b * M + nbp + c];
+    if (CPLX) oS[(long long)idx * NS + 1] = Ai[(long long)b * M + nbp + c];
+  }
+  for (int b = tid; b < nb; b += nt) {
+    oT[(long long)b * NS] = Ar[(long long)b * M + nbp + ni];
+    if (CPLX) oT[(long long)b * NS + 1] = Ai[(long long)b * M + nbp + ni];
+  }
+}
+
+}  // namespace hp3d

@@ -208,6 +208,16 @@ template <bool CPLX>
 static void run_dense_and_scatter(Signature &S, Signature::Lane &L, const Signature::Lane::Out &o, int nel, bool want_schur, cudaStream_t st, StageEvents *ev) {
   const SigHost &h = S.h;
   const DenseDims &d = h.dims;
+  if (h.gen_stc) {   // pivoted-LU condensation: one kernel, writes the caller-layout outputs itself
+    const long long P = CPLX ? 2 : 1;
+    stc_gen_kernel<CPLX><<<nel, 512, sizeof(double) * 2 * d.M(), st>>>(d.nb, d.nbp, d.ni, d.M(), L.ws.b.Am, (long long)d.a_plane(), P * (long long)d.a_plane(),
+                                                                       o.Aii, o.Bi, o.AS, o.BS, (long long)h.ni * h.ni, (long long)h.ni,
+                                                                       (long long)h.nb * h.ni, (long long)h.nb, want_schur ? 1 : 0, L.ws.b.info);
+    g_launches++;
+    if (ev && ev->on) cudaEventRecord(ev->e[2], st);
+    cudaMemcpyAsync(o.info, L.ws.b.info, sizeof(int) * nel, cudaMemcpyDeviceToDevice, st);
+    return;
+  }
   dense_phase<CPLX>(d, L.ws.b, nel, st);
   g_launches += dense_phase_launches(d);
   if (ev && ev->on) cudaEventRecord(ev->e[2], st);

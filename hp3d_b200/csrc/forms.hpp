@@ -45,6 +45,7 @@ struct SigHost {
   int nH = 0;                 // geometry dofs
   int ni = 0, nb = 0, ntest = 0;
   bool cplx = false, dpg = false;
+  bool gen_stc = false;        // condensation by pivoted LU (stc_fwd_gen) instead of Cholesky
   DenseDims dims;
   std::vector<double> tab, wq;
   std::vector<int> hdof;
@@ -392,6 +393,39 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
     {
       BlockBuilder b(S, unit, fu, channel(1, 0, D.nbp + S.ni, 0, -1, mapU), no_channel());
       b.add(-1, -1, F_SRC, 1.0, 1.0, 0.0);
+      b.finish();
+    }
+  } else if (P.kind == 3) {
+    // =============================================================== Maxwell Galerkin (complex symmetric, bilinear)
+    // A = (1/mu curl E, curl F) - ((w^2 eps - i w sigma) E, F),  b = -i w (J, F): no conjugation (ZSYRK in the reference),
+    // bubble block indefinite -> pivoted-LU condensation (HERM_STC = .false.)
+    const std::vector<TensorDof> ed = hexa_dofs_Hcurl(norder, norie, norif);
+    const int nE = (int)ed.size(), iE = nE - bE;
+    S.cplx = true; S.dpg = false; S.gen_stc = true; S.ntest = 0; S.ni = iE; S.nb = bE;
+    DenseDims &D = S.dims;
+    D.cplx = true; D.dpg = false; D.n = 0; D.nb = S.nb; D.ni = S.ni; D.finish();
+    int fe[3], mapE[3];
+    for (int a = 0; a < 3; a++) {
+      int n[3], t[3];
+      for (int d = 0; d < 3; d++) { n[d] = d == a ? pmax[d] : pmax[d] + 1; t[d] = d == a ? T_Q : T_H; }
+      fe[a] = add_family(S, n[0], n[1], n[2], t[0], t[1], t[2]);
+      mapE[a] = add_grid_map(S, ed, a, n, [&](int k) { return k < iE ? D.nbp + k : k - iE; });
+    }
+    const std::complex<double> zb(P.omega * P.omega * P.eps, -P.omega * P.sigma);
+    for (int a = 0; a < 3; a++)
+      for (int a2 = 0; a2 < 3; a2++) {
+        BlockBuilder b(S, fe[a], fe[a2], channel(1, 0, 0, 0, mapE[a], mapE[a2]), channel(1, 1, 0, 0, mapE[a], mapE[a2]));
+        b.add(-1, -1, F_D + sym_idx(a, a2), 1.0, -zb.real(), -zb.imag());
+        CurlComp ca[2], cb[2];
+        curl_comps(a, ca); curl_comps(a2, cb);
+        for (int i = 0; i < 2; i++)
+          for (int j = 0; j < 2; j++) b.add(ca[i].dax, cb[j].dax, F_C + sym_idx(ca[i].comp, cb[j].comp), ca[i].sgn * cb[j].sgn, 1.0 / P.mu, 0.0);
+        b.finish();
+      }
+    for (int a = 0; a < 3; a++) {  // load as a COLUMN (the LU condensation eliminates rows)
+      BlockBuilder b(S, fe[a], unit, channel(1, 0, 0, D.nbp + S.ni, mapE[a]), channel(1, 1, 0, D.nbp + S.ni, mapE[a]));
+      b.add(-1, -1, F_SRC + 2 * a, 1.0, 1.0, 0.0);
+      b.add(-1, -1, F_SRC + 2 * a + 1, 1.0, 0.0, 1.0);
       b.finish();
     }
   } else {

@@ -122,7 +122,6 @@ int hp3d_gpu_plan(int problem_kind, const hp3d_params *prm) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!prm) return fail(HP3D_EINVAL, "null params");
   if (problem_kind < HP3D_POIS_GAL || problem_kind > HP3D_MAXW_UW) return fail(HP3D_EINVAL, "unknown problem kind %d", problem_kind);
-  if (problem_kind == HP3D_MAXW_GAL) return fail(HP3D_EINVAL, "MAXW_GAL (pivoted-LU condensation) is not implemented on the GPU yet");
   // constant isotropic permittivity only (the reference's default get_permittivity is the identity,
   // problems/MAXWELL/ULTRAWEAK_DPG/common/commonRoutines.F90:126-150)
   for (int j = 0; j < 3; j++)

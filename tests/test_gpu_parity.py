@@ -62,6 +62,7 @@ CASES = [
     # kind, p, nel, tolerances on (Aii, Bi)
     (1, 1, 3), (1, 2, 3), (1, 3, 4), (1, 4, 2),
     (2, 1, 3), (2, 2, 3), (2, 3, 2), (2, 4, 2),
+    (3, 1, 3), (3, 2, 3), (3, 3, 2), (3, 4, 2), (3, 5, 1),
     (4, 1, 3), (4, 2, 3), (4, 3, 2),
 ]
 
@@ -78,7 +79,7 @@ def test_condensed_vs_oracle(oracle, gpu, kind, p, nel):
     norie[0] = 0; norif[0] = 0
     nH = oracle.celndof(norder[0])[0]
     X = np.stack([hexa_xnod(nH, h=0.5, origin=(0.1 * e, 0.2, 0.3), jitter=0.15, curved=0.01 if p > 1 else 0.0, rng=rng) for e in range(nel)])
-    om = 2 * np.pi if kind == 4 else 1.0
+    om = 2 * np.pi if kind == 4 else (np.pi if kind == 3 else 1.0)
     prm = _oracle_params(oracle, omega=om)
     eng = _engine(kind, omega=om)
     res = eng.elem_stc_batch(norder, norie, norif, X)
@@ -116,7 +117,7 @@ def test_mixed_signatures_one_call(oracle, gpu):
     for e in range(nel):
         nH = oracle.celndof(norder[e])[0]
         X[e, :nH] = hexa_xnod(nH, h=0.4, jitter=0.1, rng=rng)
-    for kind in (1, 2, 4):
+    for kind in (1, 2, 3, 4):
         om = 2 * np.pi if kind == 4 else 1.0
         prm = _oracle_params(oracle, omega=om)
         eng = _engine(kind, omega=om)
