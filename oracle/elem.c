@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#define MIDX(et) (orc_nedge(et) + orc_nface(et))
 #define IDX(A, ld, i, j) (A)[(size_t)(i) + (size_t)(ld) * (size_t)(j)]
 static void *xmalloc(size_t n) { void *p = calloc(n ? n : 1, 1); if (!p) { fprintf(stderr, "oracle: out of memory\n"); exit(1); } return p; }
 
@@ -97,19 +98,19 @@ static void check_jac(int iflag, double rjac) {
 }
 
 /* ======================================================================= POISSON / GALERKIN */
-int orc_elem_poisson_galerkin(const int norder[19], const int norie[12], const int norif[6], const double *xnod,
+int orc_elem_poisson_galerkin_t(int et, const int norder[19], const int norie[12], const int norif[6], const double *xnod,
                               const orc_params *prm, double *Aloc, double *Bloc, int *n_out) {
   int nH, nE, nV, nQ;
-  orc_celndof_hexa(norder, &nH, &nE, &nV, &nQ);
+  orc_celndof(et, norder, &nH, &nE, &nV, &nQ);
   double *xiloc = xmalloc(sizeof(double) * 3 * 1000), *waloc = xmalloc(sizeof(double) * 1000);
-  int nint = orc_set_3D_int_hexa(norder, norif, 0, orc_get_maxp(), xiloc, waloc);
+  int nint = orc_set_3D_int(et, norder, norif, 0, orc_get_maxp(), xiloc, waloc);
   int nda = 3 * nint;
   double *AT = xmalloc(sizeof(double) * nH * nda);
   double *shapH = xmalloc(sizeof(double) * nH), *gradH = xmalloc(sizeof(double) * 3 * nH);
   for (int k = 0; k < nH; k++) Bloc[k] = 0.0;
   for (int l = 0; l < nint; l++) {
     double x[3], J[9], Ji[9], rjac; int iflag;
-    orc_shape3DH_hexa(xiloc + 3 * l, norder, norie, norif, shapH, gradH);
+    orc_shape3DH(et, xiloc + 3 * l, norder, norie, norif, shapH, gradH);
     orc_geom3D(xnod, shapH, gradH, nH, x, J, Ji, &rjac, &iflag);
     check_jac(iflag, rjac);
     double weight = rjac * waloc[l], fval = poisson_source(prm, x, l), sw = sqrt(weight);
@@ -128,12 +129,12 @@ int orc_elem_poisson_galerkin(const int norder[19], const int norie[12], const i
 }
 
 /* ======================================================================= MAXWELL / GALERKIN */
-int orc_elem_maxwell_galerkin(const int norder[19], const int norie[12], const int norif[6], const double *xnod,
+int orc_elem_maxwell_galerkin_t(int et, const int norder[19], const int norie[12], const int norif[6], const double *xnod,
                               const orc_params *prm, zdouble *Aloc, zdouble *Bloc, int *n_out) {
   int nH, nE, nV, nQ;
-  orc_celndof_hexa(norder, &nH, &nE, &nV, &nQ);
+  orc_celndof(et, norder, &nH, &nE, &nV, &nQ);
   double *xiloc = xmalloc(sizeof(double) * 3 * 1000), *waloc = xmalloc(sizeof(double) * 1000);
-  int nint = orc_set_3D_int_hexa(norder, norif, 0, orc_get_maxp(), xiloc, waloc);
+  int nint = orc_set_3D_int(et, norder, norif, 0, orc_get_maxp(), xiloc, waloc);
   int nda = 3 * nint;
   zdouble *AT = xmalloc(sizeof(zdouble) * nE * nda), *MT = xmalloc(sizeof(zdouble) * nE * nda);
   double *shapH = xmalloc(sizeof(double) * nH), *gradH = xmalloc(sizeof(double) * 3 * nH);
@@ -142,8 +143,8 @@ int orc_elem_maxwell_galerkin(const int norder[19], const int norie[12], const i
   zdouble zb = prm->omega * prm->omega * prm->eps - I * prm->omega * prm->sigma;
   for (int l = 0; l < nint; l++) {
     double x[3], J[9], Ji[9], rjac; int iflag;
-    orc_shape3DH_hexa(xiloc + 3 * l, norder, norie, norif, shapH, gradH);
-    orc_shape3DE_hexa(xiloc + 3 * l, norder, norie, norif, shapE, curlE);
+    orc_shape3DH(et, xiloc + 3 * l, norder, norie, norif, shapH, gradH);
+    orc_shape3DE(et, xiloc + 3 * l, norder, norie, norif, shapE, curlE);
     orc_geom3D(xnod, shapH, gradH, nH, x, J, Ji, &rjac, &iflag);
     check_jac(iflag, rjac);
     double weight = rjac * waloc[l];
@@ -169,18 +170,18 @@ int orc_elem_maxwell_galerkin(const int norder[19], const int norie[12], const i
 }
 
 /* ======================================================================= POISSON / PRIMAL DPG */
-int orc_elem_poisson_primal_dpg(const int norder[19], const int norie[12], const int norif[6],
+int orc_elem_poisson_primal_dpg_t(int et, const int norder[19], const int norie[12], const int norif[6],
                                 const double *xnod, const orc_params *prm, double *Aloc, double *Bloc, int *nH_out,
                                 int *nVi_out) {
   int nH, nE, nV, nQ, nHH, nEE, nVV, nQQ, bH, bE, bV, bQ, norderP[19];
-  int dp = prm->nord_add, nordP = norder[18] + dp * 111;
-  orc_compute_enriched_order_hexa(nordP, norderP);
-  orc_celndof_hexa(norder, &nH, &nE, &nV, &nQ);
-  orc_celndof_hexa(norderP, &nHH, &nEE, &nVV, &nQQ);
-  orc_ndof_nod_hexa(norder[18], &bH, &bE, &bV, &bQ);
+  int dp = prm->nord_add, nordP = orc_enriched_mid(et, norder[MIDX(et)], dp);
+  orc_compute_enriched_order(et, nordP, norderP);
+  orc_celndof(et, norder, &nH, &nE, &nV, &nQ);
+  orc_celndof(et, norderP, &nHH, &nEE, &nVV, &nQQ);
+  orc_ndof_nod_mid(et, norder[MIDX(et)], &bH, &bE, &bV, &bQ);
   int nVi = nV - bV, nTest = nHH, nTrial = nH + nVi, maxpp = orc_get_maxp() + 1;
   double *xiloc = xmalloc(sizeof(double) * 3 * 1000), *waloc = xmalloc(sizeof(double) * 1000);
-  int nint = orc_set_3D_int_hexa(norder, norif, dp, maxpp, xiloc, waloc);
+  int nint = orc_set_3D_int(et, norder, norif, dp, maxpp, xiloc, waloc);
   int nda = 3 * nint;
   double *testH = xmalloc(sizeof(double) * nHH * nint), *testGH = xmalloc(sizeof(double) * nHH * nda);
   double *trialGH = xmalloc(sizeof(double) * nH * nda), *bload = xmalloc(sizeof(double) * nTest);
@@ -189,8 +190,8 @@ int orc_elem_poisson_primal_dpg(const int norder[19], const int norie[12], const
   double *shapV = xmalloc(sizeof(double) * 3 * nV), *divV = xmalloc(sizeof(double) * nV);
   for (int l = 0; l < nint; l++) {
     double x[3], J[9], Ji[9], rjac; int iflag;
-    orc_shape3DH_hexa(xiloc + 3 * l, norder, norie, norif, shapH, gradH);
-    orc_shape3HH_hexa(xiloc + 3 * l, nordP, shapHH, gradHH);
+    orc_shape3DH(et, xiloc + 3 * l, norder, norie, norif, shapH, gradH);
+    orc_shape3HH(et, xiloc + 3 * l, nordP, shapHH, gradHH);
     orc_geom3D(xnod, shapH, gradH, nH, x, J, Ji, &rjac, &iflag);
     check_jac(iflag, rjac);
     double weight = rjac * waloc[l], sw = sqrt(weight), fval = poisson_source(prm, x, l);
@@ -217,24 +218,23 @@ int orc_elem_poisson_primal_dpg(const int norder[19], const int norie[12], const
   double *stiffHV = xmalloc(sizeof(double) * nTest * (nVi ? nVi : 1));
   double *tH = xmalloc(sizeof(double) * nHH * 100), *tV = xmalloc(sizeof(double) * (nVi ? nVi : 1) * 100);
   int noff = 0;
-  for (int ifc = 1; ifc <= 6; ifc++) {
+  for (int ifc = 1; ifc <= orc_nface(et); ifc++) {
     int nordf[5], nord_ifc[19], fh, fe, fv, fq;
     double tloc[200], wtloc[100];
-    int nsign = orc_nsign_param_hexa(ifc);
-    orc_face_order_hexa(ifc, norder, nordf);
-    int nintf = orc_set_2D_int_quad(nordf, norif[ifc - 1], dp, maxpp, tloc, wtloc);
-    orc_ndof_nod_quad(norder[12 + ifc - 1], &fh, &fe, &fv, &fq);
-    for (int i = 0; i < 12; i++) nord_ifc[i] = norder[i];       /* initiate_order + edges (elem_opt.F90:322-324) */
-    for (int i = 12; i < 18; i++) nord_ifc[i] = 11;
-    nord_ifc[18] = 111;
-    nord_ifc[12 + ifc - 1] = norder[12 + ifc - 1];
+    int nsign = orc_nsign_param(et, ifc);
+    orc_face_order(et, ifc, norder, nordf);
+    int nintf = orc_set_2D_int(orc_face_is_tri(et, ifc), nordf, norif[ifc - 1], dp, maxpp, tloc, wtloc);
+    orc_ndof_nod_face(et, ifc, norder[orc_nedge(et) + ifc - 1], &fh, &fe, &fv, &fq);
+    orc_initiate_order(et, nord_ifc);                            /* initiate_order + edges (elem_opt.F90:322-324) */
+    for (int i = 0; i < orc_nedge(et); i++) nord_ifc[i] = norder[i];
+    nord_ifc[orc_nedge(et) + ifc - 1] = norder[orc_nedge(et) + ifc - 1];
     memset(tV, 0, sizeof(double) * (nVi ? nVi : 1) * 100);
     for (int l = 0; l < nintf; l++) {
       double xi[3], dxidt[6], x[3], J[9], Ji[9], rjac, dxdt[6], rn[3], bjac;
-      orc_face_param_hexa(ifc, tloc + 2 * l, xi, dxidt);
-      orc_shape3HH_hexa(xi, nordP, shapHH, gradHH);
-      orc_shape3DV_hexa(xi, nord_ifc, norif, shapV, divV);
-      orc_shape3DH_hexa(xi, norder, norie, norif, shapH, gradH);
+      orc_face_param(et, ifc, tloc + 2 * l, xi, dxidt);
+      orc_shape3HH(et, xi, nordP, shapHH, gradHH);
+      orc_shape3DV(et, xi, nord_ifc, norif, shapV, divV);
+      orc_shape3DH(et, xi, norder, norie, norif, shapH, gradH);
       orc_bgeom3D(xnod, shapH, gradH, nH, dxidt, nsign, x, J, Ji, &rjac, dxdt, rn, &bjac);
       double weight = bjac * wtloc[l], sw = sqrt(weight);
       for (int k = 0; k < nHH; k++) IDX(tH, nHH, k, l) = shapHH[k] * sw;
@@ -267,18 +267,18 @@ int orc_elem_poisson_primal_dpg(const int norder[19], const int norie[12], const
 }
 
 /* ======================================================================= MAXWELL / ULTRAWEAK DPG */
-int orc_elem_maxwell_uw_dpg(const int norder[19], const int norie[12], const int norif[6], const double *xnod,
+int orc_elem_maxwell_uw_dpg_t(int et, const int norder[19], const int norie[12], const int norif[6], const double *xnod,
                             const orc_params *prm, zdouble *Aloc, zdouble *Bloc, int *nEi_out, int *nQ_out,
                             zdouble *gram_out, zdouble *stiff_out) {
   int nH, nE, nV, nQ, nHH, nEE, nVV, nQQ, bH, bE, bV, bQ, norderP[19];
-  int dp = prm->nord_add, nordP = norder[18] + dp * 111, maxpp = orc_get_maxp() + 1;
-  orc_compute_enriched_order_hexa(nordP, norderP);
-  orc_celndof_hexa(norder, &nH, &nE, &nV, &nQ);
-  orc_celndof_hexa(norderP, &nHH, &nEE, &nVV, &nQQ);
-  orc_ndof_nod_hexa(norder[18], &bH, &bE, &bV, &bQ);
+  int dp = prm->nord_add, nordP = orc_enriched_mid(et, norder[MIDX(et)], dp), maxpp = orc_get_maxp() + 1;
+  orc_compute_enriched_order(et, nordP, norderP);
+  orc_celndof(et, norder, &nH, &nE, &nV, &nQ);
+  orc_celndof(et, norderP, &nHH, &nEE, &nVV, &nQQ);
+  orc_ndof_nod_mid(et, norder[MIDX(et)], &bH, &bE, &bV, &bQ);
   int nEi = nE - bE, nTest = 2 * nEE, nTrial = 2 * nEi + 6 * nQ;
   double *xiloc = xmalloc(sizeof(double) * 3 * 1000), *waloc = xmalloc(sizeof(double) * 1000);
-  int nint = orc_set_3D_int_hexa(norder, norif, dp, maxpp, xiloc, waloc);
+  int nint = orc_set_3D_int(et, norder, norif, dp, maxpp, xiloc, waloc);
   int nda = 3 * nint, n3Q = 3 * nQ;
   double *test_rE = xmalloc(sizeof(double) * nEE * nda), *test_rCE = xmalloc(sizeof(double) * nEE * nda);
   double *trial_rQ = xmalloc(sizeof(double) * n3Q * nda);
@@ -292,9 +292,9 @@ int orc_elem_maxwell_uw_dpg(const int norder[19], const int norie[12], const int
   /* ---- volume loop: elem_opt.F90:236-325 */
   for (int l = 0; l < nint; l++) {
     double x[3], J[9], Ji[9], rjac; int iflag;
-    orc_shape3DH_hexa(xiloc + 3 * l, norder, norie, norif, shapH, gradH);
-    orc_shape3DQ_hexa(xiloc + 3 * l, norder, shapQ);
-    orc_shape3EE_hexa(xiloc + 3 * l, nordP, shapEE, curlEE);
+    orc_shape3DH(et, xiloc + 3 * l, norder, norie, norif, shapH, gradH);
+    orc_shape3DQ(et, xiloc + 3 * l, norder, shapQ);
+    orc_shape3EE(et, xiloc + 3 * l, nordP, shapEE, curlEE);
     orc_geom3D(xnod, shapH, gradH, nH, x, J, Ji, &rjac, &iflag);
     check_jac(iflag, rjac);
     for (int j = 0; j < 3; j++)
@@ -381,26 +381,25 @@ int orc_elem_maxwell_uw_dpg(const int norder[19], const int norie[12], const int
   double *st_rEE = xmalloc(sizeof(double) * nEE * nEi);
   double *t_rE = xmalloc(sizeof(double) * nEE * 300), *t_rnE = xmalloc(sizeof(double) * nEi * 300);
   int noffE = 0;
-  for (int ifc = 1; ifc <= 6; ifc++) {
+  for (int ifc = 1; ifc <= orc_nface(et); ifc++) {
     int nordf[5], nord_ifc[19], fh, fe, fv, fq;
     double tloc[200], wtloc[100];
-    int nsign = orc_nsign_param_hexa(ifc);
-    orc_face_order_hexa(ifc, norder, nordf);
-    int nintf = orc_set_2D_int_quad(nordf, norif[ifc - 1], dp, maxpp, tloc, wtloc);
-    orc_ndof_nod_quad(norder[12 + ifc - 1], &fh, &fe, &fv, &fq);
-    for (int i = 0; i < 12; i++) nord_ifc[i] = norder[i];
-    for (int i = 12; i < 18; i++) nord_ifc[i] = 11;
-    nord_ifc[18] = 111;
-    nord_ifc[12 + ifc - 1] = norder[12 + ifc - 1];
+    int nsign = orc_nsign_param(et, ifc);
+    orc_face_order(et, ifc, norder, nordf);
+    int nintf = orc_set_2D_int(orc_face_is_tri(et, ifc), nordf, norif[ifc - 1], dp, maxpp, tloc, wtloc);
+    orc_ndof_nod_face(et, ifc, norder[orc_nedge(et) + ifc - 1], &fh, &fe, &fv, &fq);
+    orc_initiate_order(et, nord_ifc);                            /* initiate_order + edges (elem_opt.F90:322-324) */
+    for (int i = 0; i < orc_nedge(et); i++) nord_ifc[i] = norder[i];
+    nord_ifc[orc_nedge(et) + ifc - 1] = norder[orc_nedge(et) + ifc - 1];
     memset(t_rnE, 0, sizeof(double) * nEi * 300);
     for (int l = 0; l < nintf; l++) {
       double xi[3], dxidt[6], x[3], J[9], Ji[9], rjac, dxdt[6], rn[3], bjac;
-      orc_face_param_hexa(ifc, tloc + 2 * l, xi, dxidt);
-      orc_shape3EE_hexa(xi, nordP, shapEE, curlEE);
-      orc_shape3DH_hexa(xi, norder, norie, norif, shapH, gradH);
+      orc_face_param(et, ifc, tloc + 2 * l, xi, dxidt);
+      orc_shape3EE(et, xi, nordP, shapEE, curlEE);
+      orc_shape3DH(et, xi, norder, norie, norif, shapH, gradH);
       orc_bgeom3D(xnod, shapH, gradH, nH, dxidt, nsign, x, J, Ji, &rjac, dxdt, rn, &bjac);
       double weight = bjac * wtloc[l], sw = sqrt(weight);
-      int nE_ifc = orc_shape3DE_hexa(xi, nord_ifc, norie, norif, shapE, curlE);
+      int nE_ifc = orc_shape3DE(et, xi, nord_ifc, norie, norif, shapE, curlE);
       for (int k = 0; k < nEE; k++) {
         double F[3];
         pull_grad(shapEE + 3 * k, Ji, F);
@@ -525,10 +524,10 @@ int orc_stc_fwd_cplx(int herm, int ni, int nb, zdouble *Aii, zdouble *Abi, zdoub
  *  2 POIS_PDPG: H1 (PHYSAi=F) + H(div) trace (PHYSAi=T) -> [H1 interface | trace] then [H1 bubbles]
  *  3 MAXW_GAL : one H(curl) variable
  *  4 MAXW_UW  : H(curl) traces x2 (PHYSAi=T) + L2 x6 (all bubble) */
-int orc_stc_partition(int kind, const int norder[19], int *perm, int *ni_out, int *nb_out) {
+int orc_stc_partition_t(int et, int kind, const int norder[19], int *perm, int *ni_out, int *nb_out) {
   int nH, nE, nV, nQ, bH, bE, bV, bQ, ni = 0, nb = 0, n = 0;
-  orc_celndof_hexa(norder, &nH, &nE, &nV, &nQ);
-  orc_ndof_nod_hexa(norder[18], &bH, &bE, &bV, &bQ);
+  orc_celndof(et, norder, &nH, &nE, &nV, &nQ);
+  orc_ndof_nod_mid(et, norder[MIDX(et)], &bH, &bE, &bV, &bQ);
   switch (kind) {
     case 1: ni = nH - bH; nb = bH; n = nH; for (int i = 0; i < n; i++) perm[i] = i; break;
     case 3: ni = nE - bE; nb = bE; n = nE; for (int i = 0; i < n; i++) perm[i] = i; break;
@@ -546,20 +545,20 @@ int orc_stc_partition(int kind, const int norder[19], int *perm, int *ni_out, in
   return 0;
 }
 
-int orc_condensed_element(int kind, const int norder[19], const int norie[12], const int norif[6], const double *xnod,
+int orc_condensed_element_t(int et, int kind, const int norder[19], const int norie[12], const int norif[6], const double *xnod,
                           const orc_params *prm, void *Aii_o, void *Bi_o, void *AS_o, void *BS_o, int *ni_o, int *nb_o) {
   int ni, nb, info = 0;
   int *perm = xmalloc(sizeof(int) * 8192);
-  if (orc_stc_partition(kind, norder, perm, &ni, &nb)) { free(perm); return -1; }
+  if (orc_stc_partition_t(et, kind, norder, perm, &ni, &nb)) { free(perm); return -1; }
   int n = ni + nb, cplx = (kind >= 3), herm = (kind == 2 || kind == 4);
   size_t es = cplx ? sizeof(zdouble) : sizeof(double);
   void *A = xmalloc(es * n * n), *b = xmalloc(es * n);
   int a1, a2;
   switch (kind) {
-    case 1: info = orc_elem_poisson_galerkin(norder, norie, norif, xnod, prm, A, b, &a1); break;
-    case 2: info = orc_elem_poisson_primal_dpg(norder, norie, norif, xnod, prm, A, b, &a1, &a2); break;
-    case 3: info = orc_elem_maxwell_galerkin(norder, norie, norif, xnod, prm, A, b, &a1); break;
-    case 4: info = orc_elem_maxwell_uw_dpg(norder, norie, norif, xnod, prm, A, b, &a1, &a2, NULL, NULL); break;
+    case 1: info = orc_elem_poisson_galerkin_t(et, norder, norie, norif, xnod, prm, A, b, &a1); break;
+    case 2: info = orc_elem_poisson_primal_dpg_t(et, norder, norie, norif, xnod, prm, A, b, &a1, &a2); break;
+    case 3: info = orc_elem_maxwell_galerkin_t(et, norder, norie, norif, xnod, prm, A, b, &a1); break;
+    case 4: info = orc_elem_maxwell_uw_dpg_t(et, norder, norie, norif, xnod, prm, A, b, &a1, &a2, NULL, NULL); break;
   }
   if (info) { free(A); free(b); free(perm); return info; }
   void *Abb = xmalloc(es * nb * nb), *Aib = xmalloc(es * ni * nb);
@@ -587,7 +586,7 @@ int orc_condensed_element(int kind, const int norder[19], const int norie[12], c
 /* Element loop with the structure of par_mumps_sc.F90:318-357 (!$OMP DO SCHEDULE(DYNAMIC) over the
  * subdomain's elements, thread-private workspaces).  Outputs are packed per element with the given
  * strides (in scalars).  Returns the number of elements whose info != 0. */
-int orc_condensed_batch(int kind, int nel, const int *norder, const int *norie, const int *norif, const double *xnod,
+int orc_condensed_batch_t(int kind, int nel, const int *etype, const int *norder, const int *norie, const int *norif, const double *xnod,
                         int xnod_stride, const orc_params *prm, void *Aii, void *Bi, void *ASchur, void *BSchur,
                         long sAii, long sBi, long sAS, long sBS, int *info, int nthreads) {
   int cplx = (kind >= 3), bad = 0;
@@ -595,11 +594,43 @@ int orc_condensed_batch(int kind, int nel, const int *norder, const int *norie, 
 #pragma omp parallel for schedule(dynamic) num_threads(nthreads) reduction(+ : bad)
   for (int e = 0; e < nel; e++) {
     int ni, nb;
-    int r = orc_condensed_element(kind, norder + 19 * e, norie + 12 * e, norif + 6 * e, xnod + (size_t)xnod_stride * e, prm,
+    int r = orc_condensed_element_t(etype ? etype[e] : ORC_MDLB, kind, norder + 19 * e, norie + 12 * e, norif + 6 * e, xnod + (size_t)xnod_stride * e, prm,
                                   (char *)Aii + es * sAii * e, (char *)Bi + es * sBi * e, (char *)ASchur + es * sAS * e,
                                   (char *)BSchur + es * sBS * e, &ni, &nb);
     if (info) info[e] = r;
     if (r) bad++;
   }
   return bad;
+}
+
+/* ---- brick-only entry points kept for the existing callers */
+int orc_elem_poisson_galerkin(const int norder[19], const int norie[12], const int norif[6], const double *xnod,
+                              const orc_params *prm, double *Aloc, double *Bloc, int *n) {
+  return orc_elem_poisson_galerkin_t(ORC_MDLB, norder, norie, norif, xnod, prm, Aloc, Bloc, n);
+}
+int orc_elem_poisson_primal_dpg(const int norder[19], const int norie[12], const int norif[6], const double *xnod,
+                                const orc_params *prm, double *Aloc, double *Bloc, int *nH, int *nVi) {
+  return orc_elem_poisson_primal_dpg_t(ORC_MDLB, norder, norie, norif, xnod, prm, Aloc, Bloc, nH, nVi);
+}
+int orc_elem_maxwell_galerkin(const int norder[19], const int norie[12], const int norif[6], const double *xnod,
+                              const orc_params *prm, zdouble *Aloc, zdouble *Bloc, int *n) {
+  return orc_elem_maxwell_galerkin_t(ORC_MDLB, norder, norie, norif, xnod, prm, Aloc, Bloc, n);
+}
+int orc_elem_maxwell_uw_dpg(const int norder[19], const int norie[12], const int norif[6], const double *xnod,
+                            const orc_params *prm, zdouble *Aloc, zdouble *Bloc, int *nEi, int *nQ, zdouble *gram_out,
+                            zdouble *stiff_out) {
+  return orc_elem_maxwell_uw_dpg_t(ORC_MDLB, norder, norie, norif, xnod, prm, Aloc, Bloc, nEi, nQ, gram_out, stiff_out);
+}
+int orc_stc_partition(int kind, const int norder[19], int *perm, int *ni, int *nb) {
+  return orc_stc_partition_t(ORC_MDLB, kind, norder, perm, ni, nb);
+}
+int orc_condensed_element(int kind, const int norder[19], const int norie[12], const int norif[6], const double *xnod,
+                          const orc_params *prm, void *Aii, void *Bi, void *ASchur, void *BSchur, int *ni, int *nb) {
+  return orc_condensed_element_t(ORC_MDLB, kind, norder, norie, norif, xnod, prm, Aii, Bi, ASchur, BSchur, ni, nb);
+}
+int orc_condensed_batch(int kind, int nel, const int *norder, const int *norie, const int *norif, const double *xnod,
+                        int xnod_stride, const orc_params *prm, void *Aii, void *Bi, void *ASchur, void *BSchur,
+                        long sAii, long sBi, long sAS, long sBS, int *info, int nthreads) {
+  return orc_condensed_batch_t(kind, nel, NULL, norder, norie, norif, xnod, xnod_stride, prm, Aii, Bi, ASchur, BSchur, sAii,
+                               sBi, sAS, sBS, info, nthreads);
 }

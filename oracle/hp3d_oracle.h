@@ -93,6 +93,49 @@ void orc_face_param_hexa(int iface, const double t[2], double xi[3], double dxid
 int orc_nsign_param_hexa(int iface);
 void orc_face_order_hexa(int iface, const int norder[19], int nordf[5]);
 
+/* ---- element types (src/modules/node_types.F90:8-10) and the prism / triangle branch (shape_prism.c, etype.c) */
+#define ORC_MDLB 1
+#define ORC_MDLP 3
+int orc_nvert(int et); int orc_nedge(int et); int orc_nface(int et); int orc_face_is_tri(int et, int iface);
+/* triangle: src/element/shape_1/Triangle.F90:30,140,270,330 ; nord[4] = 3 edges + face */
+int orc_shape2DH_tri(const double x[2], const int nord[4], const int norie[3], double *shapH, double *gradH /*(2,n)*/);
+int orc_shape2DE_tri(const double x[2], const int nord[4], const int norie[3], double *shapE /*(2,n)*/, double *curlE);
+int orc_shape2DV_tri(const double x[2], const int nord[4], const int norie[3], double *shapV /*(2,n)*/, double *divV);
+int orc_shape2DQ_tri(const double x[2], int nordf, double *shapQ);
+/* prism: src/element/shape_1/Prism.F90:38,358,760,1040 ; nord[15] = 9 edges, 2 triangle faces, 3 quad faces, middle */
+int orc_shape3DH_pris(const double x[3], const int nord[15], const int norie[9], const int norif[5], double *shapH, double *gradH);
+int orc_shape3DE_pris(const double x[3], const int nord[15], const int norie[9], const int norif[5], double *shapE, double *curlE);
+int orc_shape3DV_pris(const double x[3], const int nord[15], const int norif[5], double *shapV, double *divV);
+int orc_shape3DQ_pris(const double x[3], const int nord[15], double *shapQ);
+/* broken prism: src/element/shape_1/broken/BrokenPrism.F90 ; nordM = 10*p_tri + p_z */
+int orc_shape3HH_pris(const double xi[3], int nordM, double *shapH, double *gradH);
+int orc_shape3EE_pris(const double xi[3], int nordM, double *shapE, double *curlE);
+int orc_shape3VV_pris(const double xi[3], int nordM, double *shapV, double *divV);
+int orc_shape3QQ_pris(const double xi[3], int nordM, double *shapQ);
+/* select case(ntype) dispatchers: ContExactSequence.F90:397-634, broken/BrokenExactSequence.F90:401-691 */
+int orc_shape3DH(int et, const double xi[3], const int *nord, const int *norie, const int *norif, double *s, double *g);
+int orc_shape3DE(int et, const double xi[3], const int *nord, const int *norie, const int *norif, double *s, double *c);
+int orc_shape3DV(int et, const double xi[3], const int *nord, const int *norif, double *s, double *d);
+int orc_shape3DQ(int et, const double xi[3], const int *nord, double *s);
+int orc_shape3HH(int et, const double xi[3], int nordM, double *s, double *g);
+int orc_shape3EE(int et, const double xi[3], int nordM, double *s, double *c);
+int orc_shape3VV(int et, const double xi[3], int nordM, double *s, double *d);
+int orc_shape3QQ(int et, const double xi[3], int nordM, double *s);
+void orc_ndof_nod_tria(int nord, int *h, int *e, int *v, int *q);
+void orc_ndof_nod_pris(int nord, int *h, int *e, int *v, int *q);
+void orc_ndof_nod_mid(int et, int nord, int *h, int *e, int *v, int *q);
+void orc_ndof_nod_face(int et, int iface, int nord, int *h, int *e, int *v, int *q);
+void orc_celndof(int et, const int *nord, int *H, int *E, int *V, int *Q);
+int orc_enriched_mid(int et, int nord_mid, int dp);
+int orc_trace_mid(int et);
+void orc_compute_enriched_order(int et, int nordP, int *norder);
+void orc_initiate_order(int et, int *norder);
+int orc_set_3D_int(int et, const int *norder, const int *norif, int integration, int maxp, double *xiloc, double *waloc);
+int orc_set_2D_int(int is_tri, const int nordf[5], int norif, int integration, int maxp, double *tloc, double *wtloc);
+void orc_face_param(int et, int iface, const double t[2], double xi[3], double dxidt[6]);
+int orc_nsign_param(int et, int iface);
+void orc_face_order(int et, int iface, const int *norder, int nordf[5]);
+
 /* ---- dense kernels (BLAS/LAPACK subset the path calls; see dense.c).  If orc_dense_use_blas() finds
  *      an OpenBLAS it forwards to it, else runs the built-in textbook loops. */
 int orc_dense_use_blas(const char *libpath); /* returns 1 if loaded */
@@ -148,6 +191,25 @@ int orc_condensed_batch(int problem_kind, int nel, const int *norder, const int 
                         const double *xnod, int xnod_stride, const orc_params *prm, void *Aii, void *Bi,
                         void *ASchur, void *BSchur, long sAii, long sBi, long sAS, long sBS, int *info,
                         int nthreads);
+
+/* element-type aware variants (et = ORC_MDLB / ORC_MDLP; descriptor arrays keep the 19/12/6 layout, a prism uses
+ * the first 15/9/5 entries) */
+int orc_elem_poisson_galerkin_t(int et, const int norder[19], const int norie[12], const int norif[6], const double *xnod,
+                                const orc_params *prm, double *Aloc, double *Bloc, int *n);
+int orc_elem_poisson_primal_dpg_t(int et, const int norder[19], const int norie[12], const int norif[6], const double *xnod,
+                                  const orc_params *prm, double *Aloc, double *Bloc, int *nH, int *nVi);
+int orc_elem_maxwell_galerkin_t(int et, const int norder[19], const int norie[12], const int norif[6], const double *xnod,
+                                const orc_params *prm, zdouble *Aloc, zdouble *Bloc, int *n);
+int orc_elem_maxwell_uw_dpg_t(int et, const int norder[19], const int norie[12], const int norif[6], const double *xnod,
+                              const orc_params *prm, zdouble *Aloc, zdouble *Bloc, int *nEi, int *nQ, zdouble *gram_out,
+                              zdouble *stiff_out);
+int orc_stc_partition_t(int et, int problem_kind, const int norder[19], int *perm, int *ni, int *nb);
+int orc_condensed_element_t(int et, int problem_kind, const int norder[19], const int norie[12], const int norif[6],
+                            const double *xnod, const orc_params *prm, void *Aii, void *Bi, void *ASchur, void *BSchur,
+                            int *ni, int *nb);
+int orc_condensed_batch_t(int problem_kind, int nel, const int *etype, const int *norder, const int *norie, const int *norif,
+                          const double *xnod, int xnod_stride, const orc_params *prm, void *Aii, void *Bi, void *ASchur,
+                          void *BSchur, long sAii, long sBi, long sAS, long sBS, int *info, int nthreads);
 
 #ifdef __cplusplus
 }

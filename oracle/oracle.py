@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 POIS_GAL, POIS_PDPG, MAXW_GAL, MAXW_UW = 1, 2, 3, 4
+MDLB, MDLP = 1, 3   # element types (src/modules/node_types.F90:8-10)
 
 
 class Params(C.Structure):
@@ -25,7 +26,7 @@ class Params(C.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, "libhp3d_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("shape.c", "quad_geom.c", "dense.c", "elem.c", "hp3d_oracle.h", "dense.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("shape.c", "shape_prism.c", "quad_geom.c", "etype.c", "tri_rules.h", "dense.c", "elem.c", "hp3d_oracle.h", "dense.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "libhp3d_oracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -68,6 +69,16 @@ def _ip(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
+def _pad(a, n):
+    """descriptor arrays keep the brick layout (19/12/6); a prism uses the first 15/9/5 entries"""
+    a = _ip(a).ravel()
+    if a.size >= n:
+        return a
+    out = np.zeros(n, dtype=np.int32)
+    out[:a.size] = a
+    return out
+
+
 def _i(a):
     return a.ctypes.data_as(C.POINTER(C.c_int))
 
@@ -93,20 +104,27 @@ def set_maxp(maxp):
     lib().orc_set_maxp(int(maxp))
 
 
-def uniform_order(p):
-    """norder(19) of an isotropic order-p hexa (find_order.F90:41-58 layout)."""
+def uniform_order(p, etype=MDLB, pz=None):
+    """norder(19) of an isotropic order-p hexa / an order-(p, pz) prism (find_order.F90:41-58 layout)."""
+    if etype == MDLP:
+        pz = p if pz is None else pz
+        return np.array([p] * 6 + [pz] * 3 + [p] * 2 + [10 * p + pz] * 3 + [10 * p + pz] + [0] * 4, dtype=np.int32)
     return np.array([p] * 12 + [11 * p] * 6 + [111 * p], dtype=np.int32)
 
 
-def celndof(norder):
+def mid_index(etype):
+    return 14 if etype == MDLP else 18
+
+
+def celndof(norder, etype=MDLB):
     h, e, v, q = (C.c_int() for _ in range(4))
-    lib().orc_celndof_hexa(_i(_ip(norder)), C.byref(h), C.byref(e), C.byref(v), C.byref(q))
+    lib().orc_celndof(int(etype), _i(_pad(norder, 19)), C.byref(h), C.byref(e), C.byref(v), C.byref(q))
     return h.value, e.value, v.value, q.value
 
 
-def ndof_mdl(nord):
+def ndof_mdl(nord, etype=MDLB):
     h, e, v, q = (C.c_int() for _ in range(4))
-    lib().orc_ndof_nod_hexa(int(nord), C.byref(h), C.byref(e), C.byref(v), C.byref(q))
+    lib().orc_ndof_nod_mid(int(etype), int(nord), C.byref(h), C.byref(e), C.byref(v), C.byref(q))
     return h.value, e.value, v.value, q.value
 
 
@@ -117,101 +135,101 @@ def gauss1(n):
     return x, w
 
 
-def shape3DH(xi, norder, norie, norif):
-    nH = celndof(norder)[0]
+def shape3DH(xi, norder, norie, norif, etype=MDLB):
+    nH = celndof(norder, etype)[0]
     s = np.zeros(nH)
     g = np.zeros((nH, 3))
     xi = np.ascontiguousarray(xi, dtype=np.float64)
-    n = lib().orc_shape3DH_hexa(_d(xi), _i(_ip(norder)), _i(_ip(norie)), _i(_ip(norif)), _d(s), _d(g))
+    n = lib().orc_shape3DH(int(etype), _d(xi), _i(_pad(norder, 19)), _i(_pad(norie, 12)), _i(_pad(norif, 6)), _d(s), _d(g))
     assert n == nH
     return s, g
 
 
-def shape3DE(xi, norder, norie, norif):
-    nE = celndof(norder)[1]
+def shape3DE(xi, norder, norie, norif, etype=MDLB):
+    nE = celndof(norder, etype)[1]
     s = np.zeros((nE, 3))
     c = np.zeros((nE, 3))
     xi = np.ascontiguousarray(xi, dtype=np.float64)
-    n = lib().orc_shape3DE_hexa(_d(xi), _i(_ip(norder)), _i(_ip(norie)), _i(_ip(norif)), _d(s), _d(c))
+    n = lib().orc_shape3DE(int(etype), _d(xi), _i(_pad(norder, 19)), _i(_pad(norie, 12)), _i(_pad(norif, 6)), _d(s), _d(c))
     assert n == nE
     return s, c
 
 
-def shape3DV(xi, norder, norif):
-    nV = celndof(norder)[2]
+def shape3DV(xi, norder, norif, etype=MDLB):
+    nV = celndof(norder, etype)[2]
     s = np.zeros((nV, 3))
     d = np.zeros(nV)
     xi = np.ascontiguousarray(xi, dtype=np.float64)
-    n = lib().orc_shape3DV_hexa(_d(xi), _i(_ip(norder)), _i(_ip(norif)), _d(s), _d(d))
+    n = lib().orc_shape3DV(int(etype), _d(xi), _i(_pad(norder, 19)), _i(_pad(norif, 6)), _d(s), _d(d))
     assert n == nV
     return s, d
 
 
-def shape3DQ(xi, norder):
-    nQ = celndof(norder)[3]
+def shape3DQ(xi, norder, etype=MDLB):
+    nQ = celndof(norder, etype)[3]
     s = np.zeros(nQ)
     xi = np.ascontiguousarray(xi, dtype=np.float64)
-    n = lib().orc_shape3DQ_hexa(_d(xi), _i(_ip(norder)), _d(s))
+    n = lib().orc_shape3DQ(int(etype), _d(xi), _i(_pad(norder, 19)), _d(s))
     assert n == nQ
     return s
 
 
-def shape3HH(xi, nordM):
-    n = int(np.prod([d + 1 for d in divmod(nordM // 10, 10)] + [nordM % 10 + 1]))
+def shape3HH(xi, nordM, etype=MDLB):
+    n = celndof(enriched_order(nordM, etype), etype)[0]
     s = np.zeros(n)
     g = np.zeros((n, 3))
     xi = np.ascontiguousarray(xi, dtype=np.float64)
-    m = lib().orc_shape3HH_hexa(_d(xi), int(nordM), _d(s), _d(g))
+    m = lib().orc_shape3HH(int(etype), _d(xi), int(nordM), _d(s), _d(g))
     assert m == n
     return s, g
 
 
-def shape3EE(xi, nordM):
-    px, py, pz = nordM // 100, (nordM // 10) % 10, nordM % 10
-    n = px * (py + 1) * (pz + 1) + (px + 1) * py * (pz + 1) + (px + 1) * (py + 1) * pz
+def shape3EE(xi, nordM, etype=MDLB):
+    n = celndof(enriched_order(nordM, etype), etype)[1]
     s = np.zeros((n, 3))
     c = np.zeros((n, 3))
     xi = np.ascontiguousarray(xi, dtype=np.float64)
-    m = lib().orc_shape3EE_hexa(_d(xi), int(nordM), _d(s), _d(c))
+    m = lib().orc_shape3EE(int(etype), _d(xi), int(nordM), _d(s), _d(c))
     assert m == n
     return s, c
 
 
-def quad3(norder, norif, integration, maxp):
+def quad3(norder, norif, integration, maxp, etype=MDLB):
     xi = np.zeros((1000, 3))
     w = np.zeros(1000)
-    n = lib().orc_set_3D_int_hexa(_i(_ip(norder)), _i(_ip(norif)), int(integration), int(maxp), _d(xi), _d(w))
+    n = lib().orc_set_3D_int(int(etype), _i(_pad(norder, 19)), _i(_pad(norif, 6)), int(integration), int(maxp), _d(xi), _d(w))
     return xi[:n].copy(), w[:n].copy()
 
 
-def stc_partition(kind, norder):
+def stc_partition(kind, norder, etype=MDLB):
     perm = np.zeros(8192, dtype=np.int32)
     ni, nb = C.c_int(), C.c_int()
-    r = lib().orc_stc_partition(int(kind), _i(_ip(norder)), _i(perm), C.byref(ni), C.byref(nb))
+    r = lib().orc_stc_partition_t(int(etype), int(kind), _i(_pad(norder, 19)), _i(perm), C.byref(ni), C.byref(nb))
     assert r == 0
     return perm[: ni.value + nb.value].copy(), ni.value, nb.value
 
 
-def elem(kind, norder, norie, norif, xnod, prm, want_dpg=False):
+def elem(kind, norder, norie, norif, xnod, prm, want_dpg=False, etype=MDLB):
     """Full (uncondensed) local matrix/load of one element, reference dof ordering. xnod: (nrdofH,3)."""
     L = lib()
-    norder, norie, norif = _ip(norder), _ip(norie), _ip(norif)
+    norder, norie, norif = _pad(norder, 19), _pad(norie, 12), _pad(norif, 6)
     xnod = np.ascontiguousarray(xnod, dtype=np.float64)
-    nH, nE, nV, nQ = celndof(norder)
-    bH, bE, bV, bQ = ndof_mdl(int(norder[18]))
+    et = int(etype)
+    nH, nE, nV, nQ = celndof(norder, et)
+    bH, bE, bV, bQ = ndof_mdl(int(norder[mid_index(et)]), et)
     a1, a2 = C.c_int(), C.c_int()
     if kind == POIS_GAL:
         n = nH
         A = np.zeros((n, n), order="F"); b = np.zeros(n)
-        r = L.orc_elem_poisson_galerkin(_i(norder), _i(norie), _i(norif), _d(xnod), C.byref(prm), _d(A), _d(b), C.byref(a1))
+        r = L.orc_elem_poisson_galerkin_t(et, _i(norder), _i(norie), _i(norif), _d(xnod), C.byref(prm), _d(A), _d(b), C.byref(a1))
     elif kind == POIS_PDPG:
         n = nH + nV - bV
         A = np.zeros((n, n), order="F"); b = np.zeros(n)
-        r = L.orc_elem_poisson_primal_dpg(_i(norder), _i(norie), _i(norif), _d(xnod), C.byref(prm), _d(A), _d(b), C.byref(a1), C.byref(a2))
+        r = L.orc_elem_poisson_primal_dpg_t(et, _i(norder), _i(norie), _i(norif), _d(xnod), C.byref(prm), _d(A), _d(b), C.byref(a1), C.byref(a2))
     elif kind == MAXW_GAL:
         n = nE
         A = np.zeros((n, n), order="F", dtype=np.complex128); b = np.zeros(n, dtype=np.complex128)
-        r = L.orc_elem_maxwell_galerkin(_i(norder), _i(norie), _i(norif), _d(xnod), C.byref(prm), _d(A), _d(b), C.byref(a1))
+        r = L.orc_elem_maxwell_galerkin_t(et, _i(norder), _i(norie), _i(norif), _d(xnod), C.byref(prm), _d(A), _d(b), C.byref(a1))
     elif kind == MAXW_UW:
         n = 2 * (nE - bE) + 6 * nQ
         A = np.zeros((n, n), order="F", dtype=np.complex128); b = np.zeros(n, dtype=np.complex128)
@@ -219,11 +237,11 @@ def elem(kind, norder, norie, norif, xnod, prm, want_dpg=False):
         gp = sp = None
         if want_dpg:
             dp = prm.nord_add
-            nEE = celndof(enriched_order(int(norder[18]) + dp * 111))[1]
+            nEE = celndof(enriched_order(int(norder[mid_index(et)]) + dp * (11 if et == MDLP else 111), et), et)[1]
             gram = np.zeros((2 * nEE, 2 * nEE), order="F", dtype=np.complex128)
             stiff = np.zeros((2 * nEE, n + 1), order="F", dtype=np.complex128)
             gp, sp = _d(gram), _d(stiff)
-        r = L.orc_elem_maxwell_uw_dpg(_i(norder), _i(norie), _i(norif), _d(xnod), C.byref(prm), _d(A), _d(b), C.byref(a1), C.byref(a2), gp, sp)
+        r = L.orc_elem_maxwell_uw_dpg_t(et, _i(norder), _i(norie), _i(norif), _d(xnod), C.byref(prm), _d(A), _d(b), C.byref(a1), C.byref(a2), gp, sp)
         if want_dpg:
             assert r == 0
             return A, b, gram, stiff
@@ -233,23 +251,23 @@ def elem(kind, norder, norie, norif, xnod, prm, want_dpg=False):
     return A, b
 
 
-def enriched_order(nordP):
+def enriched_order(nordP, etype=MDLB):
     no = np.zeros(19, dtype=np.int32)
-    lib().orc_compute_enriched_order_hexa(int(nordP), _i(no))
+    lib().orc_compute_enriched_order(int(etype), int(nordP), _i(no))
     return no
 
 
-def condensed(kind, norder, norie, norif, xnod, prm):
+def condensed(kind, norder, norie, norif, xnod, prm, etype=MDLB):
     """elem + stc_fwd_wrapper for one element -> Aii, Bi, ASchur, BSchur."""
     L = lib()
-    norder, norie, norif = _ip(norder), _ip(norie), _ip(norif)
+    norder, norie, norif = _pad(norder, 19), _pad(norie, 12), _pad(norif, 6)
     xnod = np.ascontiguousarray(xnod, dtype=np.float64)
-    _, ni, nb = stc_partition(kind, norder)
+    _, ni, nb = stc_partition(kind, norder, etype)
     dt = np.complex128 if kind >= 3 else np.float64
     Aii = np.zeros((ni, ni), order="F", dtype=dt); Bi = np.zeros(ni, dtype=dt)
     AS = np.zeros((nb, ni), order="F", dtype=dt); BS = np.zeros(nb, dtype=dt)
     a, b = C.c_int(), C.c_int()
-    r = L.orc_condensed_element(int(kind), _i(norder), _i(norie), _i(norif), _d(xnod), C.byref(prm), _d(Aii), _d(Bi), _d(AS), _d(BS), C.byref(a), C.byref(b))
+    r = L.orc_condensed_element_t(int(etype), int(kind), _i(norder), _i(norie), _i(norif), _d(xnod), C.byref(prm), _d(Aii), _d(Bi), _d(AS), _d(BS), C.byref(a), C.byref(b))
     assert r == 0, r
     return Aii, Bi, AS, BS
 

@@ -547,3 +547,6 @@ int orc_shape3QQ_hexa(const double xi[3], int nordM, double *shapQ) {
   norder[18] = nordM;
   return orc_shape3DQ_hexa(xi, norder, shapQ);
 }
+
+/* triangle + prism shape functions share the static helpers above */
+#include "shape_prism.c"
