@@ -19,7 +19,7 @@ from . import _lib
 POIS_GAL, POIS_PDPG, MAXW_GAL, MAXW_UW = 1, 2, 3, 4
 GRAPH_NORM, MATH_NORM, GRAPH_DIAG = 1, 2, 3
 SRC_ZERO, SRC_SIN, SRC_TABLE = 0, 1, 9
-MDLB = 1
+MDLB, MDLP = 1, 3   # element types (src/modules/node_types.F90:8-10)
 
 
 def _ptr(a, t=C.c_void_p):
@@ -95,28 +95,31 @@ class ElemEngine:
             self.L.hp3d_gpu_plan_destroy(self.plan)
             self.plan = None
 
-    def sizes(self, norder):
+    def sizes(self, norder, etype=MDLB):
         """(ni, nb, nint, nrdofH) for one element order vector, as stc_get_nrdof (stc.F90:94) / set_3D_int / celndof."""
         norder = _i32(norder)
         v = [C.c_int() for _ in range(4)]
-        _lib.check(self.L.hp3d_gpu_sizes(self.plan, _ptr(norder), *[C.byref(x) for x in v]))
+        _lib.check(self.L.hp3d_gpu_sizes_t(self.plan, int(etype), _ptr(norder), *[C.byref(x) for x in v]))
         return tuple(x.value for x in v)
 
-    def quad_points(self, norder, norient_edge, norient_face, xnod):
+    def quad_points(self, norder, norient_edge, norient_face, xnod, etype=None):
         norder, noe, nof = _i32(norder).reshape(-1, 19), _i32(norient_edge).reshape(-1, 12), _i32(norient_face).reshape(-1, 6)
         xnod = np.ascontiguousarray(xnod, dtype=np.float64)
         nel = norder.shape[0]
-        nint = max(self.sizes(norder[e])[2] for e in range(nel))
+        et = None if etype is None else _i32(np.broadcast_to(etype, (nel,)))
+        nint = max(self.sizes(norder[e], MDLB if et is None else et[e])[2] for e in range(nel))
         xq = np.zeros((nel, nint, 3))
-        _lib.check(self.L.hp3d_gpu_quad_points(self.plan, nel, None, _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod),
+        _lib.check(self.L.hp3d_gpu_quad_points(self.plan, nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod),
                                                int(xnod[0].size), _ptr(xq), C.c_longlong(nint * 3)))
         return xq
 
-    def elem_stc_batch(self, norder, norient_edge, norient_face, xnod, source_qp=None, out=None):
+    def elem_stc_batch(self, norder, norient_edge, norient_face, xnod, source_qp=None, out=None, etype=None):
         """elem + stc_fwd_wrapper for nel elements.
 
         norder (nel,19), norient_edge (nel,12), norient_face (nel,6): find_order / find_orient output;
         xnod (nel, nrdofH_max, 3): nodcor output (geometry dofs; row k = coordinates of dof k).
+        etype: None (all bricks), a scalar, or (nel,) element types MDLB / MDLP; a prism uses the first 15 / 9 / 5 entries
+        of its norder / norient_edge / norient_face rows.
         Returns dict(Aii (nel,ni,ni) [Fortran order per element: Aii[e].T is the column-major block], Bi, ASchur, BSchur,
         ni, nb, info).  All elements are padded to the largest ni/nb of the batch.
         """
@@ -125,11 +128,13 @@ class ElemEngine:
         xnod = np.ascontiguousarray(xnod, dtype=np.float64)
         nel = norder.shape[0]
         assert xnod.shape[0] == nel
+        et = None if etype is None else _i32(np.broadcast_to(etype, (nel,)))
         sz = {}
         for e in range(nel):
-            k = norder[e].tobytes()
+            t = MDLB if et is None else int(et[e])
+            k = bytes([t]) + norder[e].tobytes()
             if k not in sz:
-                sz[k] = self.sizes(norder[e])
+                sz[k] = self.sizes(norder[e], t)
         ni = max(s[0] for s in sz.values())
         nb = max(s[1] for s in sz.values())
         if out is None:
@@ -144,7 +149,7 @@ class ElemEngine:
         L.hp3d_gpu_elem_batch.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                           C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
                                           C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
-        rc = L.hp3d_gpu_elem_batch(self.plan, nel, None, _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(xnod[0].size),
+        rc = L.hp3d_gpu_elem_batch(self.plan, nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(xnod[0].size),
                                    _ptr(source_qp), src_ld, _ptr(Aii), Aii[0].size, _ptr(Bi), Bi[0].size, _ptr(AS), AS[0].size,
                                    _ptr(BS), BS[0].size, _ptr(nio), _ptr(nbo), _ptr(info))
         _lib.check(rc)
@@ -169,13 +174,14 @@ class ElemEngine:
         _lib.check(self.L.hp3d_gpu_stc_bwd_batch(int(self.complex), nel, ni, nb, _ptr(A), nb * ni, _ptr(B), nb, _ptr(x), ni, _ptr(xb), nb))
         return xb
 
-    def integrate_debug(self, norder, norient_edge, norient_face, xnod, source_qp=None):
+    def integrate_debug(self, norder, norient_edge, norient_face, xnod, source_qp=None, etype=MDLB):
         """Raw dense-phase input of one element (test hook): returns (W (planes,R,np), dims dict)."""
         norder, noe, nof = _i32(norder), _i32(norient_edge), _i32(norient_face)
         xnod = np.ascontiguousarray(xnod, dtype=np.float64)
         dims = np.zeros(8, np.int32)
-        f = self.L.hp3d_gpu_integrate_debug
-        f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
+        g = self.L.hp3d_gpu_integrate_debug_t
+        g.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
+        f = lambda plan, *a: g(plan, int(etype), *a)   # noqa: E731
         _lib.check(f(self.plan, _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), _ptr(source_qp), None, 0, _ptr(dims)))
         np_, nbp, nip, n, nb, ni, R, P = [int(v) for v in dims]
         ld = np_ if np_ else R
@@ -183,13 +189,14 @@ class ElemEngine:
         _lib.check(f(self.plan, _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), _ptr(source_qp), _ptr(W), W.size, _ptr(dims)))
         return W, dict(np=np_, nbp=nbp, nip=nip, n=n, nb=nb, ni=ni, R=R, planes=P)
 
-    def bench(self, norder, norient_edge, norient_face, xnod, reps=1, max_chunk=0, lanes=2):
+    def bench(self, norder, norient_edge, norient_face, xnod, reps=1, max_chunk=0, lanes=2, etype=None):
         """Device-resident throughput run (hp3d_gpu_bench): returns dict(ms_total, ms_integ, ms_dense, launches)."""
         norder, noe, nof = _i32(norder).reshape(-1, 19), _i32(norient_edge).reshape(-1, 12), _i32(norient_face).reshape(-1, 6)
         xnod = np.ascontiguousarray(xnod, dtype=np.float64)
         nel = norder.shape[0]
         t = [C.c_double() for _ in range(3)]
         ln = C.c_longlong()
-        _lib.check(self.L.hp3d_gpu_bench(self.plan, nel, _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(xnod[0].size), int(reps),
+        et = None if etype is None else _i32(np.broadcast_to(etype, (nel,)))
+        _lib.check(self.L.hp3d_gpu_bench_t(self.plan, nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(xnod[0].size), int(reps),
                                          int(max_chunk), int(lanes), C.byref(t[0]), C.byref(t[1]), C.byref(t[2]), C.byref(ln)))
         return dict(ms_total=t[0].value, ms_integ=t[1].value, ms_dense=t[2].value, launches=ln.value)

@@ -4,6 +4,7 @@
 #include "dense_pipeline.cuh"
 #include "formats.cuh"
 #include "forms.hpp"
+#include "forms_prism.hpp"
 #include "integ_kernels.cuh"
 
 #include <complex>
@@ -64,7 +65,7 @@ struct DenseWorkspace {
 // One element signature compiled and resident on the device.
 struct Signature {
   SigHost h;
-  double *d_tab = nullptr, *d_wq = nullptr, *d_CW = nullptr, *d_ones = nullptr;
+  double *d_tab = nullptr, *d_wq = nullptr, *d_CW = nullptr, *d_ones = nullptr, *d_ttab = nullptr;
   int *d_hdof = nullptr, *d_maps = nullptr, *d_crow = nullptr, *d_iota = nullptr;
   FamilyDesc *d_fam = nullptr; TermDesc *d_term = nullptr; SlotDesc *d_slot = nullptr; BlockDesc *d_block = nullptr; WorkItem *d_work = nullptr;
   // A lane = one complete set of per-chunk buffers.  Two lanes run on two streams so that the latency-bound steps of one
@@ -88,7 +89,7 @@ struct Signature {
   Lane lane[NLANE];
   int cap = 0;   // elements per lane
   ~Signature() {
-    cudaFree(d_tab); cudaFree(d_wq); cudaFree(d_CW); cudaFree(d_ones); cudaFree(d_hdof); cudaFree(d_maps); cudaFree(d_crow); cudaFree(d_iota);
+    cudaFree(d_tab); cudaFree(d_wq); cudaFree(d_CW); cudaFree(d_ones); cudaFree(d_ttab); cudaFree(d_hdof); cudaFree(d_maps); cudaFree(d_crow); cudaFree(d_iota);
     cudaFree(d_fam); cudaFree(d_term); cudaFree(d_slot); cudaFree(d_block); cudaFree(d_work);
     free_chunk();
   }
@@ -107,7 +108,8 @@ struct Signature {
   int upload(std::string &err) {
     if (dev_upload(h.tab, &d_tab, err) || dev_upload(h.wq, &d_wq, err) || dev_upload(h.hdof, &d_hdof, err) || dev_upload(h.maps, &d_maps, err) ||
         dev_upload(h.fam, &d_fam, err) || dev_upload(h.term, &d_term, err) || dev_upload(h.slot, &d_slot, err) ||
-        dev_upload(h.block, &d_block, err) || dev_upload(h.work, &d_work, err) || dev_upload(h.crow, &d_crow, err) || dev_upload(h.CW, &d_CW, err))
+        dev_upload(h.block, &d_block, err) || dev_upload(h.work, &d_work, err) || dev_upload(h.crow, &d_crow, err) || dev_upload(h.CW, &d_CW, err) ||
+        dev_upload(h.ttab, &d_ttab, err))
       return -2;
     const int n = std::max(h.ni, h.nb) + 1;
     std::vector<int> iota(n);
@@ -145,9 +147,22 @@ struct Signature {
 template <int NMAX> static cudaError_t tp3_configure() {
   return cudaFuncSetAttribute(tp3_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
+template <int NMAX> static cudaError_t tp2_configure() {
+  return cudaFuncSetAttribute(tp2_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
 static void launch_tp3(const Signature &S, const Tp3Args &A, int nel, cudaStream_t st) {
   dim3 grid((unsigned)S.h.work.size(), nel);
   const int off = (int)S.h.smem_u_off;
+  if (S.h.etype == 3) {   // prism: (triangle list) x (z table) families
+    switch (S.h.nmax) {
+      case 4: tp2_kernel<4><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, S.d_ttab, off); break;
+      case 6: tp2_kernel<6><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, S.d_ttab, off); break;
+      case 8: tp2_kernel<8><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, S.d_ttab, off); break;
+      default: tp2_kernel<10><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, S.d_ttab, off); break;
+    }
+    g_launches++;
+    return;
+  }
   switch (S.h.nmax) {
     case 4: tp3_kernel<4><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, off); break;
     case 6: tp3_kernel<6><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, off); break;
@@ -166,10 +181,12 @@ static void run_integration(Signature &S, Signature::Lane &L, const GeomParams &
   const long long P = h.cplx ? 2 : 1;
   SigTables sg;
   sg.tab = S.d_tab; sg.wq = S.d_wq; sg.hdof = S.d_hdof; sg.nH = h.nH; sg.nint = h.nint;
+  sg.ttab = S.d_ttab ? S.d_ttab + h.geo_toff : nullptr; sg.nT = h.geo_nT;
   for (int i = 0; i < 3; i++) sg.nq[i] = h.nq[i];
   cudaMemsetAsync(L.ws.b.info, 0, sizeof(int) * nel, st);
   const long long npts = (long long)nel * h.nint;
-  geom_fields_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(sg, gp, nel, d_xnod, 3LL * h.nH, d_src, L.d_WF, L.ws.b.info);
+  if (h.etype == 3) geom_fields_prism_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(sg, gp, nel, d_xnod, 3LL * h.nH, d_src, L.d_WF, L.ws.b.info);
+  else geom_fields_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(sg, gp, nel, d_xnod, 3LL * h.nH, d_src, L.d_WF, L.ws.b.info);
   g_launches++;
   Tp3Args A;
   A.tab = S.d_tab; A.fam = S.d_fam; A.term = S.d_term; A.slot = S.d_slot; A.block = S.d_block; A.work = S.d_work; A.maps = S.d_maps;
@@ -252,19 +269,24 @@ struct Plan {
     GeomParams g; g.kind = fp.kind; g.source = fp.source; g.icomp = fp.icomp; g.omega = fp.omega; g.eps = fp.eps; g.mu = fp.mu; g.sigma = fp.sigma;
     return g;
   }
-  static std::string key(const int *norder, const int *norie, const int *norif) {
-    std::string k((const char *)norder, 19 * sizeof(int));
-    k.append((const char *)norie, 12 * sizeof(int));
-    k.append((const char *)norif, 6 * sizeof(int));
+  // descriptor arrays keep the brick layout (19/12/6 ints per element); a prism uses the first 15/9/5 entries
+  static std::string key(int etype, const int *norder, const int *norie, const int *norif) {
+    const bool pr = etype == 3;
+    std::string k(1, (char)etype);
+    k.append((const char *)norder, (pr ? 15 : 19) * sizeof(int));
+    k.append((const char *)norie, (pr ? 9 : 12) * sizeof(int));
+    k.append((const char *)norif, (pr ? 5 : 6) * sizeof(int));
     return k;
   }
   // find or compile; device upload only when `device` is set
-  Signature *get(const int *norder, const int *norie, const int *norif, bool device, std::string &err) {
-    const std::string k = key(norder, norie, norif);
+  Signature *get(int etype, const int *norder, const int *norie, const int *norif, bool device, std::string &err) {
+    if (etype != 1 && etype != 3) { err = "unknown element type (HP3D_MDLB = 1 and HP3D_MDLP = 3 are implemented)"; return nullptr; }
+    const std::string k = key(etype, norder, norie, norif);
     auto it = sigs.find(k);
     if (it == sigs.end()) {
       std::unique_ptr<Signature> s(new Signature());
-      if (!compile_signature(fp, norder, norie, norif, s->h)) { err = s->h.err; return nullptr; }
+      const bool ok = etype == 3 ? compile_signature_prism(fp, norder, norie, norif, s->h) : compile_signature(fp, norder, norie, norif, s->h);
+      if (!ok) { err = s->h.err; return nullptr; }
       it = sigs.emplace(k, std::move(s)).first;
     }
     Signature *s = it->second.get();

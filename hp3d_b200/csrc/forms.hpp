@@ -40,6 +40,9 @@ static const int FACE_EDGES[6][4] = {{0, 1, 2, 3}, {4, 5, 6, 7}, {0, 9, 4, 8}, {
 
 struct SigHost {
   int kind = 0;
+  int etype = 1;               // HP3D_MDLB / HP3D_MDLP
+  std::vector<double> ttab;    // prism: pool of triangle-function tables, one block [3 comps][nT][nqt] per list
+  int geo_toff = 0, geo_nT = 0; // prism: pool offset / size of the geometry (H1) list
   int norder[19], norie[12], norif[6];
   int nq[3] = {0, 0, 0}, nint = 0;
   int nH = 0;                 // geometry dofs
@@ -88,6 +91,20 @@ struct BlockBuilder {
     }
     if (s < 0) { SlotDesc sl; sl.zA = zA; sl.zB = zB; sl.c[0] = c0; sl.c[1] = c1; S.slot.push_back(sl); s = B.ns++; }
     TermDesc t; t.dA = dA; t.dB = dB; t.field = field; t.slot = s; t.coef = coef;
+    S.term.push_back(t); B.nt++;
+  }
+  // prism variant: the A / B factor is (component tcA of the triangle table) x (z table, differentiated if zdA)
+  void addp(int tcA, int zdA, int tcB, int zdB, int field, double coef, double c0, double c1) {
+    if (coef == 0.0 || (c0 == 0.0 && c1 == 0.0)) return;
+    const FamilyDesc &fa = S.fam[B.famA], &fb = S.fam[B.famB];
+    const int zA = zdA ? (int)T_DH : fa.tab[2], zB = zdB ? (int)T_DH : fb.tab[2];
+    int s = -1;
+    for (int i = 0; i < B.ns; i++) {
+      const SlotDesc &sl = S.slot[B.s0 + i];
+      if (sl.zA == zA && sl.zB == zB && sl.c[0] == c0 && sl.c[1] == c1) { s = i; break; }
+    }
+    if (s < 0) { SlotDesc sl; sl.zA = zA; sl.zB = zB; sl.c[0] = c0; sl.c[1] = c1; S.slot.push_back(sl); s = B.ns++; }
+    TermDesc t; t.dA = tcA; t.dB = tcB; t.field = field; t.slot = s; t.coef = coef;
     S.term.push_back(t); B.nt++;
   }
   void finish() {

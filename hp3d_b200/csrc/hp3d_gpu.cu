@@ -100,6 +100,7 @@ int hp3d_gpu_init(int device) {
   CUDA_TRY(dense_configure<true>());
   CUDA_TRY(dense_configure<false>());
   CUDA_TRY(tp3_configure<4>()); CUDA_TRY(tp3_configure<6>()); CUDA_TRY(tp3_configure<8>()); CUDA_TRY(tp3_configure<10>());
+  CUDA_TRY(tp2_configure<4>()); CUDA_TRY(tp2_configure<6>()); CUDA_TRY(tp2_configure<8>()); CUDA_TRY(tp2_configure<10>());
   for (int i = 0; i < 2; i++)
     if (!g_lane_stream[i]) CUDA_TRY(cudaStreamCreateWithFlags(&g_lane_stream[i], cudaStreamNonBlocking));
   if (!g_copy) CUDA_TRY(cudaStreamCreateWithFlags(&g_copy, cudaStreamNonBlocking));
@@ -159,12 +160,16 @@ int hp3d_gpu_plan_destroy(int plan) {
 }
 
 int hp3d_gpu_sizes(int plan, const int *norder, int *ni, int *nb, int *nint, int *nrdofH) {
+  return hp3d_gpu_sizes_t(plan, HP3D_MDLB, norder, ni, nb, nint, nrdofH);
+}
+
+int hp3d_gpu_sizes_t(int plan, int etype, const int *norder, int *ni, int *nb, int *nint, int *nrdofH) {
   std::lock_guard<std::mutex> lk(g_mu);
   Plan *p = plan_of(plan);
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
   const int z12[12] = {0}, z6[6] = {0};
   std::string err;
-  Signature *s = p->get(norder, z12, z6, false, err);
+  Signature *s = p->get(etype, norder, z12, z6, false, err);
   if (!s) return fail(HP3D_EINVAL, "%s", err.c_str());
   if (ni) *ni = s->h.ni;
   if (nb) *nb = s->h.nb;
@@ -189,6 +194,46 @@ int hp3d_gpu_dof_map(int space, const int *norder, const int *norie, const int *
     if (fam) fam[k] = d[k].fam;
     if (sgn) sgn[k] = d[k].sgn;
     if (idx) for (int a = 0; a < 3; a++) idx[3 * k + a] = d[k].idx[a];
+  }
+  return n;
+}
+
+// pointwise values of the prism shape functions through the T x Z decomposition (host only; parity tests)
+int hp3d_gpu_prism_shape(int space, const int *norder, const int *norie, const int *norif, const double *xi, int cap, double *val, double *der) {
+  using namespace hp3d::detail;
+  TriList T0, T1;
+  std::vector<PrismDof> d;
+  switch (space) {
+    case 0: d = prism_dofs_H1(norder, norie, norif, T0); break;
+    case 1: d = prism_dofs_Hcurl(norder, norie, norif, T0, T1); break;
+    case 2: d = prism_dofs_Hdiv_faces(norder, norif, T0, T1); break;
+    case 3: d = prism_dofs_L2(norder, T0); break;
+    default: return fail(HP3D_EINVAL, "unknown space %d", space);
+  }
+  const int n = (int)d.size();
+  if (!val) return n;
+  if (cap < n) return fail(HP3D_EINVAL, "prism_shape: capacity %d < %d", cap, n);
+  const TriVals v0 = eval_list(T0, xi[0], xi[1]), v1 = eval_list(T1, xi[0], xi[1]);
+  const ZVals Z = eval_z(MAXN1D - 1, xi[2]);
+  for (int k = 0; k < n; k++) {
+    const PrismDof &q = d[k];
+    const double *t = (q.list == 0 ? v0 : v1).at(q.t), s = q.sgn;
+    double *V = val + 3 * k, *D = der ? der + 3 * k : nullptr;
+    if (space == 0) {          // val[0] = value ; der = gradient
+      V[0] = s * t[0] * Z.H[q.zi]; V[1] = V[2] = 0.0;
+      if (D) { D[0] = s * t[1] * Z.H[q.zi]; D[1] = s * t[2] * Z.H[q.zi]; D[2] = s * t[0] * Z.dH[q.zi]; }
+    } else if (space == 1) {   // val = E ; der = curl E
+      if (q.list == 0) { V[0] = s * t[0] * Z.H[q.zi]; V[1] = s * t[1] * Z.H[q.zi]; V[2] = 0.0;
+        if (D) { D[0] = -s * t[1] * Z.dH[q.zi]; D[1] = s * t[0] * Z.dH[q.zi]; D[2] = s * t[2] * Z.H[q.zi]; } }
+      else { V[0] = V[1] = 0.0; V[2] = s * t[0] * Z.Q[q.zi];
+        if (D) { D[0] = s * t[2] * Z.Q[q.zi]; D[1] = -s * t[1] * Z.Q[q.zi]; D[2] = 0.0; } }
+    } else if (space == 2) {   // val = V (face functions only) ; der[0] = div V
+      if (q.list == 0) { V[0] = V[1] = 0.0; V[2] = s * t[0] * Z.H[q.zi]; if (D) { D[0] = s * t[0] * Z.dH[q.zi]; D[1] = D[2] = 0.0; } }
+      else { V[0] = s * t[1] * Z.Q[q.zi]; V[1] = -s * t[0] * Z.Q[q.zi]; V[2] = 0.0; if (D) { D[0] = s * t[2] * Z.Q[q.zi]; D[1] = D[2] = 0.0; } }
+    } else {
+      V[0] = s * t[0] * Z.Q[q.zi]; V[1] = V[2] = 0.0;
+      if (D) D[0] = D[1] = D[2] = 0.0;
+    }
   }
   return n;
 }
@@ -226,8 +271,9 @@ int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, 
   // ---- group by signature
   std::map<std::string, std::vector<int>> groups;
   for (int e = 0; e < nel; e++) {
-    if (etype && etype[e] != HP3D_MDLB) return fail(HP3D_EINVAL, "element %d: only bricks (HP3D_MDLB) are implemented", e);
-    groups[Plan::key(norder + 19 * e, norie + 12 * e, norif + 6 * e)].push_back(e);
+    const int et = etype ? etype[e] : HP3D_MDLB;
+    if (et != HP3D_MDLB && et != HP3D_MDLP) return fail(HP3D_EINVAL, "element %d: element type %d is not implemented (bricks and prisms are)", e, et);
+    groups[Plan::key(et, norder + 19 * e, norie + 12 * e, norif + 6 * e)].push_back(e);
   }
   const GeomParams gp = p->geom();
   std::string err;
@@ -242,7 +288,7 @@ int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, 
   for (auto &g : groups) {
     const std::vector<int> &el = g.second;
     const int e0 = el[0];
-    Signature *S = p->get(norder + 19 * e0, norie + 12 * e0, norif + 6 * e0, true, err);
+    Signature *S = p->get(etype ? etype[e0] : HP3D_MDLB, norder + 19 * e0, norie + 12 * e0, norif + 6 * e0, true, err);
     if (!S) { rc = fail(HP3D_EINVAL, "element %d: %s", e0, err.c_str()); break; }
     if (xnod_ld < 3 * S->h.nH) { rc = fail(HP3D_EINVAL, "xnod_ld=%d < 3*nrdofH=%d", xnod_ld, 3 * S->h.nH); break; }
     int want = (int)el.size();
@@ -337,8 +383,7 @@ int hp3d_gpu_quad_points(int plan, int nel, const int *etype, const int *norder,
   std::string err;
   std::vector<double> f;
   for (int e = 0; e < nel; e++) {  // not a hot path: one element at a time
-    if (etype && etype[e] != HP3D_MDLB) return fail(HP3D_EINVAL, "element %d: only bricks are implemented", e);
-    Signature *S = p->get(norder + 19 * e, norie + 12 * e, norif + 6 * e, true, err);
+    Signature *S = p->get(etype ? etype[e] : HP3D_MDLB, norder + 19 * e, norie + 12 * e, norif + 6 * e, true, err);
     if (!S) return fail(HP3D_EINVAL, "element %d: %s", e, err.c_str());
     if (S->cap < 1 && S->reserve(1, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());
     const SigHost &h = S->h;
@@ -346,8 +391,10 @@ int hp3d_gpu_quad_points(int plan, int nel, const int *etype, const int *norder,
     CUDA_TRY(cudaMemcpyAsync(L.d_xnod, xnod + (size_t)e * xnod_ld, sizeof(double) * 3 * h.nH, cudaMemcpyHostToDevice, g_compute));
     SigTables sg;
     sg.tab = S->d_tab; sg.wq = S->d_wq; sg.hdof = S->d_hdof; sg.nH = h.nH; sg.nint = h.nint;
+    sg.ttab = S->d_ttab ? S->d_ttab + h.geo_toff : nullptr; sg.nT = h.geo_nT;
     for (int i = 0; i < 3; i++) sg.nq[i] = h.nq[i];
-    geom_fields_kernel<<<(h.nint + 127) / 128, 128, 0, g_compute>>>(sg, gp, 1, L.d_xnod, 3LL * h.nH, nullptr, L.d_WF, L.ws.b.info);
+    if (h.etype == HP3D_MDLP) geom_fields_prism_kernel<<<(h.nint + 127) / 128, 128, 0, g_compute>>>(sg, gp, 1, L.d_xnod, 3LL * h.nH, nullptr, L.d_WF, L.ws.b.info);
+    else geom_fields_kernel<<<(h.nint + 127) / 128, 128, 0, g_compute>>>(sg, gp, 1, L.d_xnod, 3LL * h.nH, nullptr, L.d_WF, L.ws.b.info);
     f.resize(3 * (size_t)h.nint);
     CUDA_TRY(cudaMemcpyAsync(f.data(), L.d_WF + (size_t)F_X * h.nint, sizeof(double) * 3 * h.nint, cudaMemcpyDeviceToHost, g_compute));
     CUDA_TRY(cudaStreamSynchronize(g_compute));
@@ -381,6 +428,12 @@ int hp3d_gpu_stc_bwd_batch(int cplx, int nel, int ni, int nb, const void *ASchur
 
 int hp3d_gpu_bench(int plan, int nel, const int *norder, const int *norie, const int *norif, const double *xnod, int xnod_ld, int reps,
                    int max_chunk, int lanes, double *ms_total, double *ms_integ, double *ms_dense, long long *launches) {
+  return hp3d_gpu_bench_t(plan, nel, nullptr, norder, norie, norif, xnod, xnod_ld, reps, max_chunk, lanes, ms_total, ms_integ, ms_dense, launches);
+}
+
+int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif, const double *xnod,
+                     int xnod_ld, int reps, int max_chunk, int lanes, double *ms_total, double *ms_integ, double *ms_dense,
+                     long long *launches) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
   Plan *p = plan_of(plan);
@@ -388,14 +441,14 @@ int hp3d_gpu_bench(int plan, int nel, const int *norder, const int *norie, const
   if (nel <= 0 || reps <= 0 || lanes < 1 || lanes > 2) return fail(HP3D_EINVAL, "bad sizes");
   if (p->fp.source == HP3D_SRC_TABLE) return fail(HP3D_EINVAL, "bench: table sources are not supported");
   std::map<std::string, std::vector<int>> groups;
-  for (int e = 0; e < nel; e++) groups[Plan::key(norder + 19 * e, norie + 12 * e, norif + 6 * e)].push_back(e);
+  for (int e = 0; e < nel; e++) groups[Plan::key(etype ? etype[e] : HP3D_MDLB, norder + 19 * e, norie + 12 * e, norif + 6 * e)].push_back(e);
   const GeomParams gp = p->geom();
   std::string err;
   struct Grp { Signature *S; double *dx; int n, chunk; };
   std::vector<Grp> gs;
   for (auto &g : groups) {
     const int e0 = g.second[0];
-    Signature *S = p->get(norder + 19 * e0, norie + 12 * e0, norif + 6 * e0, true, err);
+    Signature *S = p->get(etype ? etype[e0] : HP3D_MDLB, norder + 19 * e0, norie + 12 * e0, norif + 6 * e0, true, err);
     if (!S) return fail(HP3D_EINVAL, "%s", err.c_str());
     int want = (int)g.second.size();
     if (lanes == 2) want = (want + 1) / 2;
@@ -456,12 +509,17 @@ int hp3d_gpu_bench(int plan, int nel, const int *norder, const int *norie, const
 
 int hp3d_gpu_integrate_debug(int plan, const int *norder, const int *norie, const int *norif, const double *xnod, const void *source_qp,
                              double *W, long long cap_doubles, int *dims) {
+  return hp3d_gpu_integrate_debug_t(plan, HP3D_MDLB, norder, norie, norif, xnod, source_qp, W, cap_doubles, dims);
+}
+
+int hp3d_gpu_integrate_debug_t(int plan, int etype, const int *norder, const int *norie, const int *norif, const double *xnod,
+                               const void *source_qp, double *W, long long cap_doubles, int *dims) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
   Plan *p = plan_of(plan);
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
   std::string err;
-  Signature *S = p->get(norder, norie, norif, true, err);
+  Signature *S = p->get(etype, norder, norie, norif, true, err);
   if (!S) return fail(HP3D_EINVAL, "%s", err.c_str());
   if (S->cap < 1 && S->reserve(1, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());
   const SigHost &h = S->h;

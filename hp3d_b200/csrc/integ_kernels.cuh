@@ -51,7 +51,9 @@ struct GeomParams {
 struct SigTables {               // element-signature tables, device memory
   const double *tab;             // [3 axes][4 types][TABSZ] ; entry [i*nq + q]
   const double *wq;              // [3][MAXQ] 1-D weights
-  const int *hdof;               // [nH] geometry dofs: idx0 | idx1<<8 | idx2<<16 | (sign<0)<<24
+  const int *hdof;               // [nH] geometry dofs: idx0 | idx1<<8 | idx2<<16 | (sign<0)<<24   (prism: t | zi<<8 | (sign<0)<<24)
+  const double *ttab;            // prism: triangle tables of the geometry list [3][nT][nqt]
+  int nT;
   int nq[3];
   int nH;
   int nint;
@@ -71,6 +73,81 @@ __device__ inline void sin_potential_hess(double a, const double x[3], double &p
   h[1] = h[3] = a2 * c[0] * c[1] * s[2];
   h[2] = h[6] = a2 * c[0] * c[2] * s[1];
   h[5] = h[7] = a2 * c[1] * c[2] * s[0];
+}
+
+// All weight fields of one quadrature point from (x, J, w): determinant (Sarrus) and inverse by cofactors as
+// src/element/util/geom.F90:57-113, then the Piola maps folded into per-point fields.  J[c + 3*d] = dx_c/dxi_d.
+__device__ __forceinline__ void emit_fields(const GeomParams &gp, int e, int q, int nint, const double x[3], const double J[9], double w,
+                                            const double *__restrict__ src_tab, double *__restrict__ WF, int *__restrict__ info) {
+  const double det = J[0] * J[4] * J[8] + J[1] * J[5] * J[6] + J[2] * J[3] * J[7] - J[2] * J[4] * J[6] - J[0] * J[5] * J[7] - J[1] * J[3] * J[8];
+  if (!(det > 0.0)) info[e] = -1;
+  double Ji[9];  // Ji[a + 3*c] = dxi_a/dx_c
+  Ji[0] = (J[4] * J[8] - J[5] * J[7]) / det;
+  Ji[1] = (-J[1] * J[8] + J[2] * J[7]) / det;
+  Ji[2] = (J[1] * J[5] - J[2] * J[4]) / det;
+  Ji[3] = (J[5] * J[6] - J[3] * J[8]) / det;
+  Ji[4] = (J[0] * J[8] - J[2] * J[6]) / det;
+  Ji[5] = (-J[0] * J[5] + J[2] * J[3]) / det;
+  Ji[6] = (J[3] * J[7] - J[4] * J[6]) / det;
+  Ji[7] = (-J[0] * J[7] + J[1] * J[6]) / det;
+  Ji[8] = (J[0] * J[4] - J[1] * J[3]) / det;
+  double *F = WF + (long long)e * NFIELD * nint + q;
+  const long long fs = nint;
+  const double wd = w * det, wod = w / det;
+  for (int a = 0; a < 3; a++)
+    for (int b = a; b < 3; b++) {
+      double dd = 0, cc = 0;
+      for (int c = 0; c < 3; c++) { dd += Ji[a + 3 * c] * Ji[b + 3 * c]; cc += J[c + 3 * a] * J[c + 3 * b]; }
+      F[(F_D + sym_idx(a, b)) * fs] = wd * dd;
+      F[(F_C + sym_idx(a, b)) * fs] = wod * cc;
+    }
+  F[F_W * fs] = w;
+  F[F_WDET * fs] = wd;
+  for (int a = 0; a < 3; a++)
+    for (int c = 0; c < 3; c++) {
+      F[(F_WJI + 3 * a + c) * fs] = w * Ji[a + 3 * c];
+      F[(F_WJD + 3 * c + a) * fs] = wod * J[c + 3 * a];
+    }
+  for (int c = 0; c < 3; c++) F[(F_X + c) * fs] = x[c];
+  // ---- source term
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  if (gp.kind == 1 || gp.kind == 2) {  // Poisson: f(x)
+    double f = 0.0;
+    if (gp.source == 9) f = src_tab[(long long)e * nint + q];
+    else if (gp.source == 1) { double p, h[9]; sin_potential_hess(3.14159265358979323846, x, p, h); f = -(h[0] + h[4] + h[8]); }
+    s[0] = wd * f;
+  } else {  // Maxwell: complex vector zJ(x)
+    double jr[3] = {0, 0, 0}, ji[3] = {0, 0, 0};
+    if (gp.source == 9) {
+      const double *t = src_tab + ((long long)e * nint + q) * 6;
+      for (int c = 0; c < 3; c++) { jr[c] = t[2 * c]; ji[c] = t[2 * c + 1]; }
+    } else if (gp.source == 1) {
+      double p, h[9], cc[3];
+      sin_potential_hess(gp.omega, x, p, h);      // real profile; amplitude (1+i) applied below
+      const int ic = gp.icomp;
+      for (int c = 0; c < 3; c++) cc[c] = h[c + 3 * ic];
+      cc[ic] -= h[0] + h[4] + h[8];               // curl curl (p e_ic) = grad(d_ic p) - Laplace(p) e_ic
+      if (gp.kind == 4) {
+        // J = curl H - i w eps E, H = curl E / (-i w mu)  (MAXWELL/ULTRAWEAK_DPG/getf.F90)  => J = (i/(w mu)) cc(1+i) - i w eps p(1+i) e_ic
+        const double a = 1.0 / (gp.omega * gp.mu), b = gp.omega * gp.eps;
+        for (int c = 0; c < 3; c++) { jr[c] = -a * cc[c]; ji[c] = a * cc[c]; }   // i*(1+i) = -1 + i
+        jr[ic] += b * p; ji[ic] -= b * p;                                           // -i*(1+i) = 1 - i
+      } else {
+        // -i w J = curl(1/mu curl E) - (w^2 eps - i w sigma) E   (MAXWELL/GALERKIN/common/getf.F90:50-73)
+        // store g = -i w J directly (the load vector is -i w (J,F))
+        const double zr = gp.omega * gp.omega * gp.eps, zi = -gp.omega * gp.sigma;  // zb = zr + i zi
+        for (int c = 0; c < 3; c++) { jr[c] = cc[c] / gp.mu; ji[c] = cc[c] / gp.mu; }
+        // zb*(1+i)*p = (zr - zi) + i (zr + zi)
+        jr[ic] -= (zr - zi) * p; ji[ic] -= (zr + zi) * p;
+      }
+    }
+    for (int a = 0; a < 3; a++) {
+      double gr = 0, gi = 0;
+      for (int c = 0; c < 3; c++) { gr += Ji[a + 3 * c] * jr[c]; gi += Ji[a + 3 * c] * ji[c]; }
+      s[2 * a] = wd * gr; s[2 * a + 1] = wd * gi;
+    }
+  }
+  for (int i = 0; i < 6; i++) F[(F_SRC + i) * fs] = s[i];
 }
 
 // grid: ceil(nel*nint/128) x 1, block 128
@@ -104,77 +181,45 @@ __global__ void __launch_bounds__(128) geom_fields_kernel(SigTables sg, GeomPara
       J[c] += xc * d0; J[c + 3] += xc * d1; J[c + 6] += xc * d2;
     }
   }
-  // determinant (Sarrus) and inverse by cofactors, as src/element/util/geom.F90:57-113
-  const double det = J[0] * J[4] * J[8] + J[1] * J[5] * J[6] + J[2] * J[3] * J[7] - J[2] * J[4] * J[6] - J[0] * J[5] * J[7] - J[1] * J[3] * J[8];
-  if (!(det > 0.0)) info[e] = -1;
-  double Ji[9];  // Ji[a + 3*c] = dxi_a/dx_c
-  Ji[0] = (J[4] * J[8] - J[5] * J[7]) / det;
-  Ji[1] = (-J[1] * J[8] + J[2] * J[7]) / det;
-  Ji[2] = (J[1] * J[5] - J[2] * J[4]) / det;
-  Ji[3] = (J[5] * J[6] - J[3] * J[8]) / det;
-  Ji[4] = (J[0] * J[8] - J[2] * J[6]) / det;
-  Ji[5] = (-J[0] * J[5] + J[2] * J[3]) / det;
-  Ji[6] = (J[3] * J[7] - J[4] * J[6]) / det;
-  Ji[7] = (-J[0] * J[7] + J[1] * J[6]) / det;
-  Ji[8] = (J[0] * J[4] - J[1] * J[3]) / det;
   const double w = sg.wq[qx] * sg.wq[MAXQ + qy] * sg.wq[2 * MAXQ + qz];
-  double *F = WF + (long long)e * NFIELD * sg.nint + q;
-  const long long fs = sg.nint;
-  const double wd = w * det, wod = w / det;
-  for (int a = 0; a < 3; a++)
-    for (int b = a; b < 3; b++) {
-      double dd = 0, cc = 0;
-      for (int c = 0; c < 3; c++) { dd += Ji[a + 3 * c] * Ji[b + 3 * c]; cc += J[c + 3 * a] * J[c + 3 * b]; }
-      F[(F_D + sym_idx(a, b)) * fs] = wd * dd;
-      F[(F_C + sym_idx(a, b)) * fs] = wod * cc;
-    }
-  F[F_W * fs] = w;
-  F[F_WDET * fs] = wd;
-  for (int a = 0; a < 3; a++)
+  emit_fields(gp, e, q, sg.nint, x, J, w, src_tab, WF, info);
+}
+
+// Prism variant: geometry dofs are sign * T[t](x,y) * H[zi](z) with the triangle tables (value, d/dx, d/dy) of the
+// signature's geometry list in global memory; quadrature point q = qt + nqt*qz, weights wq[0..nqt) | wq[nqt..nqt+nqz).
+// grid: ceil(nel*nint/128), block 128
+__global__ void __launch_bounds__(128) geom_fields_prism_kernel(SigTables sg, GeomParams gp, int nel, const double *__restrict__ xnod,
+                                                                long long xnod_ld, const double *__restrict__ src_tab,
+                                                                double *__restrict__ WF, int *__restrict__ info) {
+  __shared__ double sH[TABSZ], sdH[TABSZ];
+  for (int i = threadIdx.x; i < TABSZ; i += blockDim.x) {
+    sH[i] = sg.tab[(2 * 4 + T_H) * TABSZ + i];
+    sdH[i] = sg.tab[(2 * 4 + T_DH) * TABSZ + i];
+  }
+  __syncthreads();
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)nel * sg.nint) return;
+  const int e = (int)(gid / sg.nint), q = (int)(gid % sg.nint);
+  const int nqt = sg.nq[0], nqz = sg.nq[2], qt = q % nqt, qz = q / nqt;
+  const double *xn = xnod + (long long)e * xnod_ld;
+  const double *Tv = sg.ttab, *Tx = sg.ttab + (long long)sg.nT * nqt, *Ty = sg.ttab + 2LL * sg.nT * nqt;
+  double x[3] = {0, 0, 0}, J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = 0; k < sg.nH; k++) {
+    const int d = sg.hdof[k];
+    const int t = d & 255, zi = (d >> 8) & 255;
+    const double sgn = (d >> 24) ? -1.0 : 1.0;
+    const double h = sgn * sH[zi * nqz + qz], dh = sgn * sdH[zi * nqz + qz];
+    const double tv = __ldg(Tv + t * nqt + qt), tx = __ldg(Tx + t * nqt + qt), ty = __ldg(Ty + t * nqt + qt);
+    const double v = tv * h, d0 = tx * h, d1 = ty * h, d2 = tv * dh;
+#pragma unroll
     for (int c = 0; c < 3; c++) {
-      F[(F_WJI + 3 * a + c) * fs] = w * Ji[a + 3 * c];
-      F[(F_WJD + 3 * c + a) * fs] = wod * J[c + 3 * a];
-    }
-  for (int c = 0; c < 3; c++) F[(F_X + c) * fs] = x[c];
-  // ---- source term
-  double s[6] = {0, 0, 0, 0, 0, 0};
-  if (gp.kind == 1 || gp.kind == 2) {  // Poisson: f(x)
-    double f = 0.0;
-    if (gp.source == 9) f = src_tab[(long long)e * sg.nint + q];
-    else if (gp.source == 1) { double p, h[9]; sin_potential_hess(3.14159265358979323846, x, p, h); f = -(h[0] + h[4] + h[8]); }
-    s[0] = wd * f;
-  } else {  // Maxwell: complex vector zJ(x)
-    double jr[3] = {0, 0, 0}, ji[3] = {0, 0, 0};
-    if (gp.source == 9) {
-      const double *t = src_tab + ((long long)e * sg.nint + q) * 6;
-      for (int c = 0; c < 3; c++) { jr[c] = t[2 * c]; ji[c] = t[2 * c + 1]; }
-    } else if (gp.source == 1) {
-      double p, h[9], cc[3];
-      sin_potential_hess(gp.omega, x, p, h);      // real profile; amplitude (1+i) applied below
-      const int ic = gp.icomp;
-      for (int c = 0; c < 3; c++) cc[c] = h[c + 3 * ic];
-      cc[ic] -= h[0] + h[4] + h[8];               // curl curl (p e_ic) = grad(d_ic p) - Laplace(p) e_ic
-      if (gp.kind == 4) {
-        // J = curl H - i w eps E, H = curl E / (-i w mu)  (MAXWELL/ULTRAWEAK_DPG/getf.F90)  => J = (i/(w mu)) cc(1+i) - i w eps p(1+i) e_ic
-        const double a = 1.0 / (gp.omega * gp.mu), b = gp.omega * gp.eps;
-        for (int c = 0; c < 3; c++) { jr[c] = -a * cc[c]; ji[c] = a * cc[c]; }   // i*(1+i) = -1 + i
-        jr[ic] += b * p; ji[ic] -= b * p;                                           // -i*(1+i) = 1 - i
-      } else {
-        // -i w J = curl(1/mu curl E) - (w^2 eps - i w sigma) E   (MAXWELL/GALERKIN/common/getf.F90:50-73)
-        // store g = -i w J directly (the load vector is -i w (J,F))
-        const double zr = gp.omega * gp.omega * gp.eps, zi = -gp.omega * gp.sigma;  // zb = zr + i zi
-        for (int c = 0; c < 3; c++) { jr[c] = cc[c] / gp.mu; ji[c] = cc[c] / gp.mu; }
-        // zb*(1+i)*p = (zr - zi) + i (zr + zi)
-        jr[ic] -= (zr - zi) * p; ji[ic] -= (zr + zi) * p;
-      }
-    }
-    for (int a = 0; a < 3; a++) {
-      double gr = 0, gi = 0;
-      for (int c = 0; c < 3; c++) { gr += Ji[a + 3 * c] * jr[c]; gi += Ji[a + 3 * c] * ji[c]; }
-      s[2 * a] = wd * gr; s[2 * a + 1] = wd * gi;
+      const double xc = xn[3 * k + c];
+      x[c] += xc * v;
+      J[c] += xc * d0; J[c + 3] += xc * d1; J[c + 6] += xc * d2;
     }
   }
-  for (int i = 0; i < 6; i++) F[(F_SRC + i) * fs] = s[i];
+  const double w = sg.wq[qt] * sg.wq[nqt + qz];
+  emit_fields(gp, e, q, sg.nint, x, J, w, src_tab, WF, info);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -205,6 +250,62 @@ struct Tp3Args {
   int nint;
   MatTarget mat[2];
 };
+
+// z contraction shared by the hexahedron and prism kernels; thread item = (kA, (iB,jB)), registers over kB.
+// sTabZ: the four z tables [type][TABSZ]; sU: [ns][nqz][nij] partial sums; lA = lA0 + strideA*kA, lB = ij + nij*kB.
+template <int NMAX>
+__device__ __forceinline__ void tp_stage2(const Tp3Args &A, const BlockDesc &B, const double *sTabZ, const double *sU, int e, int nqz,
+                                          int nij, int nBz, int nAz, int lA0, int strideA) {
+  const ChannelDesc c0 = B.ch[0], c1 = B.ch[1];
+  for (int it = threadIdx.x; it < nAz * nij; it += blockDim.x) {
+    const int ij = it % nij, kA = it / nij;
+    double acc0[NMAX], acc1[NMAX];
+#pragma unroll
+    for (int k = 0; k < NMAX; k++) { acc0[k] = 0.0; acc1[k] = 0.0; }
+    for (int s = 0; s < B.ns; s++) {
+      const SlotDesc S = A.slot[B.s0 + s];
+      const double *ZA = (sTabZ + S.zA * TABSZ) + kA * nqz;
+      const double *ZB = (sTabZ + S.zB * TABSZ);
+      const double *U = sU + s * nqz * nij + ij;
+      double v[NMAX];
+#pragma unroll
+      for (int qz = 0; qz < NMAX; qz++) v[qz] = (qz < nqz) ? ZA[qz] * U[qz * nij] : 0.0;
+#pragma unroll
+      for (int kB = 0; kB < NMAX; kB++) {
+        if (kB < nBz) {
+          double d = 0.0;
+#pragma unroll
+          for (int qz = 0; qz < NMAX; qz++)
+            if (qz < nqz) d += v[qz] * ZB[kB * nqz + qz];
+          acc0[kB] += S.c[0] * d;
+          acc1[kB] += S.c[1] * d;
+        }
+      }
+    }
+    // write out
+    const int lA = lA0 + strideA * kA;
+#pragma unroll
+    for (int ch = 0; ch < 2; ch++) {
+      const ChannelDesc C = ch ? c1 : c0;
+      if (C.mat < 0) continue;
+      long long row; double sg = 1.0;
+      if (C.rowmap >= 0) { int m = A.maps[C.rowmap + lA]; if (m == 0) continue; row = (m < 0 ? -m : m) - 1; if (m < 0) sg = -1.0; }
+      else row = C.row0 + lA;
+      const MatTarget M = A.mat[C.mat];
+      double *dst = M.base + (long long)e * M.batch + (long long)C.plane * M.plane + row * M.ld;
+#pragma unroll
+      for (int kB = 0; kB < NMAX; kB++) {
+        if (kB < nBz) {
+          const int lB = ij + nij * kB;
+          long long col; double sc = sg;
+          if (C.colmap >= 0) { int m = A.maps[C.colmap + lB]; if (m == 0) continue; col = (m < 0 ? -m : m) - 1; if (m < 0) sc = -sc; }
+          else col = C.col0 + lB;
+          dst[col] = sc * (ch ? acc1[kB] : acc0[kB]);
+        }
+      }
+    }
+  }
+}
 
 // dynamic smem: tables 12*TABSZ | T1 [nBx*nqy*nqz] | U [ns][nqz][nBx*nBy]   (sized by the host for the signature)
 template <int NMAX>
@@ -249,57 +350,48 @@ __global__ void __launch_bounds__(384) tp3_kernel(Tp3Args A, int smem_u_off) {
     }
     __syncthreads();
   }
-  // ---- stage 2: z contraction; thread item = (kA, iB, jB), registers over kB
-  const ChannelDesc c0 = B.ch[0], c1 = B.ch[1];
-  const int lA0 = iA + fa.n[0] * jA, strideA = fa.n[0] * fa.n[1];
-  for (int it = threadIdx.x; it < nAz * nij; it += blockDim.x) {
-    const int ij = it % nij, kA = it / nij;
-    double acc0[NMAX], acc1[NMAX];
-#pragma unroll
-    for (int k = 0; k < NMAX; k++) { acc0[k] = 0.0; acc1[k] = 0.0; }
-    for (int s = 0; s < B.ns; s++) {
-      const SlotDesc S = A.slot[B.s0 + s];
-      const double *ZA = tabp(2, S.zA) + kA * nqz;
-      const double *ZB = tabp(2, S.zB);
-      const double *U = sU + s * nqz * nij + ij;
-      double v[NMAX];
-#pragma unroll
-      for (int qz = 0; qz < NMAX; qz++) v[qz] = (qz < nqz) ? ZA[qz] * U[qz * nij] : 0.0;
-#pragma unroll
-      for (int kB = 0; kB < NMAX; kB++) {
-        if (kB < nBz) {
-          double d = 0.0;
-#pragma unroll
-          for (int qz = 0; qz < NMAX; qz++)
-            if (qz < nqz) d += v[qz] * ZB[kB * nqz + qz];
-          acc0[kB] += S.c[0] * d;
-          acc1[kB] += S.c[1] * d;
-        }
-      }
+  // ---- stage 2: z contraction
+  tp_stage2<NMAX>(A, B, sTab + 8 * TABSZ, sU, e, nqz, nij, nBz, nAz, iA + fa.n[0] * jA, fa.n[0] * fa.n[1]);
+}
+
+// Prism kernel: one CTA per (element, block, tA).  A family is a (triangle list) x (z table) grid:
+//   M[(tA,kA),(tB,kB)] = sum_{qt,qz} TA_cA[tA][qt] TB_cB[tB][qt] ZA[kA][qz] ZB[kB][qz] F(qt + nqt*qz)
+// stage 1 (per term): G[qt][qz] = TA_cA[tA][qt] * F[qt,qz] in shared memory, then U[slot][qz][tB] += coef * sum_qt TB_cB[tB][qt] G[qt][qz];
+// stage 2: the z contraction of the hexahedron kernel.  Triangle tables live in global memory (L1/L2-resident, read-only).
+// dynamic smem: z tables 4*TABSZ | G [nqt*nqz] | U [ns][nqz][nTB]
+template <int NMAX>
+__global__ void __launch_bounds__(384) tp2_kernel(Tp3Args A, const double *__restrict__ ttab, int smem_u_off) {
+  extern __shared__ __align__(16) double sm[];
+  double *sTabZ = sm, *sG = sm + 4 * TABSZ, *sU = sm + smem_u_off;
+  const int e = blockIdx.y;
+  const WorkItem wi = A.work[blockIdx.x];
+  const BlockDesc &B = A.block[wi.block];
+  const FamilyDesc fa = A.fam[B.famA], fb = A.fam[B.famB];
+  const int tA = wi.iA;
+  const int nqt = A.nq[0], nqz = A.nq[2];
+  const int nTA = fa.n[0], nTB = fb.n[0], nBz = fb.n[2], nAz = fa.n[2];
+  for (int i = threadIdx.x; i < 4 * TABSZ; i += blockDim.x) sTabZ[i] = A.tab[8 * TABSZ + i];
+  for (int i = threadIdx.x; i < B.ns * nqz * nTB; i += blockDim.x) sU[i] = 0.0;
+  __syncthreads();
+  const double *WFe = A.WF + (long long)e * NFIELD * A.nint;
+  for (int t = 0; t < B.nt; t++) {
+    const TermDesc T = A.term[B.t0 + t];
+    const double *TA = ttab + fa.tab[0] + ((long long)T.dA * nTA + tA) * nqt;
+    const double *TB = ttab + fb.tab[0] + (long long)T.dB * nTB * nqt;
+    const double *Fq = WFe + (long long)T.field * A.nint;
+    for (int o = threadIdx.x; o < nqt * nqz; o += blockDim.x) sG[o] = __ldg(TA + o % nqt) * Fq[o] * T.coef;   // [qz][qt]
+    __syncthreads();
+    double *U = sU + T.slot * nqz * nTB;
+    for (int o = threadIdx.x; o < nTB * nqz; o += blockDim.x) {
+      const int tB = o % nTB, qz = o / nTB;
+      const double *tb = TB + (long long)tB * nqt, *g = sG + qz * nqt;
+      double s = 0.0;
+      for (int qt = 0; qt < nqt; qt++) s += __ldg(tb + qt) * g[qt];
+      U[qz * nTB + tB] += s;
     }
-    // write out
-    const int lA = lA0 + strideA * kA;
-#pragma unroll
-    for (int ch = 0; ch < 2; ch++) {
-      const ChannelDesc C = ch ? c1 : c0;
-      if (C.mat < 0) continue;
-      long long row; double sg = 1.0;
-      if (C.rowmap >= 0) { int m = A.maps[C.rowmap + lA]; if (m == 0) continue; row = (m < 0 ? -m : m) - 1; if (m < 0) sg = -1.0; }
-      else row = C.row0 + lA;
-      const MatTarget M = A.mat[C.mat];
-      double *dst = M.base + (long long)e * M.batch + (long long)C.plane * M.plane + row * M.ld;
-#pragma unroll
-      for (int kB = 0; kB < NMAX; kB++) {
-        if (kB < nBz) {
-          const int lB = ij + nij * kB;
-          long long col; double sc = sg;
-          if (C.colmap >= 0) { int m = A.maps[C.colmap + lB]; if (m == 0) continue; col = (m < 0 ? -m : m) - 1; if (m < 0) sc = -sc; }
-          else col = C.col0 + lB;
-          dst[col] = sc * (ch ? acc1[kB] : acc0[kB]);
-        }
-      }
-    }
+    __syncthreads();
   }
+  tp_stage2<NMAX>(A, B, sTabZ, sU, e, nqz, nTB, nBz, nAz, tA, nTA);
 }
 
 // Element-independent rows of W (trace pairings): W[e][plane 0][crow[r]][0..ncol) = CW[r][0..ncol)

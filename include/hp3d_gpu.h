@@ -34,8 +34,11 @@ extern "C" {
 #define HP3D_MAXW_GAL 3  /* problems/MAXWELL/GALERKIN/elem_opt.F90:22      complex, stc LU       */
 #define HP3D_MAXW_UW 4   /* problems/MAXWELL/ULTRAWEAK_DPG/elem/elem_opt.F90:25  complex, stc Cholesky */
 
-/* element types (src/modules/node_types.F90): only the brick is implemented in this round */
+/* element types (src/modules/node_types.F90:8-10): hexahedron (brick) and triangular prism.  Per-element descriptor arrays
+ * always use the brick layout (19 orders, 12 edge orientations, 6 face orientations); a prism fills the first 15 / 9 / 5
+ * entries (9 edges: 6 triangle edges then 3 vertical; 2 triangle faces then 3 quad faces; middle node 10*p_xy + p_z). */
 #define HP3D_MDLB 1
+#define HP3D_MDLP 3
 
 /* test norms of the ultraweak Maxwell problem (problems/MAXWELL/ULTRAWEAK_DPG/modules/commonParam.F90) */
 #define HP3D_GRAPH_NORM 1
@@ -73,11 +76,12 @@ int hp3d_gpu_plan_destroy(int plan);
 
 /* Sizes for one element signature: ni/nb as stc_get_nrdof (stc.F90:94), nint = # volume quadrature points,
  * nrdofH = # geometry dofs (columns of xnod actually read). */
-int hp3d_gpu_sizes(int plan, const int *norder /*19*/, int *ni, int *nb, int *nint, int *nrdofH);
+int hp3d_gpu_sizes(int plan, const int *norder /*19*/, int *ni, int *nb, int *nint, int *nrdofH);   /* brick */
+int hp3d_gpu_sizes_t(int plan, int etype, const int *norder /*19*/, int *ni, int *nb, int *nint, int *nrdofH);
 
 /* The batched unit of work.  For e = 0..nel-1 (elements may differ in order and orientation; they are grouped
  * by signature internally):
- *   etype[e]             element type (HP3D_MDLB)
+ *   etype[e]             element type (HP3D_MDLB or HP3D_MDLP; NULL = all bricks)
  *   norder[19*e..]       find_order            (src/datstrs/find_order.F90:5)
  *   norient_edge[12*e..] , norient_face[6*e..]  find_orient (find_orient.F90:8)
  *   xnod[xnod_ld*e..]    nodcor: geometry dofs, (3, nrdofH) column-major (src/constrs/nodcor.F90:19)
@@ -119,6 +123,11 @@ int hp3d_gpu_bench(int plan, int nel, const int *norder, const int *norient_edge
                    const double *xnod, int xnod_ld, int reps, int max_chunk, int lanes, double *ms_total,
                    double *ms_integ, double *ms_dense, long long *launches);
 
+/* same, with per-element element types (NULL = all bricks) */
+int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, const int *norient_edge, const int *norient_face,
+                     const double *xnod, int xnod_ld, int reps, int max_chunk, int lanes, double *ms_total, double *ms_integ,
+                     double *ms_dense, long long *launches);
+
 /* Page-locked host memory for the caller's result arrays (so that the D2H copies of hp3d_gpu_elem_batch are
  * asynchronous DMA transfers that overlap the next chunk's kernels).  Pageable buffers work too, only slower. */
 void *hp3d_gpu_host_alloc(long long bytes);
@@ -130,6 +139,12 @@ void hp3d_gpu_host_free(void *p);
  * Returns the number of dofs (or a negative error); arrays may be NULL to query the count. */
 int hp3d_gpu_dof_map(int space, const int *norder, const int *norient_edge, const int *norient_face, int cap, int *fam,
                      int *idx, int *sgn);
+/* Prism analogue (host only): values of the shape functions of one prism at the master point xi[3], evaluated through the
+ * product's (triangle function) x (1-D table) decomposition, reference dof order (src/element/shape_1/Prism.F90).
+ *   space 0: val[3k] = phi_k, der[3k..] = grad ; 1: val = E_k, der = curl E_k ; 2: face functions only, val = V_k, der[3k] = div ;
+ *   3: val[3k] = q_k.  Returns the number of functions; val == NULL queries the count. */
+int hp3d_gpu_prism_shape(int space, const int *norder, const int *norient_edge, const int *norient_face, const double *xi, int cap,
+                         double *val, double *der);
 /* 1-D Gauss rule on [0,1] (nq points) and the tables H[(p+1) x nq], dH[(p+1) x nq], Q[p x nq] evaluated at it */
 int hp3d_gpu_tables_1d(int p, int nq, double *x, double *w, double *H, double *dH, double *Q);
 
@@ -138,6 +153,9 @@ int hp3d_gpu_tables_1d(int p, int nq, double *x, double *w, double *H, double *d
  * {np, nbp, nip, n, nb, ni, R, planes}.  For non-DPG plans the buffer is Am (planes x M x M), dims[0] = 0. */
 int hp3d_gpu_integrate_debug(int plan, const int *norder, const int *norient_edge, const int *norient_face,
                              const double *xnod, const void *source_qp, double *W, long long cap_doubles, int *dims);
+
+int hp3d_gpu_integrate_debug_t(int plan, int etype, const int *norder, const int *norient_edge, const int *norient_face,
+                               const double *xnod, const void *source_qp, double *W, long long cap_doubles, int *dims);
 
 /* Test hook: run only the dense phase (DPG normal equations + static condensation) on caller-provided
  * Gram / enriched stiffness matrices.  G: (n x n) Hermitian, upper triangle read; Bm: n x (nb+ni+1), columns

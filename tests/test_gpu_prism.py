@@ -1,0 +1,138 @@
+"""GPU parity for TRIANGULAR PRISMS (BASELINE.json configs[4]: hp meshes of hexahedra and prisms): the CUDA path through the
+C ABI against the CPU oracle's prism branch on the same seeded inputs.  Tolerances as in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from tests.test_oracle_prism import PV, prism_signature
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def prism_xnod(nH, rng, h=0.5, curved=0.0):
+    """Geometry dofs of a prism: an affine image of the master prism, jittered vertices, optional higher-order dofs."""
+    T = np.eye(3) + rng.normal(size=(3, 3)) * 0.15
+    X = np.zeros((nH, 3))
+    X[:6] = h * (PV @ T.T) + rng.uniform(0, 0.3, 3) + rng.uniform(-0.05 * h, 0.05 * h, (6, 3))
+    if curved:
+        X[6:] = rng.uniform(-curved * h, curved * h, (nH - 6, 3))
+    return X
+
+
+def _engine(kind, **kw):
+    from hp3d_b200.api import ElemEngine
+    return ElemEngine(kind, **kw)
+
+
+@pytest.mark.parametrize("p,pz,curved", [(1, 1, 0.0), (2, 2, 0.0), (2, 3, 0.02), (3, 2, 0.02)])
+def test_prism_uw_integration_vs_oracle(oracle, gpu, p, pz, curved):
+    """Gram matrix, enriched stiffness, trace pairings and load of ultraweak Maxwell on a prism, straight out of the
+    integration kernels, vs the oracle's BLAS3 restatement of elem_opt.F90:236-768."""
+    oracle.set_maxp(8)
+    P = oracle.MDLP
+    rng = np.random.default_rng(300 + 10 * p + pz)
+    no, ne, nf = prism_signature(rng, p, pz)
+    nH = oracle.celndof(no, P)[0]
+    X = prism_xnod(nH, rng, curved=curved)
+    om = 2 * np.pi
+    prm = oracle.default_params(omega=om)
+    A, b, G, S = oracle.elem(oracle.MAXW_UW, no, ne, nf, X, prm, want_dpg=True, etype=P)
+    eng = _engine(4, omega=om, maxp=8)
+    W, d = eng.integrate_debug(no, ne, nf, X, etype=P)
+    n, nb, ni, np_, nbp = d["n"], d["nb"], d["ni"], d["np"], d["nbp"]
+    nEE = n // 2
+    assert G.shape[0] == n and S.shape[1] == ni + nb + 1
+    Wc = W[0] + 1j * W[1]
+    Gi = np.tril(Wc[:n, :n]); Gi = Gi + np.tril(Gi, -1).conj().T
+    perm = np.empty(n, int); perm[0::2] = np.arange(nEE); perm[1::2] = nEE + np.arange(nEE)
+    Gg = Gi[np.ix_(perm, perm)]
+    Gu = np.triu(G); Go = Gu + np.triu(Gu, 1).conj().T
+    assert relerr(Gg, Go) < 1e-13, relerr(Gg, Go)
+    rows = np.r_[np_ + nbp + np.arange(ni), np_ + np.arange(nb), np_ + nbp + ni]
+    Bg = Wc[rows][:, :n].conj().T[perm]
+    assert relerr(Bg[:, :ni], S[:, :ni]) < 1e-13, relerr(Bg[:, :ni], S[:, :ni])          # trace pairings
+    assert relerr(Bg[:, ni:ni + nb], S[:, ni:ni + nb]) < 1e-13
+    assert relerr(Bg[:, -1], S[:, -1]) < 1e-13                                             # load
+    eng.close()
+
+
+CASES = [(1, 1, 1), (1, 2, 2), (1, 3, 2), (1, 4, 3),
+         (2, 1, 1), (2, 2, 2), (2, 3, 2),
+         (3, 1, 1), (3, 2, 2), (3, 3, 3), (3, 4, 2),
+         (4, 1, 1), (4, 2, 2), (4, 3, 2), (4, 2, 3)]
+
+
+@pytest.mark.parametrize("kind,p,pz", CASES)
+def test_prism_condensed_vs_oracle(oracle, gpu, kind, p, pz):
+    """elem + stc_fwd_wrapper for prisms through hp3d_gpu_elem_batch vs the oracle: random edge / face orientations,
+    non-uniform node orders for the second element, jittered and slightly curved geometry."""
+    oracle.set_maxp(8)
+    oracle.use_blas(True)
+    P = oracle.MDLP
+    rng = np.random.default_rng(5000 + 100 * kind + 10 * p + pz)
+    nel = 3
+    sig = [prism_signature(rng, p, pz, uniform=(e != 1)) for e in range(nel)]
+    norder = np.stack([s[0] for s in sig]); norie = np.stack([s[1] for s in sig]); norif = np.stack([s[2] for s in sig])
+    nHs = [oracle.celndof(norder[e], P)[0] for e in range(nel)]
+    X = np.zeros((nel, max(nHs), 3))
+    for e in range(nel):
+        X[e, :nHs[e]] = prism_xnod(nHs[e], rng, curved=0.01 if p > 1 else 0.0)
+    om = 2 * np.pi if kind == 4 else (np.pi if kind == 3 else 1.0)
+    prm = oracle.default_params(omega=om)
+    eng = _engine(kind, omega=om, maxp=8)
+    res = eng.elem_stc_batch(norder, norie, norif, X, etype=P)
+    assert (res["info"] == 0).all(), res["info"]
+    for e in range(nel):
+        Aii, Bi, AS, BS = eng.unpack(res, e)
+        rA, rB, rAS, rBS = oracle.condensed(kind, norder[e], norie[e], norif[e], X[e, :nHs[e]], prm, etype=P)
+        assert Aii.shape == rA.shape and AS.shape == rAS.shape
+        assert relerr(Aii, rA) < 1e-12, (e, relerr(Aii, rA))
+        assert relerr(Bi, rB) < 1e-12, (e, relerr(Bi, rB))
+        if AS.size:
+            Afull, bfull = oracle.elem(kind, norder[e], norie[e], norif[e], X[e, :nHs[e]], prm, etype=P)
+            perm, ni, nb = oracle.stc_partition(kind, norder[e], P)
+            Ap = Afull[np.ix_(perm, perm)]; bp = bfull[perm]
+            Abb, Abi = Ap[ni:, ni:], Ap[ni:, :ni]
+            assert relerr(Abb @ AS, Abi) < 1e-12
+            assert relerr(Abb @ BS, bp[ni:]) < 1e-12
+    eng.close()
+
+
+def test_mixed_hexa_prism_batch(oracle, gpu):
+    """One call holding bricks and prisms of different orders (the hp-mesh situation of configs[4])."""
+    from tests.util import hexa_xnod, random_signature
+    oracle.set_maxp(8)
+    rng = np.random.default_rng(77)
+    B, P = oracle.MDLB, oracle.MDLP
+    items = []
+    for e in range(6):
+        if e % 2 == 0:
+            no, ne, nf = random_signature(rng, pmax=3)
+            nH = oracle.celndof(no, B)[0]
+            items.append((B, no, ne, nf, hexa_xnod(nH, h=0.4, jitter=0.1, rng=rng)))
+        else:
+            no, ne, nf = prism_signature(rng, int(rng.integers(1, 4)), int(rng.integers(1, 4)), uniform=False)
+            nH = oracle.celndof(no, P)[0]
+            items.append((P, no, ne, nf, prism_xnod(nH, rng)))
+    nel = len(items)
+    et = np.array([it[0] for it in items], np.int32)
+    norder = np.stack([it[1] for it in items]); norie = np.stack([it[2] for it in items]); norif = np.stack([it[3] for it in items])
+    X = np.zeros((nel, max(it[4].shape[0] for it in items), 3))
+    for e, it in enumerate(items):
+        X[e, :it[4].shape[0]] = it[4]
+    for kind in (1, 4):
+        om = 2 * np.pi if kind == 4 else 1.0
+        prm = oracle.default_params(omega=om)
+        eng = _engine(kind, omega=om, maxp=8)
+        res = eng.elem_stc_batch(norder, norie, norif, X, etype=et)
+        assert (res["info"] == 0).all()
+        for e, it in enumerate(items):
+            Aii, Bi, AS, BS = eng.unpack(res, e)
+            rA, rB, _, _ = oracle.condensed(kind, it[1], it[2], it[3], it[4], prm, etype=it[0])
+            assert Aii.shape == rA.shape
+            assert relerr(Aii, rA) < 1e-12, (kind, e, relerr(Aii, rA))
+            assert relerr(Bi, rB) < 1e-12, (kind, e)
+        eng.close()
