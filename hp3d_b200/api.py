@@ -102,6 +102,12 @@ class ElemEngine:
         _lib.check(self.L.hp3d_gpu_sizes_t(self.plan, int(etype), _ptr(norder), *[C.byref(x) for x in v]))
         return tuple(x.value for x in v)
 
+    def sig_dims(self, norder, norient_edge, norient_face, etype=MDLB):
+        """dict(ntest, ni, nb, nint, nrdofH, np, nbp, nip) of one element signature (host only)."""
+        d = np.zeros(8, np.int32)
+        _lib.check(self.L.hp3d_gpu_sig_dims(self.plan, int(etype), _ptr(_i32(norder)), _ptr(_i32(norient_edge)), _ptr(_i32(norient_face)), _ptr(d)))
+        return dict(zip(("ntest", "ni", "nb", "nint", "nrdofH", "np", "nbp", "nip"), (int(v) for v in d)))
+
     def quad_points(self, norder, norient_edge, norient_face, xnod, etype=None):
         norder, noe, nof = _i32(norder).reshape(-1, 19), _i32(norient_edge).reshape(-1, 12), _i32(norient_face).reshape(-1, 6)
         xnod = np.ascontiguousarray(xnod, dtype=np.float64)

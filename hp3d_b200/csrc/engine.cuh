@@ -31,32 +31,70 @@ template <class T> static int dev_upload(const std::vector<T> &h, T **d, std::st
   return 0;
 }
 
+// One device allocation + one pinned host allocation shared by ALL signatures of the process: element groups are
+// processed one after the other, so a signature only *binds* its chunk buffers into the arena (pointer arithmetic, no
+// cudaMalloc / cudaFree per signature).  hp meshes produce thousands of signatures (order x orientation combinations).
+struct Arena {
+  char *d = nullptr, *h = nullptr;
+  size_t dcap = 0, hcap = 0;
+  const void *owner = nullptr;   // signature whose buffers are currently bound
+  int owner_batch = 0;
+  int ensure(size_t dbytes, size_t hbytes, std::string &err) {
+    if (dbytes > dcap) {
+      cudaDeviceSynchronize();
+      cudaFree(d); d = nullptr; dcap = 0; owner = nullptr;
+      HP3D_CK(cudaMalloc((void **)&d, dbytes));
+      dcap = dbytes;
+    }
+    if (hbytes > hcap) {
+      cudaDeviceSynchronize();
+      cudaFreeHost(h); h = nullptr; hcap = 0; owner = nullptr;
+      HP3D_CK(cudaMallocHost((void **)&h, hbytes));
+      hcap = hbytes;
+    }
+    return 0;
+  }
+  void release() { cudaFree(d); cudaFreeHost(h); d = h = nullptr; dcap = hcap = 0; owner = nullptr; }
+};
+static Arena g_arena;
+
+struct Bump {   // 256-byte aligned carving; with base == nullptr it only measures
+  char *base; size_t off = 0;
+  explicit Bump(char *b) : base(b) {}
+  template <class T> T *take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T *p = base ? (T *)(base + off) : nullptr;
+    off += sizeof(T) * n;
+    return p;
+  }
+};
+
 struct DenseWorkspace {
   DenseDims d;
   DenseBuffers b;
-  int cap = 0;  // elements
-  void release() {
-    cudaFree(b.W); cudaFree(b.Am); cudaFree(b.LH); cudaFree(b.Linv); cudaFree(b.LinvH); cudaFree(b.LinvS); cudaFree(b.LinvSH); cudaFree(b.info);
-    b = DenseBuffers{}; cap = 0;
-  }
-  static size_t bytes_per_element(const DenseDims &d) {
-    const size_t P = d.planes(), lp = d.linv_plane(), ns = d.nsteps_stc() ? d.nsteps_stc() : 1;
-    return sizeof(double) * P * ((d.dpg ? d.w_plane() : 0) + d.a_plane() + (d.lh_plane() ? d.lh_plane() : 1) + 2 * lp + 2 * lp * ns) + sizeof(int);
-  }
-  int reserve(const DenseDims &dims, int batch, std::string &err) {
-    release();
+  char *owned_base = nullptr;   // non-null: stand-alone allocation (test hook); otherwise the buffers are bound into the arena
+  void release() { cudaFree(owned_base); owned_base = nullptr; b = DenseBuffers{}; }
+  void bind(const DenseDims &dims, int batch, Bump &m) {
     d = dims;
-    const size_t P = d.planes(), lp = d.linv_plane();
-    if (d.dpg) HP3D_CK(cudaMalloc(&b.W, sizeof(double) * P * d.w_plane() * batch));
-    HP3D_CK(cudaMalloc(&b.Am, sizeof(double) * P * d.a_plane() * batch));
-    HP3D_CK(cudaMalloc(&b.LH, sizeof(double) * P * (d.lh_plane() ? d.lh_plane() : 1) * batch));
-    HP3D_CK(cudaMalloc(&b.Linv, sizeof(double) * P * lp * batch));
-    HP3D_CK(cudaMalloc(&b.LinvH, sizeof(double) * P * lp * batch));
-    const size_t ns = d.nsteps_stc() ? d.nsteps_stc() : 1;
-    HP3D_CK(cudaMalloc(&b.LinvS, sizeof(double) * P * lp * ns * batch));
-    HP3D_CK(cudaMalloc(&b.LinvSH, sizeof(double) * P * lp * ns * batch));
-    HP3D_CK(cudaMalloc(&b.info, sizeof(int) * batch));
-    cap = batch;
+    const size_t P = d.planes(), lp = d.linv_plane(), ns = d.nsteps_stc() ? d.nsteps_stc() : 1;
+    b.W = d.dpg ? m.take<double>(P * d.w_plane() * batch) : nullptr;
+    b.Am = m.take<double>(P * d.a_plane() * batch);
+    b.LH = m.take<double>(P * (d.lh_plane() ? d.lh_plane() : 1) * batch);
+    b.Linv = m.take<double>(P * lp * batch);
+    b.LinvH = m.take<double>(P * lp * batch);
+    b.LinvS = m.take<double>(P * lp * ns * batch);
+    b.LinvSH = m.take<double>(P * lp * ns * batch);
+    b.info = m.take<int>(batch);
+  }
+  int reserve(const DenseDims &dims, int batch, std::string &err) {   // stand-alone allocation (dense_debug_run)
+    release();
+    Bump meas(nullptr);
+    bind(dims, batch, meas);
+    char *base = nullptr;
+    HP3D_CK(cudaMalloc((void **)&base, meas.off + 256));
+    Bump m(base);
+    bind(dims, batch, m);
+    owned_base = base;
     return 0;
   }
 };
@@ -77,33 +115,44 @@ struct Signature {
     struct Out { double *Aii = nullptr, *Bi = nullptr, *AS = nullptr, *BS = nullptr; int *info = nullptr, *h_info = nullptr; };  // h_info: pinned
     Out out[2];   // chunk outputs (device staging), double-buffered: the D2H of one chunk overlaps the lane's next chunk
     double *h_xnod = nullptr, *h_src = nullptr;                          // pinned host staging of the chunk inputs
-    void release() {
-      ws.release();
-      cudaFree(d_WF); cudaFree(d_xnod); cudaFree(d_src);
-      for (int i = 0; i < 2; i++) { cudaFree(out[i].Aii); cudaFree(out[i].Bi); cudaFree(out[i].AS); cudaFree(out[i].BS); cudaFree(out[i].info); cudaFreeHost(out[i].h_info); out[i] = Out(); }
-      cudaFreeHost(h_xnod); cudaFreeHost(h_src);
-      d_WF = d_xnod = d_src = nullptr; h_xnod = h_src = nullptr;
-    }
   };
   static constexpr int NLANE = 2;
   Lane lane[NLANE];
-  int cap = 0;   // elements per lane
+  int cap = 0;   // elements per lane currently bound in the arena (0: not bound)
   ~Signature() {
     cudaFree(d_tab); cudaFree(d_wq); cudaFree(d_CW); cudaFree(d_ones); cudaFree(d_ttab); cudaFree(d_hdof); cudaFree(d_maps); cudaFree(d_crow); cudaFree(d_iota);
     cudaFree(d_fam); cudaFree(d_term); cudaFree(d_slot); cudaFree(d_block); cudaFree(d_work);
-    free_chunk();
-  }
-  void free_chunk() {
-    for (int i = 0; i < NLANE; i++) lane[i].release();
-    cap = 0;
+    if (g_arena.owner == this) g_arena.owner = nullptr;
   }
   int ns() const { return h.cplx ? 2 : 1; }
   size_t src_doubles() const { return (size_t)h.nint * (h.cplx ? 6 : 1); }
-  size_t bytes_per_element() const {   // device bytes per element of ONE lane
+  // carve (or, with null bases, measure) the chunk buffers of both lanes for `batch` elements per lane
+  void layout(int batch, Bump &dm, Bump &hm) {
     const size_t NS = ns();
-    return DenseWorkspace::bytes_per_element(h.dims) +
-           sizeof(double) * ((size_t)NFIELD * h.nint + 3 * (size_t)h.nH + src_doubles() +
-                             2 * NS * ((size_t)h.ni * h.ni + h.ni + (size_t)h.nb * h.ni + h.nb + 2));
+    for (int i = 0; i < NLANE; i++) {
+      Lane &L = lane[i];
+      L.ws.bind(h.dims, batch, dm);
+      L.d_WF = dm.take<double>((size_t)NFIELD * h.nint * batch);
+      L.d_xnod = dm.take<double>((size_t)3 * h.nH * batch);
+      L.d_src = dm.take<double>(src_doubles() * batch);
+      for (int o = 0; o < 2; o++) {
+        L.out[o].Aii = dm.take<double>(NS * (size_t)h.ni * h.ni * batch);
+        L.out[o].Bi = dm.take<double>(NS * (size_t)h.ni * batch);
+        L.out[o].AS = dm.take<double>(NS * ((size_t)h.nb * h.ni + 1) * batch);
+        L.out[o].BS = dm.take<double>(NS * ((size_t)h.nb + 1) * batch);
+        L.out[o].info = dm.take<int>(batch);
+        L.out[o].h_info = hm.take<int>(batch);
+      }
+      L.h_xnod = hm.take<double>((size_t)3 * h.nH * batch);
+      L.h_src = hm.take<double>(src_doubles() * batch);
+    }
+  }
+  size_t bytes_per_element() {   // device bytes per element of ONE lane (asymptotic; alignment slack excluded)
+    Bump d1(nullptr), h1(nullptr), d2(nullptr), h2(nullptr);
+    Lane keep[NLANE] = {lane[0], lane[1]};
+    layout(1, d1, h1); layout(65, d2, h2);
+    lane[0] = keep[0]; lane[1] = keep[1];
+    return (d2.off - d1.off) / 64 / NLANE + 1;
   }
   int upload(std::string &err) {
     if (dev_upload(h.tab, &d_tab, err) || dev_upload(h.wq, &d_wq, err) || dev_upload(h.hdof, &d_hdof, err) || dev_upload(h.maps, &d_maps, err) ||
@@ -118,30 +167,23 @@ struct Signature {
     if (dev_upload(iota, &d_iota, err) || dev_upload(ones, &d_ones, err)) return -2;
     return 0;
   }
+  // bind the chunk buffers for `batch` elements per lane into the shared arena (no-op if they are still bound)
   int reserve(int batch, std::string &err) {
-    if (batch <= cap) return 0;
-    free_chunk();
-    const size_t NS = ns();
-    for (int i = 0; i < NLANE; i++) {
-      Lane &L = lane[i];
-      if (int rc = L.ws.reserve(h.dims, batch, err)) return rc;
-      HP3D_CK(cudaMalloc(&L.d_WF, sizeof(double) * NFIELD * h.nint * batch));
-      HP3D_CK(cudaMalloc(&L.d_xnod, sizeof(double) * 3 * h.nH * batch));
-      HP3D_CK(cudaMalloc(&L.d_src, sizeof(double) * src_doubles() * batch));
-      for (int o = 0; o < 2; o++) {
-        HP3D_CK(cudaMalloc(&L.out[o].Aii, sizeof(double) * NS * (size_t)h.ni * h.ni * batch));
-        HP3D_CK(cudaMalloc(&L.out[o].Bi, sizeof(double) * NS * h.ni * batch));
-        HP3D_CK(cudaMalloc(&L.out[o].AS, sizeof(double) * NS * ((size_t)h.nb * h.ni + 1) * batch));
-        HP3D_CK(cudaMalloc(&L.out[o].BS, sizeof(double) * NS * (h.nb + 1) * batch));
-        HP3D_CK(cudaMalloc(&L.out[o].info, sizeof(int) * batch));
-        HP3D_CK(cudaMallocHost(&L.out[o].h_info, sizeof(int) * batch));
-      }
-      HP3D_CK(cudaMallocHost(&L.h_xnod, sizeof(double) * 3 * h.nH * batch));
-      HP3D_CK(cudaMallocHost(&L.h_src, sizeof(double) * src_doubles() * batch));
-    }
+    if (g_arena.owner == this && batch <= g_arena.owner_batch) { cap = g_arena.owner_batch; return 0; }
+    Bump dmeas(nullptr), hmeas(nullptr);
+    layout(batch, dmeas, hmeas);
+    // grow geometrically so that a sequence of slightly larger signatures does not reallocate every time
+    size_t dneed = dmeas.off + 256, hneed = hmeas.off + 256;
+    if (dneed > g_arena.dcap) dneed = std::max(dneed, g_arena.dcap + g_arena.dcap / 4);
+    if (hneed > g_arena.hcap) hneed = std::max(hneed, g_arena.hcap + g_arena.hcap / 4);
+    if (int rc = g_arena.ensure(dneed, hneed, err)) { cap = 0; return rc; }
+    Bump dm(g_arena.d), hm(g_arena.h);
+    layout(batch, dm, hm);
+    g_arena.owner = this; g_arena.owner_batch = batch;
     cap = batch;
     return 0;
   }
+  bool bound() const { return g_arena.owner == this; }
 };
 
 template <int NMAX> static cudaError_t tp3_configure() {

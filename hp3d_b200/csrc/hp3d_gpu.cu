@@ -39,12 +39,11 @@ int fail(int code, const char *fmt, ...) {
 Plan *plan_of(int id) { return (id >= 0 && id < (int)g_plans.size()) ? g_plans[id] : nullptr; }
 
 // largest chunk (elements) of this signature that fits in the free device memory
-int chunk_capacity(const Signature &S, int want) {
+int chunk_capacity(Signature &S, int want) {
   size_t fre = 0, tot = 0;
   cudaMemGetInfo(&fre, &tot);
-  // memory already held by this signature's chunk buffers is reusable; two lanes share the budget
-  size_t have = (size_t)Signature::NLANE * S.cap * S.bytes_per_element();
-  double budget = 0.80 * (double)(fre + have);
+  // the shared arena is reusable; two lanes share the budget
+  double budget = 0.80 * (double)(fre + g_arena.dcap);
   long long cap = (long long)(budget / (double)(Signature::NLANE * S.bytes_per_element()));
   if (cap > 1024) cap = 1024;
   if (cap > want) cap = want;
@@ -112,6 +111,8 @@ int hp3d_gpu_finalize(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   for (Plan *p : g_plans) delete p;
   g_plans.clear();
+  cudaDeviceSynchronize();
+  g_arena.release();
   for (int i = 0; i < 2; i++)
     if (g_lane_stream[i]) { cudaStreamDestroy(g_lane_stream[i]); g_lane_stream[i] = nullptr; }
   if (g_copy) { cudaStreamDestroy(g_copy); g_copy = nullptr; }
@@ -175,6 +176,18 @@ int hp3d_gpu_sizes_t(int plan, int etype, const int *norder, int *ni, int *nb, i
   if (nb) *nb = s->h.nb;
   if (nint) *nint = s->h.nint;
   if (nrdofH) *nrdofH = s->h.nH;
+  return HP3D_OK;
+}
+
+int hp3d_gpu_sig_dims(int plan, int etype, const int *norder, const int *norie, const int *norif, int *dims) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Plan *p = plan_of(plan);
+  if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
+  std::string err;
+  Signature *s = p->get(etype, norder, norie, norif, false, err);
+  if (!s) return fail(HP3D_EINVAL, "%s", err.c_str());
+  const SigHost &h = s->h;
+  dims[0] = h.ntest; dims[1] = h.ni; dims[2] = h.nb; dims[3] = h.nint; dims[4] = h.nH; dims[5] = h.dims.np; dims[6] = h.dims.nbp; dims[7] = h.dims.nip;
   return HP3D_OK;
 }
 
@@ -385,7 +398,7 @@ int hp3d_gpu_quad_points(int plan, int nel, const int *etype, const int *norder,
   for (int e = 0; e < nel; e++) {  // not a hot path: one element at a time
     Signature *S = p->get(etype ? etype[e] : HP3D_MDLB, norder + 19 * e, norie + 12 * e, norif + 6 * e, true, err);
     if (!S) return fail(HP3D_EINVAL, "element %d: %s", e, err.c_str());
-    if (S->cap < 1 && S->reserve(1, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());
+    if (S->reserve(1, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());
     const SigHost &h = S->h;
     Signature::Lane &L = S->lane[0];
     CUDA_TRY(cudaMemcpyAsync(L.d_xnod, xnod + (size_t)e * xnod_ld, sizeof(double) * 3 * h.nH, cudaMemcpyHostToDevice, g_compute));
@@ -473,8 +486,17 @@ int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, con
   CUDA_TRY(cudaEventRecord(t0, g_lane_stream[0]));
   if (lanes == 2) CUDA_TRY(cudaStreamWaitEvent(g_lane_stream[1], t0, 0));   // lane 1 starts inside the timed region
   int k = 0;
+  cudaEvent_t tsw[2];
+  for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&tsw[i], cudaEventDisableTiming));
   for (int r = 0; r < reps; r++)
-    for (Grp &g : gs)
+    for (Grp &g : gs) {
+      if (!g.S->bound()) {   // another group's buffers occupy the arena: both lanes must drain before they are reused
+        if (lanes == 2) {
+          for (int i = 0; i < 2; i++) cudaEventRecord(tsw[i], g_lane_stream[i]);
+          cudaStreamWaitEvent(g_lane_stream[0], tsw[1], 0); cudaStreamWaitEvent(g_lane_stream[1], tsw[0], 0);
+        }
+        if (g.S->reserve(g.chunk, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());
+      }
       for (int c0 = 0; c0 < g.n; c0 += g.chunk, k++) {
         const int n = std::min(g.n - c0, g.chunk), ln = lanes == 2 ? (k & 1) : 0;
         StageEvents ev;
@@ -483,6 +505,8 @@ int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, con
         run_chunk(*g.S, g.S->lane[ln], 0, gp, n, g.dx + (size_t)c0 * 3 * g.S->h.nH, nullptr, p->store_schur != 0, g_lane_stream[ln], &ev);
         if (ev.on) evs.push_back(ev);
       }
+    }
+  for (int i = 0; i < 2; i++) cudaEventDestroy(tsw[i]);
   if (lanes == 2) { CUDA_TRY(cudaEventRecord(tj, g_lane_stream[1])); CUDA_TRY(cudaStreamWaitEvent(g_lane_stream[0], tj, 0)); }
   CUDA_TRY(cudaEventRecord(t1, g_lane_stream[0]));
   CUDA_TRY(cudaStreamSynchronize(g_lane_stream[0]));
@@ -521,7 +545,7 @@ int hp3d_gpu_integrate_debug_t(int plan, int etype, const int *norder, const int
   std::string err;
   Signature *S = p->get(etype, norder, norie, norif, true, err);
   if (!S) return fail(HP3D_EINVAL, "%s", err.c_str());
-  if (S->cap < 1 && S->reserve(1, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());
+  if (S->reserve(1, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());
   const SigHost &h = S->h;
   const DenseDims &d = h.dims;
   const size_t P = d.planes();

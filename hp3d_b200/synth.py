@@ -80,3 +80,135 @@ def problem_sizes(kind, p, dp=1):
     if kind == 4:
         return 2 * 3 * pe * (pe + 1) ** 2, 2 * (E - bE) + 6 * Q, 2 * (E - bE), 6 * Q
     raise ValueError(kind)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# hp-refined mixed hexahedron / prism mesh (BASELINE.json configs[4])
+# master-element topology, 0-based (src/modules/element_data.F90:25-35, 62-70, 85-93)
+MDLB, MDLP = 1, 3
+BRICK_EDGE = [(0, 1), (1, 2), (3, 2), (0, 3), (4, 5), (5, 6), (7, 6), (4, 7), (0, 4), (1, 5), (2, 6), (3, 7)]
+BRICK_FACE = [(0, 1, 2, 3), (4, 5, 6, 7), (0, 1, 5, 4), (1, 2, 6, 5), (3, 2, 6, 7), (0, 3, 7, 4)]
+PRISM_VERT = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [0, 1, 1]], dtype=np.float64)
+PRISM_EDGE = [(0, 1), (1, 2), (0, 2), (3, 4), (4, 5), (3, 5), (0, 3), (1, 4), (2, 5)]
+PRISM_FACE = [(0, 1, 2), (3, 4, 5), (0, 1, 4, 3), (1, 2, 5, 4), (0, 2, 5, 3)]
+TRI_ORIENT = {(0, 1, 2): 0, (1, 2, 0): 1, (2, 0, 1): 2, (0, 2, 1): 3, (1, 0, 2): 4, (2, 1, 0): 5}   # Orient.F90:119-160
+
+
+def quad_orientation(gids):
+    """Orientation code 0..7 (Orient.F90:39-99) of a quad face whose element-local cyclic vertices carry the global ids
+    `gids`: the face's own frame has its origin at the vertex with the smallest id and its first axis towards the
+    neighbour with the smaller id.  Codes 0-3: origin at local vertex 0..3, first axis towards the NEXT vertex of the
+    cycle; 4-7: towards the PREVIOUS one."""
+    o = int(np.argmin(gids))
+    nxt, prv = gids[(o + 1) % 4], gids[(o - 1) % 4]
+    return o if nxt < prv else 4 + o
+
+
+def tri_orientation(gids):
+    """Orientation code 0..5 (Orient.F90:119-160): global vertex k of the face = local vertex perm[k], ids ascending."""
+    return TRI_ORIENT[tuple(int(i) for i in np.argsort(gids))]
+
+
+def nrdof_h1_prism(norder):
+    n = 6 + sum(int(norder[e]) - 1 for e in range(9))
+    for f in (9, 10):
+        n += (norder[f] - 1) * (norder[f] - 2) // 2
+    for f in (11, 12, 13):
+        n += (norder[f] // 10 - 1) * (norder[f] % 10 - 1)
+    p, pz = norder[14] // 10, norder[14] % 10
+    return int(n + (p - 1) * (p - 2) // 2 * (pz - 1))
+
+
+def nrdof_h1_brick(norder):
+    n = 8 + sum(int(norder[e]) - 1 for e in range(12))
+    for f in range(12, 18):
+        n += (norder[f] // 10 - 1) * (norder[f] % 10 - 1)
+    m = int(norder[18])
+    return int(n + (m // 100 - 1) * ((m // 10) % 10 - 1) * (m % 10 - 1))
+
+
+def hp_mesh(N, prism_frac=0.3, pmin=2, pmax=7, seed_p=2024, seed_g=7, jitter=0.0, seed_x=12345, rotate_local=True):
+    """A conforming mixed mesh of the unit cube: N^3 cells; whole (i,j) columns of cells are split into two prisms each
+    (along the vertical diagonal plane) so that about `prism_frac` of the ELEMENTS are prisms, the others are hexahedra.  Every element draws an
+    isotropic order uniformly from {pmin..pmax} (seed_p); edges and faces get the MINIMUM order of the adjacent elements
+    (hp3D's min rule); edge and face orientations follow from a random global vertex numbering (seed_g): an edge runs from
+    the smaller to the larger vertex id, a face's frame starts at its smallest id (see quad_orientation / tri_orientation).
+    With `rotate_local` the element-local vertex numbering of every element is rotated about its vertical axis by a random
+    multiple of 90 (brick) / 120 (prism) degrees, so that neighbours see a shared face with different local numberings.
+
+    Returns dict(etype (nel,), norder (nel,19), norient_edge (nel,12), norient_face (nel,6), xnod (nel,nHmax,3),
+    nrdofH (nel,), verts (nel,8) global vertex ids in element-local order (-1 padded), p (nel,))."""
+    rng_p, rng_g, rng_x = np.random.default_rng(seed_p), np.random.default_rng(seed_g), np.random.default_rng(seed_x)
+    n1 = N + 1
+    gid = rng_g.permutation(n1 ** 3)
+    h = 1.0 / N
+    vid = lambda i, j, k: i + n1 * (j + n1 * k)   # noqa: E731
+    coords = np.zeros((n1 ** 3, 3))
+    for k in range(n1):
+        for j in range(n1):
+            for i in range(n1):
+                c = np.array([i, j, k]) * h
+                if jitter:
+                    d = rng_x.uniform(-jitter * h, jitter * h, 3)
+                    for a, idx in enumerate((i, j, k)):
+                        if idx in (0, N):
+                            d[a] = 0.0
+                    c = c + d
+                coords[vid(i, j, k)] = c
+    split = rng_p.random((N, N)) < prism_frac / (2.0 - prism_frac)   # a split cell yields two prisms
+    elems = []   # (etype, [vertex ids in element-local order])
+    for k in range(N):
+        for j in range(N):
+            for i in range(N):
+                c = [vid(i, j, k), vid(i + 1, j, k), vid(i + 1, j + 1, k), vid(i, j + 1, k),
+                     vid(i, j, k + 1), vid(i + 1, j, k + 1), vid(i + 1, j + 1, k + 1), vid(i, j + 1, k + 1)]
+                if split[i, j]:
+                    elems.append((MDLP, [c[0], c[1], c[2], c[4], c[5], c[6]]))
+                    elems.append((MDLP, [c[0], c[2], c[3], c[4], c[6], c[7]]))
+                else:
+                    elems.append((MDLB, c))
+    nel = len(elems)
+    if rotate_local:
+        for e, (et, v) in enumerate(elems):
+            n = 4 if et == MDLB else 3
+            r = int(rng_g.integers(0, n))
+            elems[e] = (et, [v[(i + r) % n] for i in range(n)] + [v[n + (i + r) % n] for i in range(n)])
+    p = rng_p.integers(pmin, pmax + 1, nel)
+    # min rule over the elements adjacent to each edge / face
+    emin, fmin = {}, {}
+    for e, (et, v) in enumerate(elems):
+        E, F = (BRICK_EDGE, BRICK_FACE) if et == MDLB else (PRISM_EDGE, PRISM_FACE)
+        for a, b in E:
+            key = frozenset((v[a], v[b]))
+            emin[key] = min(emin.get(key, 99), int(p[e]))
+        for f in F:
+            key = frozenset(v[i] for i in f)
+            fmin[key] = min(fmin.get(key, 99), int(p[e]))
+    etype = np.zeros(nel, np.int32); norder = np.zeros((nel, 19), np.int32)
+    noe = np.zeros((nel, 12), np.int32); nof = np.zeros((nel, 6), np.int32)
+    verts = -np.ones((nel, 8), np.int64); nH = np.zeros(nel, np.int32)
+    for e, (et, v) in enumerate(elems):
+        etype[e] = et
+        verts[e, :len(v)] = v
+        E, F = (BRICK_EDGE, BRICK_FACE) if et == MDLB else (PRISM_EDGE, PRISM_FACE)
+        g = gid[np.array(v)]
+        for ie, (a, b) in enumerate(E):
+            norder[e, ie] = emin[frozenset((v[a], v[b]))]
+            noe[e, ie] = 0 if g[a] < g[b] else 1
+        for jf, f in enumerate(F):
+            pf = fmin[frozenset(v[i] for i in f)]
+            if len(f) == 3:
+                norder[e, len(E) + jf] = pf
+                nof[e, jf] = tri_orientation(g[list(f)])
+            else:
+                norder[e, len(E) + jf] = 11 * pf
+                nof[e, jf] = quad_orientation(g[list(f)])
+        if et == MDLB:
+            norder[e, 18] = 111 * int(p[e]); nH[e] = nrdof_h1_brick(norder[e])
+        else:
+            norder[e, 14] = 11 * int(p[e]); nH[e] = nrdof_h1_prism(norder[e])
+    xnod = np.zeros((nel, int(nH.max()), 3))
+    for e, (et, v) in enumerate(elems):
+        xnod[e, :len(v)] = coords[np.array(v)]
+    return dict(etype=etype, norder=norder, norient_edge=noe, norient_face=nof, xnod=xnod, nrdofH=nH, verts=verts, p=p,
+                gid=gid, coords=coords)

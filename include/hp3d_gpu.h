@@ -79,6 +79,10 @@ int hp3d_gpu_plan_destroy(int plan);
 int hp3d_gpu_sizes(int plan, const int *norder /*19*/, int *ni, int *nb, int *nint, int *nrdofH);   /* brick */
 int hp3d_gpu_sizes_t(int plan, int etype, const int *norder /*19*/, int *ni, int *nb, int *nint, int *nrdofH);
 
+/* Host-only: dims[8] = {ntest, ni, nb, nint, nrdofH, np, nbp, nip} of one element signature (np/nbp/nip: the padded
+ * extents of the dense phase) -- what a caller needs to weight elements for load balancing (Zoltan OBJ_WEIGHT). */
+int hp3d_gpu_sig_dims(int plan, int etype, const int *norder, const int *norient_edge, const int *norient_face, int *dims);
+
 /* The batched unit of work.  For e = 0..nel-1 (elements may differ in order and orientation; they are grouped
  * by signature internally):
  *   etype[e]             element type (HP3D_MDLB or HP3D_MDLP; NULL = all bricks)

@@ -136,3 +136,29 @@ def test_mixed_hexa_prism_batch(oracle, gpu):
             assert relerr(Aii, rA) < 1e-12, (kind, e, relerr(Aii, rA))
             assert relerr(Bi, rB) < 1e-12, (kind, e)
         eng.close()
+
+
+def test_hp_mesh_batch_vs_oracle(oracle, gpu):
+    """BASELINE.json configs[4] in miniature: a conforming hp mesh of hexahedra and prisms (min-rule orders 2..4, orientations
+    from a random global vertex numbering, ~30 distinct signatures) through ONE hp3d_gpu_elem_batch call, every element
+    against the oracle; ultraweak Maxwell."""
+    from hp3d_b200 import synth
+    oracle.set_maxp(8)
+    oracle.use_blas(True)
+    m = synth.hp_mesh(2, prism_frac=0.5, pmin=2, pmax=4, seed_p=3, seed_g=9, jitter=0.1)
+    nel = len(m["etype"])
+    assert (m["etype"] == 3).any() and (m["etype"] == 1).any()
+    om = 2 * np.pi
+    prm = oracle.default_params(omega=om)
+    eng = _engine(4, omega=om, maxp=8)
+    res = eng.elem_stc_batch(m["norder"], m["norient_edge"], m["norient_face"], m["xnod"], etype=m["etype"])
+    assert (res["info"] == 0).all()
+    for e in range(nel):
+        nH = int(m["nrdofH"][e])
+        Aii, Bi, AS, BS = eng.unpack(res, e)
+        rA, rB, _, _ = oracle.condensed(4, m["norder"][e], m["norient_edge"][e], m["norient_face"][e], m["xnod"][e, :nH], prm,
+                                        etype=int(m["etype"][e]))
+        assert Aii.shape == rA.shape
+        assert relerr(Aii, rA) < 1e-12, (e, relerr(Aii, rA))
+        assert relerr(Bi, rB) < 1e-12, (e, relerr(Bi, rB))
+    eng.close()
