@@ -241,10 +241,10 @@ __global__ void conj_transpose_kernel(MatRef In, MatRef Out, int R, int Cn) {
   }
 }
 
-// unit diagonal on the padded rows [n0, n1) of a square row-major planar matrix (keeps the factorization regular)
-__global__ void pad_diag_kernel(double *A, long long batch_stride, int ld, int n0, int n1) {
-  int i = n0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n1) A[(long long)blockIdx.y * batch_stride + (long long)i * ld + i] = 1.0;
+// unit diagonal on the padded rows [n0[e], n1) of a square row-major planar matrix (keeps the factorization regular)
+__global__ void pad_diag_kernel(double *A, long long batch_stride, int ld, const int *__restrict__ n0, int n1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n0[blockIdx.y] && i < n1) A[(long long)blockIdx.y * batch_stride + (long long)i * ld + i] = 1.0;
 }
 
 }  // namespace hp3d
@@ -258,12 +258,12 @@ namespace hp3d {
 // element matrix [A_bb A_bi b_b ; A_ib A_ii b_i] with partial pivoting restricted to the bubble rows: after nb steps the
 // interface rows hold the Schur complement and the condensed load, and a back substitution on the bubble rows gives
 // ASchur = A_bb^-1 A_bi, BSchur = A_bb^-1 b_b.  One CTA per element, matrix in global memory (L2-resident), planar.
-// Layout of Am: [M][M] row-major, bubbles at rows/cols [0,nb), interface at [nbp, nbp+ni), load COLUMN nbp+ni.
+// Layout of Am: [M][M] row-major, bubbles at rows/cols [0,nb), interface at [nbp, nbp+ni), load COLUMN M-1; nb, ni per element.
 // Outputs are written directly in the caller's layout (column-major, interleaved complex).
 template <bool CPLX>
-__global__ void __launch_bounds__(512) stc_gen_kernel(int nb, int nbp, int ni, int M, double *Am, long long a_plane, long long a_batch,
-                                                      double *Aii, double *Bi, double *AS, double *BS, long long sA, long long sB,
-                                                      long long sAS, long long sBS, int want_schur, int *info) {
+__global__ void __launch_bounds__(512) stc_gen_kernel(const int *__restrict__ nb_e, int nbp, const int *__restrict__ ni_e, int M, double *Am,
+                                                      long long a_plane, long long a_batch, double *Aii, double *Bi, double *AS, double *BS,
+                                                      long long sA, long long sB, long long sAS, long long sBS, int want_schur, int *info) {
   constexpr int NS = CPLX ? 2 : 1;
   extern __shared__ __align__(16) double sh[];   // pivot row: [2][M]
   __shared__ double red_v[16];
@@ -271,8 +271,9 @@ __global__ void __launch_bounds__(512) stc_gen_kernel(int nb, int nbp, int ni, i
   __shared__ int s_piv;
   __shared__ double s_pr, s_pi;
   const int e = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const int nb = nb_e[e], ni = ni_e[e];
   double *Ar = Am + (long long)e * a_batch, *Ai = Ar + a_plane;
-  const int ncol = nbp + ni + 1;          // columns in use (load column last)
+  const int ncol = M, lc = M - 1;         // all columns (padding columns are zero); load column = last padded interface column
   double *pr = sh, *pi = sh + M;
   int bad = 0;
   for (int k = 0; k < nb; k++) {
@@ -339,8 +340,8 @@ __global__ void __launch_bounds__(512) stc_gen_kernel(int nb, int nbp, int ni, i
     if (CPLX) oA[(long long)idx * NS + 1] = Ai[(long long)(nbp + r) * M + nbp + c];
   }
   for (int r = tid; r < ni; r += nt) {
-    oB[(long long)r * NS] = Ar[(long long)(nbp + r) * M + nbp + ni];
-    if (CPLX) oB[(long long)r * NS + 1] = Ai[(long long)(nbp + r) * M + nbp + ni];
+    oB[(long long)r * NS] = Ar[(long long)(nbp + r) * M + lc];
+    if (CPLX) oB[(long long)r * NS + 1] = Ai[(long long)(nbp + r) * M + lc];
   }
   if (tid == 0 && bad && info[e] == 0) info[e] = bad;
   if (!want_schur || nb == 0) return;
@@ -375,8 +376,8 @@ __global__ void __launch_bounds__(512) stc_gen_kernel(int nb, int nbp, int ni, i
     if (CPLX) oS[(long long)idx * NS + 1] = Ai[(long long)b * M + nbp + c];
   }
   for (int b = tid; b < nb; b += nt) {
-    oT[(long long)b * NS] = Ar[(long long)b * M + nbp + ni];
-    if (CPLX) oT[(long long)b * NS + 1] = Ai[(long long)b * M + nbp + ni];
+    oT[(long long)b * NS] = Ar[(long long)b * M + lc];
+    if (CPLX) oT[(long long)b * NS + 1] = Ai[(long long)b * M + lc];
   }
 }
 

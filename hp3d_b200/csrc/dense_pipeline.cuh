@@ -18,7 +18,9 @@ struct DenseDims {
   bool dpg = true;     // true: Gram + enriched stiffness present; false: A is given directly
   int n = 0;           // test dofs (rows of the Gram)
   int nb = 0, ni = 0;  // bubble / interface trial dofs
-  int np = 0, nbp = 0, nip = 0;  // padded: np=pad64(n), nbp=pad64(nb), nip=pad64(ni+1)
+  int np = 0, nbp = 0, nip = 0;  // padded: np=pad64(n), nbp=pad64(nb), nip=pad64(ni+1); the load sits at interface index nip-1
+  // A batch may mix elements with different n / nb / ni as long as the PADDED extents agree ("dense class"): the kernels
+  // below only use np/nbp/nip plus the per-element counts in DenseBuffers::ni_e / nb_e; n, nb, ni here are the class maxima.
   __host__ __device__ int M() const { return nbp + nip; }
   __host__ __device__ int R() const { return np + nbp + nip; }
   void finish() { np = dpg ? pad64(n) : 0; nbp = pad64(nb); nip = pad64(ni + 1); }
@@ -40,6 +42,7 @@ struct DenseBuffers {
   double *LinvS = nullptr;  // [batch][nsteps][planes][64][64]  kept for the stc backward solve
   double *LinvSH = nullptr;
   int *info = nullptr;      // [batch]
+  int *ni_e = nullptr, *nb_e = nullptr;  // [batch] per-element interface / bubble dof counts
 };
 
 template <bool CPLX>
@@ -104,9 +107,9 @@ static void dense_phase(const DenseDims &d, const DenseBuffers &b, int batch, cu
   }
   if (d.nb == 0) return;
   const long long apl = (long long)d.a_plane(), ab = P * apl;
-  if (d.nbp > d.nb) {  // padded bubble rows: unit diagonal keeps the factorization regular
-    dim3 grid((d.nbp - d.nb + 63) / 64, batch);
-    pad_diag_kernel<<<grid, 64, 0, st>>>(b.Am, ab, M, d.nb, d.nbp);
+  {  // padded bubble rows [nb_e, nbp): unit diagonal keeps the factorization regular
+    dim3 grid(d.nbp / 64, batch);
+    pad_diag_kernel<<<grid, 64, 0, st>>>(b.Am, ab, M, b.nb_e, d.nbp);
   }
   const int ns = d.nsteps_stc();
   // A_bb = L L^H ; rows below become Y~ = A_ib L^-H (and the load row y_b^H)

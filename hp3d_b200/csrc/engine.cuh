@@ -100,91 +100,132 @@ struct DenseWorkspace {
 };
 
 // ------------------------------------------------------------------------------------------------
-// One element signature compiled and resident on the device.
+// One element signature (element type + node orders + orientations) compiled and resident on the device: only the
+// small tables the integration kernels read.  Chunk buffers belong to the "dense class" (below), not to the signature.
 struct Signature {
   SigHost h;
-  double *d_tab = nullptr, *d_wq = nullptr, *d_CW = nullptr, *d_ones = nullptr, *d_ttab = nullptr;
-  int *d_hdof = nullptr, *d_maps = nullptr, *d_crow = nullptr, *d_iota = nullptr;
+  double *d_tab = nullptr, *d_wq = nullptr, *d_CW = nullptr, *d_ttab = nullptr;
+  int *d_hdof = nullptr, *d_maps = nullptr, *d_crow = nullptr;
   FamilyDesc *d_fam = nullptr; TermDesc *d_term = nullptr; SlotDesc *d_slot = nullptr; BlockDesc *d_block = nullptr; WorkItem *d_work = nullptr;
-  // A lane = one complete set of per-chunk buffers.  Two lanes run on two streams so that the latency-bound steps of one
-  // chunk (64x64 tile factorizations, launch tails) overlap the GEMMs of the other, and D2H of a finished chunk
-  // overlaps compute.
-  struct Lane {
-    DenseWorkspace ws;
-    double *d_WF = nullptr, *d_xnod = nullptr, *d_src = nullptr;         // chunk inputs / weight fields
-    struct Out { double *Aii = nullptr, *Bi = nullptr, *AS = nullptr, *BS = nullptr; int *info = nullptr, *h_info = nullptr; };  // h_info: pinned
-    Out out[2];   // chunk outputs (device staging), double-buffered: the D2H of one chunk overlaps the lane's next chunk
-    double *h_xnod = nullptr, *h_src = nullptr;                          // pinned host staging of the chunk inputs
-  };
-  static constexpr int NLANE = 2;
-  Lane lane[NLANE];
-  int cap = 0;   // elements per lane currently bound in the arena (0: not bound)
   ~Signature() {
-    cudaFree(d_tab); cudaFree(d_wq); cudaFree(d_CW); cudaFree(d_ones); cudaFree(d_ttab); cudaFree(d_hdof); cudaFree(d_maps); cudaFree(d_crow); cudaFree(d_iota);
+    cudaFree(d_tab); cudaFree(d_wq); cudaFree(d_CW); cudaFree(d_ttab); cudaFree(d_hdof); cudaFree(d_maps); cudaFree(d_crow);
     cudaFree(d_fam); cudaFree(d_term); cudaFree(d_slot); cudaFree(d_block); cudaFree(d_work);
-    if (g_arena.owner == this) g_arena.owner = nullptr;
   }
   int ns() const { return h.cplx ? 2 : 1; }
   size_t src_doubles() const { return (size_t)h.nint * (h.cplx ? 6 : 1); }
-  // carve (or, with null bases, measure) the chunk buffers of both lanes for `batch` elements per lane
-  void layout(int batch, Bump &dm, Bump &hm) {
-    const size_t NS = ns();
-    for (int i = 0; i < NLANE; i++) {
-      Lane &L = lane[i];
-      L.ws.bind(h.dims, batch, dm);
-      L.d_WF = dm.take<double>((size_t)NFIELD * h.nint * batch);
-      L.d_xnod = dm.take<double>((size_t)3 * h.nH * batch);
-      L.d_src = dm.take<double>(src_doubles() * batch);
-      for (int o = 0; o < 2; o++) {
-        L.out[o].Aii = dm.take<double>(NS * (size_t)h.ni * h.ni * batch);
-        L.out[o].Bi = dm.take<double>(NS * (size_t)h.ni * batch);
-        L.out[o].AS = dm.take<double>(NS * ((size_t)h.nb * h.ni + 1) * batch);
-        L.out[o].BS = dm.take<double>(NS * ((size_t)h.nb + 1) * batch);
-        L.out[o].info = dm.take<int>(batch);
-        L.out[o].h_info = hm.take<int>(batch);
-      }
-      L.h_xnod = hm.take<double>((size_t)3 * h.nH * batch);
-      L.h_src = hm.take<double>(src_doubles() * batch);
-    }
-  }
-  size_t bytes_per_element() {   // device bytes per element of ONE lane (asymptotic; alignment slack excluded)
-    Bump d1(nullptr), h1(nullptr), d2(nullptr), h2(nullptr);
-    Lane keep[NLANE] = {lane[0], lane[1]};
-    layout(1, d1, h1); layout(65, d2, h2);
-    lane[0] = keep[0]; lane[1] = keep[1];
-    return (d2.off - d1.off) / 64 / NLANE + 1;
-  }
   int upload(std::string &err) {
     if (dev_upload(h.tab, &d_tab, err) || dev_upload(h.wq, &d_wq, err) || dev_upload(h.hdof, &d_hdof, err) || dev_upload(h.maps, &d_maps, err) ||
         dev_upload(h.fam, &d_fam, err) || dev_upload(h.term, &d_term, err) || dev_upload(h.slot, &d_slot, err) ||
         dev_upload(h.block, &d_block, err) || dev_upload(h.work, &d_work, err) || dev_upload(h.crow, &d_crow, err) || dev_upload(h.CW, &d_CW, err) ||
         dev_upload(h.ttab, &d_ttab, err))
       return -2;
-    const int n = std::max(h.ni, h.nb) + 1;
-    std::vector<int> iota(n);
-    std::vector<double> ones(n, 1.0);
-    for (int i = 0; i < n; i++) iota[i] = i;
-    if (dev_upload(iota, &d_iota, err) || dev_upload(ones, &d_ones, err)) return -2;
     return 0;
   }
-  // bind the chunk buffers for `batch` elements per lane into the shared arena (no-op if they are still bound)
-  int reserve(int batch, std::string &err) {
-    if (g_arena.owner == this && batch <= g_arena.owner_batch) { cap = g_arena.owner_batch; return 0; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Dense class: all signatures whose PADDED dense-phase extents (np, nbp, nip) agree run through the dense phase in the
+// same batch, whatever their element type, orders below the padding granularity and orientations -- this is the
+// heterogeneous batching of hp meshes.  ChunkShape carries the class extents plus the per-element maxima that size the
+// chunk buffers.
+struct ChunkShape {
+  DenseDims d;                 // np/nbp/nip of the class; n/nb/ni = maxima over the members seen in this call
+  bool gen_stc = false;
+  int nint_max = 0, nH_max = 0;
+  size_t src_max = 0;          // doubles per element of a caller-supplied source table
+  int ns() const { return d.cplx ? 2 : 1; }
+  bool covers(const ChunkShape &o) const {
+    return d.cplx == o.d.cplx && d.dpg == o.d.dpg && gen_stc == o.gen_stc && d.np == o.d.np && d.nbp == o.d.nbp && d.nip == o.d.nip &&
+           d.ni >= o.d.ni && d.nb >= o.d.nb && nint_max >= o.nint_max && nH_max >= o.nH_max && src_max >= o.src_max;
+  }
+  void absorb(const SigHost &h) {
+    if (d.np == 0 && d.nip == 0) { d = h.dims; gen_stc = h.gen_stc; }
+    d.n = std::max(d.n, h.dims.n); d.nb = std::max(d.nb, h.nb); d.ni = std::max(d.ni, h.ni);
+    nint_max = std::max(nint_max, h.nint); nH_max = std::max(nH_max, h.nH);
+    src_max = std::max(src_max, (size_t)h.nint * (h.cplx ? 6 : 1));
+  }
+  static std::string key(const SigHost &h) {
+    char b[96];
+    snprintf(b, sizeof b, "%d/%d/%d/%d/%d/%d", (int)h.cplx, (int)h.dpg, (int)h.gen_stc, h.dims.np, h.dims.nbp, h.dims.nip);
+    return b;
+  }
+};
+
+// A lane = one complete set of per-chunk buffers.  Two lanes run on two streams so that the latency-bound steps of one
+// chunk (64x64 tile factorizations, launch tails) overlap the GEMMs of the other, and D2H of a finished chunk overlaps compute.
+struct Lane {
+  DenseWorkspace ws;
+  double *d_WF = nullptr, *d_xnod = nullptr, *d_src = nullptr;         // chunk inputs / weight fields
+  struct Out { double *Aii = nullptr, *Bi = nullptr, *AS = nullptr, *BS = nullptr; int *info = nullptr, *h_info = nullptr; };  // h_info: pinned
+  Out out[2];   // chunk outputs (device staging), double-buffered: the D2H of one chunk overlaps the lane's next chunk
+  double *h_xnod = nullptr, *h_src = nullptr;                          // pinned host staging of the chunk inputs
+  int *h_cnt = nullptr;                                                // pinned [2][batch]: ni_e | nb_e
+};
+struct LaneSet {
+  static constexpr int NLANE = 2;
+  Lane lane[NLANE];
+  ChunkShape shape;
+  int cap = 0;   // elements per lane currently bound in the arena
+  double *d_ones = nullptr; int *d_iota = nullptr; int n_iota = 0;   // identity output maps (grown on demand, plain cudaMalloc)
+  void layout(const ChunkShape &sh, int batch, Bump &dm, Bump &hm) {
+    const size_t NS = sh.ns();
+    const DenseDims &d = sh.d;
+    for (int i = 0; i < NLANE; i++) {
+      Lane &L = lane[i];
+      L.ws.bind(d, batch, dm);
+      L.ws.b.ni_e = dm.take<int>(batch); L.ws.b.nb_e = dm.take<int>(batch);
+      L.d_WF = dm.take<double>((size_t)NFIELD * sh.nint_max * batch);
+      L.d_xnod = dm.take<double>((size_t)3 * sh.nH_max * batch);
+      L.d_src = dm.take<double>(sh.src_max * batch);
+      for (int o = 0; o < 2; o++) {
+        L.out[o].Aii = dm.take<double>(NS * (size_t)d.ni * d.ni * batch);
+        L.out[o].Bi = dm.take<double>(NS * (size_t)d.ni * batch);
+        L.out[o].AS = dm.take<double>(NS * ((size_t)d.nb * d.ni + 1) * batch);
+        L.out[o].BS = dm.take<double>(NS * ((size_t)d.nb + 1) * batch);
+        L.out[o].info = dm.take<int>(batch);
+        L.out[o].h_info = hm.take<int>(batch);
+      }
+      L.h_xnod = hm.take<double>((size_t)3 * sh.nH_max * batch);
+      L.h_src = hm.take<double>(sh.src_max * batch);
+      L.h_cnt = hm.take<int>(2 * (size_t)batch);
+    }
+  }
+  size_t bytes_per_element(const ChunkShape &sh) {   // device bytes per element of ONE lane (alignment slack excluded)
+    Bump d1(nullptr), h1(nullptr), d2(nullptr), h2(nullptr);
+    LaneSet tmp;
+    tmp.layout(sh, 1, d1, h1); tmp.layout(sh, 65, d2, h2);
+    return (d2.off - d1.off) / 64 / NLANE + 1;
+  }
+  // bind the chunk buffers for `batch` elements per lane of shape `sh` into the shared arena (no-op if still bound)
+  int reserve(const ChunkShape &sh, int batch, std::string &err) {
+    if (cap >= batch && shape.covers(sh) && g_arena.owner == this) return 0;
     Bump dmeas(nullptr), hmeas(nullptr);
-    layout(batch, dmeas, hmeas);
-    // grow geometrically so that a sequence of slightly larger signatures does not reallocate every time
+    LaneSet tmp;
+    tmp.layout(sh, batch, dmeas, hmeas);
     size_t dneed = dmeas.off + 256, hneed = hmeas.off + 256;
-    if (dneed > g_arena.dcap) dneed = std::max(dneed, g_arena.dcap + g_arena.dcap / 4);
+    if (dneed > g_arena.dcap) dneed = std::max(dneed, g_arena.dcap + g_arena.dcap / 4);   // geometric growth
     if (hneed > g_arena.hcap) hneed = std::max(hneed, g_arena.hcap + g_arena.hcap / 4);
     if (int rc = g_arena.ensure(dneed, hneed, err)) { cap = 0; return rc; }
     Bump dm(g_arena.d), hm(g_arena.h);
-    layout(batch, dm, hm);
-    g_arena.owner = this; g_arena.owner_batch = batch;
-    cap = batch;
+    layout(sh, batch, dm, hm);
+    const int need = std::max(sh.d.ni, sh.d.nb) + 1;
+    if (need > n_iota) {
+      cudaDeviceSynchronize();
+      cudaFree(d_ones); cudaFree(d_iota);
+      std::vector<int> iota(need); std::vector<double> ones(need, 1.0);
+      for (int i = 0; i < need; i++) iota[i] = i;
+      if (dev_upload(iota, &d_iota, err) || dev_upload(ones, &d_ones, err)) return -2;
+      n_iota = need;
+    }
+    g_arena.owner = this; shape = sh; cap = batch;
     return 0;
   }
-  bool bound() const { return g_arena.owner == this; }
+  void release() { cudaFree(d_ones); cudaFree(d_iota); d_ones = nullptr; d_iota = nullptr; n_iota = 0; cap = 0; shape = ChunkShape(); }
 };
+static LaneSet g_lanes;
+
+// a run of consecutive chunk slots [start, start+n) holding elements of ONE signature
+struct Seg { Signature *S; int start, n; };
 
 template <int NMAX> static cudaError_t tp3_configure() {
   return cudaFuncSetAttribute(tp3_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -216,37 +257,45 @@ static void launch_tp3(const Signature &S, const Tp3Args &A, int nel, cudaStream
 
 struct StageEvents { cudaEvent_t e[4]; bool on = false; };  // start, after integration, after dense, after scatter
 
-// Integration of `nel` resident elements (d_xnod/d_src filled) into the dense phase's input buffers.
-static void run_integration(Signature &S, Signature::Lane &L, const GeomParams &gp, int nel, const double *d_xnod, const double *d_src, cudaStream_t st) {
-  const SigHost &h = S.h;
-  const DenseDims &d = h.dims;
-  const long long P = h.cplx ? 2 : 1;
-  SigTables sg;
-  sg.tab = S.d_tab; sg.wq = S.d_wq; sg.hdof = S.d_hdof; sg.nH = h.nH; sg.nint = h.nint;
-  sg.ttab = S.d_ttab ? S.d_ttab + h.geo_toff : nullptr; sg.nT = h.geo_nT;
-  for (int i = 0; i < 3; i++) sg.nq[i] = h.nq[i];
+// Integration of the `nel` elements of a chunk (segments of equal signature) into the dense phase's input buffers.
+// Element slot i reads its geometry dofs at d_xnod + i*xnod_ld (and its source table at d_src + i*src_ld).
+static void run_integration(const ChunkShape &sh, Lane &L, const GeomParams &gp, const std::vector<Seg> &segs, int nel, const double *d_xnod,
+                            long long xnod_ld, const double *d_src, long long src_ld, cudaStream_t st) {
+  const DenseDims &d = sh.d;
+  const long long P = d.cplx ? 2 : 1;
   cudaMemsetAsync(L.ws.b.info, 0, sizeof(int) * nel, st);
-  const long long npts = (long long)nel * h.nint;
-  if (h.etype == 3) geom_fields_prism_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(sg, gp, nel, d_xnod, 3LL * h.nH, d_src, L.d_WF, L.ws.b.info);
-  else geom_fields_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(sg, gp, nel, d_xnod, 3LL * h.nH, d_src, L.d_WF, L.ws.b.info);
-  g_launches++;
-  Tp3Args A;
-  A.tab = S.d_tab; A.fam = S.d_fam; A.term = S.d_term; A.slot = S.d_slot; A.block = S.d_block; A.work = S.d_work; A.maps = S.d_maps;
-  A.WF = L.d_WF; A.nint = h.nint;
-  for (int i = 0; i < 3; i++) A.nq[i] = h.nq[i];
-  A.mat[0] = MatTarget{L.ws.b.W, P * (long long)d.w_plane(), (long long)d.w_plane(), d.np};
-  A.mat[1] = MatTarget{L.ws.b.Am, P * (long long)d.a_plane(), (long long)d.a_plane(), d.M()};
-  if (d.dpg) {
-    cudaMemsetAsync(L.ws.b.W, 0, sizeof(double) * P * d.w_plane() * nel, st);
-    if (d.np > d.n) { dim3 g((d.np - d.n + 63) / 64, nel); unit_diag_kernel<<<g, 64, 0, st>>>(A.mat[0], d.n, d.np); g_launches++; }
-  } else {
-    cudaMemsetAsync(L.ws.b.Am, 0, sizeof(double) * P * d.a_plane() * nel, st);
-  }
-  launch_tp3(S, A, nel, st);
-  if (!h.crow.empty()) {
-    dim3 g((d.np + 255) / 256, (unsigned)h.crow.size(), nel);
-    const_rows_kernel<<<g, 256, 0, st>>>(S.d_CW, S.d_crow, d.np, A.mat[0]);
+  if (d.dpg) cudaMemsetAsync(L.ws.b.W, 0, sizeof(double) * P * d.w_plane() * nel, st);
+  else cudaMemsetAsync(L.ws.b.Am, 0, sizeof(double) * P * d.a_plane() * nel, st);
+  size_t wf_off = 0;
+  for (const Seg &sg_ : segs) {
+    Signature &S = *sg_.S;
+    const SigHost &h = S.h;
+    SigTables sg;
+    sg.tab = S.d_tab; sg.wq = S.d_wq; sg.hdof = S.d_hdof; sg.nH = h.nH; sg.nint = h.nint;
+    sg.ttab = S.d_ttab ? S.d_ttab + h.geo_toff : nullptr; sg.nT = h.geo_nT;
+    for (int i = 0; i < 3; i++) sg.nq[i] = h.nq[i];
+    double *WF = L.d_WF + wf_off;
+    wf_off += (size_t)NFIELD * h.nint * sg_.n;
+    const double *xn = d_xnod + (long long)sg_.start * xnod_ld, *src = d_src ? d_src + (long long)sg_.start * src_ld : nullptr;
+    int *info = L.ws.b.info + sg_.start;
+    const long long npts = (long long)sg_.n * h.nint;
+    if (h.etype == 3) geom_fields_prism_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(sg, gp, sg_.n, xn, xnod_ld, src, src_ld, WF, info);
+    else geom_fields_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(sg, gp, sg_.n, xn, xnod_ld, src, src_ld, WF, info);
     g_launches++;
+    Tp3Args A;
+    A.tab = S.d_tab; A.fam = S.d_fam; A.term = S.d_term; A.slot = S.d_slot; A.block = S.d_block; A.work = S.d_work; A.maps = S.d_maps;
+    A.WF = WF; A.nint = h.nint;
+    for (int i = 0; i < 3; i++) A.nq[i] = h.nq[i];
+    const long long wb = P * (long long)d.w_plane(), ab = P * (long long)d.a_plane();
+    A.mat[0] = MatTarget{d.dpg ? L.ws.b.W + wb * sg_.start : nullptr, wb, (long long)d.w_plane(), d.np};
+    A.mat[1] = MatTarget{L.ws.b.Am + ab * sg_.start, ab, (long long)d.a_plane(), d.M()};
+    if (d.dpg && d.np > h.dims.n) { dim3 g((d.np - h.dims.n + 63) / 64, sg_.n); unit_diag_kernel<<<g, 64, 0, st>>>(A.mat[0], h.dims.n, d.np); g_launches++; }
+    launch_tp3(S, A, sg_.n, st);
+    if (!h.crow.empty()) {
+      dim3 g((d.np + 255) / 256, (unsigned)h.crow.size(), sg_.n);
+      const_rows_kernel<<<g, 256, 0, st>>>(S.d_CW, S.d_crow, d.np, A.mat[0]);
+      g_launches++;
+    }
   }
 }
 
@@ -254,8 +303,8 @@ static long long dense_phase_launches(const DenseDims &d) {  // mirrors the laun
   long long n = 0;
   auto chol = [&](int nt_r, int nt_c) { for (int j = 0; j < nt_c; j++) { if (j > 0) n++; n++; if (nt_r - j - 1 > 0) n++; } };
   if (d.dpg) { chol(d.R() / TILE, d.np / TILE); n++; }
-  if (d.nb == 0) return n;
-  if (d.nbp > d.nb) n++;
+  if (d.nbp == 0) return n;
+  n++;
   chol(d.M() / TILE, d.nbp / TILE);
   n += 2;
   const int ns = d.nsteps_stc();
@@ -264,14 +313,14 @@ static long long dense_phase_launches(const DenseDims &d) {  // mirrors the laun
 }
 
 template <bool CPLX>
-static void run_dense_and_scatter(Signature &S, Signature::Lane &L, const Signature::Lane::Out &o, int nel, bool want_schur, cudaStream_t st, StageEvents *ev) {
-  const SigHost &h = S.h;
-  const DenseDims &d = h.dims;
-  if (h.gen_stc) {   // pivoted-LU condensation: one kernel, writes the caller-layout outputs itself
+static void run_dense_and_scatter(const ChunkShape &sh, Lane &L, const Lane::Out &o, int nel, bool want_schur, cudaStream_t st, StageEvents *ev) {
+  const DenseDims &d = sh.d;
+  if (sh.gen_stc) {   // pivoted-LU condensation: one kernel, writes the caller-layout outputs itself
     const long long P = CPLX ? 2 : 1;
-    stc_gen_kernel<CPLX><<<nel, 512, sizeof(double) * 2 * d.M(), st>>>(d.nb, d.nbp, d.ni, d.M(), L.ws.b.Am, (long long)d.a_plane(), P * (long long)d.a_plane(),
-                                                                       o.Aii, o.Bi, o.AS, o.BS, (long long)h.ni * h.ni, (long long)h.ni,
-                                                                       (long long)h.nb * h.ni, (long long)h.nb, want_schur ? 1 : 0, L.ws.b.info);
+    stc_gen_kernel<CPLX><<<nel, 512, sizeof(double) * 2 * d.M(), st>>>(L.ws.b.nb_e, d.nbp, L.ws.b.ni_e, d.M(), L.ws.b.Am, (long long)d.a_plane(),
+                                                                       P * (long long)d.a_plane(), o.Aii, o.Bi, o.AS, o.BS, (long long)d.ni * d.ni,
+                                                                       (long long)d.ni, (long long)d.nb * d.ni, (long long)d.nb, want_schur ? 1 : 0,
+                                                                       L.ws.b.info);
     g_launches++;
     if (ev && ev->on) cudaEventRecord(ev->e[2], st);
     cudaMemcpyAsync(o.info, L.ws.b.info, sizeof(int) * nel, cudaMemcpyDeviceToDevice, st);
@@ -280,25 +329,27 @@ static void run_dense_and_scatter(Signature &S, Signature::Lane &L, const Signat
   dense_phase<CPLX>(d, L.ws.b, nel, st);
   g_launches += dense_phase_launches(d);
   if (ev && ev->on) cudaEventRecord(ev->e[2], st);
-  OutMaps mp{S.d_iota, S.d_iota, S.d_ones, S.d_ones, 0, 0, 0, 0};
-  dim3 blk(16, 16), g1((h.ni + 15) / 16, (h.ni + 15) / 16, nel);
-  scatter_condensed_kernel<CPLX><<<g1, blk, 0, st>>>(d, L.ws.b.Am, mp, o.Aii, o.Bi, (long long)h.ni * h.ni, (long long)h.ni);
+  OutMaps mp{g_lanes.d_iota, g_lanes.d_iota, g_lanes.d_ones, g_lanes.d_ones, 0, 0, 0, 0, L.ws.b.ni_e, L.ws.b.nb_e};
+  dim3 blk(16, 16), g1((d.ni + 15) / 16, (d.ni + 15) / 16, nel);
+  scatter_condensed_kernel<CPLX><<<g1, blk, 0, st>>>(d, L.ws.b.Am, mp, o.Aii, o.Bi, (long long)d.ni * d.ni, (long long)d.ni);
   g_launches++;
-  if (h.nb > 0 && want_schur) {
-    dim3 g2((h.nb + 15) / 16, (h.ni + 15) / 16, nel);
-    scatter_schur_kernel<CPLX><<<g2, blk, 0, st>>>(d, L.ws.b.Am, mp, o.AS, o.BS, (long long)h.nb * h.ni, (long long)h.nb);
+  if (d.nb > 0 && want_schur) {
+    dim3 g2((d.nb + 15) / 16, (d.ni + 15) / 16, nel);
+    scatter_schur_kernel<CPLX><<<g2, blk, 0, st>>>(d, L.ws.b.Am, mp, o.AS, o.BS, (long long)d.nb * d.ni, (long long)d.nb);
     g_launches++;
   }
   cudaMemcpyAsync(o.info, L.ws.b.info, sizeof(int) * nel, cudaMemcpyDeviceToDevice, st);
 }
 
-static void run_chunk(Signature &S, Signature::Lane &L, int ob, const GeomParams &gp, int nel, const double *d_xnod, const double *d_src, bool want_schur,
-                      cudaStream_t st, StageEvents *ev = nullptr) {
+// One chunk through the whole pipeline.  The caller has already queued the copy of the per-element dof counts into
+// L.ws.b.ni_e / nb_e on `st`.
+static void run_chunk(const ChunkShape &sh, Lane &L, int ob, const GeomParams &gp, const std::vector<Seg> &segs, int nel, const double *d_xnod,
+                      long long xnod_ld, const double *d_src, long long src_ld, bool want_schur, cudaStream_t st, StageEvents *ev = nullptr) {
   if (ev && ev->on) cudaEventRecord(ev->e[0], st);
-  run_integration(S, L, gp, nel, d_xnod, d_src, st);
+  run_integration(sh, L, gp, segs, nel, d_xnod, xnod_ld, d_src, src_ld, st);
   if (ev && ev->on) cudaEventRecord(ev->e[1], st);
-  if (S.h.cplx) run_dense_and_scatter<true>(S, L, L.out[ob], nel, want_schur, st, ev);
-  else run_dense_and_scatter<false>(S, L, L.out[ob], nel, want_schur, st, ev);
+  if (sh.d.cplx) run_dense_and_scatter<true>(sh, L, L.out[ob], nel, want_schur, st, ev);
+  else run_dense_and_scatter<false>(sh, L, L.out[ob], nel, want_schur, st, ev);
   if (ev && ev->on) cudaEventRecord(ev->e[3], st);
 }
 
@@ -362,7 +413,7 @@ int dense_debug_run(int nel, int n, int nb, int ni, const void *Gv, const void *
         else if (r == c) Wr[(size_t)r * d.np + c] = 1.0;
       }
     for (size_t c = 0; c < m1; c++) {
-      size_t row = d.np + (c < (size_t)nb ? c : d.nbp + (c - nb));
+      size_t row = d.np + (c < (size_t)nb ? c : (c < (size_t)nb + ni ? d.nbp + (c - nb) : (size_t)d.nbp + d.nip - 1));
       for (int k = 0; k < n; k++) {
         T v = Be[(size_t)k + (size_t)n * c];
         Wr[row * d.np + k] = re(v); if (CPLX) Wi[row * d.np + k] = -im(v);
@@ -372,6 +423,12 @@ int dense_debug_run(int nel, int n, int nb, int ni, const void *Gv, const void *
   HP3D_CK(cudaMemcpy(ws.b.W, hW.data(), sizeof(double) * hW.size(), cudaMemcpyHostToDevice));
   HP3D_CK(cudaMemset(ws.b.info, 0, sizeof(int) * nel));
   HP3D_CK(cudaMemset(ws.b.Am, 0, sizeof(double) * P * d.a_plane() * nel));
+  std::vector<int> cnt_i(nel, ni), cnt_b(nel, nb);
+  int *d_cnt = nullptr;
+  HP3D_CK(cudaMalloc((void **)&d_cnt, sizeof(int) * 2 * nel));
+  HP3D_CK(cudaMemcpy(d_cnt, cnt_i.data(), sizeof(int) * nel, cudaMemcpyHostToDevice));
+  HP3D_CK(cudaMemcpy(d_cnt + nel, cnt_b.data(), sizeof(int) * nel, cudaMemcpyHostToDevice));
+  ws.b.ni_e = d_cnt; ws.b.nb_e = d_cnt + nel;
   cudaStream_t st = 0;
   dense_phase<CPLX>(d, ws.b, nel, st);
   HP3D_CK(cudaGetLastError());
@@ -407,7 +464,7 @@ int dense_debug_run(int nel, int n, int nb, int ni, const void *Gv, const void *
     HP3D_CK(cudaMemcpy(BS, dBS, sizeof(double) * NS * nb * nel, cudaMemcpyDeviceToHost));
   }
   if (info) HP3D_CK(cudaMemcpy(info, ws.b.info, sizeof(int) * nel, cudaMemcpyDeviceToHost));
-  cudaFree(dpi); cudaFree(dpb); cudaFree(dsi); cudaFree(dsb); cudaFree(dA); cudaFree(dB); cudaFree(dAS); cudaFree(dBS);
+  cudaFree(dpi); cudaFree(dpb); cudaFree(dsi); cudaFree(dsb); cudaFree(dA); cudaFree(dB); cudaFree(dAS); cudaFree(dBS); cudaFree(d_cnt);
   ws.release();
   return 0;
 }

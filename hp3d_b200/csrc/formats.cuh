@@ -14,6 +14,7 @@ struct OutMaps {
   const double *sgn_b; // [nb]
   int sgn_stride_i, sgn_stride_b;  // 0: shared by the batch ; else per-element stride
   int perm_stride_i, perm_stride_b;
+  const int *ni_e, *nb_e;   // per-element dof counts (nullptr: the DenseDims values)
 };
 
 // grid = (ceil(ni/16), ceil(ni/16)+extras, batch), block (16,16).  Writes Aii (ni x ni), Bi (ni).
@@ -27,21 +28,22 @@ __global__ void scatter_condensed_kernel(DenseDims d, const double *Am, OutMaps 
   const int *pi = mp.perm_i + (long long)e * mp.perm_stride_i;
   const double *si = mp.sgn_i + (long long)e * mp.sgn_stride_i;
   constexpr int NS = CPLX ? 2 : 1;
-  if (r < d.ni && c < d.ni) {
+  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, lrow = d.nip - 1;
+  if (r < ni && c < ni) {
     int ir = pi[r], ic = pi[c];
     double s = si[r] * si[c];
     int a = ir >= ic ? ir : ic, b = ir >= ic ? ic : ir;
     double vr = S[(long long)a * M + b], vi = 0.0;
     if (CPLX) { vi = S[apl + (long long)a * M + b]; if (ir < ic) vi = -vi; if (ir == ic) vi = 0.0; }
-    double *o = Aii + (long long)e * sA * NS + ((long long)r + (long long)d.ni * c) * NS;
+    double *o = Aii + (long long)e * sA * NS + ((long long)r + (long long)ni * c) * NS;
     o[0] = s * vr;
     if (CPLX) o[1] = s * vi;
   }
-  if (blockIdx.y == 0 && threadIdx.y == 0 && r < d.ni) {
+  if (blockIdx.y == 0 && threadIdx.y == 0 && r < ni) {
     int ir = pi[r];
     double *o = Bi + (long long)e * sB * NS + (long long)r * NS;
-    o[0] = si[r] * S[(long long)d.ni * M + ir];
-    if (CPLX) o[1] = -si[r] * S[apl + (long long)d.ni * M + ir];   // b_i = conj(load row)
+    o[0] = si[r] * S[(long long)lrow * M + ir];
+    if (CPLX) o[1] = -si[r] * S[apl + (long long)lrow * M + ir];   // b_i = conj(load row)
   }
 }
 
@@ -56,18 +58,19 @@ __global__ void scatter_schur_kernel(DenseDims d, const double *Am, OutMaps mp, 
   const int *pi = mp.perm_i + (long long)e * mp.perm_stride_i, *pb = mp.perm_b + (long long)e * mp.perm_stride_b;
   const double *si = mp.sgn_i + (long long)e * mp.sgn_stride_i, *sb = mp.sgn_b + (long long)e * mp.sgn_stride_b;
   constexpr int NS = CPLX ? 2 : 1;
-  if (bq < d.nb && iq < d.ni) {
+  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, nb = mp.nb_e ? mp.nb_e[e] : d.nb, lrow = d.nip - 1;
+  if (bq < nb && iq < ni) {
     int ib = pb[bq], ii = pi[iq];
     double s = sb[bq] * si[iq];
-    double *o = AS + (long long)e * sAS * NS + ((long long)bq + (long long)d.nb * iq) * NS;
+    double *o = AS + (long long)e * sAS * NS + ((long long)bq + (long long)nb * iq) * NS;
     o[0] = s * Z[(long long)ii * M + ib];
     if (CPLX) o[1] = -s * Z[apl + (long long)ii * M + ib];
   }
-  if (blockIdx.y == 0 && threadIdx.y == 0 && bq < d.nb) {
+  if (blockIdx.y == 0 && threadIdx.y == 0 && bq < nb) {
     int ib = pb[bq];
     double *o = BS + (long long)e * sBS * NS + (long long)bq * NS;
-    o[0] = sb[bq] * Z[(long long)d.ni * M + ib];
-    if (CPLX) o[1] = -sb[bq] * Z[apl + (long long)d.ni * M + ib];
+    o[0] = sb[bq] * Z[(long long)lrow * M + ib];
+    if (CPLX) o[1] = -sb[bq] * Z[apl + (long long)lrow * M + ib];
   }
 }
 

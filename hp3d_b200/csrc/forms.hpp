@@ -235,7 +235,7 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
     S.cplx = true; S.dpg = true; S.ntest = 2 * nEE; S.ni = 2 * nEi; S.nb = 6 * nQ;
     DenseDims &D = S.dims;
     D.cplx = true; D.dpg = true; D.n = S.ntest; D.nb = S.nb; D.ni = S.ni; D.finish();
-    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + S.ni;
+    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nip - 1;   // load row: last (padded) interface row, independent of ni
     const std::complex<double> za = I * P.omega * P.eps, zc = I * P.omega * P.mu;
     const double aF = (P.test_norm == 2) ? 1.0 : P.alpha_norm + std::norm(za);
     const double aG = (P.test_norm == 2) ? 1.0 : P.alpha_norm + std::norm(zc);
@@ -348,7 +348,7 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
     S.cplx = false; S.dpg = true; S.ntest = nHH; S.ni = iH + nVi; S.nb = bH;
     DenseDims &D = S.dims;
     D.cplx = false; D.dpg = true; D.n = nHH; D.nb = S.nb; D.ni = S.ni; D.finish();
-    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + S.ni;
+    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nip - 1;   // load row: last (padded) interface row, independent of ni
     const int mapU = add_grid_map(S, hd, -1, ng, [&](int k) { return k < iH ? rowI + k : rowB + (k - iH); });
     {  // Gram (v,q) + (grad v, grad q)
       BlockBuilder b(S, ft, ft, channel(0, 0, 0, 0), no_channel());
@@ -408,7 +408,7 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
       b.finish();
     }
     {
-      BlockBuilder b(S, unit, fu, channel(1, 0, D.nbp + S.ni, 0, -1, mapU), no_channel());
+      BlockBuilder b(S, unit, fu, channel(1, 0, D.nbp + D.nip - 1, 0, -1, mapU), no_channel());
       b.add(-1, -1, F_SRC, 1.0, 1.0, 0.0);
       b.finish();
     }
@@ -440,7 +440,7 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
         b.finish();
       }
     for (int a = 0; a < 3; a++) {  // load as a COLUMN (the LU condensation eliminates rows)
-      BlockBuilder b(S, fe[a], unit, channel(1, 0, 0, D.nbp + S.ni, mapE[a]), channel(1, 1, 0, D.nbp + S.ni, mapE[a]));
+      BlockBuilder b(S, fe[a], unit, channel(1, 0, 0, D.nbp + D.nip - 1, mapE[a]), channel(1, 1, 0, D.nbp + D.nip - 1, mapE[a]));
       b.add(-1, -1, F_SRC + 2 * a, 1.0, 1.0, 0.0);
       b.add(-1, -1, F_SRC + 2 * a + 1, 1.0, 0.0, 1.0);
       b.finish();

@@ -208,7 +208,7 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
     S.cplx = true; S.dpg = true; S.ntest = 2 * nEE; S.ni = 2 * nEi; S.nb = 6 * nQ;
     DenseDims &D = S.dims;
     D.cplx = true; D.dpg = true; D.n = S.ntest; D.nb = S.nb; D.ni = S.ni; D.finish();
-    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + S.ni;
+    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nip - 1;   // load row: last (padded) interface row, independent of ni
     const std::complex<double> za = I * P.omega * P.eps, zc = I * P.omega * P.mu;
     const double aF = (P.test_norm == 2) ? 1.0 : P.alpha_norm + std::norm(za);
     const double aG = (P.test_norm == 2) ? 1.0 : P.alpha_norm + std::norm(zc);
@@ -313,7 +313,7 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
       b.finish();
     }
     {
-      BlockBuilder b(S, unit.id, fu.id, channel(1, 0, D.nbp + S.ni, 0, -1, mapU), no_channel());
+      BlockBuilder b(S, unit.id, fu.id, channel(1, 0, D.nbp + D.nip - 1, 0, -1, mapU), no_channel());
       b.addp(0, 0, 0, 0, F_SRC, 1.0, 1.0, 0.0);
       b.finish();
     }
@@ -340,7 +340,7 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
       }
     for (int a = 0; a < 2; a++) {
       if (fe[a].nT == 0) continue;
-      BlockBuilder b(S, fe[a].id, unit.id, channel(1, 0, 0, D.nbp + S.ni, mapE[a]), channel(1, 1, 0, D.nbp + S.ni, mapE[a]));
+      BlockBuilder b(S, fe[a].id, unit.id, channel(1, 0, 0, D.nbp + D.nip - 1, mapE[a]), channel(1, 1, 0, D.nbp + D.nip - 1, mapE[a]));
       for (int d = 0; d < 3; d++) {
         const CompRef v = pf_val(fe[a].kind, d);
         if (v.tc < 0) continue;
@@ -361,7 +361,7 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
     S.cplx = false; S.dpg = true; S.ntest = nHH; S.ni = iH + nVi; S.nb = bH;
     DenseDims &D = S.dims;
     D.cplx = false; D.dpg = true; D.n = nHH; D.nb = S.nb; D.ni = S.ni; D.finish();
-    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + S.ni;
+    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nip - 1;   // load row: last (padded) interface row, independent of ni
     const int mapU = add_pgrid_map(S, hd, 0, fu, [&](int k) { return k < iH ? rowI + k : rowB + (k - iH); });
     {
       BlockBuilder b(S, ft.id, ft.id, channel(0, 0, 0, 0), no_channel());

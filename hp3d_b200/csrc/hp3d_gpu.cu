@@ -38,17 +38,58 @@ int fail(int code, const char *fmt, ...) {
 
 Plan *plan_of(int id) { return (id >= 0 && id < (int)g_plans.size()) ? g_plans[id] : nullptr; }
 
-// largest chunk (elements) of this signature that fits in the free device memory
-int chunk_capacity(Signature &S, int want) {
+// largest chunk (elements per lane) of this shape that fits in the free device memory
+int chunk_capacity(const ChunkShape &sh, int want) {
   size_t fre = 0, tot = 0;
   cudaMemGetInfo(&fre, &tot);
-  // the shared arena is reusable; two lanes share the budget
-  double budget = 0.80 * (double)(fre + g_arena.dcap);
-  long long cap = (long long)(budget / (double)(Signature::NLANE * S.bytes_per_element()));
+  const size_t per = g_lanes.bytes_per_element(sh);
+  double budget = 0.80 * (double)(fre + g_arena.dcap);   // the shared arena is reusable; two lanes share the budget
+  long long cap = (long long)(budget / (double)(LaneSet::NLANE * per));
   if (cap > 1024) cap = 1024;
   if (cap > want) cap = want;
   return (int)cap;
 }
+
+// The elements of one call grouped into dense classes; inside a class sorted by signature so that a chunk is a short
+// list of equal-signature segments.
+struct ClassGroup {
+  ChunkShape shape;
+  std::vector<int> el;            // caller element indices, signature-sorted
+  std::vector<Signature *> sig;   // signature of el[i]
+};
+int build_classes(Plan *p, int nel, const int *etype, const int *norder, const int *norie, const int *norif, bool device,
+                  std::vector<ClassGroup> &out, std::string &err) {
+  std::map<std::string, std::vector<int>> bysig;
+  for (int e = 0; e < nel; e++) {
+    const int et = etype ? etype[e] : HP3D_MDLB;
+    if (et != HP3D_MDLB && et != HP3D_MDLP) { err = "element " + std::to_string(e) + ": element type " + std::to_string(et) + " is not implemented (bricks and prisms are)"; return HP3D_EINVAL; }
+    bysig[Plan::key(et, norder + 19 * e, norie + 12 * e, norif + 6 * e)].push_back(e);
+  }
+  std::map<std::string, int> cls;
+  for (auto &g : bysig) {
+    const int e0 = g.second[0];
+    Signature *S = p->get(etype ? etype[e0] : HP3D_MDLB, norder + 19 * e0, norie + 12 * e0, norif + 6 * e0, device, err);
+    if (!S) { err = "element " + std::to_string(e0) + ": " + err; return HP3D_EINVAL; }
+    const std::string k = ChunkShape::key(S->h);
+    auto it = cls.find(k);
+    if (it == cls.end()) { it = cls.emplace(k, (int)out.size()).first; out.emplace_back(); }
+    ClassGroup &C = out[it->second];
+    C.shape.absorb(S->h);
+    for (int e : g.second) { C.el.push_back(e); C.sig.push_back(S); }
+  }
+  return HP3D_OK;
+}
+// segments of the chunk [c0, c0+n) of a class
+void chunk_segments(const ClassGroup &C, size_t c0, int n, std::vector<Seg> &segs) {
+  segs.clear();
+  for (int i = 0; i < n;) {
+    int j = i + 1;
+    while (j < n && C.sig[c0 + j] == C.sig[c0 + i]) j++;
+    segs.push_back(Seg{C.sig[c0 + i], i, j - i});
+    i = j;
+  }
+}
+
 // xb = BSchur - ASchur * xi, one warp per (row, element)
 template <bool CPLX>
 __global__ void stc_bwd_kernel(int ni, int nb, const double *AS, long long sAS, const double *BS, long long sBS, const double *xi,
@@ -112,6 +153,7 @@ int hp3d_gpu_finalize(void) {
   for (Plan *p : g_plans) delete p;
   g_plans.clear();
   cudaDeviceSynchronize();
+  g_lanes.release();
   g_arena.release();
   for (int i = 0; i < 2; i++)
     if (g_lane_stream[i]) { cudaStreamDestroy(g_lane_stream[i]); g_lane_stream[i] = nullptr; }
@@ -281,15 +323,10 @@ int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, 
   if (nel < 0 || !norder || !norie || !norif || !xnod || !Aii || !Bi) return fail(HP3D_EINVAL, "null argument");
   if (p->fp.source == HP3D_SRC_TABLE && !source_qp) return fail(HP3D_EINVAL, "source == HP3D_SRC_TABLE needs source_qp");
   const bool want_schur = p->store_schur && ASchur && BSchur;
-  // ---- group by signature
-  std::map<std::string, std::vector<int>> groups;
-  for (int e = 0; e < nel; e++) {
-    const int et = etype ? etype[e] : HP3D_MDLB;
-    if (et != HP3D_MDLB && et != HP3D_MDLP) return fail(HP3D_EINVAL, "element %d: element type %d is not implemented (bricks and prisms are)", e, et);
-    groups[Plan::key(et, norder + 19 * e, norie + 12 * e, norif + 6 * e)].push_back(e);
-  }
-  const GeomParams gp = p->geom();
+  std::vector<ClassGroup> classes;
   std::string err;
+  if (int brc = build_classes(p, nel, etype, norder, norie, norif, true, classes, err)) return fail(brc, "%s", err.c_str());
+  const GeomParams gp = p->geom();
   // slot = (lane, output buffer): chunk k runs on lane k&1 and writes output buffer (k>>1)&1 of that lane
   cudaEvent_t evCompute[4], evCopy[4], evH2D[2];
   for (int i = 0; i < 4; i++) {
@@ -298,78 +335,77 @@ int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, 
   }
   for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&evH2D[i], cudaEventDisableTiming));
   int rc = HP3D_OK;
-  for (auto &g : groups) {
-    const std::vector<int> &el = g.second;
-    const int e0 = el[0];
-    Signature *S = p->get(etype ? etype[e0] : HP3D_MDLB, norder + 19 * e0, norie + 12 * e0, norif + 6 * e0, true, err);
-    if (!S) { rc = fail(HP3D_EINVAL, "element %d: %s", e0, err.c_str()); break; }
-    if (xnod_ld < 3 * S->h.nH) { rc = fail(HP3D_EINVAL, "xnod_ld=%d < 3*nrdofH=%d", xnod_ld, 3 * S->h.nH); break; }
+  std::vector<Seg> segs;
+  for (ClassGroup &C : classes) {
+    const std::vector<int> &el = C.el;
+    const ChunkShape &sh = C.shape;
+    if (xnod_ld < 3 * sh.nH_max) { rc = fail(HP3D_EINVAL, "xnod_ld=%d < 3*nrdofH=%d", xnod_ld, 3 * sh.nH_max); break; }
     int want = (int)el.size();
     if (g_max_chunk > 0) want = std::min(want, g_max_chunk);
     else if (want >= 64) want = std::max(16, (want + 7) / 8);   // >= 8 chunks: copies of finished chunks overlap compute
-    const int cap = chunk_capacity(*S, want);
-    if (cap < 1) { rc = fail(HP3D_ENOMEM, "not enough device memory for one element (%zu bytes)", S->bytes_per_element()); break; }
-    if (S->reserve(cap, err)) { rc = fail(HP3D_ENOMEM, "%s", err.c_str()); break; }
-    const SigHost &h = S->h;
-    const size_t NS = S->ns(), es = sizeof(double) * NS;
-    const size_t nx = 3 * (size_t)h.nH, nsrc = S->src_doubles();
-    const size_t bA = (size_t)h.ni * h.ni, bB = h.ni, bAS = (size_t)h.nb * h.ni, bBS = h.nb;
-    const int chunk = cap;
+    const int cap = chunk_capacity(sh, want);
+    if (cap < 1) { rc = fail(HP3D_ENOMEM, "not enough device memory for one element"); break; }
+    if (g_lanes.reserve(sh, cap, err)) { rc = fail(HP3D_ENOMEM, "%s", err.c_str()); break; }
+    const size_t NS = sh.ns(), es = sizeof(double) * NS;
+    const size_t nx = 3 * (size_t)sh.nH_max, nsrc = sh.src_max;
+    const size_t sA = (size_t)sh.d.ni * sh.d.ni, sB = sh.d.ni, sS = (size_t)sh.d.nb * sh.d.ni, sT = sh.d.nb;   // device staging strides
+    const int chunk = cap, lcap = g_lanes.cap;
     int nchunk = 0;
     auto collect_info = [&](int k) {   // host side of chunk k: wait for its D2H, publish info[]
       const int slot = (k & 1) * 2 + ((k >> 1) & 1);
       cudaEventSynchronize(evCopy[slot]);
       const size_t pc0 = (size_t)k * chunk;
       const int pn = (int)std::min(el.size() - pc0, (size_t)chunk);
-      const int *hi = S->lane[k & 1].out[(k >> 1) & 1].h_info;
+      const int *hi = g_lanes.lane[k & 1].out[(k >> 1) & 1].h_info;
       for (int i = 0; i < pn; i++) { const int e = el[pc0 + i]; if (info) info[e] = hi[i]; }
     };
     for (size_t c0 = 0; c0 < el.size(); c0 += chunk, nchunk++) {
       const int n = (int)std::min(el.size() - c0, (size_t)chunk), ln = nchunk & 1, ob = (nchunk >> 1) & 1, slot = ln * 2 + ob;
-      Signature::Lane &L = S->lane[ln];
+      Lane &L = g_lanes.lane[ln];
       cudaStream_t st = g_lane_stream[ln];
-      const bool trace = getenv("HP3D_TRACE") != nullptr;
-      auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-      const double tA = now();
       if (nchunk >= 4) collect_info(nchunk - 4);              // this slot's previous results are on the host
-      const double tB = now();
       if (nchunk >= 2) cudaEventSynchronize(evH2D[ln]);        // the lane's pinned input staging has been consumed
-      const double tC = now();
       for (int i = 0; i < n; i++) {
         const int e = el[c0 + i];
-        memcpy(L.h_xnod + (size_t)i * nx, xnod + (size_t)e * xnod_ld, sizeof(double) * nx);
-        if (gp.source == HP3D_SRC_TABLE) memcpy(L.h_src + (size_t)i * nsrc, (const double *)source_qp + (size_t)e * source_ld, sizeof(double) * nsrc);
+        const SigHost &h = C.sig[c0 + i]->h;
+        memcpy(L.h_xnod + (size_t)i * nx, xnod + (size_t)e * xnod_ld, sizeof(double) * 3 * h.nH);
+        if (gp.source == HP3D_SRC_TABLE)
+          memcpy(L.h_src + (size_t)i * nsrc, (const double *)source_qp + (size_t)e * source_ld, sizeof(double) * h.nint * (h.cplx ? 6 : 1));
+        L.h_cnt[i] = h.ni; L.h_cnt[lcap + i] = h.nb;
       }
       cudaMemcpyAsync(L.d_xnod, L.h_xnod, sizeof(double) * nx * n, cudaMemcpyHostToDevice, st);
       if (gp.source == HP3D_SRC_TABLE) cudaMemcpyAsync(L.d_src, L.h_src, sizeof(double) * nsrc * n, cudaMemcpyHostToDevice, st);
+      cudaMemcpyAsync(L.ws.b.ni_e, L.h_cnt, sizeof(int) * n, cudaMemcpyHostToDevice, st);
+      cudaMemcpyAsync(L.ws.b.nb_e, L.h_cnt + lcap, sizeof(int) * n, cudaMemcpyHostToDevice, st);
       cudaEventRecord(evH2D[ln], st);
-      run_chunk(*S, L, ob, gp, n, L.d_xnod, L.d_src, want_schur, st);
+      chunk_segments(C, c0, n, segs);
+      run_chunk(sh, L, ob, gp, segs, n, L.d_xnod, (long long)nx, L.d_src, (long long)nsrc, want_schur, st);
       cudaEventRecord(evCompute[slot], st);
       cudaStreamWaitEvent(g_copy, evCompute[slot], 0);
-      // D2H straight into the caller's arrays; runs of consecutive elements with dense strides are merged
-      const Signature::Lane::Out &o = L.out[ob];
+      // D2H straight into the caller's arrays; runs of consecutive elements with equal sizes and dense strides are merged
+      const Lane::Out &o = L.out[ob];
       for (int i = 0; i < n;) {
+        const SigHost &h = C.sig[c0 + i]->h;
         int j = i + 1;
-        while (j < n && el[c0 + j] == el[c0 + j - 1] + 1) j++;
+        while (j < n && el[c0 + j] == el[c0 + j - 1] + 1 && C.sig[c0 + j]->h.ni == h.ni && C.sig[c0 + j]->h.nb == h.nb) j++;
         const int e = el[c0 + i], run = j - i;
-        auto copy = [&](void *dst, long long stride, const double *src, size_t blk) {
+        auto copy = [&](void *dst, long long stride, const double *src, size_t dstride, size_t blk) {
           if (blk == 0) return;
-          if ((size_t)stride == blk)
-            cudaMemcpyAsync((char *)dst + es * stride * e, src + NS * blk * i, es * blk * run, cudaMemcpyDeviceToHost, g_copy);
+          if ((size_t)stride == blk && dstride == blk)
+            cudaMemcpyAsync((char *)dst + es * stride * e, src + NS * dstride * i, es * blk * run, cudaMemcpyDeviceToHost, g_copy);
           else
-            cudaMemcpy2DAsync((char *)dst + es * stride * e, es * stride, src + NS * blk * i, es * blk, es * blk, run, cudaMemcpyDeviceToHost, g_copy);
+            cudaMemcpy2DAsync((char *)dst + es * stride * e, es * stride, src + NS * dstride * i, es * dstride, es * blk, run, cudaMemcpyDeviceToHost, g_copy);
         };
-        copy(Aii, sAii, o.Aii, bA);
-        copy(Bi, sBi, o.Bi, bB);
-        if (want_schur) { copy(ASchur, sAS, o.AS, bAS); copy(BSchur, sBS, o.BS, bBS); }
+        copy(Aii, sAii, o.Aii, sA, (size_t)h.ni * h.ni);
+        copy(Bi, sBi, o.Bi, sB, (size_t)h.ni);
+        if (want_schur) { copy(ASchur, sAS, o.AS, sS, (size_t)h.nb * h.ni); copy(BSchur, sBS, o.BS, sT, (size_t)h.nb); }
         i = j;
       }
       cudaMemcpyAsync(o.h_info, o.info, sizeof(int) * n, cudaMemcpyDeviceToHost, g_copy);   // pinned: stays asynchronous
       cudaEventRecord(evCopy[slot], g_copy);
-      if (trace) fprintf(stderr, "[hp3d trace] chunk %d lane %d: t=%.1f wait_copy %.1f wait_h2d %.1f enqueue %.1f ms\n", nchunk, ln, tA, tB - tA, tC - tB, now() - tC);
     }
     for (int k = std::max(0, nchunk - 4); k < nchunk; k++) collect_info(k);
-    for (int e : el) { if (ni_out) ni_out[e] = h.ni; if (nb_out) nb_out[e] = h.nb; }
+    for (size_t i = 0; i < el.size(); i++) { const SigHost &h = C.sig[i]->h; if (ni_out) ni_out[el[i]] = h.ni; if (nb_out) nb_out[el[i]] = h.nb; }
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) { rc = fail(HP3D_ENODEV, "CUDA error in elem_batch: %s", cudaGetErrorString(ce)); break; }
   }
@@ -398,16 +434,17 @@ int hp3d_gpu_quad_points(int plan, int nel, const int *etype, const int *norder,
   for (int e = 0; e < nel; e++) {  // not a hot path: one element at a time
     Signature *S = p->get(etype ? etype[e] : HP3D_MDLB, norder + 19 * e, norie + 12 * e, norif + 6 * e, true, err);
     if (!S) return fail(HP3D_EINVAL, "element %d: %s", e, err.c_str());
-    if (S->reserve(1, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());
+    ChunkShape sh; sh.absorb(S->h);
+    if (g_lanes.reserve(sh, 1, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());
     const SigHost &h = S->h;
-    Signature::Lane &L = S->lane[0];
+    Lane &L = g_lanes.lane[0];
     CUDA_TRY(cudaMemcpyAsync(L.d_xnod, xnod + (size_t)e * xnod_ld, sizeof(double) * 3 * h.nH, cudaMemcpyHostToDevice, g_compute));
     SigTables sg;
     sg.tab = S->d_tab; sg.wq = S->d_wq; sg.hdof = S->d_hdof; sg.nH = h.nH; sg.nint = h.nint;
     sg.ttab = S->d_ttab ? S->d_ttab + h.geo_toff : nullptr; sg.nT = h.geo_nT;
     for (int i = 0; i < 3; i++) sg.nq[i] = h.nq[i];
-    if (h.etype == HP3D_MDLP) geom_fields_prism_kernel<<<(h.nint + 127) / 128, 128, 0, g_compute>>>(sg, gp, 1, L.d_xnod, 3LL * h.nH, nullptr, L.d_WF, L.ws.b.info);
-    else geom_fields_kernel<<<(h.nint + 127) / 128, 128, 0, g_compute>>>(sg, gp, 1, L.d_xnod, 3LL * h.nH, nullptr, L.d_WF, L.ws.b.info);
+    if (h.etype == HP3D_MDLP) geom_fields_prism_kernel<<<(h.nint + 127) / 128, 128, 0, g_compute>>>(sg, gp, 1, L.d_xnod, 3LL * h.nH, nullptr, 0, L.d_WF, L.ws.b.info);
+    else geom_fields_kernel<<<(h.nint + 127) / 128, 128, 0, g_compute>>>(sg, gp, 1, L.d_xnod, 3LL * h.nH, nullptr, 0, L.d_WF, L.ws.b.info);
     f.resize(3 * (size_t)h.nint);
     CUDA_TRY(cudaMemcpyAsync(f.data(), L.d_WF + (size_t)F_X * h.nint, sizeof(double) * 3 * h.nint, cudaMemcpyDeviceToHost, g_compute));
     CUDA_TRY(cudaStreamSynchronize(g_compute));
@@ -453,60 +490,69 @@ int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, con
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
   if (nel <= 0 || reps <= 0 || lanes < 1 || lanes > 2) return fail(HP3D_EINVAL, "bad sizes");
   if (p->fp.source == HP3D_SRC_TABLE) return fail(HP3D_EINVAL, "bench: table sources are not supported");
-  std::map<std::string, std::vector<int>> groups;
-  for (int e = 0; e < nel; e++) groups[Plan::key(etype ? etype[e] : HP3D_MDLB, norder + 19 * e, norie + 12 * e, norif + 6 * e)].push_back(e);
-  const GeomParams gp = p->geom();
+  std::vector<ClassGroup> classes;
   std::string err;
-  struct Grp { Signature *S; double *dx; int n, chunk; };
+  if (int brc = build_classes(p, nel, etype, norder, norie, norif, true, classes, err)) return fail(brc, "%s", err.c_str());
+  const GeomParams gp = p->geom();
+  // resident inputs per class: geometry dofs (uniform stride 3*nH_max) and the per-element dof counts
+  struct Grp { ClassGroup *C; double *dx; int *dcnt; int n, chunk; };
   std::vector<Grp> gs;
-  for (auto &g : groups) {
-    const int e0 = g.second[0];
-    Signature *S = p->get(etype ? etype[e0] : HP3D_MDLB, norder + 19 * e0, norie + 12 * e0, norif + 6 * e0, true, err);
-    if (!S) return fail(HP3D_EINVAL, "%s", err.c_str());
-    int want = (int)g.second.size();
+  for (ClassGroup &C : classes) {
+    int want = (int)C.el.size();
     if (lanes == 2) want = (want + 1) / 2;
     if (max_chunk > 0 && want > max_chunk) want = max_chunk;
-    const int cap = chunk_capacity(*S, want);
+    const int cap = chunk_capacity(C.shape, want);
     if (cap < 1) return fail(HP3D_ENOMEM, "not enough device memory");
-    if (S->reserve(cap, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());
-    const size_t nx = 3 * (size_t)S->h.nH;
-    std::vector<double> hx(nx * g.second.size());
-    for (size_t i = 0; i < g.second.size(); i++) memcpy(hx.data() + i * nx, xnod + (size_t)g.second[i] * xnod_ld, sizeof(double) * nx);
-    double *dx;
+    if (g_lanes.reserve(C.shape, cap, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());   // grows the arena to the largest class
+    const size_t nx = 3 * (size_t)C.shape.nH_max, n = C.el.size();
+    std::vector<double> hx(nx * n, 0.0);
+    std::vector<int> hc(2 * n);
+    for (size_t i = 0; i < n; i++) {
+      memcpy(hx.data() + i * nx, xnod + (size_t)C.el[i] * xnod_ld, sizeof(double) * 3 * C.sig[i]->h.nH);
+      hc[i] = C.sig[i]->h.ni; hc[n + i] = C.sig[i]->h.nb;
+    }
+    double *dx; int *dc;
     CUDA_TRY(cudaMalloc(&dx, sizeof(double) * hx.size()));
     CUDA_TRY(cudaMemcpy(dx, hx.data(), sizeof(double) * hx.size(), cudaMemcpyHostToDevice));
-    gs.push_back(Grp{S, dx, (int)g.second.size(), cap});
+    CUDA_TRY(cudaMalloc(&dc, sizeof(int) * hc.size()));
+    CUDA_TRY(cudaMemcpy(dc, hc.data(), sizeof(int) * hc.size(), cudaMemcpyHostToDevice));
+    gs.push_back(Grp{&C, dx, dc, (int)n, cap});
   }
   std::vector<StageEvents> evs;
-  cudaEvent_t t0, t1, tj;
+  cudaEvent_t t0, t1, tj, tsw[2];
   CUDA_TRY(cudaEventCreate(&t0)); CUDA_TRY(cudaEventCreate(&t1)); CUDA_TRY(cudaEventCreateWithFlags(&tj, cudaEventDisableTiming));
+  for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&tsw[i], cudaEventDisableTiming));
   const long long l0 = g_launches;
   CUDA_TRY(cudaStreamSynchronize(g_lane_stream[0]));
   CUDA_TRY(cudaStreamSynchronize(g_lane_stream[1]));
   CUDA_TRY(cudaEventRecord(t0, g_lane_stream[0]));
   if (lanes == 2) CUDA_TRY(cudaStreamWaitEvent(g_lane_stream[1], t0, 0));   // lane 1 starts inside the timed region
   int k = 0;
-  cudaEvent_t tsw[2];
-  for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&tsw[i], cudaEventDisableTiming));
+  std::vector<Seg> segs;
   for (int r = 0; r < reps; r++)
     for (Grp &g : gs) {
-      if (!g.S->bound()) {   // another group's buffers occupy the arena: both lanes must drain before they are reused
+      if (gs.size() > 1) {   // another class's buffers occupy the arena: both lanes must drain before they are re-bound
         if (lanes == 2) {
           for (int i = 0; i < 2; i++) cudaEventRecord(tsw[i], g_lane_stream[i]);
           cudaStreamWaitEvent(g_lane_stream[0], tsw[1], 0); cudaStreamWaitEvent(g_lane_stream[1], tsw[0], 0);
         }
-        if (g.S->reserve(g.chunk, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());
+        g_arena.owner = nullptr;   // force the re-layout for this class (pointer arithmetic only: the arena is large enough)
+        if (g_lanes.reserve(g.C->shape, g.chunk, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());
       }
+      const long long nx = 3LL * g.C->shape.nH_max;
       for (int c0 = 0; c0 < g.n; c0 += g.chunk, k++) {
         const int n = std::min(g.n - c0, g.chunk), ln = lanes == 2 ? (k & 1) : 0;
+        Lane &L = g_lanes.lane[ln];
         StageEvents ev;
         ev.on = (lanes == 1);
         if (ev.on) for (int i = 0; i < 4; i++) cudaEventCreate(&ev.e[i]);
-        run_chunk(*g.S, g.S->lane[ln], 0, gp, n, g.dx + (size_t)c0 * 3 * g.S->h.nH, nullptr, p->store_schur != 0, g_lane_stream[ln], &ev);
+        cudaMemcpyAsync(L.ws.b.ni_e, g.dcnt + c0, sizeof(int) * n, cudaMemcpyDeviceToDevice, g_lane_stream[ln]);
+        cudaMemcpyAsync(L.ws.b.nb_e, g.dcnt + g.n + c0, sizeof(int) * n, cudaMemcpyDeviceToDevice, g_lane_stream[ln]);
+        chunk_segments(*g.C, (size_t)c0, n, segs);
+        run_chunk(g.C->shape, L, 0, gp, segs, n, g.dx + (size_t)c0 * nx, nx, nullptr, 0, p->store_schur != 0, g_lane_stream[ln], &ev);
         if (ev.on) evs.push_back(ev);
       }
     }
-  for (int i = 0; i < 2; i++) cudaEventDestroy(tsw[i]);
   if (lanes == 2) { CUDA_TRY(cudaEventRecord(tj, g_lane_stream[1])); CUDA_TRY(cudaStreamWaitEvent(g_lane_stream[0], tj, 0)); }
   CUDA_TRY(cudaEventRecord(t1, g_lane_stream[0]));
   CUDA_TRY(cudaStreamSynchronize(g_lane_stream[0]));
@@ -527,7 +573,8 @@ int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, con
   if (ms_dense) *ms_dense = md;
   if (launches) *launches = g_launches - l0;
   cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(tj);
-  for (Grp &g : gs) cudaFree(g.dx);
+  for (int i = 0; i < 2; i++) cudaEventDestroy(tsw[i]);
+  for (Grp &g : gs) { cudaFree(g.dx); cudaFree(g.dcnt); }
   return HP3D_OK;
 }
 
@@ -545,7 +592,8 @@ int hp3d_gpu_integrate_debug_t(int plan, int etype, const int *norder, const int
   std::string err;
   Signature *S = p->get(etype, norder, norie, norif, true, err);
   if (!S) return fail(HP3D_EINVAL, "%s", err.c_str());
-  if (S->reserve(1, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());
+  ChunkShape sh; sh.absorb(S->h);
+  if (g_lanes.reserve(sh, 1, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());
   const SigHost &h = S->h;
   const DenseDims &d = h.dims;
   const size_t P = d.planes();
@@ -553,13 +601,14 @@ int hp3d_gpu_integrate_debug_t(int plan, int etype, const int *norder, const int
   if (dims) { dims[0] = d.np; dims[1] = d.nbp; dims[2] = d.nip; dims[3] = d.n; dims[4] = d.nb; dims[5] = d.ni; dims[6] = d.dpg ? d.R() : d.M(); dims[7] = (int)P; }
   if (!W) return HP3D_OK;
   if ((size_t)cap_doubles < need) return fail(HP3D_EINVAL, "integrate_debug: need %zu doubles", need);
-  Signature::Lane &L = S->lane[0];
+  Lane &L = g_lanes.lane[0];
   CUDA_TRY(cudaMemcpyAsync(L.d_xnod, xnod, sizeof(double) * 3 * h.nH, cudaMemcpyHostToDevice, g_compute));
   if (p->fp.source == HP3D_SRC_TABLE) {
     if (!source_qp) return fail(HP3D_EINVAL, "source table missing");
     CUDA_TRY(cudaMemcpyAsync(L.d_src, source_qp, sizeof(double) * S->src_doubles(), cudaMemcpyHostToDevice, g_compute));
   }
-  run_integration(*S, L, p->geom(), 1, L.d_xnod, L.d_src, g_compute);
+  std::vector<Seg> segs(1, Seg{S, 0, 1});
+  run_integration(sh, L, p->geom(), segs, 1, L.d_xnod, 3LL * h.nH, L.d_src, (long long)S->src_doubles(), g_compute);
   CUDA_TRY(cudaMemcpyAsync(W, d.dpg ? L.ws.b.W : L.ws.b.Am, sizeof(double) * need, cudaMemcpyDeviceToHost, g_compute));
   CUDA_TRY(cudaStreamSynchronize(g_compute));
   CUDA_TRY(cudaGetLastError());

@@ -78,7 +78,7 @@ __device__ inline void sin_potential_hess(double a, const double x[3], double &p
 // All weight fields of one quadrature point from (x, J, w): determinant (Sarrus) and inverse by cofactors as
 // src/element/util/geom.F90:57-113, then the Piola maps folded into per-point fields.  J[c + 3*d] = dx_c/dxi_d.
 __device__ __forceinline__ void emit_fields(const GeomParams &gp, int e, int q, int nint, const double x[3], const double J[9], double w,
-                                            const double *__restrict__ src_tab, double *__restrict__ WF, int *__restrict__ info) {
+                                            const double *__restrict__ src_tab, long long src_ld, double *__restrict__ WF, int *__restrict__ info) {
   const double det = J[0] * J[4] * J[8] + J[1] * J[5] * J[6] + J[2] * J[3] * J[7] - J[2] * J[4] * J[6] - J[0] * J[5] * J[7] - J[1] * J[3] * J[8];
   if (!(det > 0.0)) info[e] = -1;
   double Ji[9];  // Ji[a + 3*c] = dxi_a/dx_c
@@ -113,13 +113,13 @@ __device__ __forceinline__ void emit_fields(const GeomParams &gp, int e, int q, 
   double s[6] = {0, 0, 0, 0, 0, 0};
   if (gp.kind == 1 || gp.kind == 2) {  // Poisson: f(x)
     double f = 0.0;
-    if (gp.source == 9) f = src_tab[(long long)e * nint + q];
+    if (gp.source == 9) f = src_tab[(long long)e * src_ld + q];
     else if (gp.source == 1) { double p, h[9]; sin_potential_hess(3.14159265358979323846, x, p, h); f = -(h[0] + h[4] + h[8]); }
     s[0] = wd * f;
   } else {  // Maxwell: complex vector zJ(x)
     double jr[3] = {0, 0, 0}, ji[3] = {0, 0, 0};
     if (gp.source == 9) {
-      const double *t = src_tab + ((long long)e * nint + q) * 6;
+      const double *t = src_tab + (long long)e * src_ld + (long long)q * 6;
       for (int c = 0; c < 3; c++) { jr[c] = t[2 * c]; ji[c] = t[2 * c + 1]; }
     } else if (gp.source == 1) {
       double p, h[9], cc[3];
@@ -152,8 +152,8 @@ __device__ __forceinline__ void emit_fields(const GeomParams &gp, int e, int q, 
 
 // grid: ceil(nel*nint/128) x 1, block 128
 __global__ void __launch_bounds__(128) geom_fields_kernel(SigTables sg, GeomParams gp, int nel, const double *__restrict__ xnod,
-                                                          long long xnod_ld, const double *__restrict__ src_tab, double *__restrict__ WF,
-                                                          int *__restrict__ info) {
+                                                          long long xnod_ld, const double *__restrict__ src_tab, long long src_ld,
+                                                          double *__restrict__ WF, int *__restrict__ info) {
   __shared__ double sH[3][TABSZ], sdH[3][TABSZ];
   for (int i = threadIdx.x; i < 3 * TABSZ; i += blockDim.x) {
     int ax = i / TABSZ, r = i % TABSZ;
@@ -182,14 +182,14 @@ __global__ void __launch_bounds__(128) geom_fields_kernel(SigTables sg, GeomPara
     }
   }
   const double w = sg.wq[qx] * sg.wq[MAXQ + qy] * sg.wq[2 * MAXQ + qz];
-  emit_fields(gp, e, q, sg.nint, x, J, w, src_tab, WF, info);
+  emit_fields(gp, e, q, sg.nint, x, J, w, src_tab, src_ld, WF, info);
 }
 
 // Prism variant: geometry dofs are sign * T[t](x,y) * H[zi](z) with the triangle tables (value, d/dx, d/dy) of the
 // signature's geometry list in global memory; quadrature point q = qt + nqt*qz, weights wq[0..nqt) | wq[nqt..nqt+nqz).
 // grid: ceil(nel*nint/128), block 128
 __global__ void __launch_bounds__(128) geom_fields_prism_kernel(SigTables sg, GeomParams gp, int nel, const double *__restrict__ xnod,
-                                                                long long xnod_ld, const double *__restrict__ src_tab,
+                                                                long long xnod_ld, const double *__restrict__ src_tab, long long src_ld,
                                                                 double *__restrict__ WF, int *__restrict__ info) {
   __shared__ double sH[TABSZ], sdH[TABSZ];
   for (int i = threadIdx.x; i < TABSZ; i += blockDim.x) {
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(128) geom_fields_prism_kernel(SigTables sg, Ge
     }
   }
   const double w = sg.wq[qt] * sg.wq[nqt + qz];
-  emit_fields(gp, e, q, sg.nint, x, J, w, src_tab, WF, info);
+  emit_fields(gp, e, q, sg.nint, x, J, w, src_tab, src_ld, WF, info);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -50,7 +50,7 @@ def test_uw_maxwell_integration_vs_oracle(oracle, gpu, p, curved):
     Gg = Gi[np.ix_(perm, perm)]
     Gu = np.triu(G); Go = Gu + np.triu(Gu, 1).conj().T
     assert relerr(Gg, Go) < 1e-13
-    rows = np.r_[np_ + nbp + np.arange(ni), np_ + np.arange(nb), np_ + nbp + ni]
+    rows = np.r_[np_ + nbp + np.arange(ni), np_ + np.arange(nb), np_ + nbp + d["nip"] - 1]   # load: last padded interface row
     Bg = Wc[rows][:, :n].conj().T[perm]
     assert relerr(Bg[:, :ni], S[:, :ni]) < 1e-13          # trace pairings
     assert relerr(Bg[:, ni:ni + nb], S[:, ni:ni + nb]) < 1e-13

@@ -51,7 +51,7 @@ def test_prism_uw_integration_vs_oracle(oracle, gpu, p, pz, curved):
     Gg = Gi[np.ix_(perm, perm)]
     Gu = np.triu(G); Go = Gu + np.triu(Gu, 1).conj().T
     assert relerr(Gg, Go) < 1e-13, relerr(Gg, Go)
-    rows = np.r_[np_ + nbp + np.arange(ni), np_ + np.arange(nb), np_ + nbp + ni]
+    rows = np.r_[np_ + nbp + np.arange(ni), np_ + np.arange(nb), np_ + nbp + d["nip"] - 1]   # load: last padded interface row
     Bg = Wc[rows][:, :n].conj().T[perm]
     assert relerr(Bg[:, :ni], S[:, :ni]) < 1e-13, relerr(Bg[:, :ni], S[:, :ni])          # trace pairings
     assert relerr(Bg[:, ni:ni + nb], S[:, ni:ni + nb]) < 1e-13
