@@ -161,6 +161,40 @@ class ElemEngine:
         _lib.check(rc)
         return dict(Aii=Aii, Bi=Bi, ASchur=AS, BSchur=BS, ni=nio, nb=nbo, info=info)
 
+    def _descr(self, norder, norient_edge, norient_face, xnod, etype):
+        norder, noe, nof = _i32(norder).reshape(-1, 19), _i32(norient_edge).reshape(-1, 12), _i32(norient_face).reshape(-1, 6)
+        xnod = np.ascontiguousarray(xnod, dtype=np.float64)
+        nel = norder.shape[0]
+        et = None if etype is None else _i32(np.broadcast_to(etype, (nel,)))
+        return norder, noe, nof, xnod, nel, et
+
+    def elem_bwd_batch(self, norder, norient_edge, norient_face, xnod, xi, etype=None):
+        """stc_bwd without stored factors (hp3d_gpu_elem_bwd_batch): recompute the elements on the device and return
+        xb = BSchur - ASchur xi, (nel, nb_max) [+ nb per element].  xi: (nel, ni_max) interface dofs (rows of Aii)."""
+        norder, noe, nof, xnod, nel, et = self._descr(norder, norient_edge, norient_face, xnod, etype)
+        xi = np.ascontiguousarray(xi, dtype=self.dtype)
+        nb = max(self.sizes(norder[e], MDLB if et is None else int(et[e]))[1] for e in range(nel))
+        xb = np.zeros((nel, max(nb, 1)), self.dtype)
+        nbo = np.zeros(nel, np.int32); info = np.zeros(nel, np.int32)
+        f = self.L.hp3d_gpu_elem_bwd_batch
+        ll = C.c_longlong
+        f.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, ll, C.c_void_p, ll, C.c_void_p, ll, C.c_void_p, C.c_void_p]
+        _lib.check(f(self.plan, nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(xnod[0].size), None, 0,
+                     _ptr(xi), xi[0].size, _ptr(xb), xb[0].size, _ptr(nbo), _ptr(info)))
+        return dict(xb=xb, nb=nbo, info=info)
+
+    def elem_residual_batch(self, norder, norient_edge, norient_face, xnod, xi, xb, etype=None):
+        """DPG element residuals ||l - B u||^2_{V'} (hp3d_gpu_elem_residual_batch) for u = (xi | xb); returns (nel,) float64."""
+        norder, noe, nof, xnod, nel, et = self._descr(norder, norient_edge, norient_face, xnod, etype)
+        xi = np.ascontiguousarray(xi, dtype=self.dtype); xb = np.ascontiguousarray(xb, dtype=self.dtype)
+        res = np.zeros(nel); info = np.zeros(nel, np.int32)
+        f = self.L.hp3d_gpu_elem_residual_batch
+        ll = C.c_longlong
+        f.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, ll, C.c_void_p, ll, C.c_void_p, ll, C.c_void_p, C.c_void_p]
+        _lib.check(f(self.plan, nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(xnod[0].size), None, 0,
+                     _ptr(xi), xi[0].size, _ptr(xb), xb[0].size, _ptr(res), _ptr(info)))
+        return dict(resid=res, info=info)
+
     @staticmethod
     def unpack(res, e):
         """Element e of an elem_stc_batch result as (Aii (ni,ni), Bi (ni), ASchur (nb,ni), BSchur (nb)) numpy arrays."""

@@ -89,8 +89,9 @@ static void chol_trapezoid(double *Mbase, long long plane, long long batch_strid
 }
 
 // The whole dense phase for `batch` elements whose W (DPG) or Am (Galerkin) buffers have been filled.
+// `normal_eq_only`: stop after A = B~^H B~ (the uncondensed DPG system incl. the load row: what the residual needs).
 template <bool CPLX>
-static void dense_phase(const DenseDims &d, const DenseBuffers &b, int batch, cudaStream_t st) {
+static void dense_phase(const DenseDims &d, const DenseBuffers &b, int batch, cudaStream_t st, bool normal_eq_only = false) {
   const long long P = CPLX ? 2 : 1;
   const long long lp = (long long)TILE * TILE;
   const int M = d.M();
@@ -105,7 +106,7 @@ static void dense_phase(const DenseDims &d, const DenseBuffers &b, int batch, cu
     g.K = d.np; g.lower_only = 1; g.diag_shift = 0; g.use_cin = 0; g.alpha = 1.0;
     launch_gemm<CPLX>(g, M / TILE, M / TILE, batch, st);
   }
-  if (d.nb == 0) return;
+  if (d.nb == 0 || normal_eq_only) return;
   const long long apl = (long long)d.a_plane(), ab = P * apl;
   {  // padded bubble rows [nb_e, nbp): unit diagonal keeps the factorization regular
     dim3 grid(d.nbp / 64, batch);

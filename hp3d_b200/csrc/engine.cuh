@@ -160,7 +160,10 @@ struct Lane {
   Out out[2];   // chunk outputs (device staging), double-buffered: the D2H of one chunk overlaps the lane's next chunk
   double *h_xnod = nullptr, *h_src = nullptr;                          // pinned host staging of the chunk inputs
   int *h_cnt = nullptr;                                                // pinned [2][batch]: ni_e | nb_e
+  // back-substitution / residual modes: solution dofs in (xi | xb), results out (xb or one residual per element)
+  double *d_xi = nullptr, *d_xb = nullptr, *d_res = nullptr, *h_xi = nullptr, *h_xb = nullptr, *h_res = nullptr;
 };
+enum ChunkMode { MODE_ELEM = 0, MODE_BWD = 1, MODE_RESID = 2 };
 struct LaneSet {
   static constexpr int NLANE = 2;
   Lane lane[NLANE];
@@ -188,6 +191,10 @@ struct LaneSet {
       L.h_xnod = hm.take<double>((size_t)3 * sh.nH_max * batch);
       L.h_src = hm.take<double>(sh.src_max * batch);
       L.h_cnt = hm.take<int>(2 * (size_t)batch);
+      L.d_xi = dm.take<double>(NS * (size_t)d.ni * batch); L.d_xb = dm.take<double>(NS * ((size_t)d.nb + 1) * batch);
+      L.d_res = dm.take<double>(batch);
+      L.h_xi = hm.take<double>(NS * (size_t)d.ni * batch); L.h_xb = hm.take<double>(NS * ((size_t)d.nb + 1) * batch);
+      L.h_res = hm.take<double>(batch);
     }
   }
   size_t bytes_per_element(const ChunkShape &sh) {   // device bytes per element of ONE lane (alignment slack excluded)
@@ -313,8 +320,17 @@ static long long dense_phase_launches(const DenseDims &d) {  // mirrors the laun
 }
 
 template <bool CPLX>
-static void run_dense_and_scatter(const ChunkShape &sh, Lane &L, const Lane::Out &o, int nel, bool want_schur, cudaStream_t st, StageEvents *ev) {
+static void run_dense_and_scatter(const ChunkShape &sh, Lane &L, const Lane::Out &o, int nel, bool want_schur, cudaStream_t st, StageEvents *ev,
+                                  int mode) {
   const DenseDims &d = sh.d;
+  if (mode == MODE_RESID) {   // uncondensed DPG system, then eta^2 = v^H A v
+    dense_phase<CPLX>(d, L.ws.b, nel, st, true);
+    dpg_residual_kernel<CPLX><<<nel, 256, sizeof(double) * 2 * d.M(), st>>>(d, L.ws.b.Am, L.ws.b.ni_e, L.ws.b.nb_e, L.d_xi, (long long)d.ni, L.d_xb,
+                                                                           (long long)d.nb + 1, L.d_res);
+    g_launches += 2;
+    cudaMemcpyAsync(o.info, L.ws.b.info, sizeof(int) * nel, cudaMemcpyDeviceToDevice, st);
+    return;
+  }
   if (sh.gen_stc) {   // pivoted-LU condensation: one kernel, writes the caller-layout outputs itself
     const long long P = CPLX ? 2 : 1;
     stc_gen_kernel<CPLX><<<nel, 512, sizeof(double) * 2 * d.M(), st>>>(L.ws.b.nb_e, d.nbp, L.ws.b.ni_e, d.M(), L.ws.b.Am, (long long)d.a_plane(),
@@ -324,6 +340,12 @@ static void run_dense_and_scatter(const ChunkShape &sh, Lane &L, const Lane::Out
     g_launches++;
     if (ev && ev->on) cudaEventRecord(ev->e[2], st);
     cudaMemcpyAsync(o.info, L.ws.b.info, sizeof(int) * nel, cudaMemcpyDeviceToDevice, st);
+    if (mode == MODE_BWD && d.nb > 0) {
+      dim3 gb((d.nb + 7) / 8, nel);
+      stc_bwd_kernel<CPLX><<<gb, 256, 0, st>>>(L.ws.b.ni_e, L.ws.b.nb_e, 0, 0, o.AS, (long long)d.nb * d.ni, o.BS, (long long)d.nb, L.d_xi, (long long)d.ni,
+                                               L.d_xb, (long long)d.nb + 1);
+      g_launches++;
+    }
     return;
   }
   dense_phase<CPLX>(d, L.ws.b, nel, st);
@@ -339,17 +361,24 @@ static void run_dense_and_scatter(const ChunkShape &sh, Lane &L, const Lane::Out
     g_launches++;
   }
   cudaMemcpyAsync(o.info, L.ws.b.info, sizeof(int) * nel, cudaMemcpyDeviceToDevice, st);
+  if (mode == MODE_BWD && d.nb > 0) {
+    dim3 gb((d.nb + 7) / 8, nel);
+    stc_bwd_kernel<CPLX><<<gb, 256, 0, st>>>(L.ws.b.ni_e, L.ws.b.nb_e, 0, 0, o.AS, (long long)d.nb * d.ni, o.BS, (long long)d.nb, L.d_xi, (long long)d.ni,
+                                             L.d_xb, (long long)d.nb + 1);
+    g_launches++;
+  }
 }
 
 // One chunk through the whole pipeline.  The caller has already queued the copy of the per-element dof counts into
 // L.ws.b.ni_e / nb_e on `st`.
 static void run_chunk(const ChunkShape &sh, Lane &L, int ob, const GeomParams &gp, const std::vector<Seg> &segs, int nel, const double *d_xnod,
-                      long long xnod_ld, const double *d_src, long long src_ld, bool want_schur, cudaStream_t st, StageEvents *ev = nullptr) {
+                      long long xnod_ld, const double *d_src, long long src_ld, bool want_schur, cudaStream_t st, StageEvents *ev = nullptr,
+                      int mode = MODE_ELEM) {
   if (ev && ev->on) cudaEventRecord(ev->e[0], st);
   run_integration(sh, L, gp, segs, nel, d_xnod, xnod_ld, d_src, src_ld, st);
   if (ev && ev->on) cudaEventRecord(ev->e[1], st);
-  if (sh.d.cplx) run_dense_and_scatter<true>(sh, L, L.out[ob], nel, want_schur, st, ev);
-  else run_dense_and_scatter<false>(sh, L, L.out[ob], nel, want_schur, st, ev);
+  if (sh.d.cplx) run_dense_and_scatter<true>(sh, L, L.out[ob], nel, want_schur, st, ev, mode);
+  else run_dense_and_scatter<false>(sh, L, L.out[ob], nel, want_schur, st, ev, mode);
   if (ev && ev->on) cudaEventRecord(ev->e[3], st);
 }
 

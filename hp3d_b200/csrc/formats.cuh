@@ -74,4 +74,70 @@ __global__ void scatter_schur_kernel(DenseDims d, const double *Am, OutMaps mp, 
   }
 }
 
+// xb = BSchur - ASchur * xi (stc_bwd, src/modules/stc.F90:661-677), one warp per (bubble row, element); ASchur (nb x ni) and
+// xi / xb in the caller's layout (column-major, interleaved complex), per-element sizes.
+template <bool CPLX>
+__global__ void stc_bwd_kernel(const int *__restrict__ ni_e, const int *__restrict__ nb_e, int ni_u, int nb_u, const double *AS, long long sAS,
+                               const double *BS, long long sBS, const double *xi, long long sxi, double *xb, long long sxb) {
+  constexpr int NS = CPLX ? 2 : 1;
+  const int e = blockIdx.y, r = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+  const int ni = ni_e ? ni_e[e] : ni_u, nb = nb_e ? nb_e[e] : nb_u;
+  if (r >= nb) return;
+  const double *A = AS + (long long)e * sAS * NS, *x = xi + (long long)e * sxi * NS;
+  double sr = 0, si = 0;
+  for (int c = lane; c < ni; c += 32) {
+    const double *a = A + ((long long)r + (long long)nb * c) * NS;
+    if (CPLX) { sr += a[0] * x[2 * c] - a[1] * x[2 * c + 1]; si += a[0] * x[2 * c + 1] + a[1] * x[2 * c]; }
+    else sr += a[0] * x[c];
+  }
+  for (int o = 16; o; o >>= 1) { sr += __shfl_xor_sync(0xffffffffu, sr, o); if (CPLX) si += __shfl_xor_sync(0xffffffffu, si, o); }
+  if (lane == 0) {
+    const double *b = BS + (long long)e * sBS * NS + (long long)r * NS;
+    double *o = xb + (long long)e * sxb * NS + (long long)r * NS;
+    o[0] = b[0] - sr;
+    if (CPLX) o[1] = b[1] - si;
+  }
+}
+
+// DPG element residual  eta^2 = || l~ - B~ u ||^2 = v^H A v,  v = [u ; -1],  A = [B~ l~]^H [B~ l~]  (lower triangle of Am after
+// the normal equations; load at index M-1): the quantity elem_residual computes with its own Gram factorization
+// (problems/MAXWELL/ULTRAWEAK_DPG/elem/elem_residual_maxwell.F90:246-552, POISSON/PRIMAL_DPG/elem_residual.F90).
+// u is given in the caller's layout as xi (interface dofs) and xb (bubble dofs).  One CTA (256 threads) per element.
+template <bool CPLX>
+__global__ void __launch_bounds__(256) dpg_residual_kernel(DenseDims d, const double *Am, const int *__restrict__ ni_e, const int *__restrict__ nb_e,
+                                                           const double *xi, long long sxi, const double *xb, long long sxb, double *res) {
+  constexpr int NS = CPLX ? 2 : 1;
+  extern __shared__ double sv[];   // v: [2][M]
+  __shared__ double red[8];
+  const int e = blockIdx.x, M = d.M(), tid = threadIdx.x;
+  const long long apl = (long long)d.a_plane();
+  const double *Ar = Am + (long long)e * NS * apl, *Ai = Ar + apl;
+  const int ni = ni_e[e], nb = nb_e[e];
+  double *vr = sv, *vi = sv + M;
+  for (int i = tid; i < M; i += blockDim.x) {
+    double r = 0.0, im = 0.0;
+    if (i < nb) { r = xb[((long long)e * sxb + i) * NS]; if (CPLX) im = xb[((long long)e * sxb + i) * NS + 1]; }
+    else if (i >= d.nbp && i < d.nbp + ni) { const int k = i - d.nbp; r = xi[((long long)e * sxi + k) * NS]; if (CPLX) im = xi[((long long)e * sxi + k) * NS + 1]; }
+    else if (i == M - 1) r = -1.0;
+    vr[i] = r; vi[i] = im;
+  }
+  __syncthreads();
+  // eta^2 = sum_i A_ii |v_i|^2 + 2 Re sum_{i>j} conj(v_i) A_ij v_j
+  double acc = 0.0;
+  const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  for (int i = warp; i < M; i += nw) {
+    const double *ar = Ar + (long long)i * M, *ai = Ai + (long long)i * M;
+    double yr = 0.0, yi = 0.0;   // y = sum_{j<i} A_ij v_j
+    for (int j = lane; j < i; j += 32) {
+      const double a = ar[j], b = CPLX ? ai[j] : 0.0;
+      yr += a * vr[j] - b * vi[j]; yi += a * vi[j] + b * vr[j];
+    }
+    for (int o = 16; o; o >>= 1) { yr += __shfl_xor_sync(0xffffffffu, yr, o); yi += __shfl_xor_sync(0xffffffffu, yi, o); }
+    if (lane == 0) acc += ar[i] * (vr[i] * vr[i] + vi[i] * vi[i]) + 2.0 * (vr[i] * yr + vi[i] * yi);
+  }
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (tid == 0) { double s = 0.0; for (int w = 0; w < nw; w++) s += red[w]; res[e] = s; }
+}
+
 }  // namespace hp3d

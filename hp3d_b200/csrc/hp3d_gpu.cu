@@ -90,29 +90,6 @@ void chunk_segments(const ClassGroup &C, size_t c0, int n, std::vector<Seg> &seg
   }
 }
 
-// xb = BSchur - ASchur * xi, one warp per (row, element)
-template <bool CPLX>
-__global__ void stc_bwd_kernel(int ni, int nb, const double *AS, long long sAS, const double *BS, long long sBS, const double *xi,
-                               long long sxi, double *xb, long long sxb) {
-  constexpr int NS = CPLX ? 2 : 1;
-  const int e = blockIdx.y, r = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
-  if (r >= nb) return;
-  const double *A = AS + (long long)e * sAS * NS, *x = xi + (long long)e * sxi * NS;
-  double sr = 0, si = 0;
-  for (int c = lane; c < ni; c += 32) {
-    const double *a = A + ((long long)r + (long long)nb * c) * NS;
-    if (CPLX) { sr += a[0] * x[2 * c] - a[1] * x[2 * c + 1]; si += a[0] * x[2 * c + 1] + a[1] * x[2 * c]; }
-    else sr += a[0] * x[c];
-  }
-  for (int o = 16; o; o >>= 1) { sr += __shfl_xor_sync(0xffffffffu, sr, o); if (CPLX) si += __shfl_xor_sync(0xffffffffu, si, o); }
-  if (lane == 0) {
-    const double *b = BS + (long long)e * sBS * NS + (long long)r * NS;
-    double *o = xb + (long long)e * sxb * NS + (long long)r * NS;
-    o[0] = b[0] - sr;
-    if (CPLX) o[1] = b[1] - si;
-  }
-}
-
 }  // namespace
 
 extern "C" {
@@ -312,17 +289,26 @@ void *hp3d_gpu_host_alloc(long long bytes) {
 void hp3d_gpu_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 // ------------------------------------------------------------------------------------------------
-int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif,
-                        const double *xnod, int xnod_ld, const void *source_qp, long long source_ld, void *Aii, long long sAii,
-                        void *Bi, long long sBi, void *ASchur, long long sAS, void *BSchur, long long sBS, int *ni_out, int *nb_out,
-                        int *info) {
+}  // extern "C"
+
+namespace {
+// The chunked, two-lane pipeline behind hp3d_gpu_elem_batch (MODE_ELEM), hp3d_gpu_elem_bwd_batch (MODE_BWD: recompute the
+// element, return only xb = BSchur - ASchur xi) and hp3d_gpu_elem_residual_batch (MODE_RESID: DPG residual per element).
+int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif,
+               const double *xnod, int xnod_ld, const void *source_qp, long long source_ld, void *Aii, long long sAii,
+               void *Bi, long long sBi, void *ASchur, long long sAS, void *BSchur, long long sBS, int *ni_out, int *nb_out,
+               int *info, const void *xi, long long sxi, void *xb, long long sxb, double *resid) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
   Plan *p = plan_of(plan);
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
-  if (nel < 0 || !norder || !norie || !norif || !xnod || !Aii || !Bi) return fail(HP3D_EINVAL, "null argument");
+  if (nel < 0 || !norder || !norie || !norif || !xnod) return fail(HP3D_EINVAL, "null argument");
+  if (mode == MODE_ELEM && (!Aii || !Bi)) return fail(HP3D_EINVAL, "null argument");
+  if (mode == MODE_BWD && (!xi || !xb)) return fail(HP3D_EINVAL, "null argument");
+  if (mode == MODE_RESID && (!xi || !resid)) return fail(HP3D_EINVAL, "null argument");
+  if (mode == MODE_RESID && p->fp.kind != HP3D_POIS_PDPG && p->fp.kind != HP3D_MAXW_UW) return fail(HP3D_EINVAL, "the element residual is defined for the DPG problems only");
   if (p->fp.source == HP3D_SRC_TABLE && !source_qp) return fail(HP3D_EINVAL, "source == HP3D_SRC_TABLE needs source_qp");
-  const bool want_schur = p->store_schur && ASchur && BSchur;
+  const bool want_schur = mode == MODE_BWD || (mode == MODE_ELEM && p->store_schur && ASchur && BSchur);
   std::vector<ClassGroup> classes;
   std::string err;
   if (int brc = build_classes(p, nel, etype, norder, norie, norif, true, classes, err)) return fail(brc, "%s", err.c_str());
@@ -356,14 +342,21 @@ int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, 
       cudaEventSynchronize(evCopy[slot]);
       const size_t pc0 = (size_t)k * chunk;
       const int pn = (int)std::min(el.size() - pc0, (size_t)chunk);
-      const int *hi = g_lanes.lane[k & 1].out[(k >> 1) & 1].h_info;
-      for (int i = 0; i < pn; i++) { const int e = el[pc0 + i]; if (info) info[e] = hi[i]; }
+      const Lane &PL = g_lanes.lane[k & 1];
+      const int *hi = PL.out[(k >> 1) & 1].h_info;
+      for (int i = 0; i < pn; i++) {
+        const int e = el[pc0 + i];
+        if (info) info[e] = hi[i];
+        if (mode == MODE_BWD) memcpy((char *)xb + es * sxb * e, PL.h_xb + NS * (sT + 1) * i, es * C.sig[pc0 + i]->h.nb);
+        if (mode == MODE_RESID) resid[e] = PL.h_res[i];
+      }
     };
     for (size_t c0 = 0; c0 < el.size(); c0 += chunk, nchunk++) {
       const int n = (int)std::min(el.size() - c0, (size_t)chunk), ln = nchunk & 1, ob = (nchunk >> 1) & 1, slot = ln * 2 + ob;
       Lane &L = g_lanes.lane[ln];
       cudaStream_t st = g_lane_stream[ln];
-      if (nchunk >= 4) collect_info(nchunk - 4);              // this slot's previous results are on the host
+      if (mode == MODE_ELEM) { if (nchunk >= 4) collect_info(nchunk - 4); }   // this slot's previous results are on the host
+      else if (nchunk >= 2) collect_info(nchunk - 2);         // small results are staged per LANE: drain before the lane is reused
       if (nchunk >= 2) cudaEventSynchronize(evH2D[ln]);        // the lane's pinned input staging has been consumed
       for (int i = 0; i < n; i++) {
         const int e = el[c0 + i];
@@ -372,16 +365,34 @@ int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, 
         if (gp.source == HP3D_SRC_TABLE)
           memcpy(L.h_src + (size_t)i * nsrc, (const double *)source_qp + (size_t)e * source_ld, sizeof(double) * h.nint * (h.cplx ? 6 : 1));
         L.h_cnt[i] = h.ni; L.h_cnt[lcap + i] = h.nb;
+        if (mode != MODE_ELEM) {
+          memcpy(L.h_xi + NS * sB * i, (const char *)xi + es * sxi * e, es * h.ni);
+          if (mode == MODE_RESID && h.nb > 0) {
+            if (!xb) { rc = fail(HP3D_EINVAL, "residual: xb (bubble dofs) is required for elements with bubbles"); break; }
+            memcpy(L.h_xb + NS * (sT + 1) * i, (const char *)xb + es * sxb * e, es * h.nb);
+          }
+        }
       }
+      if (rc != HP3D_OK) break;
       cudaMemcpyAsync(L.d_xnod, L.h_xnod, sizeof(double) * nx * n, cudaMemcpyHostToDevice, st);
       if (gp.source == HP3D_SRC_TABLE) cudaMemcpyAsync(L.d_src, L.h_src, sizeof(double) * nsrc * n, cudaMemcpyHostToDevice, st);
       cudaMemcpyAsync(L.ws.b.ni_e, L.h_cnt, sizeof(int) * n, cudaMemcpyHostToDevice, st);
       cudaMemcpyAsync(L.ws.b.nb_e, L.h_cnt + lcap, sizeof(int) * n, cudaMemcpyHostToDevice, st);
+      if (mode != MODE_ELEM) cudaMemcpyAsync(L.d_xi, L.h_xi, es * sB * n, cudaMemcpyHostToDevice, st);
+      if (mode == MODE_RESID) cudaMemcpyAsync(L.d_xb, L.h_xb, es * (sT + 1) * n, cudaMemcpyHostToDevice, st);
       cudaEventRecord(evH2D[ln], st);
       chunk_segments(C, c0, n, segs);
-      run_chunk(sh, L, ob, gp, segs, n, L.d_xnod, (long long)nx, L.d_src, (long long)nsrc, want_schur, st);
+      run_chunk(sh, L, ob, gp, segs, n, L.d_xnod, (long long)nx, L.d_src, (long long)nsrc, want_schur, st, nullptr, mode);
       cudaEventRecord(evCompute[slot], st);
       cudaStreamWaitEvent(g_copy, evCompute[slot], 0);
+      if (mode != MODE_ELEM) {   // small results: staged through pinned memory, scattered to the caller in collect_info
+        const Lane::Out &o2 = L.out[ob];
+        if (mode == MODE_BWD) cudaMemcpyAsync(L.h_xb, L.d_xb, es * (sT + 1) * n, cudaMemcpyDeviceToHost, g_copy);
+        else cudaMemcpyAsync(L.h_res, L.d_res, sizeof(double) * n, cudaMemcpyDeviceToHost, g_copy);
+        cudaMemcpyAsync(o2.h_info, o2.info, sizeof(int) * n, cudaMemcpyDeviceToHost, g_copy);
+        cudaEventRecord(evCopy[slot], g_copy);
+        continue;
+      }
       // D2H straight into the caller's arrays; runs of consecutive elements with equal sizes and dense strides are merged
       const Lane::Out &o = L.out[ob];
       for (int i = 0; i < n;) {
@@ -404,7 +415,7 @@ int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, 
       cudaMemcpyAsync(o.h_info, o.info, sizeof(int) * n, cudaMemcpyDeviceToHost, g_copy);   // pinned: stays asynchronous
       cudaEventRecord(evCopy[slot], g_copy);
     }
-    for (int k = std::max(0, nchunk - 4); k < nchunk; k++) collect_info(k);
+    for (int k = std::max(0, nchunk - (mode == MODE_ELEM ? 4 : 2)); k < nchunk; k++) collect_info(k);
     for (size_t i = 0; i < el.size(); i++) { const SigHost &h = C.sig[i]->h; if (ni_out) ni_out[el[i]] = h.ni; if (nb_out) nb_out[el[i]] = h.nb; }
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) { rc = fail(HP3D_ENODEV, "CUDA error in elem_batch: %s", cudaGetErrorString(ce)); break; }
@@ -419,6 +430,32 @@ int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, 
     if (ce != cudaSuccess) rc = fail(HP3D_ENODEV, "CUDA error in elem_batch: %s", cudaGetErrorString(ce));
   }
   return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif,
+                        const double *xnod, int xnod_ld, const void *source_qp, long long source_ld, void *Aii, long long sAii,
+                        void *Bi, long long sBi, void *ASchur, long long sAS, void *BSchur, long long sBS, int *ni_out, int *nb_out,
+                        int *info) {
+  return batch_impl(MODE_ELEM, plan, nel, etype, norder, norie, norif, xnod, xnod_ld, source_qp, source_ld, Aii, sAii, Bi, sBi, ASchur, sAS,
+                    BSchur, sBS, ni_out, nb_out, info, nullptr, 0, nullptr, 0, nullptr);
+}
+
+int hp3d_gpu_elem_bwd_batch(int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif,
+                            const double *xnod, int xnod_ld, const void *source_qp, long long source_ld, const void *xi, long long sxi,
+                            void *xb, long long sxb, int *nb_out, int *info) {
+  return batch_impl(MODE_BWD, plan, nel, etype, norder, norie, norif, xnod, xnod_ld, source_qp, source_ld, nullptr, 0, nullptr, 0, nullptr, 0,
+                    nullptr, 0, nullptr, nb_out, info, xi, sxi, xb, sxb, nullptr);
+}
+
+int hp3d_gpu_elem_residual_batch(int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif,
+                                 const double *xnod, int xnod_ld, const void *source_qp, long long source_ld, const void *xi,
+                                 long long sxi, const void *xb, long long sxb, double *resid, int *info) {
+  return batch_impl(MODE_RESID, plan, nel, etype, norder, norie, norif, xnod, xnod_ld, source_qp, source_ld, nullptr, 0, nullptr, 0, nullptr, 0,
+                    nullptr, 0, nullptr, nullptr, info, xi, sxi, const_cast<void *>(xb), sxb, resid);
 }
 
 int hp3d_gpu_quad_points(int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif,
@@ -468,8 +505,8 @@ int hp3d_gpu_stc_bwd_batch(int cplx, int nel, int ni, int nb, const void *ASchur
   CUDA_TRY(cudaMemcpy2D(dB, es * nb, BSchur, es * sBS, es * nb, nel, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy2D(dx, es * ni, xi, es * sxi, es * ni, nel, cudaMemcpyHostToDevice));
   dim3 grid((nb + 7) / 8, nel);
-  if (cplx) stc_bwd_kernel<true><<<grid, 256>>>(ni, nb, dA, (long long)nb * ni, dB, nb, dx, ni, dy, nb);
-  else stc_bwd_kernel<false><<<grid, 256>>>(ni, nb, dA, (long long)nb * ni, dB, nb, dx, ni, dy, nb);
+  if (cplx) stc_bwd_kernel<true><<<grid, 256>>>(nullptr, nullptr, ni, nb, dA, (long long)nb * ni, dB, nb, dx, ni, dy, nb);
+  else stc_bwd_kernel<false><<<grid, 256>>>(nullptr, nullptr, ni, nb, dA, (long long)nb * ni, dB, nb, dx, ni, dy, nb);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpy2D(xb, es * sxb, dy, es * nb, es * nb, nel, cudaMemcpyDeviceToHost));
   cudaFree(dA); cudaFree(dB); cudaFree(dx); cudaFree(dy);

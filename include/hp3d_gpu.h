@@ -102,6 +102,24 @@ int hp3d_gpu_elem_batch(int plan, int nel, const int *etype, const int *norder, 
                         long long source_ld, void *Aii, long long sAii, void *Bi, long long sBi, void *ASchur,
                         long long sAS, void *BSchur, long long sBS, int *ni_out, int *nb_out, int *info);
 
+/* Back-substitution WITHOUT stored Schur factors (the "recompute" option the reference leaves unimplemented, stc.F90:279-281;
+ * stc_bwd_wrapper stc.F90:529): the element matrices and their condensation are recomputed on the device and only
+ *   xb = BSchur - ASchur * xi      (nb values per element; stc_bwd, stc.F90:661-677)
+ * returns to the host, instead of storing / shipping nb x ni factors per element (7.2 MB at p=5 ultraweak Maxwell).
+ * xi: interface dofs of element e at xi + e*sxi scalars, in the order of the rows of Aii; xb likewise (order of ASchur rows). */
+int hp3d_gpu_elem_bwd_batch(int plan, int nel, const int *etype, const int *norder, const int *norient_edge,
+                            const int *norient_face, const double *xnod, int xnod_ld, const void *source_qp, long long source_ld,
+                            const void *xi, long long sxi, void *xb, long long sxb, int *nb_out, int *info);
+
+/* DPG element residual (error indicator), problems/MAXWELL/ULTRAWEAK_DPG/elem/elem_residual_maxwell.F90:246-552 and
+ * POISSON/PRIMAL_DPG/elem_residual.F90 (called from residual.F90:48-57):  resid[e] = || l - B u ||^2 in the dual of the
+ * test norm = (G^-1 (l - B u), l - B u), for the element solution u = (xi | xb) in the dof order of hp3d_gpu_elem_batch's
+ * condensed system (interface dofs) and Schur factors (bubble dofs).  DPG problem kinds only. */
+int hp3d_gpu_elem_residual_batch(int plan, int nel, const int *etype, const int *norder, const int *norient_edge,
+                                 const int *norient_face, const double *xnod, int xnod_ld, const void *source_qp,
+                                 long long source_ld, const void *xi, long long sxi, const void *xb, long long sxb, double *resid,
+                                 int *info);
+
 /* Upper bound on the number of elements processed per internal chunk by hp3d_gpu_elem_batch (0 = automatic: as many
  * as fit in device memory, but at least four chunks for large groups so that result copies overlap compute). */
 int hp3d_gpu_set_chunk(int max_elements);

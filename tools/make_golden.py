@@ -30,3 +30,25 @@ for kind, p, seed in CASES:
                         norie=norie, norif=norif, xnod=xnod, Aii=np.array([o[0] for o in out]), Bi=np.array([o[1] for o in out]),
                         ASchur=np.array([o[2] for o in out]), BSchur=np.array([o[3] for o in out]))
     print(kind, p, out[0][0].shape, out[0][2].shape)
+
+# ---- triangular prisms (element type MDLP = 3): two elements per fixture, the second with non-uniform node orders
+from tests.test_gpu_prism import prism_xnod  # noqa: E402
+from tests.test_oracle_prism import prism_signature  # noqa: E402
+
+O.set_maxp(8)
+for kind, p, pz, seed in [(1, 3, 2, 51), (2, 2, 2, 52), (3, 2, 3, 53), (4, 2, 2, 54)]:
+    rng = np.random.default_rng(seed)
+    sig = [prism_signature(rng, p, pz, uniform=(e == 0)) for e in range(2)]
+    norder = np.stack([s[0] for s in sig]); norie = np.stack([s[1] for s in sig]); norif = np.stack([s[2] for s in sig])
+    nHs = [O.celndof(norder[e], O.MDLP)[0] for e in range(2)]
+    xnod = np.zeros((2, max(nHs), 3))
+    for e in range(2):
+        xnod[e, :nHs[e]] = prism_xnod(nHs[e], rng, curved=0.01)
+    omega = 2 * np.pi if kind == 4 else (np.pi if kind == 3 else 1.0)
+    prm = O.default_params(omega=omega)
+    out = [O.condensed(kind, norder[e], norie[e], norif[e], xnod[e, :nHs[e]], prm, etype=O.MDLP) for e in range(2)]
+    obj = lambda k: np.array([o[k] for o in out], dtype=object)   # noqa: E731  (elements differ in size)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"prism_kind{kind}_p{p}{pz}.npz"), kind=kind, etype=3, omega=omega,
+                        norder=norder, norie=norie, norif=norif, xnod=xnod, nrdofH=np.array(nHs),
+                        **{f"{n}{e}": out[e][k] for e in range(2) for k, n in enumerate(("Aii", "Bi", "ASchur", "BSchur"))})
+    print("prism", kind, p, pz, out[0][0].shape, out[1][0].shape)
