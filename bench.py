@@ -146,7 +146,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--elements", type=int, default=256, help="elements per GPU per step")
-    ap.add_argument("--e2e-elements", type=int, default=128)
+    ap.add_argument("--e2e-elements", type=int, default=512, help="elements per GPU per end-to-end step (a subdomain slice; 6.8 GB of results at p=5)")
     ap.add_argument("--p", type=int, default=5)
     ap.add_argument("--kind", type=int, default=4)
     ap.add_argument("--cpu-sample", type=int, default=0)
@@ -205,7 +205,9 @@ def main():
     # ---- end to end through hp3d_gpu_elem_batch with pinned host buffers
     e2e = None
     if not args.no_e2e:
-        Be = min(args.e2e_elements, B)
+        Be = args.e2e_elements
+        if Be > B:
+            norder, noe, nof, xnod = synth.cube_mesh(Be, args.p, first=rank * Be, total=world * Be)
         dt = eng.dtype
         bufs = [pinned_empty((Be, ni * ni), dt), pinned_empty((Be, ni), dt), pinned_empty((Be, max(nb * ni, 1)), dt), pinned_empty((Be, max(nb, 1)), dt)]
         out = dict(Aii=bufs[0].a, Bi=bufs[1].a, ASchur=bufs[2].a, BSchur=bufs[3].a)

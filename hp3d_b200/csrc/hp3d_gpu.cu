@@ -326,22 +326,37 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
     const std::vector<int> &el = C.el;
     const ChunkShape &sh = C.shape;
     if (xnod_ld < 3 * sh.nH_max) { rc = fail(HP3D_EINVAL, "xnod_ld=%d < 3*nrdofH=%d", xnod_ld, 3 * sh.nH_max); break; }
+    // chunk plan: large chunks (the 64x64 tile factorizations are latency-bound, so a chunk below ~64 elements runs the
+    // dense phase well under its throughput) that TAPER towards the end of the group, because the result copy of the
+    // last chunk is the only one no later compute hides
     int want = (int)el.size();
     if (g_max_chunk > 0) want = std::min(want, g_max_chunk);
-    else if (want >= 64) want = std::max(16, (want + 7) / 8);   // >= 8 chunks: copies of finished chunks overlap compute
+    else want = std::min(want, 128);
     const int cap = chunk_capacity(sh, want);
     if (cap < 1) { rc = fail(HP3D_ENOMEM, "not enough device memory for one element"); break; }
     if (g_lanes.reserve(sh, cap, err)) { rc = fail(HP3D_ENOMEM, "%s", err.c_str()); break; }
     const size_t NS = sh.ns(), es = sizeof(double) * NS;
     const size_t nx = 3 * (size_t)sh.nH_max, nsrc = sh.src_max;
     const size_t sA = (size_t)sh.d.ni * sh.d.ni, sB = sh.d.ni, sS = (size_t)sh.d.nb * sh.d.ni, sT = sh.d.nb;   // device staging strides
-    const int chunk = cap, lcap = g_lanes.cap;
+    const int lcap = g_lanes.cap;
+    std::vector<size_t> cstart;   // chunk k covers el[cstart[k] .. cstart[k+1])
+    {
+      size_t c0 = 0;
+      const size_t ntot = el.size();
+      while (c0 < ntot) {
+        cstart.push_back(c0);
+        size_t rem = ntot - c0, n = std::min(rem, (size_t)cap);
+        if (g_max_chunk == 0 && rem < 2 * (size_t)cap && rem > 24) n = std::min(n, std::max((size_t)16, rem / 2));   // taper: halve down to 16
+        c0 += n;
+      }
+      cstart.push_back(ntot);
+    }
     int nchunk = 0;
     auto collect_info = [&](int k) {   // host side of chunk k: wait for its D2H, publish info[]
       const int slot = (k & 1) * 2 + ((k >> 1) & 1);
       cudaEventSynchronize(evCopy[slot]);
-      const size_t pc0 = (size_t)k * chunk;
-      const int pn = (int)std::min(el.size() - pc0, (size_t)chunk);
+      const size_t pc0 = cstart[k];
+      const int pn = (int)(cstart[k + 1] - pc0);
       const Lane &PL = g_lanes.lane[k & 1];
       const int *hi = PL.out[(k >> 1) & 1].h_info;
       for (int i = 0; i < pn; i++) {
@@ -351,8 +366,9 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
         if (mode == MODE_RESID) resid[e] = PL.h_res[i];
       }
     };
-    for (size_t c0 = 0; c0 < el.size(); c0 += chunk, nchunk++) {
-      const int n = (int)std::min(el.size() - c0, (size_t)chunk), ln = nchunk & 1, ob = (nchunk >> 1) & 1, slot = ln * 2 + ob;
+    for (; nchunk + 1 < (int)cstart.size(); nchunk++) {
+      const size_t c0 = cstart[nchunk];
+      const int n = (int)(cstart[nchunk + 1] - c0), ln = nchunk & 1, ob = (nchunk >> 1) & 1, slot = ln * 2 + ob;
       Lane &L = g_lanes.lane[ln];
       cudaStream_t st = g_lane_stream[ln];
       if (mode == MODE_ELEM) { if (nchunk >= 4) collect_info(nchunk - 4); }   // this slot's previous results are on the host
