@@ -165,15 +165,16 @@ struct Lane {
 };
 enum ChunkMode { MODE_ELEM = 0, MODE_BWD = 1, MODE_RESID = 2 };
 struct LaneSet {
-  static constexpr int NLANE = 2;
+  static constexpr int NLANE = 4;   // lanes that can be bound; hp3d_gpu_elem_batch uses two
   Lane lane[NLANE];
   ChunkShape shape;
   int cap = 0;   // elements per lane currently bound in the arena
+  int nl = 2;    // lanes currently bound
   double *d_ones = nullptr; int *d_iota = nullptr; int n_iota = 0;   // identity output maps (grown on demand, plain cudaMalloc)
-  void layout(const ChunkShape &sh, int batch, Bump &dm, Bump &hm) {
+  void layout(const ChunkShape &sh, int batch, Bump &dm, Bump &hm, int nlanes = 2) {
     const size_t NS = sh.ns();
     const DenseDims &d = sh.d;
-    for (int i = 0; i < NLANE; i++) {
+    for (int i = 0; i < nlanes; i++) {
       Lane &L = lane[i];
       L.ws.bind(d, batch, dm);
       L.ws.b.ni_e = dm.take<int>(batch); L.ws.b.nb_e = dm.take<int>(batch);
@@ -200,21 +201,22 @@ struct LaneSet {
   size_t bytes_per_element(const ChunkShape &sh) {   // device bytes per element of ONE lane (alignment slack excluded)
     Bump d1(nullptr), h1(nullptr), d2(nullptr), h2(nullptr);
     LaneSet tmp;
-    tmp.layout(sh, 1, d1, h1); tmp.layout(sh, 65, d2, h2);
-    return (d2.off - d1.off) / 64 / NLANE + 1;
+    tmp.layout(sh, 1, d1, h1, 1); tmp.layout(sh, 65, d2, h2, 1);
+    return (d2.off - d1.off) / 64 + 1;
   }
   // bind the chunk buffers for `batch` elements per lane of shape `sh` into the shared arena (no-op if still bound)
-  int reserve(const ChunkShape &sh, int batch, std::string &err) {
-    if (cap >= batch && shape.covers(sh) && g_arena.owner == this) return 0;
+  int reserve(const ChunkShape &sh, int batch, std::string &err, int nlanes = 2) {
+    if (cap >= batch && nl >= nlanes && shape.covers(sh) && g_arena.owner == this) return 0;
     Bump dmeas(nullptr), hmeas(nullptr);
     LaneSet tmp;
-    tmp.layout(sh, batch, dmeas, hmeas);
+    tmp.layout(sh, batch, dmeas, hmeas, nlanes);
     size_t dneed = dmeas.off + 256, hneed = hmeas.off + 256;
     if (dneed > g_arena.dcap) dneed = std::max(dneed, g_arena.dcap + g_arena.dcap / 4);   // geometric growth
     if (hneed > g_arena.hcap) hneed = std::max(hneed, g_arena.hcap + g_arena.hcap / 4);
     if (int rc = g_arena.ensure(dneed, hneed, err)) { cap = 0; return rc; }
     Bump dm(g_arena.d), hm(g_arena.h);
-    layout(sh, batch, dm, hm);
+    layout(sh, batch, dm, hm, nlanes);
+    nl = nlanes;
     const int need = std::max(sh.d.ni, sh.d.nb) + 1;
     if (need > n_iota) {
       cudaDeviceSynchronize();

@@ -17,7 +17,7 @@ std::mutex g_mu;
 std::string g_err;
 int g_device = -1;
 std::vector<Plan *> g_plans;
-cudaStream_t g_lane_stream[2] = {nullptr, nullptr}, g_copy = nullptr;
+cudaStream_t g_lane_stream[LaneSet::NLANE] = {nullptr, nullptr, nullptr, nullptr}, g_copy = nullptr;
 #define g_compute g_lane_stream[0]
 int g_max_chunk = 0;
 
@@ -39,12 +39,12 @@ int fail(int code, const char *fmt, ...) {
 Plan *plan_of(int id) { return (id >= 0 && id < (int)g_plans.size()) ? g_plans[id] : nullptr; }
 
 // largest chunk (elements per lane) of this shape that fits in the free device memory
-int chunk_capacity(const ChunkShape &sh, int want) {
+int chunk_capacity(const ChunkShape &sh, int want, int nlanes = 2) {
   size_t fre = 0, tot = 0;
   cudaMemGetInfo(&fre, &tot);
   const size_t per = g_lanes.bytes_per_element(sh);
   double budget = 0.80 * (double)(fre + g_arena.dcap);   // the shared arena is reusable; two lanes share the budget
-  long long cap = (long long)(budget / (double)(LaneSet::NLANE * per));
+  long long cap = (long long)(budget / (double)(nlanes * per));
   if (cap > 1024) cap = 1024;
   if (cap > want) cap = want;
   return (int)cap;
@@ -118,7 +118,7 @@ int hp3d_gpu_init(int device) {
   CUDA_TRY(dense_configure<false>());
   CUDA_TRY(tp3_configure<4>()); CUDA_TRY(tp3_configure<6>()); CUDA_TRY(tp3_configure<8>()); CUDA_TRY(tp3_configure<10>());
   CUDA_TRY(tp2_configure<4>()); CUDA_TRY(tp2_configure<6>()); CUDA_TRY(tp2_configure<8>()); CUDA_TRY(tp2_configure<10>());
-  for (int i = 0; i < 2; i++)
+  for (int i = 0; i < LaneSet::NLANE; i++)
     if (!g_lane_stream[i]) CUDA_TRY(cudaStreamCreateWithFlags(&g_lane_stream[i], cudaStreamNonBlocking));
   if (!g_copy) CUDA_TRY(cudaStreamCreateWithFlags(&g_copy, cudaStreamNonBlocking));
   g_device = device;
@@ -132,7 +132,7 @@ int hp3d_gpu_finalize(void) {
   cudaDeviceSynchronize();
   g_lanes.release();
   g_arena.release();
-  for (int i = 0; i < 2; i++)
+  for (int i = 0; i < LaneSet::NLANE; i++)
     if (g_lane_stream[i]) { cudaStreamDestroy(g_lane_stream[i]); g_lane_stream[i] = nullptr; }
   if (g_copy) { cudaStreamDestroy(g_copy); g_copy = nullptr; }
   g_device = -1;
@@ -313,28 +313,31 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
   std::string err;
   if (int brc = build_classes(p, nel, etype, norder, norie, norif, true, classes, err)) return fail(brc, "%s", err.c_str());
   const GeomParams gp = p->geom();
-  // slot = (lane, output buffer): chunk k runs on lane k&1 and writes output buffer (k>>1)&1 of that lane
-  cudaEvent_t evCompute[4], evCopy[4], evH2D[2];
-  for (int i = 0; i < 4; i++) {
+  // slot = (lane, output buffer): chunk k runs on lane k % NL and writes output buffer (k / NL) & 1 of that lane.
+  // Four lanes of modest chunks keep the GPU as busy as two lanes of large ones (the latency-bound tile factorizations and
+  // the last partial wave of every GEMM launch of one lane are filled by the other lanes) while results stream to the host
+  // in smaller pieces.
+  constexpr int NL = LaneSet::NLANE, NSLOT = 2 * NL;
+  cudaEvent_t evCompute[NSLOT], evCopy[NSLOT], evH2D[NL];
+  for (int i = 0; i < NSLOT; i++) {
     CUDA_TRY(cudaEventCreateWithFlags(&evCompute[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&evCopy[i], cudaEventDisableTiming));
   }
-  for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&evH2D[i], cudaEventDisableTiming));
+  for (int i = 0; i < NL; i++) CUDA_TRY(cudaEventCreateWithFlags(&evH2D[i], cudaEventDisableTiming));
   int rc = HP3D_OK;
   std::vector<Seg> segs;
   for (ClassGroup &C : classes) {
     const std::vector<int> &el = C.el;
     const ChunkShape &sh = C.shape;
     if (xnod_ld < 3 * sh.nH_max) { rc = fail(HP3D_EINVAL, "xnod_ld=%d < 3*nrdofH=%d", xnod_ld, 3 * sh.nH_max); break; }
-    // chunk plan: large chunks (the 64x64 tile factorizations are latency-bound, so a chunk below ~64 elements runs the
-    // dense phase well under its throughput) that TAPER towards the end of the group, because the result copy of the
-    // last chunk is the only one no later compute hides
+    // chunk plan: chunks of up to 64 elements round-robin over the lanes, TAPERED towards the end of the group because the
+    // result copy of the last chunk is the only one no later compute hides
     int want = (int)el.size();
     if (g_max_chunk > 0) want = std::min(want, g_max_chunk);
-    else want = std::min(want, 128);
-    const int cap = chunk_capacity(sh, want);
+    else want = std::min(64, std::max(4, (want + NL - 1) / NL));   // small groups are spread over the lanes
+    const int cap = chunk_capacity(sh, want, NL);
     if (cap < 1) { rc = fail(HP3D_ENOMEM, "not enough device memory for one element"); break; }
-    if (g_lanes.reserve(sh, cap, err)) { rc = fail(HP3D_ENOMEM, "%s", err.c_str()); break; }
+    if (g_lanes.reserve(sh, cap, err, NL)) { rc = fail(HP3D_ENOMEM, "%s", err.c_str()); break; }
     const size_t NS = sh.ns(), es = sizeof(double) * NS;
     const size_t nx = 3 * (size_t)sh.nH_max, nsrc = sh.src_max;
     const size_t sA = (size_t)sh.d.ni * sh.d.ni, sB = sh.d.ni, sS = (size_t)sh.d.nb * sh.d.ni, sT = sh.d.nb;   // device staging strides
@@ -353,12 +356,12 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
     }
     int nchunk = 0;
     auto collect_info = [&](int k) {   // host side of chunk k: wait for its D2H, publish info[]
-      const int slot = (k & 1) * 2 + ((k >> 1) & 1);
+      const int slot = (k % NL) * 2 + ((k / NL) & 1);
       cudaEventSynchronize(evCopy[slot]);
       const size_t pc0 = cstart[k];
       const int pn = (int)(cstart[k + 1] - pc0);
-      const Lane &PL = g_lanes.lane[k & 1];
-      const int *hi = PL.out[(k >> 1) & 1].h_info;
+      const Lane &PL = g_lanes.lane[k % NL];
+      const int *hi = PL.out[(k / NL) & 1].h_info;
       for (int i = 0; i < pn; i++) {
         const int e = el[pc0 + i];
         if (info) info[e] = hi[i];
@@ -368,12 +371,12 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
     };
     for (; nchunk + 1 < (int)cstart.size(); nchunk++) {
       const size_t c0 = cstart[nchunk];
-      const int n = (int)(cstart[nchunk + 1] - c0), ln = nchunk & 1, ob = (nchunk >> 1) & 1, slot = ln * 2 + ob;
+      const int n = (int)(cstart[nchunk + 1] - c0), ln = nchunk % NL, ob = (nchunk / NL) & 1, slot = ln * 2 + ob;
       Lane &L = g_lanes.lane[ln];
       cudaStream_t st = g_lane_stream[ln];
-      if (mode == MODE_ELEM) { if (nchunk >= 4) collect_info(nchunk - 4); }   // this slot's previous results are on the host
-      else if (nchunk >= 2) collect_info(nchunk - 2);         // small results are staged per LANE: drain before the lane is reused
-      if (nchunk >= 2) cudaEventSynchronize(evH2D[ln]);        // the lane's pinned input staging has been consumed
+      if (mode == MODE_ELEM) { if (nchunk >= NSLOT) collect_info(nchunk - NSLOT); }   // this slot's previous results are on the host
+      else if (nchunk >= NL) collect_info(nchunk - NL);       // small results are staged per LANE: drain before the lane is reused
+      if (nchunk >= NL) cudaEventSynchronize(evH2D[ln]);        // the lane's pinned input staging has been consumed
       for (int i = 0; i < n; i++) {
         const int e = el[c0 + i];
         const SigHost &h = C.sig[c0 + i]->h;
@@ -431,16 +434,15 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
       cudaMemcpyAsync(o.h_info, o.info, sizeof(int) * n, cudaMemcpyDeviceToHost, g_copy);   // pinned: stays asynchronous
       cudaEventRecord(evCopy[slot], g_copy);
     }
-    for (int k = std::max(0, nchunk - (mode == MODE_ELEM ? 4 : 2)); k < nchunk; k++) collect_info(k);
+    for (int k = std::max(0, nchunk - (mode == MODE_ELEM ? NSLOT : NL)); k < nchunk; k++) collect_info(k);
     for (size_t i = 0; i < el.size(); i++) { const SigHost &h = C.sig[i]->h; if (ni_out) ni_out[el[i]] = h.ni; if (nb_out) nb_out[el[i]] = h.nb; }
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) { rc = fail(HP3D_ENODEV, "CUDA error in elem_batch: %s", cudaGetErrorString(ce)); break; }
   }
-  cudaStreamSynchronize(g_lane_stream[0]);
-  cudaStreamSynchronize(g_lane_stream[1]);
+  for (int i = 0; i < NL; i++) cudaStreamSynchronize(g_lane_stream[i]);
   cudaStreamSynchronize(g_copy);
-  for (int i = 0; i < 4; i++) { cudaEventDestroy(evCompute[i]); cudaEventDestroy(evCopy[i]); }
-  for (int i = 0; i < 2; i++) cudaEventDestroy(evH2D[i]);
+  for (int i = 0; i < NSLOT; i++) { cudaEventDestroy(evCompute[i]); cudaEventDestroy(evCopy[i]); }
+  for (int i = 0; i < NL; i++) cudaEventDestroy(evH2D[i]);
   if (rc == HP3D_OK) {
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) rc = fail(HP3D_ENODEV, "CUDA error in elem_batch: %s", cudaGetErrorString(ce));
@@ -541,7 +543,7 @@ int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, con
   if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
   Plan *p = plan_of(plan);
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
-  if (nel <= 0 || reps <= 0 || lanes < 1 || lanes > 2) return fail(HP3D_EINVAL, "bad sizes");
+  if (nel <= 0 || reps <= 0 || lanes < 1 || lanes > LaneSet::NLANE) return fail(HP3D_EINVAL, "bad sizes");
   if (p->fp.source == HP3D_SRC_TABLE) return fail(HP3D_EINVAL, "bench: table sources are not supported");
   std::vector<ClassGroup> classes;
   std::string err;
@@ -552,11 +554,11 @@ int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, con
   std::vector<Grp> gs;
   for (ClassGroup &C : classes) {
     int want = (int)C.el.size();
-    if (lanes == 2) want = (want + 1) / 2;
+    want = (want + lanes - 1) / lanes;
     if (max_chunk > 0 && want > max_chunk) want = max_chunk;
-    const int cap = chunk_capacity(C.shape, want);
+    const int cap = chunk_capacity(C.shape, want, lanes);
     if (cap < 1) return fail(HP3D_ENOMEM, "not enough device memory");
-    if (g_lanes.reserve(C.shape, cap, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());   // grows the arena to the largest class
+    if (g_lanes.reserve(C.shape, cap, err, lanes)) return fail(HP3D_ENOMEM, "%s", err.c_str());   // grows the arena to the largest class
     const size_t nx = 3 * (size_t)C.shape.nH_max, n = C.el.size();
     std::vector<double> hx(nx * n, 0.0);
     std::vector<int> hc(2 * n);
@@ -572,29 +574,27 @@ int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, con
     gs.push_back(Grp{&C, dx, dc, (int)n, cap});
   }
   std::vector<StageEvents> evs;
-  cudaEvent_t t0, t1, tj, tsw[2];
+  cudaEvent_t t0, t1, tj, tsw[LaneSet::NLANE];
   CUDA_TRY(cudaEventCreate(&t0)); CUDA_TRY(cudaEventCreate(&t1)); CUDA_TRY(cudaEventCreateWithFlags(&tj, cudaEventDisableTiming));
-  for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&tsw[i], cudaEventDisableTiming));
+  for (int i = 0; i < LaneSet::NLANE; i++) CUDA_TRY(cudaEventCreateWithFlags(&tsw[i], cudaEventDisableTiming));
   const long long l0 = g_launches;
-  CUDA_TRY(cudaStreamSynchronize(g_lane_stream[0]));
-  CUDA_TRY(cudaStreamSynchronize(g_lane_stream[1]));
+  for (int i = 0; i < LaneSet::NLANE; i++) CUDA_TRY(cudaStreamSynchronize(g_lane_stream[i]));
   CUDA_TRY(cudaEventRecord(t0, g_lane_stream[0]));
-  if (lanes == 2) CUDA_TRY(cudaStreamWaitEvent(g_lane_stream[1], t0, 0));   // lane 1 starts inside the timed region
+  for (int i = 1; i < lanes; i++) CUDA_TRY(cudaStreamWaitEvent(g_lane_stream[i], t0, 0));   // the other lanes start inside the timed region
   int k = 0;
   std::vector<Seg> segs;
   for (int r = 0; r < reps; r++)
     for (Grp &g : gs) {
       if (gs.size() > 1) {   // another class's buffers occupy the arena: both lanes must drain before they are re-bound
-        if (lanes == 2) {
-          for (int i = 0; i < 2; i++) cudaEventRecord(tsw[i], g_lane_stream[i]);
-          cudaStreamWaitEvent(g_lane_stream[0], tsw[1], 0); cudaStreamWaitEvent(g_lane_stream[1], tsw[0], 0);
-        }
+        for (int i = 0; i < lanes; i++) cudaEventRecord(tsw[i], g_lane_stream[i]);
+        for (int i = 0; i < lanes; i++)
+          for (int j = 0; j < lanes; j++) if (i != j) cudaStreamWaitEvent(g_lane_stream[i], tsw[j], 0);
         g_arena.owner = nullptr;   // force the re-layout for this class (pointer arithmetic only: the arena is large enough)
-        if (g_lanes.reserve(g.C->shape, g.chunk, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());
+        if (g_lanes.reserve(g.C->shape, g.chunk, err, lanes)) return fail(HP3D_ENOMEM, "%s", err.c_str());
       }
       const long long nx = 3LL * g.C->shape.nH_max;
       for (int c0 = 0; c0 < g.n; c0 += g.chunk, k++) {
-        const int n = std::min(g.n - c0, g.chunk), ln = lanes == 2 ? (k & 1) : 0;
+        const int n = std::min(g.n - c0, g.chunk), ln = k % lanes;
         Lane &L = g_lanes.lane[ln];
         StageEvents ev;
         ev.on = (lanes == 1);
@@ -606,10 +606,9 @@ int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, con
         if (ev.on) evs.push_back(ev);
       }
     }
-  if (lanes == 2) { CUDA_TRY(cudaEventRecord(tj, g_lane_stream[1])); CUDA_TRY(cudaStreamWaitEvent(g_lane_stream[0], tj, 0)); }
+  for (int i = 1; i < lanes; i++) { CUDA_TRY(cudaEventRecord(tj, g_lane_stream[i])); CUDA_TRY(cudaStreamWaitEvent(g_lane_stream[0], tj, 0)); }
   CUDA_TRY(cudaEventRecord(t1, g_lane_stream[0]));
-  CUDA_TRY(cudaStreamSynchronize(g_lane_stream[0]));
-  CUDA_TRY(cudaStreamSynchronize(g_lane_stream[1]));
+  for (int i = 0; i < LaneSet::NLANE; i++) CUDA_TRY(cudaStreamSynchronize(g_lane_stream[i]));
   CUDA_TRY(cudaGetLastError());
   float ms = 0;
   cudaEventElapsedTime(&ms, t0, t1);
@@ -626,7 +625,7 @@ int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, con
   if (ms_dense) *ms_dense = md;
   if (launches) *launches = g_launches - l0;
   cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(tj);
-  for (int i = 0; i < 2; i++) cudaEventDestroy(tsw[i]);
+  for (int i = 0; i < LaneSet::NLANE; i++) cudaEventDestroy(tsw[i]);
   for (Grp &g : gs) { cudaFree(g.dx); cudaFree(g.dcnt); }
   return HP3D_OK;
 }
