@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(512) stc_gen_kernel(const int *__restrict__ nb
   __shared__ double red_v[16];
   __shared__ int red_i[16];
   __shared__ int s_piv;
-  __shared__ double s_pr, s_pi;
+
   const int e = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   const int nb = nb_e[e], ni = ni_e[e];
   double *Ar = Am + (long long)e * a_batch, *Ai = Ar + a_plane;
