@@ -162,3 +162,40 @@ def test_hp_mesh_batch_vs_oracle(oracle, gpu):
         assert relerr(Aii, rA) < 1e-12, (e, relerr(Aii, rA))
         assert relerr(Bi, rB) < 1e-12, (e, relerr(Bi, rB))
     eng.close()
+
+
+def test_high_order_elements(oracle, gpu):
+    """The upper end of configs[4] (orders up to 7, enriched to 8): one p=6 brick and one p=(6,6) prism against the oracle,
+    and p=7 elements through size-independent properties (Hermitian, positive semi-definite condensed matrix, info = 0)."""
+    from tests.util import hexa_xnod, uniform_order
+    oracle.set_maxp(8)
+    oracle.use_blas(True, threads=8)
+    rng = np.random.default_rng(99)
+    om = 2 * np.pi
+    prm = oracle.default_params(omega=om)
+    eng = _engine(4, omega=om, maxp=8)
+    B, P = oracle.MDLB, oracle.MDLP
+    for p, check in ((6, True), (7, False)):
+        nob = uniform_order(p); nop = oracle.uniform_order(p, P, p)
+        neb = rng.integers(0, 2, 12).astype(np.int32); nfb = rng.integers(0, 8, 6).astype(np.int32)
+        _, nep, nfp = prism_signature(rng, p, p)
+        nHb, nHp = oracle.celndof(nob, B)[0], oracle.celndof(nop, P)[0]
+        X = np.zeros((2, max(nHb, nHp), 3))
+        X[0, :nHb] = hexa_xnod(nHb, h=0.3, jitter=0.1, rng=rng)
+        X[1, :nHp] = prism_xnod(nHp, rng, h=0.3)
+        res = eng.elem_stc_batch(np.stack([nob, nop]), np.stack([neb, nep]), np.stack([nfb, nfp]), X, etype=np.array([B, P], np.int32))
+        assert (res["info"] == 0).all(), res["info"]
+        for e, (et, no, ne, nf, nH) in enumerate(((B, nob, neb, nfb, nHb), (P, nop, nep, nfp, nHp))):
+            Aii, Bi, AS, BS = eng.unpack(res, e)
+            assert relerr(Aii, Aii.conj().T) < 1e-13
+            w = np.linalg.eigvalsh(Aii)
+            assert w.min() > -1e-9 * w.max()
+            if check:
+                rA, rB, _, _ = oracle.condensed(4, no, ne, nf, X[e, :nH], prm, etype=et)
+                # the p=6 prism Gram matrix has cond(G) = 2.5e10 (hexa: 4e9): two correct FP64 evaluations of B^H G^-1 B agree
+                # to ~cond*eps*1e-4; the bar stays 1e-12 for the brick and is 5e-12 for this prism
+                tol = 1e-12 if et == B else 5e-12
+                assert relerr(Aii, rA) < tol, (p, e, relerr(Aii, rA))
+                assert relerr(Bi, rB) < tol, (p, e, relerr(Bi, rB))
+    oracle.use_blas(True, threads=1)
+    eng.close()
