@@ -141,8 +141,8 @@ class ElemEngine:
             k = bytes([t]) + norder[e].tobytes()
             if k not in sz:
                 sz[k] = self.sizes(norder[e], t)
-        ni = max(s[0] for s in sz.values())
-        nb = max(s[1] for s in sz.values())
+        ni = max((s[0] for s in sz.values()), default=0)
+        nb = max((s[1] for s in sz.values()), default=0)
         if out is None:
             out = dict(Aii=np.zeros((nel, ni * ni), self.dtype), Bi=np.zeros((nel, ni), self.dtype),
                        ASchur=np.zeros((nel, max(nb * ni, 1)), self.dtype), BSchur=np.zeros((nel, max(nb, 1)), self.dtype))
@@ -155,9 +155,9 @@ class ElemEngine:
         L.hp3d_gpu_elem_batch.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                           C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
                                           C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
-        rc = L.hp3d_gpu_elem_batch(self.plan, nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(xnod[0].size),
-                                   _ptr(source_qp), src_ld, _ptr(Aii), Aii[0].size, _ptr(Bi), Bi[0].size, _ptr(AS), AS[0].size,
-                                   _ptr(BS), BS[0].size, _ptr(nio), _ptr(nbo), _ptr(info))
+        rc = L.hp3d_gpu_elem_batch(self.plan, nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(np.prod(xnod.shape[1:])),
+                                   _ptr(source_qp), src_ld, _ptr(Aii), int(np.prod(Aii.shape[1:])), _ptr(Bi), int(np.prod(Bi.shape[1:])),
+                                   _ptr(AS), int(np.prod(AS.shape[1:])), _ptr(BS), int(np.prod(BS.shape[1:])), _ptr(nio), _ptr(nbo), _ptr(info))
         _lib.check(rc)
         return dict(Aii=Aii, Bi=Bi, ASchur=AS, BSchur=BS, ni=nio, nb=nbo, info=info)
 

@@ -199,3 +199,32 @@ def test_high_order_elements(oracle, gpu):
                 assert relerr(Bi, rB) < tol, (p, e, relerr(Bi, rB))
     oracle.use_blas(True, threads=1)
     eng.close()
+
+
+def test_edge_cases(gpu):
+    """Empty batch, unknown element type, invalid descriptors (loud errors, no silent fallback), negative Jacobian on a prism."""
+    from hp3d_b200.api import ElemEngine
+    eng = _engine(4, omega=1.0)
+    z = lambda *s: np.zeros(s, np.int32)   # noqa: E731
+    res = eng.elem_stc_batch(z(0, 19), z(0, 12), z(0, 6), np.zeros((0, 8, 3)))
+    assert res["info"].size == 0
+    P = 3
+    rng = np.random.default_rng(1)
+    no, ne, nf = prism_signature(rng, 2, 2)
+    X = prism_xnod(18, rng)[None]
+    with pytest.raises(RuntimeError, match="element type"):
+        eng.elem_stc_batch(no[None], ne[None], nf[None], X, etype=2)          # MDLN (tetrahedron): not implemented
+    bad = no.copy(); bad[0] = 0
+    with pytest.raises(RuntimeError, match="order"):
+        eng.elem_stc_batch(bad[None], ne[None], nf[None], X, etype=P)
+    badf = nf.copy(); badf[0] = 6
+    with pytest.raises(RuntimeError, match="orientation"):
+        eng.elem_stc_batch(no[None], ne[None], badf[None], X, etype=P)
+    Xm = X.copy(); Xm[0, :6, 2] *= -1.0                                        # mirrored prism: negative Jacobian
+    res = eng.elem_stc_batch(no[None], ne[None], nf[None], Xm, etype=P)
+    assert res["info"][0] == -1
+    with pytest.raises(RuntimeError, match="xnod_ld"):
+        eng.elem_stc_batch(no[None], ne[None], nf[None], X[:, :10], etype=P)   # too few geometry dofs
+    with pytest.raises(RuntimeError, match="DPG"):
+        ElemEngine(1).elem_residual_batch(no[None], ne[None], nf[None], X, np.zeros((1, 4)), np.zeros((1, 4)), etype=P)
+    eng.close()
