@@ -111,7 +111,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = host_cores()
-    nsample = args.cpu_sample or max(2 * cores, 8)
+    nsample = args.cpu_sample or max(8 * cores, 32)   # ~8 s of CPU work per step on the 16-core box
     omega = 2 * np.pi
     for _ in range(min(args.warmup, 1)):
         cpu_reference_rate(args.kind, args.p, max(cores, 1), cores, omega)
@@ -254,7 +254,7 @@ def main():
     }
     if not args.no_cpu:
         cores = host_cores()
-        ns = args.cpu_sample or max(2 * cores, 8)
+        ns = args.cpu_sample or max(16 * cores, 64)   # ~15 s of CPU work (bounded sample)
         v, dtc, blas = cpu_reference_rate(args.kind, args.p, ns, cores, omega)
         out["cpu_baseline"] = {"value": v, "unit": "elements/s", "cores": cores, "kind": "port",
                                "sample": f"{ns} elements of the same workload in {dtc:.1f} s; OpenMP over elements ({cores} threads), single-threaded {'OpenBLAS' if blas else 'built-in loops'} per element"}

@@ -66,6 +66,48 @@ class _Pinned:
             pass
 
 
+class Physics(C.Structure):
+    """Mirror of `hp3d_physics` (include/hp3d_gpu.h): the problem's physics table (src/modules/physics.F90)."""
+    _fields_ = [("nphys", C.c_int), ("dtype", C.c_int * 8), ("ncomp", C.c_int * 8), ("adres", C.c_int * 8), ("nrvar", C.c_int * 3)]
+
+
+def physics_default(kind):
+    ph = Physics()
+    _lib.check(_lib.lib().hp3d_gpu_physics_default(int(kind), C.byref(ph)))
+    return ph
+
+
+def celem_pack(ph, nrdofl, nrcon, nac, constr, nrdofm_f):
+    """Flat per-modified-dof lists (cptr, cidx, cval) of ONE element from the output of `logic` (hp3d_gpu_celem_pack).
+    nrcon/nac/constr: per family (H1, H(curl), H(div)) arrays (nk,), (nk,nacdim), (nk,nacdim); nac holds 1-based indices."""
+    L = _lib.lib()
+    nrdofl, nrdofm_f = _i32(nrdofl), _i32(nrdofm_f)
+    nacdim = max([np.asarray(a).shape[1] for a in nac if np.asarray(a).ndim == 2 and np.asarray(a).size] + [1])
+    arrs = []
+    for f in range(3):
+        k = int(nrdofl[f])
+        rc = np.zeros(k, np.int32); na = np.zeros((k, nacdim), np.int32); co = np.zeros((k, nacdim))
+        if k:
+            rc[:] = np.asarray(nrcon[f])[:k]
+            a = np.asarray(nac[f]); c = np.asarray(constr[f])
+            na[:, :a.shape[1]] = a[:k]; co[:, :c.shape[1]] = c[:k]
+        arrs += [rc, na, co]
+    nm = int(nrdofm_f.sum())
+    cptr = np.zeros(nm + 1, np.int64)
+    f_ = L.hp3d_gpu_celem_pack
+    f_.restype = C.c_longlong
+    f_.argtypes = [C.c_void_p] * 11 + [C.c_int] + [C.c_void_p] * 4 + [C.c_longlong]
+    args = [C.byref(ph), _ptr(nrdofl)] + [_ptr(a) for a in arrs] + [int(nacdim), _ptr(nrdofm_f), _ptr(cptr)]
+    n = f_(*args, None, None, 0)
+    if n < 0:
+        _lib.check(int(n))
+    cidx = np.zeros(max(n, 1), np.int32); cval = np.zeros(max(n, 1))
+    n2 = f_(*args, _ptr(cidx), _ptr(cval), int(n))
+    if n2 < 0:
+        _lib.check(int(n2))
+    return cptr, cidx[:n], cval[:n]
+
+
 class ElemEngine:
     """One plan = one problem (`elem` plugin of the reference) with fixed parameters."""
 
@@ -194,6 +236,53 @@ class ElemEngine:
         _lib.check(f(self.plan, nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(xnod[0].size), None, 0,
                      _ptr(xi), xi[0].size, _ptr(xb), xb[0].size, _ptr(res), _ptr(info)))
         return dict(resid=res, info=info)
+
+    def celem_batch(self, norder, norient_edge, norient_face, xnod, cons, isym_flag=2, want_coo=False, want_schur=False,
+                    source_qp=None, etype=None):
+        """elem + stc_fwd_wrapper + the rest of celem_systemI (constraints, Dirichlet lift, compression; :543-785) for nel
+        elements (hp3d_gpu_celem_batch).  cons: one dict per element with the flat lists of `celem_pack` (cptr, cidx, cval) and
+        idbc, zdofd (Nrdofm,), nextract (Nrdofc,) [1-based], optionally lcon (Nrdofc,) global dof numbers.
+        Returns dict(zbload, zastif [flat, element e at aptr[e]], xptr, aptr, irn, jcn, ASchur, BSchur, ni, nb, info)."""
+        norder, noe, nof, xnod, nel, et = self._descr(norder, norient_edge, norient_face, xnod, etype)
+        assert len(cons) == nel
+        mptr = np.zeros(nel + 1, np.int64); xptr = np.zeros(nel + 1, np.int64); aptr = np.zeros(nel + 1, np.int64)
+        for e, c in enumerate(cons):
+            nm, nc = len(c["idbc"]), len(c["nextract"])
+            mptr[e + 1] = mptr[e] + nm; xptr[e + 1] = xptr[e] + nc
+            aptr[e + 1] = aptr[e] + (nc * (nc + 1) // 2 if isym_flag == 1 else nc * nc)
+        cptr = np.zeros(mptr[-1] + 1, np.int64)
+        base = 0
+        for e, c in enumerate(cons):
+            cp = np.asarray(c["cptr"], np.int64)
+            cptr[mptr[e]:mptr[e + 1] + 1] = base + cp
+            base += int(cp[-1])
+        cat = lambda k, dt: (np.ascontiguousarray(np.concatenate([np.asarray(c[k]).ravel() for c in cons]), dtype=dt) if nel else np.zeros(0, dt))  # noqa: E731
+        cidx, cval = cat("cidx", np.int32), cat("cval", np.float64)
+        idbc, zdofd, nextract = cat("idbc", np.int32), cat("zdofd", self.dtype), cat("nextract", np.int32)
+        lcon = cat("lcon", np.int32) if want_coo else None
+        zb = np.zeros(max(int(xptr[-1]), 1), self.dtype); za = np.zeros(max(int(aptr[-1]), 1), self.dtype)
+        irn = np.zeros(max(int(aptr[-1]), 1), np.int32) if want_coo else None
+        jcn = np.zeros(max(int(aptr[-1]), 1), np.int32) if want_coo else None
+        AS = BS = None
+        sAS = sBS = 0
+        if want_schur:
+            szs = [self.sizes(norder[e], MDLB if et is None else int(et[e])) for e in range(nel)]
+            ni = max(s_[0] for s_ in szs); nb = max(s_[1] for s_ in szs)
+            AS = np.zeros((nel, max(nb * ni, 1)), self.dtype); BS = np.zeros((nel, max(nb, 1)), self.dtype)
+            sAS, sBS = AS[0].size, BS[0].size
+        nio = np.zeros(nel, np.int32); nbo = np.zeros(nel, np.int32); info = np.zeros(nel, np.int32)
+        src_ld = 0
+        if source_qp is not None:
+            source_qp = np.ascontiguousarray(source_qp)
+            src_ld = source_qp[0].size * (2 if np.iscomplexobj(source_qp) else 1)
+        f = self.L.hp3d_gpu_celem_batch
+        ll = C.c_longlong
+        f.argtypes = ([C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, ll] + [C.c_void_p] * 9 + [C.c_int] + [C.c_void_p] * 5 +
+                      [C.c_void_p, ll, C.c_void_p, ll] + [C.c_void_p] * 3)
+        _lib.check(f(self.plan, nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(np.prod(xnod.shape[1:])), _ptr(source_qp), src_ld,
+                     _ptr(mptr), _ptr(cptr), _ptr(cidx), _ptr(cval), _ptr(idbc), _ptr(zdofd), _ptr(xptr), _ptr(nextract), _ptr(lcon), int(isym_flag),
+                     _ptr(aptr), _ptr(zb), _ptr(za), _ptr(irn), _ptr(jcn), _ptr(AS), sAS, _ptr(BS), sBS, _ptr(nio), _ptr(nbo), _ptr(info)))
+        return dict(zbload=zb, zastif=za, xptr=xptr, aptr=aptr, irn=irn, jcn=jcn, ASchur=AS, BSchur=BS, ni=nio, nb=nbo, info=info)
 
     @staticmethod
     def unpack(res, e):

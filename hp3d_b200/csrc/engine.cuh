@@ -1,6 +1,7 @@
 // engine.cuh -- batch engine behind the C ABI: per-signature device programs, workspaces, the per-chunk pipeline
 //   descriptors -> geometry/weight fields -> sum-factorised integration -> dense phase -> condensed outputs.
 #pragma once
+#include "celem_kernels.cuh"
 #include "dense_pipeline.cuh"
 #include "formats.cuh"
 #include "forms.hpp"
@@ -133,10 +134,13 @@ struct ChunkShape {
   bool gen_stc = false;
   int nint_max = 0, nH_max = 0;
   size_t src_max = 0;          // doubles per element of a caller-supplied source table
+  size_t nz_max = 0, nc_max = 0;   // hp3d_gpu_celem_batch only: scalars of Zastif / Zbload per element (maxima of the group)
+  bool coo = false;                //   ... and IRN/JCN staging
   int ns() const { return d.cplx ? 2 : 1; }
   bool covers(const ChunkShape &o) const {
     return d.cplx == o.d.cplx && d.dpg == o.d.dpg && gen_stc == o.gen_stc && d.np == o.d.np && d.nbp == o.d.nbp && d.nip == o.d.nip &&
-           d.ni >= o.d.ni && d.nb >= o.d.nb && nint_max >= o.nint_max && nH_max >= o.nH_max && src_max >= o.src_max;
+           d.ni >= o.d.ni && d.nb >= o.d.nb && nint_max >= o.nint_max && nH_max >= o.nH_max && src_max >= o.src_max &&
+           nz_max >= o.nz_max && nc_max >= o.nc_max && (coo || !o.coo);
   }
   void absorb(const SigHost &h) {
     if (d.np == 0 && d.nip == 0) { d = h.dims; gen_stc = h.gen_stc; }
@@ -156,14 +160,18 @@ struct ChunkShape {
 struct Lane {
   DenseWorkspace ws;
   double *d_WF = nullptr, *d_xnod = nullptr, *d_src = nullptr;         // chunk inputs / weight fields
-  struct Out { double *Aii = nullptr, *Bi = nullptr, *AS = nullptr, *BS = nullptr; int *info = nullptr, *h_info = nullptr; };  // h_info: pinned
+  struct Out {
+    double *Aii = nullptr, *Bi = nullptr, *AS = nullptr, *BS = nullptr; int *info = nullptr, *h_info = nullptr;   // h_info: pinned
+    double *Z = nullptr, *zb = nullptr; int *irn = nullptr, *jcn = nullptr;   // compressed system (hp3d_gpu_celem_batch)
+  };
   Out out[2];   // chunk outputs (device staging), double-buffered: the D2H of one chunk overlaps the lane's next chunk
   double *h_xnod = nullptr, *h_src = nullptr;                          // pinned host staging of the chunk inputs
   int *h_cnt = nullptr;                                                // pinned [2][batch]: ni_e | nb_e
+  int *d_cel = nullptr, *h_cel = nullptr;                              // caller element index of each slot (celem mode)
   // back-substitution / residual modes: solution dofs in (xi | xb), results out (xb or one residual per element)
   double *d_xi = nullptr, *d_xb = nullptr, *d_res = nullptr, *h_xi = nullptr, *h_xb = nullptr, *h_res = nullptr;
 };
-enum ChunkMode { MODE_ELEM = 0, MODE_BWD = 1, MODE_RESID = 2 };
+enum ChunkMode { MODE_ELEM = 0, MODE_BWD = 1, MODE_RESID = 2, MODE_CELEM = 3 };
 struct LaneSet {
   static constexpr int NLANE = 4;   // lanes that can be bound; hp3d_gpu_elem_batch uses two
   Lane lane[NLANE];
@@ -188,10 +196,15 @@ struct LaneSet {
         L.out[o].BS = dm.take<double>(NS * ((size_t)d.nb + 1) * batch);
         L.out[o].info = dm.take<int>(batch);
         L.out[o].h_info = hm.take<int>(batch);
+        L.out[o].Z = dm.take<double>(NS * sh.nz_max * batch);
+        L.out[o].zb = dm.take<double>(NS * sh.nc_max * batch);
+        L.out[o].irn = dm.take<int>(sh.coo ? sh.nz_max * batch : 0);
+        L.out[o].jcn = dm.take<int>(sh.coo ? sh.nz_max * batch : 0);
       }
       L.h_xnod = hm.take<double>((size_t)3 * sh.nH_max * batch);
       L.h_src = hm.take<double>(sh.src_max * batch);
       L.h_cnt = hm.take<int>(2 * (size_t)batch);
+      L.d_cel = dm.take<int>(batch); L.h_cel = hm.take<int>(batch);
       L.d_xi = dm.take<double>(NS * (size_t)d.ni * batch); L.d_xb = dm.take<double>(NS * ((size_t)d.nb + 1) * batch);
       L.d_res = dm.take<double>(batch);
       L.h_xi = hm.take<double>(NS * (size_t)d.ni * batch); L.h_xb = hm.take<double>(NS * ((size_t)d.nb + 1) * batch);
@@ -382,6 +395,39 @@ static void run_chunk(const ChunkShape &sh, Lane &L, int ob, const GeomParams &g
   if (sh.d.cplx) run_dense_and_scatter<true>(sh, L, L.out[ob], nel, want_schur, st, ev, mode);
   else run_dense_and_scatter<false>(sh, L, L.out[ob], nel, want_schur, st, ev, mode);
   if (ev && ev->on) cudaEventRecord(ev->e[3], st);
+}
+
+// The constraint data of one hp3d_gpu_celem_batch call, resident on the device for the duration of the call.
+struct CelemCall {
+  long long *d_mptr = nullptr, *d_cptr = nullptr, *d_xptr = nullptr;
+  int *d_cidx = nullptr, *d_idbc = nullptr, *d_nextract = nullptr, *d_lcon = nullptr, *d_hasd = nullptr;
+  double *d_cval = nullptr, *d_zdofd = nullptr;
+  const long long *xptr = nullptr;   // host
+  std::vector<long long> aoff;       // host: scalar offset of every element's Zastif in the caller's array
+  int isym = 2;
+  void *zbload = nullptr, *zastif = nullptr; int *irn = nullptr, *jcn = nullptr;   // caller's (host) outputs
+  long long nz(int e) const { const long long n = xptr[e + 1] - xptr[e]; return isym == 1 ? n * (n + 1) / 2 : n * n; }
+  void release() {
+    cudaFree(d_mptr); cudaFree(d_cptr); cudaFree(d_xptr); cudaFree(d_cidx); cudaFree(d_idbc); cudaFree(d_nextract); cudaFree(d_lcon);
+    cudaFree(d_hasd); cudaFree(d_cval); cudaFree(d_zdofd);
+  }
+};
+
+// constraint transform + Dirichlet lift + compression of the `nel` condensed systems a chunk left in o.Aii / o.Bi
+static void run_celem(const ChunkShape &sh, Lane &L, const Lane::Out &o, const CelemCall &cc, int nel, cudaStream_t st) {
+  CelemArgs a;
+  a.mptr = cc.d_mptr; a.cptr = cc.d_cptr; a.xptr = cc.d_xptr; a.cidx = cc.d_cidx; a.cval = cc.d_cval; a.idbc = cc.d_idbc; a.zdofd = cc.d_zdofd;
+  a.nextract = cc.d_nextract; a.lcon = cc.d_lcon; a.hasd = cc.d_hasd;
+  a.cel = L.d_cel; a.ni_e = L.ws.b.ni_e;
+  a.Aii = o.Aii; a.Bi = o.Bi; a.sA = (long long)sh.d.ni * sh.d.ni; a.sB = sh.d.ni;
+  a.Z = o.Z; a.zb = o.zb; a.irn = cc.irn ? o.irn : nullptr; a.jcn = cc.irn ? o.jcn : nullptr; a.sZ = (long long)sh.nz_max; a.sZb = (long long)sh.nc_max;
+  a.isym = cc.isym;
+  if (sh.nc_max == 0) return;
+  const unsigned nt = (unsigned)((sh.nc_max + 31) / 32);
+  dim3 gl((unsigned)((sh.nc_max + 127) / 128), nel), gc(nt, nt, nel), bc(32, 8);
+  if (sh.d.cplx) { celem_load_kernel<true><<<gl, 128, 0, st>>>(a); celem_compress_kernel<true><<<gc, bc, 0, st>>>(a); }
+  else { celem_load_kernel<false><<<gl, 128, 0, st>>>(a); celem_compress_kernel<false><<<gc, bc, 0, st>>>(a); }
+  g_launches += 2;
 }
 
 // ------------------------------------------------------------------------------------------------

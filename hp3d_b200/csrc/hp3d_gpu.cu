@@ -13,7 +13,7 @@
 using namespace hp3d;
 
 namespace {
-std::mutex g_mu;
+std::recursive_mutex g_mu;
 std::string g_err;
 int g_device = -1;
 std::vector<Plan *> g_plans;
@@ -105,7 +105,7 @@ void hp3d_gpu_params_default(hp3d_params *p) {
 }
 
 int hp3d_gpu_init(int device) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) return fail(HP3D_ENODEV, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
@@ -126,7 +126,7 @@ int hp3d_gpu_init(int device) {
 }
 
 int hp3d_gpu_finalize(void) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   for (Plan *p : g_plans) delete p;
   g_plans.clear();
   cudaDeviceSynchronize();
@@ -140,7 +140,7 @@ int hp3d_gpu_finalize(void) {
 }
 
 int hp3d_gpu_plan(int problem_kind, const hp3d_params *prm) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   if (!prm) return fail(HP3D_EINVAL, "null params");
   if (problem_kind < HP3D_POIS_GAL || problem_kind > HP3D_MAXW_UW) return fail(HP3D_EINVAL, "unknown problem kind %d", problem_kind);
   // constant isotropic permittivity only (the reference's default get_permittivity is the identity,
@@ -164,14 +164,14 @@ int hp3d_gpu_plan(int problem_kind, const hp3d_params *prm) {
 }
 
 int hp3d_gpu_set_chunk(int max_elements) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   if (max_elements < 0) return fail(HP3D_EINVAL, "negative chunk size");
   g_max_chunk = max_elements;
   return HP3D_OK;
 }
 
 int hp3d_gpu_plan_destroy(int plan) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   Plan *p = plan_of(plan);
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
   delete p;
@@ -184,7 +184,7 @@ int hp3d_gpu_sizes(int plan, const int *norder, int *ni, int *nb, int *nint, int
 }
 
 int hp3d_gpu_sizes_t(int plan, int etype, const int *norder, int *ni, int *nb, int *nint, int *nrdofH) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   Plan *p = plan_of(plan);
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
   const int z12[12] = {0}, z6[6] = {0};
@@ -199,7 +199,7 @@ int hp3d_gpu_sizes_t(int plan, int etype, const int *norder, int *ni, int *nb, i
 }
 
 int hp3d_gpu_sig_dims(int plan, int etype, const int *norder, const int *norie, const int *norif, int *dims) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   Plan *p = plan_of(plan);
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
   std::string err;
@@ -297,21 +297,31 @@ namespace {
 int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif,
                const double *xnod, int xnod_ld, const void *source_qp, long long source_ld, void *Aii, long long sAii,
                void *Bi, long long sBi, void *ASchur, long long sAS, void *BSchur, long long sBS, int *ni_out, int *nb_out,
-               int *info, const void *xi, long long sxi, void *xb, long long sxb, double *resid) {
-  std::lock_guard<std::mutex> lk(g_mu);
+               int *info, const void *xi, long long sxi, void *xb, long long sxb, double *resid, const CelemCall *cc = nullptr) {
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
   Plan *p = plan_of(plan);
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
   if (nel < 0 || !norder || !norie || !norif || !xnod) return fail(HP3D_EINVAL, "null argument");
   if (mode == MODE_ELEM && (!Aii || !Bi)) return fail(HP3D_EINVAL, "null argument");
+  if (mode == MODE_CELEM && !cc) return fail(HP3D_EINVAL, "null argument");
+  const bool big = mode == MODE_ELEM || mode == MODE_CELEM;   // results go straight from the device staging into the caller's arrays
   if (mode == MODE_BWD && (!xi || !xb)) return fail(HP3D_EINVAL, "null argument");
   if (mode == MODE_RESID && (!xi || !resid)) return fail(HP3D_EINVAL, "null argument");
   if (mode == MODE_RESID && p->fp.kind != HP3D_POIS_PDPG && p->fp.kind != HP3D_MAXW_UW) return fail(HP3D_EINVAL, "the element residual is defined for the DPG problems only");
   if (p->fp.source == HP3D_SRC_TABLE && !source_qp) return fail(HP3D_EINVAL, "source == HP3D_SRC_TABLE needs source_qp");
-  const bool want_schur = mode == MODE_BWD || (mode == MODE_ELEM && p->store_schur && ASchur && BSchur);
+  const bool want_schur = mode == MODE_BWD || (big && p->store_schur && ASchur && BSchur);
   std::vector<ClassGroup> classes;
   std::string err;
   if (int brc = build_classes(p, nel, etype, norder, norie, norif, true, classes, err)) return fail(brc, "%s", err.c_str());
+  if (mode == MODE_CELEM)
+    for (ClassGroup &C : classes) {
+      for (int e : C.el) {
+        C.shape.nz_max = std::max(C.shape.nz_max, (size_t)cc->nz(e));
+        C.shape.nc_max = std::max(C.shape.nc_max, (size_t)(cc->xptr[e + 1] - cc->xptr[e]));
+      }
+      C.shape.coo = cc->irn != nullptr;
+    }
   const GeomParams gp = p->geom();
   // slot = (lane, output buffer): chunk k runs on lane k % NL and writes output buffer (k / NL) & 1 of that lane.
   // Four lanes of modest chunks keep the GPU as busy as two lanes of large ones (the latency-bound tile factorizations and
@@ -374,7 +384,7 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
       const int n = (int)(cstart[nchunk + 1] - c0), ln = nchunk % NL, ob = (nchunk / NL) & 1, slot = ln * 2 + ob;
       Lane &L = g_lanes.lane[ln];
       cudaStream_t st = g_lane_stream[ln];
-      if (mode == MODE_ELEM) { if (nchunk >= NSLOT) collect_info(nchunk - NSLOT); }   // this slot's previous results are on the host
+      if (big) { if (nchunk >= NSLOT) collect_info(nchunk - NSLOT); }   // this slot's previous results are on the host
       else if (nchunk >= NL) collect_info(nchunk - NL);       // small results are staged per LANE: drain before the lane is reused
       if (nchunk >= NL) cudaEventSynchronize(evH2D[ln]);        // the lane's pinned input staging has been consumed
       for (int i = 0; i < n; i++) {
@@ -384,7 +394,8 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
         if (gp.source == HP3D_SRC_TABLE)
           memcpy(L.h_src + (size_t)i * nsrc, (const double *)source_qp + (size_t)e * source_ld, sizeof(double) * h.nint * (h.cplx ? 6 : 1));
         L.h_cnt[i] = h.ni; L.h_cnt[lcap + i] = h.nb;
-        if (mode != MODE_ELEM) {
+        if (mode == MODE_CELEM) L.h_cel[i] = e;
+        if (!big) {
           memcpy(L.h_xi + NS * sB * i, (const char *)xi + es * sxi * e, es * h.ni);
           if (mode == MODE_RESID && h.nb > 0) {
             if (!xb) { rc = fail(HP3D_EINVAL, "residual: xb (bubble dofs) is required for elements with bubbles"); break; }
@@ -397,14 +408,16 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
       if (gp.source == HP3D_SRC_TABLE) cudaMemcpyAsync(L.d_src, L.h_src, sizeof(double) * nsrc * n, cudaMemcpyHostToDevice, st);
       cudaMemcpyAsync(L.ws.b.ni_e, L.h_cnt, sizeof(int) * n, cudaMemcpyHostToDevice, st);
       cudaMemcpyAsync(L.ws.b.nb_e, L.h_cnt + lcap, sizeof(int) * n, cudaMemcpyHostToDevice, st);
-      if (mode != MODE_ELEM) cudaMemcpyAsync(L.d_xi, L.h_xi, es * sB * n, cudaMemcpyHostToDevice, st);
+      if (!big) cudaMemcpyAsync(L.d_xi, L.h_xi, es * sB * n, cudaMemcpyHostToDevice, st);
+      if (mode == MODE_CELEM) cudaMemcpyAsync(L.d_cel, L.h_cel, sizeof(int) * n, cudaMemcpyHostToDevice, st);
       if (mode == MODE_RESID) cudaMemcpyAsync(L.d_xb, L.h_xb, es * (sT + 1) * n, cudaMemcpyHostToDevice, st);
       cudaEventRecord(evH2D[ln], st);
       chunk_segments(C, c0, n, segs);
       run_chunk(sh, L, ob, gp, segs, n, L.d_xnod, (long long)nx, L.d_src, (long long)nsrc, want_schur, st, nullptr, mode);
+      if (mode == MODE_CELEM) run_celem(sh, L, L.out[ob], *cc, n, st);
       cudaEventRecord(evCompute[slot], st);
       cudaStreamWaitEvent(g_copy, evCompute[slot], 0);
-      if (mode != MODE_ELEM) {   // small results: staged through pinned memory, scattered to the caller in collect_info
+      if (!big) {   // small results: staged through pinned memory, scattered to the caller in collect_info
         const Lane::Out &o2 = L.out[ob];
         if (mode == MODE_BWD) cudaMemcpyAsync(L.h_xb, L.d_xb, es * (sT + 1) * n, cudaMemcpyDeviceToHost, g_copy);
         else cudaMemcpyAsync(L.h_res, L.d_res, sizeof(double) * n, cudaMemcpyDeviceToHost, g_copy);
@@ -414,6 +427,27 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
       }
       // D2H straight into the caller's arrays; runs of consecutive elements with equal sizes and dense strides are merged
       const Lane::Out &o = L.out[ob];
+      if (mode == MODE_CELEM) {   // compressed systems: Zastif / IRN / JCN at the caller's offsets, Zbload at xptr
+        const size_t zmax = sh.nz_max, cmax = sh.nc_max;
+        for (int i = 0; i < n;) {
+          const int e = el[c0 + i];
+          int j = i + 1;   // merge elements that are adjacent in the caller's arrays AND fill their staging slots completely
+          while (j < n && el[c0 + j] == el[c0 + j - 1] + 1 && (size_t)cc->nz(el[c0 + j - 1]) == zmax &&
+                 (size_t)(cc->xptr[el[c0 + j - 1] + 1] - cc->xptr[el[c0 + j - 1]]) == cmax &&
+                 cc->aoff[el[c0 + j]] == cc->aoff[el[c0 + j - 1]] + (long long)zmax) j++;
+          const int el_last = el[c0 + j - 1];
+          const size_t nzr = (size_t)(j - 1 - i) * zmax + (size_t)cc->nz(el_last), ncr = (size_t)(j - 1 - i) * cmax + (size_t)(cc->xptr[el_last + 1] - cc->xptr[el_last]);
+          if (nzr) {
+            cudaMemcpyAsync((char *)cc->zastif + es * cc->aoff[e], o.Z + NS * zmax * i, es * nzr, cudaMemcpyDeviceToHost, g_copy);
+            if (cc->irn) {
+              cudaMemcpyAsync(cc->irn + cc->aoff[e], o.irn + zmax * i, sizeof(int) * nzr, cudaMemcpyDeviceToHost, g_copy);
+              cudaMemcpyAsync(cc->jcn + cc->aoff[e], o.jcn + zmax * i, sizeof(int) * nzr, cudaMemcpyDeviceToHost, g_copy);
+            }
+          }
+          if (ncr) cudaMemcpyAsync((char *)cc->zbload + es * cc->xptr[e], o.zb + NS * cmax * i, es * ncr, cudaMemcpyDeviceToHost, g_copy);
+          i = j;
+        }
+      }
       for (int i = 0; i < n;) {
         const SigHost &h = C.sig[c0 + i]->h;
         int j = i + 1;
@@ -426,15 +460,14 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
           else
             cudaMemcpy2DAsync((char *)dst + es * stride * e, es * stride, src + NS * dstride * i, es * dstride, es * blk, run, cudaMemcpyDeviceToHost, g_copy);
         };
-        copy(Aii, sAii, o.Aii, sA, (size_t)h.ni * h.ni);
-        copy(Bi, sBi, o.Bi, sB, (size_t)h.ni);
+        if (mode == MODE_ELEM) { copy(Aii, sAii, o.Aii, sA, (size_t)h.ni * h.ni); copy(Bi, sBi, o.Bi, sB, (size_t)h.ni); }
         if (want_schur) { copy(ASchur, sAS, o.AS, sS, (size_t)h.nb * h.ni); copy(BSchur, sBS, o.BS, sT, (size_t)h.nb); }
         i = j;
       }
       cudaMemcpyAsync(o.h_info, o.info, sizeof(int) * n, cudaMemcpyDeviceToHost, g_copy);   // pinned: stays asynchronous
       cudaEventRecord(evCopy[slot], g_copy);
     }
-    for (int k = std::max(0, nchunk - (mode == MODE_ELEM ? NSLOT : NL)); k < nchunk; k++) collect_info(k);
+    for (int k = std::max(0, nchunk - (big ? NSLOT : NL)); k < nchunk; k++) collect_info(k);
     for (size_t i = 0; i < el.size(); i++) { const SigHost &h = C.sig[i]->h; if (ni_out) ni_out[el[i]] = h.ni; if (nb_out) nb_out[el[i]] = h.nb; }
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) { rc = fail(HP3D_ENODEV, "CUDA error in elem_batch: %s", cudaGetErrorString(ce)); break; }
@@ -476,9 +509,137 @@ int hp3d_gpu_elem_residual_batch(int plan, int nel, const int *etype, const int 
                     nullptr, 0, nullptr, nullptr, info, xi, sxi, const_cast<void *>(xb), sxb, resid);
 }
 
+int hp3d_gpu_physics_default(int problem_kind, hp3d_physics *ph) {
+  if (!ph) return fail(HP3D_EINVAL, "null argument");
+  memset(ph, 0, sizeof *ph);
+  // problems/<PROB>/input/physics: (D_TYPE, NR_COMP) per attribute
+  static const int tab[4][2][2] = {{{0, 1}, {-1, 0}}, {{0, 1}, {2, 1}}, {{1, 1}, {-1, 0}}, {{1, 2}, {3, 6}}};
+  if (problem_kind < HP3D_POIS_GAL || problem_kind > HP3D_MAXW_UW) return fail(HP3D_EINVAL, "unknown problem kind %d", problem_kind);
+  int nvar[4] = {0, 0, 0, 0};
+  for (int i = 0; i < 2; i++) {
+    const int dt = tab[problem_kind - 1][i][0], nc = tab[problem_kind - 1][i][1];
+    if (dt < 0) break;
+    ph->dtype[i] = dt; ph->ncomp[i] = nc; ph->adres[i] = nvar[dt]; nvar[dt] += nc; ph->nphys++;
+  }
+  for (int f = 0; f < 3; f++) ph->nrvar[f] = nvar[f];
+  return HP3D_OK;
+}
+
+long long hp3d_gpu_celem_pack(const hp3d_physics *ph, const int *nrdofl, const int *nrconH, const int *nacH, const double *constrH,
+                              const int *nrconE, const int *nacE, const double *constrE, const int *nrconV, const int *nacV,
+                              const double *constrV, int nacdim, const int *nrdofm_f, long long *cptr, int *cidx, double *cval, long long cap) {
+  if (!ph || !nrdofl || !nrdofm_f || !cptr || nacdim < 1 || ph->nphys < 1 || ph->nphys > HP3D_MAXPHYS) return fail(HP3D_EINVAL, "celem_pack: bad argument");
+  const int *nrcon[3] = {nrconH, nrconE, nrconV}, *nac[3] = {nacH, nacE, nacV};
+  const double *con[3] = {constrH, constrE, constrV};
+  const int nrdofm = nrdofm_f[0] + nrdofm_f[1] + nrdofm_f[2];
+  const int base[3] = {0, nrdofm_f[0], nrdofm_f[0] + nrdofm_f[1]};
+  // rows of the condensed system are physics-blocked (stc.F90:305-323): off(i) = sum_{j<i} Nrdofs(j), Nrdofs = nrdofl(family) * NR_COMP
+  int off[HP3D_MAXPHYS], tot = 0;
+  for (int i = 0; i < ph->nphys; i++) {
+    off[i] = tot;
+    if (ph->dtype[i] >= 0 && ph->dtype[i] <= 2) tot += nrdofl[ph->dtype[i]] * ph->ncomp[i];
+  }
+  // the reference's loop nest (celem_systemI.F90:553-647): physics, element dof k, connected dof kp, component ivar
+  auto visit = [&](auto &&fn) -> int {
+    for (int p1 = 0; p1 < ph->nphys; p1++) {
+      const int f = ph->dtype[p1];
+      if (f < 0 || f > 2 || nrdofl[f] == 0) continue;
+      if (!nrcon[f] || !nac[f] || !con[f]) return -1;
+      for (int k = 1; k <= nrdofl[f]; k++)
+        for (int kp = 1; kp <= nrcon[f][k - 1]; kp++) {
+          if (kp > nacdim) return -2;
+          const int l = nac[f][(kp - 1) + (long long)nacdim * (k - 1)];
+          const double c = con[f][(kp - 1) + (long long)nacdim * (k - 1)];
+          for (int ivar = 1; ivar <= ph->ncomp[p1]; ivar++) {
+            const int ll = base[f] + (l - 1) * ph->nrvar[f] + ph->adres[p1] + ivar;
+            if (l < 1 || ll > base[f] + nrdofm_f[f]) return -3;
+            fn(ll, off[p1] + (k - 1) * ph->ncomp[p1] + ivar, c);
+          }
+        }
+    }
+    return 0;
+  };
+  std::vector<long long> cnt(nrdofm + 1, 0);
+  int rc = visit([&](int ll, int, double) { cnt[ll]++; });
+  if (rc == -1) return fail(HP3D_EINVAL, "celem_pack: missing constraint arrays for a family with dofs");
+  if (rc == -2) return fail(HP3D_EINVAL, "celem_pack: nrcon exceeds nacdim");
+  if (rc == -3) return fail(HP3D_EINVAL, "celem_pack: nac points outside the modified element");
+  cptr[0] = 0;
+  for (int ll = 1; ll <= nrdofm; ll++) cptr[ll] = cptr[ll - 1] + cnt[ll];
+  const long long nent = cptr[nrdofm];
+  if (!cidx || !cval) return nent;
+  if (nent > cap) return fail(HP3D_EINVAL, "celem_pack: capacity %lld < %lld entries", cap, nent);
+  std::vector<long long> pos(cptr, cptr + nrdofm);
+  visit([&](int ll, int row, double c) { const long long q = pos[ll - 1]++; cidx[q] = row; cval[q] = c; });
+  return nent;
+}
+
+int hp3d_gpu_celem_batch(int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif, const double *xnod,
+                         int xnod_ld, const void *source_qp, long long source_ld, const long long *mptr, const long long *cptr,
+                         const int *cidx, const double *cval, const int *idbc, const void *zdofd, const long long *xptr,
+                         const int *nextract, const int *lcon, int isym_flag, const long long *aptr, void *zbload, void *zastif, int *irn,
+                         int *jcn, void *ASchur, long long sAS, void *BSchur, long long sBS, int *ni_out, int *nb_out, int *info) {
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
+  Plan *p = plan_of(plan);
+  if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
+  if (isym_flag < 1 || isym_flag > 3) return fail(HP3D_EINVAL, "celem_batch: ISYM_FLAG must be 1, 2 or 3");
+  if ((irn == nullptr) != (jcn == nullptr)) return fail(HP3D_EINVAL, "celem_batch: irn and jcn go together");
+  if (irn && (isym_flag == 1 || !lcon)) return fail(HP3D_EINVAL, "celem_batch: IRN/JCN need lcon and an unsymmetric ISYM_FLAG (2 or 3)");
+  if (nel == 0) return HP3D_OK;
+  if (nel < 0 || !norder || !norie || !norif || !xnod || !mptr || !cptr || !idbc || !zdofd || !xptr || !zbload || !zastif)
+    return fail(HP3D_EINVAL, "celem_batch: null argument");
+  const bool cplx = p->fp.kind >= HP3D_MAXW_GAL;
+  const long long nm = mptr[nel], nx = xptr[nel], nent = cptr[nm];
+  if (mptr[0] != 0 || xptr[0] != 0 || cptr[0] != 0) return fail(HP3D_EINVAL, "celem_batch: prefix arrays must start at 0");
+  if (nent > 0 && (!cidx || !cval)) return fail(HP3D_EINVAL, "celem_batch: null argument");
+  if (nx > 0 && !nextract) return fail(HP3D_EINVAL, "celem_batch: null argument");
+  // validate the index data against the element sizes (a bad index would read outside the condensed matrix on the device)
+  std::vector<int> hasd(nel, 0);
+  std::string err;
+  CelemCall cc;
+  cc.aoff.resize(nel + 1);
+  cc.xptr = xptr; cc.isym = isym_flag;
+  for (int e = 0; e < nel; e++) {
+    if (mptr[e + 1] < mptr[e] || xptr[e + 1] < xptr[e]) return fail(HP3D_EINVAL, "celem_batch: element %d: prefix arrays must be non-decreasing", e);
+    Signature *S = p->get(etype ? etype[e] : HP3D_MDLB, norder + 19 * e, norie + 12 * e, norif + 6 * e, false, err);
+    if (!S) return fail(HP3D_EINVAL, "element %d: %s", e, err.c_str());
+    const int ni = S->h.ni;
+    const long long nme = mptr[e + 1] - mptr[e];
+    for (long long g = mptr[e]; g < mptr[e + 1]; g++) {
+      if (cptr[g + 1] < cptr[g]) return fail(HP3D_EINVAL, "celem_batch: element %d: cptr must be non-decreasing", e);
+      for (long long q = cptr[g]; q < cptr[g + 1]; q++)
+        if (cidx[q] < 1 || cidx[q] > ni) return fail(HP3D_EINVAL, "celem_batch: element %d: cidx %d outside 1..ni=%d", e, cidx[q], ni);
+      if (idbc[g] == 1) hasd[e] = 1;
+    }
+    for (long long l = xptr[e]; l < xptr[e + 1]; l++)
+      if (nextract[l] < 1 || nextract[l] > nme) return fail(HP3D_EINVAL, "celem_batch: element %d: NEXTRACT %d outside 1..Nrdofm=%lld", e, nextract[l], nme);
+    cc.aoff[e] = aptr ? aptr[e] : (e ? cc.aoff[e - 1] + cc.nz(e - 1) : 0);
+  }
+  cc.zbload = zbload; cc.zastif = zastif; cc.irn = irn; cc.jcn = jcn;
+  auto up = [&](void **d, const void *h, size_t bytes) -> bool {
+    *d = nullptr;
+    if (cudaMalloc(d, bytes ? bytes : 8) != cudaSuccess) return false;
+    return bytes == 0 || cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+  };
+  const size_t es = sizeof(double) * (cplx ? 2 : 1);
+  bool ok = up((void **)&cc.d_mptr, mptr, sizeof(long long) * (nel + 1)) && up((void **)&cc.d_cptr, cptr, sizeof(long long) * (nm + 1)) &&
+            up((void **)&cc.d_xptr, xptr, sizeof(long long) * (nel + 1)) && up((void **)&cc.d_cidx, cidx, sizeof(int) * nent) &&
+            up((void **)&cc.d_cval, cval, sizeof(double) * nent) && up((void **)&cc.d_idbc, idbc, sizeof(int) * nm) &&
+            up((void **)&cc.d_zdofd, zdofd, es * nm) && up((void **)&cc.d_nextract, nextract, sizeof(int) * nx) &&
+            up((void **)&cc.d_lcon, lcon, lcon ? sizeof(int) * nx : 0) && up((void **)&cc.d_hasd, hasd.data(), sizeof(int) * nel);
+  int rc;
+  if (!ok) rc = fail(HP3D_ENOMEM, "celem_batch: cannot place the constraint data on the device: %s", cudaGetErrorString(cudaGetLastError()));
+  else
+    rc = batch_impl(MODE_CELEM, plan, nel, etype, norder, norie, norif, xnod, xnod_ld, source_qp, source_ld, nullptr, 0, nullptr, 0, ASchur, sAS,
+                    BSchur, sBS, ni_out, nb_out, info, nullptr, 0, nullptr, 0, nullptr, &cc);
+  cc.release();
+  return rc;
+}
+
 int hp3d_gpu_quad_points(int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif,
                          const double *xnod, int xnod_ld, double *xq, long long sxq) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
   Plan *p = plan_of(plan);
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
@@ -511,7 +672,7 @@ int hp3d_gpu_quad_points(int plan, int nel, const int *etype, const int *norder,
 
 int hp3d_gpu_stc_bwd_batch(int cplx, int nel, int ni, int nb, const void *ASchur, long long sAS, const void *BSchur, long long sBS,
                            const void *xi, long long sxi, void *xb, long long sxb) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
   if (nel <= 0 || ni <= 0 || nb <= 0) return fail(HP3D_EINVAL, "bad sizes");
   const size_t es = sizeof(double) * (cplx ? 2 : 1);
@@ -539,7 +700,7 @@ int hp3d_gpu_bench(int plan, int nel, const int *norder, const int *norie, const
 int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif, const double *xnod,
                      int xnod_ld, int reps, int max_chunk, int lanes, double *ms_total, double *ms_integ, double *ms_dense,
                      long long *launches) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
   Plan *p = plan_of(plan);
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
@@ -637,7 +798,7 @@ int hp3d_gpu_integrate_debug(int plan, const int *norder, const int *norie, cons
 
 int hp3d_gpu_integrate_debug_t(int plan, int etype, const int *norder, const int *norie, const int *norif, const double *xnod,
                                const void *source_qp, double *W, long long cap_doubles, int *dims) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
   Plan *p = plan_of(plan);
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
@@ -669,7 +830,7 @@ int hp3d_gpu_integrate_debug_t(int plan, int etype, const int *norder, const int
 
 int hp3d_gpu_dense_debug(int cplx, int nel, int n, int nb, int ni, const void *G, const void *Bm, void *Aii, void *Bi,
                          void *ASchur, void *BSchur, int *info) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
   if (nel <= 0 || n <= 0 || nb < 0 || ni <= 0) return fail(HP3D_EINVAL, "bad sizes");
   std::string err;

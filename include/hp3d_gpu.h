@@ -120,6 +120,53 @@ int hp3d_gpu_elem_residual_batch(int plan, int nel, const int *etype, const int 
                                  long long source_ld, const void *xi, long long sxi, const void *xb, long long sxb, double *resid,
                                  int *info);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * what celem_systemI does AFTER elem + stc_fwd_wrapper, fused into the batched call --
+ * constrained-approximation transform ZAMOD = C^T A C, ZBMOD = C^T b, Dirichlet lift, compression to Zbload / Zastif
+ * (src/constrs/celem_systemI.F90:543-785) and, optionally, the COO triplets of the distributed MUMPS interface
+ * (src/solver/par_mumps/par_mumps_sc.F90:419-448).  Only the compressed system travels to the host.
+ *
+ * Physics table of the problem (src/modules/physics.F90), needed to address the modified-element dofs. */
+#define HP3D_MAXPHYS 8
+typedef struct hp3d_physics {
+  int nphys;                  /* NR_PHYSA                                                                     */
+  int dtype[HP3D_MAXPHYS];    /* D_TYPE: 0 CONTIN, 1 TANGEN, 2 NORMAL, 3 DISCON                                */
+  int ncomp[HP3D_MAXPHYS];    /* NR_COMP                                                                       */
+  int adres[HP3D_MAXPHYS];    /* ADRES (offset of the variable's first component within its family, 0-based)   */
+  int nrvar[3];               /* NRHVAR, NREVAR, NRVVAR                                                        */
+} hp3d_physics;
+/* the table of problem_kind as its input/physics file defines it */
+int hp3d_gpu_physics_default(int problem_kind, hp3d_physics *ph);
+
+/* Host-only: turn the output of `logic` (src/constrs/logic.F90) for ONE element into the flat per-modified-dof lists
+ * hp3d_gpu_celem_batch takes.  nrcon?/nac?/constr? are the Fortran arrays nrconH(MAXbrickH), nacH(NACDIM,MAXbrickH),
+ * constrH(NACDIM,MAXbrickH) (and E, V) with nacdim = NACDIM; nrdofl = (nrdoflHi, nrdoflEi, nrdoflVi), nrdofm_f =
+ * (nrdofmH, nrdofmE, nrdofmV) as celem_systemI computes them (:104-236).  Modified dof ll (1..Nrdofm) receives the entries
+ * cidx/cval[cptr[ll-1] .. cptr[ll]-1]: cidx = 1-based row of the condensed element system (order of the rows of Aii, i.e.
+ * physics-blocked as stc.F90:305-323), in the order celem_systemI's loops meet them (so sums are formed in the same order).
+ * Returns the number of entries written (<= cap) or a negative error. */
+long long hp3d_gpu_celem_pack(const hp3d_physics *ph, const int *nrdofl, const int *nrconH, const int *nacH, const double *constrH,
+                              const int *nrconE, const int *nacE, const double *constrE, const int *nrconV, const int *nacV,
+                              const double *constrV, int nacdim, const int *nrdofm_f, long long *cptr /*[Nrdofm+1]*/, int *cidx,
+                              double *cval, long long cap);
+
+/* elem + stc_fwd_wrapper + (celem_systemI.F90:543-785) for nel elements.  Descriptors as hp3d_gpu_elem_batch.  Per element e:
+ *   mptr[e]..mptr[e+1]   its modified dofs g = mptr[e] + ll - 1   (mptr[nel+1]: prefix sums of Nrdofm)
+ *   cptr[g]..cptr[g+1]   entries (cidx 1-based row of Aii, cval) of modified dof g   (cptr[mptr[nel]+1], ABSOLUTE offsets)
+ *   idbc[g], zdofd[g]    IDBC / ZDOFD (value type of the problem; NR_RHS = 1)
+ *   xptr[e]..xptr[e+1]   its compressed dofs (prefix sums of Nrdofc);  nextract[] = NEXTRACT (1-based ll), lcon[] = LCON
+ *                        (global dof numbers, only read when irn/jcn are requested)
+ *   isym_flag            ISYM_FLAG: 1 symmetric packed k=(l1-1)l1/2+l2 with (ZAMOD(k1,k2)+ZAMOD(k2,k1))/2, 2 row-major, 3 column-major
+ * Outputs: zbload[xptr[e] + l1-1]; zastif at aptr[e] (SCALARS; aptr[nel+1] prefix sums of Nrdofc^2 or Nrdofc(Nrdofc+1)/2,
+ * i.e. exactly the layout of mumps_par%A_loc when elements are appended one after the other); irn/jcn (may be NULL; isym_flag
+ * 2 or 3) at the same positions: irn = LCON(row), jcn = LCON(column).  ASchur/BSchur as hp3d_gpu_elem_batch (may be NULL). */
+int hp3d_gpu_celem_batch(int plan, int nel, const int *etype, const int *norder, const int *norient_edge, const int *norient_face,
+                         const double *xnod, int xnod_ld, const void *source_qp, long long source_ld, const long long *mptr,
+                         const long long *cptr, const int *cidx, const double *cval, const int *idbc, const void *zdofd,
+                         const long long *xptr, const int *nextract, const int *lcon, int isym_flag, const long long *aptr,
+                         void *zbload, void *zastif, int *irn, int *jcn, void *ASchur, long long sAS, void *BSchur, long long sBS,
+                         int *ni_out, int *nb_out, int *info);
+
 /* Upper bound on the number of elements processed per internal chunk by hp3d_gpu_elem_batch (0 = automatic: as many
  * as fit in device memory, but at least four chunks for large groups so that result copies overlap compute). */
 int hp3d_gpu_set_chunk(int max_elements);

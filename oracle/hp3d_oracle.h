@@ -211,6 +211,26 @@ int orc_condensed_batch_t(int problem_kind, int nel, const int *etype, const int
                           const double *xnod, int xnod_stride, const orc_params *prm, void *Aii, void *Bi, void *ASchur,
                           void *BSchur, long sAii, long sBi, long sAS, long sBS, int *info, int nthreads);
 
+/* ---- after the element: constrained-approximation transform, Dirichlet lift, compression, COO fill (celem.c).
+ * Physics table of the problem (src/modules/physics.F90): D_TYPE 0 CONTIN, 1 TANGEN, 2 NORMAL, 3 DISCON. */
+#define ORC_MAXPHYS 8
+typedef struct orc_physics {
+  int nphys;                 /* NR_PHYSA */
+  int dtype[ORC_MAXPHYS];    /* D_TYPE   */
+  int ncomp[ORC_MAXPHYS];    /* NR_COMP  */
+  int adres[ORC_MAXPHYS];    /* ADRES: offset of the variable's first component within its family (0-based) */
+  int active[ORC_MAXPHYS];   /* itest(i) = jtrial(i) = 1 and the variable has interface dofs */
+  int nrvar[3];              /* NRHVAR, NREVAR, NRVVAR */
+} orc_physics;
+/* celem_systemI.F90:543-785 */
+int orc_celem_modify(const orc_physics *ph, const int nrdofl[3], const int *const nrcon[3], const int *const nac[3],
+                     const double *const constr[3], int nacdim, const int nrdofm_f[3], int ni, const zdouble *A,
+                     const zdouble *b, const int *idbc, const zdouble *zdofd, int nrdofc, const int *nextract, int isym,
+                     zdouble *zbload, zdouble *zastif, zdouble *zamod_out);
+/* par_mumps_sc.F90:419-448 */
+void orc_coo_fill(int ndof, const int *lcon, const zdouble *ztemp, const zdouble *zload, zdouble *a_loc, int *irn, int *jcn,
+                  zdouble *rhs);
+
 #ifdef __cplusplus
 }
 #endif

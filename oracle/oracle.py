@@ -26,7 +26,7 @@ class Params(C.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, "libhp3d_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("shape.c", "shape_prism.c", "quad_geom.c", "etype.c", "tri_rules.h", "dense.c", "elem.c", "hp3d_oracle.h", "dense.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("shape.c", "shape_prism.c", "quad_geom.c", "etype.c", "tri_rules.h", "dense.c", "elem.c", "celem.c", "hp3d_oracle.h", "dense.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "libhp3d_oracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -290,3 +290,74 @@ def condensed_batch(kind, norder, norie, norif, xnod, prm, nthreads=1):
                                 _d(Aii), _d(Bi), _d(AS), _d(BS), ni * ni, ni, ni * nb, nb, _d(info), int(nthreads))
     # per-element blocks are column-major: expose them as (nel, rows, cols)
     return (np.transpose(Aii, (0, 2, 1)), Bi, np.transpose(AS.reshape(nel, ni, nb), (0, 2, 1)), BS, info, bad)
+
+
+# ---- celem_systemI after the element (celem.c): constraints, Dirichlet lift, compression, COO fill ----------------
+class Physics(C.Structure):
+    _fields_ = [("nphys", C.c_int), ("dtype", C.c_int * 8), ("ncomp", C.c_int * 8), ("adres", C.c_int * 8), ("active", C.c_int * 8),
+                ("nrvar", C.c_int * 3)]
+
+
+def physics_of(kind):
+    """Physics table of the four problems (problems/<PROB>/input/physics): D_TYPE 0 contin, 1 tangen, 2 normal, 3 discon."""
+    table = {POIS_GAL: [(0, 1)], POIS_PDPG: [(0, 1), (2, 1)], MAXW_GAL: [(1, 1)], MAXW_UW: [(1, 2), (3, 6)]}[kind]
+    ph = Physics()
+    ph.nphys = len(table)
+    nvar = [0, 0, 0, 0]
+    for i, (dt, nc) in enumerate(table):
+        ph.dtype[i], ph.ncomp[i], ph.adres[i], ph.active[i] = dt, nc, nvar[dt], int(dt != 3)
+        nvar[dt] += nc
+    for f in range(3):
+        ph.nrvar[f] = nvar[f]
+    return ph
+
+
+def celem_modify(ph, nrdofl, nrcon, nac, constr, nrdofm_f, A, b, idbc, zdofd, nextract, isym, want_zamod=False):
+    """celem_systemI.F90:543-785 on the condensed system (A (ni,ni), b (ni)); nrcon/nac/constr: per family (H,E,V) arrays
+    (nk,), (nk,nacdim), (nk,nacdim) as `logic` returns them (1-based nac).  Returns zbload, zastif[, zamod]."""
+    L = lib()
+    ni = A.shape[0]
+    cplx = np.iscomplexobj(A) or np.iscomplexobj(zdofd)
+    Ac = np.asfortranarray(A, dtype=np.complex128); bc = np.ascontiguousarray(b, dtype=np.complex128)
+    nacdim = max([np.asarray(x).shape[1] for x in nac if np.asarray(x).ndim == 2 and np.asarray(x).size] + [1])
+    keep = []
+
+    def fam(arrs, dt, two_d):
+        out = (C.c_void_p * 3)()
+        for f in range(3):
+            a = np.asarray(arrs[f], dtype=dt)
+            if two_d:
+                full = np.zeros((a.shape[0] if a.ndim == 2 else 0, nacdim), dtype=dt)
+                if a.size:
+                    full[:, :a.shape[1]] = a
+                a = full
+            a = np.ascontiguousarray(a)
+            keep.append(a)
+            out[f] = a.ctypes.data if a.size else None
+        return out
+    p_nrcon, p_nac, p_con = fam(nrcon, np.int32, False), fam(nac, np.int32, True), fam(constr, np.float64, True)
+    nrdofl = _ip(nrdofl); nrdofm_f = _ip(nrdofm_f)
+    nrdofm = int(nrdofm_f.sum())
+    idbc = _ip(idbc); zd = np.ascontiguousarray(zdofd, dtype=np.complex128); nx = _ip(nextract)
+    nc = nx.size
+    zb = np.zeros(nc, np.complex128)
+    za = np.zeros(nc * (nc + 1) // 2 if isym == 1 else nc * nc, np.complex128)
+    zm = np.zeros((nrdofm, nrdofm), np.complex128, order="F") if want_zamod else None
+    r = L.orc_celem_modify(C.byref(ph), _i(nrdofl), p_nrcon, p_nac, p_con, int(nacdim), _i(nrdofm_f), int(ni), _d(Ac), _d(bc), _i(idbc), _d(zd),
+                           int(nc), _i(nx), int(isym), _d(zb), _d(za), _d(zm) if want_zamod else None)
+    assert r == 0, r
+    if not cplx:
+        zb, za = zb.real.copy(), za.real.copy()
+        zm = zm.real.copy() if want_zamod else None
+    return (zb, za, zm) if want_zamod else (zb, za)
+
+
+def coo_fill(lcon, ztemp, zload, ndof_global):
+    """par_mumps_sc.F90:419-448 for one element: (A_loc, IRN, JCN, RHS contribution)."""
+    lcon = _ip(lcon)
+    n = lcon.size
+    zt = np.ascontiguousarray(ztemp, dtype=np.complex128); zl = np.ascontiguousarray(zload, dtype=np.complex128)
+    a = np.zeros(n * n, np.complex128); irn = np.zeros(n * n, np.int32); jcn = np.zeros(n * n, np.int32)
+    rhs = np.zeros(ndof_global, np.complex128)
+    lib().orc_coo_fill(int(n), _i(lcon), _d(zt), _d(zl), _d(a), _i(irn), _i(jcn), _d(rhs))
+    return a, irn, jcn, rhs
