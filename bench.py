@@ -131,6 +131,48 @@ def run_reference(args):
     }))
 
 
+def celem_leg(args, eng, norder, noe, nof, xs, ni, nb, bufs, rank):
+    """End-to-end elements/s of hp3d_gpu_celem_batch (elem + stc + constraints + Dirichlet lift + compression + IRN/JCN) on the
+    e2e workload, plus -- on rank 0 -- the host cost it removes: the oracle's restatement of celem_systemI.F90:543-785 and the
+    COO fill (par_mumps_sc.F90:433-448) timed on one core over a bounded sample."""
+    from hp3d_b200 import synth
+    from hp3d_b200.api import pinned_empty
+    Be = norder.shape[0]
+    cons = synth.synthetic_constraints(args.kind, ni, Be)
+    pk = eng.pack_constraints(cons, 2, True)
+    nz, nx = int(pk["aptr"][-1]), int(pk["xptr"][-1])
+    za = pinned_empty((nz,), eng.dtype); zb = pinned_empty((nx,), eng.dtype); irn = pinned_empty((nz,), np.int32); jcn = pinned_empty((nz,), np.int32)
+    out = dict(zastif=za.a, zbload=zb.a, irn=irn.a, jcn=jcn.a, ASchur=bufs[2].a, BSchur=bufs[3].a)
+    kw = dict(isym_flag=2, want_coo=True, want_schur=True, out=out, packed=pk)
+    for _ in range(2):
+        eng.celem_batch(norder, noe, nof, xs, None, **kw)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = eng.celem_batch(norder, noe, nof, xs, None, **kw)
+    te = time.perf_counter() - t0
+    assert (res["info"] == 0).all()
+    es = 16 if args.kind >= 3 else 8
+    r = {"e2e_value": Be * args.steps / te, "unit": "elements/s (this rank)", "elements_per_step": Be,
+         "d2h_bytes_per_step": int(es * (nz + nx + Be * (nb * ni + nb)) + 8 * nz + 4 * Be),
+         "what": "hp3d_gpu_celem_batch: Zastif (row-major) + Zbload + IRN/JCN + Schur factors to pinned host arrays; 10% of the elements with hanging-node constraints, 20% with Dirichlet data"}
+    if rank == 0 and not args.no_cpu:
+        from oracle import oracle as O
+        pho = O.physics_of(args.kind)
+        Aii = np.zeros((ni, ni), eng.dtype); Aii[...] = np.arange(ni)[:, None] + 1.0
+        Bi = np.ones(ni, eng.dtype)
+        ns = min(Be, 16)
+        t0 = time.perf_counter()
+        for c in cons[:ns]:
+            zbl, zas = O.celem_modify(pho, c["nrdofl"], c["nrcon"], c["nac"], c["constr"], c["nrdofm_f"], Aii, Bi, c["idbc"], c["zdofd"], c["nextract"], 2)
+            O.coo_fill(c["lcon"], zas, zbl, int(c["lcon"].max()))
+        tc = time.perf_counter() - t0
+        r["cpu_port"] = {"value": ns / tc, "unit": "elements/s", "cores": 1, "kind": "port",
+                         "sample": f"{ns} elements: oracle celem_modify + coo_fill (restatement of the host loops), one thread"}
+    for b in (za, zb, irn, jcn):
+        b.free()
+    return r
+
+
 def workload_config(args, B):
     names = {1: "Poisson Galerkin", 2: "Poisson primal DPG (dp=1)", 3: "Maxwell Galerkin", 4: "Maxwell ultraweak DPG (dp=1, adjoint-graph norm)"}
     return {"workload": f"{names[args.kind]}, hexa p={args.p}, complex FP64, perturbed cube mesh (jitter 0.15h, seed 12345)" if args.kind >= 3
@@ -152,6 +194,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--celem", action="store_true", help="also time SURVEY 8f row f1 (constraints + compression + COO fused into the batched call)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -231,6 +274,10 @@ def main():
         e2e = {"value": world * Be * args.steps / te, "unit": "elements/s", "elements_per_gpu_per_step": Be,
                "h2d_bytes_per_step": int(xs.a.nbytes), "d2h_bytes_per_step": int(Be * (es * (ni * ni + ni + nb * ni + nb) + 4)),
                "timer": "host wall clock around the synchronous C-ABI calls (they return after the last D2H)"}
+        # ---- optional: the same step with celem_systemI's transform / compression / COO indices fused in (hp3d_gpu_celem_batch)
+        celem = None
+        if args.celem:
+            celem = celem_leg(args, eng, norder[:Be], noe[:Be], nof[:Be], xs.a, ni, nb, bufs, rank)
         for b in bufs + [xs]:
             b.free()
 
@@ -252,6 +299,8 @@ def main():
                      "peak_source": "own probe: raw FP64 DMMA loop on this pool's B200 (profiles/r01_dmma_probe.jsonl); MEASURED_PEAKS.json has no FP64 entry",
                      "whole_step_frac": F_dense * B * args.steps / (ms * 1e-3) / 1e12 / DMMA_PEAK_TFLOPS},
     }
+    if not args.no_e2e and args.celem:
+        out["celem"] = celem
     if not args.no_cpu:
         cores = host_cores()
         ns = args.cpu_sample or max(16 * cores, 64)   # ~15 s of CPU work (bounded sample)

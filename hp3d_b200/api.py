@@ -238,13 +238,53 @@ class ElemEngine:
         return dict(resid=res, info=info)
 
     def celem_batch(self, norder, norient_edge, norient_face, xnod, cons, isym_flag=2, want_coo=False, want_schur=False,
-                    source_qp=None, etype=None):
+                    source_qp=None, etype=None, out=None, packed=None):
         """elem + stc_fwd_wrapper + the rest of celem_systemI (constraints, Dirichlet lift, compression; :543-785) for nel
         elements (hp3d_gpu_celem_batch).  cons: one dict per element with the flat lists of `celem_pack` (cptr, cidx, cval) and
         idbc, zdofd (Nrdofm,), nextract (Nrdofc,) [1-based], optionally lcon (Nrdofc,) global dof numbers.
+        out: optional dict of preallocated (e.g. pinned) result arrays zbload/zastif/irn/jcn/ASchur/BSchur;
+        packed: the dict `pack_constraints(cons, isym_flag, want_coo)` returns, to keep the Python-side packing out of a timed call.
         Returns dict(zbload, zastif [flat, element e at aptr[e]], xptr, aptr, irn, jcn, ASchur, BSchur, ni, nb, info)."""
         norder, noe, nof, xnod, nel, et = self._descr(norder, norient_edge, norient_face, xnod, etype)
-        assert len(cons) == nel
+        pk = packed if packed is not None else self.pack_constraints(cons, isym_flag, want_coo)
+        mptr, xptr, aptr, cptr = pk["mptr"], pk["xptr"], pk["aptr"], pk["cptr"]
+        assert len(mptr) == nel + 1
+        cidx, cval, idbc, zdofd, nextract, lcon = pk["cidx"], pk["cval"], pk["idbc"], pk["zdofd"], pk["nextract"], pk["lcon"]
+        out = out or {}
+        zb = out.get("zbload"); za = out.get("zastif"); irn = out.get("irn"); jcn = out.get("jcn")
+        if zb is None:
+            zb = np.zeros(max(int(xptr[-1]), 1), self.dtype)
+        if za is None:
+            za = np.zeros(max(int(aptr[-1]), 1), self.dtype)
+        if want_coo and irn is None:
+            irn = np.zeros(max(int(aptr[-1]), 1), np.int32); jcn = np.zeros(max(int(aptr[-1]), 1), np.int32)
+        AS, BS = out.get("ASchur"), out.get("BSchur")
+        sAS = sBS = 0
+        if want_schur and AS is None:
+            szs = [self.sizes(norder[e], MDLB if et is None else int(et[e])) for e in range(nel)]
+            ni = max(s_[0] for s_ in szs); nb = max(s_[1] for s_ in szs)
+            AS = np.zeros((nel, max(nb * ni, 1)), self.dtype); BS = np.zeros((nel, max(nb, 1)), self.dtype)
+        if want_schur:
+            sAS, sBS = AS[0].size, BS[0].size
+        else:
+            AS = BS = None
+        nio = np.zeros(nel, np.int32); nbo = np.zeros(nel, np.int32); info = np.zeros(nel, np.int32)
+        src_ld = 0
+        if source_qp is not None:
+            source_qp = np.ascontiguousarray(source_qp)
+            src_ld = source_qp[0].size * (2 if np.iscomplexobj(source_qp) else 1)
+        f = self.L.hp3d_gpu_celem_batch
+        ll = C.c_longlong
+        f.argtypes = ([C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, ll] + [C.c_void_p] * 9 + [C.c_int] + [C.c_void_p] * 5 +
+                      [C.c_void_p, ll, C.c_void_p, ll] + [C.c_void_p] * 3)
+        _lib.check(f(self.plan, nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(np.prod(xnod.shape[1:])), _ptr(source_qp), src_ld,
+                     _ptr(mptr), _ptr(cptr), _ptr(cidx), _ptr(cval), _ptr(idbc), _ptr(zdofd), _ptr(xptr), _ptr(nextract), _ptr(lcon), int(isym_flag),
+                     _ptr(aptr), _ptr(zb), _ptr(za), _ptr(irn), _ptr(jcn), _ptr(AS), sAS, _ptr(BS), sBS, _ptr(nio), _ptr(nbo), _ptr(info)))
+        return dict(zbload=zb, zastif=za, xptr=xptr, aptr=aptr, irn=irn, jcn=jcn, ASchur=AS, BSchur=BS, ni=nio, nb=nbo, info=info)
+
+    def pack_constraints(self, cons, isym_flag=2, want_coo=False):
+        """Concatenate per-element constraint dicts into the flat arrays of hp3d_gpu_celem_batch (what the Fortran shim builds)."""
+        nel = len(cons)
         mptr = np.zeros(nel + 1, np.int64); xptr = np.zeros(nel + 1, np.int64); aptr = np.zeros(nel + 1, np.int64)
         for e, c in enumerate(cons):
             nm, nc = len(c["idbc"]), len(c["nextract"])
@@ -260,29 +300,7 @@ class ElemEngine:
         cidx, cval = cat("cidx", np.int32), cat("cval", np.float64)
         idbc, zdofd, nextract = cat("idbc", np.int32), cat("zdofd", self.dtype), cat("nextract", np.int32)
         lcon = cat("lcon", np.int32) if want_coo else None
-        zb = np.zeros(max(int(xptr[-1]), 1), self.dtype); za = np.zeros(max(int(aptr[-1]), 1), self.dtype)
-        irn = np.zeros(max(int(aptr[-1]), 1), np.int32) if want_coo else None
-        jcn = np.zeros(max(int(aptr[-1]), 1), np.int32) if want_coo else None
-        AS = BS = None
-        sAS = sBS = 0
-        if want_schur:
-            szs = [self.sizes(norder[e], MDLB if et is None else int(et[e])) for e in range(nel)]
-            ni = max(s_[0] for s_ in szs); nb = max(s_[1] for s_ in szs)
-            AS = np.zeros((nel, max(nb * ni, 1)), self.dtype); BS = np.zeros((nel, max(nb, 1)), self.dtype)
-            sAS, sBS = AS[0].size, BS[0].size
-        nio = np.zeros(nel, np.int32); nbo = np.zeros(nel, np.int32); info = np.zeros(nel, np.int32)
-        src_ld = 0
-        if source_qp is not None:
-            source_qp = np.ascontiguousarray(source_qp)
-            src_ld = source_qp[0].size * (2 if np.iscomplexobj(source_qp) else 1)
-        f = self.L.hp3d_gpu_celem_batch
-        ll = C.c_longlong
-        f.argtypes = ([C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, ll] + [C.c_void_p] * 9 + [C.c_int] + [C.c_void_p] * 5 +
-                      [C.c_void_p, ll, C.c_void_p, ll] + [C.c_void_p] * 3)
-        _lib.check(f(self.plan, nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(np.prod(xnod.shape[1:])), _ptr(source_qp), src_ld,
-                     _ptr(mptr), _ptr(cptr), _ptr(cidx), _ptr(cval), _ptr(idbc), _ptr(zdofd), _ptr(xptr), _ptr(nextract), _ptr(lcon), int(isym_flag),
-                     _ptr(aptr), _ptr(zb), _ptr(za), _ptr(irn), _ptr(jcn), _ptr(AS), sAS, _ptr(BS), sBS, _ptr(nio), _ptr(nbo), _ptr(info)))
-        return dict(zbload=zb, zastif=za, xptr=xptr, aptr=aptr, irn=irn, jcn=jcn, ASchur=AS, BSchur=BS, ni=nio, nb=nbo, info=info)
+        return dict(mptr=mptr, xptr=xptr, aptr=aptr, cptr=cptr, cidx=cidx, cval=cval, idbc=idbc, zdofd=zdofd, nextract=nextract, lcon=lcon)
 
     @staticmethod
     def unpack(res, e):

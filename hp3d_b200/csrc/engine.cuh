@@ -397,27 +397,25 @@ static void run_chunk(const ChunkShape &sh, Lane &L, int ob, const GeomParams &g
   if (ev && ev->on) cudaEventRecord(ev->e[3], st);
 }
 
-// The constraint data of one hp3d_gpu_celem_batch call, resident on the device for the duration of the call.
+// The constraint data of one hp3d_gpu_celem_batch call, resident on the device for the duration of the call (buffers owned by
+// the library's grow-only store).
 struct CelemCall {
   long long *d_mptr = nullptr, *d_cptr = nullptr, *d_xptr = nullptr;
-  int *d_cidx = nullptr, *d_idbc = nullptr, *d_nextract = nullptr, *d_lcon = nullptr, *d_hasd = nullptr;
+  int *d_cidx = nullptr, *d_dlist = nullptr, *d_nextract = nullptr, *d_lcon = nullptr;
+  long long *d_dptr = nullptr;
   double *d_cval = nullptr, *d_zdofd = nullptr;
   const long long *xptr = nullptr;   // host
   std::vector<long long> aoff;       // host: scalar offset of every element's Zastif in the caller's array
   int isym = 2;
   void *zbload = nullptr, *zastif = nullptr; int *irn = nullptr, *jcn = nullptr;   // caller's (host) outputs
   long long nz(int e) const { const long long n = xptr[e + 1] - xptr[e]; return isym == 1 ? n * (n + 1) / 2 : n * n; }
-  void release() {
-    cudaFree(d_mptr); cudaFree(d_cptr); cudaFree(d_xptr); cudaFree(d_cidx); cudaFree(d_idbc); cudaFree(d_nextract); cudaFree(d_lcon);
-    cudaFree(d_hasd); cudaFree(d_cval); cudaFree(d_zdofd);
-  }
 };
 
 // constraint transform + Dirichlet lift + compression of the `nel` condensed systems a chunk left in o.Aii / o.Bi
 static void run_celem(const ChunkShape &sh, Lane &L, const Lane::Out &o, const CelemCall &cc, int nel, cudaStream_t st) {
   CelemArgs a;
-  a.mptr = cc.d_mptr; a.cptr = cc.d_cptr; a.xptr = cc.d_xptr; a.cidx = cc.d_cidx; a.cval = cc.d_cval; a.idbc = cc.d_idbc; a.zdofd = cc.d_zdofd;
-  a.nextract = cc.d_nextract; a.lcon = cc.d_lcon; a.hasd = cc.d_hasd;
+  a.mptr = cc.d_mptr; a.cptr = cc.d_cptr; a.xptr = cc.d_xptr; a.cidx = cc.d_cidx; a.cval = cc.d_cval; a.zdofd = cc.d_zdofd;
+  a.nextract = cc.d_nextract; a.lcon = cc.d_lcon; a.dptr = cc.d_dptr; a.dlist = cc.d_dlist;
   a.cel = L.d_cel; a.ni_e = L.ws.b.ni_e;
   a.Aii = o.Aii; a.Bi = o.Bi; a.sA = (long long)sh.d.ni * sh.d.ni; a.sB = sh.d.ni;
   a.Z = o.Z; a.zb = o.zb; a.irn = cc.irn ? o.irn : nullptr; a.jcn = cc.irn ? o.jcn : nullptr; a.sZ = (long long)sh.nz_max; a.sZb = (long long)sh.nc_max;

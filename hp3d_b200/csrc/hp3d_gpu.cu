@@ -21,6 +21,21 @@ cudaStream_t g_lane_stream[LaneSet::NLANE] = {nullptr, nullptr, nullptr, nullptr
 #define g_compute g_lane_stream[0]
 int g_max_chunk = 0;
 
+struct CelemStore {   // grow-only device buffers for the constraint arrays of hp3d_gpu_celem_batch
+  void *p[10] = {nullptr}; size_t cap[10] = {0};
+  void *get(int i, size_t bytes) {
+    if (bytes > cap[i]) {
+      cudaDeviceSynchronize();
+      cudaFree(p[i]); p[i] = nullptr; cap[i] = 0;
+      const size_t want = bytes + bytes / 4;
+      if (cudaMalloc(&p[i], want) != cudaSuccess) return nullptr;
+      cap[i] = want;
+    }
+    return p[i];
+  }
+  void release() { for (int i = 0; i < 10; i++) { cudaFree(p[i]); p[i] = nullptr; cap[i] = 0; } }
+} g_celem_store;
+
 int fail(int code, const char *fmt, ...) {
   char buf[512];
   va_list ap;
@@ -132,6 +147,7 @@ int hp3d_gpu_finalize(void) {
   cudaDeviceSynchronize();
   g_lanes.release();
   g_arena.release();
+  g_celem_store.release();
   for (int i = 0; i < LaneSet::NLANE; i++)
     if (g_lane_stream[i]) { cudaStreamDestroy(g_lane_stream[i]); g_lane_stream[i] = nullptr; }
   if (g_copy) { cudaStreamDestroy(g_copy); g_copy = nullptr; }
@@ -336,6 +352,10 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
   for (int i = 0; i < NL; i++) CUDA_TRY(cudaEventCreateWithFlags(&evH2D[i], cudaEventDisableTiming));
   int rc = HP3D_OK;
   std::vector<Seg> segs;
+  const bool trace = getenv("HP3D_TRACE") != nullptr;   // host-side phase times of the call on stderr
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = now();
+  double t_wait = 0.0, t_stage = 0.0;
   for (ClassGroup &C : classes) {
     const std::vector<int> &el = C.el;
     const ChunkShape &sh = C.shape;
@@ -384,9 +404,12 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
       const int n = (int)(cstart[nchunk + 1] - c0), ln = nchunk % NL, ob = (nchunk / NL) & 1, slot = ln * 2 + ob;
       Lane &L = g_lanes.lane[ln];
       cudaStream_t st = g_lane_stream[ln];
+      const double tw0 = now();
       if (big) { if (nchunk >= NSLOT) collect_info(nchunk - NSLOT); }   // this slot's previous results are on the host
       else if (nchunk >= NL) collect_info(nchunk - NL);       // small results are staged per LANE: drain before the lane is reused
       if (nchunk >= NL) cudaEventSynchronize(evH2D[ln]);        // the lane's pinned input staging has been consumed
+      const double tw1 = now();
+      t_wait += tw1 - tw0;
       for (int i = 0; i < n; i++) {
         const int e = el[c0 + i];
         const SigHost &h = C.sig[c0 + i]->h;
@@ -404,6 +427,7 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
         }
       }
       if (rc != HP3D_OK) break;
+      t_stage += now() - tw1;
       cudaMemcpyAsync(L.d_xnod, L.h_xnod, sizeof(double) * nx * n, cudaMemcpyHostToDevice, st);
       if (gp.source == HP3D_SRC_TABLE) cudaMemcpyAsync(L.d_src, L.h_src, sizeof(double) * nsrc * n, cudaMemcpyHostToDevice, st);
       cudaMemcpyAsync(L.ws.b.ni_e, L.h_cnt, sizeof(int) * n, cudaMemcpyHostToDevice, st);
@@ -472,8 +496,13 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) { rc = fail(HP3D_ENODEV, "CUDA error in elem_batch: %s", cudaGetErrorString(ce)); break; }
   }
+  const double t_submitted = now();
   for (int i = 0; i < NL; i++) cudaStreamSynchronize(g_lane_stream[i]);
+  const double t_computed = now();
   cudaStreamSynchronize(g_copy);
+  if (trace)
+    fprintf(stderr, "[hp3d] mode %d nel %d: submit %.1f ms (waits %.1f, staging %.1f), compute drained +%.1f ms, copies drained +%.1f ms\n", mode, nel,
+            t_submitted - t_begin, t_wait, t_stage, t_computed - t_submitted, now() - t_computed);
   for (int i = 0; i < NSLOT; i++) { cudaEventDestroy(evCompute[i]); cudaEventDestroy(evCopy[i]); }
   for (int i = 0; i < NL; i++) cudaEventDestroy(evH2D[i]);
   if (rc == HP3D_OK) {
@@ -590,12 +619,16 @@ int hp3d_gpu_celem_batch(int plan, int nel, const int *etype, const int *norder,
   if (nel < 0 || !norder || !norie || !norif || !xnod || !mptr || !cptr || !idbc || !zdofd || !xptr || !zbload || !zastif)
     return fail(HP3D_EINVAL, "celem_batch: null argument");
   const bool cplx = p->fp.kind >= HP3D_MAXW_GAL;
+  const bool trace = getenv("HP3D_TRACE") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
   const long long nm = mptr[nel], nx = xptr[nel], nent = cptr[nm];
   if (mptr[0] != 0 || xptr[0] != 0 || cptr[0] != 0) return fail(HP3D_EINVAL, "celem_batch: prefix arrays must start at 0");
   if (nent > 0 && (!cidx || !cval)) return fail(HP3D_EINVAL, "celem_batch: null argument");
   if (nx > 0 && !nextract) return fail(HP3D_EINVAL, "celem_batch: null argument");
   // validate the index data against the element sizes (a bad index would read outside the condensed matrix on the device)
-  std::vector<int> hasd(nel, 0);
+  std::vector<long long> dptr(nel + 1, 0);   // Dirichlet dofs per element (compact, ascending)
+  std::vector<int> dlist;
   std::string err;
   CelemCall cc;
   cc.aoff.resize(nel + 1);
@@ -610,30 +643,39 @@ int hp3d_gpu_celem_batch(int plan, int nel, const int *etype, const int *norder,
       if (cptr[g + 1] < cptr[g]) return fail(HP3D_EINVAL, "celem_batch: element %d: cptr must be non-decreasing", e);
       for (long long q = cptr[g]; q < cptr[g + 1]; q++)
         if (cidx[q] < 1 || cidx[q] > ni) return fail(HP3D_EINVAL, "celem_batch: element %d: cidx %d outside 1..ni=%d", e, cidx[q], ni);
-      if (idbc[g] == 1) hasd[e] = 1;
+      if (idbc[g] == 1) dlist.push_back((int)(g - mptr[e]));
     }
     for (long long l = xptr[e]; l < xptr[e + 1]; l++)
       if (nextract[l] < 1 || nextract[l] > nme) return fail(HP3D_EINVAL, "celem_batch: element %d: NEXTRACT %d outside 1..Nrdofm=%lld", e, nextract[l], nme);
+    dptr[e + 1] = (long long)dlist.size();
     cc.aoff[e] = aptr ? aptr[e] : (e ? cc.aoff[e - 1] + cc.nz(e - 1) : 0);
   }
   cc.zbload = zbload; cc.zastif = zastif; cc.irn = irn; cc.jcn = jcn;
-  auto up = [&](void **d, const void *h, size_t bytes) -> bool {
-    *d = nullptr;
-    if (cudaMalloc(d, bytes ? bytes : 8) != cudaSuccess) return false;
-    return bytes == 0 || cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+  const double t1 = now();
+  // the constraint arrays live in grow-only device buffers owned by the library (no cudaMalloc / cudaFree per call)
+  auto up = [&](int slot, const void *h, size_t bytes) -> void * {
+    void *d = g_celem_store.get(slot, bytes ? bytes : 8);
+    if (d && bytes && cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, g_compute) != cudaSuccess) return nullptr;
+    return d;
   };
   const size_t es = sizeof(double) * (cplx ? 2 : 1);
-  bool ok = up((void **)&cc.d_mptr, mptr, sizeof(long long) * (nel + 1)) && up((void **)&cc.d_cptr, cptr, sizeof(long long) * (nm + 1)) &&
-            up((void **)&cc.d_xptr, xptr, sizeof(long long) * (nel + 1)) && up((void **)&cc.d_cidx, cidx, sizeof(int) * nent) &&
-            up((void **)&cc.d_cval, cval, sizeof(double) * nent) && up((void **)&cc.d_idbc, idbc, sizeof(int) * nm) &&
-            up((void **)&cc.d_zdofd, zdofd, es * nm) && up((void **)&cc.d_nextract, nextract, sizeof(int) * nx) &&
-            up((void **)&cc.d_lcon, lcon, lcon ? sizeof(int) * nx : 0) && up((void **)&cc.d_hasd, hasd.data(), sizeof(int) * nel);
+  cc.d_mptr = (long long *)up(0, mptr, sizeof(long long) * (nel + 1)); cc.d_cptr = (long long *)up(1, cptr, sizeof(long long) * (nm + 1));
+  cc.d_xptr = (long long *)up(2, xptr, sizeof(long long) * (nel + 1)); cc.d_cidx = (int *)up(3, cidx, sizeof(int) * nent);
+  cc.d_cval = (double *)up(4, cval, sizeof(double) * nent); cc.d_dlist = (int *)up(5, dlist.data(), sizeof(int) * dlist.size());
+  cc.d_zdofd = (double *)up(6, zdofd, es * nm); cc.d_nextract = (int *)up(7, nextract, sizeof(int) * nx);
+  cc.d_lcon = (int *)up(8, lcon, lcon ? sizeof(int) * nx : 0); cc.d_dptr = (long long *)up(9, dptr.data(), sizeof(long long) * (nel + 1));
+  bool ok = cc.d_mptr && cc.d_cptr && cc.d_xptr && cc.d_cidx && cc.d_cval && cc.d_dlist && cc.d_zdofd && cc.d_nextract && cc.d_lcon && cc.d_dptr;
+  // the lanes read these arrays: every lane stream waits for the uploads (pageable sources: the copies are staged by the driver
+  // before cudaMemcpyAsync returns, so the local vectors may go out of scope)
+  if (ok) ok = cudaStreamSynchronize(g_compute) == cudaSuccess;
   int rc;
+  const double t2 = now();
   if (!ok) rc = fail(HP3D_ENOMEM, "celem_batch: cannot place the constraint data on the device: %s", cudaGetErrorString(cudaGetLastError()));
   else
     rc = batch_impl(MODE_CELEM, plan, nel, etype, norder, norie, norif, xnod, xnod_ld, source_qp, source_ld, nullptr, 0, nullptr, 0, ASchur, sAS,
                     BSchur, sBS, ni_out, nb_out, info, nullptr, 0, nullptr, 0, nullptr, &cc);
-  cc.release();
+  const double t3 = now();
+  if (trace) fprintf(stderr, "[hp3d] celem_batch: validate %.1f ms, upload %.1f ms, pipeline %.1f ms, release %.1f ms\n", t1 - t0, t2 - t1, t3 - t2, now() - t3);
   return rc;
 }
 

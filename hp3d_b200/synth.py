@@ -212,3 +212,48 @@ def hp_mesh(N, prism_frac=0.3, pmin=2, pmax=7, seed_p=2024, seed_g=7, jitter=0.0
         xnod[e, :len(v)] = coords[np.array(v)]
     return dict(etype=etype, norder=norder, norient_edge=noe, norient_face=nof, xnod=xnod, nrdofH=nH, verts=verts, p=p,
                 gid=gid, coords=coords)
+
+
+def synthetic_constraints(kind, ni, nel, frac_hanging=0.1, frac_boundary=0.2, seed=99, nacdim=4):
+    """Per-element input of celem_systemI's transform/compression step for a synthetic mesh: most elements
+    are regular (every element dof is its own modified dof), `frac_hanging` of them have 30 % of their dofs constrained to
+    2..nacdim parents (1-irregular refinement), `frac_boundary` of them carry Dirichlet data on 15 % of their dofs.
+    Single-family problems only (kinds 1, 3, 4).  Returns a list of dicts for ElemEngine.celem_batch."""
+    from . import api
+    if kind == 2:
+        raise ValueError("synthetic_constraints: single-family problems only")
+    ph = api.physics_default(kind)
+    fam = ph.dtype[0]
+    ncomp = ph.ncomp[0]
+    nk = ni // ncomp
+    cplx = kind >= 3
+    rng = np.random.default_rng(seed)
+    out = []
+    gdof = 1
+    for e in range(nel):
+        hang = rng.random() < frac_hanging
+        nm = nk + (nk // 10 if hang else 0)
+        rc = np.ones(nk, np.int32); na = np.zeros((nk, nacdim), np.int32); co = np.zeros((nk, nacdim))
+        na[:, 0] = np.arange(1, nk + 1); co[:, 0] = 1.0
+        if hang:
+            for k in np.flatnonzero(rng.random(nk) < 0.3):
+                m = int(rng.integers(2, nacdim + 1))
+                rc[k] = m; na[k, :m] = rng.choice(nm, m, replace=False) + 1; co[k, :m] = 1.0 / m
+        nrdofl = [0, 0, 0]; nrdofm_f = [0, 0, 0]
+        nrdofl[fam] = nk; nrdofm_f[fam] = nm * ncomp
+        z = np.zeros((0, nacdim))
+        nrcon = [np.zeros(0, np.int32)] * 3; nac = [z.astype(np.int32)] * 3; con = [z] * 3
+        nrcon[fam], nac[fam], con[fam] = rc, na, co
+        cptr, cidx, cval = api.celem_pack(ph, nrdofl, nrcon, nac, con, nrdofm_f)
+        nrdofm = nm * ncomp
+        idbc = np.zeros(nrdofm, np.int32)
+        if rng.random() < frac_boundary:
+            idbc[rng.random(nrdofm) < 0.15] = 1
+        zd = np.where(idbc == 1, rng.standard_normal(nrdofm) + (1j * rng.standard_normal(nrdofm) if cplx else 0), 0)
+        zd = zd.astype(np.complex128 if cplx else np.float64)
+        nextract = (np.flatnonzero(idbc == 0)[::-1] + 1).astype(np.int32)
+        lcon = (gdof + np.arange(len(nextract))).astype(np.int32)
+        gdof += len(nextract) // 2          # neighbours share dofs
+        out.append(dict(nrdofl=nrdofl, nrcon=nrcon, nac=nac, constr=con, nrdofm_f=nrdofm_f, idbc=idbc, zdofd=zd, nextract=nextract, lcon=lcon,
+                        cptr=cptr, cidx=cidx, cval=cval))
+    return out
