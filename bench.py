@@ -32,6 +32,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+GEMM_DRAM_BYTES_PER_ELEMENT_LAUNCH = 1230.5e6 / 103   # ncu, p=5 ultraweak Maxwell (profiles/r01_launches_traffic_b32_summary.csv)
 DMMA_PEAK_TFLOPS = 37.05   # measured on this pool's B200: raw mma.sync m16n8k16.f64 loop (profiles/r01_dmma_probe.jsonl);
                            # cuBLAS DGEMM 8192^3 reaches 35.5, ZGEMM 4096^3 36.8 (profiles/r01_fp64_peak.json)
 
@@ -292,7 +293,9 @@ def main():
         "dtype": "c128" if args.kind >= 3 else "f64", "data": "synthetic", "config": workload_config(args, B),
         "gpu_launches": int(r["launches"]), "clocks": clocks, "e2e": e2e,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / DMMA_PEAK_TFLOPS,
-                     "traffic": None, "kernel": "gemm_nc_kernel<complex> (all launches of the dense phase: Cholesky panels, solves, HERK, Schur)",
+                     "traffic": GEMM_DRAM_BYTES_PER_ELEMENT_LAUNCH * ((B + 1) // 2) if args.kind == 4 and args.p == 5 else None,
+                     "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, average over the 103 gemm_nc_kernel launches of one 32-element chunk, scaled to this run's chunk (profiles/r01_launches_traffic_b32_summary.csv): bytes per launch; the operands stream from HBM once per panel, 12 % of HBM bandwidth",
+                     "kernel": "gemm_nc_kernel<complex> (all launches of the dense phase: Cholesky panels, solves, HERK, Schur)",
                      "flops_per_element": F_dense, "ms_dense_per_step": ms_dense / args.steps, "ms_integration_per_step": ms_integ / args.steps,
                      "ms_per_step_single_stream": ms_single / args.steps,
                      "timing": "achieved = algorithmic dense flops / CUDA-event time of the dense phase in a single-stream pass of the same K steps; whole_step_frac uses the two-stream step time that `value` reports",
@@ -301,7 +304,7 @@ def main():
     }
     if not args.no_e2e and args.celem:
         out["celem"] = celem
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:   # CPU baseline beside the GPU number: rank 0 at N=1 only
         cores = host_cores()
         ns = args.cpu_sample or max(16 * cores, 64)   # ~15 s of CPU work (bounded sample)
         v, dtc, blas = cpu_reference_rate(args.kind, args.p, ns, cores, omega)

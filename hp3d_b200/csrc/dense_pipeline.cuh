@@ -16,6 +16,11 @@ inline int pad64(int n) { return (n + TILE - 1) / TILE * TILE; }
 struct DenseDims {
   bool cplx = true;
   bool dpg = true;     // true: Gram + enriched stiffness present; false: A is given directly
+  // "real-structured" complex problem: the element system is T A~ T^H with A~ REAL and T a diagonal matrix of powers of i
+  // (lossless ultraweak Maxwell, see forms.hpp); the dense phase then runs in real arithmetic (cplx = false, one plane) with the
+  // complex load carried as TWO real rows (nload = 2), and the output kernels re-apply the phases.
+  bool rs = false;
+  int nload = 1;       // load rows: the last `nload` padded interface rows
   int n = 0;           // test dofs (rows of the Gram)
   int nb = 0, ni = 0;  // bubble / interface trial dofs
   int np = 0, nbp = 0, nip = 0;  // padded: np=pad64(n), nbp=pad64(nb), nip=pad64(ni+1); the load sits at interface index nip-1
@@ -23,7 +28,7 @@ struct DenseDims {
   // below only use np/nbp/nip plus the per-element counts in DenseBuffers::ni_e / nb_e; n, nb, ni here are the class maxima.
   __host__ __device__ int M() const { return nbp + nip; }
   __host__ __device__ int R() const { return np + nbp + nip; }
-  void finish() { np = dpg ? pad64(n) : 0; nbp = pad64(nb); nip = pad64(ni + 1); }
+  void finish() { np = dpg ? pad64(n) : 0; nbp = pad64(nb); nip = pad64(ni + nload); }
   // doubles per element
   __host__ __device__ size_t planes() const { return cplx ? 2 : 1; }
   __host__ __device__ size_t w_plane() const { return (size_t)R() * np; }

@@ -136,9 +136,9 @@ struct ChunkShape {
   size_t src_max = 0;          // doubles per element of a caller-supplied source table
   size_t nz_max = 0, nc_max = 0;   // hp3d_gpu_celem_batch only: scalars of Zastif / Zbload per element (maxima of the group)
   bool coo = false;                //   ... and IRN/JCN staging
-  int ns() const { return d.cplx ? 2 : 1; }
+  int ns() const { return (d.cplx || d.rs) ? 2 : 1; }   // doubles per scalar of the caller's value type
   bool covers(const ChunkShape &o) const {
-    return d.cplx == o.d.cplx && d.dpg == o.d.dpg && gen_stc == o.gen_stc && d.np == o.d.np && d.nbp == o.d.nbp && d.nip == o.d.nip &&
+    return d.cplx == o.d.cplx && d.rs == o.d.rs && d.nload == o.d.nload && d.dpg == o.d.dpg && gen_stc == o.gen_stc && d.np == o.d.np && d.nbp == o.d.nbp && d.nip == o.d.nip &&
            d.ni >= o.d.ni && d.nb >= o.d.nb && nint_max >= o.nint_max && nH_max >= o.nH_max && src_max >= o.src_max &&
            nz_max >= o.nz_max && nc_max >= o.nc_max && (coo || !o.coo);
   }
@@ -150,7 +150,7 @@ struct ChunkShape {
   }
   static std::string key(const SigHost &h) {
     char b[96];
-    snprintf(b, sizeof b, "%d/%d/%d/%d/%d/%d", (int)h.cplx, (int)h.dpg, (int)h.gen_stc, h.dims.np, h.dims.nbp, h.dims.nip);
+    snprintf(b, sizeof b, "%d/%d/%d/%d/%d/%d/%d", (int)h.cplx, (int)h.dims.rs, (int)h.dpg, (int)h.gen_stc, h.dims.np, h.dims.nbp, h.dims.nip);
     return b;
   }
 };
@@ -334,14 +334,19 @@ static long long dense_phase_launches(const DenseDims &d) {  // mirrors the laun
   return n;
 }
 
-template <bool CPLX>
+// CPLX: arithmetic of the dense phase; RS: real-structured complex problem (real dense phase, complex outputs: DenseDims::rs)
+template <bool CPLX, bool RS>
 static void run_dense_and_scatter(const ChunkShape &sh, Lane &L, const Lane::Out &o, int nel, bool want_schur, cudaStream_t st, StageEvents *ev,
                                   int mode) {
+  static_assert(!(CPLX && RS), "the real-structured path runs the dense phase in real arithmetic");
+  constexpr bool OUTC = CPLX || RS;   // value type of the outputs
   const DenseDims &d = sh.d;
   if (mode == MODE_RESID) {   // uncondensed DPG system, then eta^2 = v^H A v
     dense_phase<CPLX>(d, L.ws.b, nel, st, true);
-    dpg_residual_kernel<CPLX><<<nel, 256, sizeof(double) * 2 * d.M(), st>>>(d, L.ws.b.Am, L.ws.b.ni_e, L.ws.b.nb_e, L.d_xi, (long long)d.ni, L.d_xb,
-                                                                           (long long)d.nb + 1, L.d_res);
+    if (RS) dpg_residual_rs_kernel<<<nel, 256, sizeof(double) * 2 * d.M(), st>>>(d, L.ws.b.Am, L.ws.b.ni_e, L.ws.b.nb_e, L.d_xi, (long long)d.ni, L.d_xb,
+                                                                                (long long)d.nb + 1, L.d_res);
+    else dpg_residual_kernel<CPLX><<<nel, 256, sizeof(double) * 2 * d.M(), st>>>(d, L.ws.b.Am, L.ws.b.ni_e, L.ws.b.nb_e, L.d_xi, (long long)d.ni, L.d_xb,
+                                                                                (long long)d.nb + 1, L.d_res);
     g_launches += 2;
     cudaMemcpyAsync(o.info, L.ws.b.info, sizeof(int) * nel, cudaMemcpyDeviceToDevice, st);
     return;
@@ -368,17 +373,19 @@ static void run_dense_and_scatter(const ChunkShape &sh, Lane &L, const Lane::Out
   if (ev && ev->on) cudaEventRecord(ev->e[2], st);
   OutMaps mp{g_lanes.d_iota, g_lanes.d_iota, g_lanes.d_ones, g_lanes.d_ones, 0, 0, 0, 0, L.ws.b.ni_e, L.ws.b.nb_e};
   dim3 blk(16, 16), g1((d.ni + 15) / 16, (d.ni + 15) / 16, nel);
-  scatter_condensed_kernel<CPLX><<<g1, blk, 0, st>>>(d, L.ws.b.Am, mp, o.Aii, o.Bi, (long long)d.ni * d.ni, (long long)d.ni);
+  if (RS) scatter_condensed_rs_kernel<<<g1, blk, 0, st>>>(d, L.ws.b.Am, mp, o.Aii, o.Bi, (long long)d.ni * d.ni, (long long)d.ni);
+  else scatter_condensed_kernel<CPLX><<<g1, blk, 0, st>>>(d, L.ws.b.Am, mp, o.Aii, o.Bi, (long long)d.ni * d.ni, (long long)d.ni);
   g_launches++;
   if (d.nb > 0 && want_schur) {
     dim3 g2((d.nb + 15) / 16, (d.ni + 15) / 16, nel);
-    scatter_schur_kernel<CPLX><<<g2, blk, 0, st>>>(d, L.ws.b.Am, mp, o.AS, o.BS, (long long)d.nb * d.ni, (long long)d.nb);
+    if (RS) scatter_schur_rs_kernel<<<g2, blk, 0, st>>>(d, L.ws.b.Am, mp, o.AS, o.BS, (long long)d.nb * d.ni, (long long)d.nb);
+    else scatter_schur_kernel<CPLX><<<g2, blk, 0, st>>>(d, L.ws.b.Am, mp, o.AS, o.BS, (long long)d.nb * d.ni, (long long)d.nb);
     g_launches++;
   }
   cudaMemcpyAsync(o.info, L.ws.b.info, sizeof(int) * nel, cudaMemcpyDeviceToDevice, st);
   if (mode == MODE_BWD && d.nb > 0) {
     dim3 gb((d.nb + 7) / 8, nel);
-    stc_bwd_kernel<CPLX><<<gb, 256, 0, st>>>(L.ws.b.ni_e, L.ws.b.nb_e, 0, 0, o.AS, (long long)d.nb * d.ni, o.BS, (long long)d.nb, L.d_xi, (long long)d.ni,
+    stc_bwd_kernel<OUTC><<<gb, 256, 0, st>>>(L.ws.b.ni_e, L.ws.b.nb_e, 0, 0, o.AS, (long long)d.nb * d.ni, o.BS, (long long)d.nb, L.d_xi, (long long)d.ni,
                                              L.d_xb, (long long)d.nb + 1);
     g_launches++;
   }
@@ -392,8 +399,9 @@ static void run_chunk(const ChunkShape &sh, Lane &L, int ob, const GeomParams &g
   if (ev && ev->on) cudaEventRecord(ev->e[0], st);
   run_integration(sh, L, gp, segs, nel, d_xnod, xnod_ld, d_src, src_ld, st);
   if (ev && ev->on) cudaEventRecord(ev->e[1], st);
-  if (sh.d.cplx) run_dense_and_scatter<true>(sh, L, L.out[ob], nel, want_schur, st, ev, mode);
-  else run_dense_and_scatter<false>(sh, L, L.out[ob], nel, want_schur, st, ev, mode);
+  if (sh.d.rs) run_dense_and_scatter<false, true>(sh, L, L.out[ob], nel, want_schur, st, ev, mode);
+  else if (sh.d.cplx) run_dense_and_scatter<true, false>(sh, L, L.out[ob], nel, want_schur, st, ev, mode);
+  else run_dense_and_scatter<false, false>(sh, L, L.out[ob], nel, want_schur, st, ev, mode);
   if (ev && ev->on) cudaEventRecord(ev->e[3], st);
 }
 
@@ -423,7 +431,7 @@ static void run_celem(const ChunkShape &sh, Lane &L, const Lane::Out &o, const C
   if (sh.nc_max == 0) return;
   const unsigned nt = (unsigned)((sh.nc_max + 31) / 32);
   dim3 gl((unsigned)((sh.nc_max + 127) / 128), nel), gc(nt, nt, nel), bc(32, 8);
-  if (sh.d.cplx) { celem_load_kernel<true><<<gl, 128, 0, st>>>(a); celem_compress_kernel<true><<<gc, bc, 0, st>>>(a); }
+  if (sh.ns() == 2) { celem_load_kernel<true><<<gl, 128, 0, st>>>(a); celem_compress_kernel<true><<<gc, bc, 0, st>>>(a); }
   else { celem_load_kernel<false><<<gl, 128, 0, st>>>(a); celem_compress_kernel<false><<<gc, bc, 0, st>>>(a); }
   g_launches += 2;
 }

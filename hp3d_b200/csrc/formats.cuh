@@ -140,4 +140,102 @@ __global__ void __launch_bounds__(256) dpg_residual_kernel(DenseDims d, const do
   if (tid == 0) { double s = 0.0; for (int w = 0; w < nw; w++) s += red[w]; res[e] = s; }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Real-structured complex problems (DenseDims::rs): the dense phase worked on A~ (real) with A = T A~ T^H, T = diag(i^ph);
+// the output kernels re-apply the phases.  ph of reference dof k: ultraweak Maxwell interface dofs 2j+ivar -> ivar (E-trace 0,
+// H-trace 1), bubble dofs 6j+c -> (c >= 3) (E components 0, H components 1).  The complex load is carried as two real rows
+// (lrow, lrow+1) = W~_B G~^-1 (Re, Im of the stored load row); b_t = -i * i^ph_t * (y_re - i y_im)   (see forms.hpp).
+__device__ __forceinline__ int rs_phase_i(int k) { return k & 1; }
+__device__ __forceinline__ int rs_phase_b(int k) { return (k % 6) >= 3; }
+// multiply the real number v by i^(pr - pc) (pr, pc in {0,1})
+__device__ __forceinline__ void rs_apply(double v, int pr, int pc, double &re, double &im) {
+  const int d = pr - pc;
+  re = d == 0 ? v : 0.0;
+  im = d == 0 ? 0.0 : (d > 0 ? v : -v);
+}
+__device__ __forceinline__ void rs_load(double yre, double yim, int ph, double &re, double &im) {
+  if (ph == 0) { re = -yim; im = -yre; }   // -i (y_re - i y_im)
+  else { re = yre; im = -yim; }            //  i * -i (y_re - i y_im)
+}
+
+// grid = (ceil(ni/16), ceil(ni/16), batch), block (16,16): complex Aii (ni x ni), Bi (ni) from the real Schur complement
+__global__ void scatter_condensed_rs_kernel(DenseDims d, const double *Am, OutMaps mp, double *Aii, double *Bi, long long sA, long long sB) {
+  const int e = blockIdx.z;
+  const int r = blockIdx.x * 16 + threadIdx.x, c = blockIdx.y * 16 + threadIdx.y;
+  const int M = d.M();
+  const double *S = Am + (long long)e * (long long)d.a_plane() + (long long)d.nbp * M + d.nbp;
+  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, lrow = d.nip - 2;
+  if (r < ni && c < ni) {
+    const int a = r >= c ? r : c, b = r >= c ? c : r;
+    double re, im;
+    rs_apply(S[(long long)a * M + b], rs_phase_i(r), rs_phase_i(c), re, im);
+    double *o = Aii + (long long)e * sA * 2 + ((long long)r + (long long)ni * c) * 2;
+    o[0] = re; o[1] = im;
+  }
+  if (blockIdx.y == 0 && threadIdx.y == 0 && r < ni) {
+    double re, im;
+    rs_load(S[(long long)lrow * M + r], S[(long long)(lrow + 1) * M + r], rs_phase_i(r), re, im);
+    double *o = Bi + (long long)e * sB * 2 + (long long)r * 2;
+    o[0] = re; o[1] = im;
+  }
+}
+
+// grid = (ceil(nb/16), ceil(ni/16), batch), block (16,16): ASchur[b,i] = conj(Z[i,b]) = i^(ph_b - ph_i) Z~[i,b], BSchur like Bi
+__global__ void scatter_schur_rs_kernel(DenseDims d, const double *Am, OutMaps mp, double *AS, double *BS, long long sAS, long long sBS) {
+  const int e = blockIdx.z;
+  const int bq = blockIdx.x * 16 + threadIdx.x, iq = blockIdx.y * 16 + threadIdx.y;
+  const int M = d.M();
+  const double *Z = Am + (long long)e * (long long)d.a_plane() + (long long)d.nbp * M;
+  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, nb = mp.nb_e ? mp.nb_e[e] : d.nb, lrow = d.nip - 2;
+  if (bq < nb && iq < ni) {
+    double re, im;
+    rs_apply(Z[(long long)iq * M + bq], rs_phase_b(bq), rs_phase_i(iq), re, im);
+    double *o = AS + (long long)e * sAS * 2 + ((long long)bq + (long long)nb * iq) * 2;
+    o[0] = re; o[1] = im;
+  }
+  if (blockIdx.y == 0 && threadIdx.y == 0 && bq < nb) {
+    double re, im;
+    rs_load(Z[(long long)lrow * M + bq], Z[(long long)(lrow + 1) * M + bq], rs_phase_b(bq), re, im);
+    double *o = BS + (long long)e * sBS * 2 + (long long)bq * 2;
+    o[0] = re; o[1] = im;
+  }
+}
+
+// DPG residual in the real-structured form: with u~ = T^H u,  eta^2 = v1^T A~ v1 + v2^T A~ v2 on the uncondensed real normal
+// equations (two load rows at M-2, M-1): with phi = i W~_B^T u~ - conj(load),  Im phi = [W~_B; l_re; l_im]^T v1, -Re phi = [..]^T v2,
+// v1 = [Re u~ ; 0 ; 1], v2 = [Im u~ ; 1 ; 0].  One CTA (256 threads) per element.
+__global__ void __launch_bounds__(256) dpg_residual_rs_kernel(DenseDims d, const double *Am, const int *__restrict__ ni_e, const int *__restrict__ nb_e,
+                                                              const double *xi, long long sxi, const double *xb, long long sxb, double *res) {
+  extern __shared__ double sv[];   // v1, v2: [2][M]
+  __shared__ double red[8];
+  const int e = blockIdx.x, M = d.M(), tid = threadIdx.x;
+  const double *A = Am + (long long)e * (long long)d.a_plane();
+  const int ni = ni_e[e], nb = nb_e[e];
+  double *v1 = sv, *v2 = sv + M;
+  for (int i = tid; i < M; i += blockDim.x) {
+    double ur = 0.0, ui = 0.0;
+    int ph = 0;
+    if (i < nb) { ur = xb[((long long)e * sxb + i) * 2]; ui = xb[((long long)e * sxb + i) * 2 + 1]; ph = rs_phase_b(i); }
+    else if (i >= d.nbp && i < d.nbp + ni) { const int k = i - d.nbp; ur = xi[((long long)e * sxi + k) * 2]; ui = xi[((long long)e * sxi + k) * 2 + 1]; ph = rs_phase_i(k); }
+    // u~ = conj(i^ph) u
+    double a = ph ? ui : ur, b = ph ? -ur : ui;
+    if (i == M - 2) { a = 0.0; b = 1.0; }
+    if (i == M - 1) { a = 1.0; b = 0.0; }
+    v1[i] = a; v2[i] = b;
+  }
+  __syncthreads();
+  double acc = 0.0;
+  const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  for (int i = warp; i < M; i += nw) {
+    const double *ar = A + (long long)i * M;
+    double y1 = 0.0, y2 = 0.0;
+    for (int j = lane; j < i; j += 32) { const double a = ar[j]; y1 += a * v1[j]; y2 += a * v2[j]; }
+    for (int o = 16; o; o >>= 1) { y1 += __shfl_xor_sync(0xffffffffu, y1, o); y2 += __shfl_xor_sync(0xffffffffu, y2, o); }
+    if (lane == 0) acc += ar[i] * (v1[i] * v1[i] + v2[i] * v2[i]) + 2.0 * (v1[i] * y1 + v2[i] * y2);
+  }
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (tid == 0) { double s = 0.0; for (int w = 0; w < nw; w++) s += red[w]; res[e] = s; }
+}
+
 }  // namespace hp3d

@@ -33,6 +33,11 @@ struct FormParams {
   int kind = 0, nord_add = 1, maxp = 6, test_norm = 1;
   double alpha_norm = 1, omega = 1, eps = 1, mu = 1, sigma = 0;
   int source = 1, icomp = 0;
+  // Ultraweak Maxwell with real eps, mu and no conductivity: with T = diag(i^ph) (ph = 0 for E-type trial dofs and the test
+  // functions F, 1 for H-type dofs and G), the Gram matrix D^H G D is REAL and the enriched stiffness D^H B T is purely
+  // imaginary, so A = T A~ T^H with A~ = R G~^-1 R^T real: the whole dense phase runs in real arithmetic (a quarter of the
+  // flops of the reference's ZPOTRF/ZTRTRS/ZHERK) and the phases come back in the output kernels (formats.cuh).
+  bool real_struct = true;
 };
 
 // element_data.F90:106-109 (0-based): edges of face f: [0],[2] run along the face's first axis, [1],[3] along the second
@@ -116,6 +121,15 @@ struct BlockBuilder {
       for (int i = 0; i < fa.n[0]; i++) { WorkItem w; w.block = (short)bi; w.iA = (short)i; w.jA = (short)j; w.pad = 0; S.work.push_back(w); }
   }
 };
+
+// Real-structured storage of the dense phase's input W = [G ; B^H] (rows: test dofs of the Gram, then trial dofs; columns: test
+// dofs): W~[r,c] = kappa * conj(i^pr) * i^pc * W[r,c] with kappa = 1 on Gram rows and i on trial rows; real by construction.
+inline double rs_real(std::complex<double> w, int pr, int pc, bool trial_row) {
+  const std::complex<double> I(0, 1);
+  const std::complex<double> z = w * (pr ? -I : std::complex<double>(1, 0)) * (pc ? I : std::complex<double>(1, 0)) * (trial_row ? I : std::complex<double>(1, 0));
+  return z.real();
+}
+inline bool rs_applicable(const FormParams &P) { return P.kind == 4 && P.real_struct && P.sigma == 0.0; }
 
 inline int add_family(SigHost &S, int n0, int n1, int n2, int t0, int t1, int t2) {
   FamilyDesc f; f.n[0] = n0; f.n[1] = n1; f.n[2] = n2; f.tab[0] = t0; f.tab[1] = t1; f.tab[2] = t2;
@@ -234,8 +248,9 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
     const int fq = add_family(S, o.mid[0], o.mid[1], o.mid[2], T_Q, T_Q, T_Q);
     S.cplx = true; S.dpg = true; S.ntest = 2 * nEE; S.ni = 2 * nEi; S.nb = 6 * nQ;
     DenseDims &D = S.dims;
-    D.cplx = true; D.dpg = true; D.n = S.ntest; D.nb = S.nb; D.ni = S.ni; D.finish();
-    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nip - 1;   // load row: last (padded) interface row, independent of ni
+    const bool rs = rs_applicable(P);
+    D.cplx = !rs; D.rs = rs; D.nload = rs ? 2 : 1; D.dpg = true; D.n = S.ntest; D.nb = S.nb; D.ni = S.ni; D.finish();
+    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nip - D.nload;   // load row(s): last padded interface rows, independent of ni
     const std::complex<double> za = I * P.omega * P.eps, zc = I * P.omega * P.mu;
     const double aF = (P.test_norm == 2) ? 1.0 : P.alpha_norm + std::norm(za);
     const double aG = (P.test_norm == 2) ? 1.0 : P.alpha_norm + std::norm(zc);
@@ -255,13 +270,13 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
       for (int a = 0; a < 3; a++)      // G row family
         for (int a2 = 0; a2 < 3; a2++) {  // F column family
           if (a == a2) continue;
-          BlockBuilder b(S, tf[a], tf[a2], channel(0, 0, nEE + offE[a], offE[a2]), channel(0, 1, nEE + offE[a], offE[a2]));
+          BlockBuilder b(S, tf[a], tf[a2], channel(0, 0, nEE + offE[a], offE[a2]), rs ? no_channel() : channel(0, 1, nEE + offE[a], offE[a2]));
           CurlComp cg[2], cf[2];
           curl_comps(a, cg); curl_comps(a2, cf);
           const std::complex<double> m1 = -std::conj(za), m2 = zc;
           for (int i = 0; i < 2; i++) {
-            if (cg[i].comp == a2) b.add(cg[i].dax, -1, F_W, cg[i].sgn, m1.real(), m1.imag());
-            if (cf[i].comp == a) b.add(-1, cf[i].dax, F_W, cf[i].sgn, m2.real(), m2.imag());
+            if (cg[i].comp == a2) b.add(cg[i].dax, -1, F_W, cg[i].sgn, rs ? rs_real(m1, 1, 0, false) : m1.real(), rs ? 0.0 : m1.imag());
+            if (cf[i].comp == a) b.add(-1, cf[i].dax, F_W, cf[i].sgn, rs ? rs_real(m2, 1, 0, false) : m2.real(), rs ? 0.0 : m2.imag());
           }
           b.finish();
         }
@@ -277,27 +292,28 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
       for (int a = 0; a < 3; a++) {
         {  // B(F_i, E_jc) = -za (E_c, F_i)  ->  W = conj
           const std::complex<double> m = -std::conj(za);
-          BlockBuilder b(S, fq, tf[a], channel(0, 0, 0, offE[a], mapE[c]), channel(0, 1, 0, offE[a], mapE[c]));
-          b.add(-1, -1, F_WJI + 3 * a + c, 1.0, m.real(), m.imag());
+          BlockBuilder b(S, fq, tf[a], channel(0, 0, 0, offE[a], mapE[c]), rs ? no_channel() : channel(0, 1, 0, offE[a], mapE[c]));
+          b.add(-1, -1, F_WJI + 3 * a + c, 1.0, rs ? rs_real(m, 0, 0, true) : m.real(), rs ? 0.0 : m.imag());
           b.finish();
         }
         {  // B(F_i, H_jc) = B(G_i, E_jc) = (H_c, curl F_i)   real
           BlockBuilder b(S, fq, tf[a], channel(0, 0, 0, offE[a], mapH[c]), channel(0, 0, 0, nEE + offE[a], mapE[c]));
           CurlComp cf[2];
           curl_comps(a, cf);
-          for (int i = 0; i < 2; i++) b.add(-1, cf[i].dax, F_WJD + 3 * c + cf[i].comp, cf[i].sgn, 1.0, 1.0);
+          for (int i = 0; i < 2; i++) b.add(-1, cf[i].dax, F_WJD + 3 * c + cf[i].comp, cf[i].sgn, rs ? rs_real(1.0, 1, 0, true) : 1.0, rs ? rs_real(1.0, 0, 1, true) : 1.0);
           b.finish();
         }
         {  // B(G_i, H_jc) = zc (H_c, G_i)  ->  W = conj
           const std::complex<double> m = std::conj(zc);
-          BlockBuilder b(S, fq, tf[a], channel(0, 0, 0, nEE + offE[a], mapH[c]), channel(0, 1, 0, nEE + offE[a], mapH[c]));
-          b.add(-1, -1, F_WJI + 3 * a + c, 1.0, m.real(), m.imag());
+          BlockBuilder b(S, fq, tf[a], channel(0, 0, 0, nEE + offE[a], mapH[c]), rs ? no_channel() : channel(0, 1, 0, nEE + offE[a], mapH[c]));
+          b.add(-1, -1, F_WJI + 3 * a + c, 1.0, rs ? rs_real(m, 1, 1, true) : m.real(), rs ? 0.0 : m.imag());
           b.finish();
         }
       }
     // load: l(F_i) = (J, F_i) ; W[load][F_i] = conj
     for (int a = 0; a < 3; a++) {
-      BlockBuilder b(S, unit, tf[a], channel(0, 0, rowL, offE[a]), channel(0, 1, rowL, offE[a]));
+      // real-structured: Re and Im of the stored load row (= conj(l)) go to the two load rows of the single plane
+      BlockBuilder b(S, unit, tf[a], channel(0, 0, rowL, offE[a]), rs ? channel(0, 0, rowL + 1, offE[a]) : channel(0, 1, rowL, offE[a]));
       b.add(-1, -1, F_SRC + 2 * a, 1.0, 1.0, 0.0);
       b.add(-1, -1, F_SRC + 2 * a + 1, 1.0, 0.0, -1.0);
       b.finish();
@@ -332,8 +348,8 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
               const double Ib = pair1d.val(nqb, kind_of(SP_HCURL, dj.fam, b), dj.idx[b], kind_of(SP_HCURL, fk, b), ik[b]);
               const int k = offE[fk] + k0 + F.n[0] * (k1 + F.n[1] * k2);
               const double v = s * vk * Ia * Ib;
-              S.CW[(size_t)(2 * j + 1) * D.np + k] += v;        // row H^_j, column F_k
-              S.CW[(size_t)(2 * j) * D.np + nEE + k] += v;      // row E^_j, column G_k
+              S.CW[(size_t)(2 * j + 1) * D.np + k] += rs ? rs_real(v, 1, 0, true) : v;        // row H^_j, column F_k
+              S.CW[(size_t)(2 * j) * D.np + nEE + k] += rs ? rs_real(v, 0, 1, true) : v;      // row E^_j, column G_k
             }
       }
     }

@@ -207,8 +207,9 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
     const PFam fq = add_pfam(S, PF_L2, TQ, o.mid[1], T_Q, nqt, tpts);
     S.cplx = true; S.dpg = true; S.ntest = 2 * nEE; S.ni = 2 * nEi; S.nb = 6 * nQ;
     DenseDims &D = S.dims;
-    D.cplx = true; D.dpg = true; D.n = S.ntest; D.nb = S.nb; D.ni = S.ni; D.finish();
-    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nip - 1;   // load row: last (padded) interface row, independent of ni
+    const bool rs = rs_applicable(P);   // real-structured dense phase (forms.hpp)
+    D.cplx = !rs; D.rs = rs; D.nload = rs ? 2 : 1; D.dpg = true; D.n = S.ntest; D.nb = S.nb; D.ni = S.ni; D.finish();
+    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nip - D.nload;   // load row(s): last padded interface rows, independent of ni
     const std::complex<double> za = I * P.omega * P.eps, zc = I * P.omega * P.mu;
     const double aF = (P.test_norm == 2) ? 1.0 : P.alpha_norm + std::norm(za);
     const double aG = (P.test_norm == 2) ? 1.0 : P.alpha_norm + std::norm(zc);
@@ -221,13 +222,15 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
     if (P.test_norm == 1)
       for (int a = 0; a < 2; a++)        // G row family
         for (int a2 = 0; a2 < 2; a2++) { // F column family
-          BlockBuilder b(S, tf[a].id, tf[a2].id, channel(0, 0, nEE + tf[a].off, tf[a2].off), channel(0, 1, nEE + tf[a].off, tf[a2].off));
+          BlockBuilder b(S, tf[a].id, tf[a2].id, channel(0, 0, nEE + tf[a].off, tf[a2].off), rs ? no_channel() : channel(0, 1, nEE + tf[a].off, tf[a2].off));
           const std::complex<double> m1 = -std::conj(za), m2 = zc;
+          const double m1r = rs ? rs_real(m1, 1, 0, false) : m1.real(), m1i = rs ? 0.0 : m1.imag();
+          const double m2r = rs ? rs_real(m2, 1, 0, false) : m2.real(), m2i = rs ? 0.0 : m2.imag();
           for (int c = 0; c < 3; c++) {
             const CompRef cg = pf_curl(tf[a].kind, c), vf = pf_val(tf[a2].kind, c);
-            if (cg.tc >= 0 && vf.tc >= 0) b.addp(cg.tc, cg.zd, vf.tc, vf.zd, F_W, cg.sgn * vf.sgn, m1.real(), m1.imag());
+            if (cg.tc >= 0 && vf.tc >= 0) b.addp(cg.tc, cg.zd, vf.tc, vf.zd, F_W, cg.sgn * vf.sgn, m1r, m1i);
             const CompRef vg = pf_val(tf[a].kind, c), cf = pf_curl(tf[a2].kind, c);
-            if (vg.tc >= 0 && cf.tc >= 0) b.addp(vg.tc, vg.zd, cf.tc, cf.zd, F_W, vg.sgn * cf.sgn, m2.real(), m2.imag());
+            if (vg.tc >= 0 && cf.tc >= 0) b.addp(vg.tc, vg.zd, cf.tc, cf.zd, F_W, vg.sgn * cf.sgn, m2r, m2i);
           }
           b.finish();
         }
@@ -242,24 +245,27 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
       for (int a = 0; a < 2; a++) {
         {  // B(F_i, E_jc) = -za (E_c, F_i)
           const std::complex<double> m = -std::conj(za);
-          BlockBuilder b(S, fq.id, tf[a].id, channel(0, 0, 0, tf[a].off, mapE[c]), channel(0, 1, 0, tf[a].off, mapE[c]));
-          for (int d = 0; d < 3; d++) { const CompRef v = pf_val(tf[a].kind, d); if (v.tc >= 0) b.addp(0, 0, v.tc, v.zd, F_WJI + 3 * d + c, v.sgn, m.real(), m.imag()); }
+          BlockBuilder b(S, fq.id, tf[a].id, channel(0, 0, 0, tf[a].off, mapE[c]), rs ? no_channel() : channel(0, 1, 0, tf[a].off, mapE[c]));
+          const double mr = rs ? rs_real(m, 0, 0, true) : m.real(), mi = rs ? 0.0 : m.imag();
+          for (int d = 0; d < 3; d++) { const CompRef v = pf_val(tf[a].kind, d); if (v.tc >= 0) b.addp(0, 0, v.tc, v.zd, F_WJI + 3 * d + c, v.sgn, mr, mi); }
           b.finish();
         }
         {  // B(F_i, H_jc) = B(G_i, E_jc) = (H_c, curl F_i)
           BlockBuilder b(S, fq.id, tf[a].id, channel(0, 0, 0, tf[a].off, mapH[c]), channel(0, 0, 0, nEE + tf[a].off, mapE[c]));
-          for (int d = 0; d < 3; d++) { const CompRef v = pf_curl(tf[a].kind, d); if (v.tc >= 0) b.addp(0, 0, v.tc, v.zd, F_WJD + 3 * c + d, v.sgn, 1.0, 1.0); }
+          const double c0 = rs ? rs_real(1.0, 1, 0, true) : 1.0, c1 = rs ? rs_real(1.0, 0, 1, true) : 1.0;
+          for (int d = 0; d < 3; d++) { const CompRef v = pf_curl(tf[a].kind, d); if (v.tc >= 0) b.addp(0, 0, v.tc, v.zd, F_WJD + 3 * c + d, v.sgn, c0, c1); }
           b.finish();
         }
         {  // B(G_i, H_jc) = zc (H_c, G_i)
           const std::complex<double> m = std::conj(zc);
-          BlockBuilder b(S, fq.id, tf[a].id, channel(0, 0, 0, nEE + tf[a].off, mapH[c]), channel(0, 1, 0, nEE + tf[a].off, mapH[c]));
-          for (int d = 0; d < 3; d++) { const CompRef v = pf_val(tf[a].kind, d); if (v.tc >= 0) b.addp(0, 0, v.tc, v.zd, F_WJI + 3 * d + c, v.sgn, m.real(), m.imag()); }
+          BlockBuilder b(S, fq.id, tf[a].id, channel(0, 0, 0, nEE + tf[a].off, mapH[c]), rs ? no_channel() : channel(0, 1, 0, nEE + tf[a].off, mapH[c]));
+          const double mr = rs ? rs_real(m, 1, 1, true) : m.real(), mi = rs ? 0.0 : m.imag();
+          for (int d = 0; d < 3; d++) { const CompRef v = pf_val(tf[a].kind, d); if (v.tc >= 0) b.addp(0, 0, v.tc, v.zd, F_WJI + 3 * d + c, v.sgn, mr, mi); }
           b.finish();
         }
       }
     for (int a = 0; a < 2; a++) {   // load
-      BlockBuilder b(S, unit.id, tf[a].id, channel(0, 0, rowL, tf[a].off), channel(0, 1, rowL, tf[a].off));
+      BlockBuilder b(S, unit.id, tf[a].id, channel(0, 0, rowL, tf[a].off), rs ? channel(0, 0, rowL + 1, tf[a].off) : channel(0, 1, rowL, tf[a].off));
       for (int d = 0; d < 3; d++) {
         const CompRef v = pf_val(tf[a].kind, d);
         if (v.tc < 0) continue;
@@ -294,7 +300,7 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
           double *rowH = &S.CW[(size_t)(2 * j + 1) * D.np], *rowE = &S.CW[(size_t)(2 * j) * D.np + nEE];
           for (int k = 0; k < nEE; k++) {
             const double v = w * (nx[0] * Ft[3 * k] + nx[1] * Ft[3 * k + 1] + nx[2] * Ft[3 * k + 2]);
-            rowH[k] += v; rowE[k] += v;
+            rowH[k] += rs ? rs_real(v, 1, 0, true) : v; rowE[k] += rs ? rs_real(v, 0, 1, true) : v;
           }
         }
       }

@@ -116,7 +116,7 @@ void hp3d_gpu_params_default(hp3d_params *p) {
   p->nord_add = 1; p->maxp = 6; p->test_norm = HP3D_GRAPH_NORM; p->alpha_norm = 1.0;
   p->omega = 1.0; p->eps = 1.0; p->mu = 1.0; p->sigma = 0.0;
   p->eps_tensor[0] = p->eps_tensor[8] = p->eps_tensor[16] = 1.0;
-  p->source = HP3D_SRC_SIN; p->icomp_exact = 1; p->store_schur = 1;
+  p->source = HP3D_SRC_SIN; p->icomp_exact = 1; p->store_schur = 1; p->real_reduction = 1;
 }
 
 int hp3d_gpu_init(int device) {
@@ -173,6 +173,7 @@ int hp3d_gpu_plan(int problem_kind, const hp3d_params *prm) {
   p->fp.alpha_norm = prm->alpha_norm; p->fp.omega = prm->omega; p->fp.eps = prm->eps; p->fp.mu = prm->mu; p->fp.sigma = prm->sigma;
   p->fp.source = prm->source; p->fp.icomp = prm->icomp_exact - 1;
   p->store_schur = prm->store_schur;
+  p->fp.real_struct = prm->real_reduction != 0;
   for (size_t i = 0; i < g_plans.size(); i++)
     if (!g_plans[i]) { g_plans[i] = p; return (int)i; }
   g_plans.push_back(p);

@@ -60,6 +60,9 @@ typedef struct hp3d_params {
   int source;            /* HP3D_SRC_*                                                                 */
   int icomp_exact;       /* ICOMP_EXACT 1..3 (Maxwell manufactured solutions)                          */
   int store_schur;       /* STORE_STC: also return ASchur/BSchur (stc.F90:273-277)                     */
+  int real_reduction;    /* 1 (default): ultraweak Maxwell with real eps, mu and sigma = 0 is computed through its
+                            REAL form (A = T A~ T^H, T = diag(i^k): a quarter of the flops of the reference's
+                            ZPOTRF/ZTRTRS/ZHERK, same result); 0: always the general complex kernels            */
 } hp3d_params;
 
 void hp3d_gpu_params_default(hp3d_params *p);

@@ -92,3 +92,57 @@ def h1_seminorm_error_sq(oracle, mesh, u_loc_full, grad_exact, nq=4):
             d = gh - grad_exact(x)
             err += w * h ** 3 * float(d @ d)
     return err
+
+
+class CubeMeshHcurl:
+    """H(curl) analogue of CubeMeshH1 for the Maxwell problems: global tangential dofs of the N^3 structured mesh (all
+    orientations 0), `ncomp` components per dof interleaved as the reference stores multi-component variables
+    (kk = (k-1)*NR_COMP + ivar; ultraweak Maxwell: ncomp = 2, the E- and H-traces)."""
+
+    def __init__(self, gpulib, N, p, ncomp=1):
+        self.N, self.p, self.h, self.ncomp = N, p, 1.0 / N, ncomp
+        self.norder = uniform_order(p)
+        fam, idx, sgn = dof_map(gpulib, 1, self.norder, np.zeros(12, np.int32), np.zeros(6, np.int32))
+        assert (sgn == 1).all()
+        nbub = 3 * p * (p - 1) ** 2
+        self.nE = len(idx)
+        self.nEi = self.nE - nbub                 # interface dofs come first (edges, faces)
+        self.cells = [(i, j, k) for k in range(N) for j in range(N) for i in range(N)]
+        keys = {}
+        self.l2g = np.zeros((N ** 3, self.nEi * ncomp), dtype=np.int64)
+        for e, c in enumerate(self.cells):
+            for a in range(self.nEi):
+                key = (int(fam[a]),) + tuple(("q", c[d], idx[a, d]) if d == fam[a] else (("v", c[d] + idx[a, d]) if idx[a, d] < 2 else ("m", c[d], idx[a, d]))
+                                             for d in range(3))
+                g = keys.setdefault(key, len(keys))
+                for iv in range(ncomp):
+                    self.l2g[e, a * ncomp + iv] = g * ncomp + iv
+        self.ndof = len(keys) * ncomp
+        on_bdry = np.zeros(len(keys), bool)
+        for key, g in keys.items():
+            if any(t[0] == "v" and t[1] in (0, N) for d, t in enumerate(key[1:]) if d != key[0]):
+                on_bdry[g] = True
+        self.bdry_scalar = on_bdry
+
+    def descriptors(self):
+        nel = self.N ** 3
+        X = np.zeros((nel, (self.p + 1) ** 3, 3))
+        for e, c in enumerate(self.cells):
+            X[e, :8] = (np.array(c) + VERT) * self.h
+        return np.tile(self.norder, (nel, 1)), np.zeros((nel, 12), np.int32), np.zeros((nel, 6), np.int32), X
+
+    def solve(self, Aii, Bi, dirichlet_comps=(0,)):
+        """Assemble the condensed systems and solve with homogeneous Dirichlet data on the boundary dofs of the listed
+        components (the electric trace / field: a PEC cavity)."""
+        K = np.zeros((self.ndof, self.ndof), complex); F = np.zeros(self.ndof, complex)
+        for e in range(self.N ** 3):
+            g = self.l2g[e]
+            K[np.ix_(g, g)] += Aii[e]
+            F[g] += Bi[e]
+        fixed = np.zeros(self.ndof, bool)
+        for iv in dirichlet_comps:
+            fixed[iv::self.ncomp] = self.bdry_scalar
+        free = ~fixed
+        u = np.zeros(self.ndof, complex)
+        u[free] = np.linalg.solve(K[np.ix_(free, free)], F[free])
+        return u, K, F, free

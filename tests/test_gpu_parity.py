@@ -8,7 +8,7 @@ and by a conditioning-scaled forward bound.
 import numpy as np
 import pytest
 
-from tests.util import hexa_xnod, random_signature, uniform_order
+from tests.util import complex_W, hexa_xnod, random_signature, uniform_order
 
 pytestmark = pytest.mark.gpu
 
@@ -26,8 +26,9 @@ def _oracle_params(oracle, **kw):
     return oracle.default_params(**kw)
 
 
+@pytest.mark.parametrize("rr", [1, 0])
 @pytest.mark.parametrize("p,curved", [(1, 0.0), (2, 0.0), (2, 0.03), (3, 0.02)])
-def test_uw_maxwell_integration_vs_oracle(oracle, gpu, p, curved):
+def test_uw_maxwell_integration_vs_oracle(oracle, gpu, p, curved, rr):
     """Gram matrix and enriched stiffness of ultraweak Maxwell straight out of the integration kernels
     (MAXWELL/ULTRAWEAK_DPG/elem/elem_opt.F90:236-768) vs the oracle's BLAS3 restatement."""
     oracle.set_maxp(6)
@@ -40,11 +41,12 @@ def test_uw_maxwell_integration_vs_oracle(oracle, gpu, p, curved):
     om = 2 * np.pi
     prm = _oracle_params(oracle, omega=om)
     A, b, G, S = oracle.elem(oracle.MAXW_UW, norder, norie, norif, X, prm, want_dpg=True)
-    eng = _engine(4, omega=om)
+    eng = _engine(4, omega=om, real_reduction=rr)   # rr = 1: real-structured storage (one plane), 0: general complex layout
     W, d = eng.integrate_debug(norder, norie, norif, X)
+    assert W.shape[0] == (1 if rr else 2)
     n, nb, ni, np_, nbp = d["n"], d["nb"], d["ni"], d["np"], d["nbp"]
     nEE = n // 2
-    Wc = W[0] + 1j * W[1]
+    Wc = complex_W(W, d)
     Gi = np.tril(Wc[:n, :n]); Gi = Gi + np.tril(Gi, -1).conj().T
     perm = np.empty(n, int); perm[0::2] = np.arange(nEE); perm[1::2] = nEE + np.arange(nEE)
     Gg = Gi[np.ix_(perm, perm)]
@@ -102,6 +104,46 @@ def test_condensed_vs_oracle(oracle, gpu, kind, p, nel):
             assert relerr(AS, rAS) < 1e-15 * cond * 50 + 1e-12
             assert relerr(BS, rBS) < 1e-15 * cond * 50 + 1e-12
     eng.close()
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_general_complex_path_matches_real_reduction(oracle, gpu, p):
+    """Ultraweak Maxwell has two implementations of the dense phase: the real-structured one (default for real eps, mu and
+    sigma = 0: A = T A~ T^H with A~ real) and the general complex kernels (real_reduction = 0, the reference's ZPOTRF / ZTRTRS /
+    ZHERK sequence).  Both must match the oracle, and each other, on every output incl. the Schur factors and residuals."""
+    oracle.set_maxp(6)
+    oracle.use_blas(True)
+    rng = np.random.default_rng(4242 + p)
+    nel = 3
+    norder = np.tile(uniform_order(p), (nel, 1))
+    norie = rng.integers(0, 2, (nel, 12)).astype(np.int32); norif = rng.integers(0, 8, (nel, 6)).astype(np.int32)
+    nH = oracle.celndof(norder[0])[0]
+    X = np.stack([hexa_xnod(nH, h=0.5, jitter=0.15, curved=0.01 if p > 1 else 0.0, rng=rng) for e in range(nel)])
+    om = 2 * np.pi
+    prm = _oracle_params(oracle, omega=om)
+    outs = []
+    for rr in (1, 0):
+        eng = _engine(4, omega=om, real_reduction=rr)
+        res = eng.elem_stc_batch(norder, norie, norif, X)
+        assert (res["info"] == 0).all()
+        u = [eng.unpack(res, e) for e in range(nel)]
+        xi = np.array([rng.standard_normal(u[e][1].size) + 1j * rng.standard_normal(u[e][1].size) for e in range(nel)])
+        rng2 = np.random.default_rng(7)
+        xi = np.array([rng2.standard_normal(u[e][1].size) + 1j * rng2.standard_normal(u[e][1].size) for e in range(nel)])
+        xb = eng.elem_bwd_batch(norder, norie, norif, X, xi)["xb"]
+        eta = eng.elem_residual_batch(norder, norie, norif, X, xi, xb)["resid"]
+        outs.append((u, xb, eta))
+        eng.close()
+    for e in range(nel):
+        rA, rB, rAS, rBS = oracle.condensed(4, norder[e], norie[e], norif[e], X[e], prm)
+        for k in range(2):
+            Aii, Bi, AS, BS = outs[k][0][e]
+            assert relerr(Aii, rA) < 1e-12 and relerr(Bi, rB) < 1e-12
+        for a, b in zip(outs[0][0][e], outs[1][0][e]):
+            if a.size:
+                assert relerr(a, b) < 1e-10
+    assert relerr(outs[0][1], outs[1][1]) < 1e-10          # recomputed back-substitution
+    assert np.abs(outs[0][2] - outs[1][2]).max() < 1e-9 * np.abs(outs[1][2]).max()   # DPG residuals
 
 
 def test_mixed_signatures_one_call(oracle, gpu):

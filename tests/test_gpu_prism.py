@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from tests.test_oracle_prism import PV, prism_signature
+from tests.util import complex_W
 
 pytestmark = pytest.mark.gpu
 
@@ -27,8 +28,9 @@ def _engine(kind, **kw):
     return ElemEngine(kind, **kw)
 
 
+@pytest.mark.parametrize("rr", [1, 0])
 @pytest.mark.parametrize("p,pz,curved", [(1, 1, 0.0), (2, 2, 0.0), (2, 3, 0.02), (3, 2, 0.02)])
-def test_prism_uw_integration_vs_oracle(oracle, gpu, p, pz, curved):
+def test_prism_uw_integration_vs_oracle(oracle, gpu, p, pz, curved, rr):
     """Gram matrix, enriched stiffness, trace pairings and load of ultraweak Maxwell on a prism, straight out of the
     integration kernels, vs the oracle's BLAS3 restatement of elem_opt.F90:236-768."""
     oracle.set_maxp(8)
@@ -40,12 +42,13 @@ def test_prism_uw_integration_vs_oracle(oracle, gpu, p, pz, curved):
     om = 2 * np.pi
     prm = oracle.default_params(omega=om)
     A, b, G, S = oracle.elem(oracle.MAXW_UW, no, ne, nf, X, prm, want_dpg=True, etype=P)
-    eng = _engine(4, omega=om, maxp=8)
+    eng = _engine(4, omega=om, maxp=8, real_reduction=rr)
     W, d = eng.integrate_debug(no, ne, nf, X, etype=P)
+    assert W.shape[0] == (1 if rr else 2)
     n, nb, ni, np_, nbp = d["n"], d["nb"], d["ni"], d["np"], d["nbp"]
     nEE = n // 2
     assert G.shape[0] == n and S.shape[1] == ni + nb + 1
-    Wc = W[0] + 1j * W[1]
+    Wc = complex_W(W, d)
     Gi = np.tril(Wc[:n, :n]); Gi = Gi + np.tril(Gi, -1).conj().T
     perm = np.empty(n, int); perm[0::2] = np.arange(nEE); perm[1::2] = nEE + np.arange(nEE)
     Gg = Gi[np.ix_(perm, perm)]

@@ -70,3 +70,30 @@ def hexa_xnod(nH, h=0.25, origin=(0.0, 0.0, 0.0), jitter=0.0, seed=0, curved=0.0
     if curved:
         X[8:] = rng.uniform(-curved * h, curved * h, (nH - 8, 3))
     return X
+
+
+def complex_W(W, d):
+    """The complex dense-phase input [G ; B^H ; load] from hp3d_gpu_integrate_debug.  Two planes: the general complex layout.
+    One plane: the REAL-STRUCTURED storage of lossless ultraweak Maxwell (forms.hpp): W~[r,c] = kappa conj(i^pr) i^pc W[r,c],
+    kappa = 1 on Gram rows / i on trial rows, test phases 0 (F) / 1 (G), trial phases 0 (E-type) / 1 (H-type), the load as two
+    real rows (Re, Im) -- undone here so that callers can compare with the oracle's complex matrices.  The complex load is
+    returned in the LAST padded interface row in both cases."""
+    if W.shape[0] == 2:
+        return W[0] + 1j * W[1]
+    n, nb, ni, np_, nbp, nip = d["n"], d["nb"], d["ni"], d["np"], d["nbp"], d["nip"]
+    nEE = n // 2
+    Wt = W[0]
+    R = Wt.shape[0]
+    sig = np.ones(np_, complex); sig[nEE:n] = 1j
+    rowph = np.ones(R, complex); kap = np.ones(R, complex)
+    rowph[:np_] = sig
+    kap[np_:] = 1j
+    b = np.arange(nb); rowph[np_ + b] = np.where(b % 6 >= 3, 1j, 1.0)
+    i = np.arange(ni); rowph[np_ + nbp + i] = np.where(i % 2 == 1, 1j, 1.0)
+    # W = conj(kappa) * i^pr * conj(i^pc) * W~
+    Wc = (np.conj(kap) * rowph)[:, None] * Wt * np.conj(sig)[None, :]
+    l0 = np_ + nbp + nip - 2
+    lam = Wt[l0] + 1j * Wt[l0 + 1]
+    Wc[l0] = 0.0
+    Wc[l0 + 1] = lam * np.conj(sig)
+    return Wc
