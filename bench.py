@@ -32,7 +32,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-GEMM_DRAM_BYTES_PER_ELEMENT_LAUNCH = 1230.5e6 / 103   # ncu, p=5 ultraweak Maxwell (profiles/r01_launches_traffic_b32_summary.csv)
+GEMM_DRAM_BYTES_PER_ELEMENT_LAUNCH = 589.1e6 / 103   # ncu, p=5 ultraweak Maxwell, real-form dense phase (profiles/r01_rs_launches_traffic_b32_summary.csv)
 DMMA_PEAK_TFLOPS = 37.05   # measured on this pool's B200: raw mma.sync m16n8k16.f64 loop (profiles/r01_dmma_probe.jsonl);
                            # cuBLAS DGEMM 8192^3 reaches 35.5, ZGEMM 4096^3 36.8 (profiles/r01_fp64_peak.json)
 
@@ -189,7 +189,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--elements", type=int, default=256, help="elements per GPU per step")
-    ap.add_argument("--e2e-elements", type=int, default=512, help="elements per GPU per end-to-end step (a subdomain slice; 6.8 GB of results at p=5)")
+    ap.add_argument("--e2e-elements", type=int, default=1024, help="elements per GPU per end-to-end step (a subdomain slice; 13.3 GB of results at p=5)")
+    ap.add_argument("--complex-kernels", action="store_true", help="force the general complex dense phase (hp3d_params.real_reduction = 0), the reference's ZPOTRF/ZTRTRS/ZHERK sequence")
     ap.add_argument("--p", type=int, default=5)
     ap.add_argument("--kind", type=int, default=4)
     ap.add_argument("--cpu-sample", type=int, default=0)
@@ -210,11 +211,13 @@ def main():
     from hp3d_b200 import synth
     from hp3d_b200.api import ElemEngine, pinned_empty
     omega = 2 * np.pi if args.kind == 4 else 1.0
-    eng = ElemEngine(args.kind, device=local, omega=omega)
+    eng = ElemEngine(args.kind, device=local, omega=omega, real_reduction=0 if args.complex_kernels else 1)
     B = args.elements
     norder, noe, nof, xnod = synth.cube_mesh(B, args.p, first=rank * B, total=world * B)
     ntest, ntrial, ni, nb = synth.problem_sizes(args.kind, args.p)
-    F_dense = synth.dense_flops(args.kind, ntest, ntrial, ni, nb)
+    F_ref = synth.dense_flops(args.kind, ntest, ntrial, ni, nb)          # the reference's algorithm (complex: c = 4)
+    real_form = args.kind == 4 and not args.complex_kernels               # lossless ultraweak Maxwell: A = T A~ T^H, A~ real
+    F_dense = synth.dense_flops_real_form(ntest, ntrial, ni, nb) if real_form else F_ref
 
     def barrier():
         if dist is not None:
@@ -295,8 +298,13 @@ def main():
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / DMMA_PEAK_TFLOPS,
                      "traffic": GEMM_DRAM_BYTES_PER_ELEMENT_LAUNCH * ((B + 1) // 2) if args.kind == 4 and args.p == 5 else None,
                      "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, average over the 103 gemm_nc_kernel launches of one 32-element chunk, scaled to this run's chunk (profiles/r01_launches_traffic_b32_summary.csv): bytes per launch; the operands stream from HBM once per panel, 12 % of HBM bandwidth",
-                     "kernel": "gemm_nc_kernel<complex> (all launches of the dense phase: Cholesky panels, solves, HERK, Schur)",
-                     "flops_per_element": F_dense, "ms_dense_per_step": ms_dense / args.steps, "ms_integration_per_step": ms_integ / args.steps,
+                     "kernel": ("gemm_nc_kernel<real>" if (real_form or args.kind < 3) else "gemm_nc_kernel<complex>") + " (all launches of the dense phase: Cholesky panels, solves, HERK, Schur)",
+                     "flops_per_element": F_dense,
+                     "algorithm": ("real form of the lossless ultraweak Maxwell system (A = T A~ T^H, T = diag(i^k), A~ real: DESIGN.md 2.7): the flops counted are "
+                                   "those of the real factor/solve/rank-k sequence with two load columns; the reference's complex ZPOTRF/ZTRTRS/ZHERK sequence "
+                                   "costs reference_flops_per_element for the same result") if real_form else "the reference's factor/solve/rank-k sequence (SURVEY 8d)",
+                     "reference_flops_per_element": F_ref,
+                     "tflops_on_reference_count": F_ref * B * args.steps / (ms_dense * 1e-3) / 1e12, "ms_dense_per_step": ms_dense / args.steps, "ms_integration_per_step": ms_integ / args.steps,
                      "ms_per_step_single_stream": ms_single / args.steps,
                      "timing": "achieved = algorithmic dense flops / CUDA-event time of the dense phase in a single-stream pass of the same K steps; whole_step_frac uses the two-stream step time that `value` reports",
                      "peak_source": "own probe: raw FP64 DMMA loop on this pool's B200 (profiles/r01_dmma_probe.jsonl); MEASURED_PEAKS.json has no FP64 entry",

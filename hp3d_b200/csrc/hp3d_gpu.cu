@@ -133,6 +133,8 @@ int hp3d_gpu_init(int device) {
   CUDA_TRY(dense_configure<false>());
   CUDA_TRY(tp3_configure<4>()); CUDA_TRY(tp3_configure<6>()); CUDA_TRY(tp3_configure<8>()); CUDA_TRY(tp3_configure<10>());
   CUDA_TRY(tp2_configure<4>()); CUDA_TRY(tp2_configure<6>()); CUDA_TRY(tp2_configure<8>()); CUDA_TRY(tp2_configure<10>());
+  // (descending stream priorities per lane were tried to stagger the chunk completions: 4 % slower device-resident and 8 %
+  // slower end to end than equal priorities; the chunk plan's ramped start does the staggering instead)
   for (int i = 0; i < LaneSet::NLANE; i++)
     if (!g_lane_stream[i]) CUDA_TRY(cudaStreamCreateWithFlags(&g_lane_stream[i], cudaStreamNonBlocking));
   if (!g_copy) CUDA_TRY(cudaStreamCreateWithFlags(&g_copy, cudaStreamNonBlocking));
@@ -361,8 +363,7 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
     const std::vector<int> &el = C.el;
     const ChunkShape &sh = C.shape;
     if (xnod_ld < 3 * sh.nH_max) { rc = fail(HP3D_EINVAL, "xnod_ld=%d < 3*nrdofH=%d", xnod_ld, 3 * sh.nH_max); break; }
-    // chunk plan: chunks of up to 64 elements round-robin over the lanes, TAPERED towards the end of the group because the
-    // result copy of the last chunk is the only one no later compute hides
+    // chunk plan: chunks of up to 64 elements round-robin over the lanes, with a ramped start and a tapered end (below)
     int want = (int)el.size();
     if (g_max_chunk > 0) want = std::min(want, g_max_chunk);
     else want = std::min(64, std::max(4, (want + NL - 1) / NL));   // small groups are spread over the lanes
@@ -375,14 +376,32 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
     const int lcap = g_lanes.cap;
     std::vector<size_t> cstart;   // chunk k covers el[cstart[k] .. cstart[k+1])
     {
-      size_t c0 = 0;
       const size_t ntot = el.size();
-      while (c0 < ntot) {
-        cstart.push_back(c0);
-        size_t rem = ntot - c0, n = std::min(rem, (size_t)cap);
-        if (g_max_chunk == 0 && rem < 2 * (size_t)cap && rem > 24) n = std::min(n, std::max((size_t)16, rem / 2));   // taper: halve down to 16
-        c0 += n;
+      std::vector<size_t> sizes;
+      if (g_max_chunk > 0) {
+        for (size_t left = ntot; left;) { const size_t n = std::min(left, (size_t)cap); sizes.push_back(n); left -= n; }
+      } else {
+        // RAMPED start: the lanes share the SMs evenly, so equal first chunks would all finish at the same moment and their
+        // result copies would pile up behind the compute; first chunks of cap/NL, 2cap/NL, ... keep the lanes out of phase and
+        // D2H streams continuously under the kernels of the other lanes.
+        // GEOMETRIC taper: whatever the lanes compute last is copied after the compute has ended, so the last NL chunks are 8
+        // elements, the NL before them 16, then 32 (the result copy of an element costs half its compute time).
+        std::vector<size_t> head, tail;
+        size_t hsum = 0, tsum = 0;
+        if (ntot >= (size_t)2 * NL * cap && cap >= 4 * NL)
+          for (int k = 0; k < NL; k++) { head.push_back(std::max((size_t)8, (size_t)cap * (k + 1) / NL)); hsum += head.back(); }
+        const size_t avail = ntot - hsum;
+        for (size_t sz : {(size_t)8, (size_t)16, (size_t)32})
+          if (sz < (size_t)cap)
+            for (int i = 0; i < NL; i++)
+              if (tsum + sz <= avail / 2) { tail.push_back(sz); tsum += sz; }
+        const size_t body = avail - tsum, nbody = (body + cap - 1) / cap;
+        sizes = head;
+        for (size_t i = 0, left = body; i < nbody; i++) { const size_t n = (left + (nbody - i) - 1) / (nbody - i); sizes.push_back(n); left -= n; }
+        for (size_t i = tail.size(); i-- > 0;) sizes.push_back(tail[i]);
       }
+      size_t c0 = 0;
+      for (size_t n : sizes) { cstart.push_back(c0); c0 += n; }
       cstart.push_back(ntot);
     }
     int nchunk = 0;

@@ -66,6 +66,13 @@ def dense_flops(kind, n, m, ni, nb, nrhs=1):
     return c * f
 
 
+def dense_flops_real_form(n, m, ni, nb):
+    """Real flops of the dense phase of one lossless ultraweak-Maxwell element in its REAL form (A = T A~ T^H, forms.hpp):
+    the same factor / solve / rank-k sequence on real matrices (c = 1), with the complex load as TWO real right-hand sides."""
+    r = 2.0
+    return (n ** 3 / 3.0 + n ** 2 * (m + r) + n * (m + r) ** 2) + (nb ** 3 / 3.0 + 2.0 * nb ** 2 * (ni + r) + 2.0 * ni * nb * (ni + r))
+
+
 def problem_sizes(kind, p, dp=1):
     """(ntest, ntrial, ni, nb) for an isotropic order-p brick."""
     H, E, V, Q = (p + 1) ** 3, 3 * p * (p + 1) ** 2, 3 * p * p * (p + 1), p ** 3
