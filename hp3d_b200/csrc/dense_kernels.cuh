@@ -147,6 +147,125 @@ constexpr size_t potrf_smem_bytes() { return (size_t)4 * TILE * (TILE + 1) * siz
 template <bool CPLX> constexpr size_t gemm_smem_bytes() { return (size_t)2 * 2 * (CPLX ? 2 : 1) * TILE * LDS_K * sizeof(double); }
 
 // ---------------------------------------------------------------------------------------------------
+// potrf_inv_tile_real: the REAL 64x64 diagonal-tile step (factor L L^T, write L back with the upper part zeroed, write
+// Linv = L^-1 and LinvH = L^-T), one CTA of 256 threads per element, register-blocked: thread (tx,ty) of a 16x16 grid owns
+// the 4x4 entries (ty+16i, tx+16j) (cyclic, so the shrinking trailing matrix stays balanced).  Each of the 64 elimination
+// steps is one rank-1 update from a column (factorization) / row (inversion) broadcast through a double-buffered shared
+// vector: ONE barrier per step and no integer division -- ~15 us per launch instead of ~100 us for the generic kernel below,
+// and 35 KB of shared memory instead of 133 KB, so it co-resides with the GEMM CTAs of the other lanes.
+__global__ void __launch_bounds__(256) potrf_inv_tile_real_kernel(MatRef D, MatRef Linv, MatRef LinvH, int *info, int info_stride, int col0) {
+  constexpr int N = TILE, LD = TILE + 1;
+  __shared__ double Ls[N * LD];
+  __shared__ double vec[2][N];
+  __shared__ double rs[N];      // 1 / sqrt(pivot)
+  __shared__ int bad;
+  const int e = blockIdx.x, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  double *Dg = D.re + (long long)e * D.batch;
+  if (tid == 0) bad = 0;
+  double a[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) a[i][j] = Dg[(long long)(ty + 16 * i) * D.ld + tx + 16 * j];
+  // ---- right-looking Cholesky, columns scaled at the end: A(r,c) -= A(r,k) A(c,k) / d_k  for r >= c > k
+#pragma unroll 1
+  for (int k4 = 0; k4 < 4; k4++) {
+#pragma unroll 1
+    for (int kk = 0; kk < 16; kk++) {
+      const int k = 16 * k4 + kk, buf = k & 1;
+      if (tx == kk) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {   // a[i][k4] with a compile-time second index
+          double v = k4 == 0 ? a[i][0] : (k4 == 1 ? a[i][1] : (k4 == 2 ? a[i][2] : a[i][3]));
+          vec[buf][ty + 16 * i] = v;
+        }
+      }
+      __syncthreads();
+      double d = vec[buf][k];
+      if (!(d > 0.0)) { if (tid == 0 && bad == 0) bad = k + 1; d = 1.0; }
+      const double dinv = 1.0 / d;
+      if (tid == 0) rs[k] = 1.0 / sqrt(d);
+      double cr[4], cc[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) { cr[i] = vec[buf][ty + 16 * i]; cc[i] = vec[buf][tx + 16 * i] * dinv; }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int r = ty + 16 * i, c = tx + 16 * j;
+          if (c > k && r >= c) a[i][j] -= cr[i] * cc[j];
+        }
+    }
+  }
+  __syncthreads();
+  // ---- L = A * diag(rs) (lower), to shared memory and back to the matrix
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = ty + 16 * i, c = tx + 16 * j;
+      const double l = r >= c ? a[i][j] * rs[c] : 0.0;
+      Ls[r * LD + c] = l;
+      Dg[(long long)r * D.ld + c] = l;
+    }
+  // ---- X = L^-1: residual R = I; for k: X(k,:) = R(k,:) / L(k,k); R(r,:) -= L(r,k) X(k,:) for r > k
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) a[i][j] = (ty + 16 * i == tx + 16 * j) ? 1.0 : 0.0;
+  __syncthreads();
+#pragma unroll 1
+  for (int k4 = 0; k4 < 4; k4++) {
+#pragma unroll 1
+    for (int kk = 0; kk < 16; kk++) {
+      const int k = 16 * k4 + kk, buf = k & 1;
+      if (ty == kk) {
+        const double s = rs[k];   // 1 / L(k,k)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          double v = (k4 == 0 ? a[0][j] : (k4 == 1 ? a[1][j] : (k4 == 2 ? a[2][j] : a[3][j]))) * s;
+          vec[buf][tx + 16 * j] = v;
+          if (k4 == 0) a[0][j] = v; else if (k4 == 1) a[1][j] = v; else if (k4 == 2) a[2][j] = v; else a[3][j] = v;
+        }
+      }
+      __syncthreads();
+      double xr[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) xr[j] = vec[buf][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int r = ty + 16 * i;
+        if (r > k) {
+          const double l = Ls[r * LD + k];
+#pragma unroll
+          for (int j = 0; j < 4; j++) a[i][j] -= l * xr[j];
+        }
+      }
+    }
+  }
+  __syncthreads();   // all reads of Ls are done: reuse it for the transpose
+  double *Xg = Linv.re + (long long)e * Linv.batch, *XHg = LinvH.re + (long long)e * LinvH.batch;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = ty + 16 * i, c = tx + 16 * j;
+      const double x = r >= c ? a[i][j] : 0.0;
+      Xg[(long long)r * Linv.ld + c] = x;
+      Ls[c * LD + r] = x;
+    }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = ty + 16 * i, c = tx + 16 * j;
+      XHg[(long long)r * LinvH.ld + c] = Ls[r * LD + c];
+    }
+  if (tid == 0 && bad && info && info[(long long)e * info_stride] == 0) info[(long long)e * info_stride] = col0 + bad;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // potrf_inv_tile: factor the Hermitian positive definite 64x64 diagonal tile (lower, L L^H), write L back
 // (upper part zeroed), and write Linv = L^-1 and LinvH = L^-H (both row-major planar 64x64) for the
 // "triangular solve = GEMM with the inverted block" steps.  One CTA (256 threads) per element.

@@ -82,7 +82,8 @@ static void chol_trapezoid(double *Mbase, long long plane, long long batch_strid
       launch_gemm<CPLX>(g, nt_r - j, 1, batch, st);
     }
     MatRef Li{Linv + j * linv_step, lp, linv_batch, TILE}, LiH{LinvH + j * linv_step, lp, linv_batch, TILE};
-    potrf_inv_tile_kernel<CPLX><<<batch, 256, potrf_smem_bytes(), st>>>(Dj, Li, LiH, info, 1, j * TILE);
+    if (CPLX) potrf_inv_tile_kernel<CPLX><<<batch, 256, potrf_smem_bytes(), st>>>(Dj, Li, LiH, info, 1, j * TILE);
+    else potrf_inv_tile_real_kernel<<<batch, 256, 0, st>>>(Dj, Li, LiH, info, 1, j * TILE);
     if (nt_r - j - 1 > 0) {  // rows below the diagonal block:  L(i,j) = P(i,j) * Linv_jj^H
       GemmArgs g{};
       MatRef Pj{Mbase + (long long)(j + 1) * TILE * ld + (long long)j * TILE, plane, batch_stride, ld};
