@@ -48,6 +48,8 @@ struct DenseBuffers {
   double *LinvSH = nullptr;
   int *info = nullptr;      // [batch]
   int *ni_e = nullptr, *nb_e = nullptr;  // [batch] per-element interface / bubble dof counts
+  int *nip_e = nullptr;                  // [batch] per-element OWN padded interface extent: the element's load rows sit at interface
+                                         // index nip_e - nload (classes merged across nip keep each signature's row layout)
 };
 
 template <bool CPLX>

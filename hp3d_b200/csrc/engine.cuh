@@ -145,12 +145,16 @@ struct ChunkShape {
   void absorb(const SigHost &h) {
     if (d.np == 0 && d.nip == 0) { d = h.dims; gen_stc = h.gen_stc; }
     d.n = std::max(d.n, h.dims.n); d.nb = std::max(d.nb, h.nb); d.ni = std::max(d.ni, h.ni);
+    d.nip = std::max(d.nip, h.dims.nip);   // classes merged across nip (Cholesky path): every element keeps its own row layout (nip_e)
     nint_max = std::max(nint_max, h.nint); nH_max = std::max(nH_max, h.nH);
     src_max = std::max(src_max, (size_t)h.nint * (h.cplx ? 6 : 1));
   }
-  static std::string key(const SigHost &h) {
+  // classes may merge across nip when the condensation is the Cholesky pipeline (the load rows are located per element);
+  // the pivoted-LU kernel addresses the load column through the class extent, so its classes keep nip in the key
+  static bool nip_mergeable(const SigHost &h) { return !h.gen_stc; }
+  static std::string key(const SigHost &h) {   // base key: everything but nip
     char b[96];
-    snprintf(b, sizeof b, "%d/%d/%d/%d/%d/%d/%d", (int)h.cplx, (int)h.dims.rs, (int)h.dpg, (int)h.gen_stc, h.dims.np, h.dims.nbp, h.dims.nip);
+    snprintf(b, sizeof b, "%d/%d/%d/%d/%d/%d/%d", (int)h.cplx, (int)h.dims.rs, (int)h.dpg, (int)h.gen_stc, h.dims.np, h.dims.nbp, nip_mergeable(h) ? -1 : h.dims.nip);
     return b;
   }
 };
@@ -166,7 +170,7 @@ struct Lane {
   };
   Out out[2];   // chunk outputs (device staging), double-buffered: the D2H of one chunk overlaps the lane's next chunk
   double *h_xnod = nullptr, *h_src = nullptr;                          // pinned host staging of the chunk inputs
-  int *h_cnt = nullptr;                                                // pinned [2][batch]: ni_e | nb_e
+  int *h_cnt = nullptr;                                                // pinned [3][batch]: ni_e | nb_e | nip_e
   int *d_cel = nullptr, *h_cel = nullptr;                              // caller element index of each slot (celem mode)
   // back-substitution / residual modes: solution dofs in (xi | xb), results out (xb or one residual per element)
   double *d_xi = nullptr, *d_xb = nullptr, *d_res = nullptr, *h_xi = nullptr, *h_xb = nullptr, *h_res = nullptr;
@@ -185,7 +189,7 @@ struct LaneSet {
     for (int i = 0; i < nlanes; i++) {
       Lane &L = lane[i];
       L.ws.bind(d, batch, dm);
-      L.ws.b.ni_e = dm.take<int>(batch); L.ws.b.nb_e = dm.take<int>(batch);
+      L.ws.b.ni_e = dm.take<int>(batch); L.ws.b.nb_e = dm.take<int>(batch); L.ws.b.nip_e = dm.take<int>(batch);
       L.d_WF = dm.take<double>((size_t)NFIELD * sh.nint_max * batch);
       L.d_xnod = dm.take<double>((size_t)3 * sh.nH_max * batch);
       L.d_src = dm.take<double>(sh.src_max * batch);
@@ -203,7 +207,7 @@ struct LaneSet {
       }
       L.h_xnod = hm.take<double>((size_t)3 * sh.nH_max * batch);
       L.h_src = hm.take<double>(sh.src_max * batch);
-      L.h_cnt = hm.take<int>(2 * (size_t)batch);
+      L.h_cnt = hm.take<int>(3 * (size_t)batch);
       L.d_cel = dm.take<int>(batch); L.h_cel = hm.take<int>(batch);
       L.d_xi = dm.take<double>(NS * (size_t)d.ni * batch); L.d_xb = dm.take<double>(NS * ((size_t)d.nb + 1) * batch);
       L.d_res = dm.take<double>(batch);
@@ -343,9 +347,9 @@ static void run_dense_and_scatter(const ChunkShape &sh, Lane &L, const Lane::Out
   const DenseDims &d = sh.d;
   if (mode == MODE_RESID) {   // uncondensed DPG system, then eta^2 = v^H A v
     dense_phase<CPLX>(d, L.ws.b, nel, st, true);
-    if (RS) dpg_residual_rs_kernel<<<nel, 256, sizeof(double) * 2 * d.M(), st>>>(d, L.ws.b.Am, L.ws.b.ni_e, L.ws.b.nb_e, L.d_xi, (long long)d.ni, L.d_xb,
+    if (RS) dpg_residual_rs_kernel<<<nel, 256, sizeof(double) * 2 * d.M(), st>>>(d, L.ws.b.Am, L.ws.b.ni_e, L.ws.b.nb_e, L.ws.b.nip_e, L.d_xi, (long long)d.ni, L.d_xb,
                                                                                 (long long)d.nb + 1, L.d_res);
-    else dpg_residual_kernel<CPLX><<<nel, 256, sizeof(double) * 2 * d.M(), st>>>(d, L.ws.b.Am, L.ws.b.ni_e, L.ws.b.nb_e, L.d_xi, (long long)d.ni, L.d_xb,
+    else dpg_residual_kernel<CPLX><<<nel, 256, sizeof(double) * 2 * d.M(), st>>>(d, L.ws.b.Am, L.ws.b.ni_e, L.ws.b.nb_e, L.ws.b.nip_e, L.d_xi, (long long)d.ni, L.d_xb,
                                                                                 (long long)d.nb + 1, L.d_res);
     g_launches += 2;
     cudaMemcpyAsync(o.info, L.ws.b.info, sizeof(int) * nel, cudaMemcpyDeviceToDevice, st);
@@ -371,7 +375,7 @@ static void run_dense_and_scatter(const ChunkShape &sh, Lane &L, const Lane::Out
   dense_phase<CPLX>(d, L.ws.b, nel, st);
   g_launches += dense_phase_launches(d);
   if (ev && ev->on) cudaEventRecord(ev->e[2], st);
-  OutMaps mp{g_lanes.d_iota, g_lanes.d_iota, g_lanes.d_ones, g_lanes.d_ones, 0, 0, 0, 0, L.ws.b.ni_e, L.ws.b.nb_e};
+  OutMaps mp{g_lanes.d_iota, g_lanes.d_iota, g_lanes.d_ones, g_lanes.d_ones, 0, 0, 0, 0, L.ws.b.ni_e, L.ws.b.nb_e, L.ws.b.nip_e};
   dim3 blk(16, 16), g1((d.ni + 15) / 16, (d.ni + 15) / 16, nel);
   if (RS) scatter_condensed_rs_kernel<<<g1, blk, 0, st>>>(d, L.ws.b.Am, mp, o.Aii, o.Bi, (long long)d.ni * d.ni, (long long)d.ni);
   else scatter_condensed_kernel<CPLX><<<g1, blk, 0, st>>>(d, L.ws.b.Am, mp, o.Aii, o.Bi, (long long)d.ni * d.ni, (long long)d.ni);

@@ -15,6 +15,7 @@ struct OutMaps {
   int sgn_stride_i, sgn_stride_b;  // 0: shared by the batch ; else per-element stride
   int perm_stride_i, perm_stride_b;
   const int *ni_e, *nb_e;   // per-element dof counts (nullptr: the DenseDims values)
+  const int *nip_e;         // per-element padded interface extent (position of the load rows; nullptr: DenseDims::nip)
 };
 
 // grid = (ceil(ni/16), ceil(ni/16)+extras, batch), block (16,16).  Writes Aii (ni x ni), Bi (ni).
@@ -28,7 +29,7 @@ __global__ void scatter_condensed_kernel(DenseDims d, const double *Am, OutMaps 
   const int *pi = mp.perm_i + (long long)e * mp.perm_stride_i;
   const double *si = mp.sgn_i + (long long)e * mp.sgn_stride_i;
   constexpr int NS = CPLX ? 2 : 1;
-  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, lrow = d.nip - 1;
+  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, lrow = (mp.nip_e ? mp.nip_e[e] : d.nip) - 1;
   if (r < ni && c < ni) {
     int ir = pi[r], ic = pi[c];
     double s = si[r] * si[c];
@@ -58,7 +59,7 @@ __global__ void scatter_schur_kernel(DenseDims d, const double *Am, OutMaps mp, 
   const int *pi = mp.perm_i + (long long)e * mp.perm_stride_i, *pb = mp.perm_b + (long long)e * mp.perm_stride_b;
   const double *si = mp.sgn_i + (long long)e * mp.sgn_stride_i, *sb = mp.sgn_b + (long long)e * mp.sgn_stride_b;
   constexpr int NS = CPLX ? 2 : 1;
-  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, nb = mp.nb_e ? mp.nb_e[e] : d.nb, lrow = d.nip - 1;
+  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, nb = mp.nb_e ? mp.nb_e[e] : d.nb, lrow = (mp.nip_e ? mp.nip_e[e] : d.nip) - 1;
   if (bq < nb && iq < ni) {
     int ib = pb[bq], ii = pi[iq];
     double s = sb[bq] * si[iq];
@@ -105,7 +106,8 @@ __global__ void stc_bwd_kernel(const int *__restrict__ ni_e, const int *__restri
 // u is given in the caller's layout as xi (interface dofs) and xb (bubble dofs).  One CTA (256 threads) per element.
 template <bool CPLX>
 __global__ void __launch_bounds__(256) dpg_residual_kernel(DenseDims d, const double *Am, const int *__restrict__ ni_e, const int *__restrict__ nb_e,
-                                                           const double *xi, long long sxi, const double *xb, long long sxb, double *res) {
+                                                           const int *__restrict__ nip_e, const double *xi, long long sxi, const double *xb, long long sxb,
+                                                           double *res) {
   constexpr int NS = CPLX ? 2 : 1;
   extern __shared__ double sv[];   // v: [2][M]
   __shared__ double red[8];
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(256) dpg_residual_kernel(DenseDims d, const do
     double r = 0.0, im = 0.0;
     if (i < nb) { r = xb[((long long)e * sxb + i) * NS]; if (CPLX) im = xb[((long long)e * sxb + i) * NS + 1]; }
     else if (i >= d.nbp && i < d.nbp + ni) { const int k = i - d.nbp; r = xi[((long long)e * sxi + k) * NS]; if (CPLX) im = xi[((long long)e * sxi + k) * NS + 1]; }
-    else if (i == M - 1) r = -1.0;
+    else if (i == d.nbp + (nip_e ? nip_e[e] : d.nip) - 1) r = -1.0;   // the element's load row
     vr[i] = r; vi[i] = im;
   }
   __syncthreads();
@@ -164,7 +166,7 @@ __global__ void scatter_condensed_rs_kernel(DenseDims d, const double *Am, OutMa
   const int r = blockIdx.x * 16 + threadIdx.x, c = blockIdx.y * 16 + threadIdx.y;
   const int M = d.M();
   const double *S = Am + (long long)e * (long long)d.a_plane() + (long long)d.nbp * M + d.nbp;
-  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, lrow = d.nip - 2;
+  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, lrow = (mp.nip_e ? mp.nip_e[e] : d.nip) - 2;
   if (r < ni && c < ni) {
     const int a = r >= c ? r : c, b = r >= c ? c : r;
     double re, im;
@@ -186,7 +188,7 @@ __global__ void scatter_schur_rs_kernel(DenseDims d, const double *Am, OutMaps m
   const int bq = blockIdx.x * 16 + threadIdx.x, iq = blockIdx.y * 16 + threadIdx.y;
   const int M = d.M();
   const double *Z = Am + (long long)e * (long long)d.a_plane() + (long long)d.nbp * M;
-  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, nb = mp.nb_e ? mp.nb_e[e] : d.nb, lrow = d.nip - 2;
+  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, nb = mp.nb_e ? mp.nb_e[e] : d.nb, lrow = (mp.nip_e ? mp.nip_e[e] : d.nip) - 2;
   if (bq < nb && iq < ni) {
     double re, im;
     rs_apply(Z[(long long)iq * M + bq], rs_phase_b(bq), rs_phase_i(iq), re, im);
@@ -205,12 +207,13 @@ __global__ void scatter_schur_rs_kernel(DenseDims d, const double *Am, OutMaps m
 // equations (two load rows at M-2, M-1): with phi = i W~_B^T u~ - conj(load),  Im phi = [W~_B; l_re; l_im]^T v1, -Re phi = [..]^T v2,
 // v1 = [Re u~ ; 0 ; 1], v2 = [Im u~ ; 1 ; 0].  One CTA (256 threads) per element.
 __global__ void __launch_bounds__(256) dpg_residual_rs_kernel(DenseDims d, const double *Am, const int *__restrict__ ni_e, const int *__restrict__ nb_e,
-                                                              const double *xi, long long sxi, const double *xb, long long sxb, double *res) {
+                                                              const int *__restrict__ nip_e, const double *xi, long long sxi, const double *xb, long long sxb,
+                                                              double *res) {
   extern __shared__ double sv[];   // v1, v2: [2][M]
   __shared__ double red[8];
   const int e = blockIdx.x, M = d.M(), tid = threadIdx.x;
   const double *A = Am + (long long)e * (long long)d.a_plane();
-  const int ni = ni_e[e], nb = nb_e[e];
+  const int ni = ni_e[e], nb = nb_e[e], l0 = d.nbp + (nip_e ? nip_e[e] : d.nip) - 2;   // the element's two load rows
   double *v1 = sv, *v2 = sv + M;
   for (int i = tid; i < M; i += blockDim.x) {
     double ur = 0.0, ui = 0.0;
@@ -219,8 +222,8 @@ __global__ void __launch_bounds__(256) dpg_residual_rs_kernel(DenseDims d, const
     else if (i >= d.nbp && i < d.nbp + ni) { const int k = i - d.nbp; ur = xi[((long long)e * sxi + k) * 2]; ui = xi[((long long)e * sxi + k) * 2 + 1]; ph = rs_phase_i(k); }
     // u~ = conj(i^ph) u
     double a = ph ? ui : ur, b = ph ? -ur : ui;
-    if (i == M - 2) { a = 0.0; b = 1.0; }
-    if (i == M - 1) { a = 1.0; b = 0.0; }
+    if (i == l0) { a = 0.0; b = 1.0; }
+    if (i == l0 + 1) { a = 1.0; b = 0.0; }
     v1[i] = a; v2[i] = b;
   }
   __syncthreads();

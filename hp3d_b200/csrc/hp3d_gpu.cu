@@ -80,17 +80,38 @@ int build_classes(Plan *p, int nel, const int *etype, const int *norder, const i
     if (et != HP3D_MDLB && et != HP3D_MDLP) { err = "element " + std::to_string(e) + ": element type " + std::to_string(et) + " is not implemented (bricks and prisms are)"; return HP3D_EINVAL; }
     bysig[Plan::key(et, norder + 19 * e, norie + 12 * e, norif + 6 * e)].push_back(e);
   }
-  std::map<std::string, int> cls;
+  // signatures -> dense classes.  Signatures whose padded extents (np, nbp) agree but whose padded interface extent nip differs
+  // (hp meshes: the min rule gives every element its own trace orders) are MERGED into a class of the largest nip as long as
+  // the class stays small: a class is a chain of ~100 dependent launches per chunk, so many tiny classes leave the GPU idle,
+  // while the zero rows a merged element carries cost a few per cent of flops.
+  struct SigGroup { Signature *S; const std::vector<int> *el; };
+  std::map<std::string, std::vector<SigGroup>> base;
   for (auto &g : bysig) {
     const int e0 = g.second[0];
     Signature *S = p->get(etype ? etype[e0] : HP3D_MDLB, norder + 19 * e0, norie + 12 * e0, norif + 6 * e0, device, err);
     if (!S) { err = "element " + std::to_string(e0) + ": " + err; return HP3D_EINVAL; }
-    const std::string k = ChunkShape::key(S->h);
-    auto it = cls.find(k);
-    if (it == cls.end()) { it = cls.emplace(k, (int)out.size()).first; out.emplace_back(); }
-    ClassGroup &C = out[it->second];
-    C.shape.absorb(S->h);
-    for (int e : g.second) { C.el.push_back(e); C.sig.push_back(S); }
+    base[ChunkShape::key(S->h)].push_back(SigGroup{S, &g.second});
+  }
+  size_t MERGE_TARGET = 32;   // elements (sweep on the 576-element hp mesh: 1 -> 881, 8 -> 1128, 16 -> 1261, 32 -> 1306, 64 -> 1268 elements/s)
+  if (const char *mt = getenv("HP3D_MERGE_TARGET")) MERGE_TARGET = (size_t)atoi(mt);
+  for (auto &b : base) {
+    std::vector<SigGroup> &v = b.second;
+    std::stable_sort(v.begin(), v.end(), [](const SigGroup &a, const SigGroup &c) { return a.S->h.dims.nip < c.S->h.dims.nip; });
+    size_t i = 0;
+    while (i < v.size()) {
+      out.emplace_back();
+      ClassGroup &C = out.back();
+      size_t cnt = 0;
+      int nip_open = -1;
+      // take whole nip levels until the class holds MERGE_TARGET elements
+      while (i < v.size() && (cnt < MERGE_TARGET || v[i].S->h.dims.nip == nip_open)) {
+        nip_open = v[i].S->h.dims.nip;
+        C.shape.absorb(v[i].S->h);
+        for (int e : *v[i].el) { C.el.push_back(e); C.sig.push_back(v[i].S); }
+        cnt += v[i].el->size();
+        i++;
+      }
+    }
   }
   return HP3D_OK;
 }
@@ -436,7 +457,7 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
         memcpy(L.h_xnod + (size_t)i * nx, xnod + (size_t)e * xnod_ld, sizeof(double) * 3 * h.nH);
         if (gp.source == HP3D_SRC_TABLE)
           memcpy(L.h_src + (size_t)i * nsrc, (const double *)source_qp + (size_t)e * source_ld, sizeof(double) * h.nint * (h.cplx ? 6 : 1));
-        L.h_cnt[i] = h.ni; L.h_cnt[lcap + i] = h.nb;
+        L.h_cnt[i] = h.ni; L.h_cnt[lcap + i] = h.nb; L.h_cnt[2 * lcap + i] = h.dims.nip;
         if (mode == MODE_CELEM) L.h_cel[i] = e;
         if (!big) {
           memcpy(L.h_xi + NS * sB * i, (const char *)xi + es * sxi * e, es * h.ni);
@@ -452,6 +473,7 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
       if (gp.source == HP3D_SRC_TABLE) cudaMemcpyAsync(L.d_src, L.h_src, sizeof(double) * nsrc * n, cudaMemcpyHostToDevice, st);
       cudaMemcpyAsync(L.ws.b.ni_e, L.h_cnt, sizeof(int) * n, cudaMemcpyHostToDevice, st);
       cudaMemcpyAsync(L.ws.b.nb_e, L.h_cnt + lcap, sizeof(int) * n, cudaMemcpyHostToDevice, st);
+      cudaMemcpyAsync(L.ws.b.nip_e, L.h_cnt + 2 * lcap, sizeof(int) * n, cudaMemcpyHostToDevice, st);
       if (!big) cudaMemcpyAsync(L.d_xi, L.h_xi, es * sB * n, cudaMemcpyHostToDevice, st);
       if (mode == MODE_CELEM) cudaMemcpyAsync(L.d_cel, L.h_cel, sizeof(int) * n, cudaMemcpyHostToDevice, st);
       if (mode == MODE_RESID) cudaMemcpyAsync(L.d_xb, L.h_xb, es * (sT + 1) * n, cudaMemcpyHostToDevice, st);
@@ -784,10 +806,10 @@ int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, con
     if (g_lanes.reserve(C.shape, cap, err, lanes)) return fail(HP3D_ENOMEM, "%s", err.c_str());   // grows the arena to the largest class
     const size_t nx = 3 * (size_t)C.shape.nH_max, n = C.el.size();
     std::vector<double> hx(nx * n, 0.0);
-    std::vector<int> hc(2 * n);
+    std::vector<int> hc(3 * n);
     for (size_t i = 0; i < n; i++) {
       memcpy(hx.data() + i * nx, xnod + (size_t)C.el[i] * xnod_ld, sizeof(double) * 3 * C.sig[i]->h.nH);
-      hc[i] = C.sig[i]->h.ni; hc[n + i] = C.sig[i]->h.nb;
+      hc[i] = C.sig[i]->h.ni; hc[n + i] = C.sig[i]->h.nb; hc[2 * n + i] = C.sig[i]->h.dims.nip;
     }
     double *dx; int *dc;
     CUDA_TRY(cudaMalloc(&dx, sizeof(double) * hx.size()));
@@ -824,6 +846,7 @@ int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, con
         if (ev.on) for (int i = 0; i < 4; i++) cudaEventCreate(&ev.e[i]);
         cudaMemcpyAsync(L.ws.b.ni_e, g.dcnt + c0, sizeof(int) * n, cudaMemcpyDeviceToDevice, g_lane_stream[ln]);
         cudaMemcpyAsync(L.ws.b.nb_e, g.dcnt + g.n + c0, sizeof(int) * n, cudaMemcpyDeviceToDevice, g_lane_stream[ln]);
+        cudaMemcpyAsync(L.ws.b.nip_e, g.dcnt + 2 * g.n + c0, sizeof(int) * n, cudaMemcpyDeviceToDevice, g_lane_stream[ln]);
         chunk_segments(*g.C, (size_t)c0, n, segs);
         run_chunk(g.C->shape, L, 0, gp, segs, n, g.dx + (size_t)c0 * nx, nx, nullptr, 0, p->store_schur != 0, g_lane_stream[ln], &ev);
         if (ev.on) evs.push_back(ev);
