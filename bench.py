@@ -189,7 +189,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--elements", type=int, default=256, help="elements per GPU per step")
-    ap.add_argument("--e2e-elements", type=int, default=1024, help="elements per GPU per end-to-end step (a subdomain slice; 13.3 GB of results at p=5)")
+    ap.add_argument("--e2e-elements", type=int, default=0, help="elements per GPU per end-to-end step (a subdomain slice; default 1024 = 13.3 GB of results at p=5 on one GPU, 512 per GPU on several: the ranks share the host's pinned memory)")
     ap.add_argument("--complex-kernels", action="store_true", help="force the general complex dense phase (hp3d_params.real_reduction = 0), the reference's ZPOTRF/ZTRTRS/ZHERK sequence")
     ap.add_argument("--p", type=int, default=5)
     ap.add_argument("--kind", type=int, default=4)
@@ -252,7 +252,7 @@ def main():
     # ---- end to end through hp3d_gpu_elem_batch with pinned host buffers
     e2e = None
     if not args.no_e2e:
-        Be = args.e2e_elements
+        Be = args.e2e_elements or (1024 if world == 1 else 512)
         if Be > B:
             norder, noe, nof, xnod = synth.cube_mesh(Be, args.p, first=rank * Be, total=world * Be)
         dt = eng.dtype

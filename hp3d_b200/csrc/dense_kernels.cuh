@@ -51,6 +51,10 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// pipeline depth (a third stage for the real kernel was measured: 94.8 vs 93.7 ms per 256 elements, no gain -- the DMMA pipe is
+// already 88 % active and the rest is not load latency)
+template <bool CPLX> __host__ __device__ constexpr int gemm_stages() { return 2; }
+
 // One 64x64 output tile per CTA, 4 warps (2x2), each warp a 32x32 sub-tile = 4x4 DMMA tiles.
 // grid = (row tiles, col tiles, batch)
 template <bool CPLX>
@@ -58,8 +62,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, CPLX ? 2 : 3) gemm_nc_kernel(con
   const int ti = blockIdx.x, tj = blockIdx.y, e = blockIdx.z;
   if (g.lower_only && tj > ti + g.diag_shift) return;
   constexpr int NP = CPLX ? 2 : 1;
+  constexpr int NSTAGE = gemm_stages<CPLX>();
   extern __shared__ __align__(16) double smem[];
-  // smem: [stage 2][operand 2][plane NP][TILE][LDS_K]
+  // smem: [stage NSTAGE][operand 2][plane NP][TILE][LDS_K]
   auto sm = [&](int stage, int op, int pl) { return smem + (size_t)((stage * 2 + op) * NP + pl) * TILE * LDS_K; };
 
   const double *Ag = g.A.re + (long long)e * g.A.batch + (long long)ti * TILE * g.A.ld;
@@ -88,12 +93,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, CPLX ? 2 : 3) gemm_nc_kernel(con
     cp_async_commit();
   };
 
+  // NSTAGE-deep cp.async pipeline, one barrier per k-chunk: at the top of iteration kc the group of chunk kc has landed
+  // (NSTAGE-2 younger groups may still be in flight) and every warp has finished chunk kc-1, whose buffer the next load reuses.
   const int nk = g.K / KC;
-  if (nk > 0) load_stage(0, 0);
+#pragma unroll
+  for (int s0 = 0; s0 < NSTAGE - 1; s0++) { if (s0 < nk) load_stage(s0, s0 * KC); else cp_async_commit(); }
   for (int kc = 0; kc < nk; kc++) {
-    const int st = kc & 1;
-    if (kc + 1 < nk) { load_stage(st ^ 1, (kc + 1) * KC); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    const int st = kc % NSTAGE;
+    cp_async_wait<NSTAGE - 2>();
     __syncthreads();
+    if (kc + NSTAGE - 1 < nk) load_stage((kc + NSTAGE - 1) % NSTAGE, (kc + NSTAGE - 1) * KC); else cp_async_commit();
     const double *Ar = sm(st, 0, 0) + (32 * wm + gq) * LDS_K + tq;
     const double *Br = sm(st, 1, 0) + (32 * wn + gq) * LDS_K + tq;
     const double *Ai = CPLX ? sm(st, 0, 1) + (32 * wm + gq) * LDS_K + tq : nullptr;
@@ -119,7 +128,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, CPLX ? 2 : 3) gemm_nc_kernel(con
           }
         }
     }
-    __syncthreads();
   }
 
   // epilogue: C = [Cin] + alpha*S ; each thread owns (row = 32wm+8m+gq, cols 32wn+8n+2tq, +1)
@@ -144,7 +152,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, CPLX ? 2 : 3) gemm_nc_kernel(con
 }
 
 constexpr size_t potrf_smem_bytes() { return (size_t)4 * TILE * (TILE + 1) * sizeof(double); }
-template <bool CPLX> constexpr size_t gemm_smem_bytes() { return (size_t)2 * 2 * (CPLX ? 2 : 1) * TILE * LDS_K * sizeof(double); }
+template <bool CPLX> constexpr size_t gemm_smem_bytes() { return (size_t)gemm_stages<CPLX>() * 2 * (CPLX ? 2 : 1) * TILE * LDS_K * sizeof(double); }
 
 // ---------------------------------------------------------------------------------------------------
 // potrf_inv_tile_real: the REAL 64x64 diagonal-tile step (factor L L^T, write L back with the upper part zeroed, write
