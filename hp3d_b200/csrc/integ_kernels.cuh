@@ -309,7 +309,7 @@ __device__ __forceinline__ void tp_stage2(const Tp3Args &A, const BlockDesc &B, 
 
 // dynamic smem: tables 12*TABSZ | T1 [nBx*nqy*nqz] | U [ns][nqz][nBx*nBy]   (sized by the host for the signature)
 template <int NMAX>
-__global__ void __launch_bounds__(384, 2) tp3_kernel(Tp3Args A, int smem_u_off) {
+__global__ void __launch_bounds__(384, 3) tp3_kernel(Tp3Args A, int smem_u_off) {
   extern __shared__ __align__(16) double sm[];
   double *sTab = sm, *sT1 = sm + 12 * TABSZ, *sU = sm + smem_u_off;
   const int e = blockIdx.y;
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(384, 2) tp3_kernel(Tp3Args A, int smem_u_off) 
 // stage 2: the z contraction of the hexahedron kernel.  Triangle tables live in global memory (L1/L2-resident, read-only).
 // dynamic smem: z tables 4*TABSZ | G [nqt*nqz] | U [ns][nqz][nTB]
 template <int NMAX>
-__global__ void __launch_bounds__(384, 2) tp2_kernel(Tp3Args A, const double *__restrict__ ttab, int smem_u_off) {
+__global__ void __launch_bounds__(384, 3) tp2_kernel(Tp3Args A, const double *__restrict__ ttab, int smem_u_off) {
   extern __shared__ __align__(16) double sm[];
   double *sTabZ = sm, *sG = sm + 4 * TABSZ, *sU = sm + smem_u_off;
   const int e = blockIdx.y;

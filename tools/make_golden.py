@@ -52,3 +52,25 @@ for kind, p, pz, seed in [(1, 3, 2, 51), (2, 2, 2, 52), (3, 2, 3, 53), (4, 2, 2,
                         norder=norder, norie=norie, norif=norif, xnod=xnod, nrdofH=np.array(nHs),
                         **{f"{n}{e}": out[e][k] for e in range(2) for k, n in enumerate(("Aii", "Bi", "ASchur", "BSchur"))})
     print("prism", kind, p, pz, out[0][0].shape, out[1][0].shape)
+
+# ---- celem_systemI after the element: constraints, Dirichlet lift, compression on the golden elements above
+from hp3d_b200 import api  # noqa: E402  (host-only entry points: hp3d_gpu_celem_pack)
+from tests import celem_util as CU  # noqa: E402
+
+O.set_maxp(6)
+for kind, p, seed in [(1, 2, 61), (2, 2, 62), (3, 2, 63), (4, 1, 64)]:
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"cond_kind{kind}_p{p}.npz"))
+    rng = np.random.default_rng(seed)
+    cplx = kind >= 3
+    save = dict(kind=kind, p=p)
+    for e in range(2):
+        c = CU.random_constraints(rng, O, api, kind, g["norder"][e], O.MDLB, cplx, dof0=1 + 500 * e)
+        for k in ("nrdofl", "nrdofm_f", "idbc", "zdofd", "nextract", "lcon", "cptr", "cidx", "cval"):
+            save[f"{k}{e}"] = np.asarray(c[k])
+        for f in range(3):
+            save[f"nrcon{e}_{f}"] = c["nrcon"][f]; save[f"nac{e}_{f}"] = c["nac"][f]; save[f"constr{e}_{f}"] = c["constr"][f]
+        for isym in (1, 2, 3):
+            zb, za = CU.oracle_celem(O, c, g["Aii"][e], g["Bi"][e], isym)
+            save[f"zbload{e}"] = zb; save[f"zastif{e}_{isym}"] = za
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"celem_kind{kind}_p{p}.npz"), **save)
+    print("celem", kind, p, save["zastif0_2"].shape)
