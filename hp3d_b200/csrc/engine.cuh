@@ -190,7 +190,7 @@ struct LaneSet {
       Lane &L = lane[i];
       L.ws.bind(d, batch, dm);
       L.ws.b.ni_e = dm.take<int>(batch); L.ws.b.nb_e = dm.take<int>(batch); L.ws.b.nip_e = dm.take<int>(batch);
-      L.d_WF = dm.take<double>((size_t)NFIELD * sh.nint_max * batch);
+      L.d_WF = dm.take<double>((size_t)NFIELD * wf_stride(sh.nint_max) * batch);
       L.d_xnod = dm.take<double>((size_t)3 * sh.nH_max * batch);
       L.d_src = dm.take<double>(sh.src_max * batch);
       for (int o = 0; o < 2; o++) {
@@ -261,7 +261,7 @@ template <int NMAX> static cudaError_t tp2_configure() {
 }
 static void launch_tp3(const Signature &S, const Tp3Args &A, int nel, cudaStream_t st) {
   dim3 grid((unsigned)S.h.work.size(), nel);
-  const int off = (int)S.h.smem_u_off;
+  const int off = (int)S.h.smem_u_off, offF = (int)S.h.smem_f_off, offT1 = (int)S.h.smem_t1_off;
   if (S.h.etype == 3) {   // prism: (triangle list) x (z table) families
     switch (S.h.nmax) {
       case 4: tp2_kernel<4><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, S.d_ttab, off); break;
@@ -273,10 +273,10 @@ static void launch_tp3(const Signature &S, const Tp3Args &A, int nel, cudaStream
     return;
   }
   switch (S.h.nmax) {
-    case 4: tp3_kernel<4><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, off); break;
-    case 6: tp3_kernel<6><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, off); break;
-    case 8: tp3_kernel<8><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, off); break;
-    default: tp3_kernel<10><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, off); break;
+    case 4: tp3_kernel<4><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, offF, offT1, off); break;
+    case 6: tp3_kernel<6><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, offF, offT1, off); break;
+    case 8: tp3_kernel<8><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, offF, offT1, off); break;
+    default: tp3_kernel<10><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, offF, offT1, off); break;
   }
   g_launches++;
 }
@@ -301,7 +301,7 @@ static void run_integration(const ChunkShape &sh, Lane &L, const GeomParams &gp,
     sg.ttab = S.d_ttab ? S.d_ttab + h.geo_toff : nullptr; sg.nT = h.geo_nT;
     for (int i = 0; i < 3; i++) sg.nq[i] = h.nq[i];
     double *WF = L.d_WF + wf_off;
-    wf_off += (size_t)NFIELD * h.nint * sg_.n;
+    wf_off += (size_t)NFIELD * wf_stride(h.nint) * sg_.n;
     const double *xn = d_xnod + (long long)sg_.start * xnod_ld, *src = d_src ? d_src + (long long)sg_.start * src_ld : nullptr;
     int *info = L.ws.b.info + sg_.start;
     const long long npts = (long long)sg_.n * h.nint;

@@ -67,6 +67,7 @@ struct SigHost {
   std::vector<double> CW;      // [crow.size()][np]
   int nmax = 4, threads = 64;
   size_t smem_u_off = 0, smem_bytes = 0;
+  size_t smem_f_off = 0, smem_t1_off = 0;   // hexahedron kernel: weight-field staging and x-contracted terms
   std::string err;
 };
 
@@ -117,8 +118,8 @@ struct BlockBuilder {
     const int bi = (int)S.block.size();
     S.block.push_back(B);
     const FamilyDesc &fa = S.fam[B.famA];
-    for (int j = 0; j < fa.n[1]; j++)
-      for (int i = 0; i < fa.n[0]; i++) { WorkItem w; w.block = (short)bi; w.iA = (short)i; w.jA = (short)j; w.pad = 0; S.work.push_back(w); }
+    // one work item (CTA) per first-axis index of the A family; the kernels loop over the second axis themselves
+    for (int i = 0; i < fa.n[0]; i++) { WorkItem w; w.block = (short)bi; w.iA = (short)i; w.jA = 0; w.pad = 0; S.work.push_back(w); }
   }
 };
 
@@ -466,19 +467,24 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
     return false;
   }
   // ---- launch geometry of the tp3 kernel
+  int items = 1, nm = 1, ntmax = 1;
   size_t t1 = 0, u = 0;
-  int items = 1, nm = 1;
   for (const BlockDesc &B : S.block) {
     const FamilyDesc &fa = S.fam[B.famA], &fb = S.fam[B.famB];
-    t1 = std::max(t1, (size_t)fb.n[0] * S.nq[1] * S.nq[2]);
+    t1 = std::max(t1, (size_t)B.nt * fb.n[0] * S.nq[1] * S.nq[2]);
     u = std::max(u, (size_t)B.ns * S.nq[2] * fb.n[0] * fb.n[1]);
     items = std::max(items, fa.n[2] * fb.n[0] * fb.n[1]);
     nm = std::max(nm, std::max(fb.n[2], S.nq[2]));
+    ntmax = std::max(ntmax, B.nt);
   }
   S.nmax = nm <= 4 ? 4 : nm <= 6 ? 6 : nm <= 8 ? 8 : 10;
   S.threads = std::min(384, std::max(64, (items + 31) / 32 * 32));
-  S.smem_u_off = (size_t)12 * TABSZ + ((t1 + 1) & ~(size_t)1);
+  // dynamic smem of tp3_kernel: tables | F [ntmax][fs] | T1 | U   (all offsets even: 16-byte aligned for the TMA bulk copies)
+  S.smem_f_off = (size_t)12 * TABSZ;
+  S.smem_t1_off = S.smem_f_off + (size_t)ntmax * wf_stride(S.nint);
+  S.smem_u_off = S.smem_t1_off + ((t1 + 1) & ~(size_t)1);
   S.smem_bytes = (S.smem_u_off + u) * sizeof(double);
+  if (S.smem_bytes > 200 * 1024) { S.err = "integration kernel needs more than 200 KB of shared memory"; return false; }
   return true;
 }
 

@@ -745,11 +745,12 @@ int hp3d_gpu_quad_points(int plan, int nel, const int *etype, const int *norder,
     for (int i = 0; i < 3; i++) sg.nq[i] = h.nq[i];
     if (h.etype == HP3D_MDLP) geom_fields_prism_kernel<<<(h.nint + 127) / 128, 128, 0, g_compute>>>(sg, gp, 1, L.d_xnod, 3LL * h.nH, nullptr, 0, L.d_WF, L.ws.b.info);
     else geom_fields_kernel<<<(h.nint + 127) / 128, 128, 0, g_compute>>>(sg, gp, 1, L.d_xnod, 3LL * h.nH, nullptr, 0, L.d_WF, L.ws.b.info);
-    f.resize(3 * (size_t)h.nint);
-    CUDA_TRY(cudaMemcpyAsync(f.data(), L.d_WF + (size_t)F_X * h.nint, sizeof(double) * 3 * h.nint, cudaMemcpyDeviceToHost, g_compute));
+    const size_t fs = (size_t)wf_stride(h.nint);
+    f.resize(3 * fs);
+    CUDA_TRY(cudaMemcpyAsync(f.data(), L.d_WF + (size_t)F_X * fs, sizeof(double) * 3 * fs, cudaMemcpyDeviceToHost, g_compute));
     CUDA_TRY(cudaStreamSynchronize(g_compute));
     for (int q = 0; q < h.nint; q++)
-      for (int c = 0; c < 3; c++) xq[(size_t)e * sxq + 3 * q + c] = f[(size_t)c * h.nint + q];
+      for (int c = 0; c < 3; c++) xq[(size_t)e * sxq + 3 * q + c] = f[(size_t)c * fs + q];
   }
   return HP3D_OK;
 }

@@ -39,6 +39,10 @@ enum Field {
   F_X = 38,    // 3: physical coordinates
   NFIELD = 41
 };
+// weight fields are stored [element][field][fs] with fs = nint rounded up to even: every field starts on a 16-byte boundary,
+// so one field is one TMA bulk copy (cp.async.bulk needs 16-byte aligned addresses and sizes)
+__host__ __device__ inline int wf_stride(int nint) { return (nint + 1) & ~1; }
+
 __host__ __device__ inline int sym_idx(int a, int b) { return a == b ? a : (a + b + 2); }  // 01->3, 02->4, 12->5
 
 struct GeomParams {
@@ -91,8 +95,8 @@ __device__ __forceinline__ void emit_fields(const GeomParams &gp, int e, int q, 
   Ji[6] = (J[3] * J[7] - J[4] * J[6]) / det;
   Ji[7] = (-J[0] * J[7] + J[1] * J[6]) / det;
   Ji[8] = (J[0] * J[4] - J[1] * J[3]) / det;
-  double *F = WF + (long long)e * NFIELD * nint + q;
-  const long long fs = nint;
+  const long long fs = wf_stride(nint);
+  double *F = WF + (long long)e * NFIELD * fs + q;
   const double wd = w * det, wod = w / det;
   for (int a = 0; a < 3; a++)
     for (int b = a; b < 3; b++) {
@@ -307,51 +311,100 @@ __device__ __forceinline__ void tp_stage2(const Tp3Args &A, const BlockDesc &B, 
   }
 }
 
-// dynamic smem: tables 12*TABSZ | T1 [nBx*nqy*nqz] | U [ns][nqz][nBx*nBy]   (sized by the host for the signature)
+// ---- TMA (bulk async copy) + mbarrier helpers: global -> shared staging of the geometry weight fields
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// Hexahedron kernel: one CTA per (element, block, iA); the CTA loops over jA.
+//   * the weight fields of the block's terms (geometry Jacobians folded with the quadrature weights, geom_fields_kernel) are
+//     staged in shared memory by TMA bulk copies, one per term, completing on one mbarrier while the 1-D tables are loaded;
+//   * the x contraction depends on iA only: it is done ONCE per term (T1) and reused by all jA;
+//   * per jA: y contraction of all terms into U (registers per slot, no accumulation through shared memory), then the z
+//     contraction with the output column in registers (tp_stage2).
+// dynamic smem: tables 12*TABSZ | F [nt][fs] | T1 [nt][nBx*nqy*nqz] | U [ns][nqz][nBx*nBy]   (offsets from the host, per signature)
 template <int NMAX>
-__global__ void __launch_bounds__(384, 3) tp3_kernel(Tp3Args A, int smem_u_off) {
+__global__ void __launch_bounds__(384, 3) tp3_kernel(Tp3Args A, int off_F, int off_T1, int off_U) {
   extern __shared__ __align__(16) double sm[];
-  double *sTab = sm, *sT1 = sm + 12 * TABSZ, *sU = sm + smem_u_off;
-  const int e = blockIdx.y;
+  __shared__ __align__(8) unsigned long long mbar;
+  double *sTab = sm, *sF = sm + off_F, *sT1 = sm + off_T1, *sU = sm + off_U;
+  const int e = blockIdx.y, tid = threadIdx.x;
   const WorkItem wi = A.work[blockIdx.x];
   const BlockDesc &B = A.block[wi.block];
   const FamilyDesc fa = A.fam[B.famA], fb = A.fam[B.famB];
-  const int iA = wi.iA, jA = wi.jA;
+  const int iA = wi.iA;
   const int nqx = A.nq[0], nqy = A.nq[1], nqz = A.nq[2];
-  const int nBx = fb.n[0], nBy = fb.n[1], nBz = fb.n[2], nAz = fa.n[2];
-  const int nij = nBx * nBy;
-  for (int i = threadIdx.x; i < 12 * TABSZ; i += blockDim.x) sTab[i] = A.tab[i];
-  for (int i = threadIdx.x; i < B.ns * nqz * nij; i += blockDim.x) sU[i] = 0.0;
+  const int nBx = fb.n[0], nBy = fb.n[1], nBz = fb.n[2], nAy = fa.n[1], nAz = fa.n[2];
+  const int nij = nBx * nBy, t1sz = nBx * nqy * nqz, fs = wf_stride(A.nint);
+  const double *WFe = A.WF + (long long)e * NFIELD * fs;
+  if (tid == 0) mbar_init(&mbar, 1);
   __syncthreads();
-  const double *WFe = A.WF + (long long)e * NFIELD * A.nint;
+  if (tid == 0) {
+    mbar_expect_tx(&mbar, (unsigned)(B.nt * fs * sizeof(double)));
+    for (int t = 0; t < B.nt; t++) tma_bulk_g2s(sF + (size_t)t * fs, WFe + (long long)A.term[B.t0 + t].field * fs, (unsigned)(fs * sizeof(double)), &mbar);
+  }
+  for (int i = tid; i < 12 * TABSZ; i += blockDim.x) sTab[i] = A.tab[i];
+  __syncthreads();
+  mbar_wait(&mbar, 0);
   auto tabp = [&](int axis, int type) { return sTab + (axis * 4 + type) * TABSZ; };
-  // ---- stage 1: x and y contractions, term by term, accumulated per slot
-  for (int t = 0; t < B.nt; t++) {
+  // ---- x contraction of every term (shared by all jA)
+  for (int o = tid; o < B.nt * t1sz; o += blockDim.x) {
+    const int t = o / t1sz, r = o - t * t1sz, iB = r % nBx, qyz = r / nBx;
     const TermDesc T = A.term[B.t0 + t];
     const double *XA = tabp(0, T.dA == 0 ? T_DH : fa.tab[0]) + iA * nqx;
-    const double *XB = tabp(0, T.dB == 0 ? T_DH : fb.tab[0]);
-    const double *YA = tabp(1, T.dA == 1 ? T_DH : fa.tab[1]) + jA * nqy;
-    const double *YB = tabp(1, T.dB == 1 ? T_DH : fb.tab[1]);
-    const double *Fq = WFe + (long long)T.field * A.nint;
-    for (int o = threadIdx.x; o < nBx * nqy * nqz; o += blockDim.x) {
-      const int iB = o % nBx, qyz = o / nBx;
-      const double *f = Fq + qyz * nqx;
-      double s = 0.0;
-      for (int qx = 0; qx < nqx; qx++) s += XA[qx] * XB[iB * nqx + qx] * f[qx];
-      sT1[o] = s * T.coef;   // [qyz][iB]
+    const double *XB = tabp(0, T.dB == 0 ? T_DH : fb.tab[0]) + iB * nqx;
+    const double *f = sF + (size_t)t * fs + qyz * nqx;
+    double sacc = 0.0;
+    for (int qx = 0; qx < nqx; qx++) sacc += XA[qx] * XB[qx] * f[qx];
+    sT1[o] = sacc * T.coef;   // [t][qyz][iB]
+  }
+  __syncthreads();
+  for (int jA = 0; jA < nAy; jA++) {
+    // ---- y contraction: U[slot][qz][ij] = sum over the slot's terms
+    for (int o = tid; o < nij * nqz; o += blockDim.x) {
+      const int ij = o % nij, qz = o / nij, iB = ij % nBx, jB = ij / nBx;
+      for (int sl = 0; sl < B.ns; sl++) {
+        double acc = 0.0;
+        for (int t = 0; t < B.nt; t++) {
+          const TermDesc T = A.term[B.t0 + t];
+          if (T.slot != sl) continue;
+          const double *YA = tabp(1, T.dA == 1 ? T_DH : fa.tab[1]) + jA * nqy;
+          const double *YB = tabp(1, T.dB == 1 ? T_DH : fb.tab[1]) + jB * nqy;
+          const double *t1 = sT1 + (size_t)t * t1sz + (size_t)qz * nqy * nBx + iB;
+          double sacc = 0.0;
+          for (int qy = 0; qy < nqy; qy++) sacc += YA[qy] * YB[qy] * t1[qy * nBx];
+          acc += sacc;
+        }
+        sU[(size_t)sl * nqz * nij + o] = acc;
+      }
     }
     __syncthreads();
-    double *U = sU + T.slot * nqz * nij;
-    for (int o = threadIdx.x; o < nij * nqz; o += blockDim.x) {
-      const int ij = o % nij, qz = o / nij, iB = ij % nBx, jB = ij / nBx;
-      double s = 0.0;
-      for (int qy = 0; qy < nqy; qy++) s += YA[qy] * YB[jB * nqy + qy] * sT1[(qz * nqy + qy) * nBx + iB];
-      U[qz * nij + ij] += s;
-    }
+    // ---- z contraction and output
+    tp_stage2<NMAX>(A, B, sTab + 8 * TABSZ, sU, e, nqz, nij, nBz, nAz, iA + fa.n[0] * jA, fa.n[0] * fa.n[1]);
     __syncthreads();
   }
-  // ---- stage 2: z contraction
-  tp_stage2<NMAX>(A, B, sTab + 8 * TABSZ, sU, e, nqz, nij, nBz, nAz, iA + fa.n[0] * jA, fa.n[0] * fa.n[1]);
 }
 
 // Prism kernel: one CTA per (element, block, tA).  A family is a (triangle list) x (z table) grid:
@@ -373,12 +426,13 @@ __global__ void __launch_bounds__(384, 3) tp2_kernel(Tp3Args A, const double *__
   for (int i = threadIdx.x; i < 4 * TABSZ; i += blockDim.x) sTabZ[i] = A.tab[8 * TABSZ + i];
   for (int i = threadIdx.x; i < B.ns * nqz * nTB; i += blockDim.x) sU[i] = 0.0;
   __syncthreads();
-  const double *WFe = A.WF + (long long)e * NFIELD * A.nint;
+  const int fs = wf_stride(A.nint);
+  const double *WFe = A.WF + (long long)e * NFIELD * fs;
   for (int t = 0; t < B.nt; t++) {
     const TermDesc T = A.term[B.t0 + t];
     const double *TA = ttab + fa.tab[0] + ((long long)T.dA * nTA + tA) * nqt;
     const double *TB = ttab + fb.tab[0] + (long long)T.dB * nTB * nqt;
-    const double *Fq = WFe + (long long)T.field * A.nint;
+    const double *Fq = WFe + (long long)T.field * fs;
     for (int o = threadIdx.x; o < nqt * nqz; o += blockDim.x) sG[o] = __ldg(TA + o % nqt) * Fq[o] * T.coef;   // [qz][qt]
     __syncthreads();
     double *U = sU + T.slot * nqz * nTB;
