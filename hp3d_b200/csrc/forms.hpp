@@ -472,15 +472,16 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
   for (const BlockDesc &B : S.block) {
     const FamilyDesc &fa = S.fam[B.famA], &fb = S.fam[B.famB];
     t1 = std::max(t1, (size_t)B.nt * fb.n[0] * S.nq[1] * S.nq[2]);
-    u = std::max(u, (size_t)B.ns * S.nq[2] * fb.n[0] * fb.n[1]);
+    u = std::max(u, (size_t)B.ns * fb.n[0] * fb.n[1]);   // x NMAX rows below
     items = std::max(items, fa.n[2] * fb.n[0] * fb.n[1]);
     nm = std::max(nm, std::max(fb.n[2], S.nq[2]));
     ntmax = std::max(ntmax, B.nt);
   }
   S.nmax = nm <= 4 ? 4 : nm <= 6 ? 6 : nm <= 8 ? 8 : 10;
   S.threads = std::min(384, std::max(64, (items + 31) / 32 * 32));
-  // dynamic smem of tp3_kernel: tables | F [ntmax][fs] | T1 | U   (all offsets even: 16-byte aligned for the TMA bulk copies)
-  S.smem_f_off = (size_t)12 * TABSZ;
+  // dynamic smem of tp3_kernel: tables | Z | F [ntmax][fs] | T1 | U [ns][NMAX][nij]  (all offsets even: 16-byte aligned for the TMA bulk copies)
+  u *= S.nmax;
+  S.smem_f_off = (size_t)12 * TABSZ + (size_t)4 * S.nmax * S.nmax;   // tables | z tables re-laid out [4][NMAX][NMAX]
   S.smem_t1_off = S.smem_f_off + (size_t)ntmax * wf_stride(S.nint);
   S.smem_u_off = S.smem_t1_off + ((t1 + 1) & ~(size_t)1);
   S.smem_bytes = (S.smem_u_off + u) * sizeof(double);

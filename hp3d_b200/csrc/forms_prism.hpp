@@ -414,19 +414,21 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
     S.err = "problem kind not implemented for prisms";
     return false;
   }
-  // ---- launch geometry of the prism kernel: smem = z tables (4*TABSZ) | G [nqt*nqz] | U [ns][nqz][nTB]
+  // ---- launch geometry of the prism kernel: smem = z tables (4*TABSZ) | Z [4][NMAX][NMAX] | G [nqt*nqz] | U [ns][NMAX][nTB]
   size_t u = 0;
   int items = 1, nm = 1;
   for (const BlockDesc &B : S.block) {
     const FamilyDesc &fa = S.fam[B.famA], &fb = S.fam[B.famB];
-    u = std::max(u, (size_t)B.ns * nqz * fb.n[0]);
+    u = std::max(u, (size_t)B.ns * fb.n[0]);   // x NMAX rows below
     items = std::max(items, std::max(fa.n[2], nqz) * fb.n[0]);
     nm = std::max(nm, std::max(fb.n[2], nqz));
   }
   S.nmax = nm <= 4 ? 4 : nm <= 6 ? 6 : nm <= 8 ? 8 : 10;
   S.threads = std::min(384, std::max(64, (items + 31) / 32 * 32));
-  S.smem_u_off = (size_t)4 * TABSZ + (((size_t)nqt * nqz + 1) & ~(size_t)1);
+  u *= S.nmax;
+  S.smem_u_off = (size_t)4 * TABSZ + (size_t)4 * S.nmax * S.nmax + (((size_t)nqt * nqz + 1) & ~(size_t)1);
   S.smem_bytes = (S.smem_u_off + u) * sizeof(double);
+  if (S.smem_bytes > 200 * 1024) { S.err = "integration kernel needs more than 200 KB of shared memory"; return false; }
   return true;
 }
 

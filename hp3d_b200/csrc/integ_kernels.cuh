@@ -256,10 +256,19 @@ struct Tp3Args {
 };
 
 // z contraction shared by the hexahedron and prism kernels; thread item = (kA, (iB,jB)), registers over kB.
-// sTabZ: the four z tables [type][TABSZ]; sU: [ns][nqz][nij] partial sums; lA = lA0 + strideA*kA, lB = ij + nij*kB.
+// sZ: the four z tables re-laid out [type][NMAX][NMAX] and ZERO padded (build_ztab), sU: [ns][NMAX][nij] partial sums with
+// the rows >= nqz zeroed: every inner loop has compile-time bounds and immediate shared-memory offsets (the padding adds
+// zeros instead of being predicated off).  lA = lA0 + strideA*kA, lB = ij + nij*kB.
 template <int NMAX>
-__device__ __forceinline__ void tp_stage2(const Tp3Args &A, const BlockDesc &B, const double *sTabZ, const double *sU, int e, int nqz,
-                                          int nij, int nBz, int nAz, int lA0, int strideA) {
+__device__ __forceinline__ void build_ztab(const double *sTabZ, double *sZ, int nqz) {
+  for (int i = threadIdx.x; i < 4 * NMAX * NMAX; i += blockDim.x) {
+    const int type = i / (NMAX * NMAX), r = (i / NMAX) % NMAX, q = i % NMAX;
+    sZ[i] = (q < nqz && r * nqz + q < TABSZ) ? sTabZ[type * TABSZ + r * nqz + q] : 0.0;
+  }
+}
+template <int NMAX>
+__device__ __forceinline__ void tp_stage2(const Tp3Args &A, const BlockDesc &B, const double *sZ, const double *sU, int e, int nij, int nBz, int nAz,
+                                          int lA0, int strideA) {
   const ChannelDesc c0 = B.ch[0], c1 = B.ch[1];
   for (int it = threadIdx.x; it < nAz * nij; it += blockDim.x) {
     const int ij = it % nij, kA = it / nij;
@@ -268,22 +277,19 @@ __device__ __forceinline__ void tp_stage2(const Tp3Args &A, const BlockDesc &B, 
     for (int k = 0; k < NMAX; k++) { acc0[k] = 0.0; acc1[k] = 0.0; }
     for (int s = 0; s < B.ns; s++) {
       const SlotDesc S = A.slot[B.s0 + s];
-      const double *ZA = (sTabZ + S.zA * TABSZ) + kA * nqz;
-      const double *ZB = (sTabZ + S.zB * TABSZ);
-      const double *U = sU + s * nqz * nij + ij;
+      const double *ZA = sZ + (S.zA * NMAX + kA) * NMAX;
+      const double *ZB = sZ + S.zB * NMAX * NMAX;
+      const double *U = sU + (size_t)s * NMAX * nij + ij;
       double v[NMAX];
 #pragma unroll
-      for (int qz = 0; qz < NMAX; qz++) v[qz] = (qz < nqz) ? ZA[qz] * U[qz * nij] : 0.0;
+      for (int qz = 0; qz < NMAX; qz++) v[qz] = ZA[qz] * U[qz * nij];
 #pragma unroll
       for (int kB = 0; kB < NMAX; kB++) {
-        if (kB < nBz) {
-          double d = 0.0;
+        double d = 0.0;
 #pragma unroll
-          for (int qz = 0; qz < NMAX; qz++)
-            if (qz < nqz) d += v[qz] * ZB[kB * nqz + qz];
-          acc0[kB] += S.c[0] * d;
-          acc1[kB] += S.c[1] * d;
-        }
+        for (int qz = 0; qz < NMAX; qz++) d += v[qz] * ZB[kB * NMAX + qz];
+        acc0[kB] += S.c[0] * d;
+        acc1[kB] += S.c[1] * d;
       }
     }
     // write out
@@ -349,7 +355,7 @@ template <int NMAX>
 __global__ void __launch_bounds__(384, 3) tp3_kernel(Tp3Args A, int off_F, int off_T1, int off_U) {
   extern __shared__ __align__(16) double sm[];
   __shared__ __align__(8) unsigned long long mbar;
-  double *sTab = sm, *sF = sm + off_F, *sT1 = sm + off_T1, *sU = sm + off_U;
+  double *sTab = sm, *sZ = sm + 12 * TABSZ, *sF = sm + off_F, *sT1 = sm + off_T1, *sU = sm + off_U;   // sZ: 4*NMAX*NMAX
   const int e = blockIdx.y, tid = threadIdx.x;
   const WorkItem wi = A.work[blockIdx.x];
   const BlockDesc &B = A.block[wi.block];
@@ -366,7 +372,9 @@ __global__ void __launch_bounds__(384, 3) tp3_kernel(Tp3Args A, int off_F, int o
     for (int t = 0; t < B.nt; t++) tma_bulk_g2s(sF + (size_t)t * fs, WFe + (long long)A.term[B.t0 + t].field * fs, (unsigned)(fs * sizeof(double)), &mbar);
   }
   for (int i = tid; i < 12 * TABSZ; i += blockDim.x) sTab[i] = A.tab[i];
+  for (int i = tid; i < B.ns * NMAX * nij; i += blockDim.x) sU[i] = 0.0;   // rows >= nqz stay zero
   __syncthreads();
+  build_ztab<NMAX>(sTab + 8 * TABSZ, sZ, nqz);
   mbar_wait(&mbar, 0);
   auto tabp = [&](int axis, int type) { return sTab + (axis * 4 + type) * TABSZ; };
   // ---- x contraction of every term (shared by all jA)
@@ -397,12 +405,12 @@ __global__ void __launch_bounds__(384, 3) tp3_kernel(Tp3Args A, int off_F, int o
           for (int qy = 0; qy < nqy; qy++) sacc += YA[qy] * YB[qy] * t1[qy * nBx];
           acc += sacc;
         }
-        sU[(size_t)sl * nqz * nij + o] = acc;
+        sU[(size_t)sl * NMAX * nij + o] = acc;   // o = qz*nij + ij, qz < nqz
       }
     }
     __syncthreads();
     // ---- z contraction and output
-    tp_stage2<NMAX>(A, B, sTab + 8 * TABSZ, sU, e, nqz, nij, nBz, nAz, iA + fa.n[0] * jA, fa.n[0] * fa.n[1]);
+    tp_stage2<NMAX>(A, B, sZ, sU, e, nij, nBz, nAz, iA + fa.n[0] * jA, fa.n[0] * fa.n[1]);
     __syncthreads();
   }
 }
@@ -415,7 +423,7 @@ __global__ void __launch_bounds__(384, 3) tp3_kernel(Tp3Args A, int off_F, int o
 template <int NMAX>
 __global__ void __launch_bounds__(384, 3) tp2_kernel(Tp3Args A, const double *__restrict__ ttab, int smem_u_off) {
   extern __shared__ __align__(16) double sm[];
-  double *sTabZ = sm, *sG = sm + 4 * TABSZ, *sU = sm + smem_u_off;
+  double *sTabZ = sm, *sZ = sm + 4 * TABSZ, *sG = sZ + 4 * NMAX * NMAX, *sU = sm + smem_u_off;
   const int e = blockIdx.y;
   const WorkItem wi = A.work[blockIdx.x];
   const BlockDesc &B = A.block[wi.block];
@@ -424,7 +432,9 @@ __global__ void __launch_bounds__(384, 3) tp2_kernel(Tp3Args A, const double *__
   const int nqt = A.nq[0], nqz = A.nq[2];
   const int nTA = fa.n[0], nTB = fb.n[0], nBz = fb.n[2], nAz = fa.n[2];
   for (int i = threadIdx.x; i < 4 * TABSZ; i += blockDim.x) sTabZ[i] = A.tab[8 * TABSZ + i];
-  for (int i = threadIdx.x; i < B.ns * nqz * nTB; i += blockDim.x) sU[i] = 0.0;
+  for (int i = threadIdx.x; i < B.ns * NMAX * nTB; i += blockDim.x) sU[i] = 0.0;
+  __syncthreads();
+  build_ztab<NMAX>(sTabZ, sZ, nqz);
   __syncthreads();
   const int fs = wf_stride(A.nint);
   const double *WFe = A.WF + (long long)e * NFIELD * fs;
@@ -435,7 +445,7 @@ __global__ void __launch_bounds__(384, 3) tp2_kernel(Tp3Args A, const double *__
     const double *Fq = WFe + (long long)T.field * fs;
     for (int o = threadIdx.x; o < nqt * nqz; o += blockDim.x) sG[o] = __ldg(TA + o % nqt) * Fq[o] * T.coef;   // [qz][qt]
     __syncthreads();
-    double *U = sU + T.slot * nqz * nTB;
+    double *U = sU + T.slot * NMAX * nTB;
     for (int o = threadIdx.x; o < nTB * nqz; o += blockDim.x) {
       const int tB = o % nTB, qz = o / nTB;
       const double *tb = TB + (long long)tB * nqt, *g = sG + qz * nqt;
@@ -445,7 +455,7 @@ __global__ void __launch_bounds__(384, 3) tp2_kernel(Tp3Args A, const double *__
     }
     __syncthreads();
   }
-  tp_stage2<NMAX>(A, B, sTabZ, sU, e, nqz, nTB, nBz, nAz, tA, nTA);
+  tp_stage2<NMAX>(A, B, sZ, sU, e, nTB, nBz, nAz, tA, nTA);
 }
 
 // Element-independent rows of W (trace pairings): W[e][plane 0][crow[r]][0..ncol) = CW[r][0..ncol)
