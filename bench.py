@@ -234,7 +234,7 @@ def main():
     if rank == 0:
         sampler.start()
     barrier()
-    # K steps; each step = the B elements as two half-batches on two streams (the way hp3d_gpu_elem_batch runs chunks);
+    # K steps; each step = the B elements as two half-batches on two streams (hp3d_gpu_elem_batch rotates its chunks over four);
     # CUDA events on the launching stream bracket the K steps (the second stream is fenced inside that interval)
     r = eng.bench(norder, noe, nof, xnod, reps=args.steps, lanes=2)
     barrier()

@@ -159,7 +159,7 @@ struct ChunkShape {
   }
 };
 
-// A lane = one complete set of per-chunk buffers.  Two lanes run on two streams so that the latency-bound steps of one
+// A lane = one complete set of per-chunk buffers.  The lanes (four in hp3d_gpu_elem_batch) run on their own streams so that the latency-bound steps of one
 // chunk (64x64 tile factorizations, launch tails) overlap the GEMMs of the other, and D2H of a finished chunk overlaps compute.
 struct Lane {
   DenseWorkspace ws;

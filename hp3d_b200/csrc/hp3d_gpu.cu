@@ -58,7 +58,7 @@ int chunk_capacity(const ChunkShape &sh, int want, int nlanes = 2) {
   size_t fre = 0, tot = 0;
   cudaMemGetInfo(&fre, &tot);
   const size_t per = g_lanes.bytes_per_element(sh);
-  double budget = 0.80 * (double)(fre + g_arena.dcap);   // the shared arena is reusable; two lanes share the budget
+  double budget = 0.80 * (double)(fre + g_arena.dcap);   // the shared arena is reusable; the lanes share the budget
   long long cap = (long long)(budget / (double)(nlanes * per));
   if (cap > 1024) cap = 1024;
   if (cap > want) cap = want;
@@ -332,7 +332,7 @@ void hp3d_gpu_host_free(void *p) { if (p) cudaFreeHost(p); }
 }  // extern "C"
 
 namespace {
-// The chunked, two-lane pipeline behind hp3d_gpu_elem_batch (MODE_ELEM), hp3d_gpu_elem_bwd_batch (MODE_BWD: recompute the
+// The chunked, multi-lane pipeline behind hp3d_gpu_elem_batch (MODE_ELEM), hp3d_gpu_elem_bwd_batch (MODE_BWD: recompute the
 // element, return only xb = BSchur - ASchur xi) and hp3d_gpu_elem_residual_batch (MODE_RESID: DPG residual per element).
 int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif,
                const double *xnod, int xnod_ld, const void *source_qp, long long source_ld, void *Aii, long long sAii,

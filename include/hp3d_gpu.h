@@ -5,9 +5,10 @@
  *   subroutine elem(Mdle, Itest,Itrial)          problems/<PROB>/elem.F90:20  (fills ALOC/BLOC, src/modules/assembly.F90:36-37)
  *   subroutine stc_fwd_wrapper(Iel,Mdle)         src/modules/stc.F90:182      (condenses ALOC/BLOC, stores CLOC(Iel)%ASchur/BSchur)
  * for ALL elements of a subdomain at once (the !$OMP DO element loop of src/solver/par_mumps/par_mumps_sc.F90:347-357
- * becomes "one batched call, then copy-out inside the unchanged loop").  Everything above that boundary
- * (celem_systemI constraints/compression, LCON, MUMPS) and below it on the host (find_order, find_orient,
- * nodcor: the per-element descriptors) stays in the Fortran code.  INTEGRATION.md shows the ISO_C_BINDING stub.
+ * becomes "one batched call, then copy-out inside the unchanged loop").  Everything above that boundary (LCON, MUMPS;
+ * celem_systemI's constraint transform / compression too, unless the fused hp3d_gpu_celem_batch is used) and below it on the
+ * host (find_order, find_orient, nodcor, logic: the per-element descriptors) stays in the Fortran code.  INTEGRATION.md
+ * shows the ISO_C_BINDING stub.
  *
  * Conventions: plain C, no C++/torch types.  All matrices are column-major; complex values are interleaved
  * (re,im) doubles == Fortran complex(8) (HP3D_COMPLEX=1, src/common/hp3d/typedefs.h:2-6).  Device, not host,
@@ -187,7 +188,7 @@ int hp3d_gpu_stc_bwd_batch(int complex_mode, int nel, int ni, int nb, const void
 /* Throughput driver used by bench.py: runs the hot path `reps` times over `nel` RESIDENT elements (geometry dofs
  * already in HBM, condensed outputs left in HBM), timed with CUDA events on the launching stream.
  *   lanes      1: chunks run back to back on one stream (stage times ms_integ / ms_dense are then meaningful);
- *              2: chunks alternate between two buffer sets on two streams, as hp3d_gpu_elem_batch runs them
+ *              2..4: chunks rotate over that many buffer sets / streams, as hp3d_gpu_elem_batch runs them (it uses four)
  *   ms_total   device time of all reps;  ms_integ / ms_dense: the part spent in integration / in the dense phase
  *   launches   kernels launched inside the timed region
  * (The end-to-end number with host buffers is measured by calling hp3d_gpu_elem_batch itself.) */
