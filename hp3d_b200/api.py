@@ -302,6 +302,34 @@ class ElemEngine:
         lcon = cat("lcon", np.int32) if want_coo else None
         return dict(mptr=mptr, xptr=xptr, aptr=aptr, cptr=cptr, cidx=cidx, cval=cval, idbc=idbc, zdofd=zdofd, nextract=nextract, lcon=lcon)
 
+    def elem_error_batch(self, norder, norient_edge, norient_face, xnod, zdof, exact_qp=None, l2proj=False, etype=None):
+        """element_error (compute_error.F90:226) for the field variable of the problem (hp3d_gpu_elem_error_batch).
+        zdof (nel, nrdof_max, ncomp): the variable's dofs, interface dofs first then the middle node's; exact_qp: None (built-in
+        manufactured solution) or (nel, nint_max, nvals) exact values at `error_points`.  Returns dict(err, rnorm, info)."""
+        norder, noe, nof, xnod, nel, et = self._descr(norder, norient_edge, norient_face, xnod, etype)
+        zdof = np.ascontiguousarray(zdof, dtype=self.dtype)
+        ex = None if exact_qp is None else np.ascontiguousarray(exact_qp, dtype=self.dtype)
+        err = np.zeros(nel); rn = np.zeros(nel); info = np.zeros(nel, np.int32)
+        f = self.L.hp3d_gpu_elem_error_batch
+        ll = C.c_longlong
+        f.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, ll, C.c_void_p, ll, C.c_int] + [C.c_void_p] * 3
+        _lib.check(f(self.plan, nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(np.prod(xnod.shape[1:])),
+                     _ptr(zdof), int(np.prod(zdof.shape[1:])) if nel else 0, _ptr(ex), 0 if ex is None else int(np.prod(ex.shape[1:])), int(bool(l2proj)),
+                     _ptr(err), _ptr(rn), _ptr(info)))
+        return dict(err=err, rnorm=rn, info=info)
+
+    def error_points(self, norder, norient_edge, norient_face, xnod, etype=None):
+        """Physical coordinates of element_error's quadrature points: (xq (nel, nint_max, 3), nint (nel,))."""
+        norder, noe, nof, xnod, nel, et = self._descr(norder, norient_edge, norient_face, xnod, etype)
+        nint = np.zeros(nel, np.int32)
+        f = self.L.hp3d_gpu_error_points
+        f.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]
+        _lib.check(f(self.plan, nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(np.prod(xnod.shape[1:])), None, 0, _ptr(nint)))
+        xq = np.zeros((nel, int(nint.max()) if nel else 0, 3))
+        _lib.check(f(self.plan, nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(np.prod(xnod.shape[1:])), _ptr(xq),
+                     int(np.prod(xq.shape[1:])), _ptr(nint)))
+        return xq, nint
+
     @staticmethod
     def unpack(res, e):
         """Element e of an elem_stc_batch result as (Aii (ni,ni), Bi (ni), ASchur (nb,ni), BSchur (nb)) numpy arrays."""

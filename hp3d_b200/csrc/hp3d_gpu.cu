@@ -1,6 +1,7 @@
 // hp3d_gpu.cu -- C-ABI entry points of the B200 element engine (see include/hp3d_gpu.h).
 #include "../../include/hp3d_gpu.h"
 #include "engine.cuh"
+#include "error_eval.cuh"
 
 #include <cstdarg>
 #include <chrono>
@@ -35,6 +36,8 @@ struct CelemStore {   // grow-only device buffers for the constraint arrays of h
   }
   void release() { for (int i = 0; i < 10; i++) { cudaFree(p[i]); p[i] = nullptr; cap[i] = 0; } }
 } g_celem_store;
+
+void release_error_signatures();   // error-evaluation tables (defined with hp3d_gpu_elem_error_batch below)
 
 int fail(int code, const char *fmt, ...) {
   char buf[512];
@@ -171,6 +174,7 @@ int hp3d_gpu_finalize(void) {
   g_lanes.release();
   g_arena.release();
   g_celem_store.release();
+  release_error_signatures();
   for (int i = 0; i < LaneSet::NLANE; i++)
     if (g_lane_stream[i]) { cudaStreamDestroy(g_lane_stream[i]); g_lane_stream[i] = nullptr; }
   if (g_copy) { cudaStreamDestroy(g_copy); g_copy = nullptr; }
@@ -924,6 +928,130 @@ int hp3d_gpu_dense_debug(int cplx, int nel, int n, int nb, int ni, const void *G
                 : dense_debug_run<false>(nel, n, nb, ni, G, Bm, Aii, Bi, ASchur, BSchur, info, err);
   if (rc) return fail(rc, "%s", err.c_str());
   return HP3D_OK;
+}
+
+}  // extern "C"
+
+namespace {
+// device-resident tables of one error signature (cached in g_errsigs for the life of the library)
+struct ErrSig {
+  ErrSigHost h;
+  double *d_w = nullptr, *d_tabH = nullptr, *d_tabF = nullptr;
+  ~ErrSig() { cudaFree(d_w); cudaFree(d_tabH); if (d_tabF != d_tabH) cudaFree(d_tabF); }
+};
+std::map<std::string, std::unique_ptr<ErrSig>> g_errsigs;
+}  // namespace
+namespace {
+void release_error_signatures() { g_errsigs.clear(); }
+
+// shared implementation of hp3d_gpu_elem_error_batch / hp3d_gpu_error_points
+int error_impl(int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif, const double *xnod, int xnod_ld,
+               const void *zdof, long long szdof, const void *exact_qp, long long exact_ld, int l2proj, double *err, double *rnorm, int *info,
+               double *xq, long long sxq, int *nint_out) {
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
+  Plan *p = plan_of(plan);
+  if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
+  if (nel < 0 || (nel > 0 && (!norder || !norie || !norif || !xnod))) return fail(HP3D_EINVAL, "null argument");
+  const int kind = p->fp.kind;
+  const bool cplx = kind >= HP3D_MAXW_GAL;
+  const size_t es = sizeof(double) * (cplx ? 2 : 1);
+  // group by signature (element type, orders, orientations)
+  std::map<std::string, std::vector<int>> bysig;
+  for (int e = 0; e < nel; e++) {
+    const int et = etype ? etype[e] : HP3D_MDLB;
+    bysig[std::to_string(kind) + "/" + std::to_string(p->fp.maxp) + "/" + Plan::key(et, norder + 19 * e, norie + 12 * e, norif + 6 * e)].push_back(e);
+  }
+  GeomParams gp = p->geom();
+  for (auto &g : bysig) {
+    const std::vector<int> &el = g.second;
+    const int e0 = el[0];
+    auto it = g_errsigs.find(g.first);
+    if (it == g_errsigs.end()) {
+      std::unique_ptr<ErrSig> S(new ErrSig());
+      if (!compile_error_signature(kind, p->fp.maxp, etype ? etype[e0] : HP3D_MDLB, norder + 19 * e0, norie + 12 * e0, norif + 6 * e0, S->h))
+        return fail(HP3D_EINVAL, "element %d: %s", e0, S->h.err.c_str());
+      std::string uerr;
+      if (dev_upload(S->h.w, &S->d_w, uerr) || dev_upload(S->h.tabH, &S->d_tabH, uerr)) return fail(HP3D_ENOMEM, "%s", uerr.c_str());
+      if (S->h.space == ES_H1) S->d_tabF = S->d_tabH;
+      else if (dev_upload(S->h.tabF, &S->d_tabF, uerr)) return fail(HP3D_ENOMEM, "%s", uerr.c_str());
+      it = g_errsigs.emplace(g.first, std::move(S)).first;
+    }
+    const ErrSig &S = *it->second;
+    const ErrSigHost &h = S.h;
+    if (xnod_ld < 3 * h.nH) return fail(HP3D_EINVAL, "xnod_ld=%d < 3*nrdofH=%d", xnod_ld, 3 * h.nH);
+    const int n = (int)el.size(), nv = h.space == ES_H1 ? 4 : 6;
+    const size_t nz = (size_t)h.ncomp * h.nF, nex = (size_t)nv * h.nint;
+    if (zdof && szdof < (long long)nz) return fail(HP3D_EINVAL, "zdof stride %lld < ncomp*nrdof = %zu", szdof, nz);
+    if (exact_qp && exact_ld < (long long)nex) return fail(HP3D_EINVAL, "exact_ld %lld < nvals*nint = %zu", exact_ld, nex);
+    if (xq && sxq < 3LL * h.nint) return fail(HP3D_EINVAL, "xq stride %lld < 3*nint = %d", sxq, 3 * h.nint);
+    // gather the group's inputs (host) and run it as one launch
+    std::vector<double> hx((size_t)3 * h.nH * n), hz(zdof ? nz * n * (cplx ? 2 : 1) : 0), hex(exact_qp ? nex * n * (cplx ? 2 : 1) : 0);
+    for (int i = 0; i < n; i++) {
+      memcpy(hx.data() + (size_t)i * 3 * h.nH, xnod + (size_t)el[i] * xnod_ld, sizeof(double) * 3 * h.nH);
+      if (zdof) memcpy((char *)hz.data() + es * nz * i, (const char *)zdof + es * szdof * el[i], es * nz);
+      if (exact_qp) memcpy((char *)hex.data() + es * nex * i, (const char *)exact_qp + es * exact_ld * el[i], es * nex);
+    }
+    double *dx = nullptr, *dz = nullptr, *dex = nullptr, *dout = nullptr, *dxq = nullptr;
+    int *dinfo = nullptr;
+    std::string uerr;
+    if (dev_upload(hx, &dx, uerr) || dev_upload(hz, &dz, uerr) || dev_upload(hex, &dex, uerr)) return fail(HP3D_ENOMEM, "%s", uerr.c_str());
+    CUDA_TRY(cudaMalloc(&dout, sizeof(double) * 2 * n)); CUDA_TRY(cudaMalloc(&dinfo, sizeof(int) * n));
+    CUDA_TRY(cudaMemsetAsync(dinfo, 0, sizeof(int) * n, g_compute));
+    CUDA_TRY(cudaMemsetAsync(dout, 0, sizeof(double) * 2 * n, g_compute));
+    if (xq) CUDA_TRY(cudaMalloc(&dxq, sizeof(double) * 3 * h.nint * n));
+    ErrArgs A;
+    A.w = S.d_w; A.tabH = S.d_tabH; A.tabF = S.d_tabF; A.nint = h.nint; A.nH = h.nH; A.nF = h.nF; A.space = h.space; A.ncomp = h.ncomp;
+    A.gp = gp; A.nel = n; A.xnod = dx; A.xnod_ld = 3LL * h.nH; A.zdof = dz; A.szd = (long long)nz; A.exact = dex; A.sex = (long long)nex;
+    A.l2proj = l2proj; A.err = dout; A.rnorm = dout + n; A.info = dinfo; A.want_points = xq != nullptr; A.xq = dxq; A.sxq = 3LL * h.nint;
+    if (cplx) elem_error_kernel<true><<<n, 256, 0, g_compute>>>(A);
+    else elem_error_kernel<false><<<n, 256, 0, g_compute>>>(A);
+    g_launches++;
+    std::vector<double> hout(2 * (size_t)n), hxq(xq ? (size_t)3 * h.nint * n : 0);
+    std::vector<int> hinfo(n);
+    CUDA_TRY(cudaMemcpyAsync(hout.data(), dout, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, g_compute));
+    CUDA_TRY(cudaMemcpyAsync(hinfo.data(), dinfo, sizeof(int) * n, cudaMemcpyDeviceToHost, g_compute));
+    if (xq) CUDA_TRY(cudaMemcpyAsync(hxq.data(), dxq, sizeof(double) * hxq.size(), cudaMemcpyDeviceToHost, g_compute));
+    CUDA_TRY(cudaStreamSynchronize(g_compute));
+    CUDA_TRY(cudaGetLastError());
+    for (int i = 0; i < n; i++) {
+      if (err) err[el[i]] = hout[i];
+      if (rnorm) rnorm[el[i]] = hout[n + i];
+      if (info) info[el[i]] = hinfo[i];
+      if (nint_out) nint_out[el[i]] = h.nint;
+      if (xq) memcpy(xq + (size_t)el[i] * sxq, hxq.data() + (size_t)i * 3 * h.nint, sizeof(double) * 3 * h.nint);
+    }
+    cudaFree(dx); cudaFree(dz); cudaFree(dex); cudaFree(dout); cudaFree(dinfo); cudaFree(dxq);
+  }
+  return HP3D_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int hp3d_gpu_elem_error_batch(int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif, const double *xnod,
+                              int xnod_ld, const void *zdof, long long szdof, const void *exact_qp, long long exact_ld, int l2proj, double *err,
+                              double *rnorm, int *info) {
+  if (!zdof || !err || !rnorm) return fail(HP3D_EINVAL, "elem_error: null argument");
+  return error_impl(plan, nel, etype, norder, norie, norif, xnod, xnod_ld, zdof, szdof, exact_qp, exact_ld, l2proj, err, rnorm, info, nullptr, 0, nullptr);
+}
+
+int hp3d_gpu_error_points(int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif, const double *xnod,
+                          int xnod_ld, double *xq, long long sxq, int *nint_out) {
+  if (!xq && !nint_out) return fail(HP3D_EINVAL, "error_points: null argument");
+  if (!xq) {   // sizes only
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    Plan *p = plan_of(plan);
+    if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
+    for (int e = 0; e < nel; e++) {
+      ErrSigHost h;
+      if (!compile_error_signature(p->fp.kind, p->fp.maxp, etype ? etype[e] : HP3D_MDLB, norder + 19 * e, norie + 12 * e, norif + 6 * e, h))
+        return fail(HP3D_EINVAL, "element %d: %s", e, h.err.c_str());
+      nint_out[e] = h.nint;
+    }
+    return HP3D_OK;
+  }
+  return error_impl(plan, nel, etype, norder, norie, norif, xnod, xnod_ld, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, nullptr, xq, sxq, nint_out);
 }
 
 }  // extern "C"

@@ -171,6 +171,27 @@ int hp3d_gpu_celem_batch(int plan, int nel, const int *etype, const int *norder,
                          void *zbload, void *zastif, int *irn, int *jcn, void *ASchur, long long sAS, void *BSchur, long long sBS,
                          int *ni_out, int *nb_out, int *info);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * SURVEY 8(f) row f4, error-evaluation half: soleval + element_error (src/element/util/soleval.F90:30,
+ * src/element/util/compute_error.F90:226-579) for the FIELD variable of the plan's problem, batched over elements:
+ *   err[e] = sum_l wa_l rjac_l |u_exact - u_h|^2 ,  rnorm[e] = sum_l wa_l rjac_l |u_exact|^2
+ * over the points of set_3Dint with INTEGRATION = 2 (compute_error.F90:305-307), accumulated over components, values plus --
+ * unless l2proj (L2PROJ) -- the gradient (H1) / curl (H(curl)).  Field variable and the layout of one point's exact values:
+ *   HP3D_POIS_GAL, HP3D_POIS_PDPG  H1, 1 component        [u, du/dx, du/dy, du/dz]
+ *   HP3D_MAXW_GAL                  H(curl), 1 component   [E(3), curl E(3)]
+ *   HP3D_MAXW_UW                   L2, 6 components       [E(3), H(3)]
+ * zdof: the variable's dofs of element e at zdof + e*szdof scalars, (ncomp, nrdof) column-major = solelm's zdofH / zdofE /
+ * zdofQ rows of that variable (interface dofs first, then the middle node's: [xi ; xb] of the condensed solve).
+ * exact_qp: NULL = the built-in manufactured solution (isol = 1: exact.F90 of the problem directory, mfd_solutions.F90:80-100),
+ * else element e's exact values at exact_qp + e*exact_ld scalars, nvals per point in quadrature order (evaluate the problem's
+ * `exact` at the points hp3d_gpu_error_points returns).  info[e] = -1 for a non-positive Jacobian. */
+int hp3d_gpu_elem_error_batch(int plan, int nel, const int *etype, const int *norder, const int *norient_edge, const int *norient_face,
+                              const double *xnod, int xnod_ld, const void *zdof, long long szdof, const void *exact_qp, long long exact_ld,
+                              int l2proj, double *err, double *rnorm, int *info);
+/* physical coordinates (3, nint) of element_error's quadrature points per element (xq may be NULL to query nint_out only) */
+int hp3d_gpu_error_points(int plan, int nel, const int *etype, const int *norder, const int *norient_edge, const int *norient_face,
+                          const double *xnod, int xnod_ld, double *xq, long long sxq, int *nint_out);
+
 /* Upper bound on the number of elements processed per internal chunk by hp3d_gpu_elem_batch (0 = automatic: as many
  * as fit in device memory, but at least four chunks for large groups so that result copies overlap compute). */
 int hp3d_gpu_set_chunk(int max_elements);

@@ -10,7 +10,9 @@
  *   - integer encodings: trunk/test/decode.F90, encod_decod.F90, ij_to_packed.F90 (exact);
  *   - trunk/test/poly_pois.F90:101  (u=xyz reproduced to 1e-15 through elem + stc + solve);
  *   - trunk/test/poly_maxw.F90:101  (polynomial E reproduced to 1e-14, complex);
- *   - BLAS3 `elem_opt` == scalar-loop `elem_*` twins, exact-sequence identities.
+ *   - BLAS3 `elem_opt` == scalar-loop `elem_*` twins, exact-sequence identities;
+ *   - celem.c (constraints/compression): identity case, C^T A C algebra, u = xyz on a mesh with hanging nodes;
+ *   - soleval.c (soleval/element_error): closed-form norms of the manufactured solutions, exactly reproduced polynomials.
  * DPG element matrices, Cholesky condensation and p>=3 are "parity unpinned" by the reference's own
  * tests; the oracle adds the self-consistency pins listed above.
  *
@@ -230,6 +232,17 @@ int orc_celem_modify(const orc_physics *ph, const int nrdofl[3], const int *cons
 /* par_mumps_sc.F90:419-448 */
 void orc_coo_fill(int ndof, const int *lcon, const zdouble *ztemp, const zdouble *zload, zdouble *a_loc, int *irn, int *jcn,
                   zdouble *rhs);
+
+/* ---- solution evaluation and element error (soleval.c): soleval.F90:30, compute_error.F90:226 */
+int orc_soleval(int et, const double xi[3], const int *norder, const int *norie, const int *norif, const double *xnod, int ncH,
+                const zdouble *zdofH, int ncE, const zdouble *zdofE, int ncV, const zdouble *zdofV, int ncQ, const zdouble *zdofQ,
+                double x[3], double dxdxi[9], double *rjac, zdouble *zsolH, zdouble *zgradH, zdouble *zsolE, zdouble *zcurlE,
+                zdouble *zsolV, zdouble *zdivV, zdouble *zsolQ);
+int orc_error_nvals(int kind);
+void orc_exact_field(int kind, const orc_params *prm, const double x[3], zdouble *val);
+int orc_element_error(int et, int kind, const int *norder, const int *norie, const int *norif, const double *xnod, const zdouble *zdof,
+                      const orc_params *prm, const zdouble *exact_tab, int l2proj, double *err, double *rnorm);
+int orc_error_points(int et, const int *norder, const int *norie, const int *norif, const double *xnod, double *xq);
 
 #ifdef __cplusplus
 }

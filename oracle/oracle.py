@@ -26,7 +26,7 @@ class Params(C.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, "libhp3d_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("shape.c", "shape_prism.c", "quad_geom.c", "etype.c", "tri_rules.h", "dense.c", "elem.c", "celem.c", "hp3d_oracle.h", "dense.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("shape.c", "shape_prism.c", "quad_geom.c", "etype.c", "tri_rules.h", "dense.c", "elem.c", "celem.c", "soleval.c", "hp3d_oracle.h", "dense.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "libhp3d_oracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -361,3 +361,36 @@ def coo_fill(lcon, ztemp, zload, ndof_global):
     rhs = np.zeros(ndof_global, np.complex128)
     lib().orc_coo_fill(int(n), _i(lcon), _d(zt), _d(zl), _d(a), _i(irn), _i(jcn), _d(rhs))
     return a, irn, jcn, rhs
+
+
+# ---- solution evaluation / element error (soleval.c): soleval.F90, compute_error.F90:226 -------------------------------------
+def error_nvals(kind):
+    return int(lib().orc_error_nvals(int(kind)))
+
+
+def element_error(kind, norder, norie, norif, xnod, zdof, prm, exact_tab=None, l2proj=False, etype=MDLB):
+    """element_error for the field variable of problem `kind`; zdof (nrdof, ncomp).  Returns (err, rnorm, nint)."""
+    norder, norie, norif = _pad(norder, 19), _pad(norie, 12), _pad(norif, 6)
+    xnod = np.ascontiguousarray(xnod, dtype=np.float64)
+    z = np.ascontiguousarray(zdof, dtype=np.complex128)
+    tab = None if exact_tab is None else np.ascontiguousarray(exact_tab, dtype=np.complex128)
+    e, r = C.c_double(), C.c_double()
+    n = lib().orc_element_error(int(etype), int(kind), _i(norder), _i(norie), _i(norif), _d(xnod), _d(z), C.byref(prm),
+                                None if tab is None else _d(tab), int(bool(l2proj)), C.byref(e), C.byref(r))
+    assert n > 0, n
+    return e.value, r.value, n
+
+
+def error_points(norder, norie, norif, xnod, etype=MDLB):
+    norder, norie, norif = _pad(norder, 19), _pad(norie, 12), _pad(norif, 6)
+    xnod = np.ascontiguousarray(xnod, dtype=np.float64)
+    xq = np.zeros((2000, 3))
+    n = lib().orc_error_points(int(etype), _i(norder), _i(norie), _i(norif), _d(xnod), _d(xq))
+    return xq[:n].copy()
+
+
+def exact_field(kind, prm, x):
+    v = np.zeros(error_nvals(kind), np.complex128)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    lib().orc_exact_field(int(kind), C.byref(prm), _d(x), _d(v))
+    return v
