@@ -36,7 +36,7 @@ def build(verbose=False):
     import subprocess
     src = os.path.join(_HERE, "csrc", "hp3d_gpu.cu")
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH, src]
+           "-shared", "-Xcompiler", "-fPIC,-pthread", "-o", LIB_PATH, src]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd)

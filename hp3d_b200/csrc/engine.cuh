@@ -8,8 +8,10 @@
 #include "forms_prism.hpp"
 #include "integ_kernels.cuh"
 
+#include <atomic>
 #include <complex>
 #include <map>
+#include <thread>
 #include <memory>
 #include <string>
 #include <vector>
@@ -105,21 +107,34 @@ struct DenseWorkspace {
 // small tables the integration kernels read.  Chunk buffers belong to the "dense class" (below), not to the signature.
 struct Signature {
   SigHost h;
+  char *d_blob = nullptr;   // ONE device allocation holding all tables of the signature (hp meshes have thousands of signatures)
   double *d_tab = nullptr, *d_wq = nullptr, *d_CW = nullptr, *d_ttab = nullptr;
   int *d_hdof = nullptr, *d_maps = nullptr, *d_crow = nullptr;
   FamilyDesc *d_fam = nullptr; TermDesc *d_term = nullptr; SlotDesc *d_slot = nullptr; BlockDesc *d_block = nullptr; WorkItem *d_work = nullptr;
-  ~Signature() {
-    cudaFree(d_tab); cudaFree(d_wq); cudaFree(d_CW); cudaFree(d_ttab); cudaFree(d_hdof); cudaFree(d_maps); cudaFree(d_crow);
-    cudaFree(d_fam); cudaFree(d_term); cudaFree(d_slot); cudaFree(d_block); cudaFree(d_work);
-  }
+  ~Signature() { cudaFree(d_blob); }
   int ns() const { return h.cplx ? 2 : 1; }
   size_t src_doubles() const { return (size_t)h.nint * (h.cplx ? 6 : 1); }
   int upload(std::string &err) {
-    if (dev_upload(h.tab, &d_tab, err) || dev_upload(h.wq, &d_wq, err) || dev_upload(h.hdof, &d_hdof, err) || dev_upload(h.maps, &d_maps, err) ||
-        dev_upload(h.fam, &d_fam, err) || dev_upload(h.term, &d_term, err) || dev_upload(h.slot, &d_slot, err) ||
-        dev_upload(h.block, &d_block, err) || dev_upload(h.work, &d_work, err) || dev_upload(h.crow, &d_crow, err) || dev_upload(h.CW, &d_CW, err) ||
-        dev_upload(h.ttab, &d_ttab, err))
-      return -2;
+    std::vector<char> blob;
+    auto put = [&](const void *src, size_t bytes) -> size_t {   // 256-byte aligned sections
+      const size_t off = (blob.size() + 255) & ~(size_t)255;
+      blob.resize(off + bytes);
+      if (bytes) memcpy(blob.data() + off, src, bytes);
+      return off;
+    };
+    const size_t o_tab = put(h.tab.data(), sizeof(double) * h.tab.size()), o_wq = put(h.wq.data(), sizeof(double) * h.wq.size()),
+                 o_hdof = put(h.hdof.data(), sizeof(int) * h.hdof.size()), o_maps = put(h.maps.data(), sizeof(int) * h.maps.size()),
+                 o_fam = put(h.fam.data(), sizeof(FamilyDesc) * h.fam.size()), o_term = put(h.term.data(), sizeof(TermDesc) * h.term.size()),
+                 o_slot = put(h.slot.data(), sizeof(SlotDesc) * h.slot.size()), o_block = put(h.block.data(), sizeof(BlockDesc) * h.block.size()),
+                 o_work = put(h.work.data(), sizeof(WorkItem) * h.work.size()), o_crow = put(h.crow.data(), sizeof(int) * h.crow.size()),
+                 o_CW = put(h.CW.data(), sizeof(double) * h.CW.size()), o_ttab = put(h.ttab.data(), sizeof(double) * h.ttab.size());
+    HP3D_CK(cudaMalloc((void **)&d_blob, blob.size() + 256));
+    HP3D_CK(cudaMemcpy(d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    auto at = [&](size_t off, size_t n) -> char * { return n ? d_blob + off : nullptr; };
+    d_tab = (double *)at(o_tab, h.tab.size()); d_wq = (double *)at(o_wq, h.wq.size()); d_hdof = (int *)at(o_hdof, h.hdof.size());
+    d_maps = (int *)at(o_maps, h.maps.size()); d_fam = (FamilyDesc *)at(o_fam, h.fam.size()); d_term = (TermDesc *)at(o_term, h.term.size());
+    d_slot = (SlotDesc *)at(o_slot, h.slot.size()); d_block = (BlockDesc *)at(o_block, h.block.size()); d_work = (WorkItem *)at(o_work, h.work.size());
+    d_crow = (int *)at(o_crow, h.crow.size()); d_CW = (double *)at(o_CW, h.CW.size()); d_ttab = (double *)at(o_ttab, h.ttab.size());
     return 0;
   }
 };
@@ -457,6 +472,45 @@ struct Plan {
     k.append((const char *)norie, (pr ? 9 : 12) * sizeof(int));
     k.append((const char *)norif, (pr ? 5 : 6) * sizeof(int));
     return k;
+  }
+  // compile the not yet cached signatures of a call CONCURRENTLY on the host's cores: on an hp mesh nearly every element has
+  // its own signature (orientation combinations) and one compilation costs 1-100 ms (trace pairings by host quadrature)
+  int compile_missing(const std::vector<std::pair<std::string, int>> &missing, const int *etype, const int *norder, const int *norie,
+                      const int *norif, std::string &err) {
+    if (missing.empty()) return 0;
+    std::vector<std::unique_ptr<Signature>> built(missing.size());
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+      for (;;) {
+        const size_t i = next.fetch_add(1);
+        if (i >= missing.size()) break;
+        const int e0 = missing[i].second, et = etype ? etype[e0] : 1;
+        std::unique_ptr<Signature> s(new Signature());
+        if (et == 3) compile_signature_prism(fp, norder + 19 * e0, norie + 12 * e0, norif + 6 * e0, s->h);
+        else compile_signature(fp, norder + 19 * e0, norie + 12 * e0, norif + 6 * e0, s->h);
+        built[i] = std::move(s);
+      }
+    };
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = std::max(1u, std::min(nt ? nt : 4u, std::min((unsigned)missing.size(), 32u)));
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; t++) th.emplace_back(work);
+    work();
+    for (std::thread &t : th) t.join();
+    for (size_t i = 0; i < missing.size(); i++) {
+      if (!built[i]->h.err.empty()) { err = "element " + std::to_string(missing[i].second) + ": " + built[i]->h.err; return -1; }
+      sigs.emplace(missing[i].first, std::move(built[i]));
+    }
+    return 0;
+  }
+  // dof counts / quadrature size / padded extents of a signature without compiling it (cached signatures are reused)
+  bool sizes(int etype, const int *norder, const int *norie, const int *norif, SigHost &out, std::string &err) {
+    if (etype != 1 && etype != 3) { err = "unknown element type (HP3D_MDLB = 1 and HP3D_MDLP = 3 are implemented)"; return false; }
+    auto it = sigs.find(key(etype, norder, norie, norif));
+    if (it != sigs.end()) { const SigHost &h = it->second->h; out = SigHost(); out.ni = h.ni; out.nb = h.nb; out.nint = h.nint; out.nH = h.nH; out.ntest = h.ntest; out.dims = h.dims; return true; }
+    const bool ok = etype == 3 ? compile_signature_prism(fp, norder, norie, norif, out, true) : compile_signature(fp, norder, norie, norif, out, true);
+    if (!ok) err = out.err;
+    return ok;
   }
   // find or compile; device upload only when `device` is set
   Signature *get(int etype, const int *norder, const int *norie, const int *norif, bool device, std::string &err) {

@@ -189,7 +189,8 @@ inline void face_rule(const int norder[19], const int norif[6], int f, int integ
 }  // namespace detail
 
 // Build everything for one signature.  Returns false (with S.err) for unsupported input.
-inline bool compile_signature(const FormParams &P, const int norder[19], const int norie[12], const int norif[6], SigHost &S) {
+// sizes_only: stop once the dof counts, quadrature size and padded dense extents are known (no blocks, no trace pairings)
+inline bool compile_signature(const FormParams &P, const int norder[19], const int norie[12], const int norif[6], SigHost &S, bool sizes_only = false) {
   using namespace detail;
   S = SigHost();
   S.kind = P.kind;
@@ -251,6 +252,7 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
     DenseDims &D = S.dims;
     const bool rs = rs_applicable(P);
     D.cplx = !rs; D.rs = rs; D.nload = rs ? 2 : 1; D.dpg = true; D.n = S.ntest; D.nb = S.nb; D.ni = S.ni; D.finish();
+    if (sizes_only) return true;
     const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nip - D.nload;   // load row(s): last padded interface rows, independent of ni
     const std::complex<double> za = I * P.omega * P.eps, zc = I * P.omega * P.mu;
     const double aF = (P.test_norm == 2) ? 1.0 : P.alpha_norm + std::norm(za);
@@ -365,6 +367,7 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
     S.cplx = false; S.dpg = true; S.ntest = nHH; S.ni = iH + nVi; S.nb = bH;
     DenseDims &D = S.dims;
     D.cplx = false; D.dpg = true; D.n = nHH; D.nb = S.nb; D.ni = S.ni; D.finish();
+    if (sizes_only) return true;
     const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nip - 1;   // load row: last (padded) interface row, independent of ni
     const int mapU = add_grid_map(S, hd, -1, ng, [&](int k) { return k < iH ? rowI + k : rowB + (k - iH); });
     {  // Gram (v,q) + (grad v, grad q)
@@ -418,6 +421,7 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
     S.cplx = false; S.dpg = false; S.ntest = 0; S.ni = iH; S.nb = bH;
     DenseDims &D = S.dims;
     D.cplx = false; D.dpg = false; D.n = 0; D.nb = S.nb; D.ni = S.ni; D.finish();
+    if (sizes_only) return true;
     const int mapU = add_grid_map(S, hd, -1, ng, [&](int k) { return k < iH ? D.nbp + k : k - iH; });
     {
       BlockBuilder b(S, fu, fu, channel(1, 0, 0, 0, mapU, mapU), no_channel());
@@ -438,6 +442,7 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
     S.cplx = true; S.dpg = false; S.gen_stc = true; S.ntest = 0; S.ni = iE; S.nb = bE;
     DenseDims &D = S.dims;
     D.cplx = true; D.dpg = false; D.n = 0; D.nb = S.nb; D.ni = S.ni; D.finish();
+    if (sizes_only) return true;
     int fe[3], mapE[3];
     for (int a = 0; a < 3; a++) {
       int n[3], t[3];

@@ -139,7 +139,8 @@ inline void prism_hcurl_value(const PrismDof &d, const detail::TriVals &TV, cons
   else { const double *t = TS.at(d.t); E[0] = E[1] = 0.0; E[2] = t[0] * Z.Q[d.zi] * d.sgn; }
 }
 
-inline bool compile_signature_prism(const FormParams &P, const int norder[19], const int norie[12], const int norif[6], SigHost &S) {
+// sizes_only: stop once the dof counts, quadrature size and padded dense extents are known (no blocks, no trace pairings)
+inline bool compile_signature_prism(const FormParams &P, const int norder[19], const int norie[12], const int norif[6], SigHost &S, bool sizes_only = false) {
   using namespace detail;
   S = SigHost();
   S.kind = P.kind; S.etype = 3;
@@ -209,6 +210,7 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
     DenseDims &D = S.dims;
     const bool rs = rs_applicable(P);   // real-structured dense phase (forms.hpp)
     D.cplx = !rs; D.rs = rs; D.nload = rs ? 2 : 1; D.dpg = true; D.n = S.ntest; D.nb = S.nb; D.ni = S.ni; D.finish();
+    if (sizes_only) return true;
     const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nip - D.nload;   // load row(s): last padded interface rows, independent of ni
     const std::complex<double> za = I * P.omega * P.eps, zc = I * P.omega * P.mu;
     const double aF = (P.test_norm == 2) ? 1.0 : P.alpha_norm + std::norm(za);
@@ -312,6 +314,7 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
     S.cplx = false; S.dpg = false; S.ntest = 0; S.ni = iH; S.nb = bH;
     DenseDims &D = S.dims;
     D.cplx = false; D.dpg = false; D.n = 0; D.nb = S.nb; D.ni = S.ni; D.finish();
+    if (sizes_only) return true;
     const int mapU = add_pgrid_map(S, hd, 0, fu, [&](int k) { return k < iH ? D.nbp + k : k - iH; });
     {
       BlockBuilder b(S, fu.id, fu.id, channel(1, 0, 0, 0, mapU, mapU), no_channel());
@@ -331,6 +334,7 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
     S.cplx = true; S.dpg = false; S.gen_stc = true; S.ntest = 0; S.ni = iE; S.nb = bE;
     DenseDims &D = S.dims;
     D.cplx = true; D.dpg = false; D.n = 0; D.nb = S.nb; D.ni = S.ni; D.finish();
+    if (sizes_only) return true;
     PFam fe[2];
     fe[0] = add_pfam(S, PF_EH, TV, pmax[1] + 1, T_H, nqt, tpts);
     fe[1] = add_pfam(S, PF_EV, TS, std::max(pmax[1], 1), T_Q, nqt, tpts);
@@ -367,6 +371,7 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
     S.cplx = false; S.dpg = true; S.ntest = nHH; S.ni = iH + nVi; S.nb = bH;
     DenseDims &D = S.dims;
     D.cplx = false; D.dpg = true; D.n = nHH; D.nb = S.nb; D.ni = S.ni; D.finish();
+    if (sizes_only) return true;
     const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nip - 1;   // load row: last (padded) interface row, independent of ni
     const int mapU = add_pgrid_map(S, hd, 0, fu, [&](int k) { return k < iH ? rowI + k : rowB + (k - iH); });
     {

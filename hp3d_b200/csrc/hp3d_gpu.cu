@@ -89,12 +89,24 @@ int build_classes(Plan *p, int nel, const int *etype, const int *norder, const i
   // while the zero rows a merged element carries cost a few per cent of flops.
   struct SigGroup { Signature *S; const std::vector<int> *el; };
   std::map<std::string, std::vector<SigGroup>> base;
+  {
+    std::vector<std::pair<std::string, int>> missing;
+    for (auto &g : bysig) if (!p->sigs.count(g.first)) missing.emplace_back(g.first, g.second[0]);
+    const auto t0 = std::chrono::steady_clock::now();
+    if (p->compile_missing(missing, etype, norder, norie, norif, err)) return HP3D_EINVAL;
+    if (getenv("HP3D_TRACE") && !missing.empty())
+      fprintf(stderr, "[hp3d] compiled %zu signatures in %.1f ms\n", missing.size(),
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  }
+  const auto t_up0 = std::chrono::steady_clock::now();
   for (auto &g : bysig) {
     const int e0 = g.second[0];
     Signature *S = p->get(etype ? etype[e0] : HP3D_MDLB, norder + 19 * e0, norie + 12 * e0, norif + 6 * e0, device, err);
     if (!S) { err = "element " + std::to_string(e0) + ": " + err; return HP3D_EINVAL; }
     base[ChunkShape::key(S->h)].push_back(SigGroup{S, &g.second});
   }
+  if (getenv("HP3D_TRACE"))
+    fprintf(stderr, "[hp3d] signature lookup + upload: %.1f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_up0).count());
   size_t MERGE_TARGET = 32;   // elements (sweep on the 576-element hp mesh: 1 -> 881, 8 -> 1128, 16 -> 1261, 32 -> 1306, 64 -> 1268 elements/s)
   if (const char *mt = getenv("HP3D_MERGE_TARGET")) MERGE_TARGET = (size_t)atoi(mt);
   for (auto &b : base) {
@@ -233,12 +245,12 @@ int hp3d_gpu_sizes_t(int plan, int etype, const int *norder, int *ni, int *nb, i
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
   const int z12[12] = {0}, z6[6] = {0};
   std::string err;
-  Signature *s = p->get(etype, norder, z12, z6, false, err);
-  if (!s) return fail(HP3D_EINVAL, "%s", err.c_str());
-  if (ni) *ni = s->h.ni;
-  if (nb) *nb = s->h.nb;
-  if (nint) *nint = s->h.nint;
-  if (nrdofH) *nrdofH = s->h.nH;
+  SigHost h;
+  if (!p->sizes(etype, norder, z12, z6, h, err)) return fail(HP3D_EINVAL, "%s", err.c_str());
+  if (ni) *ni = h.ni;
+  if (nb) *nb = h.nb;
+  if (nint) *nint = h.nint;
+  if (nrdofH) *nrdofH = h.nH;
   return HP3D_OK;
 }
 
@@ -247,9 +259,8 @@ int hp3d_gpu_sig_dims(int plan, int etype, const int *norder, const int *norie, 
   Plan *p = plan_of(plan);
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
   std::string err;
-  Signature *s = p->get(etype, norder, norie, norif, false, err);
-  if (!s) return fail(HP3D_EINVAL, "%s", err.c_str());
-  const SigHost &h = s->h;
+  SigHost h;
+  if (!p->sizes(etype, norder, norie, norif, h, err)) return fail(HP3D_EINVAL, "%s", err.c_str());
   dims[0] = h.ntest; dims[1] = h.ni; dims[2] = h.nb; dims[3] = h.nint; dims[4] = h.nH; dims[5] = h.dims.np; dims[6] = h.dims.nbp; dims[7] = h.dims.nip;
   return HP3D_OK;
 }
