@@ -27,7 +27,7 @@ EXPORTS = [
     "hp3d_gpu_set_chunk", "hp3d_gpu_dof_map", "hp3d_gpu_tables_1d", "hp3d_gpu_integrate_debug",
     "hp3d_gpu_sizes_t", "hp3d_gpu_bench_t", "hp3d_gpu_integrate_debug_t", "hp3d_gpu_prism_shape", "hp3d_gpu_sig_dims", "hp3d_gpu_elem_bwd_batch", "hp3d_gpu_elem_residual_batch",
     "hp3d_gpu_physics_default", "hp3d_gpu_celem_pack", "hp3d_gpu_celem_batch",
-    "hp3d_gpu_elem_error_batch", "hp3d_gpu_error_points",
+    "hp3d_gpu_elem_error_batch", "hp3d_gpu_error_points", "hp3d_gpu_chunk_plan_debug",
 ]
 
 

@@ -68,6 +68,35 @@ int chunk_capacity(const ChunkShape &sh, int want, int nlanes = 2) {
   return (int)cap;
 }
 
+// Chunk sizes for `ntot` elements of one dense class, at most `cap` per chunk, rotated over NL lanes (max_chunk > 0: plain
+// chunks of that size, used by tests and sweeps).
+std::vector<size_t> chunk_plan(size_t ntot, int cap, int NL, int max_chunk) {
+      std::vector<size_t> sizes;
+      if (max_chunk > 0) {
+        for (size_t left = ntot; left;) { const size_t n = std::min(left, (size_t)cap); sizes.push_back(n); left -= n; }
+      } else {
+        // RAMPED start: the lanes share the SMs evenly, so equal first chunks would all finish at the same moment and their
+        // result copies would pile up behind the compute; first chunks of cap/NL, 2cap/NL, ... keep the lanes out of phase and
+        // D2H streams continuously under the kernels of the other lanes.
+        // GEOMETRIC taper: whatever the lanes compute last is copied after the compute has ended, so the last NL chunks are 8
+        // elements, the NL before them 16, then 32 (the result copy of an element costs half its compute time).
+        std::vector<size_t> head, tail;
+        size_t hsum = 0, tsum = 0;
+        if (ntot >= (size_t)2 * NL * cap && cap >= 4 * NL)
+          for (int k = 0; k < NL; k++) { head.push_back(std::max((size_t)8, (size_t)cap * (k + 1) / NL)); hsum += head.back(); }
+        const size_t avail = ntot - hsum;
+        for (size_t sz : {(size_t)8, (size_t)16, (size_t)32})
+          if (sz < (size_t)cap)
+            for (int i = 0; i < NL; i++)
+              if (tsum + sz <= avail / 2) { tail.push_back(sz); tsum += sz; }
+        const size_t body = avail - tsum, nbody = (body + cap - 1) / cap;
+        sizes = head;
+        for (size_t i = 0, left = body; i < nbody; i++) { const size_t n = (left + (nbody - i) - 1) / (nbody - i); sizes.push_back(n); left -= n; }
+        for (size_t i = tail.size(); i-- > 0;) sizes.push_back(tail[i]);
+      }
+  return sizes;
+}
+
 // The elements of one call grouped into dense classes; inside a class sorted by signature so that a chunk is a short
 // list of equal-signature segments.
 struct ClassGroup {
@@ -412,33 +441,10 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
     const int lcap = g_lanes.cap;
     std::vector<size_t> cstart;   // chunk k covers el[cstart[k] .. cstart[k+1])
     {
-      const size_t ntot = el.size();
-      std::vector<size_t> sizes;
-      if (g_max_chunk > 0) {
-        for (size_t left = ntot; left;) { const size_t n = std::min(left, (size_t)cap); sizes.push_back(n); left -= n; }
-      } else {
-        // RAMPED start: the lanes share the SMs evenly, so equal first chunks would all finish at the same moment and their
-        // result copies would pile up behind the compute; first chunks of cap/NL, 2cap/NL, ... keep the lanes out of phase and
-        // D2H streams continuously under the kernels of the other lanes.
-        // GEOMETRIC taper: whatever the lanes compute last is copied after the compute has ended, so the last NL chunks are 8
-        // elements, the NL before them 16, then 32 (the result copy of an element costs half its compute time).
-        std::vector<size_t> head, tail;
-        size_t hsum = 0, tsum = 0;
-        if (ntot >= (size_t)2 * NL * cap && cap >= 4 * NL)
-          for (int k = 0; k < NL; k++) { head.push_back(std::max((size_t)8, (size_t)cap * (k + 1) / NL)); hsum += head.back(); }
-        const size_t avail = ntot - hsum;
-        for (size_t sz : {(size_t)8, (size_t)16, (size_t)32})
-          if (sz < (size_t)cap)
-            for (int i = 0; i < NL; i++)
-              if (tsum + sz <= avail / 2) { tail.push_back(sz); tsum += sz; }
-        const size_t body = avail - tsum, nbody = (body + cap - 1) / cap;
-        sizes = head;
-        for (size_t i = 0, left = body; i < nbody; i++) { const size_t n = (left + (nbody - i) - 1) / (nbody - i); sizes.push_back(n); left -= n; }
-        for (size_t i = tail.size(); i-- > 0;) sizes.push_back(tail[i]);
-      }
+      const std::vector<size_t> sizes = chunk_plan(el.size(), cap, NL, g_max_chunk);
       size_t c0 = 0;
       for (size_t n : sizes) { cstart.push_back(c0); c0 += n; }
-      cstart.push_back(ntot);
+      cstart.push_back(el.size());
     }
     int nchunk = 0;
     auto collect_info = [&](int k) {   // host side of chunk k: wait for its D2H, publish info[]
@@ -1066,3 +1072,10 @@ int hp3d_gpu_error_points(int plan, int nel, const int *etype, const int *norder
 }
 
 }  // extern "C"
+
+extern "C" int hp3d_gpu_chunk_plan_debug(long long ntot, int cap, int nlanes, int max_chunk, long long *sizes, int cap_sizes) {
+  if (ntot < 0 || cap < 1 || nlanes < 1) return fail(HP3D_EINVAL, "chunk_plan: bad argument");
+  const std::vector<size_t> v = chunk_plan((size_t)ntot, cap, nlanes, max_chunk);
+  if (sizes) for (size_t i = 0; i < v.size() && (int)i < cap_sizes; i++) sizes[i] = (long long)v[i];
+  return (int)v.size();
+}

@@ -254,6 +254,10 @@ int hp3d_gpu_integrate_debug_t(int plan, int etype, const int *norder, const int
 /* Test hook: run only the dense phase (DPG normal equations + static condensation) on caller-provided
  * Gram / enriched stiffness matrices.  G: (n x n) Hermitian, upper triangle read; Bm: n x (nb+ni+1), columns
  * ordered [bubble | interface | load].  cplx selects real(8)/complex(8). */
+/* Test hook (host only): the chunk sizes hp3d_gpu_elem_batch uses for `ntot` elements of one dense class with at most `cap`
+ * elements per chunk on `nlanes` lanes (ramped start, geometric taper); returns the number of chunks. */
+int hp3d_gpu_chunk_plan_debug(long long ntot, int cap, int nlanes, int max_chunk, long long *sizes, int cap_sizes);
+
 int hp3d_gpu_dense_debug(int cplx, int nel, int n, int nb, int ni, const void *G, const void *Bm, void *Aii,
                          void *Bi, void *ASchur, void *BSchur, int *info);
 

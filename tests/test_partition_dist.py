@@ -68,3 +68,24 @@ def test_two_rank_gloo_reduction(tmp_path):
     assert all(p.returncode == 0 for p in procs), outs
     line = [ln for ln in outs[0].splitlines() if ln.startswith("RESULT")][0].split()
     assert int(line[1]) == 37 and float(line[2]) == 11.0     # all elements covered once; time = max over ranks
+
+
+def test_chunk_plan_covers_every_batch_size(gpulib):
+    """The chunk plan of hp3d_gpu_elem_batch (ramped start, geometric taper; host logic, no GPU): for every batch size the
+    chunks are non-empty, at most `cap` elements, and add up to the batch; large batches start with a ramp and end with the
+    8-element chunks that keep the exposed result copy small."""
+    import ctypes as C
+    f = gpulib.hp3d_gpu_chunk_plan_debug
+    f.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    buf = (C.c_longlong * 8192)()
+    for cap in (1, 3, 4, 16, 25, 64):
+        for nl in (1, 2, 4):
+            for n in list(range(0, 300)) + [511, 512, 513, 1000, 1024, 4097]:
+                k = f(n, cap, nl, 0, buf, 8192)
+                sizes = list(buf[:k])
+                assert sum(sizes) == n and all(1 <= s <= cap for s in sizes), (cap, nl, n, sizes)
+    k = f(1024, 64, 4, 0, buf, 4096)
+    sizes = list(buf[:k])
+    assert sizes[:4] == [16, 32, 48, 64] and sizes[-4:] == [8, 8, 8, 8] and sizes[-8:-4] == [16, 16, 16, 16]
+    k = f(100, 64, 4, 7, buf, 4096)      # forced chunk size (hp3d_gpu_set_chunk): plain chunks of `cap`
+    assert sum(buf[:k]) == 100
