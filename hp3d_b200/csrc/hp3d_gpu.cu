@@ -83,7 +83,7 @@ std::vector<size_t> chunk_plan(size_t ntot, int cap, int NL, int max_chunk) {
         std::vector<size_t> head, tail;
         size_t hsum = 0, tsum = 0;
         if (ntot >= (size_t)2 * NL * cap && cap >= 4 * NL)
-          for (int k = 0; k < NL; k++) { head.push_back(std::max((size_t)8, (size_t)cap * (k + 1) / NL)); hsum += head.back(); }
+          for (int k = 0; k < NL; k++) { head.push_back(std::min((size_t)cap, std::max((size_t)8, (size_t)cap * (k + 1) / NL))); hsum += head.back(); }
         const size_t avail = ntot - hsum;
         for (size_t sz : {(size_t)8, (size_t)16, (size_t)32})
           if (sz < (size_t)cap)
