@@ -125,6 +125,8 @@ __device__ __forceinline__ void emit_fields(const GeomParams &gp, int e, int q, 
     if (gp.source == 9) {
       const double *t = src_tab + (long long)e * src_ld + (long long)q * 6;
       for (int c = 0; c < 3; c++) { jr[c] = t[2 * c]; ji[c] = t[2 * c + 1]; }
+      if (gp.kind == 3)   // Galerkin Maxwell: the load is -i w (J,F) (MAXWELL/GALERKIN/elem_opt.F90): store g = -i w J like the built-in source below
+        for (int c = 0; c < 3; c++) { const double a = jr[c]; jr[c] = gp.omega * ji[c]; ji[c] = -gp.omega * a; }
     } else if (gp.source == 1) {
       double p, h[9], cc[3];
       sin_potential_hess(gp.omega, x, p, h);      // real profile; amplitude (1+i) applied below

@@ -232,3 +232,33 @@ def test_properties_at_full_size(gpu):
     w = np.linalg.eigvalsh(eng.unpack(a, 0)[0])
     assert w.min() > -1e-10 * w.max()
     eng.close()
+
+
+@pytest.mark.parametrize("kind,rr", [(3, 1), (4, 1), (4, 0)])
+def test_maxwell_caller_source_table(oracle, gpu, kind, rr):
+    """HP3D_SRC_TABLE for the complex problems: a caller-supplied (complex, random) source J at the quadrature points
+    (`getf` evaluated on the host) must give the same load vectors as the oracle fed with the same table -- through the real
+    form (two real load rows) and through the general complex kernels."""
+    import ctypes as C
+    oracle.set_maxp(6)
+    rng = np.random.default_rng(31 + kind)
+    p, nel = 2, 2
+    norder = np.tile(uniform_order(p), (nel, 1))
+    norie = rng.integers(0, 2, (nel, 12)).astype(np.int32); norif = rng.integers(0, 8, (nel, 6)).astype(np.int32)
+    nH = oracle.celndof(norder[0])[0]
+    X = np.stack([hexa_xnod(nH, h=0.5, jitter=0.12, rng=rng) for e in range(nel)])
+    om = 2 * np.pi if kind == 4 else np.pi
+    eng = _engine(kind, omega=om, source=9, real_reduction=rr)
+    nint = eng.sizes(norder[0])[2]
+    J = rng.standard_normal((nel, nint, 3)) + 1j * rng.standard_normal((nel, nint, 3))
+    res = eng.elem_stc_batch(norder, norie, norif, X, source_qp=J)
+    assert (res["info"] == 0).all()
+    for e in range(nel):
+        tab = np.ascontiguousarray(J[e])
+        prm = _oracle_params(oracle, omega=om, source=9, source_table=tab.ctypes.data_as(C.c_void_p))
+        rA, rB, rAS, rBS = oracle.condensed(kind, norder[e], norie[e], norif[e], X[e], prm)
+        Aii, Bi, AS, BS = eng.unpack(res, e)
+        assert relerr(Aii, rA) < 1e-12 and relerr(Bi, rB) < 1e-12, (e, relerr(Bi, rB))
+        if BS.size:
+            assert relerr(BS, rBS) < 1e-10
+    eng.close()
