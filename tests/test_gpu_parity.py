@@ -262,3 +262,29 @@ def test_maxwell_caller_source_table(oracle, gpu, kind, rr):
         if BS.size:
             assert relerr(BS, rBS) < 1e-10
     eng.close()
+
+
+@pytest.mark.parametrize("test_norm", [1, 2, 3])
+@pytest.mark.parametrize("rr", [1, 0])
+def test_uw_maxwell_material_and_norm_parameters(oracle, gpu, test_norm, rr):
+    """Ultraweak Maxwell away from the defaults: eps, mu != 1, ALPHA_NORM != 1 and the three test norms (adjoint graph,
+    mathematician's, diagonal graph), second manufactured component -- through the real form and the complex kernels."""
+    oracle.set_maxp(6)
+    oracle.use_blas(True)
+    rng = np.random.default_rng(555 + test_norm)
+    p, nel = 2, 2
+    norder = np.tile(uniform_order(p), (nel, 1))
+    norie = rng.integers(0, 2, (nel, 12)).astype(np.int32); norif = rng.integers(0, 8, (nel, 6)).astype(np.int32)
+    nH = oracle.celndof(norder[0])[0]
+    X = np.stack([hexa_xnod(nH, h=0.5, jitter=0.12, curved=0.01, rng=rng) for e in range(nel)])
+    kw = dict(omega=1.7 * np.pi, eps=2.5, mu=0.7, alpha_norm=0.3, test_norm=test_norm, icomp_exact=3)
+    prm = _oracle_params(oracle, **kw)
+    eng = _engine(4, real_reduction=rr, **kw)
+    res = eng.elem_stc_batch(norder, norie, norif, X)
+    assert (res["info"] == 0).all()
+    for e in range(nel):
+        Aii, Bi, AS, BS = eng.unpack(res, e)
+        rA, rB, rAS, rBS = oracle.condensed(4, norder[e], norie[e], norif[e], X[e], prm)
+        assert relerr(Aii, rA) < 1e-12 and relerr(Bi, rB) < 1e-12, (e, relerr(Aii, rA), relerr(Bi, rB))
+        assert relerr(AS, rAS) < 1e-9 and relerr(BS, rBS) < 1e-9
+    eng.close()
