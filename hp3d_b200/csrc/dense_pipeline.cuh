@@ -98,8 +98,9 @@ static void chol_trapezoid(double *Mbase, long long plane, long long batch_strid
 
 // The whole dense phase for `batch` elements whose W (DPG) or Am (Galerkin) buffers have been filled.
 // `normal_eq_only`: stop after A = B~^H B~ (the uncondensed DPG system incl. the load row: what the residual needs).
+// `want_z`: also form Z = Y~ L^-1 (ASchur^H and the bubble load), 6 % of the flops at config 3.
 template <bool CPLX>
-static void dense_phase(const DenseDims &d, const DenseBuffers &b, int batch, cudaStream_t st, bool normal_eq_only = false) {
+static void dense_phase(const DenseDims &d, const DenseBuffers &b, int batch, cudaStream_t st, bool normal_eq_only = false, bool want_z = true) {
   const long long P = CPLX ? 2 : 1;
   const long long lp = (long long)TILE * TILE;
   const int M = d.M();
@@ -131,6 +132,7 @@ static void dense_phase(const DenseDims &d, const DenseBuffers &b, int batch, cu
     g.K = d.nbp; g.lower_only = 1; g.use_cin = 1; g.alpha = -1.0;
     launch_gemm<CPLX>(g, d.nip / TILE, d.nip / TILE, batch, st);
   }
+  if (!want_z) return;   // the Schur factors are not wanted (STORE_STC off): the condensed system is complete
   {  // LH = L^H (upper, row-major) for the backward solve
     MatRef In{b.Am, apl, ab, M}, Out{b.LH, (long long)d.lh_plane(), P * (long long)d.lh_plane(), d.nbp};
     dim3 grid(d.nbp / 32, d.nbp / 32, batch), blk(32, 8);

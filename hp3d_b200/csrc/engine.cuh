@@ -340,14 +340,16 @@ static void run_integration(const ChunkShape &sh, Lane &L, const GeomParams &gp,
   }
 }
 
-static long long dense_phase_launches(const DenseDims &d) {  // mirrors the launch structure of dense_phase()
+static long long dense_phase_launches(const DenseDims &d, bool want_z = true) {  // mirrors the launch structure of dense_phase()
   long long n = 0;
   auto chol = [&](int nt_r, int nt_c) { for (int j = 0; j < nt_c; j++) { if (j > 0) n++; n++; if (nt_r - j - 1 > 0) n++; } };
   if (d.dpg) { chol(d.R() / TILE, d.np / TILE); n++; }
   if (d.nbp == 0) return n;
   n++;
   chol(d.M() / TILE, d.nbp / TILE);
-  n += 2;
+  n += 1;
+  if (!want_z) return n;
+  n += 1;
   const int ns = d.nsteps_stc();
   for (int j = ns - 1; j >= 0; j--) { if (j < ns - 1) n++; n++; }
   return n;
@@ -387,8 +389,8 @@ static void run_dense_and_scatter(const ChunkShape &sh, Lane &L, const Lane::Out
     }
     return;
   }
-  dense_phase<CPLX>(d, L.ws.b, nel, st);
-  g_launches += dense_phase_launches(d);
+  dense_phase<CPLX>(d, L.ws.b, nel, st, false, want_schur);
+  g_launches += dense_phase_launches(d, want_schur);
   if (ev && ev->on) cudaEventRecord(ev->e[2], st);
   OutMaps mp{g_lanes.d_iota, g_lanes.d_iota, g_lanes.d_ones, g_lanes.d_ones, 0, 0, 0, 0, L.ws.b.ni_e, L.ws.b.nb_e, L.ws.b.nip_e};
   dim3 blk(16, 16), g1((d.ni + 15) / 16, (d.ni + 15) / 16, nel);

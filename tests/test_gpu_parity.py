@@ -288,3 +288,27 @@ def test_uw_maxwell_material_and_norm_parameters(oracle, gpu, test_norm, rr):
         assert relerr(Aii, rA) < 1e-12 and relerr(Bi, rB) < 1e-12, (e, relerr(Aii, rA), relerr(Bi, rB))
         assert relerr(AS, rAS) < 1e-9 and relerr(BS, rBS) < 1e-9
     eng.close()
+
+
+@pytest.mark.parametrize("kind", [2, 4])
+def test_without_schur_factors(oracle, gpu, kind):
+    """STORE_STC off (hp3d_params.store_schur = 0): the condensed system is unchanged, the back-substitution factors are
+    neither formed (the Z = Y L^-1 steps are skipped) nor copied."""
+    oracle.set_maxp(6)
+    rng = np.random.default_rng(99 + kind)
+    p, nel = 3, 3
+    norder = np.tile(uniform_order(p), (nel, 1))
+    norie = rng.integers(0, 2, (nel, 12)).astype(np.int32); norif = rng.integers(0, 8, (nel, 6)).astype(np.int32)
+    nH = oracle.celndof(norder[0])[0]
+    X = np.stack([hexa_xnod(nH, h=0.5, jitter=0.12, rng=rng) for e in range(nel)])
+    om = 2 * np.pi if kind == 4 else 1.0
+    full = _engine(kind, omega=om)
+    ref = full.elem_stc_batch(norder, norie, norif, X)
+    eng = _engine(kind, omega=om, store_schur=0)
+    res = eng.elem_stc_batch(norder, norie, norif, X)
+    assert (res["info"] == 0).all()
+    for e in range(nel):
+        a, b = eng.unpack(res, e), full.unpack(ref, e)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])     # same kernels, same order: bit-identical
+        assert not a[2].any() and not a[3].any()                             # the Schur arrays are left untouched
+    full.close(); eng.close()
