@@ -58,7 +58,7 @@ template <bool CPLX> __host__ __device__ constexpr int gemm_stages() { return 2;
 // One 64x64 output tile per CTA, 4 warps (2x2), each warp a 32x32 sub-tile = 4x4 DMMA tiles.
 // grid = (row tiles, col tiles, batch)
 template <bool CPLX>
-__global__ void __launch_bounds__(GEMM_THREADS, CPLX ? 2 : 3) gemm_nc_kernel(const GemmArgs g) {
+__global__ void __launch_bounds__(GEMM_THREADS, CPLX ? 2 : 4) gemm_nc_kernel(const GemmArgs g) {
   const int ti = blockIdx.x, tj = blockIdx.y, e = blockIdx.z;
   if (g.lower_only && tj > ti + g.diag_shift) return;
   constexpr int NP = CPLX ? 2 : 1;
