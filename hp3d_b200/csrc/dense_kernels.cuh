@@ -54,6 +54,8 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // pipeline depth (a third stage for the real kernel was measured: 94.8 vs 93.7 ms per 256 elements, no gain -- the DMMA pipe is
 // already 88 % active and the rest is not load latency)
 template <bool CPLX> __host__ __device__ constexpr int gemm_stages() { return 2; }
+// k-chunk per pipeline stage (32 for the real kernel was measured: 3 CTAs/SM instead of 4, dense 95.3 vs 91.4 ms: worse)
+template <bool CPLX> __host__ __device__ constexpr int gemm_kc() { return 16; }
 
 // One 64x64 output tile per CTA, 4 warps (2x2), each warp a 32x32 sub-tile = 4x4 DMMA tiles.
 // grid = (row tiles, col tiles, batch)
@@ -62,6 +64,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, CPLX ? 2 : 4) gemm_nc_kernel(con
   const int ti = blockIdx.x, tj = blockIdx.y, e = blockIdx.z;
   if (g.lower_only && tj > ti + g.diag_shift) return;
   constexpr int NP = CPLX ? 2 : 1;
+  constexpr int KC = gemm_kc<CPLX>(), LDS_K = KC + 4;   // shadow the file-level defaults
   constexpr int NSTAGE = gemm_stages<CPLX>();
   extern __shared__ __align__(16) double smem[];
   // smem: [stage NSTAGE][operand 2][plane NP][TILE][LDS_K]
@@ -79,11 +82,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, CPLX ? 2 : 4) gemm_nc_kernel(con
     for (int b = 0; b < 4; b++) { cr[a][b][0] = cr[a][b][1] = 0.0; ci[a][b][0] = ci[a][b][1] = 0.0; }
 
   auto load_stage = [&](int stage, int k0) {
-    // each plane of each operand: 64 rows x 16 doubles = 64 x 8 chunks of 16 B
+    // each plane of each operand: 64 rows x KC doubles = 64 x KC/2 chunks of 16 B
 #pragma unroll
     for (int it = 0; it < (TILE * (KC / 2)) / GEMM_THREADS; it++) {
       int c = tid + it * GEMM_THREADS;
-      int row = c >> 3, ch = c & 7;
+      int row = c / (KC / 2), ch = c % (KC / 2);
 #pragma unroll
       for (int pl = 0; pl < NP; pl++) {
         cp_async16(sm(stage, 0, pl) + row * LDS_K + ch * 2, Ag + (pl ? g.A.im_off : 0) + (long long)row * g.A.ld + k0 + ch * 2);
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, CPLX ? 2 : 4) gemm_nc_kernel(con
 }
 
 constexpr size_t potrf_smem_bytes() { return (size_t)4 * TILE * (TILE + 1) * sizeof(double); }
-template <bool CPLX> constexpr size_t gemm_smem_bytes() { return (size_t)gemm_stages<CPLX>() * 2 * (CPLX ? 2 : 1) * TILE * LDS_K * sizeof(double); }
+template <bool CPLX> constexpr size_t gemm_smem_bytes() { return (size_t)gemm_stages<CPLX>() * 2 * (CPLX ? 2 : 1) * TILE * (gemm_kc<CPLX>() + 4) * sizeof(double); }
 
 // ---------------------------------------------------------------------------------------------------
 // potrf_inv_tile_real: the REAL 64x64 diagonal-tile step (factor L L^T, write L back with the upper part zeroed, write
