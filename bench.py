@@ -107,7 +107,7 @@ def cpu_reference_rate(kind, p, nsample, threads, omega):
     return nsample / dt, dt, blas
 
 
-def run_reference(args):
+def run_reference(args, out_stream):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -129,7 +129,7 @@ def run_reference(args):
         "config": workload_config(args, nsample),
         "cpu_baseline": {"value": val, "unit": "elements/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }), file=out_stream, flush=True)
 
 
 def celem_leg(args, eng, norder, noe, nof, xs, ni, nb, bufs, rank):
@@ -182,7 +182,17 @@ def workload_config(args, B):
             "l2": "per-step working set (>100 MB per element at p=5) far exceeds the 126 MB L2; no flush needed"}
 
 
+def claim_stdout():
+    """stdout must carry ONE JSON line: keep a private handle on it and point fd 1 at stderr for everything else (NCCL prints its
+    version banner on stdout, other libraries may too)."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    out_stream = claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -199,13 +209,11 @@ def main():
     ap.add_argument("--celem", action="store_true", help="also time SURVEY 8f row f1 (constraints + compression + COO fused into the batched call)")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out_stream)
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
-        # stdout carries the JSON line only: NCCL's version banner / debug output goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -320,7 +328,7 @@ def main():
         v, dtc, blas = cpu_reference_rate(args.kind, args.p, ns, cores, omega)
         out["cpu_baseline"] = {"value": v, "unit": "elements/s", "cores": cores, "kind": "port",
                                "sample": f"{ns} elements of the same workload in {dtc:.1f} s; OpenMP over elements ({cores} threads), single-threaded {'OpenBLAS' if blas else 'built-in loops'} per element"}
-    print(json.dumps(out))
+    print(json.dumps(out), file=out_stream, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
