@@ -390,11 +390,14 @@ namespace hp3d {
 // ASchur = A_bb^-1 A_bi, BSchur = A_bb^-1 b_b.  One CTA per element, matrix in global memory (L2-resident), planar.
 // Layout of Am: [M][M] row-major, bubbles at rows/cols [0,nb), interface at [nbp, nbp+ni), load COLUMN M-1; nb, ni per element.
 // Outputs are written directly in the caller's layout (column-major, interleaved complex).
-template <bool CPLX>
+// RS2 (with CPLX = false): REAL matrix with a COMPLEX load carried as two real columns (M-2: Re, M-1: Im) -- lossless Maxwell
+// Galerkin; the elimination runs in real arithmetic on all columns, the outputs are written as complex numbers.
+template <bool CPLX, bool RS2 = false>
 __global__ void __launch_bounds__(512) stc_gen_kernel(const int *__restrict__ nb_e, int nbp, const int *__restrict__ ni_e, int M, double *Am,
                                                       long long a_plane, long long a_batch, double *Aii, double *Bi, double *AS, double *BS,
                                                       long long sA, long long sB, long long sAS, long long sBS, int want_schur, int *info) {
-  constexpr int NS = CPLX ? 2 : 1;
+  static_assert(!(CPLX && RS2), "RS2 is a real elimination");
+  constexpr int NS = (CPLX || RS2) ? 2 : 1;   // scalars of the OUTPUT value type
   extern __shared__ __align__(16) double sh[];   // pivot row: [2][M]
   __shared__ double red_v[16];
   __shared__ int red_i[16];
@@ -403,7 +406,7 @@ __global__ void __launch_bounds__(512) stc_gen_kernel(const int *__restrict__ nb
   const int e = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   const int nb = nb_e[e], ni = ni_e[e];
   double *Ar = Am + (long long)e * a_batch, *Ai = Ar + a_plane;
-  const int ncol = M, lc = M - 1;         // all columns (padding columns are zero); load column = last padded interface column
+  const int ncol = M, lc = RS2 ? M - 2 : M - 1;   // all columns (padding columns are zero); load column(s) = last padded interface column(s)
   double *pr = sh, *pi = sh + M;
   int bad = 0;
   for (int k = 0; k < nb; k++) {
@@ -468,10 +471,12 @@ __global__ void __launch_bounds__(512) stc_gen_kernel(const int *__restrict__ nb
     const int r = idx % ni, c = idx / ni;   // column-major output
     oA[(long long)idx * NS] = Ar[(long long)(nbp + r) * M + nbp + c];
     if (CPLX) oA[(long long)idx * NS + 1] = Ai[(long long)(nbp + r) * M + nbp + c];
+    if (RS2) oA[(long long)idx * NS + 1] = 0.0;
   }
   for (int r = tid; r < ni; r += nt) {
     oB[(long long)r * NS] = Ar[(long long)(nbp + r) * M + lc];
     if (CPLX) oB[(long long)r * NS + 1] = Ai[(long long)(nbp + r) * M + lc];
+    if (RS2) oB[(long long)r * NS + 1] = Ar[(long long)(nbp + r) * M + lc + 1];
   }
   if (tid == 0 && bad && info[e] == 0) info[e] = bad;
   if (!want_schur || nb == 0) return;
@@ -504,10 +509,12 @@ __global__ void __launch_bounds__(512) stc_gen_kernel(const int *__restrict__ nb
     const int b = idx % nb, c = idx / nb;
     oS[(long long)idx * NS] = Ar[(long long)b * M + nbp + c];
     if (CPLX) oS[(long long)idx * NS + 1] = Ai[(long long)b * M + nbp + c];
+    if (RS2) oS[(long long)idx * NS + 1] = 0.0;
   }
   for (int b = tid; b < nb; b += nt) {
     oT[(long long)b * NS] = Ar[(long long)b * M + lc];
     if (CPLX) oT[(long long)b * NS + 1] = Ai[(long long)b * M + lc];
+    if (RS2) oT[(long long)b * NS + 1] = Ar[(long long)b * M + lc + 1];
   }
 }
 

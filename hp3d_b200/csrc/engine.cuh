@@ -374,16 +374,16 @@ static void run_dense_and_scatter(const ChunkShape &sh, Lane &L, const Lane::Out
   }
   if (sh.gen_stc) {   // pivoted-LU condensation: one kernel, writes the caller-layout outputs itself
     const long long P = CPLX ? 2 : 1;
-    stc_gen_kernel<CPLX><<<nel, 512, sizeof(double) * 2 * d.M(), st>>>(L.ws.b.nb_e, d.nbp, L.ws.b.ni_e, d.M(), L.ws.b.Am, (long long)d.a_plane(),
-                                                                       P * (long long)d.a_plane(), o.Aii, o.Bi, o.AS, o.BS, (long long)d.ni * d.ni,
-                                                                       (long long)d.ni, (long long)d.nb * d.ni, (long long)d.nb, want_schur ? 1 : 0,
-                                                                       L.ws.b.info);
+    stc_gen_kernel<CPLX, RS><<<nel, 512, sizeof(double) * 2 * d.M(), st>>>(L.ws.b.nb_e, d.nbp, L.ws.b.ni_e, d.M(), L.ws.b.Am, (long long)d.a_plane(),
+                                                                           P * (long long)d.a_plane(), o.Aii, o.Bi, o.AS, o.BS, (long long)d.ni * d.ni,
+                                                                           (long long)d.ni, (long long)d.nb * d.ni, (long long)d.nb, want_schur ? 1 : 0,
+                                                                           L.ws.b.info);
     g_launches++;
     if (ev && ev->on) cudaEventRecord(ev->e[2], st);
     cudaMemcpyAsync(o.info, L.ws.b.info, sizeof(int) * nel, cudaMemcpyDeviceToDevice, st);
     if (mode == MODE_BWD && d.nb > 0) {
       dim3 gb((d.nb + 7) / 8, nel);
-      stc_bwd_kernel<CPLX><<<gb, 256, 0, st>>>(L.ws.b.ni_e, L.ws.b.nb_e, 0, 0, o.AS, (long long)d.nb * d.ni, o.BS, (long long)d.nb, L.d_xi, (long long)d.ni,
+      stc_bwd_kernel<OUTC><<<gb, 256, 0, st>>>(L.ws.b.ni_e, L.ws.b.nb_e, 0, 0, o.AS, (long long)d.nb * d.ni, o.BS, (long long)d.nb, L.d_xi, (long long)d.ni,
                                                L.d_xb, (long long)d.nb + 1);
       g_launches++;
     }

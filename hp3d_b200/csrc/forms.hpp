@@ -441,7 +441,10 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
     const int nE = (int)ed.size(), iE = nE - bE;
     S.cplx = true; S.dpg = false; S.gen_stc = true; S.ntest = 0; S.ni = iE; S.nb = bE;
     DenseDims &D = S.dims;
-    D.cplx = true; D.dpg = false; D.n = 0; D.nb = S.nb; D.ni = S.ni; D.finish();
+    // lossless medium (sigma = 0): A is REAL symmetric and only the load is complex -> real LU on a real matrix with the load as
+    // two real columns (Re, Im); the output kernel interleaves them (same idea as the ultraweak real form, without phases)
+    const bool rsg = P.real_struct && P.sigma == 0.0;
+    D.cplx = !rsg; D.rs = rsg; D.nload = rsg ? 2 : 1; D.dpg = false; D.n = 0; D.nb = S.nb; D.ni = S.ni; D.finish();
     if (sizes_only) return true;
     int fe[3], mapE[3];
     for (int a = 0; a < 3; a++) {
@@ -453,8 +456,8 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
     const std::complex<double> zb(P.omega * P.omega * P.eps, -P.omega * P.sigma);
     for (int a = 0; a < 3; a++)
       for (int a2 = 0; a2 < 3; a2++) {
-        BlockBuilder b(S, fe[a], fe[a2], channel(1, 0, 0, 0, mapE[a], mapE[a2]), channel(1, 1, 0, 0, mapE[a], mapE[a2]));
-        b.add(-1, -1, F_D + sym_idx(a, a2), 1.0, -zb.real(), -zb.imag());
+        BlockBuilder b(S, fe[a], fe[a2], channel(1, 0, 0, 0, mapE[a], mapE[a2]), rsg ? no_channel() : channel(1, 1, 0, 0, mapE[a], mapE[a2]));
+        b.add(-1, -1, F_D + sym_idx(a, a2), 1.0, -zb.real(), rsg ? 0.0 : -zb.imag());
         CurlComp ca[2], cb[2];
         curl_comps(a, ca); curl_comps(a2, cb);
         for (int i = 0; i < 2; i++)
@@ -462,7 +465,7 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
         b.finish();
       }
     for (int a = 0; a < 3; a++) {  // load as a COLUMN (the LU condensation eliminates rows)
-      BlockBuilder b(S, fe[a], unit, channel(1, 0, 0, D.nbp + D.nip - 1, mapE[a]), channel(1, 1, 0, D.nbp + D.nip - 1, mapE[a]));
+      BlockBuilder b(S, fe[a], unit, channel(1, 0, 0, D.nbp + D.nip - D.nload, mapE[a]), rsg ? channel(1, 0, 0, D.nbp + D.nip - 1, mapE[a]) : channel(1, 1, 0, D.nbp + D.nip - 1, mapE[a]));
       b.add(-1, -1, F_SRC + 2 * a, 1.0, 1.0, 0.0);
       b.add(-1, -1, F_SRC + 2 * a + 1, 1.0, 0.0, 1.0);
       b.finish();

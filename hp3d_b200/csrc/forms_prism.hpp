@@ -333,7 +333,10 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
     const int nE = (int)ed.size(), iE = nE - bE;
     S.cplx = true; S.dpg = false; S.gen_stc = true; S.ntest = 0; S.ni = iE; S.nb = bE;
     DenseDims &D = S.dims;
-    D.cplx = true; D.dpg = false; D.n = 0; D.nb = S.nb; D.ni = S.ni; D.finish();
+    // lossless medium (sigma = 0): A is REAL symmetric and only the load is complex -> real LU on a real matrix with the load as
+    // two real columns (Re, Im); the output kernel interleaves them (same idea as the ultraweak real form, without phases)
+    const bool rsg = P.real_struct && P.sigma == 0.0;
+    D.cplx = !rsg; D.rs = rsg; D.nload = rsg ? 2 : 1; D.dpg = false; D.n = 0; D.nb = S.nb; D.ni = S.ni; D.finish();
     if (sizes_only) return true;
     PFam fe[2];
     fe[0] = add_pfam(S, PF_EH, TV, pmax[1] + 1, T_H, nqt, tpts);
@@ -344,13 +347,13 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
     for (int a = 0; a < 2; a++)
       for (int a2 = 0; a2 < 2; a2++) {
         if (fe[a].nT == 0 || fe[a2].nT == 0) continue;
-        BlockBuilder b(S, fe[a].id, fe[a2].id, channel(1, 0, 0, 0, mapE[a], mapE[a2]), channel(1, 1, 0, 0, mapE[a], mapE[a2]));
-        add_hcurl_pair(b, fe[a].kind, fe[a2].kind, -zb.real(), -zb.imag(), 1.0 / P.mu, 0.0);
+        BlockBuilder b(S, fe[a].id, fe[a2].id, channel(1, 0, 0, 0, mapE[a], mapE[a2]), rsg ? no_channel() : channel(1, 1, 0, 0, mapE[a], mapE[a2]));
+        add_hcurl_pair(b, fe[a].kind, fe[a2].kind, -zb.real(), rsg ? 0.0 : -zb.imag(), 1.0 / P.mu, 0.0);
         b.finish();
       }
     for (int a = 0; a < 2; a++) {
       if (fe[a].nT == 0) continue;
-      BlockBuilder b(S, fe[a].id, unit.id, channel(1, 0, 0, D.nbp + D.nip - 1, mapE[a]), channel(1, 1, 0, D.nbp + D.nip - 1, mapE[a]));
+      BlockBuilder b(S, fe[a].id, unit.id, channel(1, 0, 0, D.nbp + D.nip - D.nload, mapE[a]), rsg ? channel(1, 0, 0, D.nbp + D.nip - 1, mapE[a]) : channel(1, 1, 0, D.nbp + D.nip - 1, mapE[a]));
       for (int d = 0; d < 3; d++) {
         const CompRef v = pf_val(fe[a].kind, d);
         if (v.tc < 0) continue;

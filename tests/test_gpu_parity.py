@@ -234,7 +234,7 @@ def test_properties_at_full_size(gpu):
     eng.close()
 
 
-@pytest.mark.parametrize("kind,rr", [(3, 1), (4, 1), (4, 0)])
+@pytest.mark.parametrize("kind,rr", [(3, 1), (3, 0), (4, 1), (4, 0)])
 def test_maxwell_caller_source_table(oracle, gpu, kind, rr):
     """HP3D_SRC_TABLE for the complex problems: a caller-supplied (complex, random) source J at the quadrature points
     (`getf` evaluated on the host) must give the same load vectors as the oracle fed with the same table -- through the real
