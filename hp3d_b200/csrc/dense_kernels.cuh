@@ -154,6 +154,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, CPLX ? 2 : 4) gemm_nc_kernel(con
     }
 }
 
+// pivots per block and dynamic shared memory of stc_gen_kernel for padded extent M
+inline int stc_gen_block(int M, bool cplx) { const size_t row = (size_t)(cplx ? 2 : 1) * M * sizeof(double); int r = (int)((size_t)(160 * 1024) / row); return r > 8 ? 8 : (r < 1 ? 1 : r); }
+inline size_t stc_gen_smem(int M, bool cplx) { const size_t a = (size_t)(cplx ? 2 : 1) * stc_gen_block(M, cplx) * M * sizeof(double), b = (size_t)2 * M * sizeof(double); return a > b ? a : b; }
+
 constexpr size_t potrf_smem_bytes() { return (size_t)4 * TILE * (TILE + 1) * sizeof(double); }
 template <bool CPLX> constexpr size_t gemm_smem_bytes() { return (size_t)gemm_stages<CPLX>() * 2 * (CPLX ? 2 : 1) * TILE * (gemm_kc<CPLX>() + 4) * sizeof(double); }
 
@@ -387,7 +391,8 @@ namespace hp3d {
 // stc_fwd_gen (src/modules/stc.F90:443-507: ?GETRF, 2 x ?GETRS, 2 x ?GEMM) as one Gaussian elimination of the full
 // element matrix [A_bb A_bi b_b ; A_ib A_ii b_i] with partial pivoting restricted to the bubble rows: after nb steps the
 // interface rows hold the Schur complement and the condensed load, and a back substitution on the bubble rows gives
-// ASchur = A_bb^-1 A_bi, BSchur = A_bb^-1 b_b.  One CTA per element, matrix in global memory (L2-resident), planar.
+// ASchur = A_bb^-1 A_bi, BSchur = A_bb^-1 b_b.  One CTA per element, matrix in global memory (L2-resident), planar;
+// the elimination is blocked (rblk pivots per sweep of the trailing matrix, U block rows in shared memory).
 // Layout of Am: [M][M] row-major, bubbles at rows/cols [0,nb), interface at [nbp, nbp+ni), load COLUMN M-1; nb, ni per element.
 // Outputs are written directly in the caller's layout (column-major, interleaved complex).
 // RS2 (with CPLX = false): REAL matrix with a COMPLEX load carried as two real columns (M-2: Re, M-1: Im) -- lossless Maxwell
@@ -395,72 +400,120 @@ namespace hp3d {
 template <bool CPLX, bool RS2 = false>
 __global__ void __launch_bounds__(512) stc_gen_kernel(const int *__restrict__ nb_e, int nbp, const int *__restrict__ ni_e, int M, double *Am,
                                                       long long a_plane, long long a_batch, double *Aii, double *Bi, double *AS, double *BS,
-                                                      long long sA, long long sB, long long sAS, long long sBS, int want_schur, int *info) {
+                                                      long long sA, long long sB, long long sAS, long long sBS, int want_schur, int *info, int rblk) {
   static_assert(!(CPLX && RS2), "RS2 is a real elimination");
   constexpr int NS = (CPLX || RS2) ? 2 : 1;   // scalars of the OUTPUT value type
-  extern __shared__ __align__(16) double sh[];   // pivot row: [2][M]
+  constexpr int RMAX = 8;                     // pivot columns per block (rblk <= RMAX, chosen by the host from the shared-memory budget)
+  extern __shared__ __align__(16) double sh[];   // U block rows: [planes][rblk][M] (the back substitution reuses the first [2][M])
   __shared__ double red_v[16];
   __shared__ int red_i[16];
   __shared__ int s_piv;
+  __shared__ double s_inv[2];
 
   const int e = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   const int nb = nb_e[e], ni = ni_e[e];
   double *Ar = Am + (long long)e * a_batch, *Ai = Ar + a_plane;
   const int ncol = M, lc = RS2 ? M - 2 : M - 1;   // all columns (padding columns are zero); load column(s) = last padded interface column(s)
-  double *pr = sh, *pi = sh + M;
+  double *Ur = sh, *Ui = sh + (size_t)rblk * M;   // U block rows, [t][j]
+  double *pr = sh, *pi = sh + M;                  // back substitution: pivot row
   int bad = 0;
-  for (int k = 0; k < nb; k++) {
-    // ---- pivot search over bubble rows k..nb-1 of column k
-    double best = -1.0; int bi = k;
-    for (int i = k + tid; i < nb; i += nt) {
-      double vr = Ar[(long long)i * M + k], vi = CPLX ? Ai[(long long)i * M + k] : 0.0;
-      double v = vr * vr + vi * vi;
-      if (v > best) { best = v; bi = i; }
-    }
-    for (int o = 16; o; o >>= 1) {
-      double ov = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-    }
-    if (lane == 0) { red_v[warp] = best; red_i[warp] = bi; }
-    __syncthreads();
-    if (tid == 0) {
-      double b = red_v[0]; int p = red_i[0];
-      for (int w = 1; w < nw; w++) if (red_v[w] > b || (red_v[w] == b && red_i[w] < p)) { b = red_v[w]; p = red_i[w]; }
-      s_piv = p;
-      if (!(b > 0.0)) { if (!bad) bad = k + 1; }
-    }
-    __syncthreads();
-    const int p = s_piv;
-    // ---- swap rows k <-> p (columns >= k), keep the pivot row in shared memory
-    for (int j = k + tid; j < ncol; j += nt) {
-      if (j >= nb && j < nbp) continue;
-      double ar = Ar[(long long)p * M + j], ai = CPLX ? Ai[(long long)p * M + j] : 0.0;
-      if (p != k) {
-        Ar[(long long)p * M + j] = Ar[(long long)k * M + j];
-        Ar[(long long)k * M + j] = ar;
-        if (CPLX) { Ai[(long long)p * M + j] = Ai[(long long)k * M + j]; Ai[(long long)k * M + j] = ai; }
+  // Blocked right-looking elimination: the trailing matrix is swept once per block of rblk pivots instead of once per pivot
+  // (the unblocked sweep streams it through L2 for every column and is bandwidth-bound there).  Pivoting: partial, over the
+  // bubble rows, on fully updated panel columns -- the pivot sequence of the unblocked algorithm (stc_fwd_gen: ?GETRF on A_bb).
+  for (int kb = 0; kb < nb; kb += rblk) {
+    const int rb = min(rblk, nb - kb);
+    // ---- A. panel: columns kb .. kb+rb-1
+    for (int t = 0; t < rb; t++) {
+      const int k = kb + t;
+      double best = -1.0; int bi = k;
+      for (int i = k + tid; i < nb; i += nt) {
+        double vr = Ar[(long long)i * M + k], vi = CPLX ? Ai[(long long)i * M + k] : 0.0;
+        double v = vr * vr + vi * vi;
+        if (v > best) { best = v; bi = i; }
       }
-      pr[j] = ar; if (CPLX) pi[j] = ai;
+      for (int o = 16; o; o >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if (lane == 0) { red_v[warp] = best; red_i[warp] = bi; }
+      __syncthreads();
+      if (tid == 0) {
+        double b = red_v[0]; int p = red_i[0];
+        for (int w = 1; w < nw; w++) if (red_v[w] > b || (red_v[w] == b && red_i[w] < p)) { b = red_v[w]; p = red_i[w]; }
+        s_piv = p;
+        if (!(b > 0.0)) { if (!bad) bad = k + 1; }
+      }
+      __syncthreads();
+      const int p = s_piv;
+      // swap rows k <-> p: the block's multipliers (columns kb..) and everything to the right
+      if (p != k)
+        for (int j = kb + tid; j < ncol; j += nt) {
+          if (j >= nb && j < nbp) continue;
+          double a = Ar[(long long)p * M + j]; Ar[(long long)p * M + j] = Ar[(long long)k * M + j]; Ar[(long long)k * M + j] = a;
+          if (CPLX) { double b = Ai[(long long)p * M + j]; Ai[(long long)p * M + j] = Ai[(long long)k * M + j]; Ai[(long long)k * M + j] = b; }
+        }
+      __syncthreads();
+      if (tid == 0) {
+        double dr = Ar[(long long)k * M + k], di = CPLX ? Ai[(long long)k * M + k] : 0.0, dn = dr * dr + di * di;
+        if (!(dn > 0.0)) { dr = 1.0; di = 0.0; dn = 1.0; }
+        s_inv[0] = dr / dn; s_inv[1] = -di / dn;
+      }
+      __syncthreads();
+      const double ir = s_inv[0], ii = s_inv[1];
+      // multipliers of column k (stored in place) and the update of the remaining PANEL columns; one thread per row
+      const int nrows = (nb - k - 1) + ni;
+      for (int r = tid; r < nrows; r += nt) {
+        const int i = (r < nb - k - 1) ? k + 1 + r : nbp + (r - (nb - k - 1));
+        double *rr = Ar + (long long)i * M, *ri = Ai + (long long)i * M;
+        const double ar = rr[k], ai = CPLX ? ri[k] : 0.0;
+        const double lr = ar * ir - ai * ii, li = ar * ii + ai * ir;   // l = a(i,k) / pivot
+        rr[k] = lr; if (CPLX) ri[k] = li;
+        for (int j = k + 1; j < kb + rb; j++) {
+          const double ur = Ar[(long long)k * M + j], ui = CPLX ? Ai[(long long)k * M + j] : 0.0;
+          if (CPLX) { rr[j] -= lr * ur - li * ui; ri[j] -= lr * ui + li * ur; }
+          else rr[j] -= lr * ur;
+        }
+      }
+      __syncthreads();
+    }
+    // ---- B. U block rows: row kb+t, columns right of the panel, forward-substituted with the unit lower triangle of the panel
+    const int j0 = kb + rb;
+    for (int t = 0; t < rb; t++) {
+      const double *lrow_r = Ar + (long long)(kb + t) * M + kb, *lrow_i = Ai + (long long)(kb + t) * M + kb;
+      for (int j = j0 + tid; j < ncol; j += nt) {
+        if (j >= nb && j < nbp) { Ur[(size_t)t * M + j] = 0.0; if (CPLX) Ui[(size_t)t * M + j] = 0.0; continue; }
+        double vr = Ar[(long long)(kb + t) * M + j], vi = CPLX ? Ai[(long long)(kb + t) * M + j] : 0.0;
+        for (int s2 = 0; s2 < t; s2++) {
+          const double lr = lrow_r[s2], li = CPLX ? lrow_i[s2] : 0.0, ur = Ur[(size_t)s2 * M + j], ui = CPLX ? Ui[(size_t)s2 * M + j] : 0.0;
+          if (CPLX) { vr -= lr * ur - li * ui; vi -= lr * ui + li * ur; }
+          else vr -= lr * ur;
+        }
+        Ur[(size_t)t * M + j] = vr; Ar[(long long)(kb + t) * M + j] = vr;
+        if (CPLX) { Ui[(size_t)t * M + j] = vi; Ai[(long long)(kb + t) * M + j] = vi; }
+      }
+      // column j of row t only depends on column j of the rows above: no barrier needed between the t steps
     }
     __syncthreads();
-    // 1 / pivot
-    double dr = pr[k], di = CPLX ? pi[k] : 0.0, dn = dr * dr + di * di;
-    if (!(dn > 0.0)) { dr = 1.0; di = 0.0; dn = 1.0; }
-    const double ir = dr / dn, ii = -di / dn;
-    // ---- eliminate column k from every row below (bubble rows k+1..nb-1 and interface rows nbp..nbp+ni-1)
-    const int nrows = (nb - k - 1) + ni;
+    // ---- C. trailing update: one sweep, rank-rb
+    const int nrows = (nb - j0) + ni;
     for (int r = warp; r < nrows; r += nw) {
-      const int i = (r < nb - k - 1) ? k + 1 + r : nbp + (r - (nb - k - 1));
+      const int i = (r < nb - j0) ? j0 + r : nbp + (r - (nb - j0));
       double *rr = Ar + (long long)i * M, *ri = Ai + (long long)i * M;
-      const double ar = rr[k], ai = CPLX ? ri[k] : 0.0;
-      const double lr = ar * ir - ai * ii, li = ar * ii + ai * ir;   // l = a(i,k) / pivot
-      if (lr == 0.0 && li == 0.0) continue;
-      for (int j = k + 1 + lane; j < ncol; j += 32) {
+      double lr[RMAX], li[RMAX];
+#pragma unroll
+      for (int t = 0; t < RMAX; t++) { lr[t] = t < rb ? rr[kb + t] : 0.0; li[t] = (CPLX && t < rb) ? ri[kb + t] : 0.0; }
+      for (int j = j0 + lane; j < ncol; j += 32) {
         if (j >= nb && j < nbp) continue;
-        if (CPLX) {
-          rr[j] -= lr * pr[j] - li * pi[j];
-          ri[j] -= lr * pi[j] + li * pr[j];
-        } else rr[j] -= lr * pr[j];
+        double vr = rr[j], vi = CPLX ? ri[j] : 0.0;
+#pragma unroll
+        for (int t = 0; t < RMAX; t++) {
+          if (t < rb) {
+            const double ur = Ur[(size_t)t * M + j], ui = CPLX ? Ui[(size_t)t * M + j] : 0.0;
+            if (CPLX) { vr -= lr[t] * ur - li[t] * ui; vi -= lr[t] * ui + li[t] * ur; }
+            else vr -= lr[t] * ur;
+          }
+        }
+        rr[j] = vr; if (CPLX) ri[j] = vi;
       }
     }
     __syncthreads();

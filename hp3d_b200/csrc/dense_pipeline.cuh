@@ -62,7 +62,11 @@ static void launch_gemm(const GemmArgs &g, int mt, int nt, int batch, cudaStream
 template <bool CPLX> static cudaError_t dense_configure() {
   cudaError_t e = cudaFuncSetAttribute(gemm_nc_kernel<CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<CPLX>());
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(potrf_inv_tile_kernel<CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem_bytes());
+  e = cudaFuncSetAttribute(potrf_inv_tile_kernel<CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem_bytes());
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(stc_gen_kernel<CPLX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess || CPLX) return e;
+  return cudaFuncSetAttribute(stc_gen_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
 // Left-looking blocked Cholesky of the leading `ncol` columns of a lower-trapezoidal row-major matrix with

@@ -374,10 +374,10 @@ static void run_dense_and_scatter(const ChunkShape &sh, Lane &L, const Lane::Out
   }
   if (sh.gen_stc) {   // pivoted-LU condensation: one kernel, writes the caller-layout outputs itself
     const long long P = CPLX ? 2 : 1;
-    stc_gen_kernel<CPLX, RS><<<nel, 512, sizeof(double) * 2 * d.M(), st>>>(L.ws.b.nb_e, d.nbp, L.ws.b.ni_e, d.M(), L.ws.b.Am, (long long)d.a_plane(),
+    stc_gen_kernel<CPLX, RS><<<nel, 512, stc_gen_smem(d.M(), CPLX), st>>>(L.ws.b.nb_e, d.nbp, L.ws.b.ni_e, d.M(), L.ws.b.Am, (long long)d.a_plane(),
                                                                            P * (long long)d.a_plane(), o.Aii, o.Bi, o.AS, o.BS, (long long)d.ni * d.ni,
                                                                            (long long)d.ni, (long long)d.nb * d.ni, (long long)d.nb, want_schur ? 1 : 0,
-                                                                           L.ws.b.info);
+                                                                           L.ws.b.info, stc_gen_block(d.M(), CPLX));
     g_launches++;
     if (ev && ev->on) cudaEventRecord(ev->e[2], st);
     cudaMemcpyAsync(o.info, L.ws.b.info, sizeof(int) * nel, cudaMemcpyDeviceToDevice, st);
