@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(512) stc_gen_kernel(const int *__restrict__ nb
   static_assert(!(CPLX && RS2), "RS2 is a real elimination");
   constexpr int NS = (CPLX || RS2) ? 2 : 1;   // scalars of the OUTPUT value type
   constexpr int RMAX = 8;                     // pivot columns per block (rblk <= RMAX, chosen by the host from the shared-memory budget)
-  extern __shared__ __align__(16) double sh[];   // U block rows: [planes][rblk][M] (the back substitution reuses the first [2][M])
+  extern __shared__ __align__(16) double sh[];   // block rows: [planes][rblk][M]
   __shared__ double red_v[16];
   __shared__ int red_i[16];
   __shared__ int s_piv;
@@ -414,8 +414,7 @@ __global__ void __launch_bounds__(512) stc_gen_kernel(const int *__restrict__ nb
   const int nb = nb_e[e], ni = ni_e[e];
   double *Ar = Am + (long long)e * a_batch, *Ai = Ar + a_plane;
   const int ncol = M, lc = RS2 ? M - 2 : M - 1;   // all columns (padding columns are zero); load column(s) = last padded interface column(s)
-  double *Ur = sh, *Ui = sh + (size_t)rblk * M;   // U block rows, [t][j]
-  double *pr = sh, *pi = sh + M;                  // back substitution: pivot row
+  double *Ur = sh, *Ui = sh + (size_t)rblk * M;   // U block rows (elimination) / X block rows (back substitution), [t][j]
   int bad = 0;
   // Blocked right-looking elimination: the trailing matrix is swept once per block of rblk pivots instead of once per pivot
   // (the unblocked sweep streams it through L2 for every column and is bandwidth-bound there).  Pivoting: partial, over the
@@ -533,30 +532,50 @@ __global__ void __launch_bounds__(512) stc_gen_kernel(const int *__restrict__ nb
   }
   if (tid == 0 && bad && info[e] == 0) info[e] = bad;
   if (!want_schur || nb == 0) return;
-  // ---- back substitution on the bubble rows: X = U_bb^-1 [U_bi | y_b], in place in columns [nbp, ncol)
-  for (int k = nb - 1; k >= 0; k--) {
-    __syncthreads();
-    double dr = Ar[(long long)k * M + k], di = CPLX ? Ai[(long long)k * M + k] : 0.0, dn = dr * dr + di * di;
-    if (!(dn > 0.0)) { dr = 1.0; di = 0.0; dn = 1.0; }
-    const double ir = dr / dn, ii = -di / dn;
-    for (int j = nbp + tid; j < ncol; j += nt) {
-      const double ar = Ar[(long long)k * M + j], ai = CPLX ? Ai[(long long)k * M + j] : 0.0;
-      const double xr = ar * ir - ai * ii, xi = ar * ii + ai * ir;
-      Ar[(long long)k * M + j] = xr; pr[j] = xr;
-      if (CPLX) { Ai[(long long)k * M + j] = xi; pi[j] = xi; }
-    }
-    __syncthreads();
-    for (int i = warp; i < k; i += nw) {
-      double *rr = Ar + (long long)i * M, *ri = Ai + (long long)i * M;
-      const double ur = rr[k], ui = CPLX ? ri[k] : 0.0;
-      if (ur == 0.0 && ui == 0.0) continue;
-      for (int j = nbp + lane; j < ncol; j += 32) {
-        if (CPLX) { rr[j] -= ur * pr[j] - ui * pi[j]; ri[j] -= ur * pi[j] + ui * pr[j]; }
-        else rr[j] -= ur * pr[j];
+  // ---- back substitution on the bubble rows: X = U_bb^-1 [U_bi | y_b], in place in columns [nbp, ncol); blocked like the
+  // elimination: the rblk rows of a block are solved into shared memory, then the rows above are swept once (rank-rb update)
+  __syncthreads();
+  for (int kt = nb; kt > 0; kt -= rblk) {
+    const int kb = max(kt - rblk, 0), rb = kt - kb;
+    for (int t = rb - 1; t >= 0; t--) {   // rows of the block, bottom up; thread-owned columns: no barrier between the t steps
+      const int k = kb + t;
+      double dr = Ar[(long long)k * M + k], di = CPLX ? Ai[(long long)k * M + k] : 0.0, dn = dr * dr + di * di;
+      if (!(dn > 0.0)) { dr = 1.0; di = 0.0; dn = 1.0; }
+      const double ir = dr / dn, ii = -di / dn;
+      for (int j = nbp + tid; j < ncol; j += nt) {
+        double vr = Ar[(long long)k * M + j], vi = CPLX ? Ai[(long long)k * M + j] : 0.0;
+        for (int s2 = t + 1; s2 < rb; s2++) {
+          const double ur = Ar[(long long)k * M + kb + s2], ui = CPLX ? Ai[(long long)k * M + kb + s2] : 0.0;
+          const double xr = Ur[(size_t)s2 * M + j], xi = CPLX ? Ui[(size_t)s2 * M + j] : 0.0;
+          if (CPLX) { vr -= ur * xr - ui * xi; vi -= ur * xi + ui * xr; }
+          else vr -= ur * xr;
+        }
+        const double xr = vr * ir - vi * ii, xi = vr * ii + vi * ir;
+        Ur[(size_t)t * M + j] = xr; Ar[(long long)k * M + j] = xr;
+        if (CPLX) { Ui[(size_t)t * M + j] = xi; Ai[(long long)k * M + j] = xi; }
       }
     }
+    __syncthreads();
+    for (int i = warp; i < kb; i += nw) {   // rows above the block
+      double *rr = Ar + (long long)i * M, *ri = Ai + (long long)i * M;
+      double ur[RMAX], ui[RMAX];
+#pragma unroll
+      for (int t = 0; t < RMAX; t++) { ur[t] = t < rb ? rr[kb + t] : 0.0; ui[t] = (CPLX && t < rb) ? ri[kb + t] : 0.0; }
+      for (int j = nbp + lane; j < ncol; j += 32) {
+        double vr = rr[j], vi = CPLX ? ri[j] : 0.0;
+#pragma unroll
+        for (int t = 0; t < RMAX; t++) {
+          if (t < rb) {
+            const double xr = Ur[(size_t)t * M + j], xi = CPLX ? Ui[(size_t)t * M + j] : 0.0;
+            if (CPLX) { vr -= ur[t] * xr - ui[t] * xi; vi -= ur[t] * xi + ui[t] * xr; }
+            else vr -= ur[t] * xr;
+          }
+        }
+        rr[j] = vr; if (CPLX) ri[j] = vi;
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
   double *oS = AS + (long long)e * sAS * NS, *oT = BS + (long long)e * sBS * NS;
   for (int idx = tid; idx < nb * ni; idx += nt) {
     const int b = idx % nb, c = idx / nb;
