@@ -290,6 +290,10 @@ class ElemEngine:
             nm, nc = len(c["idbc"]), len(c["nextract"])
             mptr[e + 1] = mptr[e] + nm; xptr[e + 1] = xptr[e] + nc
             aptr[e + 1] = aptr[e] + (nc * (nc + 1) // 2 if isym_flag == 1 else nc * nc)
+        if nel and all("cptr" not in c for c in cons):   # regular mesh: the library builds the identity lists itself
+            cat0 = lambda k, dt: np.ascontiguousarray(np.concatenate([np.asarray(c[k]).ravel() for c in cons]), dtype=dt)  # noqa: E731
+            return dict(mptr=mptr, xptr=xptr, aptr=aptr, cptr=None, cidx=None, cval=None, idbc=cat0("idbc", np.int32), zdofd=cat0("zdofd", self.dtype),
+                        nextract=cat0("nextract", np.int32), lcon=cat0("lcon", np.int32) if want_coo else None)
         cptr = np.zeros(mptr[-1] + 1, np.int64)
         base = 0
         for e, c in enumerate(cons):

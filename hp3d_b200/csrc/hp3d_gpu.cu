@@ -679,8 +679,21 @@ int hp3d_gpu_celem_batch(int plan, int nel, const int *etype, const int *norder,
   if ((irn == nullptr) != (jcn == nullptr)) return fail(HP3D_EINVAL, "celem_batch: irn and jcn go together");
   if (irn && (isym_flag == 1 || !lcon)) return fail(HP3D_EINVAL, "celem_batch: IRN/JCN need lcon and an unsymmetric ISYM_FLAG (2 or 3)");
   if (nel == 0) return HP3D_OK;
-  if (nel < 0 || !norder || !norie || !norif || !xnod || !mptr || !cptr || !idbc || !zdofd || !xptr || !zbload || !zastif)
+  if (nel < 0 || !norder || !norie || !norif || !xnod || !mptr || !idbc || !zdofd || !xptr || !zbload || !zastif)
     return fail(HP3D_EINVAL, "celem_batch: null argument");
+  // cptr == NULL: a REGULAR mesh (no constrained dofs): modified dof ll of every element is its element dof ll with coefficient 1
+  std::vector<long long> id_cptr;
+  std::vector<int> id_cidx;
+  std::vector<double> id_cval;
+  if (!cptr) {
+    if (cidx || cval) return fail(HP3D_EINVAL, "celem_batch: cidx / cval without cptr");
+    const long long nm0 = mptr[nel];
+    id_cptr.resize(nm0 + 1); id_cidx.resize(nm0); id_cval.assign(nm0, 1.0);
+    for (long long g = 0; g <= nm0; g++) id_cptr[g] = g;
+    for (int e = 0; e < nel; e++)
+      for (long long g = mptr[e]; g < mptr[e + 1]; g++) id_cidx[g] = (int)(g - mptr[e]) + 1;
+    cptr = id_cptr.data(); cidx = id_cidx.data(); cval = id_cval.data();
+  }
   const bool cplx = p->fp.kind >= HP3D_MAXW_GAL;
   const bool trace = getenv("HP3D_TRACE") != nullptr;
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };

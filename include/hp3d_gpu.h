@@ -156,7 +156,8 @@ long long hp3d_gpu_celem_pack(const hp3d_physics *ph, const int *nrdofl, const i
 
 /* elem + stc_fwd_wrapper + (celem_systemI.F90:543-785) for nel elements.  Descriptors as hp3d_gpu_elem_batch.  Per element e:
  *   mptr[e]..mptr[e+1]   its modified dofs g = mptr[e] + ll - 1   (mptr[nel+1]: prefix sums of Nrdofm)
- *   cptr[g]..cptr[g+1]   entries (cidx 1-based row of Aii, cval) of modified dof g   (cptr[mptr[nel]+1], ABSOLUTE offsets)
+ *   cptr[g]..cptr[g+1]   entries (cidx 1-based row of Aii, cval) of modified dof g   (cptr[mptr[nel]+1], ABSOLUTE offsets);
+ *                        cptr = cidx = cval = NULL: regular mesh, modified dof ll == element dof ll (Nrdofm = ni)
  *   idbc[g], zdofd[g]    IDBC / ZDOFD (value type of the problem; NR_RHS = 1)
  *   xptr[e]..xptr[e+1]   its compressed dofs (prefix sums of Nrdofc);  nextract[] = NEXTRACT (1-based ll), lcon[] = LCON
  *                        (global dof numbers, only read when irn/jcn are requested)

@@ -143,3 +143,31 @@ def test_celem_rejects_bad_indices(oracle, gpu):
     res = eng.celem_batch(no[:0], noe[:0], nof[:0], X[:0], [])      # empty batch
     assert res["info"].size == 0
     eng.close()
+
+
+def test_celem_regular_mesh_without_lists(oracle, gpu):
+    """cptr = NULL: on a regular mesh the caller passes no constraint lists at all; the result equals the explicit identity lists
+    (and is a pure permutation / extraction of the condensed matrices)."""
+    from hp3d_b200 import api
+    O = oracle
+    rng = np.random.default_rng(8)
+    nel = 5
+    et, no, noe, nof, X = _batch(O, rng, 4, [(O.MDLB, uniform_order(2))] * nel)
+    eng = api.ElemEngine(4, omega=2 * np.pi)
+    full = [CU.random_constraints(rng, O, api, 4, no[e], O.MDLB, True, frac_con=0.0, frac_dbc=0.25, extra=0, dof0=1 + 700 * e) for e in range(nel)]
+    # make the explicit lists the identity (random_constraints permutes): modified dof ll <- element dof ll
+    for c in full:
+        n = len(c["idbc"])
+        c["cptr"] = np.arange(n + 1, dtype=np.int64); c["cidx"] = np.arange(1, n + 1, dtype=np.int32); c["cval"] = np.ones(n)
+    bare = [{k: v for k, v in c.items() if k not in ("cptr", "cidx", "cval")} for c in full]
+    a = eng.celem_batch(no, noe, nof, X, full, isym_flag=2, want_coo=True)
+    b = eng.celem_batch(no, noe, nof, X, bare, isym_flag=2, want_coo=True)
+    for k in ("zbload", "zastif", "irn", "jcn"):
+        assert np.array_equal(a[k], b[k]), k
+    ref = eng.elem_stc_batch(no, noe, nof, X)
+    for e in range(nel):
+        Aii, Bi, _, _ = eng.unpack(ref, e)
+        x = full[e]["nextract"] - 1
+        if not full[e]["idbc"].any():
+            assert np.array_equal(b["zastif"][b["aptr"][e]:b["aptr"][e + 1]].reshape(len(x), len(x)), Aii[np.ix_(x, x)])
+    eng.close()
