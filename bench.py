@@ -191,6 +191,26 @@ def claim_stdout():
     return real
 
 
+def bind_to_gpu_numa(gpu_index):
+    """Pin this rank's host threads to the CPUs next to its GPU (NVML's affinity mask) BEFORE any pinned allocation, so that the
+    result buffers live on the GPU's NUMA node: with several ranks per host the D2H copies otherwise cross the socket
+    interconnect.  (What `mpirun --bind-to` / numactl does for the reference's MPI ranks.)  Returns the CPU list or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return allowed
+    except Exception:
+        pass
+    return None
+
+
 def main():
     out_stream = claim_stdout()
     ap = argparse.ArgumentParser()
@@ -213,6 +233,7 @@ def main():
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
+    numa_cpus = bind_to_gpu_numa(local) if world > 1 and not os.environ.get("HP3D_NO_NUMA_BIND") else None
     if world > 1:
         import torch
         import torch.distributed as dist
@@ -287,7 +308,8 @@ def main():
         es = 16 if args.kind >= 3 else 8
         e2e = {"value": world * Be * args.steps / te, "unit": "elements/s", "elements_per_gpu_per_step": Be,
                "h2d_bytes_per_step": int(xs.a.nbytes), "d2h_bytes_per_step": int(Be * (es * (ni * ni + ni + nb * ni + nb) + 4)),
-               "timer": "host wall clock around the synchronous C-ABI calls (they return after the last D2H)"}
+               "timer": "host wall clock around the synchronous C-ABI calls (they return after the last D2H)",
+               "host_binding": f"rank bound to the {len(numa_cpus)} CPUs NVML lists for its GPU" if numa_cpus else "none"}
         # ---- optional: the same step with celem_systemI's transform / compression / COO indices fused in (hp3d_gpu_celem_batch)
         celem = None
         if args.celem:
