@@ -1,6 +1,6 @@
 #!/bin/bash
-# real-form pipeline (default): launch list with DRAM traffic (one 32-element chunk) + full ncu captures of the real GEMM, the
-# hexahedron integration kernel and the real potrf tile kernel; summaries are post-processed into profiles/ by tools/summarize_ncu.py
+# real-form pipeline (default): launch list with DRAM traffic (one 32-element chunk) + full ncu captures of the real GEMM
+# (argument "all": also the hexahedron integration kernel and the real potrf tile kernel)
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/r01_rs_launches_traffic_b32.csv \
     python bench.py --steps 1 --warmup 3 --elements 32 --no-cpu --no-e2e > gpurun_out/ncu_rs_launch.log 2>&1
@@ -13,6 +13,7 @@ run() { # name regex skip count
   head -c 600 gpurun_out/r01_$1_ncu_full_summary.csv; echo
 }
 run gemm_real gemm_nc 864 12
-run tp3_rs tp3_kernel 8 1
-run potrf_real potrf_inv 330 3
-ls -la gpurun_out | tail -8
+if [ "$1" = "all" ]; then
+  run tp3_rs tp3_kernel 8 1
+  run potrf_real potrf_inv 330 3
+fi
