@@ -12,7 +12,9 @@
  *   - trunk/test/poly_maxw.F90:101  (polynomial E reproduced to 1e-14, complex);
  *   - BLAS3 `elem_opt` == scalar-loop `elem_*` twins, exact-sequence identities;
  *   - celem.c (constraints/compression): identity case, C^T A C algebra, u = xyz on a mesh with hanging nodes;
- *   - soleval.c (soleval/element_error): closed-form norms of the manufactured solutions, exactly reproduced polynomials.
+ *   - soleval.c (soleval/element_error): closed-form norms of the manufactured solutions, exactly reproduced polynomials;
+ *   - pbi.c (projection-based interpolation): polynomial reproduction (what poly_pois.F90 asserts through update_gdof/update_Ddof),
+ *     zero higher-order dofs of a trilinear map, identical dofs on entities shared by neighbours.
  * DPG element matrices, Cholesky condensation and p>=3 are "parity unpinned" by the reference's own
  * tests; the oracle adds the self-consistency pins listed above.
  *
@@ -243,6 +245,19 @@ void orc_exact_field(int kind, const orc_params *prm, const double x[3], zdouble
 int orc_element_error(int et, int kind, const int *norder, const int *norie, const int *norif, const double *xnod, const zdouble *zdof,
                       const orc_params *prm, const zdouble *exact_tab, int l2proj, double *err, double *rnorm);
 int orc_error_points(int et, const int *norder, const int *norie, const int *norif, const double *xnod, double *xq);
+
+/* ---- H1 projection-based interpolation (pbi.c): hpvert/hpedge/hpface_opt/hpmdle_opt (geometry dofs, INTEGRATION = 0) and
+ * dhpvert/dhpedgeH/dhpfaceH_opt (H1 Dirichlet dofs, INTEGRATION = 1); SURVEY 8f row f4, interpolation half.
+ * f(eta, val[ncomp], dval[ncomp*3], ctx): the interpolated function and its gradient in the reference coordinates eta
+ * (dval[c + ncomp*i] = d g_c / d eta_i).  etav (3, nrv): reference coordinates of the element's vertices.
+ * dof (ncomp, nrdofH), component fastest; nodes are numbered vertices, edges, faces, middle (bit i of mask = node i). */
+typedef void (*orc_pbi_fn)(const double *eta, double *val, double *dval, void *ctx);
+void orc_edge_param(int et, int ie, double t, double xi[3], double dxidt[3]);
+void orc_pbi_offsets(int et, const int *norder, int *off);
+int orc_pbi_node(int et, const int *norder, const int *norie, const int *norif, const double *etav, int ncomp, int integration,
+                 int maxp, int node, orc_pbi_fn f, void *ctx, double *dof);
+int orc_pbi_element(int et, const int *norder, const int *norie, const int *norif, const double *etav, int ncomp, int integration,
+                    int maxp, unsigned mask, orc_pbi_fn f, void *ctx, double *dof);
 
 #ifdef __cplusplus
 }

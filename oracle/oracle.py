@@ -26,7 +26,7 @@ class Params(C.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, "libhp3d_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("shape.c", "shape_prism.c", "quad_geom.c", "etype.c", "tri_rules.h", "dense.c", "elem.c", "celem.c", "soleval.c", "hp3d_oracle.h", "dense.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("shape.c", "shape_prism.c", "quad_geom.c", "etype.c", "tri_rules.h", "dense.c", "elem.c", "celem.c", "soleval.c", "pbi.c", "hp3d_oracle.h", "dense.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "libhp3d_oracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -394,3 +394,37 @@ def exact_field(kind, prm, x):
     x = np.ascontiguousarray(x, dtype=np.float64)
     lib().orc_exact_field(int(kind), C.byref(prm), _d(x), _d(v))
     return v
+
+
+# ---- H1 projection-based interpolation (pbi.c): hpvert/hpedge/hpface_opt/hpmdle_opt, dhpvert/dhpedgeH/dhpfaceH_opt ------------
+PBI_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+
+
+def pbi_offsets(norder, etype=MDLB):
+    """offsets of the nodes' H1 dofs (vertices, edges, faces, middle) + total"""
+    off = np.zeros(32, np.int32)
+    lib().orc_pbi_offsets(int(etype), _i(_pad(norder, 19)), _i(off))
+    nn = (6 + 9 + 5 + 1) if etype == MDLP else 27
+    return off[:nn + 1].copy()
+
+
+def pbi_element(norder, norie, norif, etav, fun, ncomp, integration=0, maxp=9, mask=None, dof=None, etype=MDLB):
+    """PB interpolation of fun(eta) -> (val[ncomp], dval[ncomp, 3]) on one element; returns dof (nrdofH, ncomp)."""
+    norder, norie, norif = _pad(norder, 19), _pad(norie, 12), _pad(norif, 6)
+    etav = np.ascontiguousarray(etav, dtype=np.float64)
+    off = pbi_offsets(norder, etype)
+    nn = off.size - 1
+    out = np.zeros((int(off[-1]), ncomp)) if dof is None else np.ascontiguousarray(dof, dtype=np.float64).copy()
+    mask = (1 << nn) - 1 if mask is None else int(mask)
+
+    def cb(eta, val, dval, ctx):
+        v, dv = fun(np.array([eta[0], eta[1], eta[2]]))
+        v = np.atleast_1d(v); dv = np.asarray(dv).reshape(ncomp, 3)
+        for c in range(ncomp):
+            val[c] = v[c]
+            for i in range(3):
+                dval[c + ncomp * i] = dv[c, i]
+    r = lib().orc_pbi_element(int(etype), _i(norder), _i(norie), _i(norif), _d(etav), int(ncomp), int(integration), int(maxp),
+                              C.c_uint(mask), PBI_FN(cb), None, _d(out))
+    assert r == 0, r
+    return out

@@ -1,0 +1,196 @@
+/*
+ * pbi.c -- CPU restatement ("oracle") of hp3D's H1 projection-based interpolation (interpolation half):
+ *   geometry dofs (update_gdof)         trunk/src/hpinterp/hpvert.F90:19, hpedge.F90:27, hpface_opt.F90:27, hpmdle_opt.F90:23
+ *   H1 Dirichlet dofs (update_Ddof)     trunk/src/hpinterp/dhpvert.F90:26, edge/dhpedgeH.F90:32, face/dhpfaceH_opt.F90:32
+ * The two families are the same algorithm: the interpolated function g (the GMP map x(eta), 3 components, or the
+ * Dirichlet datum u(x(eta)), NREQNH components) is given by a callback returning its value and its gradient with respect
+ * to the REFERENCE coordinates eta of the GMP block (dxdeta, resp. zdvalH * dxdeta, dhpfaceH_opt.F90:206-212); the
+ * projections are done in eta (hpmdle_opt.F90:5-6), eta(xi) being the trilinear / linear-prism map through the element's
+ * vertex reference coordinates Etav (refgeom3D, trunk/src/element/util/geom3D.F90:235-305).  The geometry routines
+ * integrate with INTEGRATION = 0, the Dirichlet routines with INTEGRATION = 1 (dhpedgeH.F90:145, dhpfaceH_opt.F90:173).
+ * TEST INFRASTRUCTURE ONLY (see hp3d_oracle.h).
+ *
+ * Pins (tests/test_pbi_oracle.py): the reference's test-suite holds no numeric vectors for src/hpinterp; what
+ * trunk/test/poly_pois.F90 asserts through update_gdof + update_Ddof is polynomial reproduction, pinned here directly:
+ * a function of the element's polynomial space is reproduced exactly (dofs evaluated back through shape3DH), a trilinear
+ * map has zero higher-order dofs, and neighbours sharing a face obtain identical dofs for the shared entities.
+ */
+#include "dense.h"
+#include "hp3d_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+static const double BRICK_COORD[8][3] = {{0,0,0},{1,0,0},{1,1,0},{0,1,0},{0,0,1},{1,0,1},{1,1,1},{0,1,1}};
+static const int BRICK_EDGE_TO_VERT[12][2] = {{1,2},{2,3},{4,3},{1,4},{5,6},{6,7},{8,7},{5,8},{1,5},{2,6},{3,7},{4,8}};
+static const double PRISM_COORD[6][3] = {{0,0,0},{1,0,0},{0,1,0},{0,0,1},{1,0,1},{0,1,1}};
+static const int PRISM_EDGE_TO_VERT[9][2] = {{1,2},{2,3},{1,3},{4,5},{5,6},{4,6},{1,4},{2,5},{3,6}};
+
+/* element_data.F90:508-549 ; ie is 1-based */
+void orc_edge_param(int et, int ie, double t, double xi[3], double dxidt[3]) {
+  const double *x1, *x2;
+  if (et == ORC_MDLP) { x1 = PRISM_COORD[PRISM_EDGE_TO_VERT[ie - 1][0] - 1]; x2 = PRISM_COORD[PRISM_EDGE_TO_VERT[ie - 1][1] - 1]; }
+  else { x1 = BRICK_COORD[BRICK_EDGE_TO_VERT[ie - 1][0] - 1]; x2 = BRICK_COORD[BRICK_EDGE_TO_VERT[ie - 1][1] - 1]; }
+  for (int c = 0; c < 3; c++) { dxidt[c] = x2[c] - x1[c]; xi[c] = x1[c] + t * dxidt[c]; }
+}
+
+/* refgeom3D, geom3D.F90:235-305: eta = sum_v Etav_v phi_v over the nrv VERTEX functions */
+static void refgeom3D(const double *etav, const double *shapH, const double *gradH, int nrv, double eta[3], double detadxi[9],
+                      double dxideta[9], double *rjac, int *iflag) {
+  for (int c = 0; c < 3; c++) eta[c] = 0.0;
+  for (int i = 0; i < 9; i++) detadxi[i] = 0.0;
+  for (int k = 0; k < nrv; k++)
+    for (int c = 0; c < 3; c++) {
+      eta[c] += etav[c + 3 * k] * shapH[k];
+      for (int m = 0; m < 3; m++) detadxi[c + 3 * m] += etav[c + 3 * k] * gradH[m + 3 * k];
+    }
+  orc_geom(detadxi, dxideta, rjac, iflag);
+}
+
+/* offsets of the nodes' H1 dofs inside the element's dof list (vertices, edges, faces, middle): celndof.F90:24 */
+void orc_pbi_offsets(int et, const int *norder, int *off /*nrv+nre+nrf+1 entries + total*/) {
+  const int nrv = orc_nvert(et), nre = orc_nedge(et), nrf = orc_nface(et);
+  int n = 0, k = 0, h, e, v, q;
+  for (int i = 0; i < nrv; i++) { off[k++] = n; n += 1; }
+  for (int i = 0; i < nre; i++) { off[k++] = n; n += norder[i] - 1; }
+  for (int i = 0; i < nrf; i++) { off[k++] = n; orc_ndof_nod_face(et, i + 1, norder[nre + i], &h, &e, &v, &q); n += h; }
+  off[k++] = n; orc_ndof_nod_mid(et, norder[nre + nrf], &h, &e, &v, &q); n += h;
+  off[k] = n;
+}
+
+/* One node of the element.  node: 0..nrv-1 vertices, then edges, faces, middle (the element's nodesl order).
+ * dof: (ncomp, nrdofH) component fastest, full-element numbering; the lower-dimensional nodes' entries are read, the node's
+ * own entries are written. */
+int orc_pbi_node(int et, const int *norder, const int *norie, const int *norif, const double *etav, int ncomp, int integration,
+                 int maxp, int node, orc_pbi_fn f, void *ctx, double *dof) {
+  const int nrv = orc_nvert(et), nre = orc_nedge(et), nrf = orc_nface(et);
+  int off[32];
+  orc_pbi_offsets(et, norder, off);
+  const int n = off[node + 1] - off[node], t0 = off[node];
+  double *val = malloc(sizeof(double) * ncomp), *dval = malloc(sizeof(double) * 3 * ncomp);
+  if (node < nrv) { /* hpvert.F90:19-45, dhpvert.F90:60-75 */
+    f(etav + 3 * node, val, dval, ctx);
+    for (int c = 0; c < ncomp; c++) dof[c + ncomp * t0] = val[c];
+    free(val); free(dval);
+    return 0;
+  }
+  if (n <= 0) { free(val); free(dval); return 0; }
+  double *shapH = malloc(sizeof(double) * ORC_MAXBRICK_H), *gradH = malloc(sizeof(double) * 3 * ORC_MAXBRICK_H);
+  double *aa = calloc((size_t)n * n, sizeof(double)), *bb = calloc((size_t)n * ncomp, sizeof(double));
+  int nord1[19], zero6[6] = {0, 0, 0, 0, 0, 0}, info = 0;
+  int nint = 0;
+  double *pts = malloc(sizeof(double) * 3 * 1000), *wts = malloc(sizeof(double) * 1000);
+  double *atest = NULL;
+  const int kind = node < nrv + nre ? 1 : (node < nrv + nre + nrf ? 2 : 3);
+  int nknown; /* dofs of the lower-dimensional nodes that are subtracted */
+  if (kind == 1) { /* hpedge.F90:111-117 */
+    const int ie = node - nrv + 1;
+    orc_initiate_order(et, nord1);
+    nord1[ie - 1] = norder[ie - 1];
+    int na = norder[ie - 1] + integration; if (na > maxp) na = maxp;   /* set_1D_int.F90:40-43 */
+    nint = na + 1;
+    orc_gauss1(nint, pts, wts);
+    nknown = nrv;
+  } else if (kind == 2) { /* hpface_opt.F90:126-146 */
+    const int jf = node - nrv - nre + 1;
+    int nordf[5];
+    orc_initiate_order(et, nord1);
+    for (int i = 0; i < nre; i++) nord1[i] = norder[i];
+    nord1[nre + jf - 1] = norder[nre + jf - 1];
+    orc_face_order(et, jf, norder, nordf);
+    nint = orc_set_2D_int(orc_face_is_tri(et, jf), nordf, 0, integration, maxp, pts, wts);
+    nknown = off[nrv + nre];
+  } else { /* hpmdle_opt.F90:117-121 */
+    for (int i = 0; i < nre + nrf + 1; i++) nord1[i] = norder[i];
+    nint = orc_set_3D_int(et, norder, zero6, integration, maxp, pts, wts);
+    nknown = off[nrv + nre + nrf];
+  }
+  if (kind >= 2) atest = malloc(sizeof(double) * (size_t)n * 3 * nint);
+  for (int l = 0; l < nint; l++) {
+    double xi[3], dxidt[6], eta[3], detadxi[9], dxideta[9], rjac, weight = 0, rt[3] = {0, 0, 0}, rn[3] = {0, 0, 0};
+    int iflag;
+    if (kind == 1) orc_edge_param(et, node - nrv + 1, pts[l], xi, dxidt);
+    else if (kind == 2) orc_face_param(et, node - nrv - nre + 1, pts + 2 * l, xi, dxidt);
+    else for (int c = 0; c < 3; c++) xi[c] = pts[3 * l + c];
+    int nrdofH = orc_shape3DH(et, xi, nord1, norie, norif, shapH, gradH);
+    refgeom3D(etav, shapH, gradH, nrv, eta, detadxi, dxideta, &rjac, &iflag);
+    if (iflag != 0) info = -1;
+    if (kind == 1) { /* hpedge.F90:134-142 */
+      double bjac = 0;
+      for (int c = 0; c < 3; c++) { rt[c] = detadxi[c] * dxidt[0] + detadxi[c + 3] * dxidt[1] + detadxi[c + 6] * dxidt[2]; bjac += rt[c] * rt[c]; }
+      bjac = sqrt(bjac);
+      for (int c = 0; c < 3; c++) rt[c] /= bjac;
+      weight = wts[l] * bjac;
+    } else if (kind == 2) { /* brefgeom3D, geom3D.F90:343-393 */
+      double d[6], bjac;
+      for (int i = 0; i < 2; i++)
+        for (int c = 0; c < 3; c++) d[c + 3 * i] = detadxi[c] * dxidt[3 * i] + detadxi[c + 3] * dxidt[3 * i + 1] + detadxi[c + 6] * dxidt[3 * i + 2];
+      rn[0] = d[1] * d[5] - d[2] * d[4]; rn[1] = d[2] * d[3] - d[0] * d[5]; rn[2] = d[0] * d[4] - d[1] * d[3];
+      bjac = sqrt(rn[0] * rn[0] + rn[1] * rn[1] + rn[2] * rn[2]);
+      const int ns = orc_nsign_param(et, node - nrv - nre + 1);
+      for (int c = 0; c < 3; c++) rn[c] = rn[c] * ns / bjac;
+      weight = wts[l] * bjac;
+    } else weight = wts[l] * rjac;
+    f(eta, val, dval, ctx); /* dval(c, i) = d g_c / d eta_i, c fastest */
+    /* remove the lower-dimensional nodes' contributions (hpedge.F90:160-172, hpface_opt.F90:181-193, hpmdle_opt.F90:150-162);
+     * in the reduced-order element the known functions keep their positions, the node's own functions come last */
+    const int own0 = nrdofH - n;
+    for (int k = 0; k < own0; k++) {
+      double du[3];
+      for (int i = 0; i < 3; i++) du[i] = gradH[3 * k] * dxideta[3 * i] + gradH[1 + 3 * k] * dxideta[1 + 3 * i] + gradH[2 + 3 * k] * dxideta[2 + 3 * i];
+      for (int i = 0; i < 3; i++)
+        for (int c = 0; c < ncomp; c++) dval[c + ncomp * i] -= dof[c + ncomp * k] * du[i];
+    }
+    if (own0 != nknown) info = -2;
+    for (int j = 0; j < n; j++) {
+      const int kj = own0 + j;
+      double dv[3], prod = 0;
+      for (int i = 0; i < 3; i++) dv[i] = gradH[3 * kj] * dxideta[3 * i] + gradH[1 + 3 * kj] * dxideta[1 + 3 * i] + gradH[2 + 3 * kj] * dxideta[2 + 3 * i];
+      if (kind == 1) { for (int i = 0; i < 3; i++) prod += dv[i] * rt[i]; for (int i = 0; i < 3; i++) dv[i] = prod * rt[i]; }
+      if (kind == 2) { for (int i = 0; i < 3; i++) prod += dv[i] * rn[i]; for (int i = 0; i < 3; i++) dv[i] -= prod * rn[i]; }
+      for (int c = 0; c < ncomp; c++)
+        bb[j + n * c] += (dval[c] * dv[0] + dval[c + ncomp] * dv[1] + dval[c + 2 * ncomp] * dv[2]) * weight;
+      if (kind == 1) { /* hpedge.F90:197-210: full gradient of the trial function against the projected test gradient */
+        for (int i = 0; i < n; i++) {
+          const int ki = own0 + i;
+          double du[3];
+          for (int m = 0; m < 3; m++) du[m] = gradH[3 * ki] * dxideta[3 * m] + gradH[1 + 3 * ki] * dxideta[1 + 3 * m] + gradH[2 + 3 * ki] * dxideta[2 + 3 * m];
+          aa[j + n * i] += (dv[0] * du[0] + dv[1] * du[1] + dv[2] * du[2]) * weight;
+        }
+      } else { /* hpface_opt.F90:212, hpmdle_opt.F90:181 */
+        const double sw = sqrt(weight);
+        for (int i = 0; i < 3; i++) atest[j + (size_t)n * (3 * l + i)] = dv[i] * sw;
+      }
+    }
+  }
+  if (kind == 1) { /* dgetrf + dlaswp + 2 x dtrsm, hpedge.F90:236-248 */
+    int *ipiv = malloc(sizeof(int) * n);
+    if (orc_dgetrf(n, aa, n, ipiv) != 0) info = 1;
+    else orc_dgetrs(n, ncomp, aa, n, ipiv, bb, n);
+    free(ipiv);
+  } else { /* DSFRK + DPFTRF + DPFTRS (hpface_opt.F90:219-247): the RFP storage is a layout, the algebra is syrk + potrf + potrs */
+    orc_dsyrk_u('N', n, 3 * nint, 1.0, atest, n, 0.0, aa, n);
+    if (orc_dpotrf_u(n, aa, n) != 0) info = 1;
+    else { orc_dtrsm_u('T', n, ncomp, aa, n, bb, n); orc_dtrsm_u('N', n, ncomp, aa, n, bb, n); }
+  }
+  if (info == 0)
+    for (int j = 0; j < n; j++)
+      for (int c = 0; c < ncomp; c++) dof[c + ncomp * (t0 + j)] = bb[j + n * c];
+  free(val); free(dval); free(shapH); free(gradH); free(aa); free(bb); free(pts); free(wts); free(atest);
+  return info;
+}
+
+/* The element's nodes in the order update_gdof / update_Ddof visit them (vertices, then edges, then faces, then the middle
+ * node: update_gdof.F90 loops by node type in that order so that each projection finds the lower-dimensional dofs ready).
+ * mask bit i selects node i; unselected nodes keep the entries of `dof` they came with. */
+int orc_pbi_element(int et, const int *norder, const int *norie, const int *norif, const double *etav, int ncomp, int integration,
+                    int maxp, unsigned mask, orc_pbi_fn f, void *ctx, double *dof) {
+  const int nn = orc_nvert(et) + orc_nedge(et) + orc_nface(et) + 1;
+  for (int node = 0; node < nn; node++)
+    if (mask & (1u << node)) {
+      int rc = orc_pbi_node(et, norder, norie, norif, etav, ncomp, integration, maxp, node, f, ctx, dof);
+      if (rc) return rc;
+    }
+  return 0;
+}

@@ -1,0 +1,114 @@
+"""Pins of the projection-based interpolation oracle (oracle/pbi.c = hpvert / hpedge / hpface_opt / hpmdle_opt and
+dhpvert / dhpedgeH / dhpfaceH_opt).  The reference's tests hold no numeric vectors for src/hpinterp;
+trunk/test/poly_pois.F90 exercises update_gdof + update_Ddof and asserts that a polynomial is reproduced -- pinned here
+directly, together with the conformity that the node-by-node construction of update_gdof relies on (the dofs of a shared
+vertex / edge / face are the same whichever adjacent element computes them)."""
+import numpy as np
+import pytest
+
+from hp3d_b200 import synth
+from tests.mini_fem_hp import build_space
+
+MDLB, MDLP = 1, 3
+
+
+def poly(eta):
+    x, y, z = eta
+    v = np.array([1.0 + 0.5 * x - y + x * x + 2.0 * y * z - x * z + 0.25 * z * z,
+                  x * y * z - 0.3 * z * z + y,
+                  2.0 - x + 0.7 * x * y])
+    d = np.array([[0.5 + 2 * x - z, -1.0 + 2 * z, 2 * y - x + 0.5 * z],
+                  [y * z, x * z + 1.0, x * y - 0.6 * z],
+                  [-1.0 + 0.7 * y, 0.7 * x, 0.0]])
+    return v, d
+
+
+def smooth(eta):
+    x, y, z = eta
+    v = np.array([np.sin(1.3 * x + 0.4) * np.cos(0.9 * y) * np.exp(0.5 * z), x + np.sin(2.0 * y * z)])
+    d = np.array([[1.3 * np.cos(1.3 * x + 0.4) * np.cos(0.9 * y) * np.exp(0.5 * z),
+                   -0.9 * np.sin(1.3 * x + 0.4) * np.sin(0.9 * y) * np.exp(0.5 * z),
+                   0.5 * np.sin(1.3 * x + 0.4) * np.cos(0.9 * y) * np.exp(0.5 * z)],
+                  [1.0, 2.0 * z * np.cos(2.0 * y * z), 2.0 * y * np.cos(2.0 * y * z)]])
+    return v, d
+
+
+def _eval(oracle, et, no, noe, nof, dof, etav, xi):
+    s, _ = oracle.shape3DH(xi, no, noe, nof, et)
+    nv = 8 if et == MDLB else 6
+    return s @ dof, s[:nv] @ etav
+
+
+@pytest.mark.parametrize("integration", [0, 1])
+def test_polynomial_reproduction_brick(oracle, integration):
+    """degree <= 2 per variable (3 for xyz): reproduced by any brick whose nodes all have order >= 3, any orientation,
+    on an axis-aligned sub-box of the reference block (a refined element's Etav)"""
+    oracle.set_maxp(9)
+    rng = np.random.default_rng(3)
+    box0, box1 = np.array([0.25, 0.0, 0.5]), np.array([0.75, 0.5, 1.0])
+    M = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    etav = box0 + M * (box1 - box0)
+    for trial in range(3):
+        no = np.array(list(rng.integers(3, 6, 12)) + [10 * int(rng.integers(3, 6)) + int(rng.integers(3, 6)) for _ in range(6)]
+                      + [100 * int(rng.integers(3, 6)) + 10 * int(rng.integers(3, 6)) + int(rng.integers(3, 6))], np.int32)
+        noe = rng.integers(0, 2, 12).astype(np.int32); nof = rng.integers(0, 8, 6).astype(np.int32)
+        dof = oracle.pbi_element(no, noe, nof, etav, poly, 3, integration=integration)
+        for _ in range(20):
+            xi = rng.random(3)
+            u, eta = _eval(oracle, MDLB, no, noe, nof, dof, etav, xi)
+            assert np.abs(u - poly(eta)[0]).max() < 1e-13
+
+
+def test_polynomial_reproduction_prism(oracle):
+    oracle.set_maxp(9)
+    rng = np.random.default_rng(4)
+    etav = np.array([[0.2, 0.1, 0.0], [0.9, 0.2, 0.0], [0.3, 0.8, 0.0], [0.2, 0.1, 0.6], [0.9, 0.2, 0.6], [0.3, 0.8, 0.6]])
+    for trial in range(3):
+        p, pz = int(rng.integers(3, 6)), int(rng.integers(3, 6))
+        no = np.array([p] * 6 + [pz] * 3 + [p, p] + [10 * p + pz] * 3 + [10 * p + pz], np.int32)
+        noe = rng.integers(0, 2, 9).astype(np.int32)
+        nof = np.array(list(rng.integers(0, 6, 2)) + list(rng.integers(0, 8, 3)), np.int32)
+        dof = oracle.pbi_element(no, noe, nof, etav, poly, 3, etype=MDLP)
+        for _ in range(20):
+            xi = rng.random(3)
+            if xi[0] + xi[1] > 1:
+                xi[:2] = 1 - xi[:2]
+            u, eta = _eval(oracle, MDLP, no, noe, nof, dof, etav, xi)
+            assert np.abs(u - poly(eta)[0]).max() < 1e-13
+
+
+def test_trilinear_map_has_no_higher_order_dofs(oracle):
+    """update_gdof on an element of a trilinear GMP block: x(eta) trilinear => edge / face / middle dofs vanish"""
+    oracle.set_maxp(9)
+    A = np.array([[1.0, 0.2, 0.0], [0.1, 1.5, 0.3], [0.0, -0.2, 0.8]])
+
+    def tri(eta):
+        x, y, z = eta
+        v = A @ eta + np.array([0.3 * x * y, 0.2 * y * z, 0.1 * x * y * z])
+        d = A + np.array([[0.3 * y, 0.3 * x, 0.0], [0.0, 0.2 * z, 0.2 * y], [0.1 * y * z, 0.1 * x * z, 0.1 * x * y]])
+        return v, d
+    no = synth.uniform_order(4)
+    M = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    dof = oracle.pbi_element(no, np.zeros(12, np.int32), np.zeros(6, np.int32), M, tri, 3)
+    assert np.abs(dof[8:]).max() < 1e-14
+    assert np.abs(dof[:8] - np.array([tri(m)[0] for m in M])).max() == 0.0
+
+
+def test_shared_entities_get_identical_dofs(oracle):
+    """a smooth (non-polynomial) function on a mixed hexa/prism hp mesh: dofs with the same global key coincide"""
+    oracle.set_maxp(9)
+    m = synth.hp_mesh(2, prism_frac=0.45, pmin=2, pmax=4, seed_p=11, seed_g=5)
+    keys, l2g, nloc, _, _ = build_space(m)
+    U = np.full((len(keys), 2), np.nan)
+    worst, shared = 0.0, 0
+    for e in range(len(m["etype"])):
+        et = int(m["etype"][e]); nv = 8 if et == MDLB else 6
+        dof = oracle.pbi_element(m["norder"][e], m["norient_edge"][e], m["norient_face"][e], m["xnod"][e, :nv], smooth, 2,
+                                 integration=1, etype=et)
+        for k, g in enumerate(l2g[e]):
+            if np.isnan(U[g, 0]):
+                U[g] = dof[k]
+            else:
+                worst = max(worst, float(np.abs(U[g] - dof[k]).max())); shared += 1
+    assert shared > 50
+    assert worst < 1e-12
