@@ -379,3 +379,55 @@ class ElemEngine:
         _lib.check(self.L.hp3d_gpu_bench_t(self.plan, nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(xnod[0].size), int(reps),
                                          int(max_chunk), int(lanes), C.byref(t[0]), C.byref(t[1]), C.byref(t[2]), C.byref(ln)))
         return dict(ms_total=t[0].value, ms_integ=t[1].value, ms_dense=t[2].value, launches=ln.value)
+
+
+# ---- H1 projection-based interpolation: update_gdof / update_Ddof (src/hpinterp), SURVEY 8f row f4 -----------------------------
+def _pbi_descr(norder, norient_edge, norient_face, etype):
+    norder = _i32(norder).reshape(-1, 19); noe = _i32(norient_edge).reshape(-1, 12); nof = _i32(norient_face).reshape(-1, 6)
+    nel = norder.shape[0]
+    et = None if etype is None else _i32(np.broadcast_to(np.asarray(etype, np.int32), (nel,)))
+    return norder, noe, nof, nel, et
+
+
+def pbi_points(norder, norient_edge, norient_face, integration=0, maxp=9, etype=None):
+    """Where the host evaluates the interpolated function (hp3d_gpu_pbi_points; host only, no GPU needed).
+    Returns dict(xi (nel, npts_max, 3) master coordinates, npts (nel,), nrdofH (nel,), nodes (nel, 27, 4) = first dof, # dofs,
+    first point, # points of every node (vertices, edges, faces, middle))."""
+    norder, noe, nof, nel, et = _pbi_descr(norder, norient_edge, norient_face, etype)
+    L = _lib.lib()
+    f = L.hp3d_gpu_pbi_points
+    f.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p, C.c_longlong] + [C.c_void_p] * 3
+    npts = np.zeros(nel, np.int32); nH = np.zeros(nel, np.int32); nodes = np.zeros((nel, 27, 4), np.int32)
+    _lib.check(f(nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), int(integration), int(maxp), None, 0, _ptr(npts), _ptr(nH), _ptr(nodes)))
+    xi = np.zeros((nel, int(npts.max()) if nel else 0, 3))
+    _lib.check(f(nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), int(integration), int(maxp), _ptr(xi), int(np.prod(xi.shape[1:])), None, None, None))
+    return dict(xi=xi, npts=npts, nrdofH=nH, nodes=nodes)
+
+
+def pbi_h1_batch(norder, norient_edge, norient_face, etav, fvert, fgrad, integration=0, maxp=9, mask=None, dof=None, etype=None, device=0):
+    """hpvert/hpedge/hpface_opt/hpmdle_opt (integration=0, the GMP map) or dhpvert/dhpedgeH/dhpfaceH_opt (integration=1, Dirichlet
+    data) for all elements at once (hp3d_gpu_pbi_h1_batch).
+    etav (nel, 8, 3); fvert (nel, 8, ncomp); fgrad (nel, npts_max, 3, ncomp) = d g_c / d eta_i at `pbi_points`; mask (nel,) node bits
+    or None; dof (nel, nrdofH_max, ncomp) incoming dofs of the unselected nodes or None.  Returns dict(dof, info)."""
+    norder, noe, nof, nel, et = _pbi_descr(norder, norient_edge, norient_face, etype)
+    L = _lib.lib()
+    _lib.check(L.hp3d_gpu_init(int(device)))
+    etav = np.ascontiguousarray(etav, dtype=np.float64).reshape(nel, 8, 3)
+    fvert = np.ascontiguousarray(fvert, dtype=np.float64)
+    ncomp = int(fvert.shape[-1])
+    fvert = fvert.reshape(nel, 8, ncomp)
+    fgrad = np.ascontiguousarray(fgrad, dtype=np.float64).reshape(nel, -1, 3, ncomp)
+    nH = np.zeros(nel, np.int32)
+    fp = L.hp3d_gpu_pbi_points
+    fp.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p, C.c_longlong] + [C.c_void_p] * 3
+    _lib.check(fp(nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), int(integration), int(maxp), None, 0, None, _ptr(nH), None))
+    nHmax = int(nH.max()) if nel else 0
+    out = np.zeros((nel, nHmax, ncomp)) if dof is None else np.ascontiguousarray(dof, dtype=np.float64).reshape(nel, -1, ncomp).copy()
+    m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint32)
+    info = np.zeros(nel, np.int32)
+    f = L.hp3d_gpu_pbi_h1_batch
+    ll = C.c_longlong
+    f.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, ll, C.c_void_p, C.c_void_p, ll, C.c_void_p]
+    _lib.check(f(nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), int(integration), int(maxp), _ptr(etav), ncomp, _ptr(fvert), _ptr(fgrad),
+                 int(np.prod(fgrad.shape[1:])), _ptr(m), _ptr(out), int(np.prod(out.shape[1:])), _ptr(info)))
+    return dict(dof=out, info=info)

@@ -2,6 +2,7 @@
 #include "../../include/hp3d_gpu.h"
 #include "engine.cuh"
 #include "error_eval.cuh"
+#include "pbi.cuh"
 
 #include <cstdarg>
 #include <chrono>
@@ -38,6 +39,7 @@ struct CelemStore {   // grow-only device buffers for the constraint arrays of h
 } g_celem_store;
 
 void release_error_signatures();   // error-evaluation tables (defined with hp3d_gpu_elem_error_batch below)
+void release_pbi_signatures();     // interpolation tables (defined with hp3d_gpu_pbi_h1_batch below)
 
 int fail(int code, const char *fmt, ...) {
   char buf[512];
@@ -216,6 +218,7 @@ int hp3d_gpu_finalize(void) {
   g_arena.release();
   g_celem_store.release();
   release_error_signatures();
+  release_pbi_signatures();
   for (int i = 0; i < LaneSet::NLANE; i++)
     if (g_lane_stream[i]) { cudaStreamDestroy(g_lane_stream[i]); g_lane_stream[i] = nullptr; }
   if (g_copy) { cudaStreamDestroy(g_copy); g_copy = nullptr; }
@@ -1082,6 +1085,157 @@ int hp3d_gpu_error_points(int plan, int nel, const int *etype, const int *norder
     return HP3D_OK;
   }
   return error_impl(plan, nel, etype, norder, norie, norif, xnod, xnod_ld, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, nullptr, xq, sxq, nint_out);
+}
+
+}  // extern "C"
+
+// ---- H1 projection-based interpolation (pbi.cuh) -----------------------------------------------------------------------------
+namespace {
+struct PbiSig {
+  PbiSigHost h;   // node descriptors + points; the gradient table lives on the device only
+  bool on_device = false;
+  double *d_wa = nullptr, *d_tan = nullptr, *d_grad = nullptr;
+  PbiNode *d_nodes = nullptr;
+  ~PbiSig() { cudaFree(d_wa); cudaFree(d_tan); cudaFree(d_grad); cudaFree(d_nodes); }
+};
+std::map<std::string, std::unique_ptr<PbiSig>> g_pbisigs;
+CelemStore g_pbi_store;   // grow-only device buffers of hp3d_gpu_pbi_h1_batch
+void release_pbi_signatures() { g_pbisigs.clear(); g_pbi_store.release(); }
+
+// descriptors + points of a signature (host only); `tables` also builds and uploads the gradient table
+PbiSig *pbi_signature(int et, const int *norder, const int *norie, const int *norif, int integration, int maxp, bool tables, std::string &err) {
+  const std::string key = std::to_string(integration) + "/" + std::to_string(maxp) + "/" + Plan::key(et, norder, norie, norif);
+  auto it = g_pbisigs.find(key);
+  if (it == g_pbisigs.end()) {
+    std::unique_ptr<PbiSig> S(new PbiSig());
+    if (!compile_pbi_signature(et, norder, norie, norif, integration, maxp, false, S->h)) { err = S->h.err; return nullptr; }
+    it = g_pbisigs.emplace(key, std::move(S)).first;
+  }
+  PbiSig *S = it->second.get();
+  if (tables && !S->on_device) {
+    PbiSigHost full;
+    if (!compile_pbi_signature(et, norder, norie, norif, integration, maxp, true, full)) { err = full.err; return nullptr; }
+    std::vector<PbiNode> nodes(full.node, full.node + full.nnode);
+    if (dev_upload(full.wa, &S->d_wa, err) || dev_upload(full.tan, &S->d_tan, err) || dev_upload(full.grad, &S->d_grad, err) ||
+        dev_upload(nodes, &S->d_nodes, err))
+      return nullptr;
+    S->on_device = true;
+  }
+  return S;
+}
+}  // namespace
+
+extern "C" {
+
+int hp3d_gpu_pbi_points(int nel, const int *etype, const int *norder, const int *norie, const int *norif, int integration, int maxp,
+                        double *xi, long long xi_ld, int *npts, int *nrdofH, int *nodes) {
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  if (nel < 0 || (nel > 0 && (!norder || !norie || !norif))) return fail(HP3D_EINVAL, "pbi_points: null argument");
+  for (int e = 0; e < nel; e++) {
+    std::string err;
+    const PbiSig *S = pbi_signature(etype ? etype[e] : HP3D_MDLB, norder + 19 * e, norie + 12 * e, norif + 6 * e, integration, maxp, false, err);
+    if (!S) return fail(HP3D_EINVAL, "element %d: %s", e, err.c_str());
+    const PbiSigHost &h = S->h;
+    if (npts) npts[e] = h.npts;
+    if (nrdofH) nrdofH[e] = h.nH;
+    if (nodes) {
+      int *q = nodes + (size_t)e * 4 * PBI_MAXNODE;
+      for (int i = 0; i < 4 * PBI_MAXNODE; i++) q[i] = 0;
+      for (int i = 0; i < h.nnode; i++) { q[4 * i] = h.node[i].t0; q[4 * i + 1] = h.node[i].n; q[4 * i + 2] = h.node[i].p0; q[4 * i + 3] = h.node[i].np; }
+    }
+    if (xi) {
+      if (xi_ld < 3LL * h.npts) return fail(HP3D_EINVAL, "pbi_points: xi_ld %lld < 3*npts = %d (element %d)", xi_ld, 3 * h.npts, e);
+      memcpy(xi + (size_t)e * xi_ld, h.xi.data(), sizeof(double) * 3 * h.npts);
+    }
+  }
+  return HP3D_OK;
+}
+
+int hp3d_gpu_pbi_h1_batch(int nel, const int *etype, const int *norder, const int *norie, const int *norif, int integration, int maxp,
+                          const double *etav, int ncomp, const double *fvert, const double *fgrad, long long fgrad_ld,
+                          const unsigned *mask, double *dof, long long dof_ld, int *info) {
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
+  if (nel < 0 || (nel > 0 && (!norder || !norie || !norif || !etav || !fvert || !fgrad || !dof))) return fail(HP3D_EINVAL, "pbi_h1: null argument");
+  if (ncomp < 1 || ncomp > PBI_MAXCOMP) return fail(HP3D_EINVAL, "pbi_h1: ncomp = %d outside 1..%d (split the components over several calls)", ncomp, PBI_MAXCOMP);
+  if (nel == 0) return HP3D_OK;
+  // ---- signature groups (elements are addressed in place through an index list: no host-side gather)
+  struct Group { PbiSig *S; std::vector<int> el; };
+  std::map<const PbiSig *, size_t> where;
+  std::vector<Group> groups;
+  for (int e = 0; e < nel; e++) {
+    std::string err;
+    PbiSig *S = pbi_signature(etype ? etype[e] : HP3D_MDLB, norder + 19 * e, norie + 12 * e, norif + 6 * e, integration, maxp, true, err);
+    if (!S) return fail(HP3D_EINVAL, "element %d: %s", e, err.c_str());
+    if (dof_ld < (long long)ncomp * S->h.nH) return fail(HP3D_EINVAL, "pbi_h1: dof_ld %lld < ncomp*nrdofH = %d (element %d)", dof_ld, ncomp * S->h.nH, e);
+    if (fgrad_ld < 3LL * ncomp * S->h.npts) return fail(HP3D_EINVAL, "pbi_h1: fgrad_ld %lld < 3*ncomp*npts = %d (element %d)", fgrad_ld, 3 * ncomp * S->h.npts, e);
+    auto w = where.find(S);
+    if (w == where.end()) { w = where.emplace(S, groups.size()).first; groups.push_back(Group{S, {}}); }
+    groups[w->second].el.push_back(e);
+  }
+  // ---- workspace: (n + ncomp)(3 np + n) doubles per CTA, at most 1 GiB per launch
+  struct LaunchDims { long long stride[3]; int ny[3]; };
+  std::vector<LaunchDims> dims(groups.size());
+  long long need_ws = 0;
+  std::vector<int> elist; elist.reserve(nel);
+  for (size_t g = 0; g < groups.size(); g++) {
+    const PbiSigHost &h = groups[g].S->h;
+    const int n = (int)groups[g].el.size();
+    const int first[4] = {h.nrv, h.nrv + h.nre, h.nrv + h.nre + h.nrf, h.nnode};
+    for (int s = 0; s < 3; s++) {
+      long long st = 0;
+      for (int i = first[s]; i < first[s + 1]; i++)
+        if (h.node[i].n > 0) st = std::max(st, (long long)(h.node[i].n + ncomp) * (3LL * h.node[i].np + h.node[i].n));
+      dims[g].stride[s] = st; dims[g].ny[s] = 0;
+      if (!st) continue;
+      const long long per_row = st * (first[s + 1] - first[s]) * (long long)sizeof(double);
+      dims[g].ny[s] = (int)std::max(1LL, std::min((long long)n, (1LL << 30) / per_row));
+      need_ws = std::max(need_ws, per_row * dims[g].ny[s]);
+    }
+    elist.insert(elist.end(), groups[g].el.begin(), groups[g].el.end());
+  }
+  const size_t b_ev = sizeof(double) * 24 * (size_t)nel, b_fv = sizeof(double) * 8 * ncomp * (size_t)nel,
+               b_fg = std::max(sizeof(double) * (size_t)fgrad_ld * nel, sizeof(double)), b_d = sizeof(double) * (size_t)dof_ld * nel;
+  double *dev_ev = (double *)g_pbi_store.get(0, b_ev), *dev_fv = (double *)g_pbi_store.get(1, b_fv), *dev_fg = (double *)g_pbi_store.get(2, b_fg),
+         *dev_d = (double *)g_pbi_store.get(3, b_d), *dev_ws = (double *)g_pbi_store.get(4, (size_t)std::max(need_ws, 8LL));
+  unsigned *dev_m = mask ? (unsigned *)g_pbi_store.get(5, sizeof(unsigned) * nel) : nullptr;
+  int *dinfo = (int *)g_pbi_store.get(6, sizeof(int) * nel), *dev_el = (int *)g_pbi_store.get(7, sizeof(int) * nel);
+  if (!dev_ev || !dev_fv || !dev_fg || !dev_d || !dev_ws || (mask && !dev_m) || !dinfo || !dev_el)
+    return fail(HP3D_ENOMEM, "pbi_h1: out of device memory (%zu bytes of inputs, %lld bytes of workspace)", b_ev + b_fv + b_fg + b_d, need_ws);
+  CUDA_TRY(cudaMemcpyAsync(dev_ev, etav, b_ev, cudaMemcpyHostToDevice, g_compute));
+  CUDA_TRY(cudaMemcpyAsync(dev_fv, fvert, b_fv, cudaMemcpyHostToDevice, g_compute));
+  if (fgrad_ld > 0) CUDA_TRY(cudaMemcpyAsync(dev_fg, fgrad, sizeof(double) * (size_t)fgrad_ld * nel, cudaMemcpyHostToDevice, g_compute));
+  CUDA_TRY(cudaMemcpyAsync(dev_d, dof, b_d, cudaMemcpyHostToDevice, g_compute));   // nodes outside the mask keep (and contribute) their entries
+  if (mask) CUDA_TRY(cudaMemcpyAsync(dev_m, mask, sizeof(unsigned) * nel, cudaMemcpyHostToDevice, g_compute));
+  CUDA_TRY(cudaMemcpyAsync(dev_el, elist.data(), sizeof(int) * nel, cudaMemcpyHostToDevice, g_compute));
+  CUDA_TRY(cudaMemsetAsync(dinfo, 0, sizeof(int) * nel, g_compute));
+  // ---- per group: vertices, then the three dependent launches (edges, faces, middle node)
+  size_t pos = 0;
+  for (size_t g = 0; g < groups.size(); g++) {
+    const PbiSig &S = *groups[g].S;
+    const PbiSigHost &h = S.h;
+    const int n = (int)groups[g].el.size();
+    const int first[4] = {h.nrv, h.nrv + h.nre, h.nrv + h.nre + h.nrf, h.nnode};
+    PbiArgs A;
+    A.wa = S.d_wa; A.tan = S.d_tan; A.grad = S.d_grad; A.nodes = S.d_nodes; A.nH = h.nH; A.nrv = h.nrv; A.npts = h.npts; A.ncomp = ncomp;
+    A.node0 = 0; A.nel = n; A.elems = dev_el + pos; A.etav = dev_ev; A.fgrad = dev_fg; A.fvert = dev_fv; A.mask = dev_m; A.dof = dev_d;
+    A.fgrad_ld = fgrad_ld; A.dof_ld = dof_ld; A.ws = dev_ws; A.ws_stride = 0; A.info = dinfo;
+    pbi_vertex_kernel<<<(n * h.nrv + 127) / 128, 128, 0, g_compute>>>(A);
+    g_launches++;
+    for (int s = 0; s < 3; s++) {
+      if (!dims[g].stride[s]) continue;
+      A.node0 = first[s]; A.ws_stride = dims[g].stride[s];
+      pbi_node_kernel<<<dim3(first[s + 1] - first[s], dims[g].ny[s]), 256, 0, g_compute>>>(A);
+      g_launches++;
+    }
+    pos += n;
+  }
+  CUDA_TRY(cudaGetLastError());
+  std::vector<int> hinfo(info ? 0 : nel);
+  CUDA_TRY(cudaMemcpyAsync(dof, dev_d, b_d, cudaMemcpyDeviceToHost, g_compute));
+  CUDA_TRY(cudaMemcpyAsync(info ? info : hinfo.data(), dinfo, sizeof(int) * nel, cudaMemcpyDeviceToHost, g_compute));
+  CUDA_TRY(cudaStreamSynchronize(g_compute));
+  return HP3D_OK;
 }
 
 }  // extern "C"

@@ -1,0 +1,371 @@
+// pbi.cuh -- batched H1 projection-based interpolation (interpolation half):
+//   geometry dofs      update_gdof.F90:88-200,409-435 -> hpvert.F90:19, hpedge.F90:27, hpface_opt.F90:27, hpmdle_opt.F90:23
+//   H1 Dirichlet dofs  update_Ddof.F90              -> dhpvert.F90:26, edge/dhpedgeH.F90:32, face/dhpfaceH_opt.F90:32
+// One algorithm: the interpolated function g (the GMP map x(eta): 3 components, INTEGRATION = 0; or a Dirichlet datum
+// u(x(eta)): NREQNH real / 2 NREQNH interleaved complex components, INTEGRATION = 1) enters through its vertex values and
+// through its gradient in the reference coordinates eta of the GMP block, tabulated by the host at the points this file
+// defines (the reference calls `hexa/prism(No,eta, x,dxdeta)` and `dirichlet` at the same points).  Node by node
+// (vertices -> edges -> faces -> middle) the dofs of the node minimise the H1 seminorm in eta of
+//        g - (interpolant of the lower-dimensional nodes) - sum_j dof_j phi_j
+// over the node (tangential gradient on an edge, surface gradient on a face, full gradient inside), eta(xi) being the
+// multilinear map through the element's vertex reference coordinates Etav (refgeom3D, geom3D.F90:235-305).
+//
+// Host: per signature (type, orders, orientations, INTEGRATION) the quadrature points of every node and the master gradients
+// of all H1 functions at them are tabulated once.  Device: one CTA per (node, element):
+//   A  a thread owns a point: Jacobian of eta(xi), tangent / normal, residual gradient R = dg/deta - sum_known dof_k grad phi_k,
+//      projected test gradients; both scaled by sqrt(weight) and stored as rows of one matrix D = [test rows ; R rows]
+//   B  G = D D_test^T  (64 x 64 register-tiled product: rows 0..n-1 the stiffness, rows n.. the load vectors) -- the reference's
+//      DSFRK + load loop (hpface_opt.F90:195-222)
+//   C  Cholesky of the stiffness with the load rows carried along (forward substitution for free), back substitution
+//      (DPFTRF / DPFTRS, hpface_opt.F90:235-247; the edge routine's DGETRF solves the same SPD system).
+#pragma once
+#include "error_eval.cuh"
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+namespace hp3d {
+
+constexpr int PBI_MAXNODE = 27;   // 8 + 12 + 6 + 1 nodes of a brick
+constexpr int PBI_MAXCOMP = 12;
+
+struct PbiNode { int kind, t0, n, nknown, p0, np; };   // kind 0 vertex, 1 edge, 2 face, 3 middle ; dofs [t0, t0+n) ; points [p0, p0+np)
+
+struct PbiSigHost {
+  int etype = 1, nH = 0, nrv = 8, nre = 12, nrf = 6, nnode = 27, npts = 0;
+  PbiNode node[PBI_MAXNODE];
+  std::vector<double> xi;     // (3, npts) master coordinates
+  std::vector<double> wa;     // (npts) quadrature weights
+  std::vector<double> tan;    // (6, npts) d xi / d t of the edge (first 3) or face (both) parametrisation
+  std::vector<double> grad;   // [3][nH][npts] master gradients of the element's H1 functions
+  std::string err;
+};
+
+namespace detail {
+static const int BR_EDGE_VERT[12][2] = {{1, 2}, {2, 3}, {4, 3}, {1, 4}, {5, 6}, {6, 7}, {8, 7}, {5, 8}, {1, 5}, {2, 6}, {3, 7}, {4, 8}};   // element_data.F90:67-70
+static const int BR_FACE_VERT[6][4] = {{1, 2, 3, 4}, {5, 6, 7, 8}, {1, 2, 6, 5}, {2, 3, 7, 6}, {4, 3, 7, 8}, {1, 4, 8, 5}};                // :90-93
+static const int BR_FACE_EDGE[6][4] = {{1, 2, 3, 4}, {5, 6, 7, 8}, {1, 10, 5, 9}, {2, 11, 6, 10}, {3, 11, 7, 12}, {4, 12, 8, 9}};
+static const int PR_EDGE_VERT[9][2] = {{1, 2}, {2, 3}, {1, 3}, {4, 5}, {5, 6}, {4, 6}, {1, 4}, {2, 5}, {3, 6}};                              // :62-65
+}  // namespace detail
+
+// points + tables of one signature.  `tables = false` only fills the node descriptors and the points (size queries).
+inline bool compile_pbi_signature(int etype, const int *norder, const int *norie, const int *norif, int integration, int maxp, bool tables,
+                                  PbiSigHost &S) {
+  using namespace detail;
+  S = PbiSigHost();
+  S.etype = etype;
+  const bool brick = etype == 1;
+  if (!brick && etype != 3) { S.err = "unknown element type (HP3D_MDLB = 1 and HP3D_MDLP = 3 are implemented)"; return false; }
+  if (integration < 0 || integration > 2) { S.err = "INTEGRATION must be 0, 1 or 2"; return false; }
+  S.nrv = brick ? 8 : 6; S.nre = brick ? 12 : 9; S.nrf = brick ? 6 : 5; S.nnode = S.nrv + S.nre + S.nrf + 1;
+  const int nrv = S.nrv, nre = S.nre, nrf = S.nrf;
+  for (int e = 0; e < nre; e++) if (norder[e] < 1 || norder[e] > 9 || (norie[e] != 0 && norie[e] != 1)) { S.err = "bad edge order/orientation"; return false; }
+  for (int f = 0; f < nrf; f++) {
+    const bool tri = !brick && f < 2;
+    const int o = norder[nre + f];
+    if (tri ? (o < 1 || o > 9 || norif[f] < 0 || norif[f] > 5) : (o / 10 < 1 || o % 10 < 1 || o > 99 || norif[f] < 0 || norif[f] > 7)) { S.err = "bad face order/orientation"; return false; }
+  }
+  // ---- dofs per node (ndof_nod, element_data.F90:808-870)
+  int cnt[PBI_MAXNODE];
+  for (int v = 0; v < nrv; v++) cnt[v] = 1;
+  for (int e = 0; e < nre; e++) cnt[nrv + e] = norder[e] - 1;
+  for (int f = 0; f < nrf; f++) {
+    const int o = norder[nre + f];
+    cnt[nrv + nre + f] = (!brick && f < 2) ? (o - 1) * (o - 2) / 2 : (o / 10 - 1) * (o % 10 - 1);
+  }
+  const int om = norder[nre + nrf];
+  if (brick) { if (om / 100 < 1 || (om / 10) % 10 < 1 || om % 10 < 1) { S.err = "bad middle node order"; return false; }
+    cnt[S.nnode - 1] = (om / 100 - 1) * ((om / 10) % 10 - 1) * (om % 10 - 1); }
+  else { if (om / 10 < 1 || om % 10 < 1) { S.err = "bad prism middle node order"; return false; }
+    cnt[S.nnode - 1] = (om / 10 - 1) * (om / 10 - 2) / 2 * (om % 10 - 1); }
+  int off = 0;
+  for (int i = 0; i < S.nnode; i++) {
+    PbiNode &nd = S.node[i];
+    nd.kind = i < nrv ? 0 : (i < nrv + nre ? 1 : (i < nrv + nre + nrf ? 2 : 3));
+    nd.t0 = off; nd.n = cnt[i]; off += cnt[i];
+    nd.p0 = 0; nd.np = 0; nd.nknown = 0;
+  }
+  S.nH = off;
+  for (int i = nrv; i < S.nnode; i++)
+    S.node[i].nknown = S.node[i].kind == 1 ? nrv : (S.node[i].kind == 2 ? S.node[nrv + nre].t0 : S.node[S.nnode - 1].t0);
+  // ---- points
+  auto cap = [&](int p) { return std::min(p + integration, maxp); };
+  auto vert = [&](int v1) { return brick ? std::array<double, 3>{(double)VSIDE[v1 - 1][0], (double)VSIDE[v1 - 1][1], (double)VSIDE[v1 - 1][2]}
+                                         : std::array<double, 3>{PR_COORD[v1 - 1][0], PR_COORD[v1 - 1][1], PR_COORD[v1 - 1][2]}; };
+  auto push = [&](const double x[3], double w, const double t[6]) {
+    for (int c = 0; c < 3; c++) S.xi.push_back(x[c]);
+    S.wa.push_back(w);
+    for (int c = 0; c < 6; c++) S.tan.push_back(t[c]);
+  };
+  for (int e = 0; e < nre; e++) {   // set_1Dint + edge_param (set_1D_int.F90:24-49, element_data.F90:508-549)
+    PbiNode &nd = S.node[nrv + e];
+    nd.p0 = (int)S.wa.size();
+    if (nd.n <= 0) continue;
+    const int nq = cap(norder[e]) + 1;
+    if (nq > MAXQ) { S.err = "order exceeds the 10-point Gauss table limit"; return false; }
+    const Tables1D g = make_tables(1, nq);
+    const int *ev = brick ? BR_EDGE_VERT[e] : PR_EDGE_VERT[e];
+    const std::array<double, 3> a = vert(ev[0]), b = vert(ev[1]);
+    for (int l = 0; l < nq; l++) {
+      double x[3], t[6] = {0, 0, 0, 0, 0, 0};
+      for (int c = 0; c < 3; c++) { t[c] = b[c] - a[c]; x[c] = a[c] + g.x[l] * t[c]; }
+      push(x, g.w[l], t);
+    }
+    nd.np = nq;
+  }
+  for (int f = 0; f < nrf; f++) {   // face_order + set_2Dint + face_param (element_data.F90:750-803,554-603, set_2D_int.F90:8-21,177-247)
+    PbiNode &nd = S.node[nrv + nre + f];
+    nd.p0 = (int)S.wa.size();
+    if (nd.n <= 0) continue;
+    const bool tri = !brick && f < 2;
+    const int *fe = brick ? BR_FACE_EDGE[f] : PR_FACE_EDGE[f], *fv = brick ? BR_FACE_VERT[f] : PR_FACE_VERT[f];
+    const std::array<double, 3> a = vert(fv[0]), b = vert(fv[1]), c3 = vert(fv[tri ? 2 : 3]);
+    double t[6];
+    for (int c = 0; c < 3; c++) { t[c] = b[c] - a[c]; t[3 + c] = c3[c] - a[c]; }
+    std::vector<double> tp, tw;   // (2, n) face coordinates + weights
+    if (tri) {
+      int o = std::max(std::max(norder[fe[0] - 1], norder[fe[1] - 1]), std::max(norder[fe[2] - 1], norder[nre + f]));
+      o = cap(o);
+      if (o > 9) { S.err = "triangle rule order exceeds 9"; return false; }
+      for (int l = 0; l < TRI_RULE_NPTS[o - 1]; l++) { const double *p = TRI_RULE_PTS[TRI_RULE_OFF[o - 1] + l]; tp.push_back(p[0]); tp.push_back(p[1]); tw.push_back(p[2]); }
+    } else {
+      const int h = norder[nre + f] / 10, v = norder[nre + f] % 10;
+      const int nx = cap(std::max(std::max(norder[fe[0] - 1], norder[fe[2] - 1]), h)) + 1, ny = cap(std::max(std::max(norder[fe[1] - 1], norder[fe[3] - 1]), v)) + 1;
+      if (nx > MAXQ || ny > MAXQ) { S.err = "order exceeds the 10-point Gauss table limit"; return false; }
+      const Tables1D g1 = make_tables(1, nx), g2 = make_tables(1, ny);
+      for (int l2 = 0; l2 < ny; l2++)
+        for (int l1 = 0; l1 < nx; l1++) { tp.push_back(g1.x[l1]); tp.push_back(g2.x[l2]); tw.push_back(g1.w[l1] * g2.w[l2]); }
+    }
+    for (size_t l = 0; l < tw.size(); l++) {
+      double x[3];
+      for (int c = 0; c < 3; c++) x[c] = a[c] + tp[2 * l] * t[c] + tp[2 * l + 1] * t[3 + c];
+      push(x, tw[l], t);
+    }
+    nd.np = (int)tw.size();
+  }
+  {   // set_3Dint with the orders as stored (hpmdle_opt.F90:121; set_3D_int.F90:155-259)
+    PbiNode &nd = S.node[S.nnode - 1];
+    nd.p0 = (int)S.wa.size();
+    const int zero[6] = {0, 0, 0, 0, 0, 0};
+    const double t0[6] = {0, 0, 0, 0, 0, 0};
+    if (nd.n > 0) {
+      if (brick) {
+        int pmax[3], nq[3];
+        hexa_axis_max_order(norder, zero, pmax);
+        Tables1D g[3];
+        for (int d = 0; d < 3; d++) { nq[d] = cap(pmax[d]) + 1; if (nq[d] > MAXQ) { S.err = "order exceeds the 10-point Gauss table limit"; return false; } g[d] = make_tables(1, nq[d]); }
+        for (int qz = 0; qz < nq[2]; qz++)
+          for (int qy = 0; qy < nq[1]; qy++)
+            for (int qx = 0; qx < nq[0]; qx++) { const double x[3] = {g[0].x[qx], g[1].x[qy], g[2].x[qz]}; push(x, g[0].w[qx] * g[1].w[qy] * g[2].w[qz], t0); }
+        nd.np = nq[0] * nq[1] * nq[2];
+      } else {
+        int pmax[2];
+        prism_axis_max_order(norder, zero, pmax);
+        const int oh = cap(pmax[0]), nz = cap(pmax[1]) + 1;
+        if (oh > 9 || nz > MAXQ) { S.err = "prism order exceeds the quadrature table limits"; return false; }
+        const Tables1D gz = make_tables(1, nz);
+        const int nt = TRI_RULE_NPTS[oh - 1];
+        for (int qz = 0; qz < nz; qz++)
+          for (int qt = 0; qt < nt; qt++) { const double *p = TRI_RULE_PTS[TRI_RULE_OFF[oh - 1] + qt]; const double x[3] = {p[0], p[1], gz.x[qz]}; push(x, p[2] * gz.w[qz], t0); }
+        nd.np = nt * nz;
+      }
+    }
+  }
+  S.npts = (int)S.wa.size();
+  if (!tables) return true;
+  // ---- master gradients of the element's H1 functions at all points (reference dof order)
+  std::vector<double> val((size_t)3 * S.nH), der((size_t)3 * S.nH);
+  S.grad.assign((size_t)3 * S.nH * S.npts, 0.0);
+  if (brick) {
+    const std::vector<TensorDof> hd = hexa_dofs_H1(norder, norie, norif);
+    if ((int)hd.size() != S.nH) { S.err = "internal: H1 dof count mismatch"; return false; }
+    int ptab = 1;
+    for (int e = 0; e < 12; e++) ptab = std::max(ptab, norder[e]);
+    for (int f = 0; f < 6; f++) ptab = std::max(ptab, std::max(norder[12 + f] / 10, norder[12 + f] % 10));
+    ptab = std::max(ptab, std::max(om / 100, std::max((om / 10) % 10, om % 10)));
+    for (int l = 0; l < S.npts; l++) {
+      hexa_shape_at(ES_H1, hd, ptab, &S.xi[3 * l], val.data(), der.data());
+      for (int k = 0; k < S.nH; k++)
+        for (int j = 0; j < 3; j++) S.grad[((size_t)j * S.nH + k) * S.npts + l] = der[3 * k + j];
+    }
+  } else {
+    TriList TG;
+    const TriList none;
+    const std::vector<PrismDof> hd = prism_dofs_H1(norder, norie, norif, TG);
+    if ((int)hd.size() != S.nH) { S.err = "internal: H1 dof count mismatch"; return false; }
+    for (int l = 0; l < S.npts; l++) {
+      prism_shape_at(ES_H1, hd, TG, none, MAXN1D - 1, &S.xi[3 * l], val.data(), der.data());
+      for (int k = 0; k < S.nH; k++)
+        for (int j = 0; j < 3; j++) S.grad[((size_t)j * S.nH + k) * S.npts + l] = der[3 * k + j];
+    }
+  }
+  return true;
+}
+
+struct PbiArgs {
+  const double *wa, *tan, *grad;   // signature tables (device)
+  const PbiNode *nodes;
+  int nH, nrv, npts, ncomp;
+  int node0;                       // this launch handles nodes node0 + blockIdx.x
+  int nel;                         // elements of this signature group ...
+  const int *elems;                // ... and their positions in the call's arrays
+  const double *etav;              // (3, 8) per element
+  const double *fgrad;             // (ncomp, 3, npts) per element, component fastest, stride fgrad_ld
+  const double *fvert;             // (ncomp, 8) per element
+  const unsigned *mask;            // per element (nullptr: every node)
+  double *dof;                     // (ncomp, nH) per element, stride dof_ld
+  long long fgrad_ld, dof_ld;
+  double *ws; long long ws_stride; // workspace per CTA
+  int *info;
+};
+
+// vertices: the value of g (hpvert.F90:19-45, dhpvert.F90:60-75)
+__global__ void pbi_vertex_kernel(PbiArgs A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.nel * A.nrv) return;
+  const int e = A.elems[i / A.nrv], v = i % A.nrv;
+  if (A.mask && !((A.mask[e] >> v) & 1u)) return;
+  for (int c = 0; c < A.ncomp; c++) A.dof[(long long)e * A.dof_ld + (long long)v * A.ncomp + c] = A.fvert[((long long)e * 8 + v) * A.ncomp + c];
+}
+
+__global__ void __launch_bounds__(256) pbi_node_kernel(PbiArgs A) {
+  __shared__ double As[16][68], Bs[16][68];
+  const int tid = threadIdx.x, inode = A.node0 + blockIdx.x;
+  const PbiNode nd = A.nodes[inode];
+  const int n = nd.n, np = nd.np, nc = A.ncomp, K3 = 3 * np, R = n + nc;
+  if (n <= 0) return;
+  double *D = A.ws + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * A.ws_stride;   // [R][K3]
+  double *G = D + (long long)R * K3;                                                    // [R][n]
+  const long long HS = (long long)A.nH * A.npts;
+  for (int ie = blockIdx.y; ie < A.nel; ie += gridDim.y) {
+    const int e = A.elems[ie];
+    if (A.mask && !((A.mask[e] >> inode) & 1u)) continue;
+    const double *ev = A.etav + (long long)e * 24;
+    double *dof = A.dof + (long long)e * A.dof_ld;
+    const double *fg = A.fgrad + (long long)e * A.fgrad_ld;
+    __syncthreads();   // the previous element's solve has finished with D / G
+    // ---- A: one thread per point
+    for (int l = tid; l < np; l += blockDim.x) {
+      const int gl = nd.p0 + l;
+      double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // J[c + 3m] = d eta_c / d xi_m
+      for (int v = 0; v < A.nrv; v++) {
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+          const double g = A.grad[m * HS + (long long)v * A.npts + gl];
+#pragma unroll
+          for (int c = 0; c < 3; c++) J[c + 3 * m] += ev[3 * v + c] * g;
+        }
+      }
+      const double det = J[0] * J[4] * J[8] + J[1] * J[5] * J[6] + J[2] * J[3] * J[7] - J[2] * J[4] * J[6] - J[0] * J[5] * J[7] - J[1] * J[3] * J[8];
+      if (!(det > 0.0)) A.info[e] = -1;
+      double Ji[9];   // Ji[a + 3i] = d xi_a / d eta_i (geom.F90:57-113)
+      Ji[0] = (J[4] * J[8] - J[5] * J[7]) / det; Ji[1] = (-J[1] * J[8] + J[2] * J[7]) / det; Ji[2] = (J[1] * J[5] - J[2] * J[4]) / det;
+      Ji[3] = (J[5] * J[6] - J[3] * J[8]) / det; Ji[4] = (J[0] * J[8] - J[2] * J[6]) / det; Ji[5] = (-J[0] * J[5] + J[2] * J[3]) / det;
+      Ji[6] = (J[3] * J[7] - J[4] * J[6]) / det; Ji[7] = (-J[0] * J[7] + J[1] * J[6]) / det; Ji[8] = (J[0] * J[4] - J[1] * J[3]) / det;
+      double weight, dir[3] = {0, 0, 0};   // unit tangent (edge) / unit normal (face)
+      if (nd.kind == 3) weight = A.wa[gl] * det;
+      else {
+        const double *t = A.tan + 6LL * gl;
+        double d1[3], d2[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) { d1[c] = J[c] * t[0] + J[c + 3] * t[1] + J[c + 6] * t[2]; d2[c] = J[c] * t[3] + J[c + 3] * t[4] + J[c + 6] * t[5]; }
+        if (nd.kind == 1) { dir[0] = d1[0]; dir[1] = d1[1]; dir[2] = d1[2]; }   // hpedge.F90:134-141
+        else { dir[0] = d1[1] * d2[2] - d1[2] * d2[1]; dir[1] = d1[2] * d2[0] - d1[0] * d2[2]; dir[2] = d1[0] * d2[1] - d1[1] * d2[0]; }   // brefgeom3D
+        const double bj = sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+        dir[0] /= bj; dir[1] /= bj; dir[2] /= bj;
+        weight = A.wa[gl] * bj;
+      }
+      const double sw = sqrt(weight);
+      double Rg[3 * PBI_MAXCOMP];   // Rg[c + nc*i] = d g_c / d eta_i minus the known part
+      for (int q = 0; q < 3 * nc; q++) Rg[q] = fg[(long long)gl * 3 * nc + q];
+      for (int k = 0; k < nd.nknown; k++) {
+        const double g0 = A.grad[(long long)k * A.npts + gl], g1 = A.grad[HS + (long long)k * A.npts + gl], g2 = A.grad[2 * HS + (long long)k * A.npts + gl];
+        const double du0 = g0 * Ji[0] + g1 * Ji[1] + g2 * Ji[2], du1 = g0 * Ji[3] + g1 * Ji[4] + g2 * Ji[5], du2 = g0 * Ji[6] + g1 * Ji[7] + g2 * Ji[8];
+        for (int c = 0; c < nc; c++) { const double z = dof[(long long)k * nc + c]; Rg[c] -= z * du0; Rg[c + nc] -= z * du1; Rg[c + 2 * nc] -= z * du2; }
+      }
+      for (int c = 0; c < nc; c++)
+        for (int i = 0; i < 3; i++) D[(long long)(n + c) * K3 + 3 * l + i] = Rg[c + nc * i] * sw;
+      for (int j = 0; j < n; j++) {
+        const int k = nd.t0 + j;
+        const double g0 = A.grad[(long long)k * A.npts + gl], g1 = A.grad[HS + (long long)k * A.npts + gl], g2 = A.grad[2 * HS + (long long)k * A.npts + gl];
+        double dv[3] = {g0 * Ji[0] + g1 * Ji[1] + g2 * Ji[2], g0 * Ji[3] + g1 * Ji[4] + g2 * Ji[5], g0 * Ji[6] + g1 * Ji[7] + g2 * Ji[8]};
+        const double pr = dv[0] * dir[0] + dv[1] * dir[1] + dv[2] * dir[2];
+        if (nd.kind == 1) { dv[0] = pr * dir[0]; dv[1] = pr * dir[1]; dv[2] = pr * dir[2]; }           // hpedge.F90:186-187
+        else if (nd.kind == 2) { dv[0] -= pr * dir[0]; dv[1] -= pr * dir[1]; dv[2] -= pr * dir[2]; }    // hpface_opt.F90:205-206
+        for (int i = 0; i < 3; i++) D[(long long)j * K3 + 3 * l + i] = dv[i] * sw;
+      }
+    }
+    __syncthreads();
+    // ---- B: G[r][j] = sum_k D[r][k] D[j][k], r < R, j < n, tiles with j-tile <= r-tile (lower triangle + load rows)
+    const int tx = tid & 15, ty = tid >> 4;
+    for (int r0 = 0; r0 < R; r0 += 64)
+      for (int j0 = 0; j0 <= r0 && j0 < n; j0 += 64) {
+        double acc[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+        for (int k0 = 0; k0 < K3; k0 += 16) {
+          {   // stage 64 rows x 16 k of both operands: thread -> (row = tid / 4, 4 consecutive k)
+            const int row = tid >> 2, kk = (tid & 3) * 4;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const int k = k0 + kk + q;
+              As[kk + q][row] = (r0 + row < R && k < K3) ? D[(long long)(r0 + row) * K3 + k] : 0.0;
+              Bs[kk + q][row] = (j0 + row < n && k < K3) ? D[(long long)(j0 + row) * K3 + k] : 0.0;
+            }
+          }
+          __syncthreads();
+#pragma unroll
+          for (int k = 0; k < 16; k++) {
+            double a[4], b[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) { a[q] = As[k][ty * 4 + q]; b[q] = Bs[k][tx * 4 + q]; }
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+#pragma unroll
+              for (int q = 0; q < 4; q++) acc[p][q] += a[p] * b[q];
+          }
+          __syncthreads();
+        }
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const int r = r0 + ty * 4 + p, j = j0 + tx * 4 + q;
+            if (r < R && j < n) G[(long long)r * n + j] = acc[p][q];
+          }
+      }
+    __syncthreads();
+    // ---- C: right-looking Cholesky G = L L^T on the lower triangle; the load rows r >= n ride along (they end as y^T, L y = b)
+    bool bad = false;
+    for (int k = 0; k < n; k++) {
+      const double d = G[(long long)k * n + k];
+      if (!(d > 0.0)) { bad = true; break; }   // uniform: every thread reads the same value
+      const double piv = sqrt(d);
+      __syncthreads();
+      for (int r = k + tid; r < R; r += blockDim.x) G[(long long)r * n + k] = (r == k) ? piv : G[(long long)r * n + k] / piv;
+      __syncthreads();
+      // trailing update: rows r > k, columns k < j <= min(r, n-1); a warp takes a row, lanes run along j
+      for (int r = k + 1 + (tid >> 5); r < R; r += (blockDim.x >> 5)) {
+        const double lrk = G[(long long)r * n + k];
+        const int jmax = r < n ? r : n - 1;
+        for (int j = k + 1 + (tid & 31); j <= jmax; j += 32) G[(long long)r * n + j] -= lrk * G[(long long)j * n + k];
+      }
+      __syncthreads();
+    }
+    if (bad) { if (tid == 0) A.info[e] = inode + 1; continue; }   // LAPACK-style: the node whose stiffness is not positive definite
+    // back substitution L^T x = y, column oriented: x_k = y_k / L_kk, then y_j -= L_kj x_k for j < k
+    for (int k = n - 1; k >= 0; k--) {
+      const double lkk = G[(long long)k * n + k];
+      __syncthreads();
+      if (tid < nc) G[(long long)(n + tid) * n + k] /= lkk;
+      __syncthreads();
+      for (int q = tid; q < nc * k; q += blockDim.x) {
+        const int c = q / k, j = q % k;
+        G[(long long)(n + c) * n + j] -= G[(long long)k * n + j] * G[(long long)(n + c) * n + k];
+      }
+    }
+    __syncthreads();
+    for (int q = tid; q < nc * n; q += blockDim.x) { const int j = q / nc, c = q % nc; dof[(long long)(nd.t0 + j) * nc + c] = G[(long long)(n + c) * n + j]; }
+  }
+}
+
+}  // namespace hp3d

@@ -228,6 +228,35 @@ int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, con
 void *hp3d_gpu_host_alloc(long long bytes);
 void hp3d_gpu_host_free(void *p);
 
+/* ---- H1 projection-based interpolation (interpolation half): geometry dofs and H1 Dirichlet dofs.
+ * Replaces, for all elements of a subdomain at once, the node-by-node calls of
+ *   update_gdof  (src/hpinterp/update_gdof.F90:88-200,409-435): hpvert.F90:19, hpedge.F90:27, hpface_opt.F90:27, hpmdle_opt.F90:23
+ *   update_Ddof  (src/hpinterp/update_Ddof.F90):                 dhpvert.F90:26, edge/dhpedgeH.F90:32, face/dhpfaceH_opt.F90:32
+ * The interpolated function g has `ncomp` REAL components (the GMP map x(eta): 3; a complex Dirichlet datum: re/im interleaved,
+ * 2 NREQNH) and is projected in the reference coordinates eta of the GMP block; eta(xi) is the multilinear map through
+ *   etav   (3, 8) per element   reference coordinates of the element's vertices (refel's xsub; a prism uses the first 6).
+ * Nodes are numbered as in the element's nodesl: vertices, edges, faces, middle node (27 for a brick, 21 for a prism);
+ * bit i of mask[e] selects node i (mask == NULL: every node, update_gdof; for update_Ddof: the nodes with a Dirichlet flag).
+ *
+ * hp3d_gpu_pbi_points (host only, no GPU needed) returns where the host has to evaluate g:
+ *   xi      (3, npts[e]) master coordinates, stride xi_ld per element (NULL: sizes only); the points of the edges (set_1Dint +
+ *           edge_param), then of the faces (set_2Dint + face_param), then of the middle node (set_3Dint), each with
+ *           INTEGRATION = integration (0 in update_gdof, 1 in update_Ddof) and orders capped at maxp (MAXP)
+ *   nodes   (4, 27) per element: first dof, number of dofs, first point, number of points of every node (vertices have
+ *           no points; a node without dofs has none either, as the reference returns before integrating)
+ * hp3d_gpu_pbi_h1_batch:
+ *   fvert   (ncomp, 8) per element         g at the vertices (hpvert / dhpvert)
+ *   fgrad   (ncomp, 3, npts) per element   dg_c/deta_i at the points, component fastest (dxdeta(1:3,1:3) of `hexa/prism(No,eta,..)`;
+ *           zdvalH * dxdeta for Dirichlet data, dhpfaceH_opt.F90:206-212), stride fgrad_ld doubles
+ *   dof     (ncomp, nrdofH) per element, component fastest, reference dof order, stride dof_ld; IN: the dofs of the nodes that
+ *           are not selected (they enter the projections of the higher-dimensional nodes), OUT: the selected nodes' dofs
+ *   info    per element: 0, -1 (Jacobian of eta(xi) not positive), i > 0 (stiffness of node i not positive definite) */
+int hp3d_gpu_pbi_points(int nel, const int *etype, const int *norder, const int *norient_edge, const int *norient_face, int integration,
+                        int maxp, double *xi, long long xi_ld, int *npts, int *nrdofH, int *nodes);
+int hp3d_gpu_pbi_h1_batch(int nel, const int *etype, const int *norder, const int *norient_edge, const int *norient_face, int integration,
+                          int maxp, const double *etav, int ncomp, const double *fvert, const double *fgrad, long long fgrad_ld,
+                          const unsigned *mask, double *dof, long long dof_ld, int *info);
+
 /* ---- host-only introspection (no GPU needed): the signed tensor-product description of the shape functions.
  * space: 0 H1, 1 H(curl), 2 H(div), 3 L2.  For dof k (reference order, src/element/shape_1/Hexahedron.F90):
  *   fam[k] vector direction (0..2, -1 scalar), idx[3k..3k+2] 1-D table index per axis, sgn[k] = +-1.

@@ -142,6 +142,23 @@ module hp3d_gpu
          integer(c_int) :: etype(*), norder(19,*), norient_edge(12,*), norient_face(6,*)
          real(c_double) :: xnod(xnod_ld,*), xq(*)
       end function
+      integer(c_int) function hp3d_gpu_pbi_points(nel, etype, norder, norient_edge, norient_face, integration, maxp,          &
+                          xi, xi_ld, npts, nrdofH, nodes) bind(C)
+         import
+         integer(c_int), value :: nel, integration, maxp
+         integer(c_long_long), value :: xi_ld
+         integer(c_int) :: etype(*), norder(19,*), norient_edge(12,*), norient_face(6,*)
+         type(c_ptr), value :: xi, npts, nrdofH, nodes
+      end function
+      integer(c_int) function hp3d_gpu_pbi_h1_batch(nel, etype, norder, norient_edge, norient_face, integration, maxp,        &
+                          etav, ncomp, fvert, fgrad, fgrad_ld, mask, dof, dof_ld, info) bind(C)
+         import
+         integer(c_int), value :: nel, integration, maxp, ncomp
+         integer(c_long_long), value :: fgrad_ld, dof_ld
+         integer(c_int) :: etype(*), norder(19,*), norient_edge(12,*), norient_face(6,*), info(*)
+         real(c_double) :: etav(3,8,*), fvert(ncomp,8,*), fgrad(fgrad_ld,*), dof(dof_ld,*)
+         type(c_ptr), value :: mask
+      end function
    end interface
 !
 contains

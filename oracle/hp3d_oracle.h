@@ -256,6 +256,9 @@ void orc_edge_param(int et, int ie, double t, double xi[3], double dxidt[3]);
 void orc_pbi_offsets(int et, const int *norder, int *off);
 int orc_pbi_node(int et, const int *norder, const int *norie, const int *norif, const double *etav, int ncomp, int integration,
                  int maxp, int node, orc_pbi_fn f, void *ctx, double *dof);
+void orc_pbi_sample_fn(const double *eta, double *val, double *dval, void *ctx);
+int orc_pbi_batch_sample(int nel, const int *etype, const int *norder, const int *norie, const int *norif, const double *etav,
+                         int integration, int maxp, double *dof, long dof_ld, int nthreads);
 int orc_pbi_element(int et, const int *norder, const int *norie, const int *norif, const double *etav, int ncomp, int integration,
                     int maxp, unsigned mask, orc_pbi_fn f, void *ctx, double *dof);
 

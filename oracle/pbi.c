@@ -194,3 +194,23 @@ int orc_pbi_element(int et, const int *norder, const int *norie, const int *nori
     }
   return 0;
 }
+
+/* a fixed smooth 3-component map for timing the restatement without a Python callback (bench of tools/bench_pbi.py) */
+void orc_pbi_sample_fn(const double *eta, double *val, double *dval, void *ctx) {
+  const double x = eta[0], y = eta[1], z = eta[2];
+  (void)ctx;
+  val[0] = x + 0.1 * sin(2.0 * y) * z; val[1] = y + 0.05 * x * x; val[2] = z + 0.1 * cos(x + y);
+  dval[0] = 1.0;                dval[3] = 0.2 * cos(2.0 * y) * z; dval[6] = 0.1 * sin(2.0 * y);
+  dval[1] = 0.1 * x;            dval[4] = 1.0;                    dval[7] = 0.0;
+  dval[2] = -0.1 * sin(x + y);  dval[5] = -0.1 * sin(x + y);      dval[8] = 1.0;
+}
+/* element loop shaped like update_gdof.F90:409-435 (OpenMP over elements); dof stride = 3*nrdofH of each element's own order */
+int orc_pbi_batch_sample(int nel, const int *etype, const int *norder, const int *norie, const int *norif, const double *etav,
+                         int integration, int maxp, double *dof, long dof_ld, int nthreads) {
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic) num_threads(nthreads) reduction(+ : bad)
+  for (int e = 0; e < nel; e++)
+    bad += orc_pbi_element(etype ? etype[e] : ORC_MDLB, norder + 19 * e, norie + 12 * e, norif + 6 * e, etav + 24 * e, 3, integration, maxp,
+                           0x7ffffffu, orc_pbi_sample_fn, NULL, dof + dof_ld * e) != 0;
+  return bad;
+}
