@@ -431,3 +431,72 @@ def pbi_h1_batch(norder, norient_edge, norient_face, etav, fvert, fgrad, integra
     _lib.check(f(nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), int(integration), int(maxp), _ptr(etav), ncomp, _ptr(fvert), _ptr(fgrad),
                  int(np.prod(fgrad.shape[1:])), _ptr(m), _ptr(out), int(np.prod(out.shape[1:])), _ptr(info)))
     return dict(dof=out, info=info)
+
+
+def pbi_hcurl_points(norder, norient_edge, norient_face, maxp=9, etype=None):
+    """Points of the H(curl) Dirichlet interpolation (hp3d_gpu_pbi_hcurl_points; host only): dict(xi, npts, nrdofE, nodes)."""
+    norder, noe, nof, nel, et = _pbi_descr(norder, norient_edge, norient_face, etype)
+    f = _lib.lib().hp3d_gpu_pbi_hcurl_points
+    f.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_longlong] + [C.c_void_p] * 3
+    npts = np.zeros(nel, np.int32); nE = np.zeros(nel, np.int32); nodes = np.zeros((nel, 27, 4), np.int32)
+    _lib.check(f(nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), int(maxp), None, 0, _ptr(npts), _ptr(nE), _ptr(nodes)))
+    xi = np.zeros((nel, int(npts.max()) if nel else 0, 3))
+    _lib.check(f(nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), int(maxp), _ptr(xi), int(np.prod(xi.shape[1:])), None, None, None))
+    return dict(xi=xi, npts=npts, nrdofE=nE, nodes=nodes)
+
+
+def pbi_hcurl_batch(norder, norient_edge, norient_face, etav, fval, fcurl, maxp=9, mask=None, dof=None, etype=None, device=0):
+    """dhpedgeE / dhpfaceE_opt for all elements at once (hp3d_gpu_pbi_hcurl_batch).  fval, fcurl (nel, npts_max, 3, ncomp): the datum
+    and its curl pulled back to eta at `pbi_hcurl_points`; dof (nel, nrdofE_max, ncomp) incoming dofs or None.  Returns dict(dof, info)."""
+    norder, noe, nof, nel, et = _pbi_descr(norder, norient_edge, norient_face, etype)
+    L = _lib.lib()
+    _lib.check(L.hp3d_gpu_init(int(device)))
+    etav = np.ascontiguousarray(etav, dtype=np.float64).reshape(nel, 8, 3)
+    fval = np.ascontiguousarray(fval, dtype=np.float64)
+    ncomp = int(fval.shape[-1])
+    fval = fval.reshape(nel, -1, 3, ncomp)
+    fcurl = np.ascontiguousarray(fcurl, dtype=np.float64).reshape(fval.shape)
+    nE = pbi_hcurl_points(norder, noe, nof, maxp=maxp, etype=et)["nrdofE"]
+    out = np.zeros((nel, int(nE.max()) if nel else 0, ncomp)) if dof is None else np.ascontiguousarray(dof, dtype=np.float64).reshape(nel, -1, ncomp).copy()
+    m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint32)
+    info = np.zeros(nel, np.int32)
+    f = L.hp3d_gpu_pbi_hcurl_batch
+    ll = C.c_longlong
+    f.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, ll, C.c_void_p, C.c_void_p, ll, C.c_void_p]
+    _lib.check(f(nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), int(maxp), _ptr(etav), ncomp, _ptr(fval), _ptr(fcurl), int(np.prod(fval.shape[1:])),
+                 _ptr(m), _ptr(out), int(np.prod(out.shape[1:])), _ptr(info)))
+    return dict(dof=out, info=info)
+
+
+def pbi_hdiv_points(norder, norient_edge, norient_face, maxp=9, etype=None):
+    """Points of the H(div) Dirichlet interpolation (hp3d_gpu_pbi_hdiv_points; host only): dict(xi, npts, nrdofV, nodes)."""
+    norder, noe, nof, nel, et = _pbi_descr(norder, norient_edge, norient_face, etype)
+    f = _lib.lib().hp3d_gpu_pbi_hdiv_points
+    f.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_longlong] + [C.c_void_p] * 3
+    npts = np.zeros(nel, np.int32); nV = np.zeros(nel, np.int32); nodes = np.zeros((nel, 27, 4), np.int32)
+    _lib.check(f(nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), int(maxp), None, 0, _ptr(npts), _ptr(nV), _ptr(nodes)))
+    xi = np.zeros((nel, int(npts.max()) if nel else 0, 3))
+    _lib.check(f(nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), int(maxp), _ptr(xi), int(np.prod(xi.shape[1:])), None, None, None))
+    return dict(xi=xi, npts=npts, nrdofV=nV, nodes=nodes)
+
+
+def pbi_hdiv_batch(norder, norient_edge, norient_face, etav, fval, maxp=9, mask=None, dof=None, etype=None, device=0):
+    """dhpfaceV_opt for all elements at once (hp3d_gpu_pbi_hdiv_batch).  fval (nel, npts_max, 3, ncomp): the datum pulled back to eta
+    (Piola) at `pbi_hdiv_points`.  Returns dict(dof (nel, nrdofV_max, ncomp), info)."""
+    norder, noe, nof, nel, et = _pbi_descr(norder, norient_edge, norient_face, etype)
+    L = _lib.lib()
+    _lib.check(L.hp3d_gpu_init(int(device)))
+    etav = np.ascontiguousarray(etav, dtype=np.float64).reshape(nel, 8, 3)
+    fval = np.ascontiguousarray(fval, dtype=np.float64)
+    ncomp = int(fval.shape[-1])
+    fval = fval.reshape(nel, -1, 3, ncomp)
+    nV = pbi_hdiv_points(norder, noe, nof, maxp=maxp, etype=et)["nrdofV"]
+    out = np.zeros((nel, int(nV.max()) if nel else 0, ncomp)) if dof is None else np.ascontiguousarray(dof, dtype=np.float64).reshape(nel, -1, ncomp).copy()
+    m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint32)
+    info = np.zeros(nel, np.int32)
+    f = L.hp3d_gpu_pbi_hdiv_batch
+    ll = C.c_longlong
+    f.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p, ll, C.c_void_p, C.c_void_p, ll, C.c_void_p]
+    _lib.check(f(nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), int(maxp), _ptr(etav), ncomp, _ptr(fval), int(np.prod(fval.shape[1:])),
+                 _ptr(m), _ptr(out), int(np.prod(out.shape[1:])), _ptr(info)))
+    return dict(dof=out, info=info)

@@ -1094,30 +1094,31 @@ namespace {
 struct PbiSig {
   PbiSigHost h;   // node descriptors + points; the gradient table lives on the device only
   bool on_device = false;
-  double *d_wa = nullptr, *d_tan = nullptr, *d_grad = nullptr;
+  double *d_wa = nullptr, *d_tan = nullptr, *d_grad = nullptr, *d_tabE = nullptr;
   PbiNode *d_nodes = nullptr;
-  ~PbiSig() { cudaFree(d_wa); cudaFree(d_tan); cudaFree(d_grad); cudaFree(d_nodes); }
+  ~PbiSig() { cudaFree(d_wa); cudaFree(d_tan); cudaFree(d_grad); cudaFree(d_tabE); cudaFree(d_nodes); }
 };
 std::map<std::string, std::unique_ptr<PbiSig>> g_pbisigs;
 CelemStore g_pbi_store;   // grow-only device buffers of hp3d_gpu_pbi_h1_batch
 void release_pbi_signatures() { g_pbisigs.clear(); g_pbi_store.release(); }
 
 // descriptors + points of a signature (host only); `tables` also builds and uploads the gradient table
-PbiSig *pbi_signature(int et, const int *norder, const int *norie, const int *norif, int integration, int maxp, bool tables, std::string &err) {
-  const std::string key = std::to_string(integration) + "/" + std::to_string(maxp) + "/" + Plan::key(et, norder, norie, norif);
+PbiSig *pbi_signature(int et, const int *norder, const int *norie, const int *norif, int integration, int maxp, bool tables, std::string &err,
+                      int space = PBI_H1) {
+  const std::string key = std::to_string(space) + "/" + std::to_string(integration) + "/" + std::to_string(maxp) + "/" + Plan::key(et, norder, norie, norif);
   auto it = g_pbisigs.find(key);
   if (it == g_pbisigs.end()) {
     std::unique_ptr<PbiSig> S(new PbiSig());
-    if (!compile_pbi_signature(et, norder, norie, norif, integration, maxp, false, S->h)) { err = S->h.err; return nullptr; }
+    if (!compile_pbi_signature(et, norder, norie, norif, integration, maxp, false, S->h, space)) { err = S->h.err; return nullptr; }
     it = g_pbisigs.emplace(key, std::move(S)).first;
   }
   PbiSig *S = it->second.get();
   if (tables && !S->on_device) {
     PbiSigHost full;
-    if (!compile_pbi_signature(et, norder, norie, norif, integration, maxp, true, full)) { err = full.err; return nullptr; }
+    if (!compile_pbi_signature(et, norder, norie, norif, integration, maxp, true, full, space)) { err = full.err; return nullptr; }
     std::vector<PbiNode> nodes(full.node, full.node + full.nnode);
     if (dev_upload(full.wa, &S->d_wa, err) || dev_upload(full.tan, &S->d_tan, err) || dev_upload(full.grad, &S->d_grad, err) ||
-        dev_upload(nodes, &S->d_nodes, err))
+        dev_upload(full.tabE, &S->d_tabE, err) || dev_upload(nodes, &S->d_nodes, err))
       return nullptr;
     S->on_device = true;
   }
@@ -1238,6 +1239,142 @@ int hp3d_gpu_pbi_h1_batch(int nel, const int *etype, const int *norder, const in
   return HP3D_OK;
 }
 
+}  // extern "C"
+
+extern "C" {
+
+static int pbi_vec_points(int space, int nel, const int *etype, const int *norder, const int *norie, const int *norif, int maxp, double *xi,
+                          long long xi_ld, int *npts, int *nrdofE, int *nodes) {
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  if (nel < 0 || (nel > 0 && (!norder || !norie || !norif))) return fail(HP3D_EINVAL, "pbi_hcurl_points: null argument");
+  for (int e = 0; e < nel; e++) {
+    std::string err;
+    const PbiSig *S = pbi_signature(etype ? etype[e] : HP3D_MDLB, norder + 19 * e, norie + 12 * e, norif + 6 * e, 1, maxp, false, err, space);
+    if (!S) return fail(HP3D_EINVAL, "element %d: %s", e, err.c_str());
+    const PbiSigHost &h = S->h;
+    if (npts) npts[e] = h.npts;
+    if (nrdofE) nrdofE[e] = h.nEF;
+    if (nodes) {
+      int *q = nodes + (size_t)e * 4 * PBI_MAXNODE;
+      for (int i = 0; i < 4 * PBI_MAXNODE; i++) q[i] = 0;
+      for (int i = 0; i < h.nnode; i++) { q[4 * i] = h.node[i].t0; q[4 * i + 1] = h.node[i].n; q[4 * i + 2] = h.node[i].p0; q[4 * i + 3] = h.node[i].np; }
+    }
+    if (xi) {
+      if (xi_ld < 3LL * h.npts) return fail(HP3D_EINVAL, "pbi_hcurl_points: xi_ld %lld < 3*npts = %d (element %d)", xi_ld, 3 * h.npts, e);
+      memcpy(xi + (size_t)e * xi_ld, h.xi.data(), sizeof(double) * 3 * h.npts);
+    }
+  }
+  return HP3D_OK;
+}
+
+static int pbi_vec_batch(int space, int nel, const int *etype, const int *norder, const int *norie, const int *norif, int maxp, const double *etav,
+                         int ncomp, const double *fval, const double *fcurl, long long f_ld, const unsigned *mask, double *dof,
+                         long long dof_ld, int *info) {
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
+  if (nel < 0 || (nel > 0 && (!norder || !norie || !norif || !etav || !fval || (space == PBI_HCURL && !fcurl) || !dof))) return fail(HP3D_EINVAL, "pbi_hcurl/hdiv: null argument");
+  if (ncomp < 1 || ncomp > PBI_MAXCOMP) return fail(HP3D_EINVAL, "pbi_hcurl: ncomp = %d outside 1..%d (split the components over several calls)", ncomp, PBI_MAXCOMP);
+  if (nel == 0) return HP3D_OK;
+  struct Group { PbiSig *S; std::vector<int> el; };
+  std::map<const PbiSig *, size_t> where;
+  std::vector<Group> groups;
+  for (int e = 0; e < nel; e++) {
+    std::string err;
+    PbiSig *S = pbi_signature(etype ? etype[e] : HP3D_MDLB, norder + 19 * e, norie + 12 * e, norif + 6 * e, 1, maxp, true, err, space);
+    if (!S) return fail(HP3D_EINVAL, "element %d: %s", e, err.c_str());
+    if (dof_ld < (long long)ncomp * S->h.nEF) return fail(HP3D_EINVAL, "pbi_hcurl: dof_ld %lld < ncomp*(edge+face dofs) = %d (element %d)", dof_ld, ncomp * S->h.nEF, e);
+    if (f_ld < 3LL * ncomp * S->h.npts) return fail(HP3D_EINVAL, "pbi_hcurl: f_ld %lld < 3*ncomp*npts = %d (element %d)", f_ld, 3 * ncomp * S->h.npts, e);
+    auto w = where.find(S);
+    if (w == where.end()) { w = where.emplace(S, groups.size()).first; groups.push_back(Group{S, {}}); }
+    groups[w->second].el.push_back(e);
+  }
+  // workspace per CTA: rows [CE | E | GH | Rc | Rv] x 3 np doubles + the (nt + ncomp) x nt system
+  struct LaunchDims { long long stride[2]; int ny[2]; };
+  std::vector<LaunchDims> dims(groups.size());
+  long long need_ws = 0;
+  std::vector<int> elist; elist.reserve(nel);
+  for (size_t g = 0; g < groups.size(); g++) {
+    const PbiSigHost &h = groups[g].S->h;
+    const int n = (int)groups[g].el.size();
+    const int first[3] = {h.nrv, h.nrv + h.nre, h.nrv + h.nre + h.nrf};
+    for (int s = 0; s < 2; s++) {
+      long long st = 0;
+      for (int i = first[s]; i < first[s + 1]; i++) {
+        const PbiNode &nd = h.node[i];
+        if (nd.n <= 0) continue;
+        const long long nt = nd.n + nd.nh, rows = (s ? 2LL * nd.n : nd.n) + nd.nh + (s ? 2 : 1) * ncomp;
+        st = std::max(st, rows * 3LL * nd.np + (nt + ncomp) * nt);
+      }
+      dims[g].stride[s] = st; dims[g].ny[s] = 0;
+      if (!st) continue;
+      const long long per_row = st * (first[s + 1] - first[s]) * (long long)sizeof(double);
+      dims[g].ny[s] = (int)std::max(1LL, std::min((long long)n, (1LL << 30) / per_row));
+      need_ws = std::max(need_ws, per_row * dims[g].ny[s]);
+    }
+    elist.insert(elist.end(), groups[g].el.begin(), groups[g].el.end());
+  }
+  const size_t b_ev = sizeof(double) * 24 * (size_t)nel, b_f = std::max(sizeof(double) * (size_t)f_ld * nel, sizeof(double)), b_d = sizeof(double) * (size_t)dof_ld * nel;
+  double *dev_ev = (double *)g_pbi_store.get(0, b_ev), *dev_fv = (double *)g_pbi_store.get(1, b_f), *dev_fc = (double *)g_pbi_store.get(2, b_f),
+         *dev_d = (double *)g_pbi_store.get(3, std::max(b_d, sizeof(double))), *dev_ws = (double *)g_pbi_store.get(4, (size_t)std::max(need_ws, 8LL));
+  unsigned *dev_m = mask ? (unsigned *)g_pbi_store.get(5, sizeof(unsigned) * nel) : nullptr;
+  int *dinfo = (int *)g_pbi_store.get(6, sizeof(int) * nel), *dev_el = (int *)g_pbi_store.get(7, sizeof(int) * nel);
+  if (!dev_ev || !dev_fv || !dev_fc || !dev_d || !dev_ws || (mask && !dev_m) || !dinfo || !dev_el)
+    return fail(HP3D_ENOMEM, "pbi_hcurl: out of device memory (%zu bytes of inputs, %lld bytes of workspace)", b_ev + 2 * b_f + b_d, need_ws);
+  CUDA_TRY(cudaMemcpyAsync(dev_ev, etav, b_ev, cudaMemcpyHostToDevice, g_compute));
+  if (f_ld > 0) {
+    CUDA_TRY(cudaMemcpyAsync(dev_fv, fval, sizeof(double) * (size_t)f_ld * nel, cudaMemcpyHostToDevice, g_compute));
+    if (fcurl) CUDA_TRY(cudaMemcpyAsync(dev_fc, fcurl, sizeof(double) * (size_t)f_ld * nel, cudaMemcpyHostToDevice, g_compute));
+  }
+  if (b_d) CUDA_TRY(cudaMemcpyAsync(dev_d, dof, b_d, cudaMemcpyHostToDevice, g_compute));   // edges outside the mask keep (and contribute) their dofs
+  if (mask) CUDA_TRY(cudaMemcpyAsync(dev_m, mask, sizeof(unsigned) * nel, cudaMemcpyHostToDevice, g_compute));
+  CUDA_TRY(cudaMemcpyAsync(dev_el, elist.data(), sizeof(int) * nel, cudaMemcpyHostToDevice, g_compute));
+  CUDA_TRY(cudaMemsetAsync(dinfo, 0, sizeof(int) * nel, g_compute));
+  size_t pos = 0;
+  for (size_t g = 0; g < groups.size(); g++) {
+    const PbiSig &S = *groups[g].S;
+    const PbiSigHost &h = S.h;
+    const int n = (int)groups[g].el.size();
+    const int first[3] = {h.nrv, h.nrv + h.nre, h.nrv + h.nre + h.nrf};
+    PbiEArgs A;
+    A.wa = S.d_wa; A.tan = S.d_tan; A.grad = S.d_grad; A.tabE = S.d_tabE; A.nodes = S.d_nodes; A.nH = h.nH; A.nEF = h.nEF; A.nrv = h.nrv; A.npts = h.npts;
+    A.ncomp = ncomp; A.node0 = 0; A.nel = n; A.space = space; A.elems = dev_el + pos; A.etav = dev_ev; A.fval = dev_fv; A.fcurl = dev_fc; A.mask = dev_m; A.dof = dev_d;
+    A.f_ld = f_ld; A.dof_ld = dof_ld; A.ws = dev_ws; A.ws_stride = 0; A.info = dinfo;
+    for (int s = 0; s < 2; s++) {   // edges, then faces
+      if (!dims[g].stride[s]) continue;
+      A.node0 = first[s]; A.ws_stride = dims[g].stride[s];
+      pbi_hcurl_kernel<<<dim3(first[s + 1] - first[s], dims[g].ny[s]), 256, 0, g_compute>>>(A);
+      g_launches++;
+    }
+    pos += n;
+  }
+  CUDA_TRY(cudaGetLastError());
+  std::vector<int> hinfo(info ? 0 : nel);
+  if (b_d) CUDA_TRY(cudaMemcpyAsync(dof, dev_d, b_d, cudaMemcpyDeviceToHost, g_compute));
+  CUDA_TRY(cudaMemcpyAsync(info ? info : hinfo.data(), dinfo, sizeof(int) * nel, cudaMemcpyDeviceToHost, g_compute));
+  CUDA_TRY(cudaStreamSynchronize(g_compute));
+  return HP3D_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+int hp3d_gpu_pbi_hcurl_points(int nel, const int *etype, const int *norder, const int *norie, const int *norif, int maxp, double *xi,
+                              long long xi_ld, int *npts, int *nrdofE, int *nodes) {
+  return pbi_vec_points(PBI_HCURL, nel, etype, norder, norie, norif, maxp, xi, xi_ld, npts, nrdofE, nodes);
+}
+int hp3d_gpu_pbi_hcurl_batch(int nel, const int *etype, const int *norder, const int *norie, const int *norif, int maxp, const double *etav,
+                             int ncomp, const double *fval, const double *fcurl, long long f_ld, const unsigned *mask, double *dof,
+                             long long dof_ld, int *info) {
+  return pbi_vec_batch(PBI_HCURL, nel, etype, norder, norie, norif, maxp, etav, ncomp, fval, fcurl, f_ld, mask, dof, dof_ld, info);
+}
+int hp3d_gpu_pbi_hdiv_points(int nel, const int *etype, const int *norder, const int *norie, const int *norif, int maxp, double *xi,
+                             long long xi_ld, int *npts, int *nrdofV, int *nodes) {
+  return pbi_vec_points(PBI_HDIV, nel, etype, norder, norie, norif, maxp, xi, xi_ld, npts, nrdofV, nodes);
+}
+int hp3d_gpu_pbi_hdiv_batch(int nel, const int *etype, const int *norder, const int *norie, const int *norif, int maxp, const double *etav,
+                            int ncomp, const double *fval, long long f_ld, const unsigned *mask, double *dof, long long dof_ld, int *info) {
+  return pbi_vec_batch(PBI_HDIV, nel, etype, norder, norie, norif, maxp, etav, ncomp, fval, nullptr, f_ld, mask, dof, dof_ld, info);
+}
 }  // extern "C"
 
 extern "C" int hp3d_gpu_chunk_plan_debug(long long ntot, int cap, int nlanes, int max_chunk, long long *sizes, int cap_sizes) {

@@ -30,15 +30,19 @@ namespace hp3d {
 constexpr int PBI_MAXNODE = 27;   // 8 + 12 + 6 + 1 nodes of a brick
 constexpr int PBI_MAXCOMP = 12;
 
-struct PbiNode { int kind, t0, n, nknown, p0, np; };   // kind 0 vertex, 1 edge, 2 face, 3 middle ; dofs [t0, t0+n) ; points [p0, p0+np)
+struct PbiNode { int kind, t0, n, nknown, p0, np, th0, nh; };   // kind 0 vertex, 1 edge, 2 face, 3 middle ; dofs [t0, t0+n) ; points [p0, p0+np)
+                                                                // H(curl): [t0, t0+n) are E dofs, [th0, th0+nh) the node's H1 bubbles (multipliers)
+
+enum PbiSpace { PBI_H1 = 0, PBI_HCURL = 1, PBI_HDIV = 2 };
 
 struct PbiSigHost {
-  int etype = 1, nH = 0, nrv = 8, nre = 12, nrf = 6, nnode = 27, npts = 0;
+  int etype = 1, space = 0, nH = 0, nEF = 0, nrv = 8, nre = 12, nrf = 6, nnode = 27, npts = 0;   // nEF: H(curl) dofs of edges + faces
   PbiNode node[PBI_MAXNODE];
   std::vector<double> xi;     // (3, npts) master coordinates
   std::vector<double> wa;     // (npts) quadrature weights
   std::vector<double> tan;    // (6, npts) d xi / d t of the edge (first 3) or face (both) parametrisation
   std::vector<double> grad;   // [3][nH][npts] master gradients of the element's H1 functions
+  std::vector<double> tabE;   // H(curl) only: [6][nEF][npts] master values (3) and curls (3) of the edge and face functions
   std::string err;
 };
 
@@ -51,10 +55,10 @@ static const int PR_EDGE_VERT[9][2] = {{1, 2}, {2, 3}, {1, 3}, {4, 5}, {5, 6}, {
 
 // points + tables of one signature.  `tables = false` only fills the node descriptors and the points (size queries).
 inline bool compile_pbi_signature(int etype, const int *norder, const int *norie, const int *norif, int integration, int maxp, bool tables,
-                                  PbiSigHost &S) {
+                                  PbiSigHost &S, int space = PBI_H1) {
   using namespace detail;
   S = PbiSigHost();
-  S.etype = etype;
+  S.etype = etype; S.space = space;
   const bool brick = etype == 1;
   if (!brick && etype != 3) { S.err = "unknown element type (HP3D_MDLB = 1 and HP3D_MDLP = 3 are implemented)"; return false; }
   if (integration < 0 || integration > 2) { S.err = "INTEGRATION must be 0, 1 or 2"; return false; }
@@ -84,11 +88,42 @@ inline bool compile_pbi_signature(int etype, const int *norder, const int *norie
     PbiNode &nd = S.node[i];
     nd.kind = i < nrv ? 0 : (i < nrv + nre ? 1 : (i < nrv + nre + nrf ? 2 : 3));
     nd.t0 = off; nd.n = cnt[i]; off += cnt[i];
-    nd.p0 = 0; nd.np = 0; nd.nknown = 0;
+    nd.p0 = 0; nd.np = 0; nd.nknown = 0; nd.th0 = 0; nd.nh = 0;
   }
   S.nH = off;
   for (int i = nrv; i < S.nnode; i++)
     S.node[i].nknown = S.node[i].kind == 1 ? nrv : (S.node[i].kind == 2 ? S.node[nrv + nre].t0 : S.node[S.nnode - 1].t0);
+  if (space == PBI_HCURL) {   // E dofs of the edge and face nodes; the H1 bubbles of a face become its multipliers (dhpfaceE_opt.F90:329-347)
+    int offE = 0;
+    for (int i = 0; i < S.nnode; i++) {
+      PbiNode &nd = S.node[i];
+      nd.th0 = nd.t0; nd.nh = nd.kind == 2 ? nd.n : 0;
+      int nE = 0;
+      if (nd.kind == 1) nE = norder[i - nrv];
+      else if (nd.kind == 2) {
+        const int f = i - nrv - nre, o = norder[nre + f];
+        nE = (!brick && f < 2) ? (o - 1) * o : (o / 10) * (o % 10 - 1) + (o / 10 - 1) * (o % 10);
+      }
+      nd.t0 = offE; nd.n = nE; offE += nE;
+      nd.nknown = 0;
+    }
+    S.nEF = offE;
+    for (int f = 0; f < nrf; f++) S.node[nrv + nre + f].nknown = S.node[nrv + nre].t0;   // all edge dofs
+  }
+  if (space == PBI_HDIV) {    // V dofs of the face nodes (dhpfaceV_opt.F90): no multipliers, nothing to subtract
+    int offV = 0;
+    for (int i = 0; i < S.nnode; i++) {
+      PbiNode &nd = S.node[i];
+      nd.th0 = 0; nd.nh = 0; nd.nknown = 0;
+      int nV = 0;
+      if (nd.kind == 2) {
+        const int f = i - nrv - nre, o = norder[nre + f];
+        nV = (!brick && f < 2) ? o * (o + 1) / 2 : (o / 10) * (o % 10);
+      }
+      nd.t0 = offV; nd.n = nV; offV += nV;
+    }
+    S.nEF = offV;
+  }
   // ---- points
   auto cap = [&](int p) { return std::min(p + integration, maxp); };
   auto vert = [&](int v1) { return brick ? std::array<double, 3>{(double)VSIDE[v1 - 1][0], (double)VSIDE[v1 - 1][1], (double)VSIDE[v1 - 1][2]}
@@ -149,7 +184,7 @@ inline bool compile_pbi_signature(int etype, const int *norder, const int *norie
     nd.p0 = (int)S.wa.size();
     const int zero[6] = {0, 0, 0, 0, 0, 0};
     const double t0[6] = {0, 0, 0, 0, 0, 0};
-    if (nd.n > 0) {
+    if (nd.n > 0 && space == PBI_H1) {
       if (brick) {
         int pmax[3], nq[3];
         hexa_axis_max_order(norder, zero, pmax);
@@ -189,6 +224,31 @@ inline bool compile_pbi_signature(int etype, const int *norder, const int *norie
       for (int k = 0; k < S.nH; k++)
         for (int j = 0; j < 3; j++) S.grad[((size_t)j * S.nH + k) * S.npts + l] = der[3 * k + j];
     }
+    if (space == PBI_HDIV) {   // face functions: sign * H_normal(side) Q Q e_normal (values in planes 0..2, planes 3..5 unused)
+      const std::vector<TensorDof> fd = hexa_dofs_Hdiv(norder, norif);
+      if ((int)fd.size() < S.nEF) { S.err = "internal: H(div) dof count mismatch"; return false; }
+      S.tabE.assign((size_t)6 * S.nEF * S.npts, 0.0);
+      for (int l = 0; l < S.npts; l++) {
+        ZVals Z[3];
+        for (int a = 0; a < 3; a++) Z[a] = eval_z(ptab, S.xi[3 * l + a]);
+        for (int k = 0; k < S.nEF; k++) {
+          const TensorDof &d = fd[k];
+          const int a = d.fam, b = (a + 1) % 3, c = (a + 2) % 3;
+          S.tabE[((size_t)a * S.nEF + k) * S.npts + l] = d.sgn * Z[a].H[d.idx[a]] * Z[b].Q[d.idx[b]] * Z[c].Q[d.idx[c]];
+        }
+      }
+    }
+    if (space == PBI_HCURL) {
+      const std::vector<TensorDof> fd = hexa_dofs_Hcurl(norder, norie, norif);
+      if ((int)fd.size() < S.nEF) { S.err = "internal: H(curl) dof count mismatch"; return false; }
+      std::vector<double> v3((size_t)3 * fd.size()), c3((size_t)3 * fd.size());
+      S.tabE.assign((size_t)6 * S.nEF * S.npts, 0.0);
+      for (int l = 0; l < S.npts; l++) {
+        hexa_shape_at(ES_HCURL, fd, ptab, &S.xi[3 * l], v3.data(), c3.data());
+        for (int k = 0; k < S.nEF; k++)
+          for (int j = 0; j < 3; j++) { S.tabE[((size_t)j * S.nEF + k) * S.npts + l] = v3[3 * k + j]; S.tabE[((size_t)(3 + j) * S.nEF + k) * S.npts + l] = c3[3 * k + j]; }
+      }
+    }
   } else {
     TriList TG;
     const TriList none;
@@ -198,6 +258,36 @@ inline bool compile_pbi_signature(int etype, const int *norder, const int *norie
       prism_shape_at(ES_H1, hd, TG, none, MAXN1D - 1, &S.xi[3 * l], val.data(), der.data());
       for (int k = 0; k < S.nH; k++)
         for (int j = 0; j < 3; j++) S.grad[((size_t)j * S.nH + k) * S.npts + l] = der[3 * k + j];
+    }
+    if (space == PBI_HDIV) {   // face functions only (hp3d_gpu_prism_shape, space 2)
+      TriList TZ, TH;
+      const std::vector<PrismDof> fd = prism_dofs_Hdiv_faces(norder, norif, TZ, TH);
+      if ((int)fd.size() != S.nEF) { S.err = "internal: H(div) dof count mismatch"; return false; }
+      S.tabE.assign((size_t)6 * S.nEF * S.npts, 0.0);
+      for (int l = 0; l < S.npts; l++) {
+        const TriVals v0 = eval_list(TZ, S.xi[3 * l], S.xi[3 * l + 1]), v1 = eval_list(TH, S.xi[3 * l], S.xi[3 * l + 1]);
+        const ZVals Z = eval_z(MAXN1D - 1, S.xi[3 * l + 2]);
+        for (int k = 0; k < S.nEF; k++) {
+          const PrismDof &q = fd[k];
+          const double *t = (q.list == 0 ? v0 : v1).at(q.t), sg = q.sgn;
+          double V[3];
+          if (q.list == 0) { V[0] = V[1] = 0.0; V[2] = sg * t[0] * Z.H[q.zi]; }
+          else { V[0] = sg * t[1] * Z.Q[q.zi]; V[1] = -sg * t[0] * Z.Q[q.zi]; V[2] = 0.0; }
+          for (int j = 0; j < 3; j++) S.tabE[((size_t)j * S.nEF + k) * S.npts + l] = V[j];
+        }
+      }
+    }
+    if (space == PBI_HCURL) {
+      TriList F0, F1;
+      const std::vector<PrismDof> fd = prism_dofs_Hcurl(norder, norie, norif, F0, F1);
+      if ((int)fd.size() < S.nEF) { S.err = "internal: H(curl) dof count mismatch"; return false; }
+      std::vector<double> v3((size_t)3 * fd.size()), c3((size_t)3 * fd.size());
+      S.tabE.assign((size_t)6 * S.nEF * S.npts, 0.0);
+      for (int l = 0; l < S.npts; l++) {
+        prism_shape_at(ES_HCURL, fd, F0, F1, MAXN1D - 1, &S.xi[3 * l], v3.data(), c3.data());
+        for (int k = 0; k < S.nEF; k++)
+          for (int j = 0; j < 3; j++) { S.tabE[((size_t)j * S.nEF + k) * S.npts + l] = v3[3 * k + j]; S.tabE[((size_t)(3 + j) * S.nEF + k) * S.npts + l] = c3[3 * k + j]; }
+      }
     }
   }
   return true;
@@ -365,6 +455,222 @@ __global__ void __launch_bounds__(256) pbi_node_kernel(PbiArgs A) {
     }
     __syncthreads();
     for (int q = tid; q < nc * n; q += blockDim.x) { const int j = q / nc, c = q % nc; dof[(long long)(nd.t0 + j) * nc + c] = G[(long long)(n + c) * n + j]; }
+  }
+}
+
+// ---- H(curl) Dirichlet dofs: edge/dhpedgeE.F90:33-391, face/dhpfaceE_opt.F90:33-549 -------------------------------------------------
+// The datum enters pulled back to eta at the points of the signature (INTEGRATION = 1): E_eta = dxdeta^T E and
+// curl_eta = det(dxdeta) dxdeta^-1 curl E (dhpfaceE_opt.F90:249-259).  An edge projects the tangential component in L2; a face
+// minimises the normal component of curl_eta (E_eta - known edges - sum dof_j E_j) subject to orthogonality of the tangential
+// residual to the surface gradients of the face's H1 bubbles: the saddle-point system [C B; B^T 0] of :353-375, solved by LU with
+// partial pivoting like the reference's DGETRF (:398).
+struct PbiEArgs {
+  const double *wa, *tan, *grad, *tabE;
+  const PbiNode *nodes;
+  int nH, nEF, nrv, npts, ncomp, node0, nel, space;   // space: PBI_HCURL or PBI_HDIV (faces only, L2 projection of the normal component)
+  const int *elems;
+  const double *etav, *fval, *fcurl;   // fval / fcurl: (ncomp, 3, npts) per element, component fastest, stride f_ld
+  const unsigned *mask;
+  double *dof;                         // (ncomp, nEF) per element, stride dof_ld
+  long long f_ld, dof_ld;
+  double *ws; long long ws_stride;
+  int *info;
+};
+
+// out[(orow0 + r) * ldo + ocol0 + j] = sum_k D[(xrow0 + r) * K3 + k] * D[(yrow0 + j) * K3 + k], r < nx, j < ny (whole CTA, 256 threads)
+__device__ inline void pbi_rows_product(const double *D, int K3, int xrow0, int nx, int yrow0, int ny, double *out, int ldo, int orow0, int ocol0,
+                                        double (*As)[68], double (*Bs)[68]) {
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  for (int r0 = 0; r0 < nx; r0 += 64)
+    for (int j0 = 0; j0 < ny; j0 += 64) {
+      double acc[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+      for (int k0 = 0; k0 < K3; k0 += 16) {
+        const int row = tid >> 2, kk = (tid & 3) * 4;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int k = k0 + kk + q;
+          As[kk + q][row] = (r0 + row < nx && k < K3) ? D[(long long)(xrow0 + r0 + row) * K3 + k] : 0.0;
+          Bs[kk + q][row] = (j0 + row < ny && k < K3) ? D[(long long)(yrow0 + j0 + row) * K3 + k] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          double a[4], b[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) { a[q] = As[k][ty * 4 + q]; b[q] = Bs[k][tx * 4 + q]; }
+#pragma unroll
+          for (int p = 0; p < 4; p++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[p][q] += a[p] * b[q];
+        }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int p = 0; p < 4; p++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int r = r0 + ty * 4 + p, j = j0 + tx * 4 + q;
+          if (r < nx && j < ny) out[(long long)(orow0 + r) * ldo + ocol0 + j] = acc[p][q];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) pbi_hcurl_kernel(PbiEArgs A) {
+  __shared__ double As[16][68], Bs[16][68];
+  __shared__ double s_red[8];
+  __shared__ int s_idx[8], s_piv;
+  const int tid = threadIdx.x, inode = A.node0 + blockIdx.x;
+  const PbiNode nd = A.nodes[inode];
+  const int nE = nd.n, nHb = nd.nh, np = nd.np, nc = A.ncomp, K3 = 3 * np, nt = nE + nHb;
+  if (nE <= 0) return;
+  const bool hdiv = A.space == PBI_HDIV;
+  const bool face = nd.kind == 2 && !hdiv;   // the saddle-point path of dhpfaceE_opt
+  // rows of D: [CE (nE, faces only) | E (nE) | GH (nHb) | Rc (nc, faces only) | Rv (nc)]
+  const int rE = face ? nE : 0, rG = rE + nE, rRc = rG + nHb, rRv = rRc + (face ? nc : 0), nrows = rRv + nc;
+  double *D = A.ws + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * A.ws_stride;
+  double *W = D + (long long)nrows * K3;   // [(nt + nc)][nt]: rows < nt the (symmetric) system, rows >= nt the load vectors
+  const long long HS = (long long)A.nH * A.npts, ES = (long long)A.nEF * A.npts;
+  for (int ie = blockIdx.y; ie < A.nel; ie += gridDim.y) {
+    const int e = A.elems[ie];
+    if (A.mask && !((A.mask[e] >> inode) & 1u)) continue;
+    const double *ev = A.etav + (long long)e * 24;
+    double *dof = A.dof + (long long)e * A.dof_ld;
+    const double *fv = A.fval + (long long)e * A.f_ld, *fc = A.fcurl + (long long)e * A.f_ld;
+    __syncthreads();
+    for (int l = tid; l < np; l += blockDim.x) {
+      const int gl = nd.p0 + l;
+      double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int v = 0; v < A.nrv; v++) {
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+          const double g = A.grad[m * HS + (long long)v * A.npts + gl];
+#pragma unroll
+          for (int c = 0; c < 3; c++) J[c + 3 * m] += ev[3 * v + c] * g;
+        }
+      }
+      const double det = J[0] * J[4] * J[8] + J[1] * J[5] * J[6] + J[2] * J[3] * J[7] - J[2] * J[4] * J[6] - J[0] * J[5] * J[7] - J[1] * J[3] * J[8];
+      if (!(det > 0.0)) A.info[e] = -1;
+      double Ji[9];
+      Ji[0] = (J[4] * J[8] - J[5] * J[7]) / det; Ji[1] = (-J[1] * J[8] + J[2] * J[7]) / det; Ji[2] = (J[1] * J[5] - J[2] * J[4]) / det;
+      Ji[3] = (J[5] * J[6] - J[3] * J[8]) / det; Ji[4] = (J[0] * J[8] - J[2] * J[6]) / det; Ji[5] = (-J[0] * J[5] + J[2] * J[3]) / det;
+      Ji[6] = (J[3] * J[7] - J[4] * J[6]) / det; Ji[7] = (-J[0] * J[7] + J[1] * J[6]) / det; Ji[8] = (J[0] * J[4] - J[1] * J[3]) / det;
+      const double *t = A.tan + 6LL * gl;
+      double d1[3], d2[3], dir[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) { d1[c] = J[c] * t[0] + J[c + 3] * t[1] + J[c + 6] * t[2]; d2[c] = J[c] * t[3] + J[c + 3] * t[4] + J[c + 6] * t[5]; }
+      if (nd.kind != 2) { dir[0] = d1[0]; dir[1] = d1[1]; dir[2] = d1[2]; }
+      else { dir[0] = d1[1] * d2[2] - d1[2] * d2[1]; dir[1] = d1[2] * d2[0] - d1[0] * d2[2]; dir[2] = d1[0] * d2[1] - d1[1] * d2[0]; }
+      const double bj = sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+      dir[0] /= bj; dir[1] /= bj; dir[2] /= bj;
+      const double sw = sqrt(A.wa[gl] * bj);
+      // master -> eta: value u = Ji^T E^ (u_i = sum_a E^_a Ji[a + 3i]), curl cu = J C^ / det
+      double Rv[3 * PBI_MAXCOMP], Rc[3 * PBI_MAXCOMP];
+      for (int q = 0; q < 3 * nc; q++) { Rv[q] = fv[(long long)gl * 3 * nc + q]; Rc[q] = face ? fc[(long long)gl * 3 * nc + q] : 0.0; }
+      for (int k = 0; k < nd.nknown; k++) {   // the edges' contributions (dhpfaceE_opt.F90:275-293)
+        const double e0 = A.tabE[(long long)k * A.npts + gl], e1 = A.tabE[ES + (long long)k * A.npts + gl], e2 = A.tabE[2 * ES + (long long)k * A.npts + gl];
+        const double c0 = A.tabE[3 * ES + (long long)k * A.npts + gl], c1 = A.tabE[4 * ES + (long long)k * A.npts + gl], c2 = A.tabE[5 * ES + (long long)k * A.npts + gl];
+        const double u[3] = {e0 * Ji[0] + e1 * Ji[1] + e2 * Ji[2], e0 * Ji[3] + e1 * Ji[4] + e2 * Ji[5], e0 * Ji[6] + e1 * Ji[7] + e2 * Ji[8]};
+        const double cu[3] = {(J[0] * c0 + J[3] * c1 + J[6] * c2) / det, (J[1] * c0 + J[4] * c1 + J[7] * c2) / det, (J[2] * c0 + J[5] * c1 + J[8] * c2) / det};
+        for (int c = 0; c < nc; c++) {
+          const double z = dof[(long long)k * nc + c];
+          Rv[c] -= z * u[0]; Rv[c + nc] -= z * u[1]; Rv[c + 2 * nc] -= z * u[2];
+          Rc[c] -= z * cu[0]; Rc[c + nc] -= z * cu[1]; Rc[c + 2 * nc] -= z * cu[2];
+        }
+      }
+      for (int c = 0; c < nc; c++)
+        for (int i = 0; i < 3; i++) {
+          D[(long long)(rRv + c) * K3 + 3 * l + i] = Rv[c + nc * i] * sw;
+          if (face) D[(long long)(rRc + c) * K3 + 3 * l + i] = Rc[c + nc * i] * sw;
+        }
+      for (int j = 0; j < nE; j++) {
+        const int k = nd.t0 + j;
+        const double e0 = A.tabE[(long long)k * A.npts + gl], e1 = A.tabE[ES + (long long)k * A.npts + gl], e2 = A.tabE[2 * ES + (long long)k * A.npts + gl];
+        double v[3] = {e0 * Ji[0] + e1 * Ji[1] + e2 * Ji[2], e0 * Ji[3] + e1 * Ji[4] + e2 * Ji[5], e0 * Ji[6] + e1 * Ji[7] + e2 * Ji[8]};
+        if (hdiv) { v[0] = (J[0] * e0 + J[3] * e1 + J[6] * e2) / det; v[1] = (J[1] * e0 + J[4] * e1 + J[7] * e2) / det; v[2] = (J[2] * e0 + J[5] * e1 + J[8] * e2) / det; }   // dhpfaceV_opt.F90:223-225
+        const double pr = v[0] * dir[0] + v[1] * dir[1] + v[2] * dir[2];
+        if (!face) { v[0] = pr * dir[0]; v[1] = pr * dir[1]; v[2] = pr * dir[2]; }            // dhpedgeE.F90:218-219, dhpfaceV_opt.F90:226-227
+        else { v[0] -= pr * dir[0]; v[1] -= pr * dir[1]; v[2] -= pr * dir[2]; }                 // dhpfaceE_opt.F90:313-314
+        for (int i = 0; i < 3; i++) D[(long long)(rE + j) * K3 + 3 * l + i] = v[i] * sw;
+        if (face) {
+          const double c0 = A.tabE[3 * ES + (long long)k * A.npts + gl], c1 = A.tabE[4 * ES + (long long)k * A.npts + gl], c2 = A.tabE[5 * ES + (long long)k * A.npts + gl];
+          const double cv[3] = {(J[0] * c0 + J[3] * c1 + J[6] * c2) / det, (J[1] * c0 + J[4] * c1 + J[7] * c2) / det, (J[2] * c0 + J[5] * c1 + J[8] * c2) / det};
+          const double pc = cv[0] * dir[0] + cv[1] * dir[1] + cv[2] * dir[2];
+          for (int i = 0; i < 3; i++) D[(long long)j * K3 + 3 * l + i] = pc * dir[i] * sw;     // :315-316
+        }
+      }
+      for (int j = 0; j < nHb; j++) {   // surface gradients of the face's H1 bubbles (:329-347)
+        const int k = nd.th0 + j;
+        const double g0 = A.grad[(long long)k * A.npts + gl], g1 = A.grad[HS + (long long)k * A.npts + gl], g2 = A.grad[2 * HS + (long long)k * A.npts + gl];
+        double dv[3] = {g0 * Ji[0] + g1 * Ji[1] + g2 * Ji[2], g0 * Ji[3] + g1 * Ji[4] + g2 * Ji[5], g0 * Ji[6] + g1 * Ji[7] + g2 * Ji[8]};
+        const double pr = dv[0] * dir[0] + dv[1] * dir[1] + dv[2] * dir[2];
+        for (int i = 0; i < 3; i++) D[(long long)(rG + j) * K3 + 3 * l + i] = (dv[i] - pr * dir[i]) * sw;
+      }
+    }
+    __syncthreads();
+    // ---- the system and its load vectors
+    if (!face) {
+      pbi_rows_product(D, K3, 0, nE, 0, nE, W, nt, 0, 0, As, Bs);           // mass matrix of the tangential component
+      pbi_rows_product(D, K3, rRv, nc, 0, nE, W, nt, nt, 0, As, Bs);
+    } else {
+      pbi_rows_product(D, K3, 0, nE, 0, nE, W, nt, 0, 0, As, Bs);           // curl-curl (DSYRK, :353)
+      pbi_rows_product(D, K3, rRc, nc, 0, nE, W, nt, nt, 0, As, Bs);
+      if (nHb > 0) {
+        pbi_rows_product(D, K3, rG, nHb, rE, nE, W, nt, nE, 0, As, Bs);     // B^T (DGEMM, :356)
+        pbi_rows_product(D, K3, rRv, nc, rG, nHb, W, nt, nt, nE, As, Bs);
+        __syncthreads();
+        for (int q = tid; q < nHb * nE; q += blockDim.x) { const int j = q / nE, i = q % nE; W[(long long)i * nt + nE + j] = W[(long long)(nE + j) * nt + i]; }
+        for (int q = tid; q < nHb * nHb; q += blockDim.x) W[(long long)(nE + q / nHb) * nt + nE + q % nHb] = 0.0;
+      }
+    }
+    __syncthreads();
+    // ---- LU with partial pivoting of M (nt x nt) with the load vectors as extra columns.  Memory W[r * nt + i] is read as the
+    // column-major matrix Wc(i, r) = [M | b_1 .. b_nc] (M is symmetric), so that columns are contiguous.
+    const int ncol = nt + nc;
+    bool bad = false;
+    for (int k = 0; k < nt; k++) {
+      // pivot search in column k, rows i >= k
+      double best = -1.0; int bi = k;
+      for (int i = k + tid; i < nt; i += blockDim.x) { const double a = fabs(W[(long long)k * nt + i]); if (a > best) { best = a; bi = i; } }
+      for (int o = 16; o; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if ((tid & 31) == 0) { s_red[tid >> 5] = best; s_idx[tid >> 5] = bi; }
+      __syncthreads();
+      if (tid == 0) {
+        double b = s_red[0]; int ix = s_idx[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) if (s_red[w] > b || (s_red[w] == b && s_idx[w] < ix)) { b = s_red[w]; ix = s_idx[w]; }
+        s_piv = (b > 0.0) ? ix : -1;
+      }
+      __syncthreads();
+      const int p = s_piv;
+      if (p < 0) { bad = true; break; }
+      if (p != k) for (int r = tid; r < ncol; r += blockDim.x) { const double a = W[(long long)r * nt + k]; W[(long long)r * nt + k] = W[(long long)r * nt + p]; W[(long long)r * nt + p] = a; }
+      __syncthreads();
+      const double piv = W[(long long)k * nt + k];
+      __syncthreads();
+      for (int i = k + 1 + tid; i < nt; i += blockDim.x) W[(long long)k * nt + i] /= piv;   // multipliers
+      __syncthreads();
+      for (int r = k + 1 + (tid >> 5); r < ncol; r += (blockDim.x >> 5)) {                    // columns r > k, lanes along the rows
+        const double ukr = W[(long long)r * nt + k];
+        for (int i = k + 1 + (tid & 31); i < nt; i += 32) W[(long long)r * nt + i] -= W[(long long)k * nt + i] * ukr;
+      }
+      __syncthreads();
+    }
+    if (bad) { if (tid == 0) A.info[e] = inode + 1; continue; }
+    // back substitution with U (upper triangle of Wc) for the nc load columns, column oriented
+    for (int k = nt - 1; k >= 0; k--) {
+      const double ukk = W[(long long)k * nt + k];
+      __syncthreads();
+      if (tid < nc) W[(long long)(nt + tid) * nt + k] /= ukk;
+      __syncthreads();
+      for (int q = tid; q < nc * k; q += blockDim.x) {
+        const int c = q / k, i = q % k;
+        W[(long long)(nt + c) * nt + i] -= W[(long long)k * nt + i] * W[(long long)(nt + c) * nt + k];
+      }
+    }
+    __syncthreads();
+    for (int q = tid; q < nc * nE; q += blockDim.x) { const int j = q / nc, c = q % nc; dof[(long long)(nd.t0 + j) * nc + c] = W[(long long)(nt + c) * nt + j]; }
   }
 }
 

@@ -257,6 +257,31 @@ int hp3d_gpu_pbi_h1_batch(int nel, const int *etype, const int *norder, const in
                           int maxp, const double *etav, int ncomp, const double *fvert, const double *fgrad, long long fgrad_ld,
                           const unsigned *mask, double *dof, long long dof_ld, int *info);
 
+/* H(curl) Dirichlet dofs of update_Ddof: edge/dhpedgeE.F90:33 and face/dhpfaceE_opt.F90:33 for all elements at once (INTEGRATION = 1;
+ * middle nodes carry no Dirichlet data).  Same node numbering / mask bits as above (vertex and middle bits are ignored).
+ *   hp3d_gpu_pbi_hcurl_points: points of the edge and face nodes that own H(curl) dofs (an order-1 edge has one), nrdofE = number of
+ *           edge + face dofs of the element (they come first in the reference's H(curl) dof order), nodes (4, 27) as above
+ *   fval    (ncomp, 3, npts) per element: the datum pulled back to eta, E_eta(i) = sum_j E_j dxdeta(j,i)        (dhpfaceE_opt.F90:249-255)
+ *   fcurl   (ncomp, 3, npts) per element: curl_eta(i) = det(dxdeta) sum_j dxdeta^-1(i,j) (curl E)_j             (:256-258); edges ignore it
+ *           both component fastest, stride f_ld doubles; ncomp REAL components (complex data: re/im interleaved)
+ *   dof     (ncomp, nrdofE) per element, stride dof_ld; IN: dofs of unselected edges, OUT: selected nodes' dofs
+ *   info    per element: 0, -1 (Jacobian not positive), i > 0 (singular system at node i) */
+int hp3d_gpu_pbi_hcurl_points(int nel, const int *etype, const int *norder, const int *norient_edge, const int *norient_face, int maxp,
+                              double *xi, long long xi_ld, int *npts, int *nrdofE, int *nodes);
+int hp3d_gpu_pbi_hcurl_batch(int nel, const int *etype, const int *norder, const int *norient_edge, const int *norient_face, int maxp,
+                             const double *etav, int ncomp, const double *fval, const double *fcurl, long long f_ld, const unsigned *mask,
+                             double *dof, long long dof_ld, int *info);
+
+/* H(div) Dirichlet dofs of update_Ddof: face/dhpfaceV_opt.F90:33 (INTEGRATION = 1): L2 projection of the normal component on every
+ * selected face (bits of the face nodes in mask; the others are ignored).
+ *   fval    (ncomp, 3, npts) per element: V_eta(i) = det(dxdeta) sum_j dxdeta^-1(i,j) V_j at hp3d_gpu_pbi_hdiv_points  (:211-217)
+ *   dof     (ncomp, nrdofV) per element, nrdofV = number of face dofs (they come first in the reference's H(div) dof order) */
+int hp3d_gpu_pbi_hdiv_points(int nel, const int *etype, const int *norder, const int *norient_edge, const int *norient_face, int maxp,
+                             double *xi, long long xi_ld, int *npts, int *nrdofV, int *nodes);
+int hp3d_gpu_pbi_hdiv_batch(int nel, const int *etype, const int *norder, const int *norient_edge, const int *norient_face, int maxp,
+                            const double *etav, int ncomp, const double *fval, long long f_ld, const unsigned *mask, double *dof,
+                            long long dof_ld, int *info);
+
 /* ---- host-only introspection (no GPU needed): the signed tensor-product description of the shape functions.
  * space: 0 H1, 1 H(curl), 2 H(div), 3 L2.  For dof k (reference order, src/element/shape_1/Hexahedron.F90):
  *   fam[k] vector direction (0..2, -1 scalar), idx[3k..3k+2] 1-D table index per axis, sgn[k] = +-1.

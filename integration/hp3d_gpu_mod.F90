@@ -159,6 +159,40 @@ module hp3d_gpu
          real(c_double) :: etav(3,8,*), fvert(ncomp,8,*), fgrad(fgrad_ld,*), dof(dof_ld,*)
          type(c_ptr), value :: mask
       end function
+      integer(c_int) function hp3d_gpu_pbi_hcurl_points(nel, etype, norder, norient_edge, norient_face, maxp,                 &
+                          xi, xi_ld, npts, nrdofE, nodes) bind(C)
+         import
+         integer(c_int), value :: nel, maxp
+         integer(c_long_long), value :: xi_ld
+         integer(c_int) :: etype(*), norder(19,*), norient_edge(12,*), norient_face(6,*)
+         type(c_ptr), value :: xi, npts, nrdofE, nodes
+      end function
+      integer(c_int) function hp3d_gpu_pbi_hcurl_batch(nel, etype, norder, norient_edge, norient_face, maxp,                  &
+                          etav, ncomp, fval, fcurl, f_ld, mask, dof, dof_ld, info) bind(C)
+         import
+         integer(c_int), value :: nel, maxp, ncomp
+         integer(c_long_long), value :: f_ld, dof_ld
+         integer(c_int) :: etype(*), norder(19,*), norient_edge(12,*), norient_face(6,*), info(*)
+         real(c_double) :: etav(3,8,*), fval(f_ld,*), fcurl(f_ld,*), dof(dof_ld,*)
+         type(c_ptr), value :: mask
+      end function
+      integer(c_int) function hp3d_gpu_pbi_hdiv_points(nel, etype, norder, norient_edge, norient_face, maxp,                  &
+                          xi, xi_ld, npts, nrdofV, nodes) bind(C)
+         import
+         integer(c_int), value :: nel, maxp
+         integer(c_long_long), value :: xi_ld
+         integer(c_int) :: etype(*), norder(19,*), norient_edge(12,*), norient_face(6,*)
+         type(c_ptr), value :: xi, npts, nrdofV, nodes
+      end function
+      integer(c_int) function hp3d_gpu_pbi_hdiv_batch(nel, etype, norder, norient_edge, norient_face, maxp,                   &
+                          etav, ncomp, fval, f_ld, mask, dof, dof_ld, info) bind(C)
+         import
+         integer(c_int), value :: nel, maxp, ncomp
+         integer(c_long_long), value :: f_ld, dof_ld
+         integer(c_int) :: etype(*), norder(19,*), norient_edge(12,*), norient_face(6,*), info(*)
+         real(c_double) :: etav(3,8,*), fval(f_ld,*), dof(dof_ld,*)
+         type(c_ptr), value :: mask
+      end function
    end interface
 !
 contains

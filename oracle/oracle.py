@@ -428,3 +428,68 @@ def pbi_element(norder, norie, norif, etav, fun, ncomp, integration=0, maxp=9, m
                               C.c_uint(mask), PBI_FN(cb), None, _d(out))
     assert r == 0, r
     return out
+
+
+PBI_FNE = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+
+
+def pbi_offsets_E(norder, etype=MDLB):
+    """offsets of the edge and face nodes' H(curl) dofs + their total"""
+    off = np.zeros(32, np.int32)
+    lib().orc_pbi_offsets_E(int(etype), _i(_pad(norder, 19)), _i(off))
+    nn = (9 + 5) if etype == MDLP else 18
+    return off[:nn + 1].copy()
+
+
+def pbi_hcurl_element(norder, norie, norif, etav, fun, ncomp, maxp=9, mask=None, dof=None, etype=MDLB):
+    """dhpedgeE / dhpfaceE_opt on one element.  fun(eta) -> (E[ncomp, 3], curlE[ncomp, 3], dxdeta[3, 3]) in physical components.
+    Returns dofE (n_edge_and_face_dofs, ncomp)."""
+    norder, norie, norif = _pad(norder, 19), _pad(norie, 12), _pad(norif, 6)
+    etav = np.ascontiguousarray(etav, dtype=np.float64)
+    off = pbi_offsets_E(norder, etype)
+    nn = off.size - 1
+    out = np.zeros((int(off[-1]), ncomp)) if dof is None else np.ascontiguousarray(dof, dtype=np.float64).copy()
+    mask = (1 << nn) - 1 if mask is None else int(mask)
+
+    def cb(eta, E, cE, dxdeta, ctx):
+        e, c, J = fun(np.array([eta[0], eta[1], eta[2]]))
+        e = np.asarray(e).reshape(ncomp, 3); c = np.asarray(c).reshape(ncomp, 3); J = np.asarray(J).reshape(3, 3)
+        for n in range(ncomp):
+            for j in range(3):
+                E[n + ncomp * j] = e[n, j]; cE[n + ncomp * j] = c[n, j]
+        for j in range(3):
+            for i in range(3):
+                dxdeta[j + 3 * i] = J[j, i]
+    r = lib().orc_pbi_hcurl_element(int(etype), _i(norder), _i(norie), _i(norif), _d(etav), int(ncomp), int(maxp), C.c_uint(mask), PBI_FNE(cb),
+                                    None, _d(out))
+    assert r == 0, r
+    return out
+
+
+def pbi_offsets_V(norder, etype=MDLB):
+    off = np.zeros(8, np.int32)
+    lib().orc_pbi_offsets_V(int(etype), _i(_pad(norder, 19)), _i(off))
+    return off[:(5 if etype == MDLP else 6) + 1].copy()
+
+
+def pbi_hdiv_element(norder, norie, norif, etav, fun, ncomp, maxp=9, mask=None, dof=None, etype=MDLB):
+    """dhpfaceV_opt on one element.  fun(eta) -> (V[ncomp, 3], ignored, dxdeta[3, 3]).  Returns dofV (n_face_dofs, ncomp)."""
+    norder, norie, norif = _pad(norder, 19), _pad(norie, 12), _pad(norif, 6)
+    etav = np.ascontiguousarray(etav, dtype=np.float64)
+    off = pbi_offsets_V(norder, etype)
+    out = np.zeros((int(off[-1]), ncomp)) if dof is None else np.ascontiguousarray(dof, dtype=np.float64).copy()
+    mask = (1 << (off.size - 1)) - 1 if mask is None else int(mask)
+
+    def cb(eta, E, cE, dxdeta, ctx):
+        e, _, J = fun(np.array([eta[0], eta[1], eta[2]]))
+        e = np.asarray(e).reshape(ncomp, 3); J = np.asarray(J).reshape(3, 3)
+        for n in range(ncomp):
+            for j in range(3):
+                E[n + ncomp * j] = e[n, j]; cE[n + ncomp * j] = 0.0
+        for j in range(3):
+            for i in range(3):
+                dxdeta[j + 3 * i] = J[j, i]
+    r = lib().orc_pbi_hdiv_element(int(etype), _i(norder), _i(norie), _i(norif), _d(etav), int(ncomp), int(maxp), C.c_uint(mask), PBI_FNE(cb),
+                                   None, _d(out))
+    assert r == 0, r
+    return out

@@ -214,3 +214,258 @@ int orc_pbi_batch_sample(int nel, const int *etype, const int *norder, const int
                            0x7ffffffu, orc_pbi_sample_fn, NULL, dof + dof_ld * e) != 0;
   return bad;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------------
+ * H(curl) Dirichlet dofs: edge/dhpedgeE.F90:33-391, face/dhpfaceE_opt.F90:33-549 (INTEGRATION = 1).
+ * f(eta, E[ncomp*3], curlE[ncomp*3], dxdeta[9], ctx): the datum in PHYSICAL components (E[c + ncomp*j] = E_c,j, what `dirichlet`
+ * returns as zvalE and the curl formed from zdvalE, dhpfaceE_opt.F90:233-235) and the GMP Jacobian dxdeta(j,i) = dxdeta[j + 3i];
+ * the pullbacks to eta are done here as in the reference.  Nodes: 0..nre-1 edges, then faces.
+ * dofE: (ncomp, nrdofE) component fastest, full-element numbering. */
+void orc_pbi_offsets_E(int et, const int *norder, int *off /* nre+nrf entries + total of edges+faces */) {
+  const int nre = orc_nedge(et), nrf = orc_nface(et);
+  int n = 0, k = 0, h, e, v, q;
+  for (int i = 0; i < nre; i++) { off[k++] = n; n += norder[i]; }
+  for (int i = 0; i < nrf; i++) { off[k++] = n; orc_ndof_nod_face(et, i + 1, norder[nre + i], &h, &e, &v, &q); n += e; }
+  off[k] = n;
+}
+
+int orc_pbi_hcurl_node(int et, const int *norder, const int *norie, const int *norif, const double *etav, int ncomp, int maxp, int node,
+                       orc_pbi_fnE f, void *ctx, double *dofE) {
+  const int nrv = orc_nvert(et), nre = orc_nedge(et), nrf = orc_nface(et), integration = 1;
+  int offE[32], offH[32];
+  orc_pbi_offsets_E(et, norder, offE);
+  orc_pbi_offsets(et, norder, offH);
+  const int nE = offE[node + 1] - offE[node], t0 = offE[node];
+  if (nE <= 0) return 0;
+  const int isface = node >= nre;
+  const int nH = isface ? offH[nrv + node + 1] - offH[nrv + node] : 0;   /* H1 bubbles of the face: Lagrange multipliers */
+  const int nt = nE + nH;
+  double *shapH = malloc(sizeof(double) * ORC_MAXBRICK_H), *gradH = malloc(sizeof(double) * 3 * ORC_MAXBRICK_H);
+  double *shapE = malloc(sizeof(double) * 3 * ORC_MAXBRICK_E), *curlE = malloc(sizeof(double) * 3 * ORC_MAXBRICK_E);
+  double *aa = calloc((size_t)nt * nt, sizeof(double)), *bb = calloc((size_t)nt * ncomp, sizeof(double));
+  double *val = malloc(sizeof(double) * 3 * ncomp), *crl = malloc(sizeof(double) * 3 * ncomp);
+  double *veta = malloc(sizeof(double) * 3 * ncomp), *ceta = malloc(sizeof(double) * 3 * ncomp);
+  double *pts = malloc(sizeof(double) * 3 * 1000), *wts = malloc(sizeof(double) * 1000);
+  int nord1[19], nint, info = 0;
+  double *a_e = NULL, *a_ce = NULL, *a_gh = NULL;
+  orc_initiate_order(et, nord1);
+  if (!isface) { /* dhpedgeE.F90:146-153 */
+    nord1[node] = norder[node];
+    int na = norder[node] + integration; if (na > maxp) na = maxp;
+    nint = na + 1;
+    orc_gauss1(nint, pts, wts);
+  } else { /* dhpfaceE_opt.F90:170-186 */
+    const int jf = node - nre + 1;
+    int nordf[5];
+    for (int i = 0; i < nre; i++) nord1[i] = norder[i];
+    nord1[nre + jf - 1] = norder[nre + jf - 1];
+    orc_face_order(et, jf, norder, nordf);
+    nint = orc_set_2D_int(orc_face_is_tri(et, jf), nordf, 0, integration, maxp, pts, wts);
+    a_e = malloc(sizeof(double) * (size_t)nE * 3 * nint); a_ce = malloc(sizeof(double) * (size_t)nE * 3 * nint);
+    a_gh = malloc(sizeof(double) * (size_t)(nH > 0 ? nH : 1) * 3 * nint);
+  }
+  for (int l = 0; l < nint; l++) {
+    double xi[3], dxidt[6], eta[3], detadxi[9], dxideta[9], rjac, weight, dir[3], dxdeta[9], detadx[9], rjx;
+    int iflag;
+    if (!isface) orc_edge_param(et, node + 1, pts[l], xi, dxidt);
+    else orc_face_param(et, node - nre + 1, pts + 2 * l, xi, dxidt);
+    int nrdofH = orc_shape3DH(et, xi, nord1, norie, norif, shapH, gradH);
+    int nrdofE = orc_shape3DE(et, xi, nord1, norie, norif, shapE, curlE);
+    refgeom3D(etav, shapH, gradH, nrv, eta, detadxi, dxideta, &rjac, &iflag);
+    if (iflag != 0) info = -1;
+    if (!isface) {
+      double bjac = 0;
+      for (int c = 0; c < 3; c++) { dir[c] = detadxi[c] * dxidt[0] + detadxi[c + 3] * dxidt[1] + detadxi[c + 6] * dxidt[2]; bjac += dir[c] * dir[c]; }
+      bjac = sqrt(bjac);
+      for (int c = 0; c < 3; c++) dir[c] /= bjac;
+      weight = wts[l] * bjac;
+    } else {
+      double d[6], bjac;
+      for (int i = 0; i < 2; i++)
+        for (int c = 0; c < 3; c++) d[c + 3 * i] = detadxi[c] * dxidt[3 * i] + detadxi[c + 3] * dxidt[3 * i + 1] + detadxi[c + 6] * dxidt[3 * i + 2];
+      dir[0] = d[1] * d[5] - d[2] * d[4]; dir[1] = d[2] * d[3] - d[0] * d[5]; dir[2] = d[0] * d[4] - d[1] * d[3];
+      bjac = sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+      const int ns = orc_nsign_param(et, node - nre + 1);
+      for (int c = 0; c < 3; c++) dir[c] = dir[c] * ns / bjac;
+      weight = wts[l] * bjac;
+    }
+    f(eta, val, crl, dxdeta, ctx);
+    orc_geom(dxdeta, detadx, &rjx, &iflag);   /* dhpfaceE_opt.F90:221 */
+    /* pullbacks (dhpedgeE.F90:201-207, dhpfaceE_opt.F90:249-259): E_eta = dxdeta^T E, curl_eta = rjac * detadx * curl */
+    for (int c = 0; c < ncomp; c++)
+      for (int i = 0; i < 3; i++) {
+        double a = 0, b = 0;
+        for (int j = 0; j < 3; j++) { a += val[c + ncomp * j] * dxdeta[j + 3 * i]; b += crl[c + ncomp * j] * detadx[i + 3 * j] * rjx; }
+        veta[c + ncomp * i] = a; ceta[c + ncomp * i] = b;
+      }
+    if (!isface) { /* dhpedgeE.F90:211-243 ; the edge's functions sit after one function of each preceding edge */
+      for (int j = 0; j < nE; j++) {
+        const int kj = node + j;
+        double v[3], prod = 0;
+        for (int i = 0; i < 3; i++) v[i] = shapE[3 * kj] * dxideta[3 * i] + shapE[1 + 3 * kj] * dxideta[1 + 3 * i] + shapE[2 + 3 * kj] * dxideta[2 + 3 * i];
+        for (int i = 0; i < 3; i++) prod += v[i] * dir[i];
+        for (int i = 0; i < 3; i++) v[i] = prod * dir[i];
+        for (int c = 0; c < ncomp; c++) bb[j + nt * c] += (veta[c] * v[0] + veta[c + ncomp] * v[1] + veta[c + 2 * ncomp] * v[2]) * weight;
+        for (int i2 = 0; i2 < nE; i2++) {
+          const int ki = node + i2;
+          double u[3];
+          for (int i = 0; i < 3; i++) u[i] = shapE[3 * ki] * dxideta[3 * i] + shapE[1 + 3 * ki] * dxideta[1 + 3 * i] + shapE[2 + 3 * ki] * dxideta[2 + 3 * i];
+          aa[j + nt * i2] += (v[0] * u[0] + v[1] * u[1] + v[2] * u[2]) * weight;
+        }
+      }
+      continue;
+    }
+    /* face: remove the edges' contributions (dhpfaceE_opt.F90:275-293) */
+    const int ownE = nrdofE - nE, ownH = nrdofH - nH;
+    if (ownE != offE[nre]) info = -2;
+    for (int k = 0; k < ownE; k++) {
+      double u[3], cu[3];
+      for (int i = 0; i < 3; i++) {
+        u[i] = shapE[3 * k] * dxideta[3 * i] + shapE[1 + 3 * k] * dxideta[1 + 3 * i] + shapE[2 + 3 * k] * dxideta[2 + 3 * i];
+        cu[i] = (detadxi[i] * curlE[3 * k] + detadxi[i + 3] * curlE[1 + 3 * k] + detadxi[i + 6] * curlE[2 + 3 * k]) / rjac;
+      }
+      for (int i = 0; i < 3; i++)
+        for (int c = 0; c < ncomp; c++) { veta[c + ncomp * i] -= dofE[c + ncomp * k] * u[i]; ceta[c + ncomp * i] -= dofE[c + ncomp * k] * cu[i]; }
+    }
+    const double sw = sqrt(weight);
+    for (int j = 0; j < nE; j++) { /* :305-327 */
+      const int kj = ownE + j;
+      double v[3], cv[3], prod = 0;
+      for (int i = 0; i < 3; i++) {
+        v[i] = shapE[3 * kj] * dxideta[3 * i] + shapE[1 + 3 * kj] * dxideta[1 + 3 * i] + shapE[2 + 3 * kj] * dxideta[2 + 3 * i];
+        cv[i] = (detadxi[i] * curlE[3 * kj] + detadxi[i + 3] * curlE[1 + 3 * kj] + detadxi[i + 6] * curlE[2 + 3 * kj]) / rjac;
+      }
+      for (int i = 0; i < 3; i++) prod += v[i] * dir[i];
+      for (int i = 0; i < 3; i++) v[i] -= prod * dir[i];
+      prod = 0;
+      for (int i = 0; i < 3; i++) prod += cv[i] * dir[i];
+      for (int i = 0; i < 3; i++) cv[i] = prod * dir[i];
+      for (int c = 0; c < ncomp; c++) bb[j + nt * c] += (cv[0] * ceta[c] + cv[1] * ceta[c + ncomp] + cv[2] * ceta[c + 2 * ncomp]) * weight;
+      for (int i = 0; i < 3; i++) { a_e[j + (size_t)nE * (3 * l + i)] = v[i] * sw; a_ce[j + (size_t)nE * (3 * l + i)] = cv[i] * sw; }
+    }
+    for (int j = 0; j < nH; j++) { /* :329-347 */
+      const int kj = ownH + j;
+      double dv[3], prod = 0;
+      for (int i = 0; i < 3; i++) dv[i] = gradH[3 * kj] * dxideta[3 * i] + gradH[1 + 3 * kj] * dxideta[1 + 3 * i] + gradH[2 + 3 * kj] * dxideta[2 + 3 * i];
+      for (int i = 0; i < 3; i++) prod += dv[i] * dir[i];
+      for (int i = 0; i < 3; i++) dv[i] -= prod * dir[i];
+      for (int c = 0; c < ncomp; c++) bb[nE + j + nt * c] += (veta[c] * dv[0] + veta[c + ncomp] * dv[1] + veta[c + 2 * ncomp] * dv[2]) * weight;
+      for (int i = 0; i < 3; i++) a_gh[j + (size_t)nH * (3 * l + i)] = dv[i] * sw;
+    }
+  }
+  if (isface) { /* DSYRK + DGEMM + symmetric fill (:353-375): [curl-curl, E.grad ; (E.grad)^T, 0] */
+    orc_dsyrk_u('N', nE, 3 * nint, 1.0, a_ce, nE, 0.0, aa, nt);
+    for (int j = 0; j < nE; j++) for (int i = j + 1; i < nE; i++) aa[i + nt * j] = aa[j + nt * i];
+    if (nH > 0) {
+      orc_dgemm('N', 'T', nE, nH, 3 * nint, 1.0, a_e, nE, a_gh, nH, 0.0, aa + (size_t)nt * nE, nt);
+      for (int j = 0; j < nH; j++) for (int i = 0; i < nE; i++) aa[nE + j + nt * i] = aa[i + nt * (nE + j)];
+    }
+  }
+  { /* DGETRF + DLASWP + 2 x DTRSM (dhpedgeE.F90:268-290, dhpfaceE_opt.F90:398-425) */
+    int *ipiv = malloc(sizeof(int) * nt);
+    if (orc_dgetrf(nt, aa, nt, ipiv) != 0) info = info ? info : 1;
+    else orc_dgetrs(nt, ncomp, aa, nt, ipiv, bb, nt);
+    free(ipiv);
+  }
+  if (info == 0)
+    for (int j = 0; j < nE; j++)
+      for (int c = 0; c < ncomp; c++) dofE[c + ncomp * (t0 + j)] = bb[j + nt * c];
+  free(shapH); free(gradH); free(shapE); free(curlE); free(aa); free(bb); free(val); free(crl); free(veta); free(ceta); free(pts); free(wts);
+  free(a_e); free(a_ce); free(a_gh);
+  return info;
+}
+
+/* edges first, then faces (update_Ddof.F90 visits the nodes by type in that order); bit i of mask = node i (edges, faces) */
+int orc_pbi_hcurl_element(int et, const int *norder, const int *norie, const int *norif, const double *etav, int ncomp, int maxp, unsigned mask,
+                          orc_pbi_fnE f, void *ctx, double *dofE) {
+  const int nn = orc_nedge(et) + orc_nface(et);
+  for (int node = 0; node < nn; node++)
+    if (mask & (1u << node)) {
+      int rc = orc_pbi_hcurl_node(et, norder, norie, norif, etav, ncomp, maxp, node, f, ctx, dofE);
+      if (rc) return rc;
+    }
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------------
+ * H(div) Dirichlet dofs: face/dhpfaceV_opt.F90:33-413 (INTEGRATION = 1): L2 projection of the normal component of the datum pulled
+ * back to eta, V_eta = det(dxdeta) dxdeta^-1 V (:211-217), onto the face's H(div) functions mapped by the Piola transform of
+ * eta(xi) (:223-228).  f as for H(curl) (the curl output is ignored).  Nodes: faces 0..nrf-1.  dofV: (ncomp, sum of face dofs). */
+void orc_pbi_offsets_V(int et, const int *norder, int *off) {
+  const int nre = orc_nedge(et), nrf = orc_nface(et);
+  int n = 0, h, e, v, q;
+  for (int i = 0; i < nrf; i++) { off[i] = n; orc_ndof_nod_face(et, i + 1, norder[nre + i], &h, &e, &v, &q); n += v; }
+  off[nrf] = n;
+}
+
+int orc_pbi_hdiv_node(int et, const int *norder, const int *norie, const int *norif, const double *etav, int ncomp, int maxp, int iface0,
+                      orc_pbi_fnE f, void *ctx, double *dofV) {
+  const int nrv = orc_nvert(et), nre = orc_nedge(et), nrf = orc_nface(et), integration = 1, jf = iface0 + 1;
+  int offV[8];
+  orc_pbi_offsets_V(et, norder, offV);
+  const int n = offV[iface0 + 1] - offV[iface0], t0 = offV[iface0];
+  if (n <= 0) return 0;
+  double *shapH = malloc(sizeof(double) * ORC_MAXBRICK_H), *gradH = malloc(sizeof(double) * 3 * ORC_MAXBRICK_H);
+  double *shapV = malloc(sizeof(double) * 3 * ORC_MAXBRICK_E), *divV = malloc(sizeof(double) * ORC_MAXBRICK_E);
+  double *aa = calloc((size_t)n * n, sizeof(double)), *bb = calloc((size_t)n * ncomp, sizeof(double));
+  double *val = malloc(sizeof(double) * 3 * ncomp), *crl = malloc(sizeof(double) * 3 * ncomp), *veta = malloc(sizeof(double) * 3 * ncomp);
+  double *pts = malloc(sizeof(double) * 3 * 1000), *wts = malloc(sizeof(double) * 1000);
+  int nord1[19], nordi[19], nordf[5], info = 0;
+  orc_initiate_order(et, nord1);                       /* :151-153 */
+  memcpy(nordi, nord1, sizeof nord1);
+  nordi[nre + jf - 1] = norder[nre + jf - 1];
+  orc_face_order(et, jf, norder, nordf);
+  const int nint = orc_set_2D_int(orc_face_is_tri(et, jf), nordf, 0, integration, maxp, pts, wts);
+  double *atest = malloc(sizeof(double) * (size_t)n * 3 * nint);
+  for (int l = 0; l < nint; l++) {
+    double xi[3], dxidt[6], eta[3], detadxi[9], dxideta[9], rjac, d[6], rn[3], bjac, dxdeta[9], detadx[9], rjx;
+    int iflag;
+    orc_face_param(et, jf, pts + 2 * l, xi, dxidt);
+    orc_shape3DH(et, xi, nord1, norie, norif, shapH, gradH);
+    orc_shape3DV(et, xi, nordi, norif, shapV, divV);
+    refgeom3D(etav, shapH, gradH, nrv, eta, detadxi, dxideta, &rjac, &iflag);
+    if (iflag != 0) info = -1;
+    for (int i = 0; i < 2; i++)
+      for (int c = 0; c < 3; c++) d[c + 3 * i] = detadxi[c] * dxidt[3 * i] + detadxi[c + 3] * dxidt[3 * i + 1] + detadxi[c + 6] * dxidt[3 * i + 2];
+    rn[0] = d[1] * d[5] - d[2] * d[4]; rn[1] = d[2] * d[3] - d[0] * d[5]; rn[2] = d[0] * d[4] - d[1] * d[3];
+    bjac = sqrt(rn[0] * rn[0] + rn[1] * rn[1] + rn[2] * rn[2]);
+    const int ns = orc_nsign_param(et, jf);
+    for (int c = 0; c < 3; c++) rn[c] = rn[c] * ns / bjac;
+    const double weight = wts[l] * bjac, sw = sqrt(weight);
+    f(eta, val, crl, dxdeta, ctx);
+    orc_geom(dxdeta, detadx, &rjx, &iflag);
+    for (int c = 0; c < ncomp; c++)
+      for (int i = 0; i < 3; i++) {
+        double a = 0;
+        for (int j = 0; j < 3; j++) a += detadx[i + 3 * j] * val[c + ncomp * j] * rjx;
+        veta[c + ncomp * i] = a;
+      }
+    for (int j = 0; j < n; j++) { /* :219-236 ; one function of each preceding face comes first */
+      const int kj = iface0 + j;
+      double v[3], prod = 0;
+      for (int i = 0; i < 3; i++) v[i] = (detadxi[i] * shapV[3 * kj] + detadxi[i + 3] * shapV[1 + 3 * kj] + detadxi[i + 6] * shapV[2 + 3 * kj]) / rjac;
+      for (int i = 0; i < 3; i++) prod += v[i] * rn[i];
+      for (int i = 0; i < 3; i++) v[i] = prod * rn[i];
+      for (int c = 0; c < ncomp; c++) bb[j + n * c] += (veta[c] * v[0] + veta[c + ncomp] * v[1] + veta[c + 2 * ncomp] * v[2]) * weight;
+      for (int i = 0; i < 3; i++) atest[j + (size_t)n * (3 * l + i)] = v[i] * sw;
+    }
+  }
+  orc_dsyrk_u('N', n, 3 * nint, 1.0, atest, n, 0.0, aa, n);   /* DSFRK + DPFTRF + DPFTRS, :241-275 */
+  if (orc_dpotrf_u(n, aa, n) != 0) info = info ? info : 1;
+  else { orc_dtrsm_u('T', n, ncomp, aa, n, bb, n); orc_dtrsm_u('N', n, ncomp, aa, n, bb, n); }
+  if (info == 0)
+    for (int j = 0; j < n; j++)
+      for (int c = 0; c < ncomp; c++) dofV[c + ncomp * (t0 + j)] = bb[j + n * c];
+  free(shapH); free(gradH); free(shapV); free(divV); free(aa); free(bb); free(val); free(crl); free(veta); free(pts); free(wts); free(atest);
+  return info;
+}
+
+int orc_pbi_hdiv_element(int et, const int *norder, const int *norie, const int *norif, const double *etav, int ncomp, int maxp, unsigned mask,
+                         orc_pbi_fnE f, void *ctx, double *dofV) {
+  for (int jf = 0; jf < orc_nface(et); jf++)
+    if (mask & (1u << jf)) {
+      int rc = orc_pbi_hdiv_node(et, norder, norie, norif, etav, ncomp, maxp, jf, f, ctx, dofV);
+      if (rc) return rc;
+    }
+  return 0;
+}

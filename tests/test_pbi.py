@@ -253,3 +253,208 @@ def test_gpu_pbi_errors_are_loud(gpu):
     pts = api.pbi_points(no, z(12), z(6))
     res = api.pbi_h1_batch(no, z(12), z(6), z((1, 8, 3)), z((1, 8, 1)), z((1, int(pts["npts"][0]), 3, 1)))
     assert res["info"][0] != 0
+
+
+# ------------------------------------------------------------------------------------------- H(curl) Dirichlet dofs (dhpedgeE, dhpfaceE_opt)
+from tests.test_pbi_oracle import nedelec_poly, smooth_E  # noqa: E402
+
+
+def curved_E(eta):
+    """smooth datum on a curved GMP block: physical components, curl, dx/deta (not the identity: both pullbacks matter)"""
+    E, cE, _ = smooth_E(eta)
+    x, y, z = eta
+    J = np.array([[1.0, 0.2 * np.cos(2.0 * y) * z, 0.1 * np.sin(2.0 * y)], [0.1 * x, 1.0, 0.0], [-0.1 * np.sin(x + y), -0.1 * np.sin(x + y), 1.0]])
+    return E, cE, J
+
+
+def tabulate_E(fun, ncomp, pts, etav, etype):
+    """what the Fortran shim does: E_eta = dxdeta^T E, curl_eta = det(dxdeta) dxdeta^-1 curl E at the product's points"""
+    nel = etav.shape[0]
+    fv = np.zeros((nel, pts["xi"].shape[1], 3, ncomp)); fc = np.zeros_like(fv)
+    for e in range(nel):
+        et = int(etype[e]); nv = 8 if et == MDLB else 6
+        for l in range(int(pts["npts"][e])):
+            eta = vertex_shape(et, pts["xi"][e, l]) @ etav[e, :nv]
+            E, cE, J = fun(eta)
+            E = np.asarray(E).reshape(ncomp, 3); cE = np.asarray(cE).reshape(ncomp, 3)
+            fv[e, l] = (E @ J).T
+            fc[e, l] = (np.linalg.det(J) * np.linalg.solve(J, cE.T))
+    return fv, fc
+
+
+@pytest.mark.parametrize("et", [MDLB, MDLP])
+def test_hcurl_points_are_the_ones_the_reference_loops_visit(oracle, gpulib, et):
+    oracle.set_maxp(9)
+    rng = np.random.default_rng(2)
+    for _ in range(3):
+        no, noe, nof = (random_brick if et == MDLB else random_prism)(rng, 1, 4)
+        etav = warped_vertices(rng, et)
+        nv = 8 if et == MDLB else 6
+        seen = []
+
+        def fun(eta):
+            seen.append(eta.copy())
+            return np.zeros((1, 3)), np.zeros((1, 3)), np.eye(3)
+        oracle.pbi_hcurl_element(no, noe, nof, etav[:nv], fun, 1, etype=et)
+        pts = api.pbi_hcurl_points(no, noe, nof, etype=et)
+        n = int(pts["npts"][0])
+        assert len(seen) == n
+        mine = np.array([vertex_shape(et, x) @ etav[:nv] for x in pts["xi"][0, :n]])
+        assert np.abs(np.array(seen) - mine).max() < 1e-14
+        off = oracle.pbi_offsets_E(no, et)
+        nn = len(off) - 1
+        assert np.array_equal(pts["nodes"][0, nv:nv + nn, 0], off[:-1]) and int(pts["nrdofE"][0]) == int(off[-1])
+
+
+def _compare_E(oracle, fun, ncomp, norder, noe, nof, etav, etype, mask=None, dof_in=None):
+    nel = norder.shape[0]
+    pts = api.pbi_hcurl_points(norder, noe, nof, etype=etype)
+    fv, fc = tabulate_E(fun, ncomp, pts, etav, etype)
+    res = api.pbi_hcurl_batch(norder, noe, nof, etav, fv, fc, mask=mask, dof=dof_in, etype=etype)
+    assert not res["info"].any()
+    worst = 0.0
+    for e in range(nel):
+        et = int(etype[e]); nv = 8 if et == MDLB else 6; nE = int(pts["nrdofE"][e])
+        om = None if mask is None else (int(mask[e]) >> nv)   # the oracle numbers edges, then faces
+        ref = oracle.pbi_hcurl_element(norder[e], noe[e], nof[e], etav[e, :nv], fun, ncomp, etype=et, mask=om,
+                                       dof=None if dof_in is None else dof_in[e, :nE])
+        worst = max(worst, float(np.abs(res["dof"][e, :nE] - ref).max() / max(1.0, np.abs(ref).max())))
+    return worst, res, pts
+
+
+@pytest.mark.gpu
+def test_gpu_hcurl_matches_oracle_random_elements(oracle, gpu):
+    """bricks and prisms, anisotropic orders 1..5 (order-1 edges and (2,1) faces own H(curl) dofs but no H1 bubbles), all
+    orientation codes, warped vertex coordinates, curved GMP map, two components"""
+    oracle.set_maxp(9)
+    rng = np.random.default_rng(17)
+    rows = [(MDLB,) + random_brick(rng, 1, 5) for _ in range(4)] + [(MDLP,) + random_prism(rng, 1, 5) for _ in range(4)]
+    rows += [rows[1], rows[6]]
+    etype = np.array([r[0] for r in rows], np.int32)
+    norder = np.array([r[1] for r in rows]); noe = np.array([r[2] for r in rows]); nof = np.array([r[3] for r in rows])
+    etav = np.array([warped_vertices(rng, int(t)) for t in etype])
+    worst, _, _ = _compare_E(oracle, curved_E, 2, norder, noe, nof, etav, etype)
+    assert worst < 1e-10
+
+
+@pytest.mark.gpu
+def test_gpu_hcurl_mask_and_incoming_dofs(oracle, gpu):
+    """only one face and two of its edges are interpolated; the face projection uses the incoming dofs of the other two edges"""
+    oracle.set_maxp(9)
+    rng = np.random.default_rng(19)
+    no, noe, nof = random_brick(rng, 2, 4)
+    etav = warped_vertices(rng, MDLB)[None]
+    mask = (1 << (8 + 2 - 1)) | (1 << (8 + 11 - 1)) | (1 << (8 + 12 + 3))   # edges 2, 11 and face 4
+    pts = api.pbi_hcurl_points(no, noe, nof)
+    nE = int(pts["nrdofE"][0])
+    dof_in = rng.standard_normal((1, nE, 2))
+    worst, res, _ = _compare_E(oracle, curved_E, 2, no[None], noe[None], nof[None], etav, np.array([MDLB], np.int32),
+                               mask=np.array([mask], np.uint32), dof_in=dof_in)
+    assert worst < 1e-10
+    touched = np.zeros(nE, bool)
+    for i in range(27):
+        if mask >> i & 1:
+            t0, n = pts["nodes"][0, i, 0], pts["nodes"][0, i, 1]
+            touched[t0:t0 + n] = True
+    assert np.array_equal(res["dof"][0, ~touched], dof_in[0, ~touched])
+
+
+@pytest.mark.gpu
+def test_gpu_hcurl_polynomial_trace_full_size(oracle, gpu):
+    """p = 5 bricks (the headline order), 128 elements: the tangential trace of a field of the Nedelec space is reproduced on
+    every face (size-independent property; evaluated back through the oracle's shape3DE)"""
+    oracle.set_maxp(9)
+    rng = np.random.default_rng(23)
+    nel = 128
+    no = np.tile(synth.uniform_order(5), (nel, 1))
+    noe = rng.integers(0, 2, (nel, 12)).astype(np.int32); nof = rng.integers(0, 8, (nel, 6)).astype(np.int32)
+    noe[nel // 2:] = noe[0]; nof[nel // 2:] = nof[0]   # half of the elements share one signature
+    etav = np.zeros((nel, 8, 3))
+    for e in range(nel):
+        etav[e] = rng.uniform(0, 0.4, 3) + BRICK_M * rng.uniform(0.2, 0.6, 3)
+    etype = np.full(nel, MDLB, np.int32)
+    pts = api.pbi_hcurl_points(no, noe, nof)
+    fv, fc = tabulate_E(nedelec_poly, 1, pts, etav, etype)
+    res = api.pbi_hcurl_batch(no, noe, nof, etav, fv, fc)
+    assert not res["info"].any()
+    worst = 0.0
+    for e in rng.choice(nel, 16, replace=False):
+        nEF = int(pts["nrdofE"][e])
+        for _ in range(4):
+            xi = rng.random(3); ax = int(rng.integers(0, 3)); xi[ax] = float(rng.integers(0, 2))
+            sE, _ = oracle.shape3DE(xi, no[e], noe[e], nof[e])
+            s, g = oracle.shape3DH(xi, no[e], noe[e], nof[e])
+            J = etav[e].T @ g[:8]
+            u_eta = np.linalg.solve(J.T, res["dof"][e, :nEF, 0] @ sE[:nEF])
+            E, _, A = nedelec_poly(s[:8] @ etav[e])
+            want = A.T @ E[0]
+            t = [a for a in range(3) if a != ax]
+            worst = max(worst, float(np.abs(u_eta[t] - want[t]).max()))
+    assert worst < 1e-10
+
+
+# ----------------------------------------------------------------------------------------------------- H(div) Dirichlet dofs (dhpfaceV_opt)
+def curved_V(eta):
+    E, _, _ = smooth_E(eta)
+    return E, np.zeros_like(E), curved_E(eta)[2]
+
+
+def tabulate_V(fun, ncomp, pts, etav, etype):
+    """V_eta = det(dxdeta) dxdeta^-1 V at the product's points"""
+    nel = etav.shape[0]
+    fv = np.zeros((nel, pts["xi"].shape[1], 3, ncomp))
+    for e in range(nel):
+        et = int(etype[e]); nv = 8 if et == MDLB else 6
+        for l in range(int(pts["npts"][e])):
+            V, _, J = fun(vertex_shape(et, pts["xi"][e, l]) @ etav[e, :nv])
+            fv[e, l] = np.linalg.det(J) * np.linalg.solve(J, np.asarray(V).reshape(ncomp, 3).T)
+    return fv
+
+
+def test_hdiv_points_are_the_ones_the_reference_loops_visit(oracle, gpulib):
+    oracle.set_maxp(9)
+    rng = np.random.default_rng(3)
+    for et, gen in ((MDLB, random_brick), (MDLP, random_prism)):
+        no, noe, nof = gen(rng, 1, 4)
+        etav = warped_vertices(rng, et)
+        nv, ne = (8, 12) if et == MDLB else (6, 9)
+        seen = []
+
+        def fun(eta):
+            seen.append(eta.copy())
+            return np.zeros((1, 3)), np.zeros((1, 3)), np.eye(3)
+        oracle.pbi_hdiv_element(no, noe, nof, etav[:nv], fun, 1, etype=et)
+        pts = api.pbi_hdiv_points(no, noe, nof, etype=et)
+        n = int(pts["npts"][0])
+        assert len(seen) == n
+        mine = np.array([vertex_shape(et, x) @ etav[:nv] for x in pts["xi"][0, :n]])
+        assert np.abs(np.array(seen) - mine).max() < 1e-14
+        off = oracle.pbi_offsets_V(no, et)
+        assert np.array_equal(pts["nodes"][0, nv + ne:nv + ne + len(off) - 1, 0], off[:-1]) and int(pts["nrdofV"][0]) == int(off[-1])
+
+
+@pytest.mark.gpu
+def test_gpu_hdiv_matches_oracle_random_elements(oracle, gpu):
+    """bricks and prisms (triangle and quad faces), anisotropic orders 1..5, all orientations, warped vertices, curved GMP map;
+    one element with a face mask: unselected faces keep their incoming dofs"""
+    oracle.set_maxp(9)
+    rng = np.random.default_rng(29)
+    rows = [(MDLB,) + random_brick(rng, 1, 5) for _ in range(3)] + [(MDLP,) + random_prism(rng, 1, 5) for _ in range(3)] 
+    rows += [rows[0]]
+    etype = np.array([r[0] for r in rows], np.int32)
+    norder = np.array([r[1] for r in rows]); noe = np.array([r[2] for r in rows]); nof = np.array([r[3] for r in rows])
+    etav = np.array([warped_vertices(rng, int(t)) for t in etype])
+    nel = len(rows)
+    pts = api.pbi_hdiv_points(norder, noe, nof, etype=etype)
+    fv = tabulate_V(curved_V, 2, pts, etav, etype)
+    mask = np.full(nel, 0xFFFFFFFF, np.uint32)
+    mask[nel - 1] = (1 << (8 + 12 + 1)) | (1 << (8 + 12 + 4))   # faces 2 and 5 of the last brick
+    dof_in = rng.standard_normal((nel, int(pts["nrdofV"].max()), 2))
+    res = api.pbi_hdiv_batch(norder, noe, nof, etav, fv, mask=mask, dof=dof_in, etype=etype)
+    assert not res["info"].any()
+    for e in range(nel):
+        et = int(etype[e]); nv, ne = (8, 12) if et == MDLB else (6, 9); nV = int(pts["nrdofV"][e])
+        ref = oracle.pbi_hdiv_element(norder[e], noe[e], nof[e], etav[e, :nv], curved_V, 2, etype=et, mask=(int(mask[e]) >> (nv + ne)) & 0x3F,
+                                      dof=dof_in[e, :nV])
+        assert np.abs(res["dof"][e, :nV] - ref).max() / max(1.0, np.abs(ref).max()) < 1e-11
+    assert np.array_equal(res["dof"][nel - 1, :int(pts["nodes"][nel - 1, 20 + 1, 0])], dof_in[nel - 1, :int(pts["nodes"][nel - 1, 20 + 1, 0])])

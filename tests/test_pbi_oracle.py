@@ -112,3 +112,99 @@ def test_shared_entities_get_identical_dofs(oracle):
                 worst = max(worst, float(np.abs(U[g] - dof[k]).max())); shared += 1
     assert shared > 50
     assert worst < 1e-12
+
+
+# ---- H(curl) Dirichlet dofs (dhpedgeE, dhpfaceE_opt) -----------------------------------------------------------------------------
+SCALE = np.array([1.5, 0.8, 1.2])   # a linear GMP block x = SCALE * eta: exercises both pullbacks
+
+
+def nedelec_poly(eta):
+    """a field whose pullback lies in the order-3 Nedelec space; physical components, curl, dx/deta"""
+    x, y, z = SCALE * eta
+    E = np.array([[x * x * y * z - y, x * z * z + x * y, z * z * x * y + 1.0]])
+    cE = np.array([[z * z * x - 2.0 * x * z, x * x * y - z * z * y, z * z + y - x * x * z + 1.0]])
+    return E, cE, np.diag(SCALE)
+
+
+def smooth_E(eta):
+    x, y, z = eta
+    E = np.array([[np.sin(y + 0.3) * z, np.cos(x) * np.exp(0.3 * z), x * y + np.sin(z)],
+                  [y * y, 0.5 * x * z, np.cos(x + y)]])
+    cE = np.array([[x - 0.3 * np.cos(x) * np.exp(0.3 * z), np.sin(y + 0.3) - y, -np.sin(x) * np.exp(0.3 * z) - np.cos(y + 0.3) * z],
+                   [-np.sin(x + y) - 0.5 * x, np.sin(x + y), 0.5 * z - 2.0 * y]])
+    return E, cE, np.eye(3)
+
+
+def test_nedelec_polynomial_tangential_trace_reproduced(oracle):
+    oracle.set_maxp(9)
+    rng = np.random.default_rng(8)
+    M = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    etav = np.array([0.1, 0.2, 0.0]) + M * np.array([0.5, 0.4, 0.6])
+    no = synth.uniform_order(3)
+    for trial in range(3):
+        noe = rng.integers(0, 2, 12).astype(np.int32); nof = rng.integers(0, 8, 6).astype(np.int32)
+        dof = oracle.pbi_hcurl_element(no, noe, nof, etav, nedelec_poly, 1)
+        nEF = dof.shape[0]
+        for _ in range(12):
+            xi = rng.random(3); ax = int(rng.integers(0, 3)); xi[ax] = float(rng.integers(0, 2))   # a point on a face
+            sE, _ = oracle.shape3DE(xi, no, noe, nof)
+            s, g = oracle.shape3DH(xi, no, noe, nof)
+            J = etav.T @ g[:8]                      # d eta / d xi
+            u_eta = np.linalg.solve(J.T, (dof[:, 0] @ sE[:nEF]))   # J^-T E^
+            E, _, A = nedelec_poly(s[:8] @ etav)
+            want = A.T @ E[0]
+            t = [a for a in range(3) if a != ax]
+            assert np.abs(u_eta[t] - want[t]).max() < 1e-12
+
+
+def test_hcurl_shared_entities_get_identical_dofs(oracle):
+    from tests.test_hp_mesh_conformity import entity_blocks, topo
+    oracle.set_maxp(9)
+    m = synth.hp_mesh(2, prism_frac=0.45, pmin=1, pmax=4, seed_p=13, seed_g=6)
+    seen, worst, shared = {}, 0.0, 0
+    for e in range(len(m["etype"])):
+        et = int(m["etype"][e]); nv = 8 if et == MDLB else 6
+        E, F, _ = topo(et)
+        v = [int(x) for x in m["verts"][e] if x >= 0]
+        dof = oracle.pbi_hcurl_element(m["norder"][e], m["norient_edge"][e], m["norient_face"][e], m["xnod"][e, :nv], smooth_E, 2, etype=et)
+        blocks, ntot = entity_blocks(et, m["norder"][e], "E")
+        assert ntot == dof.shape[0]
+        for kind, idx, m0, n in blocks:
+            ent = (kind, frozenset((v[E[idx][0]], v[E[idx][1]]) if kind == "e" else tuple(v[i] for i in F[idx])))
+            for k in range(n):
+                key = ent + (k,)
+                if key in seen:
+                    worst = max(worst, float(np.abs(seen[key] - dof[m0 + k]).max())); shared += 1
+                else:
+                    seen[key] = dof[m0 + k]
+    assert shared > 50
+    assert worst < 1e-11
+
+
+# ---- H(div) Dirichlet dofs (dhpfaceV_opt) ---------------------------------------------------------------------------------------
+def rt_poly(eta):
+    """a field whose Piola pullback lies in the order-3 Raviart-Thomas space of the brick (linear GMP block x = SCALE * eta)"""
+    x, y, z = SCALE * eta
+    V = np.array([[x * x * x * y * z + y * y, x * y * y * z * z - 1.0, z * z * z * x + x * y]])
+    return V, np.zeros((1, 3)), np.diag(SCALE)
+
+
+def test_raviart_thomas_normal_trace_reproduced(oracle):
+    oracle.set_maxp(9)
+    rng = np.random.default_rng(9)
+    M = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    etav = np.array([0.1, 0.2, 0.0]) + M * np.array([0.5, 0.4, 0.6])
+    no = synth.uniform_order(3)
+    for trial in range(3):
+        noe = rng.integers(0, 2, 12).astype(np.int32); nof = rng.integers(0, 8, 6).astype(np.int32)
+        dof = oracle.pbi_hdiv_element(no, noe, nof, etav, rt_poly, 1)
+        nVF = dof.shape[0]
+        for _ in range(12):
+            xi = rng.random(3); ax = int(rng.integers(0, 3)); xi[ax] = float(rng.integers(0, 2))
+            sV, _ = oracle.shape3DV(xi, no, nof)
+            s, g = oracle.shape3DH(xi, no, noe, nof)
+            J = etav.T @ g[:8]
+            u_eta = J @ (dof[:, 0] @ sV[:nVF]) / np.linalg.det(J)      # Piola: J V^ / det
+            V, _, A = rt_poly(s[:8] @ etav)
+            want = np.linalg.det(A) * np.linalg.solve(A, V[0])         # det(dxdeta) dxdeta^-1 V
+            assert abs(u_eta[ax] - want[ax]) < 1e-12
