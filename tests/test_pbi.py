@@ -458,3 +458,60 @@ def test_gpu_hdiv_matches_oracle_random_elements(oracle, gpu):
                                       dof=dof_in[e, :nV])
         assert np.abs(res["dof"][e, :nV] - ref).max() / max(1.0, np.abs(ref).max()) < 1e-11
     assert np.array_equal(res["dof"][nel - 1, :int(pts["nodes"][nel - 1, 20 + 1, 0])], dof_in[nel - 1, :int(pts["nodes"][nel - 1, 20 + 1, 0])])
+
+
+# ------------------------------------------------------------------------------------------ golden fixtures (tools/make_golden_pbi.py)
+import glob  # noqa: E402
+import os  # noqa: E402
+
+PBI_FIXTURES = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pbi_*.npz")))
+
+
+def gmp(eta):
+    """the curved GMP block of the fixtures: x(eta) and dx/deta"""
+    x, y, z = eta
+    v = np.array([x + 0.1 * np.sin(2.0 * y) * z, y + 0.05 * x * x, z + 0.1 * np.cos(x + y)])
+    d = np.array([[1.0, 0.2 * np.cos(2.0 * y) * z, 0.1 * np.sin(2.0 * y)], [0.1 * x, 1.0, 0.0], [-0.1 * np.sin(x + y), -0.1 * np.sin(x + y), 1.0]])
+    return v, d
+
+
+@pytest.mark.parametrize("path", PBI_FIXTURES, ids=[os.path.basename(f)[:-4] for f in PBI_FIXTURES])
+def test_oracle_reproduces_pbi_golden(oracle, path):
+    g = np.load(path)
+    oracle.set_maxp(9); oracle.use_blas(False)
+    et = int(g["etype"]); nv = 8 if et == MDLB else 6
+    for e in range(2):
+        no, noe, nof, etav = g[f"norder{e}"], g[f"norie{e}"], g[f"norif{e}"], g[f"etav{e}"]
+        assert np.abs(oracle.pbi_element(no, noe, nof, etav[:nv], gmp, 3, etype=et) - g[f"h1_dof{e}"]).max() < 1e-14
+        assert np.abs(oracle.pbi_hcurl_element(no, noe, nof, etav[:nv], curved_E, 2, etype=et) - g[f"e_dof{e}"]).max() < 1e-14
+        assert np.abs(oracle.pbi_hdiv_element(no, noe, nof, etav[:nv], curved_V, 2, etype=et) - g[f"v_dof{e}"]).max() < 1e-14
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", PBI_FIXTURES, ids=[os.path.basename(f)[:-4] for f in PBI_FIXTURES])
+def test_gpu_reproduces_pbi_golden(gpu, path):
+    """the device path fed with the fixture's tabulated data (no oracle involved) reproduces the fixture's dofs"""
+    g = np.load(path)
+    et = int(g["etype"]); nv = 8 if et == MDLB else 6
+    for e in range(2):
+        no, noe, nof, etav = g[f"norder{e}"], g[f"norie{e}"], g[f"norif{e}"], g[f"etav{e}"]
+        etype = np.array([et], np.int32)
+        # H1
+        pts = api.pbi_points(no, noe, nof, etype=etype); n = int(pts["npts"][0])
+        mine = np.array([vertex_shape(et, x) @ etav[:nv] for x in pts["xi"][0, :n]]).reshape(-1, 3)
+        assert n == len(g[f"h1_eta{e}"]) and np.abs(mine - g[f"h1_eta{e}"]).max() < 1e-14
+        fv = np.zeros((1, 8, 3)); fv[0, :nv] = g[f"h1_fvert{e}"]
+        res = api.pbi_h1_batch(no, noe, nof, etav[None], fv, g[f"h1_fgrad{e}"][None], etype=etype)
+        assert not res["info"].any() and np.abs(res["dof"][0] - g[f"h1_dof{e}"]).max() < 1e-11
+        # H(curl)
+        pts = api.pbi_hcurl_points(no, noe, nof, etype=etype); n = int(pts["npts"][0])
+        mine = np.array([vertex_shape(et, x) @ etav[:nv] for x in pts["xi"][0, :n]]).reshape(-1, 3)
+        assert n == len(g[f"e_eta{e}"]) and np.abs(mine - g[f"e_eta{e}"]).max() < 1e-14
+        res = api.pbi_hcurl_batch(no, noe, nof, etav[None], g[f"e_fval{e}"][None], g[f"e_fcurl{e}"][None], etype=etype)
+        assert not res["info"].any() and np.abs(res["dof"][0] - g[f"e_dof{e}"]).max() < 1e-10
+        # H(div)
+        pts = api.pbi_hdiv_points(no, noe, nof, etype=etype); n = int(pts["npts"][0])
+        mine = np.array([vertex_shape(et, x) @ etav[:nv] for x in pts["xi"][0, :n]]).reshape(-1, 3)
+        assert n == len(g[f"v_eta{e}"]) and np.abs(mine - g[f"v_eta{e}"]).max() < 1e-14
+        res = api.pbi_hdiv_batch(no, noe, nof, etav[None], g[f"v_fval{e}"][None], etype=etype)
+        assert not res["info"].any() and np.abs(res["dof"][0] - g[f"v_dof{e}"]).max() < 1e-11

@@ -1,6 +1,6 @@
 """Throughput of the batched H1 projection-based interpolation (hp3d_gpu_pbi_h1_batch) through the C ABI with host buffers,
 beside the oracle's OpenMP element loop on the host cores (update_gdof.F90:409-435 shape).  Prints one JSON line.
-usage: python tools/bench_pbi.py [p] [nel]"""
+usage: python tools/bench_pbi.py [p] [nel] [path of an alternative libhp3d_gpu.so]"""
 import ctypes as C
 import json
 import os
@@ -10,7 +10,10 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from hp3d_b200 import api, synth  # noqa: E402
+from hp3d_b200 import _lib, api, synth  # noqa: E402
+
+if len(sys.argv) > 3:   # an alternative build of the library (kernel experiments)
+    _lib.LIB_PATH = os.path.abspath(sys.argv[3])
 
 p = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 nel = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
@@ -40,8 +43,30 @@ ts = []
 for _ in range(5):
     t = time.perf_counter(); res = api.pbi_h1_batch(no, noe, nof, etav, fv, fg); ts.append(time.perf_counter() - t)
 assert not res["info"].any()
+# the same call on page-locked caller arrays (hp3d_gpu_host_alloc): the copies become asynchronous DMA transfers
+L = _lib.lib()
+tp = []
+try:
+    keep = []
+
+    def pinned(a):
+        h = api.pinned_empty(a.shape, a.dtype); h.a[...] = a; keep.append(h); return h.a
+    pe, pfv, pfg = pinned(etav), pinned(fv), pinned(fg)
+    pd = pinned(np.zeros((nel, nH, 3))); info = np.zeros(nel, np.int32)
+    f = L.hp3d_gpu_pbi_h1_batch
+    for _ in range(5):
+        t = time.perf_counter()
+        rc = f(nel, None, api._ptr(no), api._ptr(noe), api._ptr(nof), 0, 9, api._ptr(pe), 3, api._ptr(pfv), api._ptr(pfg), int(np.prod(pfg.shape[1:])),
+               None, api._ptr(pd), 3 * nH, api._ptr(info))
+        tp.append(time.perf_counter() - t)
+        assert rc == 0 and not info.any()
+    assert np.array_equal(pd, res["dof"])
+except Exception as ex:
+    tp = []
+    print("pinned leg failed:", repr(ex), file=sys.stderr)
 out = {"what": "hp3d_gpu_pbi_h1_batch (update_gdof, 3 components), hexa p=%d, host buffers" % p, "elements": nel, "nrdofH": nH, "points_per_element": npts,
-       "e2e_elements_per_s": nel / min(ts), "ms_per_call": 1e3 * min(ts)}
+       "e2e_elements_per_s": nel / min(ts), "ms_per_call": 1e3 * min(ts),
+       "e2e_pinned_elements_per_s": (nel / min(tp)) if tp else None, "lib": os.path.basename(os.path.dirname(_lib.LIB_PATH)) + "/" + os.path.basename(_lib.LIB_PATH)}
 try:
     from oracle import oracle as O
     L = O.lib(); O.set_maxp(9)
