@@ -1226,7 +1226,10 @@ int hp3d_gpu_pbi_h1_batch(int nel, const int *etype, const int *norder, const in
     for (int s = 0; s < 3; s++) {
       if (!dims[g].stride[s]) continue;
       A.node0 = first[s]; A.ws_stride = dims[g].stride[s];
-      pbi_node_kernel<<<dim3(first[s + 1] - first[s], dims[g].ny[s]), 256, 0, g_compute>>>(A);
+      int nmax = 0;
+      for (int i = first[s]; i < first[s + 1]; i++) nmax = std::max(nmax, h.node[i].n);
+      if (nmax <= 64) pbi_node_kernel<4><<<dim3(first[s + 1] - first[s], dims[g].ny[s]), 256, 0, g_compute>>>(A);
+      else pbi_node_kernel<2><<<dim3(first[s + 1] - first[s], dims[g].ny[s]), 256, 0, g_compute>>>(A);
       g_launches++;
     }
     pos += n;

@@ -319,7 +319,10 @@ __global__ void pbi_vertex_kernel(PbiArgs A) {
   for (int c = 0; c < A.ncomp; c++) A.dof[(long long)e * A.dof_ld + (long long)v * A.ncomp + c] = A.fvert[((long long)e * 8 + v) * A.ncomp + c];
 }
 
-__global__ void __launch_bounds__(256) pbi_node_kernel(PbiArgs A) {
+// MINB = resident CTAs per SM the register budget is cut for: 4 (64 registers) wins while the node systems are small and the kernel is
+// latency-bound (p <= 5: +25..35 % measured), 2 (128 registers) for the GEMM-heavy middle nodes of higher orders (p = 7: 4 costs 9 %)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) pbi_node_kernel(PbiArgs A) {
   __shared__ double As[16][68], Bs[16][68];
   const int tid = threadIdx.x, inode = A.node0 + blockIdx.x;
   const PbiNode nd = A.nodes[inode];

@@ -67,6 +67,17 @@ except Exception as ex:
 out = {"what": "hp3d_gpu_pbi_h1_batch (update_gdof, 3 components), hexa p=%d, host buffers" % p, "elements": nel, "nrdofH": nH, "points_per_element": npts,
        "e2e_elements_per_s": nel / min(ts), "ms_per_call": 1e3 * min(ts),
        "e2e_pinned_elements_per_s": (nel / min(tp)) if tp else None, "lib": os.path.basename(os.path.dirname(_lib.LIB_PATH)) + "/" + os.path.basename(_lib.LIB_PATH)}
+# H(curl) / H(div) Dirichlet interpolation of the same elements (two real components; the systems do not depend on the data)
+for name, pts_f, run in (("hcurl", api.pbi_hcurl_points, lambda a, b: api.pbi_hcurl_batch(no, noe, nof, etav, a, b)),
+                         ("hdiv", api.pbi_hdiv_points, lambda a, b: api.pbi_hdiv_batch(no, noe, nof, etav, a))):
+    n2 = int(pts_f(no[:1], noe[:1], nof[:1])["npts"][0])
+    a = rng.standard_normal((nel, n2, 3, 2)); b = rng.standard_normal((nel, n2, 3, 2))
+    run(a, b)
+    tt = []
+    for _ in range(3):
+        t = time.perf_counter(); r2 = run(a, b); tt.append(time.perf_counter() - t)
+    assert not r2["info"].any()
+    out[name + "_e2e_elements_per_s"] = nel / min(tt)
 try:
     from oracle import oracle as O
     L = O.lib(); O.set_maxp(9)
