@@ -1190,8 +1190,8 @@ int hp3d_gpu_pbi_h1_batch(int nel, const int *etype, const int *norder, const in
       dims[g].stride[s] = st; dims[g].ny[s] = 0;
       if (!st) continue;
       const long long per_row = st * (first[s + 1] - first[s]) * (long long)sizeof(double);
-      dims[g].ny[s] = (int)std::max(1LL, std::min((long long)n, (1LL << 30) / per_row));
-      need_ws = std::max(need_ws, per_row * dims[g].ny[s]);
+      dims[g].ny[s] = (int)std::max(1LL, std::min(std::min((long long)n, 65535LL), (1LL << 30) / per_row));
+      if (st * (long long)sizeof(double) > PBI_SMALL_BYTES) need_ws = std::max(need_ws, per_row * dims[g].ny[s]);   // small nodes live in shared memory
     }
     elist.insert(elist.end(), groups[g].el.begin(), groups[g].el.end());
   }
@@ -1228,8 +1228,11 @@ int hp3d_gpu_pbi_h1_batch(int nel, const int *etype, const int *norder, const in
       A.node0 = first[s]; A.ws_stride = dims[g].stride[s];
       int nmax = 0;
       for (int i = first[s]; i < first[s + 1]; i++) nmax = std::max(nmax, h.node[i].n);
-      if (nmax <= 64) pbi_node_kernel<4><<<dim3(first[s + 1] - first[s], dims[g].ny[s]), 256, 0, g_compute>>>(A);
-      else pbi_node_kernel<2><<<dim3(first[s + 1] - first[s], dims[g].ny[s]), 256, 0, g_compute>>>(A);
+      const size_t small_bytes = sizeof(double) * (size_t)dims[g].stride[s];
+      if (small_bytes <= (size_t)PBI_SMALL_BYTES)   // D and G of every node of the launch fit in shared memory: 64-thread CTAs, no workspace traffic
+        pbi_node_kernel<4, true><<<dim3(first[s + 1] - first[s], std::min(n, 65535)), 64, small_bytes, g_compute>>>(A);
+      else if (nmax <= 64) pbi_node_kernel<4, false><<<dim3(first[s + 1] - first[s], dims[g].ny[s]), 256, 0, g_compute>>>(A);
+      else pbi_node_kernel<2, false><<<dim3(first[s + 1] - first[s], dims[g].ny[s]), 256, 0, g_compute>>>(A);
       g_launches++;
     }
     pos += n;
@@ -1311,7 +1314,7 @@ static int pbi_vec_batch(int space, int nel, const int *etype, const int *norder
       dims[g].stride[s] = st; dims[g].ny[s] = 0;
       if (!st) continue;
       const long long per_row = st * (first[s + 1] - first[s]) * (long long)sizeof(double);
-      dims[g].ny[s] = (int)std::max(1LL, std::min((long long)n, (1LL << 30) / per_row));
+      dims[g].ny[s] = (int)std::max(1LL, std::min(std::min((long long)n, 65535LL), (1LL << 30) / per_row));
       need_ws = std::max(need_ws, per_row * dims[g].ny[s]);
     }
     elist.insert(elist.end(), groups[g].el.begin(), groups[g].el.end());

@@ -321,15 +321,18 @@ __global__ void pbi_vertex_kernel(PbiArgs A) {
 
 // MINB = resident CTAs per SM the register budget is cut for: 4 (64 registers) wins while the node systems are small and the kernel is
 // latency-bound (p <= 5: +25..35 % measured), 2 (128 registers) for the GEMM-heavy middle nodes of higher orders (p = 7: 4 costs 9 %)
-template <int MINB>
-__global__ void __launch_bounds__(256, MINB) pbi_node_kernel(PbiArgs A) {
-  __shared__ double As[16][68], Bs[16][68];
+// SMALL: the node's D and G fit in shared memory (edges, faces up to p ~ 6): CTAs of 64 threads, up to 16 per SM, the products as plain
+// per-entry dot products -- these launches are barrier-bound, not flop-bound, so fewer idle threads per barrier is what pays.
+constexpr int PBI_SMALL_BYTES = 40 * 1024;
+template <int MINB, bool SMALL>
+__global__ void __launch_bounds__(SMALL ? 64 : 256, SMALL ? 16 : MINB) pbi_node_kernel(PbiArgs A) {
+  extern __shared__ double pbi_dyn[];
   const int tid = threadIdx.x, inode = A.node0 + blockIdx.x;
   const PbiNode nd = A.nodes[inode];
   const int n = nd.n, np = nd.np, nc = A.ncomp, K3 = 3 * np, R = n + nc;
   if (n <= 0) return;
-  double *D = A.ws + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * A.ws_stride;   // [R][K3]
-  double *G = D + (long long)R * K3;                                                    // [R][n]
+  double *D = SMALL ? pbi_dyn : A.ws + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * A.ws_stride;   // [R][K3]
+  double *G = D + (long long)R * K3;                                                                      // [R][n]
   const long long HS = (long long)A.nH * A.npts;
   for (int ie = blockIdx.y; ie < A.nel; ie += gridDim.y) {
     const int e = A.elems[ie];
@@ -391,41 +394,53 @@ __global__ void __launch_bounds__(256, MINB) pbi_node_kernel(PbiArgs A) {
     }
     __syncthreads();
     // ---- B: G[r][j] = sum_k D[r][k] D[j][k], r < R, j < n, tiles with j-tile <= r-tile (lower triangle + load rows)
-    const int tx = tid & 15, ty = tid >> 4;
-    for (int r0 = 0; r0 < R; r0 += 64)
-      for (int j0 = 0; j0 <= r0 && j0 < n; j0 += 64) {
-        double acc[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
-        for (int k0 = 0; k0 < K3; k0 += 16) {
-          {   // stage 64 rows x 16 k of both operands: thread -> (row = tid / 4, 4 consecutive k)
-            const int row = tid >> 2, kk = (tid & 3) * 4;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-              const int k = k0 + kk + q;
-              As[kk + q][row] = (r0 + row < R && k < K3) ? D[(long long)(r0 + row) * K3 + k] : 0.0;
-              Bs[kk + q][row] = (j0 + row < n && k < K3) ? D[(long long)(j0 + row) * K3 + k] : 0.0;
-            }
-          }
-          __syncthreads();
-#pragma unroll
-          for (int k = 0; k < 16; k++) {
-            double a[4], b[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) { a[q] = As[k][ty * 4 + q]; b[q] = Bs[k][tx * 4 + q]; }
-#pragma unroll
-            for (int p = 0; p < 4; p++)
-#pragma unroll
-              for (int q = 0; q < 4; q++) acc[p][q] += a[p] * b[q];
-          }
-          __syncthreads();
-        }
-#pragma unroll
-        for (int p = 0; p < 4; p++)
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const int r = r0 + ty * 4 + p, j = j0 + tx * 4 + q;
-            if (r < R && j < n) G[(long long)r * n + j] = acc[p][q];
-          }
+    if constexpr (SMALL) {
+      for (int q = tid; q < R * n; q += blockDim.x) {
+        const int r = q / n, j = q % n;
+        if (j > r) continue;
+        const double *a = D + r * K3, *b = D + j * K3;
+        double acc = 0.0;
+        for (int k = 0; k < K3; k++) acc += a[k] * b[k];
+        G[r * n + j] = acc;
       }
+    } else {
+      __shared__ double As[16][68], Bs[16][68];
+      const int tx = tid & 15, ty = tid >> 4;
+      for (int r0 = 0; r0 < R; r0 += 64)
+        for (int j0 = 0; j0 <= r0 && j0 < n; j0 += 64) {
+          double acc[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+          for (int k0 = 0; k0 < K3; k0 += 16) {
+            {   // stage 64 rows x 16 k of both operands: thread -> (row = tid / 4, 4 consecutive k)
+              const int row = tid >> 2, kk = (tid & 3) * 4;
+  #pragma unroll
+              for (int q = 0; q < 4; q++) {
+                const int k = k0 + kk + q;
+                As[kk + q][row] = (r0 + row < R && k < K3) ? D[(long long)(r0 + row) * K3 + k] : 0.0;
+                Bs[kk + q][row] = (j0 + row < n && k < K3) ? D[(long long)(j0 + row) * K3 + k] : 0.0;
+              }
+            }
+            __syncthreads();
+  #pragma unroll
+            for (int k = 0; k < 16; k++) {
+              double a[4], b[4];
+  #pragma unroll
+              for (int q = 0; q < 4; q++) { a[q] = As[k][ty * 4 + q]; b[q] = Bs[k][tx * 4 + q]; }
+  #pragma unroll
+              for (int p = 0; p < 4; p++)
+  #pragma unroll
+                for (int q = 0; q < 4; q++) acc[p][q] += a[p] * b[q];
+            }
+            __syncthreads();
+          }
+  #pragma unroll
+          for (int p = 0; p < 4; p++)
+  #pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const int r = r0 + ty * 4 + p, j = j0 + tx * 4 + q;
+              if (r < R && j < n) G[(long long)r * n + j] = acc[p][q];
+            }
+        }
+    }
     __syncthreads();
     // ---- C: right-looking Cholesky G = L L^T on the lower triangle; the load rows r >= n ride along (they end as y^T, L y = b)
     bool bad = false;
