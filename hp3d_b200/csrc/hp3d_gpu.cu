@@ -1315,7 +1315,7 @@ static int pbi_vec_batch(int space, int nel, const int *etype, const int *norder
       if (!st) continue;
       const long long per_row = st * (first[s + 1] - first[s]) * (long long)sizeof(double);
       dims[g].ny[s] = (int)std::max(1LL, std::min(std::min((long long)n, 65535LL), (1LL << 30) / per_row));
-      need_ws = std::max(need_ws, per_row * dims[g].ny[s]);
+      if (st * (long long)sizeof(double) > PBI_SMALL_BYTES) need_ws = std::max(need_ws, per_row * dims[g].ny[s]);
     }
     elist.insert(elist.end(), groups[g].el.begin(), groups[g].el.end());
   }
@@ -1348,7 +1348,9 @@ static int pbi_vec_batch(int space, int nel, const int *etype, const int *norder
     for (int s = 0; s < 2; s++) {   // edges, then faces
       if (!dims[g].stride[s]) continue;
       A.node0 = first[s]; A.ws_stride = dims[g].stride[s];
-      pbi_hcurl_kernel<<<dim3(first[s + 1] - first[s], dims[g].ny[s]), 256, 0, g_compute>>>(A);
+      const size_t small_bytes = sizeof(double) * (size_t)dims[g].stride[s];
+      if (small_bytes <= (size_t)PBI_SMALL_BYTES) pbi_hcurl_kernel<true><<<dim3(first[s + 1] - first[s], std::min(n, 65535)), 64, small_bytes, g_compute>>>(A);
+      else pbi_hcurl_kernel<false><<<dim3(first[s + 1] - first[s], dims[g].ny[s]), 256, 0, g_compute>>>(A);
       g_launches++;
     }
     pos += n;

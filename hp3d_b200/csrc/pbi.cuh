@@ -533,8 +533,20 @@ __device__ inline void pbi_rows_product(const double *D, int K3, int xrow0, int 
     }
 }
 
-__global__ void __launch_bounds__(256) pbi_hcurl_kernel(PbiEArgs A) {
-  __shared__ double As[16][68], Bs[16][68];
+// out[(orow0 + r) * ldo + ocol0 + j] as above by per-entry dot products (small nodes whose D lives in shared memory)
+__device__ inline void pbi_rows_product_small(const double *D, int K3, int xrow0, int nx, int yrow0, int ny, double *out, int ldo, int orow0, int ocol0) {
+  for (int q = threadIdx.x; q < nx * ny; q += blockDim.x) {
+    const int r = q / ny, j = q % ny;
+    const double *a = D + (xrow0 + r) * K3, *b = D + (yrow0 + j) * K3;
+    double acc = 0.0;
+    for (int k = 0; k < K3; k++) acc += a[k] * b[k];
+    out[(orow0 + r) * ldo + ocol0 + j] = acc;
+  }
+}
+
+template <bool SMALL>
+__global__ void __launch_bounds__(SMALL ? 64 : 256) pbi_hcurl_kernel(PbiEArgs A) {
+  extern __shared__ double pbi_dyn[];
   __shared__ double s_red[8];
   __shared__ int s_idx[8], s_piv;
   const int tid = threadIdx.x, inode = A.node0 + blockIdx.x;
@@ -545,7 +557,7 @@ __global__ void __launch_bounds__(256) pbi_hcurl_kernel(PbiEArgs A) {
   const bool face = nd.kind == 2 && !hdiv;   // the saddle-point path of dhpfaceE_opt
   // rows of D: [CE (nE, faces only) | E (nE) | GH (nHb) | Rc (nc, faces only) | Rv (nc)]
   const int rE = face ? nE : 0, rG = rE + nE, rRc = rG + nHb, rRv = rRc + (face ? nc : 0), nrows = rRv + nc;
-  double *D = A.ws + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * A.ws_stride;
+  double *D = SMALL ? pbi_dyn : A.ws + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * A.ws_stride;
   double *W = D + (long long)nrows * K3;   // [(nt + nc)][nt]: rows < nt the (symmetric) system, rows >= nt the load vectors
   const long long HS = (long long)A.nH * A.npts, ES = (long long)A.nEF * A.npts;
   for (int ie = blockIdx.y; ie < A.nel; ie += gridDim.y) {
@@ -626,15 +638,19 @@ __global__ void __launch_bounds__(256) pbi_hcurl_kernel(PbiEArgs A) {
     }
     __syncthreads();
     // ---- the system and its load vectors
+    auto product = [&](int xrow0, int nx, int yrow0, int ny, int orow0, int ocol0) {
+      if constexpr (SMALL) pbi_rows_product_small(D, K3, xrow0, nx, yrow0, ny, W, nt, orow0, ocol0);
+      else { __shared__ double As[16][68], Bs[16][68]; pbi_rows_product(D, K3, xrow0, nx, yrow0, ny, W, nt, orow0, ocol0, As, Bs); }
+    };
     if (!face) {
-      pbi_rows_product(D, K3, 0, nE, 0, nE, W, nt, 0, 0, As, Bs);           // mass matrix of the tangential component
-      pbi_rows_product(D, K3, rRv, nc, 0, nE, W, nt, nt, 0, As, Bs);
+      product(0, nE, 0, nE, 0, 0);             // mass matrix of the tangential (normal) component
+      product(rRv, nc, 0, nE, nt, 0);
     } else {
-      pbi_rows_product(D, K3, 0, nE, 0, nE, W, nt, 0, 0, As, Bs);           // curl-curl (DSYRK, :353)
-      pbi_rows_product(D, K3, rRc, nc, 0, nE, W, nt, nt, 0, As, Bs);
+      product(0, nE, 0, nE, 0, 0);             // curl-curl (DSYRK, :353)
+      product(rRc, nc, 0, nE, nt, 0);
       if (nHb > 0) {
-        pbi_rows_product(D, K3, rG, nHb, rE, nE, W, nt, nE, 0, As, Bs);     // B^T (DGEMM, :356)
-        pbi_rows_product(D, K3, rRv, nc, rG, nHb, W, nt, nt, nE, As, Bs);
+        product(rG, nHb, rE, nE, nE, 0);       // B^T (DGEMM, :356)
+        product(rRv, nc, rG, nHb, nt, nE);
         __syncthreads();
         for (int q = tid; q < nHb * nE; q += blockDim.x) { const int j = q / nE, i = q % nE; W[(long long)i * nt + nE + j] = W[(long long)(nE + j) * nt + i]; }
         for (int q = tid; q < nHb * nHb; q += blockDim.x) W[(long long)(nE + q / nHb) * nt + nE + q % nHb] = 0.0;
