@@ -1101,6 +1101,14 @@ struct PbiSig {
 std::map<std::string, std::unique_ptr<PbiSig>> g_pbisigs;
 CelemStore g_pbi_store;   // grow-only device buffers of hp3d_gpu_pbi_h1_batch
 void release_pbi_signatures() { g_pbisigs.clear(); g_pbi_store.release(); }
+// static + dynamic shared memory of the large-node variants exceeds the 48 KB default: opt in once per context
+int pbi_opt_in_smem() {
+  cudaError_t e = cudaFuncSetAttribute(pbi_node_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PBI_GSMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(pbi_node_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PBI_GSMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(pbi_hcurl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PBI_GSMEM_BYTES);
+  if (e != cudaSuccess) return fail(HP3D_ENODEV, "cudaFuncSetAttribute (projection-based interpolation kernels): %s", cudaGetErrorString(e));
+  return HP3D_OK;
+}
 
 // descriptors + points of a signature (host only); `tables` also builds and uploads the gradient table
 PbiSig *pbi_signature(int et, const int *norder, const int *norie, const int *norif, int integration, int maxp, bool tables, std::string &err,
@@ -1160,6 +1168,7 @@ int hp3d_gpu_pbi_h1_batch(int nel, const int *etype, const int *norder, const in
   if (nel < 0 || (nel > 0 && (!norder || !norie || !norif || !etav || !fvert || !fgrad || !dof))) return fail(HP3D_EINVAL, "pbi_h1: null argument");
   if (ncomp < 1 || ncomp > PBI_MAXCOMP) return fail(HP3D_EINVAL, "pbi_h1: ncomp = %d outside 1..%d (split the components over several calls)", ncomp, PBI_MAXCOMP);
   if (nel == 0) return HP3D_OK;
+  if (int rc = pbi_opt_in_smem()) return rc;
   // ---- signature groups (elements are addressed in place through an index list: no host-side gather)
   struct Group { PbiSig *S; std::vector<int> el; };
   std::map<const PbiSig *, size_t> where;
@@ -1220,7 +1229,7 @@ int hp3d_gpu_pbi_h1_batch(int nel, const int *etype, const int *norder, const in
     PbiArgs A;
     A.wa = S.d_wa; A.tan = S.d_tan; A.grad = S.d_grad; A.nodes = S.d_nodes; A.nH = h.nH; A.nrv = h.nrv; A.npts = h.npts; A.ncomp = ncomp;
     A.node0 = 0; A.nel = n; A.elems = dev_el + pos; A.etav = dev_ev; A.fgrad = dev_fg; A.fvert = dev_fv; A.mask = dev_m; A.dof = dev_d;
-    A.fgrad_ld = fgrad_ld; A.dof_ld = dof_ld; A.ws = dev_ws; A.ws_stride = 0; A.info = dinfo;
+    A.fgrad_ld = fgrad_ld; A.dof_ld = dof_ld; A.ws = dev_ws; A.ws_stride = 0; A.g_in_smem = 0; A.info = dinfo;
     pbi_vertex_kernel<<<(n * h.nrv + 127) / 128, 128, 0, g_compute>>>(A);
     g_launches++;
     for (int s = 0; s < 3; s++) {
@@ -1231,6 +1240,8 @@ int hp3d_gpu_pbi_h1_batch(int nel, const int *etype, const int *norder, const in
       const size_t small_bytes = sizeof(double) * (size_t)dims[g].stride[s];
       if (small_bytes <= (size_t)PBI_SMALL_BYTES)   // D and G of every node of the launch fit in shared memory: 64-thread CTAs, no workspace traffic
         pbi_node_kernel<4, true><<<dim3(first[s + 1] - first[s], std::min(n, 65535)), 64, small_bytes, g_compute>>>(A);
+      // (the system matrix of these larger nodes stays in the workspace: keeping it in shared memory was measured 9 % slower at p=5,
+      //  the middle-node launch is bound by the D traffic of phases A and B, not by the factorisation's barriers)
       else if (nmax <= 64) pbi_node_kernel<4, false><<<dim3(first[s + 1] - first[s], dims[g].ny[s]), 256, 0, g_compute>>>(A);
       else pbi_node_kernel<2, false><<<dim3(first[s + 1] - first[s], dims[g].ny[s]), 256, 0, g_compute>>>(A);
       g_launches++;
@@ -1281,6 +1292,7 @@ static int pbi_vec_batch(int space, int nel, const int *etype, const int *norder
   if (nel < 0 || (nel > 0 && (!norder || !norie || !norif || !etav || !fval || (space == PBI_HCURL && !fcurl) || !dof))) return fail(HP3D_EINVAL, "pbi_hcurl/hdiv: null argument");
   if (ncomp < 1 || ncomp > PBI_MAXCOMP) return fail(HP3D_EINVAL, "pbi_hcurl: ncomp = %d outside 1..%d (split the components over several calls)", ncomp, PBI_MAXCOMP);
   if (nel == 0) return HP3D_OK;
+  if (int rc = pbi_opt_in_smem()) return rc;
   struct Group { PbiSig *S; std::vector<int> el; };
   std::map<const PbiSig *, size_t> where;
   std::vector<Group> groups;
@@ -1308,7 +1320,8 @@ static int pbi_vec_batch(int space, int nel, const int *etype, const int *norder
       for (int i = first[s]; i < first[s + 1]; i++) {
         const PbiNode &nd = h.node[i];
         if (nd.n <= 0) continue;
-        const long long nt = nd.n + nd.nh, rows = (s ? 2LL * nd.n : nd.n) + nd.nh + (s ? 2 : 1) * ncomp;
+        const bool saddle = s == 1 && space == PBI_HCURL;   // H(curl) faces carry curl rows and curl residuals besides the value rows
+        const long long nt = nd.n + nd.nh, rows = (saddle ? 2LL * nd.n : nd.n) + nd.nh + (saddle ? 2 : 1) * ncomp;
         st = std::max(st, rows * 3LL * nd.np + (nt + ncomp) * nt);
       }
       dims[g].stride[s] = st; dims[g].ny[s] = 0;
@@ -1344,13 +1357,18 @@ static int pbi_vec_batch(int space, int nel, const int *etype, const int *norder
     PbiEArgs A;
     A.wa = S.d_wa; A.tan = S.d_tan; A.grad = S.d_grad; A.tabE = S.d_tabE; A.nodes = S.d_nodes; A.nH = h.nH; A.nEF = h.nEF; A.nrv = h.nrv; A.npts = h.npts;
     A.ncomp = ncomp; A.node0 = 0; A.nel = n; A.space = space; A.elems = dev_el + pos; A.etav = dev_ev; A.fval = dev_fv; A.fcurl = dev_fc; A.mask = dev_m; A.dof = dev_d;
-    A.f_ld = f_ld; A.dof_ld = dof_ld; A.ws = dev_ws; A.ws_stride = 0; A.info = dinfo;
+    A.f_ld = f_ld; A.dof_ld = dof_ld; A.ws = dev_ws; A.ws_stride = 0; A.g_in_smem = 0; A.info = dinfo;
     for (int s = 0; s < 2; s++) {   // edges, then faces
       if (!dims[g].stride[s]) continue;
       A.node0 = first[s]; A.ws_stride = dims[g].stride[s];
       const size_t small_bytes = sizeof(double) * (size_t)dims[g].stride[s];
       if (small_bytes <= (size_t)PBI_SMALL_BYTES) pbi_hcurl_kernel<true><<<dim3(first[s + 1] - first[s], std::min(n, 65535)), 64, small_bytes, g_compute>>>(A);
-      else pbi_hcurl_kernel<false><<<dim3(first[s + 1] - first[s], dims[g].ny[s]), 256, 0, g_compute>>>(A);
+      else {
+        size_t gbytes = 0;
+        for (int i = first[s]; i < first[s + 1]; i++) { const size_t nt = (size_t)h.node[i].n + h.node[i].nh; gbytes = std::max(gbytes, sizeof(double) * (nt + ncomp) * nt); }
+        A.g_in_smem = gbytes <= (size_t)PBI_GSMEM_BYTES;
+        pbi_hcurl_kernel<false><<<dim3(first[s + 1] - first[s], dims[g].ny[s]), 256, A.g_in_smem ? gbytes : 0, g_compute>>>(A);
+      }
       g_launches++;
     }
     pos += n;

@@ -307,6 +307,7 @@ struct PbiArgs {
   double *dof;                     // (ncomp, nH) per element, stride dof_ld
   long long fgrad_ld, dof_ld;
   double *ws; long long ws_stride; // workspace per CTA
+  int g_in_smem;                   // large-node variant: the n x n system (+ load rows) lives in dynamic shared memory, only D in the workspace
   int *info;
 };
 
@@ -324,6 +325,7 @@ __global__ void pbi_vertex_kernel(PbiArgs A) {
 // SMALL: the node's D and G fit in shared memory (edges, faces up to p ~ 6): CTAs of 64 threads, up to 16 per SM, the products as plain
 // per-entry dot products -- these launches are barrier-bound, not flop-bound, so fewer idle threads per barrier is what pays.
 constexpr int PBI_SMALL_BYTES = 40 * 1024;
+constexpr int PBI_GSMEM_BYTES = 36 * 1024;   // larger nodes: at least the system matrix (factorised under ~5 barriers per column) in shared memory
 template <int MINB, bool SMALL>
 __global__ void __launch_bounds__(SMALL ? 64 : 256, SMALL ? 16 : MINB) pbi_node_kernel(PbiArgs A) {
   extern __shared__ double pbi_dyn[];
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(SMALL ? 64 : 256, SMALL ? 16 : MINB) pbi_node_
   const int n = nd.n, np = nd.np, nc = A.ncomp, K3 = 3 * np, R = n + nc;
   if (n <= 0) return;
   double *D = SMALL ? pbi_dyn : A.ws + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * A.ws_stride;   // [R][K3]
-  double *G = D + (long long)R * K3;                                                                      // [R][n]
+  double *G = (!SMALL && A.g_in_smem) ? pbi_dyn : D + (long long)R * K3;                                  // [R][n]
   const long long HS = (long long)A.nH * A.npts;
   for (int ie = blockIdx.y; ie < A.nel; ie += gridDim.y) {
     const int e = A.elems[ie];
@@ -373,15 +375,20 @@ __global__ void __launch_bounds__(SMALL ? 64 : 256, SMALL ? 16 : MINB) pbi_node_
         weight = A.wa[gl] * bj;
       }
       const double sw = sqrt(weight);
-      double Rg[3 * PBI_MAXCOMP];   // Rg[c + nc*i] = d g_c / d eta_i minus the known part
-      for (int q = 0; q < 3 * nc; q++) Rg[q] = fg[(long long)gl * 3 * nc + q];
-      for (int k = 0; k < nd.nknown; k++) {
-        const double g0 = A.grad[(long long)k * A.npts + gl], g1 = A.grad[HS + (long long)k * A.npts + gl], g2 = A.grad[2 * HS + (long long)k * A.npts + gl];
-        const double du0 = g0 * Ji[0] + g1 * Ji[1] + g2 * Ji[2], du1 = g0 * Ji[3] + g1 * Ji[4] + g2 * Ji[5], du2 = g0 * Ji[6] + g1 * Ji[7] + g2 * Ji[8];
-        for (int c = 0; c < nc; c++) { const double z = dof[(long long)k * nc + c]; Rg[c] -= z * du0; Rg[c + nc] -= z * du1; Rg[c + 2 * nc] -= z * du2; }
+      // residual rows, one component at a time: R_c = d g_c / d eta minus the known part, accumulated in registers (the table
+      // entries are re-read per component from L1; independent loads, so the loop pipelines)
+      for (int c = 0; c < nc; c++) {
+        double r0 = fg[(long long)gl * 3 * nc + c], r1 = fg[(long long)gl * 3 * nc + nc + c], r2 = fg[(long long)gl * 3 * nc + 2 * nc + c];
+#pragma unroll 4
+        for (int k = 0; k < nd.nknown; k++) {
+          const double g0 = A.grad[(long long)k * A.npts + gl], g1 = A.grad[HS + (long long)k * A.npts + gl], g2 = A.grad[2 * HS + (long long)k * A.npts + gl];
+          const double z = dof[(long long)k * nc + c];
+          r0 -= z * (g0 * Ji[0] + g1 * Ji[1] + g2 * Ji[2]); r1 -= z * (g0 * Ji[3] + g1 * Ji[4] + g2 * Ji[5]); r2 -= z * (g0 * Ji[6] + g1 * Ji[7] + g2 * Ji[8]);
+        }
+        double *Dr = D + (long long)(n + c) * K3 + 3 * l;
+        Dr[0] = r0 * sw; Dr[1] = r1 * sw; Dr[2] = r2 * sw;
       }
-      for (int c = 0; c < nc; c++)
-        for (int i = 0; i < 3; i++) D[(long long)(n + c) * K3 + 3 * l + i] = Rg[c + nc * i] * sw;
+#pragma unroll 2
       for (int j = 0; j < n; j++) {
         const int k = nd.t0 + j;
         const double g0 = A.grad[(long long)k * A.npts + gl], g1 = A.grad[HS + (long long)k * A.npts + gl], g2 = A.grad[2 * HS + (long long)k * A.npts + gl];
@@ -492,6 +499,7 @@ struct PbiEArgs {
   double *dof;                         // (ncomp, nEF) per element, stride dof_ld
   long long f_ld, dof_ld;
   double *ws; long long ws_stride;
+  int g_in_smem;                       // large-node variant: W in dynamic shared memory
   int *info;
 };
 
@@ -558,7 +566,7 @@ __global__ void __launch_bounds__(SMALL ? 64 : 256) pbi_hcurl_kernel(PbiEArgs A)
   // rows of D: [CE (nE, faces only) | E (nE) | GH (nHb) | Rc (nc, faces only) | Rv (nc)]
   const int rE = face ? nE : 0, rG = rE + nE, rRc = rG + nHb, rRv = rRc + (face ? nc : 0), nrows = rRv + nc;
   double *D = SMALL ? pbi_dyn : A.ws + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * A.ws_stride;
-  double *W = D + (long long)nrows * K3;   // [(nt + nc)][nt]: rows < nt the (symmetric) system, rows >= nt the load vectors
+  double *W = (!SMALL && A.g_in_smem) ? pbi_dyn : D + (long long)nrows * K3;   // [(nt + nc)][nt]: rows < nt the (symmetric) system, rows >= nt the load vectors
   const long long HS = (long long)A.nH * A.npts, ES = (long long)A.nEF * A.npts;
   for (int ie = blockIdx.y; ie < A.nel; ie += gridDim.y) {
     const int e = A.elems[ie];
@@ -593,25 +601,24 @@ __global__ void __launch_bounds__(SMALL ? 64 : 256) pbi_hcurl_kernel(PbiEArgs A)
       const double bj = sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
       dir[0] /= bj; dir[1] /= bj; dir[2] /= bj;
       const double sw = sqrt(A.wa[gl] * bj);
-      // master -> eta: value u = Ji^T E^ (u_i = sum_a E^_a Ji[a + 3i]), curl cu = J C^ / det
-      double Rv[3 * PBI_MAXCOMP], Rc[3 * PBI_MAXCOMP];
-      for (int q = 0; q < 3 * nc; q++) { Rv[q] = fv[(long long)gl * 3 * nc + q]; Rc[q] = face ? fc[(long long)gl * 3 * nc + q] : 0.0; }
-      for (int k = 0; k < nd.nknown; k++) {   // the edges' contributions (dhpfaceE_opt.F90:275-293)
-        const double e0 = A.tabE[(long long)k * A.npts + gl], e1 = A.tabE[ES + (long long)k * A.npts + gl], e2 = A.tabE[2 * ES + (long long)k * A.npts + gl];
-        const double c0 = A.tabE[3 * ES + (long long)k * A.npts + gl], c1 = A.tabE[4 * ES + (long long)k * A.npts + gl], c2 = A.tabE[5 * ES + (long long)k * A.npts + gl];
-        const double u[3] = {e0 * Ji[0] + e1 * Ji[1] + e2 * Ji[2], e0 * Ji[3] + e1 * Ji[4] + e2 * Ji[5], e0 * Ji[6] + e1 * Ji[7] + e2 * Ji[8]};
-        const double cu[3] = {(J[0] * c0 + J[3] * c1 + J[6] * c2) / det, (J[1] * c0 + J[4] * c1 + J[7] * c2) / det, (J[2] * c0 + J[5] * c1 + J[8] * c2) / det};
-        for (int c = 0; c < nc; c++) {
-          const double z = dof[(long long)k * nc + c];
-          Rv[c] -= z * u[0]; Rv[c + nc] -= z * u[1]; Rv[c + 2 * nc] -= z * u[2];
-          Rc[c] -= z * cu[0]; Rc[c + nc] -= z * cu[1]; Rc[c + 2 * nc] -= z * cu[2];
+      // master -> eta: value u = Ji^T E^ (u_i = sum_a E^_a Ji[a + 3i]), curl cu = J C^ / det.  Residual rows one component at a time with
+      // register accumulators (the edges' contributions removed, dhpfaceE_opt.F90:275-293); the table entries are re-read from L1
+      for (int c = 0; c < nc; c++) {
+        const long long fo = (long long)gl * 3 * nc + c;
+        double v0 = fv[fo], v1 = fv[fo + nc], v2 = fv[fo + 2 * nc], c0r = 0.0, c1r = 0.0, c2r = 0.0;
+        if (face) { c0r = fc[fo]; c1r = fc[fo + nc]; c2r = fc[fo + 2 * nc]; }
+#pragma unroll 2
+        for (int k = 0; k < nd.nknown; k++) {
+          const double e0 = A.tabE[(long long)k * A.npts + gl], e1 = A.tabE[ES + (long long)k * A.npts + gl], e2 = A.tabE[2 * ES + (long long)k * A.npts + gl];
+          const double q0 = A.tabE[3 * ES + (long long)k * A.npts + gl], q1 = A.tabE[4 * ES + (long long)k * A.npts + gl], q2 = A.tabE[5 * ES + (long long)k * A.npts + gl];
+          const double z = dof[(long long)k * nc + c], zd = z / det;
+          v0 -= z * (e0 * Ji[0] + e1 * Ji[1] + e2 * Ji[2]); v1 -= z * (e0 * Ji[3] + e1 * Ji[4] + e2 * Ji[5]); v2 -= z * (e0 * Ji[6] + e1 * Ji[7] + e2 * Ji[8]);
+          c0r -= zd * (J[0] * q0 + J[3] * q1 + J[6] * q2); c1r -= zd * (J[1] * q0 + J[4] * q1 + J[7] * q2); c2r -= zd * (J[2] * q0 + J[5] * q1 + J[8] * q2);
         }
+        double *Dv = D + (long long)(rRv + c) * K3 + 3 * l;
+        Dv[0] = v0 * sw; Dv[1] = v1 * sw; Dv[2] = v2 * sw;
+        if (face) { double *Dc = D + (long long)(rRc + c) * K3 + 3 * l; Dc[0] = c0r * sw; Dc[1] = c1r * sw; Dc[2] = c2r * sw; }
       }
-      for (int c = 0; c < nc; c++)
-        for (int i = 0; i < 3; i++) {
-          D[(long long)(rRv + c) * K3 + 3 * l + i] = Rv[c + nc * i] * sw;
-          if (face) D[(long long)(rRc + c) * K3 + 3 * l + i] = Rc[c + nc * i] * sw;
-        }
       for (int j = 0; j < nE; j++) {
         const int k = nd.t0 + j;
         const double e0 = A.tabE[(long long)k * A.npts + gl], e1 = A.tabE[ES + (long long)k * A.npts + gl], e2 = A.tabE[2 * ES + (long long)k * A.npts + gl];
