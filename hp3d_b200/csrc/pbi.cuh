@@ -344,7 +344,11 @@ __global__ void __launch_bounds__(SMALL ? 64 : 256, SMALL ? 16 : MINB) pbi_node_
     const double *fg = A.fgrad + (long long)e * A.fgrad_ld;
     __syncthreads();   // the previous element's solve has finished with D / G
     // ---- A: one thread per point
-    for (int l = tid; l < np; l += blockDim.x) {
+    // a thread owns (point l, slice sl): with fewer points than threads the rows of D are dealt out over nsl slices per point (each
+    // slice recomputes the point's geometry: 8 vertex gradients)
+    const int nsl = max(1, (int)blockDim.x / np);
+    for (int item = tid; item < np * nsl; item += blockDim.x) {
+      const int l = item % np, sl = item / np;
       const int gl = nd.p0 + l;
       double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // J[c + 3m] = d eta_c / d xi_m
       for (int v = 0; v < A.nrv; v++) {
@@ -377,7 +381,7 @@ __global__ void __launch_bounds__(SMALL ? 64 : 256, SMALL ? 16 : MINB) pbi_node_
       const double sw = sqrt(weight);
       // residual rows, one component at a time: R_c = d g_c / d eta minus the known part, accumulated in registers (the table
       // entries are re-read per component from L1; independent loads, so the loop pipelines)
-      for (int c = 0; c < nc; c++) {
+      for (int c = sl; c < nc; c += nsl) {
         double r0 = fg[(long long)gl * 3 * nc + c], r1 = fg[(long long)gl * 3 * nc + nc + c], r2 = fg[(long long)gl * 3 * nc + 2 * nc + c];
 #pragma unroll 4
         for (int k = 0; k < nd.nknown; k++) {
@@ -389,7 +393,7 @@ __global__ void __launch_bounds__(SMALL ? 64 : 256, SMALL ? 16 : MINB) pbi_node_
         Dr[0] = r0 * sw; Dr[1] = r1 * sw; Dr[2] = r2 * sw;
       }
 #pragma unroll 2
-      for (int j = 0; j < n; j++) {
+      for (int j = sl; j < n; j += nsl) {
         const int k = nd.t0 + j;
         const double g0 = A.grad[(long long)k * A.npts + gl], g1 = A.grad[HS + (long long)k * A.npts + gl], g2 = A.grad[2 * HS + (long long)k * A.npts + gl];
         double dv[3] = {g0 * Ji[0] + g1 * Ji[1] + g2 * Ji[2], g0 * Ji[3] + g1 * Ji[4] + g2 * Ji[5], g0 * Ji[6] + g1 * Ji[7] + g2 * Ji[8]};
@@ -553,7 +557,7 @@ __device__ inline void pbi_rows_product_small(const double *D, int K3, int xrow0
 }
 
 template <bool SMALL>
-__global__ void __launch_bounds__(SMALL ? 64 : 256) pbi_hcurl_kernel(PbiEArgs A) {
+__global__ void __launch_bounds__(SMALL ? 64 : 256, SMALL ? 6 : 2) pbi_hcurl_kernel(PbiEArgs A) {
   extern __shared__ double pbi_dyn[];
   __shared__ double s_red[8];
   __shared__ int s_idx[8], s_piv;
@@ -575,7 +579,11 @@ __global__ void __launch_bounds__(SMALL ? 64 : 256) pbi_hcurl_kernel(PbiEArgs A)
     double *dof = A.dof + (long long)e * A.dof_ld;
     const double *fv = A.fval + (long long)e * A.f_ld, *fc = A.fcurl + (long long)e * A.f_ld;
     __syncthreads();
-    for (int l = tid; l < np; l += blockDim.x) {
+    // a thread owns (point l, slice sl): with fewer points than threads the rows of D are dealt out over nsl slices per point (each
+    // slice recomputes the point's geometry: 8 vertex gradients)
+    const int nsl = max(1, (int)blockDim.x / np);
+    for (int item = tid; item < np * nsl; item += blockDim.x) {
+      const int l = item % np, sl = item / np;
       const int gl = nd.p0 + l;
       double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
       for (int v = 0; v < A.nrv; v++) {
@@ -603,7 +611,7 @@ __global__ void __launch_bounds__(SMALL ? 64 : 256) pbi_hcurl_kernel(PbiEArgs A)
       const double sw = sqrt(A.wa[gl] * bj);
       // master -> eta: value u = Ji^T E^ (u_i = sum_a E^_a Ji[a + 3i]), curl cu = J C^ / det.  Residual rows one component at a time with
       // register accumulators (the edges' contributions removed, dhpfaceE_opt.F90:275-293); the table entries are re-read from L1
-      for (int c = 0; c < nc; c++) {
+      for (int c = sl; c < nc; c += nsl) {
         const long long fo = (long long)gl * 3 * nc + c;
         double v0 = fv[fo], v1 = fv[fo + nc], v2 = fv[fo + 2 * nc], c0r = 0.0, c1r = 0.0, c2r = 0.0;
         if (face) { c0r = fc[fo]; c1r = fc[fo + nc]; c2r = fc[fo + 2 * nc]; }
@@ -619,7 +627,7 @@ __global__ void __launch_bounds__(SMALL ? 64 : 256) pbi_hcurl_kernel(PbiEArgs A)
         Dv[0] = v0 * sw; Dv[1] = v1 * sw; Dv[2] = v2 * sw;
         if (face) { double *Dc = D + (long long)(rRc + c) * K3 + 3 * l; Dc[0] = c0r * sw; Dc[1] = c1r * sw; Dc[2] = c2r * sw; }
       }
-      for (int j = 0; j < nE; j++) {
+      for (int j = sl; j < nE; j += nsl) {
         const int k = nd.t0 + j;
         const double e0 = A.tabE[(long long)k * A.npts + gl], e1 = A.tabE[ES + (long long)k * A.npts + gl], e2 = A.tabE[2 * ES + (long long)k * A.npts + gl];
         double v[3] = {e0 * Ji[0] + e1 * Ji[1] + e2 * Ji[2], e0 * Ji[3] + e1 * Ji[4] + e2 * Ji[5], e0 * Ji[6] + e1 * Ji[7] + e2 * Ji[8]};
@@ -635,7 +643,7 @@ __global__ void __launch_bounds__(SMALL ? 64 : 256) pbi_hcurl_kernel(PbiEArgs A)
           for (int i = 0; i < 3; i++) D[(long long)j * K3 + 3 * l + i] = pc * dir[i] * sw;     // :315-316
         }
       }
-      for (int j = 0; j < nHb; j++) {   // surface gradients of the face's H1 bubbles (:329-347)
+      for (int j = sl; j < nHb; j += nsl) {   // surface gradients of the face's H1 bubbles (:329-347)
         const int k = nd.th0 + j;
         const double g0 = A.grad[(long long)k * A.npts + gl], g1 = A.grad[HS + (long long)k * A.npts + gl], g2 = A.grad[2 * HS + (long long)k * A.npts + gl];
         double dv[3] = {g0 * Ji[0] + g1 * Ji[1] + g2 * Ji[2], g0 * Ji[3] + g1 * Ji[4] + g2 * Ji[5], g0 * Ji[6] + g1 * Ji[7] + g2 * Ji[8]};
