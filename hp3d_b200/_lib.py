@@ -28,7 +28,7 @@ EXPORTS = [
     "hp3d_gpu_sizes_t", "hp3d_gpu_bench_t", "hp3d_gpu_integrate_debug_t", "hp3d_gpu_prism_shape", "hp3d_gpu_sig_dims", "hp3d_gpu_elem_bwd_batch", "hp3d_gpu_elem_residual_batch",
     "hp3d_gpu_physics_default", "hp3d_gpu_celem_pack", "hp3d_gpu_celem_batch",
     "hp3d_gpu_elem_error_batch", "hp3d_gpu_error_points", "hp3d_gpu_chunk_plan_debug",
-    "hp3d_gpu_pbi_points", "hp3d_gpu_pbi_h1_batch", "hp3d_gpu_pbi_hcurl_points", "hp3d_gpu_pbi_hcurl_batch", "hp3d_gpu_pbi_hdiv_points", "hp3d_gpu_pbi_hdiv_batch",
+    "hp3d_gpu_pbi_points", "hp3d_gpu_pbi_h1_batch", "hp3d_gpu_pbi_hcurl_points", "hp3d_gpu_pbi_hcurl_batch", "hp3d_gpu_pbi_hdiv_points", "hp3d_gpu_pbi_hdiv_batch", "hp3d_gpu_pbi_cache_limit",
 ]
 
 

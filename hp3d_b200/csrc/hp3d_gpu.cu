@@ -1100,7 +1100,21 @@ struct PbiSig {
 };
 std::map<std::string, std::unique_ptr<PbiSig>> g_pbisigs;
 CelemStore g_pbi_store;   // grow-only device buffers of hp3d_gpu_pbi_h1_batch
-void release_pbi_signatures() { g_pbisigs.clear(); g_pbi_store.release(); }
+size_t g_pbi_table_bytes = 0;                        // device bytes held by the cached signature tables
+size_t PBI_TABLE_CACHE_BYTES = 8ull << 30;           // hp meshes produce thousands of signatures (2.6 MB each at p=5): bound the cache
+void release_pbi_signatures() { g_pbisigs.clear(); g_pbi_store.release(); g_pbi_table_bytes = 0; }
+// called at the start of a batch call (no kernel of this library is in flight on the tables then): drop the device tables, keep the
+// host-side descriptors; the signatures a call needs are rebuilt on demand
+void pbi_trim_table_cache() {
+  if (g_pbi_table_bytes <= PBI_TABLE_CACHE_BYTES) return;
+  cudaDeviceSynchronize();
+  for (auto &kv : g_pbisigs) {
+    PbiSig &S = *kv.second;
+    cudaFree(S.d_wa); cudaFree(S.d_tan); cudaFree(S.d_grad); cudaFree(S.d_tabE); cudaFree(S.d_nodes);
+    S.d_wa = S.d_tan = S.d_grad = S.d_tabE = nullptr; S.d_nodes = nullptr; S.on_device = false;
+  }
+  g_pbi_table_bytes = 0;
+}
 // static + dynamic shared memory of the large-node variants exceeds the 48 KB default: opt in once per context
 int pbi_opt_in_smem() {
   cudaError_t e = cudaFuncSetAttribute(pbi_node_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PBI_GSMEM_BYTES);
@@ -1129,6 +1143,7 @@ PbiSig *pbi_signature(int et, const int *norder, const int *norie, const int *no
         dev_upload(full.tabE, &S->d_tabE, err) || dev_upload(nodes, &S->d_nodes, err))
       return nullptr;
     S->on_device = true;
+    g_pbi_table_bytes += sizeof(double) * (full.wa.size() + full.tan.size() + full.grad.size() + full.tabE.size()) + sizeof(PbiNode) * nodes.size();
   }
   return S;
 }
@@ -1169,6 +1184,7 @@ int hp3d_gpu_pbi_h1_batch(int nel, const int *etype, const int *norder, const in
   if (ncomp < 1 || ncomp > PBI_MAXCOMP) return fail(HP3D_EINVAL, "pbi_h1: ncomp = %d outside 1..%d (split the components over several calls)", ncomp, PBI_MAXCOMP);
   if (nel == 0) return HP3D_OK;
   if (int rc = pbi_opt_in_smem()) return rc;
+  pbi_trim_table_cache();
   // ---- signature groups (elements are addressed in place through an index list: no host-side gather)
   struct Group { PbiSig *S; std::vector<int> el; };
   std::map<const PbiSig *, size_t> where;
@@ -1293,6 +1309,7 @@ static int pbi_vec_batch(int space, int nel, const int *etype, const int *norder
   if (ncomp < 1 || ncomp > PBI_MAXCOMP) return fail(HP3D_EINVAL, "pbi_hcurl: ncomp = %d outside 1..%d (split the components over several calls)", ncomp, PBI_MAXCOMP);
   if (nel == 0) return HP3D_OK;
   if (int rc = pbi_opt_in_smem()) return rc;
+  pbi_trim_table_cache();
   struct Group { PbiSig *S; std::vector<int> el; };
   std::map<const PbiSig *, size_t> where;
   std::vector<Group> groups;
@@ -1402,6 +1419,13 @@ int hp3d_gpu_pbi_hdiv_batch(int nel, const int *etype, const int *norder, const 
   return pbi_vec_batch(PBI_HDIV, nel, etype, norder, norie, norif, maxp, etav, ncomp, fval, nullptr, f_ld, mask, dof, dof_ld, info);
 }
 }  // extern "C"
+
+extern "C" int hp3d_gpu_pbi_cache_limit(long long bytes) {
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  if (bytes < 0) return fail(HP3D_EINVAL, "pbi_cache_limit: negative size");
+  PBI_TABLE_CACHE_BYTES = (size_t)bytes;
+  return HP3D_OK;
+}
 
 extern "C" int hp3d_gpu_chunk_plan_debug(long long ntot, int cap, int nlanes, int max_chunk, long long *sizes, int cap_sizes) {
   if (ntot < 0 || cap < 1 || nlanes < 1) return fail(HP3D_EINVAL, "chunk_plan: bad argument");

@@ -282,6 +282,10 @@ int hp3d_gpu_pbi_hdiv_batch(int nel, const int *etype, const int *norder, const 
                             const double *etav, int ncomp, const double *fval, long long f_ld, const unsigned *mask, double *dof,
                             long long dof_ld, int *info);
 
+/* Device memory the cached signature tables of the interpolation entry points may hold (default 8 GiB; one H1 signature is 2.6 MB at
+ * p=5, an hp mesh has thousands).  When a batch call starts above the limit the tables are dropped and rebuilt on demand. */
+int hp3d_gpu_pbi_cache_limit(long long bytes);
+
 /* ---- host-only introspection (no GPU needed): the signed tensor-product description of the shape functions.
  * space: 0 H1, 1 H(curl), 2 H(div), 3 L2.  For dof k (reference order, src/element/shape_1/Hexahedron.F90):
  *   fam[k] vector direction (0..2, -1 scalar), idx[3k..3k+2] 1-D table index per axis, sgn[k] = +-1.

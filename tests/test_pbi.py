@@ -515,3 +515,23 @@ def test_gpu_reproduces_pbi_golden(gpu, path):
         assert n == len(g[f"v_eta{e}"]) and np.abs(mine - g[f"v_eta{e}"]).max() < 1e-14
         res = api.pbi_hdiv_batch(no, noe, nof, etav[None], g[f"v_fval{e}"][None], etype=etype)
         assert not res["info"].any() and np.abs(res["dof"][0] - g[f"v_dof{e}"]).max() < 1e-11
+
+
+@pytest.mark.gpu
+def test_gpu_table_cache_trim_keeps_results(oracle, gpu):
+    """with a 1-byte limit every call drops the cached device tables first and rebuilds them: same dofs as with the cache"""
+    import ctypes as C
+    rng = np.random.default_rng(31)
+    no, noe, nof = random_brick(rng, 2, 4)
+    etav = warped_vertices(rng, MDLB)[None]
+    etype = np.array([MDLB], np.int32)
+    pts = api.pbi_points(no, noe, nof, etype=etype)
+    fv, fg = tabulate(smooth, 2, pts, etav, etype)
+    ref = api.pbi_h1_batch(no, noe, nof, etav, fv, fg, etype=etype)["dof"]
+    gpu.hp3d_gpu_pbi_cache_limit.argtypes = [C.c_longlong]
+    try:
+        assert gpu.hp3d_gpu_pbi_cache_limit(1) == 0
+        for _ in range(2):
+            assert np.array_equal(api.pbi_h1_batch(no, noe, nof, etav, fv, fg, etype=etype)["dof"], ref)
+    finally:
+        gpu.hp3d_gpu_pbi_cache_limit(8 << 30)
