@@ -226,6 +226,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--condensed-only", action="store_true", help="also time the end-to-end step with hp3d_params.store_schur = 0: only the condensed system returns (5.8 instead of 13.0 MB per element at p=5); the bubbles are recovered by hp3d_gpu_elem_bwd_batch")
     ap.add_argument("--celem", action="store_true", help="also time SURVEY 8f row f1 (constraints + compression + COO fused into the batched call)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -314,6 +315,32 @@ def main():
         celem = None
         if args.celem:
             celem = celem_leg(args, eng, norder[:Be], noe[:Be], nof[:Be], xs.a, ni, nb, bufs, rank)
+        # ---- optional: STORE_STC off -- only Aii / Bi cross PCIe (SURVEY 8f row f3 recomputes the factors on the device when needed)
+        cond_only = None
+        if args.condensed_only:
+            eng2 = ElemEngine(args.kind, device=local, omega=omega, real_reduction=0 if args.complex_kernels else 1, store_schur=0)
+            tiny = [pinned_empty((Be, 1), dt), pinned_empty((Be, 1), dt)]
+            out2 = dict(Aii=bufs[0].a, Bi=bufs[1].a, ASchur=tiny[0].a, BSchur=tiny[1].a)
+            for _ in range(2):
+                eng2.elem_stc_batch(norder[:Be], noe[:Be], nof[:Be], xs.a, out=out2)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                res2 = eng2.elem_stc_batch(norder[:Be], noe[:Be], nof[:Be], xs.a, out=out2)
+            t2 = time.perf_counter() - t0
+            barrier()
+            assert (res2["info"] == 0).all()
+            if dist is not None:
+                import torch
+                t = torch.tensor([t2], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                t2 = float(t.item())
+            cond_only = {"value": world * Be * args.steps / t2, "unit": "elements/s", "elements_per_gpu_per_step": Be,
+                         "d2h_bytes_per_step": int(Be * (es * (ni * ni + ni) + 4)),
+                         "what": "hp3d_gpu_elem_batch with store_schur = 0: the condensed system only (stc.F90 STORE_STC = .false.)"}
+            for b in tiny:
+                b.free()
+            eng2.close()
         for b in bufs + [xs]:
             b.free()
 
@@ -344,6 +371,8 @@ def main():
     }
     if not args.no_e2e and args.celem:
         out["celem"] = celem
+    if not args.no_e2e and args.condensed_only:
+        out["e2e_condensed_only"] = cond_only
     if not args.no_cpu and world == 1:   # CPU baseline beside the GPU number: rank 0 at N=1 only
         cores = host_cores()
         ns = args.cpu_sample or max(16 * cores, 64)   # ~15 s of CPU work (bounded sample)
