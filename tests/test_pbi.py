@@ -535,3 +535,61 @@ def test_gpu_table_cache_trim_keeps_results(oracle, gpu):
             assert np.array_equal(api.pbi_h1_batch(no, noe, nof, etav, fv, fg, etype=etype)["dof"], ref)
     finally:
         gpu.hp3d_gpu_pbi_cache_limit(8 << 30)
+
+
+# ------------------------------------------------------------------------------------------------- more host logic (CPU): MAXP cap, tables
+@pytest.mark.parametrize("et", [MDLB, MDLP])
+def test_points_respect_the_maxp_cap(oracle, gpulib, et):
+    """order + INTEGRATION is capped at MAXP (set_1D_int.F90:40-43 and its 2-D / 3-D twins): with MAXP = 4 an order-4 node keeps 5 points
+    per direction under INTEGRATION = 1; the oracle visits the same points for all three families"""
+    oracle.set_maxp(4)
+    try:
+        rng = np.random.default_rng(41)
+        no, noe, nof = (random_brick if et == MDLB else random_prism)(rng, 3, 4)
+        etav = warped_vertices(rng, et); nv = 8 if et == MDLB else 6
+        for fam in ("h1", "hcurl", "hdiv"):
+            seen = []
+            if fam == "h1":
+                oracle.pbi_element(no, noe, nof, etav[:nv], lambda eta: (seen.append(eta.copy()), (np.zeros(1), np.zeros((1, 3))))[1], 1,
+                                   integration=1, maxp=4, etype=et)
+                seen = seen[nv:]
+                pts = api.pbi_points(no, noe, nof, integration=1, maxp=4, etype=et)
+            else:
+                f = lambda eta: (seen.append(eta.copy()), (np.zeros((1, 3)), np.zeros((1, 3)), np.eye(3)))[1]   # noqa: E731
+                (oracle.pbi_hcurl_element if fam == "hcurl" else oracle.pbi_hdiv_element)(no, noe, nof, etav[:nv], f, 1, maxp=4, etype=et)
+                pts = (api.pbi_hcurl_points if fam == "hcurl" else api.pbi_hdiv_points)(no, noe, nof, maxp=4, etype=et)
+            n = int(pts["npts"][0])
+            assert n == len(seen), fam
+            mine = np.array([vertex_shape(et, x) @ etav[:nv] for x in pts["xi"][0, :n]])
+            assert np.abs(np.array(seen) - mine).max() < 1e-14, fam
+            uncapped = (api.pbi_points(no, noe, nof, integration=1, maxp=9, etype=et) if fam == "h1" else
+                        (api.pbi_hcurl_points if fam == "hcurl" else api.pbi_hdiv_points)(no, noe, nof, maxp=9, etype=et))
+            assert int(uncapped["npts"][0]) > n, fam
+    finally:
+        oracle.set_maxp(9)
+
+
+def test_node_tables_are_consistent(gpulib):
+    """for random descriptors: dof ranges of the nodes tile [0, nrdof), point ranges tile [0, npts), nodes without dofs have no points"""
+    rng = np.random.default_rng(43)
+    for _ in range(20):
+        et = MDLB if rng.random() < 0.5 else MDLP
+        no, noe, nof = (random_brick if et == MDLB else random_prism)(rng, 1, 6)
+        nn = 27 if et == MDLB else 21
+        for pts, key in ((api.pbi_points(no, noe, nof, integration=int(rng.integers(0, 2)), etype=et), "nrdofH"),
+                         (api.pbi_hcurl_points(no, noe, nof, etype=et), "nrdofE"), (api.pbi_hdiv_points(no, noe, nof, etype=et), "nrdofV")):
+            t = pts["nodes"][0]
+            d0 = 0; p0 = 0
+            for i in range(nn):
+                if key != "nrdofH" and i == nn - 1:
+                    assert t[i, 1] == 0 and t[i, 3] == 0      # no Dirichlet data on middle nodes
+                    continue
+                assert t[i, 0] == d0
+                d0 += t[i, 1]
+                if t[i, 3]:
+                    assert t[i, 1] > 0 and t[i, 2] == p0
+                    p0 += t[i, 3]
+                elif key == "nrdofH" and i >= (8 if et == MDLB else 6):
+                    assert t[i, 1] == 0
+            assert d0 == int(pts[key][0]) and p0 == int(pts["npts"][0])
+            assert not t[nn:].any()
