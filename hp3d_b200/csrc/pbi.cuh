@@ -1,6 +1,6 @@
 // pbi.cuh -- batched H1 projection-based interpolation (interpolation half):
-//   geometry dofs      update_gdof.F90:88-200,409-435 -> hpvert.F90:19, hpedge.F90:27, hpface_opt.F90:27, hpmdle_opt.F90:23
-//   H1 Dirichlet dofs  update_Ddof.F90              -> dhpvert.F90:26, edge/dhpedgeH.F90:32, face/dhpfaceH_opt.F90:32
+//   geometry dofs      update_gdof.F90:88-200,409-435 -> hpvert.F90:22, hpedge.F90:23, hpface_opt.F90:24, hpmdle_opt.F90:23
+//   H1 Dirichlet dofs  update_Ddof.F90              -> dhpvert.F90:19, edge/dhpedgeH.F90:25, face/dhpfaceH_opt.F90:27
 // One algorithm: the interpolated function g (the GMP map x(eta): 3 components, INTEGRATION = 0; or a Dirichlet datum
 // u(x(eta)): NREQNH real / 2 NREQNH interleaved complex components, INTEGRATION = 1) enters through its vertex values and
 // through its gradient in the reference coordinates eta of the GMP block, tabulated by the host at the points this file
@@ -15,9 +15,9 @@
 //   A  a thread owns a point: Jacobian of eta(xi), tangent / normal, residual gradient R = dg/deta - sum_known dof_k grad phi_k,
 //      projected test gradients; both scaled by sqrt(weight) and stored as rows of one matrix D = [test rows ; R rows]
 //   B  G = D D_test^T  (64 x 64 register-tiled product: rows 0..n-1 the stiffness, rows n.. the load vectors) -- the reference's
-//      DSFRK + load loop (hpface_opt.F90:195-222)
+//      DSFRK + load loop (hpface_opt.F90:203-237)
 //   C  Cholesky of the stiffness with the load rows carried along (forward substitution for free), back substitution
-//      (DPFTRF / DPFTRS, hpface_opt.F90:235-247; the edge routine's DGETRF solves the same SPD system).
+//      (DPFTRF / DPFTRS, hpface_opt.F90:254-261; the edge routine's DGETRF solves the same SPD system).
 #pragma once
 #include "error_eval.cuh"
 
@@ -93,7 +93,7 @@ inline bool compile_pbi_signature(int etype, const int *norder, const int *norie
   S.nH = off;
   for (int i = nrv; i < S.nnode; i++)
     S.node[i].nknown = S.node[i].kind == 1 ? nrv : (S.node[i].kind == 2 ? S.node[nrv + nre].t0 : S.node[S.nnode - 1].t0);
-  if (space == PBI_HCURL) {   // E dofs of the edge and face nodes; the H1 bubbles of a face become its multipliers (dhpfaceE_opt.F90:329-347)
+  if (space == PBI_HCURL) {   // E dofs of the edge and face nodes; the H1 bubbles of a face become its multipliers (dhpfaceE_opt.F90:358-372)
     int offE = 0;
     for (int i = 0; i < S.nnode; i++) {
       PbiNode &nd = S.node[i];
@@ -179,7 +179,7 @@ inline bool compile_pbi_signature(int etype, const int *norder, const int *norie
     }
     nd.np = (int)tw.size();
   }
-  {   // set_3Dint with the orders as stored (hpmdle_opt.F90:121; set_3D_int.F90:155-259)
+  {   // set_3Dint with the orders as stored (hpmdle_opt.F90:119; set_3D_int.F90:155-259)
     PbiNode &nd = S.node[S.nnode - 1];
     nd.p0 = (int)S.wa.size();
     const int zero[6] = {0, 0, 0, 0, 0, 0};
@@ -311,7 +311,7 @@ struct PbiArgs {
   int *info;
 };
 
-// vertices: the value of g (hpvert.F90:19-45, dhpvert.F90:60-75)
+// vertices: the value of g (hpvert.F90:22-58, dhpvert.F90:73-111)
 __global__ void pbi_vertex_kernel(PbiArgs A) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.nel * A.nrv) return;
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(SMALL ? 64 : 256, SMALL ? 16 : MINB) pbi_node_
         double d1[3], d2[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) { d1[c] = J[c] * t[0] + J[c + 3] * t[1] + J[c + 6] * t[2]; d2[c] = J[c] * t[3] + J[c + 3] * t[4] + J[c + 6] * t[5]; }
-        if (nd.kind == 1) { dir[0] = d1[0]; dir[1] = d1[1]; dir[2] = d1[2]; }   // hpedge.F90:134-141
+        if (nd.kind == 1) { dir[0] = d1[0]; dir[1] = d1[1]; dir[2] = d1[2]; }   // hpedge.F90:140-146
         else { dir[0] = d1[1] * d2[2] - d1[2] * d2[1]; dir[1] = d1[2] * d2[0] - d1[0] * d2[2]; dir[2] = d1[0] * d2[1] - d1[1] * d2[0]; }   // brefgeom3D
         const double bj = sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
         dir[0] /= bj; dir[1] /= bj; dir[2] /= bj;
@@ -398,8 +398,8 @@ __global__ void __launch_bounds__(SMALL ? 64 : 256, SMALL ? 16 : MINB) pbi_node_
         const double g0 = A.grad[(long long)k * A.npts + gl], g1 = A.grad[HS + (long long)k * A.npts + gl], g2 = A.grad[2 * HS + (long long)k * A.npts + gl];
         double dv[3] = {g0 * Ji[0] + g1 * Ji[1] + g2 * Ji[2], g0 * Ji[3] + g1 * Ji[4] + g2 * Ji[5], g0 * Ji[6] + g1 * Ji[7] + g2 * Ji[8]};
         const double pr = dv[0] * dir[0] + dv[1] * dir[1] + dv[2] * dir[2];
-        if (nd.kind == 1) { dv[0] = pr * dir[0]; dv[1] = pr * dir[1]; dv[2] = pr * dir[2]; }           // hpedge.F90:186-187
-        else if (nd.kind == 2) { dv[0] -= pr * dir[0]; dv[1] -= pr * dir[1]; dv[2] -= pr * dir[2]; }    // hpface_opt.F90:205-206
+        if (nd.kind == 1) { dv[0] = pr * dir[0]; dv[1] = pr * dir[1]; dv[2] = pr * dir[2]; }           // hpedge.F90:188-189
+        else if (nd.kind == 2) { dv[0] -= pr * dir[0]; dv[1] -= pr * dir[1]; dv[2] -= pr * dir[2]; }    // hpface_opt.F90:213-214
         for (int i = 0; i < 3; i++) D[(long long)j * K3 + 3 * l + i] = dv[i] * sw;
       }
     }
@@ -487,12 +487,12 @@ __global__ void __launch_bounds__(SMALL ? 64 : 256, SMALL ? 16 : MINB) pbi_node_
   }
 }
 
-// ---- H(curl) Dirichlet dofs: edge/dhpedgeE.F90:33-391, face/dhpfaceE_opt.F90:33-549 -------------------------------------------------
+// ---- H(curl) Dirichlet dofs: edge/dhpedgeE.F90:24-391, face/dhpfaceE_opt.F90:26-549 -------------------------------------------------
 // The datum enters pulled back to eta at the points of the signature (INTEGRATION = 1): E_eta = dxdeta^T E and
-// curl_eta = det(dxdeta) dxdeta^-1 curl E (dhpfaceE_opt.F90:249-259).  An edge projects the tangential component in L2; a face
+// curl_eta = det(dxdeta) dxdeta^-1 curl E (dhpfaceE_opt.F90:269-279).  An edge projects the tangential component in L2; a face
 // minimises the normal component of curl_eta (E_eta - known edges - sum dof_j E_j) subject to orthogonality of the tangential
-// residual to the surface gradients of the face's H1 bubbles: the saddle-point system [C B; B^T 0] of :353-375, solved by LU with
-// partial pivoting like the reference's DGETRF (:398).
+// residual to the surface gradients of the face's H1 bubbles: the saddle-point system [C B; B^T 0] of :395-414, solved by LU with
+// partial pivoting like the reference's DGETRF (:439).
 struct PbiEArgs {
   const double *wa, *tan, *grad, *tabE;
   const PbiNode *nodes;
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(SMALL ? 64 : 256, SMALL ? 6 : 2) pbi_hcurl_ker
       dir[0] /= bj; dir[1] /= bj; dir[2] /= bj;
       const double sw = sqrt(A.wa[gl] * bj);
       // master -> eta: value u = Ji^T E^ (u_i = sum_a E^_a Ji[a + 3i]), curl cu = J C^ / det.  Residual rows one component at a time with
-      // register accumulators (the edges' contributions removed, dhpfaceE_opt.F90:275-293); the table entries are re-read from L1
+      // register accumulators (the edges' contributions removed, dhpfaceE_opt.F90:295-310); the table entries are re-read from L1
       for (int c = sl; c < nc; c += nsl) {
         const long long fo = (long long)gl * 3 * nc + c;
         double v0 = fv[fo], v1 = fv[fo + nc], v2 = fv[fo + 2 * nc], c0r = 0.0, c1r = 0.0, c2r = 0.0;
@@ -631,19 +631,19 @@ __global__ void __launch_bounds__(SMALL ? 64 : 256, SMALL ? 6 : 2) pbi_hcurl_ker
         const int k = nd.t0 + j;
         const double e0 = A.tabE[(long long)k * A.npts + gl], e1 = A.tabE[ES + (long long)k * A.npts + gl], e2 = A.tabE[2 * ES + (long long)k * A.npts + gl];
         double v[3] = {e0 * Ji[0] + e1 * Ji[1] + e2 * Ji[2], e0 * Ji[3] + e1 * Ji[4] + e2 * Ji[5], e0 * Ji[6] + e1 * Ji[7] + e2 * Ji[8]};
-        if (hdiv) { v[0] = (J[0] * e0 + J[3] * e1 + J[6] * e2) / det; v[1] = (J[1] * e0 + J[4] * e1 + J[7] * e2) / det; v[2] = (J[2] * e0 + J[5] * e1 + J[8] * e2) / det; }   // dhpfaceV_opt.F90:223-225
+        if (hdiv) { v[0] = (J[0] * e0 + J[3] * e1 + J[6] * e2) / det; v[1] = (J[1] * e0 + J[4] * e1 + J[7] * e2) / det; v[2] = (J[2] * e0 + J[5] * e1 + J[8] * e2) / det; }   // dhpfaceV_opt.F90:251-253
         const double pr = v[0] * dir[0] + v[1] * dir[1] + v[2] * dir[2];
-        if (!face) { v[0] = pr * dir[0]; v[1] = pr * dir[1]; v[2] = pr * dir[2]; }            // dhpedgeE.F90:218-219, dhpfaceV_opt.F90:226-227
-        else { v[0] -= pr * dir[0]; v[1] -= pr * dir[1]; v[2] -= pr * dir[2]; }                 // dhpfaceE_opt.F90:313-314
+        if (!face) { v[0] = pr * dir[0]; v[1] = pr * dir[1]; v[2] = pr * dir[2]; }            // dhpedgeE.F90:223-224, dhpfaceV_opt.F90:256-257
+        else { v[0] -= pr * dir[0]; v[1] -= pr * dir[1]; v[2] -= pr * dir[2]; }                 // dhpfaceE_opt.F90:337-338
         for (int i = 0; i < 3; i++) D[(long long)(rE + j) * K3 + 3 * l + i] = v[i] * sw;
         if (face) {
           const double c0 = A.tabE[3 * ES + (long long)k * A.npts + gl], c1 = A.tabE[4 * ES + (long long)k * A.npts + gl], c2 = A.tabE[5 * ES + (long long)k * A.npts + gl];
           const double cv[3] = {(J[0] * c0 + J[3] * c1 + J[6] * c2) / det, (J[1] * c0 + J[4] * c1 + J[7] * c2) / det, (J[2] * c0 + J[5] * c1 + J[8] * c2) / det};
           const double pc = cv[0] * dir[0] + cv[1] * dir[1] + cv[2] * dir[2];
-          for (int i = 0; i < 3; i++) D[(long long)j * K3 + 3 * l + i] = pc * dir[i] * sw;     // :315-316
+          for (int i = 0; i < 3; i++) D[(long long)j * K3 + 3 * l + i] = pc * dir[i] * sw;     // :341-342
         }
       }
-      for (int j = sl; j < nHb; j += nsl) {   // surface gradients of the face's H1 bubbles (:329-347)
+      for (int j = sl; j < nHb; j += nsl) {   // surface gradients of the face's H1 bubbles (:358-372)
         const int k = nd.th0 + j;
         const double g0 = A.grad[(long long)k * A.npts + gl], g1 = A.grad[HS + (long long)k * A.npts + gl], g2 = A.grad[2 * HS + (long long)k * A.npts + gl];
         double dv[3] = {g0 * Ji[0] + g1 * Ji[1] + g2 * Ji[2], g0 * Ji[3] + g1 * Ji[4] + g2 * Ji[5], g0 * Ji[6] + g1 * Ji[7] + g2 * Ji[8]};
@@ -661,10 +661,10 @@ __global__ void __launch_bounds__(SMALL ? 64 : 256, SMALL ? 6 : 2) pbi_hcurl_ker
       product(0, nE, 0, nE, 0, 0);             // mass matrix of the tangential (normal) component
       product(rRv, nc, 0, nE, nt, 0);
     } else {
-      product(0, nE, 0, nE, 0, 0);             // curl-curl (DSYRK, :353)
+      product(0, nE, 0, nE, 0, 0);             // curl-curl (DSYRK, :395)
       product(rRc, nc, 0, nE, nt, 0);
       if (nHb > 0) {
-        product(rG, nHb, rE, nE, nE, 0);       // B^T (DGEMM, :356)
+        product(rG, nHb, rE, nE, nE, 0);       // B^T (DGEMM, :399)
         product(rRv, nc, rG, nHb, nt, nE);
         __syncthreads();
         for (int q = tid; q < nHb * nE; q += blockDim.x) { const int j = q / nE, i = q % nE; W[(long long)i * nt + nE + j] = W[(long long)(nE + j) * nt + i]; }

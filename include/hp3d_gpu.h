@@ -230,8 +230,8 @@ void hp3d_gpu_host_free(void *p);
 
 /* ---- H1 projection-based interpolation (interpolation half): geometry dofs and H1 Dirichlet dofs.
  * Replaces, for all elements of a subdomain at once, the node-by-node calls of
- *   update_gdof  (src/hpinterp/update_gdof.F90:88-200,409-435): hpvert.F90:19, hpedge.F90:27, hpface_opt.F90:27, hpmdle_opt.F90:23
- *   update_Ddof  (src/hpinterp/update_Ddof.F90):                 dhpvert.F90:26, edge/dhpedgeH.F90:32, face/dhpfaceH_opt.F90:32
+ *   update_gdof  (src/hpinterp/update_gdof.F90:88-200,409-435): hpvert.F90:22, hpedge.F90:23, hpface_opt.F90:24, hpmdle_opt.F90:23
+ *   update_Ddof  (src/hpinterp/update_Ddof.F90):                 dhpvert.F90:19, edge/dhpedgeH.F90:25, face/dhpfaceH_opt.F90:27
  * The interpolated function g has `ncomp` REAL components (the GMP map x(eta): 3; a complex Dirichlet datum: re/im interleaved,
  * 2 NREQNH) and is projected in the reference coordinates eta of the GMP block; eta(xi) is the multilinear map through
  *   etav   (3, 8) per element   reference coordinates of the element's vertices (refel's xsub; a prism uses the first 6).
@@ -247,7 +247,7 @@ void hp3d_gpu_host_free(void *p);
  * hp3d_gpu_pbi_h1_batch:
  *   fvert   (ncomp, 8) per element         g at the vertices (hpvert / dhpvert)
  *   fgrad   (ncomp, 3, npts) per element   dg_c/deta_i at the points, component fastest (dxdeta(1:3,1:3) of `hexa/prism(No,eta,..)`;
- *           zdvalH * dxdeta for Dirichlet data, dhpfaceH_opt.F90:206-212), stride fgrad_ld doubles
+ *           zdvalH * dxdeta for Dirichlet data, dhpfaceH_opt.F90:217-224), stride fgrad_ld doubles
  *   dof     (ncomp, nrdofH) per element, component fastest, reference dof order, stride dof_ld; IN: the dofs of the nodes that
  *           are not selected (they enter the projections of the higher-dimensional nodes), OUT: the selected nodes' dofs
  *   info    per element: 0, -1 (Jacobian of eta(xi) not positive), i > 0 (stiffness of node i not positive definite) */
@@ -257,12 +257,12 @@ int hp3d_gpu_pbi_h1_batch(int nel, const int *etype, const int *norder, const in
                           int maxp, const double *etav, int ncomp, const double *fvert, const double *fgrad, long long fgrad_ld,
                           const unsigned *mask, double *dof, long long dof_ld, int *info);
 
-/* H(curl) Dirichlet dofs of update_Ddof: edge/dhpedgeE.F90:33 and face/dhpfaceE_opt.F90:33 for all elements at once (INTEGRATION = 1;
+/* H(curl) Dirichlet dofs of update_Ddof: edge/dhpedgeE.F90:24 and face/dhpfaceE_opt.F90:26 for all elements at once (INTEGRATION = 1;
  * middle nodes carry no Dirichlet data).  Same node numbering / mask bits as above (vertex and middle bits are ignored).
  *   hp3d_gpu_pbi_hcurl_points: points of the edge and face nodes that own H(curl) dofs (an order-1 edge has one), nrdofE = number of
  *           edge + face dofs of the element (they come first in the reference's H(curl) dof order), nodes (4, 27) as above
- *   fval    (ncomp, 3, npts) per element: the datum pulled back to eta, E_eta(i) = sum_j E_j dxdeta(j,i)        (dhpfaceE_opt.F90:249-255)
- *   fcurl   (ncomp, 3, npts) per element: curl_eta(i) = det(dxdeta) sum_j dxdeta^-1(i,j) (curl E)_j             (:256-258); edges ignore it
+ *   fval    (ncomp, 3, npts) per element: the datum pulled back to eta, E_eta(i) = sum_j E_j dxdeta(j,i)        (dhpfaceE_opt.F90:273-274)
+ *   fcurl   (ncomp, 3, npts) per element: curl_eta(i) = det(dxdeta) sum_j dxdeta^-1(i,j) (curl E)_j             (:275-277); edges ignore it
  *           both component fastest, stride f_ld doubles; ncomp REAL components (complex data: re/im interleaved)
  *   dof     (ncomp, nrdofE) per element, stride dof_ld; IN: dofs of unselected edges, OUT: selected nodes' dofs
  *   info    per element: 0, -1 (Jacobian not positive), i > 0 (singular system at node i) */
@@ -272,9 +272,9 @@ int hp3d_gpu_pbi_hcurl_batch(int nel, const int *etype, const int *norder, const
                              const double *etav, int ncomp, const double *fval, const double *fcurl, long long f_ld, const unsigned *mask,
                              double *dof, long long dof_ld, int *info);
 
-/* H(div) Dirichlet dofs of update_Ddof: face/dhpfaceV_opt.F90:33 (INTEGRATION = 1): L2 projection of the normal component on every
+/* H(div) Dirichlet dofs of update_Ddof: face/dhpfaceV_opt.F90:26 (INTEGRATION = 1): L2 projection of the normal component on every
  * selected face (bits of the face nodes in mask; the others are ignored).
- *   fval    (ncomp, 3, npts) per element: V_eta(i) = det(dxdeta) sum_j dxdeta^-1(i,j) V_j at hp3d_gpu_pbi_hdiv_points  (:211-217)
+ *   fval    (ncomp, 3, npts) per element: V_eta(i) = det(dxdeta) sum_j dxdeta^-1(i,j) V_j at hp3d_gpu_pbi_hdiv_points  (:231-238)
  *   dof     (ncomp, nrdofV) per element, nrdofV = number of face dofs (they come first in the reference's H(div) dof order) */
 int hp3d_gpu_pbi_hdiv_points(int nel, const int *etype, const int *norder, const int *norient_edge, const int *norient_face, int maxp,
                              double *xi, long long xi_ld, int *npts, int *nrdofV, int *nodes);

@@ -262,7 +262,7 @@ int orc_pbi_batch_sample(int nel, const int *etype, const int *norder, const int
 int orc_pbi_element(int et, const int *norder, const int *norie, const int *norif, const double *etav, int ncomp, int integration,
                     int maxp, unsigned mask, orc_pbi_fn f, void *ctx, double *dof);
 
-/* H(curl) Dirichlet dofs: edge/dhpedgeE.F90:33, face/dhpfaceE_opt.F90:33 (INTEGRATION = 1).  f(eta, E[ncomp*3], curlE[ncomp*3],
+/* H(curl) Dirichlet dofs: edge/dhpedgeE.F90:24, face/dhpfaceE_opt.F90:26 (INTEGRATION = 1).  f(eta, E[ncomp*3], curlE[ncomp*3],
  * dxdeta[9], ctx) returns the datum in physical components (E[c + ncomp*j]) and the GMP Jacobian; nodes = edges, then faces. */
 typedef void (*orc_pbi_fnE)(const double *eta, double *E, double *curlE, double *dxdeta, void *ctx);
 void orc_pbi_offsets_E(int et, const int *norder, int *off);
@@ -271,7 +271,7 @@ int orc_pbi_hcurl_node(int et, const int *norder, const int *norie, const int *n
 int orc_pbi_hcurl_element(int et, const int *norder, const int *norie, const int *norif, const double *etav, int ncomp, int maxp, unsigned mask,
                           orc_pbi_fnE f, void *ctx, double *dofE);
 
-/* H(div) Dirichlet dofs: face/dhpfaceV_opt.F90:33 (callback as for H(curl), the curl output is ignored); nodes = faces */
+/* H(div) Dirichlet dofs: face/dhpfaceV_opt.F90:26 (callback as for H(curl), the curl output is ignored); nodes = faces */
 void orc_pbi_offsets_V(int et, const int *norder, int *off);
 int orc_pbi_hdiv_node(int et, const int *norder, const int *norie, const int *norif, const double *etav, int ncomp, int maxp, int iface0,
                       orc_pbi_fnE f, void *ctx, double *dofV);

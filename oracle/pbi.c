@@ -1,11 +1,11 @@
 /*
  * pbi.c -- CPU restatement ("oracle") of hp3D's H1 projection-based interpolation (interpolation half):
- *   geometry dofs (update_gdof)         trunk/src/hpinterp/hpvert.F90:19, hpedge.F90:27, hpface_opt.F90:27, hpmdle_opt.F90:23
- *   H1 Dirichlet dofs (update_Ddof)     trunk/src/hpinterp/dhpvert.F90:26, edge/dhpedgeH.F90:32, face/dhpfaceH_opt.F90:32
+ *   geometry dofs (update_gdof)         trunk/src/hpinterp/hpvert.F90:22, hpedge.F90:23, hpface_opt.F90:24, hpmdle_opt.F90:23
+ *   H1 Dirichlet dofs (update_Ddof)     trunk/src/hpinterp/dhpvert.F90:19, edge/dhpedgeH.F90:25, face/dhpfaceH_opt.F90:27
  * The two families are the same algorithm: the interpolated function g (the GMP map x(eta), 3 components, or the
  * Dirichlet datum u(x(eta)), NREQNH components) is given by a callback returning its value and its gradient with respect
- * to the REFERENCE coordinates eta of the GMP block (dxdeta, resp. zdvalH * dxdeta, dhpfaceH_opt.F90:206-212); the
- * projections are done in eta (hpmdle_opt.F90:5-6), eta(xi) being the trilinear / linear-prism map through the element's
+ * to the REFERENCE coordinates eta of the GMP block (dxdeta, resp. zdvalH * dxdeta, dhpfaceH_opt.F90:217-224); the
+ * projections are done in eta (hpmdle_opt.F90:6-7), eta(xi) being the trilinear / linear-prism map through the element's
  * vertex reference coordinates Etav (refgeom3D, trunk/src/element/util/geom3D.F90:235-305).  The geometry routines
  * integrate with INTEGRATION = 0, the Dirichlet routines with INTEGRATION = 1 (dhpedgeH.F90:145, dhpfaceH_opt.F90:173).
  * TEST INFRASTRUCTURE ONLY (see hp3d_oracle.h).
@@ -69,7 +69,7 @@ int orc_pbi_node(int et, const int *norder, const int *norie, const int *norif, 
   orc_pbi_offsets(et, norder, off);
   const int n = off[node + 1] - off[node], t0 = off[node];
   double *val = malloc(sizeof(double) * ncomp), *dval = malloc(sizeof(double) * 3 * ncomp);
-  if (node < nrv) { /* hpvert.F90:19-45, dhpvert.F90:60-75 */
+  if (node < nrv) { /* hpvert.F90:22-58, dhpvert.F90:73-111 */
     f(etav + 3 * node, val, dval, ctx);
     for (int c = 0; c < ncomp; c++) dof[c + ncomp * t0] = val[c];
     free(val); free(dval);
@@ -84,15 +84,15 @@ int orc_pbi_node(int et, const int *norder, const int *norie, const int *norif, 
   double *atest = NULL;
   const int kind = node < nrv + nre ? 1 : (node < nrv + nre + nrf ? 2 : 3);
   int nknown; /* dofs of the lower-dimensional nodes that are subtracted */
-  if (kind == 1) { /* hpedge.F90:111-117 */
+  if (kind == 1) { /* hpedge.F90:113-117 */
     const int ie = node - nrv + 1;
     orc_initiate_order(et, nord1);
     nord1[ie - 1] = norder[ie - 1];
-    int na = norder[ie - 1] + integration; if (na > maxp) na = maxp;   /* set_1D_int.F90:40-43 */
+    int na = norder[ie - 1] + integration; if (na > maxp) na = maxp;   /* set_1D_int.F90:41-43 */
     nint = na + 1;
     orc_gauss1(nint, pts, wts);
     nknown = nrv;
-  } else if (kind == 2) { /* hpface_opt.F90:126-146 */
+  } else if (kind == 2) { /* hpface_opt.F90:129-146 */
     const int jf = node - nrv - nre + 1;
     int nordf[5];
     orc_initiate_order(et, nord1);
@@ -101,7 +101,7 @@ int orc_pbi_node(int et, const int *norder, const int *norie, const int *norif, 
     orc_face_order(et, jf, norder, nordf);
     nint = orc_set_2D_int(orc_face_is_tri(et, jf), nordf, 0, integration, maxp, pts, wts);
     nknown = off[nrv + nre];
-  } else { /* hpmdle_opt.F90:117-121 */
+  } else { /* hpmdle_opt.F90:119 */
     for (int i = 0; i < nre + nrf + 1; i++) nord1[i] = norder[i];
     nint = orc_set_3D_int(et, norder, zero6, integration, maxp, pts, wts);
     nknown = off[nrv + nre + nrf];
@@ -116,7 +116,7 @@ int orc_pbi_node(int et, const int *norder, const int *norie, const int *norif, 
     int nrdofH = orc_shape3DH(et, xi, nord1, norie, norif, shapH, gradH);
     refgeom3D(etav, shapH, gradH, nrv, eta, detadxi, dxideta, &rjac, &iflag);
     if (iflag != 0) info = -1;
-    if (kind == 1) { /* hpedge.F90:134-142 */
+    if (kind == 1) { /* hpedge.F90:140-146 */
       double bjac = 0;
       for (int c = 0; c < 3; c++) { rt[c] = detadxi[c] * dxidt[0] + detadxi[c + 3] * dxidt[1] + detadxi[c + 6] * dxidt[2]; bjac += rt[c] * rt[c]; }
       bjac = sqrt(bjac);
@@ -133,7 +133,7 @@ int orc_pbi_node(int et, const int *norder, const int *norie, const int *norif, 
       weight = wts[l] * bjac;
     } else weight = wts[l] * rjac;
     f(eta, val, dval, ctx); /* dval(c, i) = d g_c / d eta_i, c fastest */
-    /* remove the lower-dimensional nodes' contributions (hpedge.F90:160-172, hpface_opt.F90:181-193, hpmdle_opt.F90:150-162);
+    /* remove the lower-dimensional nodes' contributions (hpedge.F90:164-176, hpface_opt.F90:186-198, hpmdle_opt.F90:156-167);
      * in the reduced-order element the known functions keep their positions, the node's own functions come last */
     const int own0 = nrdofH - n;
     for (int k = 0; k < own0; k++) {
@@ -151,25 +151,25 @@ int orc_pbi_node(int et, const int *norder, const int *norie, const int *norif, 
       if (kind == 2) { for (int i = 0; i < 3; i++) prod += dv[i] * rn[i]; for (int i = 0; i < 3; i++) dv[i] -= prod * rn[i]; }
       for (int c = 0; c < ncomp; c++)
         bb[j + n * c] += (dval[c] * dv[0] + dval[c + ncomp] * dv[1] + dval[c + 2 * ncomp] * dv[2]) * weight;
-      if (kind == 1) { /* hpedge.F90:197-210: full gradient of the trial function against the projected test gradient */
+      if (kind == 1) { /* hpedge.F90:199-213: full gradient of the trial function against the projected test gradient */
         for (int i = 0; i < n; i++) {
           const int ki = own0 + i;
           double du[3];
           for (int m = 0; m < 3; m++) du[m] = gradH[3 * ki] * dxideta[3 * m] + gradH[1 + 3 * ki] * dxideta[1 + 3 * m] + gradH[2 + 3 * ki] * dxideta[2 + 3 * m];
           aa[j + n * i] += (dv[0] * du[0] + dv[1] * du[1] + dv[2] * du[2]) * weight;
         }
-      } else { /* hpface_opt.F90:212, hpmdle_opt.F90:181 */
+      } else { /* hpface_opt.F90:223, hpmdle_opt.F90:189 */
         const double sw = sqrt(weight);
         for (int i = 0; i < 3; i++) atest[j + (size_t)n * (3 * l + i)] = dv[i] * sw;
       }
     }
   }
-  if (kind == 1) { /* dgetrf + dlaswp + 2 x dtrsm, hpedge.F90:236-248 */
+  if (kind == 1) { /* dgetrf + dlaswp + 2 x dtrsm, hpedge.F90:240-258 */
     int *ipiv = malloc(sizeof(int) * n);
     if (orc_dgetrf(n, aa, n, ipiv) != 0) info = 1;
     else orc_dgetrs(n, ncomp, aa, n, ipiv, bb, n);
     free(ipiv);
-  } else { /* DSFRK + DPFTRF + DPFTRS (hpface_opt.F90:219-247): the RFP storage is a layout, the algebra is syrk + potrf + potrs */
+  } else { /* DSFRK + DPFTRF + DPFTRS (hpface_opt.F90:234-261): the RFP storage is a layout, the algebra is syrk + potrf + potrs */
     orc_dsyrk_u('N', n, 3 * nint, 1.0, atest, n, 0.0, aa, n);
     if (orc_dpotrf_u(n, aa, n) != 0) info = 1;
     else { orc_dtrsm_u('T', n, ncomp, aa, n, bb, n); orc_dtrsm_u('N', n, ncomp, aa, n, bb, n); }
@@ -216,9 +216,9 @@ int orc_pbi_batch_sample(int nel, const int *etype, const int *norder, const int
 }
 
 /* ------------------------------------------------------------------------------------------------------------------------
- * H(curl) Dirichlet dofs: edge/dhpedgeE.F90:33-391, face/dhpfaceE_opt.F90:33-549 (INTEGRATION = 1).
+ * H(curl) Dirichlet dofs: edge/dhpedgeE.F90:24-391, face/dhpfaceE_opt.F90:26-549 (INTEGRATION = 1).
  * f(eta, E[ncomp*3], curlE[ncomp*3], dxdeta[9], ctx): the datum in PHYSICAL components (E[c + ncomp*j] = E_c,j, what `dirichlet`
- * returns as zvalE and the curl formed from zdvalE, dhpfaceE_opt.F90:233-235) and the GMP Jacobian dxdeta(j,i) = dxdeta[j + 3i];
+ * returns as zvalE and the curl formed from zdvalE, dhpfaceE_opt.F90:249-251) and the GMP Jacobian dxdeta(j,i) = dxdeta[j + 3i];
  * the pullbacks to eta are done here as in the reference.  Nodes: 0..nre-1 edges, then faces.
  * dofE: (ncomp, nrdofE) component fastest, full-element numbering. */
 void orc_pbi_offsets_E(int et, const int *norder, int *off /* nre+nrf entries + total of edges+faces */) {
@@ -249,12 +249,12 @@ int orc_pbi_hcurl_node(int et, const int *norder, const int *norie, const int *n
   int nord1[19], nint, info = 0;
   double *a_e = NULL, *a_ce = NULL, *a_gh = NULL;
   orc_initiate_order(et, nord1);
-  if (!isface) { /* dhpedgeE.F90:146-153 */
+  if (!isface) { /* dhpedgeE.F90:147-153 */
     nord1[node] = norder[node];
     int na = norder[node] + integration; if (na > maxp) na = maxp;
     nint = na + 1;
     orc_gauss1(nint, pts, wts);
-  } else { /* dhpfaceE_opt.F90:170-186 */
+  } else { /* dhpfaceE_opt.F90:168-186 */
     const int jf = node - nre + 1;
     int nordf[5];
     for (int i = 0; i < nre; i++) nord1[i] = norder[i];
@@ -290,15 +290,15 @@ int orc_pbi_hcurl_node(int et, const int *norder, const int *norie, const int *n
       weight = wts[l] * bjac;
     }
     f(eta, val, crl, dxdeta, ctx);
-    orc_geom(dxdeta, detadx, &rjx, &iflag);   /* dhpfaceE_opt.F90:221 */
-    /* pullbacks (dhpedgeE.F90:201-207, dhpfaceE_opt.F90:249-259): E_eta = dxdeta^T E, curl_eta = rjac * detadx * curl */
+    orc_geom(dxdeta, detadx, &rjx, &iflag);   /* dhpfaceE_opt.F90:238 */
+    /* pullbacks (dhpedgeE.F90:204-211, dhpfaceE_opt.F90:269-279): E_eta = dxdeta^T E, curl_eta = rjac * detadx * curl */
     for (int c = 0; c < ncomp; c++)
       for (int i = 0; i < 3; i++) {
         double a = 0, b = 0;
         for (int j = 0; j < 3; j++) { a += val[c + ncomp * j] * dxdeta[j + 3 * i]; b += crl[c + ncomp * j] * detadx[i + 3 * j] * rjx; }
         veta[c + ncomp * i] = a; ceta[c + ncomp * i] = b;
       }
-    if (!isface) { /* dhpedgeE.F90:211-243 ; the edge's functions sit after one function of each preceding edge */
+    if (!isface) { /* dhpedgeE.F90:214-243 ; the edge's functions sit after one function of each preceding edge */
       for (int j = 0; j < nE; j++) {
         const int kj = node + j;
         double v[3], prod = 0;
@@ -315,7 +315,7 @@ int orc_pbi_hcurl_node(int et, const int *norder, const int *norie, const int *n
       }
       continue;
     }
-    /* face: remove the edges' contributions (dhpfaceE_opt.F90:275-293) */
+    /* face: remove the edges' contributions (dhpfaceE_opt.F90:295-310) */
     const int ownE = nrdofE - nE, ownH = nrdofH - nH;
     if (ownE != offE[nre]) info = -2;
     for (int k = 0; k < ownE; k++) {
@@ -328,7 +328,7 @@ int orc_pbi_hcurl_node(int et, const int *norder, const int *norie, const int *n
         for (int c = 0; c < ncomp; c++) { veta[c + ncomp * i] -= dofE[c + ncomp * k] * u[i]; ceta[c + ncomp * i] -= dofE[c + ncomp * k] * cu[i]; }
     }
     const double sw = sqrt(weight);
-    for (int j = 0; j < nE; j++) { /* :305-327 */
+    for (int j = 0; j < nE; j++) { /* :325-356 */
       const int kj = ownE + j;
       double v[3], cv[3], prod = 0;
       for (int i = 0; i < 3; i++) {
@@ -343,7 +343,7 @@ int orc_pbi_hcurl_node(int et, const int *norder, const int *norie, const int *n
       for (int c = 0; c < ncomp; c++) bb[j + nt * c] += (cv[0] * ceta[c] + cv[1] * ceta[c + ncomp] + cv[2] * ceta[c + 2 * ncomp]) * weight;
       for (int i = 0; i < 3; i++) { a_e[j + (size_t)nE * (3 * l + i)] = v[i] * sw; a_ce[j + (size_t)nE * (3 * l + i)] = cv[i] * sw; }
     }
-    for (int j = 0; j < nH; j++) { /* :329-347 */
+    for (int j = 0; j < nH; j++) { /* :358-372 */
       const int kj = ownH + j;
       double dv[3], prod = 0;
       for (int i = 0; i < 3; i++) dv[i] = gradH[3 * kj] * dxideta[3 * i] + gradH[1 + 3 * kj] * dxideta[1 + 3 * i] + gradH[2 + 3 * kj] * dxideta[2 + 3 * i];
@@ -353,7 +353,7 @@ int orc_pbi_hcurl_node(int et, const int *norder, const int *norie, const int *n
       for (int i = 0; i < 3; i++) a_gh[j + (size_t)nH * (3 * l + i)] = dv[i] * sw;
     }
   }
-  if (isface) { /* DSYRK + DGEMM + symmetric fill (:353-375): [curl-curl, E.grad ; (E.grad)^T, 0] */
+  if (isface) { /* DSYRK + DGEMM + symmetric fill (:395-414): [curl-curl, E.grad ; (E.grad)^T, 0] */
     orc_dsyrk_u('N', nE, 3 * nint, 1.0, a_ce, nE, 0.0, aa, nt);
     for (int j = 0; j < nE; j++) for (int i = j + 1; i < nE; i++) aa[i + nt * j] = aa[j + nt * i];
     if (nH > 0) {
@@ -361,7 +361,7 @@ int orc_pbi_hcurl_node(int et, const int *norder, const int *norie, const int *n
       for (int j = 0; j < nH; j++) for (int i = 0; i < nE; i++) aa[nE + j + nt * i] = aa[i + nt * (nE + j)];
     }
   }
-  { /* DGETRF + DLASWP + 2 x DTRSM (dhpedgeE.F90:268-290, dhpfaceE_opt.F90:398-425) */
+  { /* DGETRF + DLASWP + 2 x DTRSM (dhpedgeE.F90:279-309, dhpfaceE_opt.F90:439-458) */
     int *ipiv = malloc(sizeof(int) * nt);
     if (orc_dgetrf(nt, aa, nt, ipiv) != 0) info = info ? info : 1;
     else orc_dgetrs(nt, ncomp, aa, nt, ipiv, bb, nt);
@@ -388,9 +388,9 @@ int orc_pbi_hcurl_element(int et, const int *norder, const int *norie, const int
 }
 
 /* ------------------------------------------------------------------------------------------------------------------------
- * H(div) Dirichlet dofs: face/dhpfaceV_opt.F90:33-413 (INTEGRATION = 1): L2 projection of the normal component of the datum pulled
- * back to eta, V_eta = det(dxdeta) dxdeta^-1 V (:211-217), onto the face's H(div) functions mapped by the Piola transform of
- * eta(xi) (:223-228).  f as for H(curl) (the curl output is ignored).  Nodes: faces 0..nrf-1.  dofV: (ncomp, sum of face dofs). */
+ * H(div) Dirichlet dofs: face/dhpfaceV_opt.F90:26-413 (INTEGRATION = 1): L2 projection of the normal component of the datum pulled
+ * back to eta, V_eta = det(dxdeta) dxdeta^-1 V (:231-238), onto the face's H(div) functions mapped by the Piola transform of
+ * eta(xi) (:251-257).  f as for H(curl) (the curl output is ignored).  Nodes: faces 0..nrf-1.  dofV: (ncomp, sum of face dofs). */
 void orc_pbi_offsets_V(int et, const int *norder, int *off) {
   const int nre = orc_nedge(et), nrf = orc_nface(et);
   int n = 0, h, e, v, q;
@@ -411,7 +411,7 @@ int orc_pbi_hdiv_node(int et, const int *norder, const int *norie, const int *no
   double *val = malloc(sizeof(double) * 3 * ncomp), *crl = malloc(sizeof(double) * 3 * ncomp), *veta = malloc(sizeof(double) * 3 * ncomp);
   double *pts = malloc(sizeof(double) * 3 * 1000), *wts = malloc(sizeof(double) * 1000);
   int nord1[19], nordi[19], nordf[5], info = 0;
-  orc_initiate_order(et, nord1);                       /* :151-153 */
+  orc_initiate_order(et, nord1);                       /* :162-164 */
   memcpy(nordi, nord1, sizeof nord1);
   nordi[nre + jf - 1] = norder[nre + jf - 1];
   orc_face_order(et, jf, norder, nordf);
@@ -440,7 +440,7 @@ int orc_pbi_hdiv_node(int et, const int *norder, const int *norie, const int *no
         for (int j = 0; j < 3; j++) a += detadx[i + 3 * j] * val[c + ncomp * j] * rjx;
         veta[c + ncomp * i] = a;
       }
-    for (int j = 0; j < n; j++) { /* :219-236 ; one function of each preceding face comes first */
+    for (int j = 0; j < n; j++) { /* :247-266 ; one function of each preceding face comes first */
       const int kj = iface0 + j;
       double v[3], prod = 0;
       for (int i = 0; i < 3; i++) v[i] = (detadxi[i] * shapV[3 * kj] + detadxi[i + 3] * shapV[1 + 3 * kj] + detadxi[i + 6] * shapV[2 + 3 * kj]) / rjac;
@@ -450,7 +450,7 @@ int orc_pbi_hdiv_node(int et, const int *norder, const int *norie, const int *no
       for (int i = 0; i < 3; i++) atest[j + (size_t)n * (3 * l + i)] = v[i] * sw;
     }
   }
-  orc_dsyrk_u('N', n, 3 * nint, 1.0, atest, n, 0.0, aa, n);   /* DSFRK + DPFTRF + DPFTRS, :241-275 */
+  orc_dsyrk_u('N', n, 3 * nint, 1.0, atest, n, 0.0, aa, n);   /* DSFRK + DPFTRF + DPFTRS, :277-317 */
   if (orc_dpotrf_u(n, aa, n) != 0) info = info ? info : 1;
   else { orc_dtrsm_u('T', n, ncomp, aa, n, bb, n); orc_dtrsm_u('N', n, ncomp, aa, n, bb, n); }
   if (info == 0)

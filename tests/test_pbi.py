@@ -540,7 +540,7 @@ def test_gpu_table_cache_trim_keeps_results(oracle, gpu):
 # ------------------------------------------------------------------------------------------------- more host logic (CPU): MAXP cap, tables
 @pytest.mark.parametrize("et", [MDLB, MDLP])
 def test_points_respect_the_maxp_cap(oracle, gpulib, et):
-    """order + INTEGRATION is capped at MAXP (set_1D_int.F90:40-43 and its 2-D / 3-D twins): with MAXP = 4 an order-4 node keeps 5 points
+    """order + INTEGRATION is capped at MAXP (set_1D_int.F90:41-43 and its 2-D / 3-D twins): with MAXP = 4 an order-4 node keeps 5 points
     per direction under INTEGRATION = 1; the oracle visits the same points for all three families"""
     oracle.set_maxp(4)
     try:
