@@ -195,7 +195,7 @@ int orc_pbi_element(int et, const int *norder, const int *norie, const int *nori
   return 0;
 }
 
-/* a fixed smooth 3-component map for timing the restatement without a Python callback (bench of tools/bench_pbi.py) */
+/* a fixed smooth 3-component map for timing the restatement without a Python callback (bench of tests/bench_pbi.py) */
 void orc_pbi_sample_fn(const double *eta, double *val, double *dval, void *ctx) {
   const double x = eta[0], y = eta[1], z = eta[2];
   (void)ctx;

@@ -1,6 +1,7 @@
-"""Throughput of the batched H1 projection-based interpolation (hp3d_gpu_pbi_h1_batch) through the C ABI with host buffers,
+"""(Measurement script, not a test; it lives under tests/ because it times the oracle beside the device path.)
+Throughput of the batched H1 projection-based interpolation (hp3d_gpu_pbi_h1_batch) through the C ABI with host buffers,
 beside the oracle's OpenMP element loop on the host cores (update_gdof.F90:409-435 shape).  Prints one JSON line.
-usage: python tools/bench_pbi.py [p] [nel] [path of an alternative libhp3d_gpu.so]"""
+usage: python tests/bench_pbi.py [p] [nel] [path of an alternative libhp3d_gpu.so]"""
 import ctypes as C
 import json
 import os
