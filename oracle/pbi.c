@@ -13,7 +13,9 @@
  * Pins (tests/test_pbi_oracle.py): the reference's test-suite holds no numeric vectors for src/hpinterp; what
  * trunk/test/poly_pois.F90 asserts through update_gdof + update_Ddof is polynomial reproduction, pinned here directly:
  * a function of the element's polynomial space is reproduced exactly (dofs evaluated back through shape3DH), a trilinear
- * map has zero higher-order dofs, and neighbours sharing a face obtain identical dofs for the shared entities.
+ * map has zero higher-order dofs, and neighbours sharing a face obtain identical dofs for the shared entities.  Independently of the
+ * oracle's quadrature tables, assembly and solvers, the interpolants satisfy their variational definition (Galerkin orthogonality node by
+ * node in the H1 seminorm; for H(curl) faces both block rows of the saddle-point system) under numpy's own 12-point Gauss-Legendre rule.
  */
 #include "dense.h"
 #include "hp3d_oracle.h"

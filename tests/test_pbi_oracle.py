@@ -208,3 +208,120 @@ def test_raviart_thomas_normal_trace_reproduced(oracle):
             V, _, A = rt_poly(s[:8] @ etav)
             want = np.linalg.det(A) * np.linalg.solve(A, V[0])         # det(dxdeta) dxdeta^-1 V
             assert abs(u_eta[ax] - want[ax]) < 1e-12
+
+
+# ---- variational characterisation with an independent quadrature -----------------------------------------------------------------
+def test_h1_interpolant_satisfies_its_variational_definition(oracle):
+    """The PB interpolant is DEFINED by Galerkin orthogonality in the H1 seminorm, node by node: on every edge
+    int d_t(g - u_h) d_t(phi_j) = 0 for the edge's bubbles, on every face int grad_s(g - u_h).grad_s(phi_j) = 0 for the face's
+    bubbles, inside int grad(g - u_h).grad(phi_j) = 0 for the middle node's bubbles.  Checked for a polynomial g that is NOT in the
+    element's space (degree p+1 per variable, so the oracle's p+1-point rules are still exact) with numpy's own Gauss-Legendre rule
+    (12 points per direction) -- independent of the oracle's quadrature tables, system assembly and solvers."""
+    oracle.set_maxp(9)
+    rng = np.random.default_rng(12)
+    p = 3
+    no = synth.uniform_order(p)
+    noe = rng.integers(0, 2, 12).astype(np.int32); nof = rng.integers(0, 8, 6).astype(np.int32)
+    M = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    h = np.array([0.5, 0.4, 0.6]); o = np.array([0.1, 0.2, 0.0])
+    etav = o + M * h
+
+    def g(eta):
+        x, y, z = eta
+        return (np.array([x ** 4 * y * y * z + x * y ** 4 + z ** 4 * x * x]),
+                np.array([[4 * x ** 3 * y * y * z + y ** 4 + 2 * x * z ** 4, 2 * x ** 4 * y * z + 4 * x * y ** 3, x ** 4 * y * y + 4 * z ** 3 * x * x]]))
+    dof = oracle.pbi_element(no, noe, nof, etav, g, 1)[:, 0]
+    off = oracle.pbi_offsets(no)
+    t, w = np.polynomial.legendre.leggauss(12)
+    t = 0.5 * (t + 1.0); w = 0.5 * w
+
+    def resid(xi):   # grad_eta (g - u_h) and grad_eta of all shape functions at a master point
+        s, gr = oracle.shape3DH(xi, no, noe, nof)
+        gr = gr / h
+        return g(o + xi * h)[1][0] - dof @ gr, gr
+    worst = 0.0
+    EV = [(0, 1), (1, 2), (3, 2), (0, 3), (4, 5), (5, 6), (7, 6), (4, 7), (0, 4), (1, 5), (2, 6), (3, 7)]
+    for e, (a, b) in enumerate(EV):                                  # edges: tangential derivative
+        d = M[b] - M[a]; tau = d * h; L = np.linalg.norm(tau); tau = tau / L
+        for j in range(off[8 + e], off[8 + e + 1]):
+            r = sum(wi * L * (resid(M[a] + ti * d)[0] @ tau) * (resid(M[a] + ti * d)[1][j] @ tau) for ti, wi in zip(t, w))
+            worst = max(worst, abs(r))
+    FV = [(0, 1, 3), (4, 5, 7), (0, 1, 4), (1, 2, 5), (3, 2, 7), (0, 3, 4)]
+    for f, (a, b, c) in enumerate(FV):                               # faces: surface gradient
+        d1, d2 = M[b] - M[a], M[c] - M[a]
+        n = np.cross(d1 * h, d2 * h); area = np.linalg.norm(n); n = n / area
+        P = np.eye(3) - np.outer(n, n)
+        acc = np.zeros(off[20 + f + 1] - off[20 + f])
+        for t1, w1 in zip(t, w):
+            for t2, w2 in zip(t, w):
+                R, G = resid(M[a] + t1 * d1 + t2 * d2)
+                acc += w1 * w2 * area * (G[off[20 + f]:off[20 + f + 1]] @ (P @ R))
+        worst = max(worst, float(np.abs(acc).max()))
+    acc = np.zeros(off[27] - off[26])                                # middle node: full gradient
+    for t1, w1 in zip(t, w):
+        for t2, w2 in zip(t, w):
+            for t3, w3 in zip(t, w):
+                R, G = resid(np.array([t1, t2, t3]))
+                acc += w1 * w2 * w3 * np.prod(h) * (G[off[26]:off[27]] @ R)
+    worst = max(worst, float(np.abs(acc).max()))
+    assert worst < 1e-12
+    assert np.abs(dof[8:]).max() > 1e-3      # g is not in the span of the vertex functions: the test is not vacuous
+
+
+def test_hcurl_interpolant_satisfies_its_variational_definition(oracle):
+    """H(curl) Dirichlet interpolant, same idea: on an edge the tangential residual is L2-orthogonal to the edge's functions; on a
+    face the normal curl of the residual is orthogonal to the normal curls of the face's functions AND the tangential residual is
+    orthogonal to the surface gradients of the face's H1 bubbles (the two block rows of dhpfaceE_opt's saddle-point system; the
+    multiplier vanishes).  E is a polynomial of degree p+1 per variable (not in the space), numpy's Gauss-Legendre rule."""
+    oracle.set_maxp(9)
+    rng = np.random.default_rng(14)
+    p = 2
+    no = synth.uniform_order(p)
+    noe = rng.integers(0, 2, 12).astype(np.int32); nof = rng.integers(0, 8, 6).astype(np.int32)
+    M = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    h = np.array([0.5, 0.4, 0.6]); o = np.array([0.1, 0.2, 0.0])
+    etav = o + M * h
+
+    def E(eta):
+        x, y, z = eta
+        e = np.array([[x ** 3 * y + z ** 3, y ** 3 * z * x - x, z ** 3 + x * y * y * z]])
+        c = np.array([[2 * x * y * z - x * y ** 3, 3 * z * z - y * y * z, y ** 3 * z - 1.0 - x ** 3]])
+        return e, c, np.eye(3)
+    dof = oracle.pbi_hcurl_element(no, noe, nof, etav, E, 1)[:, 0]
+    offE = oracle.pbi_offsets_E(no); offH = oracle.pbi_offsets(no)
+    nEF = int(offE[-1])
+    t, w = np.polynomial.legendre.leggauss(12)
+    t = 0.5 * (t + 1.0); w = 0.5 * w
+    J = np.diag(h); detJ = float(np.prod(h))
+
+    def at(xi):
+        sE, cE = oracle.shape3DE(xi, no, noe, nof)
+        _, gH = oracle.shape3DH(xi, no, noe, nof)
+        u = sE[:nEF] / h              # J^-T E^ (J diagonal)
+        cu = cE[:nEF] * h / detJ      # J curl^ / det
+        e, c, _ = E(o + xi * h)
+        return e[0] - dof @ u, c[0] - dof @ cu, u, cu, gH / h
+    worst = 0.0
+    EV = [(0, 1), (1, 2), (3, 2), (0, 3), (4, 5), (5, 6), (7, 6), (4, 7), (0, 4), (1, 5), (2, 6), (3, 7)]
+    for e, (a, b) in enumerate(EV):
+        d = M[b] - M[a]; tau = d * h; L = np.linalg.norm(tau); tau = tau / L
+        acc = np.zeros(offE[e + 1] - offE[e])
+        for ti, wi in zip(t, w):
+            r, _, u, _, _ = at(M[a] + ti * d)
+            acc += wi * L * (r @ tau) * (u[offE[e]:offE[e + 1]] @ tau)
+        worst = max(worst, float(np.abs(acc).max()))
+    FV = [(0, 1, 3), (4, 5, 7), (0, 1, 4), (1, 2, 5), (3, 2, 7), (0, 3, 4)]
+    for f, (a, b, c3) in enumerate(FV):
+        d1, d2 = M[b] - M[a], M[c3] - M[a]
+        n = np.cross(d1 * h, d2 * h); area = np.linalg.norm(n); n = n / area
+        P = np.eye(3) - np.outer(n, n)
+        je = slice(offE[12 + f], offE[12 + f + 1]); jh = slice(offH[20 + f], offH[20 + f + 1])
+        acc_c = np.zeros(je.stop - je.start); acc_g = np.zeros(jh.stop - jh.start)
+        for t1, w1 in zip(t, w):
+            for t2, w2 in zip(t, w):
+                r, rc, u, cu, gH = at(M[a] + t1 * d1 + t2 * d2)
+                acc_c += w1 * w2 * area * (rc @ n) * (cu[je] @ n)
+                acc_g += w1 * w2 * area * (gH[jh] @ (P @ r))
+        worst = max(worst, float(np.abs(acc_c).max()), float(np.abs(acc_g).max()) if acc_g.size else 0.0)
+    assert worst < 1e-12
+    assert np.abs(dof).max() > 1e-3
