@@ -325,3 +325,42 @@ def test_hcurl_interpolant_satisfies_its_variational_definition(oracle):
         worst = max(worst, float(np.abs(acc_c).max()), float(np.abs(acc_g).max()) if acc_g.size else 0.0)
     assert worst < 1e-12
     assert np.abs(dof).max() > 1e-3
+
+
+def test_hdiv_interpolant_satisfies_its_variational_definition(oracle):
+    """H(div) Dirichlet interpolant: on every face the normal component of V - u_h is L2-orthogonal to the normal components of the
+    face's functions (dhpfaceV_opt); V of degree p per variable (one more than the face space holds), numpy's Gauss-Legendre rule."""
+    oracle.set_maxp(9)
+    rng = np.random.default_rng(15)
+    p = 2
+    no = synth.uniform_order(p)
+    noe = rng.integers(0, 2, 12).astype(np.int32); nof = rng.integers(0, 8, 6).astype(np.int32)
+    M = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    h = np.array([0.5, 0.4, 0.6]); o = np.array([0.1, 0.2, 0.0])
+    etav = o + M * h
+
+    def V(eta):
+        x, y, z = eta
+        return np.array([[x * y * y * z * z + 1.0, x * x * z * z - y, x * x * y * y + z * z]]), np.zeros((1, 3)), np.eye(3)
+    dof = oracle.pbi_hdiv_element(no, noe, nof, etav, V, 1)[:, 0]
+    offV = oracle.pbi_offsets_V(no)
+    nVF = int(offV[-1])
+    t, w = np.polynomial.legendre.leggauss(12)
+    t = 0.5 * (t + 1.0); w = 0.5 * w
+    detJ = float(np.prod(h))
+    worst = 0.0
+    FV = [(0, 1, 3), (4, 5, 7), (0, 1, 4), (1, 2, 5), (3, 2, 7), (0, 3, 4)]
+    for f, (a, b, c3) in enumerate(FV):
+        d1, d2 = M[b] - M[a], M[c3] - M[a]
+        n = np.cross(d1 * h, d2 * h); area = np.linalg.norm(n); n = n / area
+        jv = slice(offV[f], offV[f + 1])
+        acc = np.zeros(jv.stop - jv.start)
+        for t1, w1 in zip(t, w):
+            for t2, w2 in zip(t, w):
+                xi = M[a] + t1 * d1 + t2 * d2
+                sV, _ = oracle.shape3DV(xi, no, nof)
+                u = sV[:nVF] * h / detJ          # Piola: J V^ / det
+                acc += w1 * w2 * area * ((V(o + xi * h)[0][0] - dof @ u) @ n) * (u[jv] @ n)
+        worst = max(worst, float(np.abs(acc).max()))
+    assert worst < 1e-12
+    assert np.abs(dof).max() > 1e-3
