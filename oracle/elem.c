@@ -634,3 +634,140 @@ int orc_condensed_batch(int kind, int nel, const int *norder, const int *norie, 
   return orc_condensed_batch_t(kind, nel, NULL, norder, norie, norif, xnod, xnod_stride, prm, Aii, Bi, ASchur, BSchur, sAii,
                                sBi, sAS, sBS, info, nthreads);
 }
+
+/* ======================================================================= MAXWELL / ULTRAWEAK DPG, scalar-loop twin
+ * Restatement of problems/MAXWELL/ULTRAWEAK_DPG/elem/elem_maxwell.F90:25-660 -- the reference's own SECOND formulation of the
+ * element: per-point loops over test/trial functions that accumulate the load (:290-298), the field stiffness stiff_EQ_T
+ * (:303-326), the Hermitian Gram matrix entry by entry in 2x2 blocks (:330-410, packed upper storage there), the trace pairings
+ * stiff_EE_T (:445-560), then ZPPTRF / ZTPTRS / ZHERK (:588-624).  It shares NO dense kernel call pattern with the BLAS3
+ * version above (no sqrt(weight) factorisation, no real/imaginary splitting): the test-suite asserts that both give the same Gram
+ * matrix, enriched stiffness and element matrices for arbitrary complex permittivity tensors (SURVEY.md 7 step 0 iii). */
+int orc_elem_maxwell_uw_scalar_t(int et, const int norder[19], const int norie[12], const int norif[6], const double *xnod,
+                                 const orc_params *prm, zdouble *Aloc, zdouble *Bloc, zdouble *gram_out, zdouble *stiff_out) {
+  int nH, nE, nV, nQ, nHH, nEE, nVV, nQQ, bH, bE, bV, bQ, norderP[19], norderi[19];
+  int dp = prm->nord_add, nordP = orc_enriched_mid(et, norder[MIDX(et)], dp), maxpp = orc_get_maxp() + 1;
+  orc_compute_enriched_order(et, nordP, norderP);
+  orc_celndof(et, norder, &nH, &nE, &nV, &nQ);
+  orc_celndof(et, norderP, &nHH, &nEE, &nVV, &nQQ);
+  orc_ndof_nod_mid(et, norder[MIDX(et)], &bH, &bE, &bV, &bQ);
+  const int nEi = nE - bE, nTest = 2 * nEE, nTrial = 2 * nEi + 6 * nQ, ncol = nTrial + 1, jE = 2 * nEi;
+  /* norderi: the element's orders with the middle node forced to the lowest order (no interior functions; :176-189) */
+  memcpy(norderi, norder, sizeof(int) * 19);
+  norderi[MIDX(et)] = (et == ORC_MDLB) ? 111 : 11;
+  const double afac = (prm->test_norm == 2) ? 1.0 : prm->alpha_norm;
+  zdouble *gram = xmalloc(sizeof(zdouble) * nTest * nTest), *stiff = xmalloc(sizeof(zdouble) * nTest * ncol);
+  double *xiloc = xmalloc(sizeof(double) * 3 * 1000), *waloc = xmalloc(sizeof(double) * 1000);
+  double *shapH = xmalloc(sizeof(double) * nH), *gradH = xmalloc(sizeof(double) * 3 * nH), *shapQ = xmalloc(sizeof(double) * nQ);
+  double *shapEE = xmalloc(sizeof(double) * 3 * nEE), *curlEE = xmalloc(sizeof(double) * 3 * nEE);
+  double *shapE = xmalloc(sizeof(double) * 3 * nE), *curlE = xmalloc(sizeof(double) * 3 * nE);
+  double *shapF = xmalloc(sizeof(double) * 3 * nEE), *curlF = xmalloc(sizeof(double) * 3 * nEE), *shapFi = xmalloc(sizeof(double) * 3 * nE);
+  zdouble *epsTshapF = xmalloc(sizeof(zdouble) * 3 * nEE), *epscurlF = xmalloc(sizeof(zdouble) * 3 * nEE);
+  /* ---- element integrals */
+  const int nint = orc_set_3D_int(et, norder, norif, dp, maxpp, xiloc, waloc);
+  for (int l = 0; l < nint; l++) {
+    double x[3], J[9], Ji[9], rjac; int iflag;
+    orc_shape3DH(et, xiloc + 3 * l, norder, norie, norif, shapH, gradH);
+    orc_shape3DQ(et, xiloc + 3 * l, norder, shapQ);
+    orc_shape3EE(et, xiloc + 3 * l, nordP, shapEE, curlEE);
+    orc_geom3D(xnod, shapH, gradH, nH, x, J, Ji, &rjac, &iflag);
+    check_jac(iflag, rjac);
+    const double weight = rjac * waloc[l];
+    zdouble zJ[3], za[9];
+    maxwell_uw_source(prm, x, l, zJ);
+    for (int i = 0; i < 9; i++) za[i] = (I * prm->omega * prm->eps) * prm->eps_tensor[i];   /* za(i,j) at [i + 3j] */
+    const zdouble zc1 = I * prm->omega * prm->mu;
+    for (int k = 0; k < nEE; k++) {
+      pull_grad(shapEE + 3 * k, Ji, shapF + 3 * k);
+      push_curl(curlEE + 3 * k, J, rjac, curlF + 3 * k);
+      for (int c = 0; c < 3; c++) {   /* epsTshapF = za^H F ; epscurlF = za curl F */
+        zdouble a = 0, b = 0;
+        for (int d = 0; d < 3; d++) { a += conj(za[d + 3 * c]) * shapF[3 * k + d]; b += za[c + 3 * d] * curlF[3 * k + d]; }
+        epsTshapF[3 * k + c] = a; epscurlF[3 * k + c] = b;
+      }
+    }
+    for (int k1 = 0; k1 < nEE; k1++) {
+      const double *fldF = shapF + 3 * k1, *crlF = curlF + 3 * k1;
+      const zdouble *epsTfldF = epsTshapF + 3 * k1;
+      IDX(stiff, nTest, 2 * k1, nTrial) += (fldF[0] * zJ[0] + fldF[1] * zJ[1] + fldF[2] * zJ[2]) * weight;
+      for (int k2 = 0; k2 < nQ; k2++) {
+        const int m = jE + 6 * k2;
+        const double q = shapQ[k2] / rjac;
+        for (int c = 0; c < 3; c++) {
+          IDX(stiff, nTest, 2 * k1, m + c) -= q * conj(epsTfldF[c]) * weight;      /* -i w eps (E,F) */
+          IDX(stiff, nTest, 2 * k1, m + 3 + c) += q * crlF[c] * weight;            /* (H, curl F)    */
+          IDX(stiff, nTest, 2 * k1 + 1, m + c) += q * crlF[c] * weight;            /* (E, curl G)    */
+          IDX(stiff, nTest, 2 * k1 + 1, m + 3 + c) += zc1 * q * fldF[c] * weight;  /* i w mu (H,G)   */
+        }
+      }
+      for (int k2 = k1; k2 < nEE; k2++) {
+        const double *fldE = shapF + 3 * k2, *crlE = curlF + 3 * k2;
+        const zdouble *epsTfldE = epsTshapF + 3 * k2, *epscrlE = epscurlF + 3 * k2;
+        const double FF = fldF[0] * fldE[0] + fldF[1] * fldE[1] + fldF[2] * fldE[2];
+        const double CC = crlF[0] * crlE[0] + crlF[1] * crlE[1] + crlF[2] * crlE[2];
+        zdouble zaux = 0, zcux = 0;
+        if (prm->test_norm != 2) {
+          zaux = conj(epsTfldF[0]) * epsTfldE[0] + conj(epsTfldF[1]) * epsTfldE[1] + conj(epsTfldF[2]) * epsTfldE[2];
+          zcux = (creal(zc1) * creal(zc1) + cimag(zc1) * cimag(zc1)) * FF;
+        }
+        IDX(gram, nTest, 2 * k1, 2 * k2) += (zaux + afac * FF + CC) * weight;            /* G_11 */
+        IDX(gram, nTest, 2 * k1 + 1, 2 * k2 + 1) += (zcux + afac * FF + CC) * weight;    /* G_22 */
+        if (prm->test_norm != 1) continue;
+        zaux = -(fldF[0] * epscrlE[0] + fldF[1] * epscrlE[1] + fldF[2] * epscrlE[2]);
+        zcux = conj(zc1) * (crlF[0] * fldE[0] + crlF[1] * fldE[1] + crlF[2] * fldE[2]);
+        IDX(gram, nTest, 2 * k1, 2 * k2 + 1) += (zaux + zcux) * weight;                  /* G_12 */
+        if (k1 != k2) {
+          zaux = -(crlF[0] * epsTfldE[0] + crlF[1] * epsTfldE[1] + crlF[2] * epsTfldE[2]);
+          zcux = zc1 * (fldF[0] * crlE[0] + fldF[1] * crlE[1] + fldF[2] * crlE[2]);
+          IDX(gram, nTest, 2 * k1 + 1, 2 * k2) += (zaux + zcux) * weight;                /* G_21 */
+        }
+      }
+    }
+  }
+  /* ---- boundary integrals: every face, all interface functions at once (shape3DE with the middle order forced to 1) */
+  for (int ifc = 1; ifc <= orc_nface(et); ifc++) {
+    int nordf[5];
+    double tloc[200], wtloc[100];
+    const int nsign = orc_nsign_param(et, ifc);
+    orc_face_order(et, ifc, norder, nordf);
+    const int nintf = orc_set_2D_int(orc_face_is_tri(et, ifc), nordf, norif[ifc - 1], dp, maxpp, tloc, wtloc);
+    for (int l = 0; l < nintf; l++) {
+      double xi[3], dxidt[6], x[3], J[9], Ji[9], rjac, dxdt[6], rn[3], bjac;
+      orc_face_param(et, ifc, tloc + 2 * l, xi, dxidt);
+      orc_shape3EE(et, xi, nordP, shapEE, curlEE);
+      orc_shape3DH(et, xi, norder, norie, norif, shapH, gradH);
+      const int nEi_l = orc_shape3DE(et, xi, norderi, norie, norif, shapE, curlE);
+      if (nEi_l != nEi) { fprintf(stderr, "oracle scalar twin: inconsistent NrdofEi %d vs %d\n", nEi_l, nEi); exit(1); }
+      orc_bgeom3D(xnod, shapH, gradH, nH, dxidt, nsign, x, J, Ji, &rjac, dxdt, rn, &bjac);
+      const double weight = bjac * wtloc[l];
+      for (int k = 0; k < nEE; k++) pull_grad(shapEE + 3 * k, Ji, shapF + 3 * k);
+      for (int k = 0; k < nEi; k++) pull_grad(shapE + 3 * k, Ji, shapFi + 3 * k);
+      for (int k1 = 0; k1 < nEE; k1++) {
+        const double *E1 = shapF + 3 * k1;
+        for (int k2 = 0; k2 < nEi; k2++) {
+          const double *E2 = shapFi + 3 * k2;
+          const double rxE[3] = {rn[1] * E2[2] - rn[2] * E2[1], rn[2] * E2[0] - rn[0] * E2[2], rn[0] * E2[1] - rn[1] * E2[0]};
+          const double v = (E1[0] * rxE[0] + E1[1] * rxE[1] + E1[2] * rxE[2]) * weight;
+          IDX(stiff, nTest, 2 * k1, 2 * k2 + 1) += v;    /* <n x H^, F> */
+          IDX(stiff, nTest, 2 * k1 + 1, 2 * k2) += v;    /* <n x E^, G> */
+        }
+      }
+    }
+  }
+  if (gram_out) memcpy(gram_out, gram, sizeof(zdouble) * nTest * nTest);
+  if (stiff_out) memcpy(stiff_out, stiff, sizeof(zdouble) * nTest * ncol);
+  /* ---- G = U^H U, B~ = U^-H [B|l], [A|b] = B~^H B~ (ZPPTRF / ZTPTRS / ZHERK on packed storage in the reference) */
+  int info = orc_zpotrf_u(nTest, gram, nTest);
+  if (!info) {
+    orc_ztrsm_u('C', nTest, ncol, gram, nTest, stiff, nTest);
+    zdouble *zal = xmalloc(sizeof(zdouble) * ncol * ncol);
+    orc_zherk_u('C', ncol, nTest, 1.0, stiff, nTest, 0.0, zal, ncol);
+    for (int j = 0; j < nTrial; j++) {
+      for (int i = 0; i < nTrial; i++) IDX(Aloc, nTrial, i, j) = (i <= j) ? IDX(zal, ncol, i, j) : conj(IDX(zal, ncol, j, i));
+      Bloc[j] = IDX(zal, ncol, j, nTrial);
+    }
+    free(zal);
+  }
+  free(gram); free(stiff); free(xiloc); free(waloc); free(shapH); free(gradH); free(shapQ); free(shapEE); free(curlEE); free(shapE);
+  free(curlE); free(shapF); free(curlF); free(shapFi); free(epsTshapF); free(epscurlF);
+  return info;
+}

@@ -207,6 +207,9 @@ int orc_elem_maxwell_galerkin_t(int et, const int norder[19], const int norie[12
 int orc_elem_maxwell_uw_dpg_t(int et, const int norder[19], const int norie[12], const int norif[6], const double *xnod,
                               const orc_params *prm, zdouble *Aloc, zdouble *Bloc, int *nEi, int *nQ, zdouble *gram_out,
                               zdouble *stiff_out);
+/* the reference's scalar-loop twin of the same element (elem_maxwell.F90): independent second formulation, see elem.c */
+int orc_elem_maxwell_uw_scalar_t(int et, const int norder[19], const int norie[12], const int norif[6], const double *xnod,
+                                 const orc_params *prm, zdouble *Aloc, zdouble *Bloc, zdouble *gram_out, zdouble *stiff_out);
 int orc_stc_partition_t(int et, int problem_kind, const int norder[19], int *perm, int *ni, int *nb);
 int orc_condensed_element_t(int et, int problem_kind, const int norder[19], const int norie[12], const int norif[6],
                             const double *xnod, const orc_params *prm, void *Aii, void *Bi, void *ASchur, void *BSchur,

@@ -251,6 +251,24 @@ def elem(kind, norder, norie, norif, xnod, prm, want_dpg=False, etype=MDLB):
     return A, b
 
 
+def elem_uw_scalar(norder, norie, norif, xnod, prm, etype=MDLB):
+    """The reference's scalar-loop twin of the ultraweak Maxwell element (elem_maxwell.F90, oracle/elem.c:
+    orc_elem_maxwell_uw_scalar_t) -> (A, b, Gram [upper triangle filled], enriched stiffness [B | l])."""
+    norder, norie, norif = _pad(norder, 19), _pad(norie, 12), _pad(norif, 6)
+    xnod = np.ascontiguousarray(xnod, dtype=np.float64)
+    et = int(etype)
+    nH, nE, nV, nQ = celndof(norder, et)
+    bE = ndof_mdl(int(norder[mid_index(et)]), et)[1]
+    n = 2 * (nE - bE) + 6 * nQ
+    nEE = celndof(enriched_order(int(norder[mid_index(et)]) + prm.nord_add * (11 if et == MDLP else 111), et), et)[1]
+    A = np.zeros((n, n), order="F", dtype=np.complex128); b = np.zeros(n, dtype=np.complex128)
+    gram = np.zeros((2 * nEE, 2 * nEE), order="F", dtype=np.complex128)
+    stiff = np.zeros((2 * nEE, n + 1), order="F", dtype=np.complex128)
+    r = lib().orc_elem_maxwell_uw_scalar_t(et, _i(norder), _i(norie), _i(norif), _d(xnod), C.byref(prm), _d(A), _d(b), _d(gram), _d(stiff))
+    assert r == 0, r
+    return A, b, gram, stiff
+
+
 def enriched_order(nordP, etype=MDLB):
     no = np.zeros(19, dtype=np.int32)
     lib().orc_compute_enriched_order(int(etype), int(nordP), _i(no))
