@@ -241,4 +241,14 @@ __global__ void __launch_bounds__(256) dpg_residual_rs_kernel(DenseDims d, const
   if (tid == 0) { double s = 0.0; for (int w = 0; w < nw; w++) s += red[w]; res[e] = s; }
 }
 
+// opt-in of the residual kernels' dynamic shared memory (v: 2 x M doubles; M = 3328 at p = 7 ultraweak Maxwell exceeds the 48 KB default)
+constexpr int RESID_SMEM_MAX = 160 * 1024;
+static cudaError_t formats_configure() {
+  cudaError_t e = cudaFuncSetAttribute(dpg_residual_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RESID_SMEM_MAX);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(dpg_residual_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RESID_SMEM_MAX);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(dpg_residual_rs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RESID_SMEM_MAX);
+}
+
 }  // namespace hp3d

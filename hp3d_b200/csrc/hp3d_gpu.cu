@@ -198,6 +198,7 @@ int hp3d_gpu_init(int device) {
   if (prop.major < 10) return fail(HP3D_ENODEV, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
   CUDA_TRY(dense_configure<true>());
   CUDA_TRY(dense_configure<false>());
+  CUDA_TRY(formats_configure());
   CUDA_TRY(tp3_configure<4>()); CUDA_TRY(tp3_configure<6>()); CUDA_TRY(tp3_configure<8>()); CUDA_TRY(tp3_configure<10>());
   CUDA_TRY(tp2_configure<4>()); CUDA_TRY(tp2_configure<6>()); CUDA_TRY(tp2_configure<8>()); CUDA_TRY(tp2_configure<10>());
   // (descending stream priorities per lane were tried to stagger the chunk completions: 4 % slower device-resident and 8 %
@@ -431,6 +432,10 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
     const std::vector<int> &el = C.el;
     const ChunkShape &sh = C.shape;
     if (xnod_ld < 3 * sh.nH_max) { rc = fail(HP3D_EINVAL, "xnod_ld=%d < 3*nrdofH=%d", xnod_ld, 3 * sh.nH_max); break; }
+    if (mode == MODE_RESID && sizeof(double) * 2 * (size_t)sh.d.M() > (size_t)RESID_SMEM_MAX) {
+      rc = fail(HP3D_EINVAL, "element residual: %d padded trial dofs exceed the kernel's shared-memory vector (%d)", sh.d.M(), RESID_SMEM_MAX / 16);
+      break;
+    }
     // chunk plan: chunks of up to 64 elements round-robin over the lanes, with a ramped start and a tapered end (below)
     int want = (int)el.size();
     if (g_max_chunk > 0) want = std::min(want, g_max_chunk);

@@ -65,7 +65,7 @@ CASES = [
     (1, 1, 3), (1, 2, 3), (1, 3, 4), (1, 4, 2),
     (2, 1, 3), (2, 2, 3), (2, 3, 2), (2, 4, 2),
     (3, 1, 3), (3, 2, 3), (3, 3, 2), (3, 4, 2), (3, 5, 1),
-    (4, 1, 3), (4, 2, 3), (4, 3, 2),
+    (4, 1, 3), (4, 2, 3), (4, 3, 2), (4, 4, 2),
 ]
 
 
@@ -205,7 +205,7 @@ def test_full_size_p5_uw_maxwell(oracle, gpu):
         assert relerr(Aii, rA) < 1e-12, relerr(Aii, rA)
         assert relerr(Bi, rB) < 1e-12, relerr(Bi, rB)
         assert relerr(Aii, Aii.conj().T) < 1e-14            # Hermitian (ZHERK + mirror, elem_opt.F90:862-869)
-        assert relerr(AS, rAS) < 1e-9 and relerr(BS, rBS) < 1e-9
+        assert relerr(AS, rAS) < 1e-9 and relerr(BS, rBS) < 1e-9   # forward error ~ cond(A_bb) eps; the 1e-12 residual check is test_schur_factor_residual_at_full_size
     eng.close()
 
 
