@@ -16,7 +16,7 @@ class Params(C.Structure):
     _fields_ = [("nord_add", C.c_int), ("maxp", C.c_int), ("test_norm", C.c_int), ("alpha_norm", C.c_double),
                 ("omega", C.c_double), ("eps", C.c_double), ("mu", C.c_double), ("sigma", C.c_double),
                 ("eps_tensor", C.c_double * 18), ("source", C.c_int), ("icomp_exact", C.c_int),
-                ("store_schur", C.c_int), ("real_reduction", C.c_int)]
+                ("store_schur", C.c_int), ("real_reduction", C.c_int), ("aii_packed", C.c_int)]
 
 
 # every symbol include/hp3d_gpu.h declares (tests check that the library exports all of them)
@@ -29,6 +29,8 @@ EXPORTS = [
     "hp3d_gpu_physics_default", "hp3d_gpu_celem_pack", "hp3d_gpu_celem_batch",
     "hp3d_gpu_elem_error_batch", "hp3d_gpu_error_points", "hp3d_gpu_chunk_plan_debug",
     "hp3d_gpu_pbi_points", "hp3d_gpu_pbi_h1_batch", "hp3d_gpu_pbi_hcurl_points", "hp3d_gpu_pbi_hcurl_batch", "hp3d_gpu_pbi_hdiv_points", "hp3d_gpu_pbi_hdiv_batch", "hp3d_gpu_pbi_cache_limit",
+    "hp3d_gpu_cloc_create", "hp3d_gpu_cloc_clear", "hp3d_gpu_cloc_destroy", "hp3d_gpu_cloc_stats", "hp3d_gpu_elem_batch_cloc",
+    "hp3d_gpu_celem_batch_cloc", "hp3d_gpu_cloc_bwd_batch", "hp3d_gpu_cloc_fetch", "hp3d_gpu_hermitian_unpack_batch",
 ]
 
 

@@ -186,7 +186,7 @@ class ElemEngine:
         ni = max((s[0] for s in sz.values()), default=0)
         nb = max((s[1] for s in sz.values()), default=0)
         if out is None:
-            out = dict(Aii=np.zeros((nel, ni * ni), self.dtype), Bi=np.zeros((nel, ni), self.dtype),
+            out = dict(Aii=np.zeros((nel, self.aii_len(ni)), self.dtype), Bi=np.zeros((nel, ni), self.dtype),
                        ASchur=np.zeros((nel, max(nb * ni, 1)), self.dtype), BSchur=np.zeros((nel, max(nb, 1)), self.dtype))
         Aii, Bi, AS, BS = out["Aii"], out["Bi"], out["ASchur"], out["BSchur"]
         nio = np.zeros(nel, np.int32); nbo = np.zeros(nel, np.int32); info = np.zeros(nel, np.int32)
@@ -202,6 +202,99 @@ class ElemEngine:
                                    _ptr(AS), int(np.prod(AS.shape[1:])), _ptr(BS), int(np.prod(BS.shape[1:])), _ptr(nio), _ptr(nbo), _ptr(info))
         _lib.check(rc)
         return dict(Aii=Aii, Bi=Bi, ASchur=AS, BSchur=BS, ni=nio, nb=nbo, info=info)
+
+    # ---- device-resident CLOC (STORE_STC = .true. with the factors kept in HBM; include/hp3d_gpu.h "Device-resident CLOC")
+    def cloc_create(self, limit_bytes=0):
+        h = self.L.hp3d_gpu_cloc_create(self.plan, C.c_longlong(int(limit_bytes)))
+        if h < 0:
+            _lib.check(h)
+        return h
+
+    def cloc_destroy(self, cloc):
+        _lib.check(self.L.hp3d_gpu_cloc_destroy(int(cloc)))
+
+    def cloc_clear(self, cloc):
+        _lib.check(self.L.hp3d_gpu_cloc_clear(int(cloc)))
+
+    def cloc_stats(self, cloc):
+        st = np.zeros(4, np.int64)
+        _lib.check(self.L.hp3d_gpu_cloc_stats(int(cloc), _ptr(st)))
+        return dict(resident=int(st[0]), spilled=int(st[1]), bytes=int(st[2]), limit=int(st[3]))
+
+    def aii_len(self, ni):
+        """scalars of one element's Aii block: ni^2, or ni (ni+1)/2 with aii_packed"""
+        return ni * (ni + 1) // 2 if self.prm.aii_packed else ni * ni
+
+    def elem_stc_batch_cloc(self, cloc, norder, norient_edge, norient_face, xnod, iel=None, source_qp=None, out=None, etype=None):
+        """elem + stc_fwd_wrapper with the Schur factors filed in the device-resident store `cloc` under iel[e] (default e):
+        only Aii (the packed lower triangle if the plan has aii_packed = 1) and Bi return.  dict(Aii, Bi, ni, nb, info)."""
+        norder, noe, nof, xnod, nel, et = self._descr(norder, norient_edge, norient_face, xnod, etype)
+        ni = max((self.sizes(norder[e], MDLB if et is None else int(et[e]))[0] for e in range(nel)), default=0) if out is None else 0
+        if out is None:
+            out = dict(Aii=np.zeros((nel, self.aii_len(ni)), self.dtype), Bi=np.zeros((nel, ni), self.dtype))
+        Aii, Bi = out["Aii"], out["Bi"]
+        iel = None if iel is None else np.ascontiguousarray(iel, dtype=np.int64)
+        nio = np.zeros(nel, np.int32); nbo = np.zeros(nel, np.int32); info = np.zeros(nel, np.int32)
+        src_ld = 0
+        if source_qp is not None:
+            source_qp = np.ascontiguousarray(source_qp)
+            src_ld = source_qp[0].size * (2 if np.iscomplexobj(source_qp) else 1)
+        f = self.L.hp3d_gpu_elem_batch_cloc
+        ll = C.c_longlong
+        f.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p, ll, C.c_void_p, ll, C.c_void_p, ll] + [C.c_void_p] * 3
+        _lib.check(f(self.plan, int(cloc), nel, _ptr(iel), _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(np.prod(xnod.shape[1:])),
+                     _ptr(source_qp), src_ld, _ptr(Aii), int(np.prod(Aii.shape[1:])), _ptr(Bi), int(np.prod(Bi.shape[1:])), _ptr(nio), _ptr(nbo), _ptr(info)))
+        return dict(Aii=Aii, Bi=Bi, ni=nio, nb=nbo, info=info)
+
+    def cloc_bwd_batch(self, cloc, xi, iel=None, nb_max=None):
+        """stc_bwd (stc.F90:661-677) on the device-resident factors: xb = BSchur - ASchur xi for the elements iel (default 0..nel-1).
+        xi (nel, ni_max).  Returns dict(xb (nel, nb_max), nb, info)."""
+        xi = np.ascontiguousarray(xi, dtype=self.dtype)
+        nel = xi.shape[0]
+        iel = None if iel is None else np.ascontiguousarray(iel, dtype=np.int64)
+        if nb_max is None:
+            nb_max = 0
+            for e in range(nel):
+                nb_max = max(nb_max, self.cloc_fetch(cloc, e if iel is None else int(iel[e]), sizes_only=True)[1])
+        xb = np.zeros((nel, max(nb_max, 1)), self.dtype)
+        nbo = np.zeros(nel, np.int32); info = np.zeros(nel, np.int32)
+        f = self.L.hp3d_gpu_cloc_bwd_batch
+        ll = C.c_longlong
+        f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, ll, C.c_void_p, ll, C.c_void_p, C.c_void_p]
+        _lib.check(f(int(cloc), nel, _ptr(iel), _ptr(xi), xi[0].size if nel else 0, _ptr(xb), xb[0].size if nel else 0, _ptr(nbo), _ptr(info)))
+        return dict(xb=xb, nb=nbo, info=info)
+
+    def cloc_fetch(self, cloc, iel, sizes_only=False):
+        """(ASchur (nb, ni) as a Fortran-ordered array, BSchur (nb,)) of one stored element, or None if it is spilled;
+        sizes_only: (ni, nb) of a resident element, (0, 0) of a spilled one."""
+        f = self.L.hp3d_gpu_cloc_fetch
+        f.argtypes = [C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        ni, nb = C.c_int(0), C.c_int(0)
+        rc = f(int(cloc), int(iel), None, None, C.byref(ni), C.byref(nb))
+        if rc < 0:
+            _lib.check(rc)
+        if sizes_only:
+            return (ni.value, nb.value)
+        if rc == 1:
+            return None
+        AS = np.zeros(max(ni.value * nb.value, 1), self.dtype); BS = np.zeros(max(nb.value, 1), self.dtype)
+        _lib.check(f(int(cloc), int(iel), _ptr(AS), _ptr(BS), None, None))
+        return AS[:ni.value * nb.value].reshape(ni.value, nb.value).T, BS[:nb.value]
+
+    def hermitian_unpack(self, AP, ni, out=None, threads=0):
+        """Full (nel, ni*ni) column-major Hermitian blocks from packed lower triangles (hp3d_gpu_hermitian_unpack_batch; host only).
+        ni: an int or an (nel,) array of per-element sizes."""
+        AP = np.ascontiguousarray(AP, dtype=self.dtype)
+        nel = AP.shape[0]
+        nie = None if np.isscalar(ni) else _i32(ni)
+        nmax = int(ni) if nie is None else int(nie.max(initial=0))
+        if out is None:
+            out = np.zeros((nel, nmax * nmax), self.dtype)
+        f = self.L.hp3d_gpu_hermitian_unpack_batch
+        ll = C.c_longlong
+        f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, ll, C.c_void_p, ll, C.c_int]
+        _lib.check(f(int(self.complex), nel, nmax, _ptr(nie), _ptr(AP), int(np.prod(AP.shape[1:])), _ptr(out), int(np.prod(out.shape[1:])), int(threads)))
+        return out
 
     def _descr(self, norder, norient_edge, norient_face, xnod, etype):
         norder, noe, nof = _i32(norder).reshape(-1, 19), _i32(norient_edge).reshape(-1, 12), _i32(norient_face).reshape(-1, 6)

@@ -13,6 +13,7 @@
 #include <map>
 #include <thread>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -358,7 +359,7 @@ static long long dense_phase_launches(const DenseDims &d, bool want_z = true) { 
 // CPLX: arithmetic of the dense phase; RS: real-structured complex problem (real dense phase, complex outputs: DenseDims::rs)
 template <bool CPLX, bool RS>
 static void run_dense_and_scatter(const ChunkShape &sh, Lane &L, const Lane::Out &o, int nel, bool want_schur, cudaStream_t st, StageEvents *ev,
-                                  int mode) {
+                                  int mode, bool packed) {
   static_assert(!(CPLX && RS), "the real-structured path runs the dense phase in real arithmetic");
   constexpr bool OUTC = CPLX || RS;   // value type of the outputs
   const DenseDims &d = sh.d;
@@ -394,8 +395,8 @@ static void run_dense_and_scatter(const ChunkShape &sh, Lane &L, const Lane::Out
   if (ev && ev->on) cudaEventRecord(ev->e[2], st);
   OutMaps mp{g_lanes.d_iota, g_lanes.d_iota, g_lanes.d_ones, g_lanes.d_ones, 0, 0, 0, 0, L.ws.b.ni_e, L.ws.b.nb_e, L.ws.b.nip_e};
   dim3 blk(16, 16), g1((d.ni + 15) / 16, (d.ni + 15) / 16, nel);
-  if (RS) scatter_condensed_rs_kernel<<<g1, blk, 0, st>>>(d, L.ws.b.Am, mp, o.Aii, o.Bi, (long long)d.ni * d.ni, (long long)d.ni);
-  else scatter_condensed_kernel<CPLX><<<g1, blk, 0, st>>>(d, L.ws.b.Am, mp, o.Aii, o.Bi, (long long)d.ni * d.ni, (long long)d.ni);
+  if (RS) scatter_condensed_rs_kernel<<<g1, blk, 0, st>>>(d, L.ws.b.Am, mp, o.Aii, o.Bi, (long long)d.ni * d.ni, (long long)d.ni, packed ? 1 : 0);
+  else scatter_condensed_kernel<CPLX><<<g1, blk, 0, st>>>(d, L.ws.b.Am, mp, o.Aii, o.Bi, (long long)d.ni * d.ni, (long long)d.ni, packed ? 1 : 0);
   g_launches++;
   if (d.nb > 0 && want_schur) {
     dim3 g2((d.nb + 15) / 16, (d.ni + 15) / 16, nel);
@@ -416,13 +417,13 @@ static void run_dense_and_scatter(const ChunkShape &sh, Lane &L, const Lane::Out
 // L.ws.b.ni_e / nb_e on `st`.
 static void run_chunk(const ChunkShape &sh, Lane &L, int ob, const GeomParams &gp, const std::vector<Seg> &segs, int nel, const double *d_xnod,
                       long long xnod_ld, const double *d_src, long long src_ld, bool want_schur, cudaStream_t st, StageEvents *ev = nullptr,
-                      int mode = MODE_ELEM) {
+                      int mode = MODE_ELEM, bool packed = false) {
   if (ev && ev->on) cudaEventRecord(ev->e[0], st);
   run_integration(sh, L, gp, segs, nel, d_xnod, xnod_ld, d_src, src_ld, st);
   if (ev && ev->on) cudaEventRecord(ev->e[1], st);
-  if (sh.d.rs) run_dense_and_scatter<false, true>(sh, L, L.out[ob], nel, want_schur, st, ev, mode);
-  else if (sh.d.cplx) run_dense_and_scatter<true, false>(sh, L, L.out[ob], nel, want_schur, st, ev, mode);
-  else run_dense_and_scatter<false, false>(sh, L, L.out[ob], nel, want_schur, st, ev, mode);
+  if (sh.d.rs) run_dense_and_scatter<false, true>(sh, L, L.out[ob], nel, want_schur, st, ev, mode, packed);
+  else if (sh.d.cplx) run_dense_and_scatter<true, false>(sh, L, L.out[ob], nel, want_schur, st, ev, mode, packed);
+  else run_dense_and_scatter<false, false>(sh, L, L.out[ob], nel, want_schur, st, ev, mode, packed);
   if (ev && ev->on) cudaEventRecord(ev->e[3], st);
 }
 
@@ -461,7 +462,20 @@ static void run_celem(const ChunkShape &sh, Lane &L, const Lane::Out &o, const C
 struct Plan {
   FormParams fp;
   int store_schur = 1;
+  int aii_packed = 0;   // hp3d_params.aii_packed: Aii returns as the packed lower triangle
+  // signature cache; `mu` guards the map itself (nodes are never erased while the plan lives, so Signature pointers stay valid):
+  // host-only size queries from other threads may run while a batch that holds the device engine is in flight
   std::map<std::string, std::unique_ptr<Signature>> sigs;
+  std::mutex mu;
+  Signature *find(const std::string &k) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = sigs.find(k);
+    return it == sigs.end() ? nullptr : it->second.get();
+  }
+  Signature *insert(const std::string &k, std::unique_ptr<Signature> s) {   // keeps the first one if two threads raced
+    std::lock_guard<std::mutex> lk(mu);
+    return sigs.emplace(k, std::move(s)).first->second.get();
+  }
   GeomParams geom() const {
     GeomParams g; g.kind = fp.kind; g.source = fp.source; g.icomp = fp.icomp; g.omega = fp.omega; g.eps = fp.eps; g.mu = fp.mu; g.sigma = fp.sigma;
     return g;
@@ -499,17 +513,15 @@ struct Plan {
     for (unsigned t = 1; t < nt; t++) th.emplace_back(work);
     work();
     for (std::thread &t : th) t.join();
-    for (size_t i = 0; i < missing.size(); i++) {
+    for (size_t i = 0; i < missing.size(); i++)
       if (!built[i]->h.err.empty()) { err = "element " + std::to_string(missing[i].second) + ": " + built[i]->h.err; return -1; }
-      sigs.emplace(missing[i].first, std::move(built[i]));
-    }
+    for (size_t i = 0; i < missing.size(); i++) insert(missing[i].first, std::move(built[i]));
     return 0;
   }
   // dof counts / quadrature size / padded extents of a signature without compiling it (cached signatures are reused)
   bool sizes(int etype, const int *norder, const int *norie, const int *norif, SigHost &out, std::string &err) {
     if (etype != 1 && etype != 3) { err = "unknown element type (HP3D_MDLB = 1 and HP3D_MDLP = 3 are implemented)"; return false; }
-    auto it = sigs.find(key(etype, norder, norie, norif));
-    if (it != sigs.end()) { const SigHost &h = it->second->h; out = SigHost(); out.ni = h.ni; out.nb = h.nb; out.nint = h.nint; out.nH = h.nH; out.ntest = h.ntest; out.dims = h.dims; return true; }
+    if (const Signature *sg = find(key(etype, norder, norie, norif))) { const SigHost &h = sg->h; out = SigHost(); out.ni = h.ni; out.nb = h.nb; out.nint = h.nint; out.nH = h.nH; out.ntest = h.ntest; out.dims = h.dims; return true; }
     const bool ok = etype == 3 ? compile_signature_prism(fp, norder, norie, norif, out, true) : compile_signature(fp, norder, norie, norif, out, true);
     if (!ok) err = out.err;
     return ok;
@@ -518,15 +530,14 @@ struct Plan {
   Signature *get(int etype, const int *norder, const int *norie, const int *norif, bool device, std::string &err) {
     if (etype != 1 && etype != 3) { err = "unknown element type (HP3D_MDLB = 1 and HP3D_MDLP = 3 are implemented)"; return nullptr; }
     const std::string k = key(etype, norder, norie, norif);
-    auto it = sigs.find(k);
-    if (it == sigs.end()) {
-      std::unique_ptr<Signature> s(new Signature());
-      const bool ok = etype == 3 ? compile_signature_prism(fp, norder, norie, norif, s->h) : compile_signature(fp, norder, norie, norif, s->h);
-      if (!ok) { err = s->h.err; return nullptr; }
-      it = sigs.emplace(k, std::move(s)).first;
+    Signature *s = find(k);
+    if (!s) {
+      std::unique_ptr<Signature> ns(new Signature());
+      const bool ok = etype == 3 ? compile_signature_prism(fp, norder, norie, norif, ns->h) : compile_signature(fp, norder, norie, norif, ns->h);
+      if (!ok) { err = ns->h.err; return nullptr; }
+      s = insert(k, std::move(ns));
     }
-    Signature *s = it->second.get();
-    if (device && !s->d_tab) { if (s->upload(err)) return nullptr; }
+    if (device && !s->d_tab) { if (s->upload(err)) return nullptr; }   // device uploads only happen under the engine lock
     return s;
   }
 };
@@ -594,7 +605,7 @@ int dense_debug_run(int nel, int n, int nb, int ni, const void *Gv, const void *
   HP3D_CK(cudaMalloc(&dA, sizeof(double) * NS * nA * nel)); HP3D_CK(cudaMalloc(&dB, sizeof(double) * NS * ni * nel));
   HP3D_CK(cudaMalloc(&dAS, sizeof(double) * NS * nAS * nel)); HP3D_CK(cudaMalloc(&dBS, sizeof(double) * NS * (nb ? nb : 1) * nel));
   dim3 blk(16, 16), g1((ni + 15) / 16, (ni + 15) / 16, nel);
-  scatter_condensed_kernel<CPLX><<<g1, blk, 0, st>>>(d, ws.b.Am, mp, dA, dB, (long long)nA, (long long)ni);
+  scatter_condensed_kernel<CPLX><<<g1, blk, 0, st>>>(d, ws.b.Am, mp, dA, dB, (long long)nA, (long long)ni, 0);
   if (nb > 0) {
     dim3 g2((nb + 15) / 16, (ni + 15) / 16, nel);
     scatter_schur_kernel<CPLX><<<g2, blk, 0, st>>>(d, ws.b.Am, mp, dAS, dBS, (long long)nAS, (long long)nb);

@@ -19,8 +19,10 @@ struct OutMaps {
 };
 
 // grid = (ceil(ni/16), ceil(ni/16)+extras, batch), block (16,16).  Writes Aii (ni x ni), Bi (ni).
+// packed: only the lower triangle, LAPACK 'L' packed column-major storage AP[r + c(2 ni - c - 1)/2] = A(r,c), r >= c (0-based):
+// what ZHERK('L') + ZTRTTP would hold; the upper triangle is its conjugate mirror (hp3d_gpu_hermitian_unpack_batch).
 template <bool CPLX>
-__global__ void scatter_condensed_kernel(DenseDims d, const double *Am, OutMaps mp, double *Aii, double *Bi, long long sA, long long sB) {
+__global__ void scatter_condensed_kernel(DenseDims d, const double *Am, OutMaps mp, double *Aii, double *Bi, long long sA, long long sB, int packed) {
   const int e = blockIdx.z;
   const int r = blockIdx.x * 16 + threadIdx.x, c = blockIdx.y * 16 + threadIdx.y;
   const int M = d.M();
@@ -30,13 +32,14 @@ __global__ void scatter_condensed_kernel(DenseDims d, const double *Am, OutMaps 
   const double *si = mp.sgn_i + (long long)e * mp.sgn_stride_i;
   constexpr int NS = CPLX ? 2 : 1;
   const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, lrow = (mp.nip_e ? mp.nip_e[e] : d.nip) - 1;
-  if (r < ni && c < ni) {
+  if (r < ni && c < ni && (!packed || r >= c)) {
     int ir = pi[r], ic = pi[c];
     double s = si[r] * si[c];
     int a = ir >= ic ? ir : ic, b = ir >= ic ? ic : ir;
     double vr = S[(long long)a * M + b], vi = 0.0;
     if (CPLX) { vi = S[apl + (long long)a * M + b]; if (ir < ic) vi = -vi; if (ir == ic) vi = 0.0; }
-    double *o = Aii + (long long)e * sA * NS + ((long long)r + (long long)ni * c) * NS;
+    const long long at = packed ? (long long)r + ((long long)c * (2LL * ni - c - 1)) / 2 : (long long)r + (long long)ni * c;
+    double *o = Aii + (long long)e * sA * NS + at * NS;
     o[0] = s * vr;
     if (CPLX) o[1] = s * vi;
   }
@@ -94,6 +97,30 @@ __global__ void stc_bwd_kernel(const int *__restrict__ ni_e, const int *__restri
   for (int o = 16; o; o >>= 1) { sr += __shfl_xor_sync(0xffffffffu, sr, o); if (CPLX) si += __shfl_xor_sync(0xffffffffu, si, o); }
   if (lane == 0) {
     const double *b = BS + (long long)e * sBS * NS + (long long)r * NS;
+    double *o = xb + (long long)e * sxb * NS + (long long)r * NS;
+    o[0] = b[0] - sr;
+    if (CPLX) o[1] = b[1] - si;
+  }
+}
+
+// stc_bwd on the device-resident store: element e's factors at AS[e] / BS[e] (one warp per bubble row); grid (ceil(nbmax/8), nel)
+template <bool CPLX>
+__global__ void stc_bwd_ptr_kernel(const double *const *__restrict__ AS, const double *const *__restrict__ BS, const int *__restrict__ ni_e,
+                                   const int *__restrict__ nb_e, const double *xi, long long sxi, double *xb, long long sxb) {
+  constexpr int NS = CPLX ? 2 : 1;
+  const int e = blockIdx.y, r = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+  const int ni = ni_e[e], nb = nb_e[e];
+  if (r >= nb) return;
+  const double *A = AS[e], *x = xi + (long long)e * sxi * NS;
+  double sr = 0, si = 0;
+  for (int c = lane; c < ni; c += 32) {
+    const double *a = A + ((long long)r + (long long)nb * c) * NS;
+    if (CPLX) { sr += a[0] * x[2 * c] - a[1] * x[2 * c + 1]; si += a[0] * x[2 * c + 1] + a[1] * x[2 * c]; }
+    else sr += a[0] * x[c];
+  }
+  for (int o = 16; o; o >>= 1) { sr += __shfl_xor_sync(0xffffffffu, sr, o); if (CPLX) si += __shfl_xor_sync(0xffffffffu, si, o); }
+  if (lane == 0) {
+    const double *b = BS[e] + (long long)r * NS;
     double *o = xb + (long long)e * sxb * NS + (long long)r * NS;
     o[0] = b[0] - sr;
     if (CPLX) o[1] = b[1] - si;
@@ -161,17 +188,18 @@ __device__ __forceinline__ void rs_load(double yre, double yim, int ph, double &
 }
 
 // grid = (ceil(ni/16), ceil(ni/16), batch), block (16,16): complex Aii (ni x ni), Bi (ni) from the real Schur complement
-__global__ void scatter_condensed_rs_kernel(DenseDims d, const double *Am, OutMaps mp, double *Aii, double *Bi, long long sA, long long sB) {
+__global__ void scatter_condensed_rs_kernel(DenseDims d, const double *Am, OutMaps mp, double *Aii, double *Bi, long long sA, long long sB, int packed) {
   const int e = blockIdx.z;
   const int r = blockIdx.x * 16 + threadIdx.x, c = blockIdx.y * 16 + threadIdx.y;
   const int M = d.M();
   const double *S = Am + (long long)e * (long long)d.a_plane() + (long long)d.nbp * M + d.nbp;
   const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, lrow = (mp.nip_e ? mp.nip_e[e] : d.nip) - 2;
-  if (r < ni && c < ni) {
+  if (r < ni && c < ni && (!packed || r >= c)) {
     const int a = r >= c ? r : c, b = r >= c ? c : r;
     double re, im;
     rs_apply(S[(long long)a * M + b], rs_phase_i(r), rs_phase_i(c), re, im);
-    double *o = Aii + (long long)e * sA * 2 + ((long long)r + (long long)ni * c) * 2;
+    const long long at = packed ? (long long)r + ((long long)c * (2LL * ni - c - 1)) / 2 : (long long)r + (long long)ni * c;
+    double *o = Aii + (long long)e * sA * 2 + at * 2;
     o[0] = re; o[1] = im;
   }
   if (blockIdx.y == 0 && threadIdx.y == 0 && r < ni) {

@@ -4,19 +4,25 @@
 #include "error_eval.cuh"
 #include "pbi.cuh"
 
+#include <atomic>
 #include <cstdarg>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 using namespace hp3d;
 
 namespace {
+// Locking: g_mu serialises the entry points that touch the DEVICE engine (lanes, arena, streams, signature uploads) and the
+// plan table; host-only entry points (celem_pack, dof_map, tables_1d, prism_shape, physics_default, chunk_plan_debug) take
+// no lock at all and may run from the reference's OpenMP threads while a batch is in flight; the size queries
+// (hp3d_gpu_sizes*, hp3d_gpu_sig_dims) only take the plan's own mutex.  The last error message is per calling thread.
 std::recursive_mutex g_mu;
-std::string g_err;
+thread_local std::string g_err;
 int g_device = -1;
 std::vector<Plan *> g_plans;
 cudaStream_t g_lane_stream[LaneSet::NLANE] = {nullptr, nullptr, nullptr, nullptr}, g_copy = nullptr;
@@ -56,7 +62,19 @@ int fail(int code, const char *fmt, ...) {
     if (e_ != cudaSuccess) return fail(HP3D_ENODEV, "%s: %s", #x, cudaGetErrorString(e_)); \
   } while (0)
 
-Plan *plan_of(int id) { return (id >= 0 && id < (int)g_plans.size()) ? g_plans[id] : nullptr; }
+void release_clocs(int plan);   // device-resident Schur stores of one plan (-1: all), defined with ClocStore below
+std::mutex g_plans_mu;   // the plan table and the lifetime of its entries (held briefly; never while waiting for the device)
+Plan *plan_of(int id) {
+  std::lock_guard<std::mutex> lk(g_plans_mu);
+  return (id >= 0 && id < (int)g_plans.size()) ? g_plans[id] : nullptr;
+}
+// CUDA's current device is per host thread: every device entry point may be called from any of the reference's OpenMP threads
+int enter_device() {
+  if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
+  cudaError_t e = cudaSetDevice(g_device);
+  if (e != cudaSuccess) return fail(HP3D_ENODEV, "cudaSetDevice(%d): %s", g_device, cudaGetErrorString(e));
+  return HP3D_OK;
+}
 
 // largest chunk (elements per lane) of this shape that fits in the free device memory
 int chunk_capacity(const ChunkShape &sh, int want, int nlanes = 2) {
@@ -122,7 +140,7 @@ int build_classes(Plan *p, int nel, const int *etype, const int *norder, const i
   std::map<std::string, std::vector<SigGroup>> base;
   {
     std::vector<std::pair<std::string, int>> missing;
-    for (auto &g : bysig) if (!p->sigs.count(g.first)) missing.emplace_back(g.first, g.second[0]);
+    for (auto &g : bysig) if (!p->find(g.first)) missing.emplace_back(g.first, g.second[0]);
     const auto t0 = std::chrono::steady_clock::now();
     if (p->compile_missing(missing, etype, norder, norie, norif, err)) return HP3D_EINVAL;
     if (getenv("HP3D_TRACE") && !missing.empty())
@@ -192,6 +210,9 @@ int hp3d_gpu_init(int device) {
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) return fail(HP3D_ENODEV, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
   if (device < 0 || device >= n) return fail(HP3D_EINVAL, "device %d out of range (0..%d)", device, n - 1);
+  // one device per process (hp3D runs one MPI rank per GPU): streams, workspaces and cached tables belong to the first device
+  if (g_device >= 0 && g_device != device)
+    return fail(HP3D_EINVAL, "already initialised on device %d: call hp3d_gpu_finalize before selecting device %d (one device per process)", g_device, device);
   CUDA_TRY(cudaSetDevice(device));
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -212,9 +233,14 @@ int hp3d_gpu_init(int device) {
 
 int hp3d_gpu_finalize(void) {
   std::lock_guard<std::recursive_mutex> lk(g_mu);
-  for (Plan *p : g_plans) delete p;
-  g_plans.clear();
+  if (g_device >= 0) cudaSetDevice(g_device);
+  {
+    std::lock_guard<std::mutex> lp(g_plans_mu);
+    for (Plan *p : g_plans) delete p;
+    g_plans.clear();
+  }
   cudaDeviceSynchronize();
+  release_clocs(-1);
   g_lanes.release();
   g_arena.release();
   g_celem_store.release();
@@ -228,7 +254,6 @@ int hp3d_gpu_finalize(void) {
 }
 
 int hp3d_gpu_plan(int problem_kind, const hp3d_params *prm) {
-  std::lock_guard<std::recursive_mutex> lk(g_mu);
   if (!prm) return fail(HP3D_EINVAL, "null params");
   if (problem_kind < HP3D_POIS_GAL || problem_kind > HP3D_MAXW_UW) return fail(HP3D_EINVAL, "unknown problem kind %d", problem_kind);
   // constant isotropic permittivity only (the reference's default get_permittivity is the identity,
@@ -246,6 +271,12 @@ int hp3d_gpu_plan(int problem_kind, const hp3d_params *prm) {
   p->fp.source = prm->source; p->fp.icomp = prm->icomp_exact - 1;
   p->store_schur = prm->store_schur;
   p->fp.real_struct = prm->real_reduction != 0;
+  p->aii_packed = prm->aii_packed != 0;
+  if (p->aii_packed && problem_kind != HP3D_POIS_PDPG && problem_kind != HP3D_MAXW_UW) {
+    delete p;
+    return fail(HP3D_EINVAL, "aii_packed is defined for the Hermitian (DPG) problems only");
+  }
+  std::lock_guard<std::mutex> lk(g_plans_mu);
   for (size_t i = 0; i < g_plans.size(); i++)
     if (!g_plans[i]) { g_plans[i] = p; return (int)i; }
   g_plans.push_back(p);
@@ -260,11 +291,16 @@ int hp3d_gpu_set_chunk(int max_elements) {
 }
 
 int hp3d_gpu_plan_destroy(int plan) {
-  std::lock_guard<std::recursive_mutex> lk(g_mu);
-  Plan *p = plan_of(plan);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);   // waits for a batch in flight: it may be using this plan's tables
+  Plan *p = nullptr;
+  {
+    std::lock_guard<std::mutex> lp(g_plans_mu);
+    if (plan >= 0 && plan < (int)g_plans.size()) { p = g_plans[plan]; g_plans[plan] = nullptr; }
+  }
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
+  if (g_device >= 0) cudaSetDevice(g_device);
+  release_clocs(plan);
   delete p;
-  g_plans[plan] = nullptr;
   return HP3D_OK;
 }
 
@@ -273,8 +309,8 @@ int hp3d_gpu_sizes(int plan, const int *norder, int *ni, int *nb, int *nint, int
 }
 
 int hp3d_gpu_sizes_t(int plan, int etype, const int *norder, int *ni, int *nb, int *nint, int *nrdofH) {
-  std::lock_guard<std::recursive_mutex> lk(g_mu);
-  Plan *p = plan_of(plan);
+  std::lock_guard<std::mutex> lp(g_plans_mu);   // host only: keeps the plan alive, does not wait for the device engine
+  Plan *p = (plan >= 0 && plan < (int)g_plans.size()) ? g_plans[plan] : nullptr;
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
   const int z12[12] = {0}, z6[6] = {0};
   std::string err;
@@ -288,8 +324,8 @@ int hp3d_gpu_sizes_t(int plan, int etype, const int *norder, int *ni, int *nb, i
 }
 
 int hp3d_gpu_sig_dims(int plan, int etype, const int *norder, const int *norie, const int *norif, int *dims) {
-  std::lock_guard<std::recursive_mutex> lk(g_mu);
-  Plan *p = plan_of(plan);
+  std::lock_guard<std::mutex> lp(g_plans_mu);
+  Plan *p = (plan >= 0 && plan < (int)g_plans.size()) ? g_plans[plan] : nullptr;
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
   std::string err;
   SigHost h;
@@ -380,14 +416,48 @@ void hp3d_gpu_host_free(void *p) { if (p) cudaFreeHost(p); }
 }  // extern "C"
 
 namespace {
+// ------------------------------------------------------------------------------------------------
+// Device-resident CLOC: the back-substitution factors of stc_fwd_wrapper, CLOC(iel)%ASchur (nb x ni) and %BSchur (nb)
+// (src/modules/stc.F90:45-58,273-277), kept in HBM under the caller's element index instead of travelling to the host
+// (7.2 of the 13.0 MB an ultraweak Maxwell p=5 element produces); hp3d_gpu_cloc_bwd_batch is stc_bwd (stc.F90:661-677) on them.
+// Storage: one slab per hp3d_gpu_elem_batch_cloc call ([all ASchur blocks | all BSchur blocks] of the elements that did not
+// have a slot of the right size yet), column-major complex(8)/real(8) blocks exactly as the host arrays would hold them.
+// Elements that do not fit under the store's byte limit are SPILLED: their descriptors are kept on the host and stc_bwd
+// recomputes them through the MODE_BWD pipeline (the "recompute" option the reference leaves unimplemented, stc.F90:279-281).
+struct ClocStore {
+  int plan = -1;
+  bool cplx = false;
+  size_t limit = 0, bytes = 0;
+  struct Slot { double *AS, *BS; int ni, nb; };
+  struct Spill { int etype; int norder[19], norie[12], norif[6]; std::vector<double> xnod; std::vector<double> src; };
+  std::unordered_map<long long, Slot> slots;
+  std::unordered_map<long long, Spill> spilled;
+  std::vector<void *> slabs;
+  void release() { for (void *q : slabs) cudaFree(q); slabs.clear(); slots.clear(); spilled.clear(); bytes = 0; }
+};
+std::vector<ClocStore *> g_clocs;
+ClocStore *cloc_of(int id) { return (id >= 0 && id < (int)g_clocs.size()) ? g_clocs[id] : nullptr; }
+void release_clocs(int plan) {
+  for (ClocStore *&c : g_clocs)
+    if (c && (plan < 0 || c->plan == plan)) { cudaDeviceSynchronize(); c->release(); delete c; c = nullptr; }
+}
+
+struct EventSet {   // the events of one pipeline call; destroyed on every exit path
+  std::vector<cudaEvent_t> ev;
+  cudaError_t add(cudaEvent_t *e) { cudaError_t rc = cudaEventCreateWithFlags(e, cudaEventDisableTiming); if (rc == cudaSuccess) ev.push_back(*e); return rc; }
+  ~EventSet() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+};
+
 // The chunked, multi-lane pipeline behind hp3d_gpu_elem_batch (MODE_ELEM), hp3d_gpu_elem_bwd_batch (MODE_BWD: recompute the
 // element, return only xb = BSchur - ASchur xi) and hp3d_gpu_elem_residual_batch (MODE_RESID: DPG residual per element).
+// cloc != nullptr: the Schur factors of element e go to the device-resident store under the index iel[e] (e if iel == nullptr).
 int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif,
                const double *xnod, int xnod_ld, const void *source_qp, long long source_ld, void *Aii, long long sAii,
                void *Bi, long long sBi, void *ASchur, long long sAS, void *BSchur, long long sBS, int *ni_out, int *nb_out,
-               int *info, const void *xi, long long sxi, void *xb, long long sxb, double *resid, const CelemCall *cc = nullptr) {
+               int *info, const void *xi, long long sxi, void *xb, long long sxb, double *resid, const CelemCall *cc = nullptr,
+               ClocStore *cloc = nullptr, const long long *iel = nullptr) {
   std::lock_guard<std::recursive_mutex> lk(g_mu);
-  if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
+  if (int drc = enter_device()) return drc;
   Plan *p = plan_of(plan);
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
   if (nel < 0 || !norder || !norie || !norif || !xnod) return fail(HP3D_EINVAL, "null argument");
@@ -398,7 +468,10 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
   if (mode == MODE_RESID && (!xi || !resid)) return fail(HP3D_EINVAL, "null argument");
   if (mode == MODE_RESID && p->fp.kind != HP3D_POIS_PDPG && p->fp.kind != HP3D_MAXW_UW) return fail(HP3D_EINVAL, "the element residual is defined for the DPG problems only");
   if (p->fp.source == HP3D_SRC_TABLE && !source_qp) return fail(HP3D_EINVAL, "source == HP3D_SRC_TABLE needs source_qp");
-  const bool want_schur = mode == MODE_BWD || (big && p->store_schur && ASchur && BSchur);
+  if (cloc && !big) return fail(HP3D_EINVAL, "the device-resident Schur store is filled by the element / celem calls only");
+  const bool to_host_schur = big && !cloc && p->store_schur && ASchur && BSchur;
+  const bool want_schur = mode == MODE_BWD || to_host_schur || cloc != nullptr;
+  const bool packed = mode == MODE_ELEM && p->aii_packed;
   std::vector<ClassGroup> classes;
   std::string err;
   if (int brc = build_classes(p, nel, etype, norder, norie, norif, true, classes, err)) return fail(brc, "%s", err.c_str());
@@ -410,6 +483,85 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
       }
       C.shape.coo = cc->irn != nullptr;
     }
+  // ---- every caller stride is checked BEFORE anything is queued (a short stride would read / write outside the caller's arrays)
+  for (const ClassGroup &C : classes) {
+    const ChunkShape &sh = C.shape;
+    const long long ni = sh.d.ni, nb = sh.d.nb;
+    if (xnod_ld < 3 * sh.nH_max) return fail(HP3D_EINVAL, "xnod_ld=%d < 3*nrdofH=%d", xnod_ld, 3 * sh.nH_max);
+    if (p->fp.source == HP3D_SRC_TABLE && source_ld < (long long)sh.src_max)
+      return fail(HP3D_EINVAL, "source_ld=%lld < %zu doubles (nint x %d values per point)", source_ld, sh.src_max, sh.d.cplx || sh.d.rs ? 6 : 1);
+    if (mode == MODE_ELEM) {
+      const long long need = packed ? ni * (ni + 1) / 2 : ni * ni;
+      if (sAii < need) return fail(HP3D_EINVAL, "Aii stride %lld < %lld scalars (%s ni = %lld)", sAii, need, packed ? "packed triangle of" : "ni^2,", ni);
+      if (sBi < ni) return fail(HP3D_EINVAL, "Bi stride %lld < ni = %lld", sBi, ni);
+    }
+    if (to_host_schur && nb > 0) {
+      if (sAS < nb * ni) return fail(HP3D_EINVAL, "ASchur stride %lld < nb*ni = %lld", sAS, nb * ni);
+      if (sBS < nb) return fail(HP3D_EINVAL, "BSchur stride %lld < nb = %lld", sBS, nb);
+    }
+    if (!big) {
+      if (sxi < ni) return fail(HP3D_EINVAL, "xi stride %lld < ni = %lld", sxi, ni);
+      if (xb && sxb < nb) return fail(HP3D_EINVAL, "xb stride %lld < nb = %lld", sxb, nb);
+      if (mode == MODE_RESID && nb > 0 && !xb) return fail(HP3D_EINVAL, "residual: xb (bubble dofs) is required for elements with bubbles");
+    }
+    if (mode == MODE_RESID && sizeof(double) * 2 * (size_t)sh.d.M() > (size_t)RESID_SMEM_MAX)
+      return fail(HP3D_EINVAL, "element residual: %d padded trial dofs exceed the kernel's shared-memory vector (%d)", sh.d.M(), RESID_SMEM_MAX / 16);
+  }
+  // ---- device-resident Schur store: a slot per element (reused when the sizes agree), new ones carved from one slab
+  const size_t esz = sizeof(double) * ((p->fp.kind >= HP3D_MAXW_GAL) ? 2 : 1);
+  std::vector<ClocStore::Slot> eslot;   // per caller element; AS == nullptr: spilled
+  if (cloc) {
+    if (cloc->plan != plan) return fail(HP3D_EINVAL, "this Schur store belongs to plan %d", cloc->plan);
+    eslot.assign(nel, ClocStore::Slot{nullptr, nullptr, 0, 0});
+    std::vector<int> fresh;
+    size_t needA = 0, needB = 0;
+    for (const ClassGroup &C : classes)
+      for (size_t i = 0; i < C.el.size(); i++) {
+        const int e = C.el[i];
+        const SigHost &h = C.sig[i]->h;
+        const long long id = iel ? iel[e] : e;
+        cloc->spilled.erase(id);
+        auto it = cloc->slots.find(id);
+        if (it != cloc->slots.end() && it->second.ni == h.ni && it->second.nb == h.nb) { eslot[e] = it->second; continue; }
+        if (it != cloc->slots.end()) cloc->slots.erase(it);   // sizes changed (refinement): the old block stays in its slab until the store is cleared
+        eslot[e].ni = h.ni; eslot[e].nb = h.nb;
+        fresh.push_back(e);
+      }
+    // elements are granted in caller order until the limit is reached; the rest is spilled
+    std::sort(fresh.begin(), fresh.end());
+    size_t granted = 0;
+    for (; granted < fresh.size(); granted++) {
+      const ClocStore::Slot &sl = eslot[fresh[granted]];
+      const size_t a = esz * (size_t)sl.nb * sl.ni, b2 = esz * (size_t)sl.nb;
+      if (cloc->bytes + needA + needB + a + b2 + 512 > cloc->limit) break;
+      needA += a; needB += b2;
+    }
+    if (granted) {
+      char *slab = nullptr;
+      needA = (needA + 255) & ~(size_t)255;
+      cudaError_t ce = cudaMalloc((void **)&slab, needA + needB + 256);
+      if (ce != cudaSuccess) { cudaGetLastError(); granted = 0; }   // no room after all: everything new is spilled
+      else {
+        cloc->slabs.push_back(slab); cloc->bytes += needA + needB + 256;
+        size_t oa = 0, ob = needA;
+        for (size_t k = 0; k < granted; k++) {
+          ClocStore::Slot &sl = eslot[fresh[k]];
+          sl.AS = (double *)(slab + oa); sl.BS = (double *)(slab + ob);
+          oa += esz * (size_t)sl.nb * sl.ni; ob += esz * (size_t)sl.nb;
+          cloc->slots[iel ? iel[fresh[k]] : fresh[k]] = sl;
+        }
+      }
+    }
+    for (size_t k = granted; k < fresh.size(); k++) {   // spilled: keep what stc_bwd needs to recompute the element
+      const int e = fresh[k];
+      ClocStore::Spill sp;
+      sp.etype = etype ? etype[e] : HP3D_MDLB;
+      memcpy(sp.norder, norder + 19 * e, sizeof sp.norder); memcpy(sp.norie, norie + 12 * e, sizeof sp.norie); memcpy(sp.norif, norif + 6 * e, sizeof sp.norif);
+      sp.xnod.assign(xnod + (size_t)e * xnod_ld, xnod + (size_t)e * xnod_ld + xnod_ld);
+      if (p->fp.source == HP3D_SRC_TABLE) sp.src.assign((const double *)source_qp + (size_t)e * source_ld, (const double *)source_qp + (size_t)(e + 1) * source_ld);
+      cloc->spilled[iel ? iel[e] : e] = std::move(sp);
+    }
+  }
   const GeomParams gp = p->geom();
   // slot = (lane, output buffer): chunk k runs on lane k % NL and writes output buffer (k / NL) & 1 of that lane.
   // Four lanes of modest chunks keep the GPU as busy as two lanes of large ones (the latency-bound tile factorizations and
@@ -417,11 +569,9 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
   // in smaller pieces.
   constexpr int NL = LaneSet::NLANE, NSLOT = 2 * NL;
   cudaEvent_t evCompute[NSLOT], evCopy[NSLOT], evH2D[NL];
-  for (int i = 0; i < NSLOT; i++) {
-    CUDA_TRY(cudaEventCreateWithFlags(&evCompute[i], cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&evCopy[i], cudaEventDisableTiming));
-  }
-  for (int i = 0; i < NL; i++) CUDA_TRY(cudaEventCreateWithFlags(&evH2D[i], cudaEventDisableTiming));
+  EventSet events;
+  for (int i = 0; i < NSLOT; i++) { CUDA_TRY(events.add(&evCompute[i])); CUDA_TRY(events.add(&evCopy[i])); }
+  for (int i = 0; i < NL; i++) CUDA_TRY(events.add(&evH2D[i]));
   int rc = HP3D_OK;
   std::vector<Seg> segs;
   const bool trace = getenv("HP3D_TRACE") != nullptr;   // host-side phase times of the call on stderr
@@ -429,13 +579,9 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
   const double t_begin = now();
   double t_wait = 0.0, t_stage = 0.0;
   for (ClassGroup &C : classes) {
+    if (rc != HP3D_OK) break;
     const std::vector<int> &el = C.el;
     const ChunkShape &sh = C.shape;
-    if (xnod_ld < 3 * sh.nH_max) { rc = fail(HP3D_EINVAL, "xnod_ld=%d < 3*nrdofH=%d", xnod_ld, 3 * sh.nH_max); break; }
-    if (mode == MODE_RESID && sizeof(double) * 2 * (size_t)sh.d.M() > (size_t)RESID_SMEM_MAX) {
-      rc = fail(HP3D_EINVAL, "element residual: %d padded trial dofs exceed the kernel's shared-memory vector (%d)", sh.d.M(), RESID_SMEM_MAX / 16);
-      break;
-    }
     // chunk plan: chunks of up to 64 elements round-robin over the lanes, with a ramped start and a tapered end (below)
     int want = (int)el.size();
     if (g_max_chunk > 0) want = std::min(want, g_max_chunk);
@@ -490,13 +636,9 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
         if (mode == MODE_CELEM) L.h_cel[i] = e;
         if (!big) {
           memcpy(L.h_xi + NS * sB * i, (const char *)xi + es * sxi * e, es * h.ni);
-          if (mode == MODE_RESID && h.nb > 0) {
-            if (!xb) { rc = fail(HP3D_EINVAL, "residual: xb (bubble dofs) is required for elements with bubbles"); break; }
-            memcpy(L.h_xb + NS * (sT + 1) * i, (const char *)xb + es * sxb * e, es * h.nb);
-          }
+          if (mode == MODE_RESID && h.nb > 0) memcpy(L.h_xb + NS * (sT + 1) * i, (const char *)xb + es * sxb * e, es * h.nb);
         }
       }
-      if (rc != HP3D_OK) break;
       t_stage += now() - tw1;
       cudaMemcpyAsync(L.d_xnod, L.h_xnod, sizeof(double) * nx * n, cudaMemcpyHostToDevice, st);
       if (gp.source == HP3D_SRC_TABLE) cudaMemcpyAsync(L.d_src, L.h_src, sizeof(double) * nsrc * n, cudaMemcpyHostToDevice, st);
@@ -508,20 +650,33 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
       if (mode == MODE_RESID) cudaMemcpyAsync(L.d_xb, L.h_xb, es * (sT + 1) * n, cudaMemcpyHostToDevice, st);
       cudaEventRecord(evH2D[ln], st);
       chunk_segments(C, c0, n, segs);
-      run_chunk(sh, L, ob, gp, segs, n, L.d_xnod, (long long)nx, L.d_src, (long long)nsrc, want_schur, st, nullptr, mode);
+      run_chunk(sh, L, ob, gp, segs, n, L.d_xnod, (long long)nx, L.d_src, (long long)nsrc, want_schur, st, nullptr, mode, packed);
       if (mode == MODE_CELEM) run_celem(sh, L, L.out[ob], *cc, n, st);
+      const Lane::Out &o = L.out[ob];
+      if (cloc && sh.d.nb > 0) {   // Schur factors: device staging -> their slots (same stream; runs of neighbouring slots are merged)
+        for (int i = 0; i < n;) {
+          const ClocStore::Slot &s0 = eslot[el[c0 + i]];
+          if (!s0.AS) { i++; continue; }
+          const size_t ba = (size_t)s0.nb * s0.ni, bb = (size_t)s0.nb;
+          int j = i + 1;
+          if (ba == sS && bb == sT)
+            while (j < n && eslot[el[c0 + j]].AS == s0.AS + NS * ba * (j - i) && eslot[el[c0 + j]].BS == s0.BS + NS * bb * (j - i) &&
+                   eslot[el[c0 + j]].ni == s0.ni && eslot[el[c0 + j]].nb == s0.nb) j++;
+          cudaMemcpyAsync(s0.AS, o.AS + NS * sS * i, es * ba * (j - i), cudaMemcpyDeviceToDevice, st);
+          cudaMemcpyAsync(s0.BS, o.BS + NS * sT * i, es * bb * (j - i), cudaMemcpyDeviceToDevice, st);
+          i = j;
+        }
+      }
       cudaEventRecord(evCompute[slot], st);
       cudaStreamWaitEvent(g_copy, evCompute[slot], 0);
       if (!big) {   // small results: staged through pinned memory, scattered to the caller in collect_info
-        const Lane::Out &o2 = L.out[ob];
         if (mode == MODE_BWD) cudaMemcpyAsync(L.h_xb, L.d_xb, es * (sT + 1) * n, cudaMemcpyDeviceToHost, g_copy);
         else cudaMemcpyAsync(L.h_res, L.d_res, sizeof(double) * n, cudaMemcpyDeviceToHost, g_copy);
-        cudaMemcpyAsync(o2.h_info, o2.info, sizeof(int) * n, cudaMemcpyDeviceToHost, g_copy);
+        cudaMemcpyAsync(o.h_info, o.info, sizeof(int) * n, cudaMemcpyDeviceToHost, g_copy);
         cudaEventRecord(evCopy[slot], g_copy);
         continue;
       }
       // D2H straight into the caller's arrays; runs of consecutive elements with equal sizes and dense strides are merged
-      const Lane::Out &o = L.out[ob];
       if (mode == MODE_CELEM) {   // compressed systems: Zastif / IRN / JCN at the caller's offsets, Zbload at xptr
         const size_t zmax = sh.nz_max, cmax = sh.nc_max;
         for (int i = 0; i < n;) {
@@ -555,8 +710,11 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
           else
             cudaMemcpy2DAsync((char *)dst + es * stride * e, es * stride, src + NS * dstride * i, es * dstride, es * blk, run, cudaMemcpyDeviceToHost, g_copy);
         };
-        if (mode == MODE_ELEM) { copy(Aii, sAii, o.Aii, sA, (size_t)h.ni * h.ni); copy(Bi, sBi, o.Bi, sB, (size_t)h.ni); }
-        if (want_schur) { copy(ASchur, sAS, o.AS, sS, (size_t)h.nb * h.ni); copy(BSchur, sBS, o.BS, sT, (size_t)h.nb); }
+        if (mode == MODE_ELEM) {
+          copy(Aii, sAii, o.Aii, sA, packed ? (size_t)h.ni * (h.ni + 1) / 2 : (size_t)h.ni * h.ni);
+          copy(Bi, sBi, o.Bi, sB, (size_t)h.ni);
+        }
+        if (to_host_schur) { copy(ASchur, sAS, o.AS, sS, (size_t)h.nb * h.ni); copy(BSchur, sBS, o.BS, sT, (size_t)h.nb); }
         i = j;
       }
       cudaMemcpyAsync(o.h_info, o.info, sizeof(int) * n, cudaMemcpyDeviceToHost, g_copy);   // pinned: stays asynchronous
@@ -574,8 +732,6 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
   if (trace)
     fprintf(stderr, "[hp3d] mode %d nel %d: submit %.1f ms (waits %.1f, staging %.1f), compute drained +%.1f ms, copies drained +%.1f ms\n", mode, nel,
             t_submitted - t_begin, t_wait, t_stage, t_computed - t_submitted, now() - t_computed);
-  for (int i = 0; i < NSLOT; i++) { cudaEventDestroy(evCompute[i]); cudaEventDestroy(evCopy[i]); }
-  for (int i = 0; i < NL; i++) cudaEventDestroy(evH2D[i]);
   if (rc == HP3D_OK) {
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) rc = fail(HP3D_ENODEV, "CUDA error in elem_batch: %s", cudaGetErrorString(ce));
@@ -674,13 +830,16 @@ long long hp3d_gpu_celem_pack(const hp3d_physics *ph, const int *nrdofl, const i
   return nent;
 }
 
-int hp3d_gpu_celem_batch(int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif, const double *xnod,
-                         int xnod_ld, const void *source_qp, long long source_ld, const long long *mptr, const long long *cptr,
-                         const int *cidx, const double *cval, const int *idbc, const void *zdofd, const long long *xptr,
-                         const int *nextract, const int *lcon, int isym_flag, const long long *aptr, void *zbload, void *zastif, int *irn,
-                         int *jcn, void *ASchur, long long sAS, void *BSchur, long long sBS, int *ni_out, int *nb_out, int *info) {
+}  // extern "C"
+namespace {
+int celem_impl(int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif, const double *xnod,
+               int xnod_ld, const void *source_qp, long long source_ld, const long long *mptr, const long long *cptr,
+               const int *cidx, const double *cval, const int *idbc, const void *zdofd, const long long *xptr,
+               const int *nextract, const int *lcon, int isym_flag, const long long *aptr, void *zbload, void *zastif, int *irn,
+               int *jcn, void *ASchur, long long sAS, void *BSchur, long long sBS, int *ni_out, int *nb_out, int *info,
+               ClocStore *cloc, const long long *iel) {
   std::lock_guard<std::recursive_mutex> lk(g_mu);
-  if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
+  if (int drc = enter_device()) return drc;
   Plan *p = plan_of(plan);
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
   if (isym_flag < 1 || isym_flag > 3) return fail(HP3D_EINVAL, "celem_batch: ISYM_FLAG must be 1, 2 or 3");
@@ -757,16 +916,245 @@ int hp3d_gpu_celem_batch(int plan, int nel, const int *etype, const int *norder,
   if (!ok) rc = fail(HP3D_ENOMEM, "celem_batch: cannot place the constraint data on the device: %s", cudaGetErrorString(cudaGetLastError()));
   else
     rc = batch_impl(MODE_CELEM, plan, nel, etype, norder, norie, norif, xnod, xnod_ld, source_qp, source_ld, nullptr, 0, nullptr, 0, ASchur, sAS,
-                    BSchur, sBS, ni_out, nb_out, info, nullptr, 0, nullptr, 0, nullptr, &cc);
+                    BSchur, sBS, ni_out, nb_out, info, nullptr, 0, nullptr, 0, nullptr, &cc, cloc, iel);
   const double t3 = now();
   if (trace) fprintf(stderr, "[hp3d] celem_batch: validate %.1f ms, upload %.1f ms, pipeline %.1f ms, release %.1f ms\n", t1 - t0, t2 - t1, t3 - t2, now() - t3);
   return rc;
+}
+}  // namespace
+extern "C" {
+
+int hp3d_gpu_celem_batch(int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif, const double *xnod,
+                         int xnod_ld, const void *source_qp, long long source_ld, const long long *mptr, const long long *cptr,
+                         const int *cidx, const double *cval, const int *idbc, const void *zdofd, const long long *xptr,
+                         const int *nextract, const int *lcon, int isym_flag, const long long *aptr, void *zbload, void *zastif, int *irn,
+                         int *jcn, void *ASchur, long long sAS, void *BSchur, long long sBS, int *ni_out, int *nb_out, int *info) {
+  return celem_impl(plan, nel, etype, norder, norie, norif, xnod, xnod_ld, source_qp, source_ld, mptr, cptr, cidx, cval, idbc, zdofd, xptr, nextract,
+                    lcon, isym_flag, aptr, zbload, zastif, irn, jcn, ASchur, sAS, BSchur, sBS, ni_out, nb_out, info, nullptr, nullptr);
+}
+
+// ---- device-resident CLOC (see the ClocStore comment above batch_impl) ----
+int hp3d_gpu_cloc_create(int plan, long long limit_bytes) {
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  if (int drc = enter_device()) return drc;
+  Plan *p = plan_of(plan);
+  if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
+  if (limit_bytes < 0) return fail(HP3D_EINVAL, "cloc_create: negative byte limit");
+  if (limit_bytes == 0) {
+    size_t fr = 0, tot = 0;
+    CUDA_TRY(cudaMemGetInfo(&fr, &tot));
+    limit_bytes = (long long)(0.6 * (double)fr);
+  }
+  ClocStore *c = new ClocStore();
+  c->plan = plan; c->cplx = p->fp.kind >= HP3D_MAXW_GAL; c->limit = (size_t)limit_bytes;
+  for (size_t i = 0; i < g_clocs.size(); i++)
+    if (!g_clocs[i]) { g_clocs[i] = c; return (int)i; }
+  g_clocs.push_back(c);
+  return (int)g_clocs.size() - 1;
+}
+
+int hp3d_gpu_cloc_clear(int cloc) {
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  if (int drc = enter_device()) return drc;
+  ClocStore *c = cloc_of(cloc);
+  if (!c) return fail(HP3D_EINVAL, "no such Schur store %d", cloc);
+  for (int i = 0; i < LaneSet::NLANE; i++) cudaStreamSynchronize(g_lane_stream[i]);
+  c->release();
+  return HP3D_OK;
+}
+
+int hp3d_gpu_cloc_destroy(int cloc) {
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  if (int rc = hp3d_gpu_cloc_clear(cloc)) return rc;
+  delete g_clocs[cloc];
+  g_clocs[cloc] = nullptr;
+  return HP3D_OK;
+}
+
+int hp3d_gpu_cloc_stats(int cloc, long long *stats) {
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  ClocStore *c = cloc_of(cloc);
+  if (!c || !stats) return fail(HP3D_EINVAL, "no such Schur store %d", cloc);
+  stats[0] = (long long)c->slots.size(); stats[1] = (long long)c->spilled.size(); stats[2] = (long long)c->bytes; stats[3] = (long long)c->limit;
+  return HP3D_OK;
+}
+
+int hp3d_gpu_elem_batch_cloc(int plan, int cloc, int nel, const long long *iel, const int *etype, const int *norder, const int *norie,
+                             const int *norif, const double *xnod, int xnod_ld, const void *source_qp, long long source_ld, void *Aii,
+                             long long sAii, void *Bi, long long sBi, int *ni_out, int *nb_out, int *info) {
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  ClocStore *c = cloc_of(cloc);
+  if (!c) return fail(HP3D_EINVAL, "no such Schur store %d", cloc);
+  return batch_impl(MODE_ELEM, plan, nel, etype, norder, norie, norif, xnod, xnod_ld, source_qp, source_ld, Aii, sAii, Bi, sBi, nullptr, 0,
+                    nullptr, 0, ni_out, nb_out, info, nullptr, 0, nullptr, 0, nullptr, nullptr, c, iel);
+}
+
+int hp3d_gpu_celem_batch_cloc(int plan, int cloc, int nel, const long long *iel, const int *etype, const int *norder, const int *norie,
+                              const int *norif, const double *xnod, int xnod_ld, const void *source_qp, long long source_ld,
+                              const long long *mptr, const long long *cptr, const int *cidx, const double *cval, const int *idbc,
+                              const void *zdofd, const long long *xptr, const int *nextract, const int *lcon, int isym_flag,
+                              const long long *aptr, void *zbload, void *zastif, int *irn, int *jcn, int *ni_out, int *nb_out, int *info) {
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  ClocStore *c = cloc_of(cloc);
+  if (!c) return fail(HP3D_EINVAL, "no such Schur store %d", cloc);
+  return celem_impl(plan, nel, etype, norder, norie, norif, xnod, xnod_ld, source_qp, source_ld, mptr, cptr, cidx, cval, idbc, zdofd, xptr, nextract,
+                    lcon, isym_flag, aptr, zbload, zastif, irn, jcn, nullptr, 0, nullptr, 0, ni_out, nb_out, info, c, iel);
+}
+
+int hp3d_gpu_cloc_fetch(int cloc, long long iel, void *ASchur, void *BSchur, int *ni, int *nb) {
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  if (int drc = enter_device()) return drc;
+  ClocStore *c = cloc_of(cloc);
+  if (!c) return fail(HP3D_EINVAL, "no such Schur store %d", cloc);
+  if (c->spilled.count(iel)) return 1;
+  auto it = c->slots.find(iel);
+  if (it == c->slots.end()) return fail(HP3D_EINVAL, "cloc_fetch: element %lld has not been condensed into this store", iel);
+  const ClocStore::Slot &sl = it->second;
+  const size_t es = sizeof(double) * (c->cplx ? 2 : 1);
+  if (ni) *ni = sl.ni;
+  if (nb) *nb = sl.nb;
+  for (int i = 0; i < LaneSet::NLANE; i++) cudaStreamSynchronize(g_lane_stream[i]);
+  if (ASchur && sl.nb) CUDA_TRY(cudaMemcpy(ASchur, sl.AS, es * (size_t)sl.nb * sl.ni, cudaMemcpyDeviceToHost));
+  if (BSchur && sl.nb) CUDA_TRY(cudaMemcpy(BSchur, sl.BS, es * (size_t)sl.nb, cudaMemcpyDeviceToHost));
+  return HP3D_OK;
+}
+
+int hp3d_gpu_cloc_bwd_batch(int cloc, int nel, const long long *iel, const void *xi, long long sxi, void *xb, long long sxb, int *nb_out,
+                            int *info) {
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  if (int drc = enter_device()) return drc;
+  ClocStore *c = cloc_of(cloc);
+  if (!c) return fail(HP3D_EINVAL, "no such Schur store %d", cloc);
+  if (nel < 0 || (nel > 0 && (!xi || !xb))) return fail(HP3D_EINVAL, "cloc_bwd: null argument");
+  const int NS = c->cplx ? 2 : 1;
+  const size_t es = sizeof(double) * NS;
+  std::vector<int> res, spl;   // caller positions of resident / spilled elements
+  int nimax = 0, nbmax = 0;
+  for (int e = 0; e < nel; e++) {
+    const long long id = iel ? iel[e] : e;
+    auto it = c->slots.find(id);
+    if (it != c->slots.end()) {
+      res.push_back(e);
+      nimax = std::max(nimax, it->second.ni); nbmax = std::max(nbmax, it->second.nb);
+      if (sxi < it->second.ni || sxb < it->second.nb) return fail(HP3D_EINVAL, "cloc_bwd: element %lld needs strides >= (%d, %d)", id, it->second.ni, it->second.nb);
+      if (nb_out) nb_out[e] = it->second.nb;
+      if (info) info[e] = 0;
+    } else if (c->spilled.count(id)) spl.push_back(e);
+    else return fail(HP3D_EINVAL, "cloc_bwd: element %lld has not been condensed into this store", id);
+  }
+  for (int i = 0; i < LaneSet::NLANE; i++) cudaStreamSynchronize(g_lane_stream[i]);   // the factors were written on the lane streams
+  // resident elements: one warp per bubble row reads its factors in place; chunks bounded by the grid limit and a 256 MB staging budget
+  if (!res.empty() && nbmax > 0) {
+    const size_t per = es * ((size_t)nimax + nbmax) + 2 * sizeof(void *) + 2 * sizeof(int);
+    const int chunk = (int)std::min<size_t>(std::min<size_t>(res.size(), 32768), std::max<size_t>(1, ((size_t)256 << 20) / per));
+    struct Bufs {
+      void *d = nullptr, *h = nullptr;
+      ~Bufs() { if (d) cudaFree(d); if (h) cudaFreeHost(h); }
+    } bufs;
+    const size_t oX = 0, oY = oX + es * (size_t)nimax * chunk, oPA = (oY + es * (size_t)nbmax * chunk + 15) & ~(size_t)15,
+                 oPB = oPA + sizeof(void *) * chunk, oNI = oPB + sizeof(void *) * chunk, oNB = oNI + sizeof(int) * chunk, total = oNB + sizeof(int) * chunk;
+    if (cudaMalloc(&bufs.d, total) != cudaSuccess || cudaMallocHost(&bufs.h, total) != cudaSuccess) { cudaGetLastError(); return fail(HP3D_ENOMEM, "cloc_bwd: staging buffers"); }
+    char *h = (char *)bufs.h, *d = (char *)bufs.d;
+    for (size_t c0 = 0; c0 < res.size(); c0 += chunk) {
+      const int n = (int)std::min<size_t>(chunk, res.size() - c0);
+      for (int i = 0; i < n; i++) {
+        const int e = res[c0 + i];
+        const ClocStore::Slot &sl = c->slots.find(iel ? iel[e] : e)->second;
+        memcpy(h + oX + es * (size_t)nimax * i, (const char *)xi + es * sxi * e, es * sl.ni);
+        ((const double **)(h + oPA))[i] = sl.AS; ((const double **)(h + oPB))[i] = sl.BS;
+        ((int *)(h + oNI))[i] = sl.ni; ((int *)(h + oNB))[i] = sl.nb;
+      }
+      CUDA_TRY(cudaMemcpyAsync(d, h, es * (size_t)nimax * n, cudaMemcpyHostToDevice, g_compute));
+      CUDA_TRY(cudaMemcpyAsync(d + oPA, h + oPA, total - oPA, cudaMemcpyHostToDevice, g_compute));
+      dim3 grid((nbmax + 7) / 8, n);
+      if (c->cplx)
+        stc_bwd_ptr_kernel<true><<<grid, 256, 0, g_compute>>>((const double *const *)(d + oPA), (const double *const *)(d + oPB), (const int *)(d + oNI),
+                                                              (const int *)(d + oNB), (const double *)(d + oX), nimax, (double *)(d + oY), nbmax);
+      else
+        stc_bwd_ptr_kernel<false><<<grid, 256, 0, g_compute>>>((const double *const *)(d + oPA), (const double *const *)(d + oPB), (const int *)(d + oNI),
+                                                               (const int *)(d + oNB), (const double *)(d + oX), nimax, (double *)(d + oY), nbmax);
+      g_launches++;
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaMemcpyAsync(h + oY, d + oY, es * (size_t)nbmax * n, cudaMemcpyDeviceToHost, g_compute));
+      CUDA_TRY(cudaStreamSynchronize(g_compute));
+      for (int i = 0; i < n; i++) {
+        const int e = res[c0 + i];
+        memcpy((char *)xb + es * sxb * e, h + oY + es * (size_t)nbmax * i, es * ((int *)(h + oNB))[i]);
+      }
+    }
+  }
+  // spilled elements: recompute (hp3d_gpu_elem_bwd_batch's pipeline) from the descriptors kept at condensation time
+  if (!spl.empty()) {
+    const int m = (int)spl.size();
+    Plan *p = plan_of(c->plan);
+    if (!p) return fail(HP3D_ENOPLAN, "cloc_bwd: the store's plan %d is gone", c->plan);
+    size_t xl = 0, sl = 0;
+    for (int e : spl) { const ClocStore::Spill &sp = c->spilled.find(iel ? iel[e] : e)->second; xl = std::max(xl, sp.xnod.size()); sl = std::max(sl, sp.src.size()); }
+    std::vector<int> et(m), no(19 * (size_t)m), oe(12 * (size_t)m), of(6 * (size_t)m), nbo(m), inf(m);
+    std::vector<double> xn(xl * m, 0.0), src(sl * m, 0.0);
+    std::vector<char> xis(es * (size_t)sxi * m), xbs(es * (size_t)sxb * m);
+    for (int k = 0; k < m; k++) {
+      const int e = spl[k];
+      const ClocStore::Spill &sp = c->spilled.find(iel ? iel[e] : e)->second;
+      et[k] = sp.etype;
+      memcpy(&no[19 * (size_t)k], sp.norder, sizeof sp.norder); memcpy(&oe[12 * (size_t)k], sp.norie, sizeof sp.norie); memcpy(&of[6 * (size_t)k], sp.norif, sizeof sp.norif);
+      std::copy(sp.xnod.begin(), sp.xnod.end(), xn.begin() + xl * k);
+      std::copy(sp.src.begin(), sp.src.end(), src.begin() + sl * k);
+      memcpy(&xis[es * (size_t)sxi * k], (const char *)xi + es * sxi * e, es * sxi);
+    }
+    int rc = batch_impl(MODE_BWD, c->plan, m, et.data(), no.data(), oe.data(), of.data(), xn.data(), (int)xl, sl ? src.data() : nullptr, (long long)sl,
+                        nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, nbo.data(), inf.data(), xis.data(), sxi, xbs.data(), sxb, nullptr);
+    if (rc) return rc;
+    for (int k = 0; k < m; k++) {
+      const int e = spl[k];
+      memcpy((char *)xb + es * sxb * e, &xbs[es * (size_t)sxb * k], es * nbo[k]);
+      if (nb_out) nb_out[e] = nbo[k];
+      if (info) info[e] = inf[k];
+    }
+  }
+  return HP3D_OK;
+}
+
+int hp3d_gpu_hermitian_unpack_batch(int cplx, int nel, int ni, const int *ni_e, const void *AP, long long sAP, void *A, long long sA, int threads) {
+  if (nel < 0 || (nel > 0 && (!AP || !A)) || (!ni_e && ni < 0)) return fail(HP3D_EINVAL, "hermitian_unpack: bad argument");
+  if (AP == A) return fail(HP3D_EINVAL, "hermitian_unpack: in place is not supported");
+  const int NS = cplx ? 2 : 1;
+  // work unit = (element, block of 32 columns): column c is one contiguous run of the packed array (rows c..n-1) copied into
+  // the lower triangle, then mirrored (conjugated) into row c of the upper triangle while it is still in cache
+  std::atomic<long long> next{0};
+  int nimax = ni;
+  if (ni_e) { nimax = 0; for (int e = 0; e < nel; e++) nimax = std::max(nimax, ni_e[e]); }
+  const long long nblk = (nimax + 31) / 32, nwork = (long long)nel * nblk;
+  auto work = [&] {
+    for (;;) {
+      const long long w = next.fetch_add(1);
+      if (w >= nwork) return;
+      const int e = (int)(w / nblk), n = ni_e ? ni_e[e] : ni;
+      const int cb = (int)(w % nblk) * 32, ce = std::min(n, cb + 32);
+      const double *ap = (const double *)AP + (size_t)e * sAP * NS;
+      double *a = (double *)A + (size_t)e * sA * NS;
+      for (int c = cb; c < ce; c++) {
+        const double *src = ap + ((size_t)c * (2 * (size_t)n - c - 1) / 2 + c) * NS;   // AP index of (c,c)
+        double *col = a + ((size_t)c * n + c) * NS;
+        memcpy(col, src, sizeof(double) * NS * (n - c));
+        if (cplx) { col[1] = 0.0; for (int r = c + 1; r < n; r++) { double *u = a + ((size_t)r * n + c) * 2; u[0] = src[2 * (r - c)]; u[1] = -src[2 * (r - c) + 1]; } }
+        else for (int r = c + 1; r < n; r++) a[(size_t)r * n + c] = src[r - c];
+      }
+    }
+  };
+  unsigned nt = threads > 0 ? (unsigned)threads : std::max(1u, std::thread::hardware_concurrency());
+  nt = (unsigned)std::min<long long>(nt, std::max<long long>(1, nwork / 4));
+  std::vector<std::thread> th;
+  for (unsigned t = 1; t < nt; t++) th.emplace_back(work);
+  work();
+  for (std::thread &t : th) t.join();
+  return HP3D_OK;
 }
 
 int hp3d_gpu_quad_points(int plan, int nel, const int *etype, const int *norder, const int *norie, const int *norif,
                          const double *xnod, int xnod_ld, double *xq, long long sxq) {
   std::lock_guard<std::recursive_mutex> lk(g_mu);
-  if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
+  if (int drc = enter_device()) return drc;
   Plan *p = plan_of(plan);
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
   GeomParams gp = p->geom();
@@ -800,7 +1188,7 @@ int hp3d_gpu_quad_points(int plan, int nel, const int *etype, const int *norder,
 int hp3d_gpu_stc_bwd_batch(int cplx, int nel, int ni, int nb, const void *ASchur, long long sAS, const void *BSchur, long long sBS,
                            const void *xi, long long sxi, void *xb, long long sxb) {
   std::lock_guard<std::recursive_mutex> lk(g_mu);
-  if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
+  if (int drc = enter_device()) return drc;
   if (nel <= 0 || ni <= 0 || nb <= 0) return fail(HP3D_EINVAL, "bad sizes");
   const size_t es = sizeof(double) * (cplx ? 2 : 1);
   double *dA, *dB, *dx, *dy;
@@ -828,7 +1216,7 @@ int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, con
                      int xnod_ld, int reps, int max_chunk, int lanes, double *ms_total, double *ms_integ, double *ms_dense,
                      long long *launches) {
   std::lock_guard<std::recursive_mutex> lk(g_mu);
-  if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
+  if (int drc = enter_device()) return drc;
   Plan *p = plan_of(plan);
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
   if (nel <= 0 || reps <= 0 || lanes < 1 || lanes > LaneSet::NLANE) return fail(HP3D_EINVAL, "bad sizes");
@@ -927,7 +1315,7 @@ int hp3d_gpu_integrate_debug(int plan, const int *norder, const int *norie, cons
 int hp3d_gpu_integrate_debug_t(int plan, int etype, const int *norder, const int *norie, const int *norif, const double *xnod,
                                const void *source_qp, double *W, long long cap_doubles, int *dims) {
   std::lock_guard<std::recursive_mutex> lk(g_mu);
-  if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
+  if (int drc = enter_device()) return drc;
   Plan *p = plan_of(plan);
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
   std::string err;
@@ -959,7 +1347,7 @@ int hp3d_gpu_integrate_debug_t(int plan, int etype, const int *norder, const int
 int hp3d_gpu_dense_debug(int cplx, int nel, int n, int nb, int ni, const void *G, const void *Bm, void *Aii, void *Bi,
                          void *ASchur, void *BSchur, int *info) {
   std::lock_guard<std::recursive_mutex> lk(g_mu);
-  if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
+  if (int drc = enter_device()) return drc;
   if (nel <= 0 || n <= 0 || nb < 0 || ni <= 0) return fail(HP3D_EINVAL, "bad sizes");
   std::string err;
   int rc = cplx ? dense_debug_run<true>(nel, n, nb, ni, G, Bm, Aii, Bi, ASchur, BSchur, info, err)
@@ -987,7 +1375,7 @@ int error_impl(int plan, int nel, const int *etype, const int *norder, const int
                const void *zdof, long long szdof, const void *exact_qp, long long exact_ld, int l2proj, double *err, double *rnorm, int *info,
                double *xq, long long sxq, int *nint_out) {
   std::lock_guard<std::recursive_mutex> lk(g_mu);
-  if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
+  if (int drc = enter_device()) return drc;
   Plan *p = plan_of(plan);
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
   if (nel < 0 || (nel > 0 && (!norder || !norie || !norif || !xnod))) return fail(HP3D_EINVAL, "null argument");
@@ -1184,7 +1572,7 @@ int hp3d_gpu_pbi_h1_batch(int nel, const int *etype, const int *norder, const in
                           const double *etav, int ncomp, const double *fvert, const double *fgrad, long long fgrad_ld,
                           const unsigned *mask, double *dof, long long dof_ld, int *info) {
   std::lock_guard<std::recursive_mutex> lk(g_mu);
-  if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
+  if (int drc = enter_device()) return drc;
   if (nel < 0 || (nel > 0 && (!norder || !norie || !norif || !etav || !fvert || !fgrad || !dof))) return fail(HP3D_EINVAL, "pbi_h1: null argument");
   if (ncomp < 1 || ncomp > PBI_MAXCOMP) return fail(HP3D_EINVAL, "pbi_h1: ncomp = %d outside 1..%d (split the components over several calls)", ncomp, PBI_MAXCOMP);
   if (nel == 0) return HP3D_OK;
@@ -1309,7 +1697,7 @@ static int pbi_vec_batch(int space, int nel, const int *etype, const int *norder
                          int ncomp, const double *fval, const double *fcurl, long long f_ld, const unsigned *mask, double *dof,
                          long long dof_ld, int *info) {
   std::lock_guard<std::recursive_mutex> lk(g_mu);
-  if (g_device < 0) return fail(HP3D_ENODEV, "hp3d_gpu_init has not been called");
+  if (int drc = enter_device()) return drc;
   if (nel < 0 || (nel > 0 && (!norder || !norie || !norif || !etav || !fval || (space == PBI_HCURL && !fcurl) || !dof))) return fail(HP3D_EINVAL, "pbi_hcurl/hdiv: null argument");
   if (ncomp < 1 || ncomp > PBI_MAXCOMP) return fail(HP3D_EINVAL, "pbi_hcurl: ncomp = %d outside 1..%d (split the components over several calls)", ncomp, PBI_MAXCOMP);
   if (nel == 0) return HP3D_OK;

@@ -64,6 +64,10 @@ typedef struct hp3d_params {
   int real_reduction;    /* 1 (default): ultraweak Maxwell with real eps, mu and sigma = 0 is computed through its
                             REAL form (A = T A~ T^H, T = diag(i^k): a quarter of the flops of the reference's
                             ZPOTRF/ZTRTRS/ZHERK, same result); 0: always the general complex kernels            */
+  int aii_packed;        /* 1: Aii of the Hermitian (DPG) problems returns as its LOWER triangle in LAPACK packed
+                            column-major storage, AP(i + (j-1)(2 ni - j)/2) = A(i,j), i >= j (what ZTRTTP('L') makes of
+                            stc_fwd_herm's ZHERK('L') result, stc.F90:430-460): half the bytes over PCIe; the other
+                            triangle is its conjugate mirror (hp3d_gpu_hermitian_unpack_batch).  0 (default): full   */
 } hp3d_params;
 
 void hp3d_gpu_params_default(hp3d_params *p);
@@ -206,6 +210,49 @@ int hp3d_gpu_quad_points(int plan, int nel, const int *etype, const int *norder,
  *   xb = BSchur - ASchur * xi      for a batch of elements with identical (ni, nb). */
 int hp3d_gpu_stc_bwd_batch(int complex_mode, int nel, int ni, int nb, const void *ASchur, long long sAS,
                            const void *BSchur, long long sBS, const void *xi, long long sxi, void *xb, long long sxb);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Device-resident CLOC: stc_fwd_wrapper with STORE_STC = .true. keeps CLOC(iel)%ASchur (nb x ni) and %BSchur (nb) of every
+ * element until the back-substitution (src/modules/stc.F90:45-58,273-277); stc_bwd_wrapper (:529-677) reads them again after
+ * the global solve.  Nothing on the host looks at them in between, so they stay in HBM under the caller's element index
+ * (7.2 of the 13.0 MB an ultraweak Maxwell p=5 element produces never cross PCIe):
+ *   hp3d_gpu_cloc_create     a store for `plan`, holding at most limit_bytes of HBM (0 = 60 % of what is free now);
+ *                            returns a handle >= 0
+ *   hp3d_gpu_elem_batch_cloc hp3d_gpu_elem_batch, with the Schur factors of element e filed under iel[e] (NULL: e) instead
+ *                            of returning; an element met again (same iel) overwrites its factors.  Elements beyond the
+ *                            byte limit are SPILLED: only their descriptors are kept (on the host) and the
+ *                            back-substitution recomputes them (hp3d_gpu_elem_bwd_batch's path) -- same results
+ *   hp3d_gpu_celem_batch_cloc  likewise for the fused hp3d_gpu_celem_batch
+ *   hp3d_gpu_cloc_bwd_batch  stc_bwd for nel elements named by iel[]:  xb = BSchur - ASchur xi  (stc.F90:661-677);
+ *                            xi at xi + e*sxi scalars (ni values, order of the rows of Aii), xb likewise (nb values)
+ *   hp3d_gpu_cloc_fetch      one element's factors to the host (tests, debugging); ASchur / BSchur may be NULL;
+ *                            returns 1 if the element is spilled (nothing written), 0 if resident
+ *   hp3d_gpu_cloc_stats      stats[4] = {resident elements, spilled elements, bytes held, byte limit}
+ *   hp3d_gpu_cloc_clear      forget every element (between refinement steps); hp3d_gpu_cloc_destroy also frees the handle */
+int hp3d_gpu_cloc_create(int plan, long long limit_bytes);
+int hp3d_gpu_cloc_clear(int cloc);
+int hp3d_gpu_cloc_destroy(int cloc);
+int hp3d_gpu_cloc_stats(int cloc, long long *stats /*4*/);
+int hp3d_gpu_elem_batch_cloc(int plan, int cloc, int nel, const long long *iel, const int *etype, const int *norder,
+                             const int *norient_edge, const int *norient_face, const double *xnod, int xnod_ld,
+                             const void *source_qp, long long source_ld, void *Aii, long long sAii, void *Bi, long long sBi,
+                             int *ni_out, int *nb_out, int *info);
+int hp3d_gpu_celem_batch_cloc(int plan, int cloc, int nel, const long long *iel, const int *etype, const int *norder,
+                              const int *norient_edge, const int *norient_face, const double *xnod, int xnod_ld,
+                              const void *source_qp, long long source_ld, const long long *mptr, const long long *cptr,
+                              const int *cidx, const double *cval, const int *idbc, const void *zdofd, const long long *xptr,
+                              const int *nextract, const int *lcon, int isym_flag, const long long *aptr, void *zbload,
+                              void *zastif, int *irn, int *jcn, int *ni_out, int *nb_out, int *info);
+int hp3d_gpu_cloc_bwd_batch(int cloc, int nel, const long long *iel, const void *xi, long long sxi, void *xb, long long sxb,
+                            int *nb_out, int *info);
+int hp3d_gpu_cloc_fetch(int cloc, long long iel, void *ASchur, void *BSchur, int *ni, int *nb);
+
+/* Host only (threads = 0: all hardware threads): the full Hermitian (complex_mode) / symmetric matrices from packed lower
+ * triangles (hp3d_params.aii_packed): A(i,j) = AP(i + (j-1)(2 ni - j)/2) for i >= j, A(j,i) = conj(A(i,j)); element e reads
+ * AP + e*sAP scalars and writes A + e*sA scalars (ni x ni column-major, ni_e[e] or `ni` if ni_e == NULL).  In place is NOT
+ * supported.  This is the one host-side step the Fortran shim adds before copying into ALOC (ZTPTTR + mirror). */
+int hp3d_gpu_hermitian_unpack_batch(int complex_mode, int nel, int ni, const int *ni_e, const void *AP, long long sAP, void *A,
+                                    long long sA, int threads);
 
 /* Throughput driver used by bench.py: runs the hot path `reps` times over `nel` RESIDENT elements (geometry dofs
  * already in HBM, condensed outputs left in HBM), timed with CUDA events on the launching stream.

@@ -20,7 +20,7 @@ module hp3d_gpu
       integer(c_int) :: nord_add, maxp, test_norm
       real(c_double) :: alpha_norm, omega, eps, mu, sigma
       real(c_double) :: eps_tensor(18)
-      integer(c_int) :: source, icomp_exact, store_schur, real_reduction
+      integer(c_int) :: source, icomp_exact, store_schur, real_reduction, aii_packed
    end type
    type, bind(C) :: hp3d_physics                ! struct hp3d_physics (src/modules/physics.F90: D_TYPE, NR_COMP, ADRES, NR?VAR)
       integer(c_int) :: nphys
@@ -192,6 +192,59 @@ module hp3d_gpu
          integer(c_int) :: etype(*), norder(19,*), norient_edge(12,*), norient_face(6,*), info(*)
          real(c_double) :: etav(3,8,*), fval(f_ld,*), dof(dof_ld,*)
          type(c_ptr), value :: mask
+      end function
+!
+!  ...device-resident CLOC (stc.F90:45-58,273-277 with STORE_STC = .true.): the Schur factors stay in HBM under the element index
+!     Iel of the subdomain; stc_bwd (stc.F90:661-677) runs on them after the global solve
+      integer(c_int) function hp3d_gpu_cloc_create(plan, limit_bytes) bind(C)
+         import; integer(c_int), value :: plan; integer(c_long_long), value :: limit_bytes
+      end function
+      integer(c_int) function hp3d_gpu_cloc_clear(cloc) bind(C)
+         import; integer(c_int), value :: cloc
+      end function
+      integer(c_int) function hp3d_gpu_cloc_destroy(cloc) bind(C)
+         import; integer(c_int), value :: cloc
+      end function
+      integer(c_int) function hp3d_gpu_cloc_stats(cloc, stats) bind(C)
+         import; integer(c_int), value :: cloc; integer(c_long_long) :: stats(4)
+      end function
+      integer(c_int) function hp3d_gpu_elem_batch_cloc(plan, cloc, nel, iel, etype, norder, norient_edge, norient_face, xnod, &
+                          xnod_ld, source_qp, source_ld, Aii, sAii, Bi, sBi, ni_out, nb_out, info) bind(C)
+         import
+         integer(c_int), value :: plan, cloc, nel, xnod_ld
+         integer(c_long_long), value :: source_ld, sAii, sBi
+         integer(c_long_long) :: iel(*)
+         integer(c_int) :: etype(*), norder(19,*), norient_edge(12,*), norient_face(6,*), ni_out(*), nb_out(*), info(*)
+         real(c_double) :: xnod(xnod_ld,*)
+         type(c_ptr), value :: source_qp, Aii, Bi
+      end function
+      integer(c_int) function hp3d_gpu_celem_batch_cloc(plan, cloc, nel, iel, etype, norder, norient_edge, norient_face,      &
+                          xnod, xnod_ld, source_qp, source_ld, mptr, cptr, cidx, cval, idbc, zdofd, xptr, nextract, lcon,     &
+                          isym_flag, aptr, zbload, zastif, irn, jcn, ni_out, nb_out, info) bind(C)
+         import
+         integer(c_int), value :: plan, cloc, nel, xnod_ld, isym_flag
+         integer(c_long_long), value :: source_ld
+         integer(c_long_long) :: iel(*), mptr(*), cptr(*), xptr(*), aptr(*)
+         integer(c_int) :: etype(*), norder(19,*), norient_edge(12,*), norient_face(6,*), cidx(*), idbc(*), nextract(*), lcon(*)
+         integer(c_int) :: ni_out(*), nb_out(*), info(*)
+         real(c_double) :: xnod(xnod_ld,*), cval(*)
+         type(c_ptr), value :: source_qp, zdofd, zbload, zastif, irn, jcn
+      end function
+      integer(c_int) function hp3d_gpu_cloc_bwd_batch(cloc, nel, iel, xi, sxi, xb, sxb, nb_out, info) bind(C)
+         import
+         integer(c_int), value :: cloc, nel
+         integer(c_long_long), value :: sxi, sxb
+         integer(c_long_long) :: iel(*)
+         integer(c_int) :: nb_out(*), info(*)
+         type(c_ptr), value :: xi, xb
+      end function
+!
+!  ...full Hermitian blocks from the packed lower triangles of hp3d_params%aii_packed = 1 (host only; ZTPTTR + conjugate mirror)
+      integer(c_int) function hp3d_gpu_hermitian_unpack_batch(complex_mode, nel, ni, ni_e, AP, sAP, A, sA, threads) bind(C)
+         import
+         integer(c_int), value :: complex_mode, nel, ni, threads
+         integer(c_long_long), value :: sAP, sA
+         type(c_ptr), value :: ni_e, AP, A
       end function
    end interface
 !
