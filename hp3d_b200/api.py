@@ -223,7 +223,7 @@ class ElemEngine:
 
     def aii_len(self, ni):
         """scalars of one element's Aii block: ni^2, or ni (ni+1)/2 with aii_packed"""
-        return ni * (ni + 1) // 2 if self.prm.aii_packed else ni * ni
+        return ni * (ni + 1) // 2 if self.prm.aii_packed == 1 else ni * ni
 
     def elem_stc_batch_cloc(self, cloc, norder, norient_edge, norient_face, xnod, iel=None, source_qp=None, out=None, etype=None):
         """elem + stc_fwd_wrapper with the Schur factors filed in the device-resident store `cloc` under iel[e] (default e):

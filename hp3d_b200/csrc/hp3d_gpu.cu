@@ -5,7 +5,9 @@
 #include "pbi.cuh"
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdarg>
+#include <deque>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -62,6 +64,7 @@ int fail(int code, const char *fmt, ...) {
     if (e_ != cudaSuccess) return fail(HP3D_ENODEV, "%s: %s", #x, cudaGetErrorString(e_)); \
   } while (0)
 
+void pool_shutdown();           // host mirror threads (aii_packed = 2), defined with HostPool below
 void release_clocs(int plan);   // device-resident Schur stores of one plan (-1: all), defined with ClocStore below
 std::mutex g_plans_mu;   // the plan table and the lifetime of its entries (held briefly; never while waiting for the device)
 Plan *plan_of(int id) {
@@ -240,6 +243,7 @@ int hp3d_gpu_finalize(void) {
     g_plans.clear();
   }
   cudaDeviceSynchronize();
+  pool_shutdown();
   release_clocs(-1);
   g_lanes.release();
   g_arena.release();
@@ -271,7 +275,8 @@ int hp3d_gpu_plan(int problem_kind, const hp3d_params *prm) {
   p->fp.source = prm->source; p->fp.icomp = prm->icomp_exact - 1;
   p->store_schur = prm->store_schur;
   p->fp.real_struct = prm->real_reduction != 0;
-  p->aii_packed = prm->aii_packed != 0;
+  p->aii_packed = prm->aii_packed;
+  if (p->aii_packed < 0 || p->aii_packed > 2) { delete p; return fail(HP3D_EINVAL, "aii_packed must be 0, 1 or 2"); }
   if (p->aii_packed && problem_kind != HP3D_POIS_PDPG && problem_kind != HP3D_MAXW_UW) {
     delete p;
     return fail(HP3D_EINVAL, "aii_packed is defined for the Hermitian (DPG) problems only");
@@ -448,6 +453,89 @@ struct EventSet {   // the events of one pipeline call; destroyed on every exit 
   ~EventSet() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
 };
 
+// ------------------------------------------------------------------------------------------------
+// hp3d_params.aii_packed = 2: a Hermitian Aii crosses PCIe as the block-trapezoids of its lower triangle (block columns of
+// TRAP_W columns, rows from the block's first row down: 55 % of the matrix at ni = 600), placed by the copy engine straight
+// into their final position in the caller's full ni x ni block; the strictly-upper blocks are the conjugate transposes and are
+// written by these host threads while the device works on the next chunks.  The caller sees the full matrix, as before.
+constexpr int TRAP_W = 64;
+struct MirrorTask { double *a; int n; bool cplx; };
+static void mirror_upper(const MirrorTask &t) {
+  const int n = t.n;
+  constexpr int T = 16;
+  // source tiles: rows [R, R+T) x cols [C, C+T) strictly below the TRAP_W block diagonal; destination (C.., R..) = conj transpose
+  for (int cb = 0; cb < n; cb += TRAP_W) {
+    const int ce = std::min(n, cb + TRAP_W);
+    for (int R = ce; R < n; R += T) {
+      const int Re = std::min(n, R + T);
+      for (int C = cb; C < ce; C += T) {
+        const int Ce = std::min(ce, C + T);
+        if (t.cplx) {
+          for (int i = R; i < Re; i++) {           // destination column i, rows C..Ce (contiguous)
+            double *dst = t.a + 2 * ((size_t)i * n + C);
+            const double *src = t.a + 2 * ((size_t)C * n + i);
+            for (int j = 0; j < Ce - C; j++) { dst[2 * j] = src[2 * (size_t)j * n]; dst[2 * j + 1] = -src[2 * (size_t)j * n + 1]; }
+          }
+        } else {
+          for (int i = R; i < Re; i++) {
+            double *dst = t.a + (size_t)i * n + C;
+            const double *src = t.a + (size_t)C * n + i;
+            for (int j = 0; j < Ce - C; j++) dst[j] = src[(size_t)j * n];
+          }
+        }
+      }
+    }
+  }
+}
+struct HostPool {
+  std::vector<std::thread> th;
+  std::mutex m;
+  std::condition_variable cv, cv_done;
+  std::deque<MirrorTask> q;
+  size_t pending = 0;
+  bool stop = false;
+  void start() {
+    if (!th.empty()) return;
+    int n = 8;
+    if (const char *e = getenv("HP3D_HOST_THREADS")) n = std::max(1, atoi(e));
+    n = std::min<int>(n, std::max(1u, std::thread::hardware_concurrency()));
+    for (int i = 0; i < n; i++)
+      th.emplace_back([this] {
+        for (;;) {
+          MirrorTask t;
+          {
+            std::unique_lock<std::mutex> lk(m);
+            cv.wait(lk, [this] { return stop || !q.empty(); });
+            if (q.empty()) return;
+            t = q.front(); q.pop_front();
+          }
+          mirror_upper(t);
+          {
+            std::lock_guard<std::mutex> lk(m);
+            if (--pending == 0) cv_done.notify_all();
+          }
+        }
+      });
+  }
+  void push(const MirrorTask &t) {
+    { std::lock_guard<std::mutex> lk(m); q.push_back(t); pending++; }
+    cv.notify_one();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(m);
+    cv_done.wait(lk, [this] { return pending == 0; });
+  }
+  void shutdown() {
+    { std::lock_guard<std::mutex> lk(m); stop = true; }
+    cv.notify_all();
+    for (std::thread &t : th) t.join();
+    th.clear(); stop = false;
+  }
+  ~HostPool() { shutdown(); }
+};
+HostPool g_pool;
+void pool_shutdown() { g_pool.shutdown(); }
+
 // The chunked, multi-lane pipeline behind hp3d_gpu_elem_batch (MODE_ELEM), hp3d_gpu_elem_bwd_batch (MODE_BWD: recompute the
 // element, return only xb = BSchur - ASchur xi) and hp3d_gpu_elem_residual_batch (MODE_RESID: DPG residual per element).
 // cloc != nullptr: the Schur factors of element e go to the device-resident store under the index iel[e] (e if iel == nullptr).
@@ -471,7 +559,8 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
   if (cloc && !big) return fail(HP3D_EINVAL, "the device-resident Schur store is filled by the element / celem calls only");
   const bool to_host_schur = big && !cloc && p->store_schur && ASchur && BSchur;
   const bool want_schur = mode == MODE_BWD || to_host_schur || cloc != nullptr;
-  const bool packed = mode == MODE_ELEM && p->aii_packed;
+  const bool packed = mode == MODE_ELEM && p->aii_packed == 1;
+  const bool trap = mode == MODE_ELEM && p->aii_packed == 2;   // lower block-trapezoids over PCIe, upper triangle mirrored on the host
   std::vector<ClassGroup> classes;
   std::string err;
   if (int brc = build_classes(p, nel, etype, norder, norie, norif, true, classes, err)) return fail(brc, "%s", err.c_str());
@@ -568,6 +657,7 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
   // the last partial wave of every GEMM launch of one lane are filled by the other lanes) while results stream to the host
   // in smaller pieces.
   constexpr int NL = LaneSet::NLANE, NSLOT = 2 * NL;
+  if (trap) g_pool.start();
   cudaEvent_t evCompute[NSLOT], evCopy[NSLOT], evH2D[NL];
   EventSet events;
   for (int i = 0; i < NSLOT; i++) { CUDA_TRY(events.add(&evCompute[i])); CUDA_TRY(events.add(&evCopy[i])); }
@@ -600,7 +690,12 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
       for (size_t n : sizes) { cstart.push_back(c0); c0 += n; }
       cstart.push_back(el.size());
     }
-    int nchunk = 0;
+    int nchunk = 0, next_mirror = 0;
+    auto mirror_chunk = [&](int k) {   // aii_packed = 2: chunk k's trapezoids are on the host; hand its elements to the mirror threads
+      for (size_t i = cstart[k]; i < cstart[k + 1]; i++)
+        if (C.sig[i]->h.ni > TRAP_W) g_pool.push(MirrorTask{(double *)((char *)Aii + es * (size_t)sAii * el[i]), C.sig[i]->h.ni, NS == 2});
+      next_mirror = k + 1;
+    };
     auto collect_info = [&](int k) {   // host side of chunk k: wait for its D2H, publish info[]
       const int slot = (k % NL) * 2 + ((k / NL) & 1);
       cudaEventSynchronize(evCopy[slot]);
@@ -608,6 +703,7 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
       const int pn = (int)(cstart[k + 1] - pc0);
       const Lane &PL = g_lanes.lane[k % NL];
       const int *hi = PL.out[(k / NL) & 1].h_info;
+      if (trap) while (next_mirror <= k) mirror_chunk(next_mirror);   // the copy stream is in order: earlier chunks have landed too
       for (int i = 0; i < pn; i++) {
         const int e = el[pc0 + i];
         if (info) info[e] = hi[i];
@@ -624,6 +720,8 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
       if (big) { if (nchunk >= NSLOT) collect_info(nchunk - NSLOT); }   // this slot's previous results are on the host
       else if (nchunk >= NL) collect_info(nchunk - NL);       // small results are staged per LANE: drain before the lane is reused
       if (nchunk >= NL) cudaEventSynchronize(evH2D[ln]);        // the lane's pinned input staging has been consumed
+      if (trap)   // chunks whose copies have landed meanwhile (chunks complete in order on the copy stream)
+        while (next_mirror < nchunk && cudaEventQuery(evCopy[(next_mirror % NL) * 2 + ((next_mirror / NL) & 1)]) == cudaSuccess) mirror_chunk(next_mirror);
       const double tw1 = now();
       t_wait += tw1 - tw0;
       for (int i = 0; i < n; i++) {
@@ -711,7 +809,28 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
             cudaMemcpy2DAsync((char *)dst + es * stride * e, es * stride, src + NS * dstride * i, es * dstride, es * blk, run, cudaMemcpyDeviceToHost, g_copy);
         };
         if (mode == MODE_ELEM) {
-          copy(Aii, sAii, o.Aii, sA, packed ? (size_t)h.ni * (h.ni + 1) / 2 : (size_t)h.ni * h.ni);
+          if (trap && h.ni > TRAP_W) {
+            // block column b of every element of the run in one strided copy when both element strides are whole columns
+            const size_t nn = (size_t)h.ni, pitch = es * nn;
+            const bool whole = sA % nn == 0 && (size_t)sAii % nn == 0;
+            for (int c0 = 0; c0 < h.ni; c0 += TRAP_W) {
+              const size_t w = std::min(TRAP_W, h.ni - c0), rows = nn - c0;
+              if (whole) {
+                cudaMemcpy3DParms q;
+                memset(&q, 0, sizeof q);
+                q.srcPtr = make_cudaPitchedPtr((void *)(o.Aii + NS * sA * i), pitch, pitch, sA / nn);
+                q.dstPtr = make_cudaPitchedPtr((char *)Aii + es * (size_t)sAii * e, pitch, pitch, (size_t)sAii / nn);
+                q.srcPos = make_cudaPos(es * c0, c0, 0); q.dstPos = q.srcPos;
+                q.extent = make_cudaExtent(es * rows, w, run);
+                q.kind = cudaMemcpyDeviceToHost;
+                cudaMemcpy3DAsync(&q, g_copy);
+              } else
+                for (int k = 0; k < run; k++)
+                  cudaMemcpy2DAsync((char *)Aii + es * ((size_t)sAii * (e + k) + (size_t)c0 * nn + c0), pitch,
+                                    o.Aii + NS * (sA * (i + k) + (size_t)c0 * nn + c0), pitch, es * rows, w, cudaMemcpyDeviceToHost, g_copy);
+            }
+          } else
+            copy(Aii, sAii, o.Aii, sA, packed ? (size_t)h.ni * (h.ni + 1) / 2 : (size_t)h.ni * h.ni);
           copy(Bi, sBi, o.Bi, sB, (size_t)h.ni);
         }
         if (to_host_schur) { copy(ASchur, sAS, o.AS, sS, (size_t)h.nb * h.ni); copy(BSchur, sBS, o.BS, sT, (size_t)h.nb); }
@@ -726,6 +845,7 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
     if (ce != cudaSuccess) { rc = fail(HP3D_ENODEV, "CUDA error in elem_batch: %s", cudaGetErrorString(ce)); break; }
   }
   const double t_submitted = now();
+  if (trap) g_pool.wait();
   for (int i = 0; i < NL; i++) cudaStreamSynchronize(g_lane_stream[i]);
   const double t_computed = now();
   cudaStreamSynchronize(g_copy);

@@ -67,7 +67,12 @@ typedef struct hp3d_params {
   int aii_packed;        /* 1: Aii of the Hermitian (DPG) problems returns as its LOWER triangle in LAPACK packed
                             column-major storage, AP(i + (j-1)(2 ni - j)/2) = A(i,j), i >= j (what ZTRTTP('L') makes of
                             stc_fwd_herm's ZHERK('L') result, stc.F90:430-460): half the bytes over PCIe; the other
-                            triangle is its conjugate mirror (hp3d_gpu_hermitian_unpack_batch).  0 (default): full   */
+                            triangle is its conjugate mirror (hp3d_gpu_hermitian_unpack_batch).
+                            2: the caller still receives the FULL ni x ni block, but only the lower triangle crosses
+                            PCIe (as 64-column block trapezoids the copy engine places at their final position, 55 % of
+                            the bytes at ni = 600); the upper blocks are mirrored by the library's host threads
+                            (HP3D_HOST_THREADS, default 8) while the device works on the next chunks.
+                            0 (default): the full block crosses PCIe                                              */
 } hp3d_params;
 
 void hp3d_gpu_params_default(hp3d_params *p);

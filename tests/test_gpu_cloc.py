@@ -60,13 +60,16 @@ def test_cloc_spill_recomputes(oracle, gpu, kind):
     """a store too small for the batch: the first elements are resident, the rest spilled and recomputed by stc_bwd -- same xb"""
     from hp3d_b200.api import ElemEngine
     oracle.set_maxp(8)
-    rng = np.random.default_rng(150 + kind)
-    items, et, norder, norie, norif, X = _batch(oracle, rng, nel=6)
     om = 2 * np.pi if kind == 4 else 1.0
     eng = ElemEngine(kind, omega=om, maxp=8)
-    ref = eng.elem_stc_batch(norder, norie, norif, X, etype=et)
     es = 16 if kind >= 3 else 8
-    need = [es * int(ref["nb"][e]) * (int(ref["ni"][e]) + 1) for e in range(6)]
+    for seed in range(150, 170):   # a batch in which at least two elements have bubbles (low-order H1 elements have none)
+        rng = np.random.default_rng(seed + kind)
+        items, et, norder, norie, norif, X = _batch(oracle, rng, nel=6, pmax=4)
+        ref = eng.elem_stc_batch(norder, norie, norif, X, etype=et)
+        need = [es * int(ref["nb"][e]) * (int(ref["ni"][e]) + 1) for e in range(6)]
+        if sum(1 for v in need if v > 0) >= 2:
+            break
     j = max(e for e in range(6) if need[e] > 0)   # the last element that needs room does not get it: it and everything after it spills
     assert j >= 1
     cl = eng.cloc_create(limit_bytes=sum(need[:j]) + 512 + 8)
@@ -147,4 +150,38 @@ def test_short_strides_are_refused(oracle, gpu):
     eng = ElemEngine(2, maxp=8, source=9)
     with pytest.raises(RuntimeError, match="source_ld"):
         eng.elem_stc_batch(norder, norie, norif, X, etype=et, source_qp=np.zeros((2, 1)))
+    eng.close()
+
+
+@pytest.mark.parametrize("kind,rr,uniform", [(2, 1, False), (4, 1, False), (4, 0, False), (4, 1, True), (2, 1, True)])
+def test_aii_lower_trapezoids_mirrored_on_host(oracle, gpu, kind, rr, uniform):
+    """aii_packed = 2: the caller's FULL Aii blocks, bit for bit what aii_packed = 0 returns, although only the lower block
+    trapezoids crossed PCIe (output pre-filled with NaN: every entry must have been written by the copy or by the mirror threads).
+    uniform: equal sizes and whole-column strides (one strided 3-D copy per block column); else per-element 2-D copies."""
+    from hp3d_b200.api import ElemEngine
+    from tests.util import hexa_xnod, uniform_order
+    oracle.set_maxp(8)
+    rng = np.random.default_rng(180 + kind)
+    if uniform:
+        nel, p = 7, (4 if kind == 2 else 3)
+        no = uniform_order(p)
+        norder = np.tile(no, (nel, 1)); norie = np.zeros((nel, 12), np.int32); norif = np.zeros((nel, 6), np.int32)
+        X = np.stack([hexa_xnod(oracle.celndof(no, oracle.MDLB)[0], h=0.4, jitter=0.1, rng=rng) for _ in range(nel)])
+        et = None
+    else:
+        items, et, norder, norie, norif, X = _batch(oracle, rng, nel=7, pmax=4)
+        nel = 7
+    om = 2 * np.pi if kind == 4 else 1.0
+    full = ElemEngine(kind, omega=om, maxp=8, real_reduction=rr)
+    ref = full.elem_stc_batch(norder, norie, norif, X, etype=et)
+    full.close()
+    assert int(ref["ni"].max()) > 64   # otherwise the trapezoid path is not exercised
+    eng = ElemEngine(kind, omega=om, maxp=8, real_reduction=rr, aii_packed=2)
+    out = {k: np.full_like(v, np.nan) for k, v in ref.items() if k in ("Aii", "Bi", "ASchur", "BSchur")}
+    res = eng.elem_stc_batch(norder, norie, norif, X, etype=et, out=out)
+    assert (res["info"] == 0).all()
+    for e in range(nel):
+        n, nb = int(ref["ni"][e]), int(ref["nb"][e])
+        assert np.array_equal(res["Aii"][e, :n * n], ref["Aii"][e, :n * n])
+        assert np.array_equal(res["Bi"][e, :n], ref["Bi"][e, :n]) and np.array_equal(res["ASchur"][e, :n * nb], ref["ASchur"][e, :n * nb])
     eng.close()
