@@ -30,7 +30,7 @@ EXPORTS = [
     "hp3d_gpu_elem_error_batch", "hp3d_gpu_error_points", "hp3d_gpu_chunk_plan_debug",
     "hp3d_gpu_pbi_points", "hp3d_gpu_pbi_h1_batch", "hp3d_gpu_pbi_hcurl_points", "hp3d_gpu_pbi_hcurl_batch", "hp3d_gpu_pbi_hdiv_points", "hp3d_gpu_pbi_hdiv_batch", "hp3d_gpu_pbi_cache_limit",
     "hp3d_gpu_cloc_create", "hp3d_gpu_cloc_clear", "hp3d_gpu_cloc_destroy", "hp3d_gpu_cloc_stats", "hp3d_gpu_elem_batch_cloc",
-    "hp3d_gpu_celem_batch_cloc", "hp3d_gpu_cloc_bwd_batch", "hp3d_gpu_cloc_fetch", "hp3d_gpu_hermitian_unpack_batch",
+    "hp3d_gpu_celem_batch_cloc", "hp3d_gpu_cloc_bwd_batch", "hp3d_gpu_cloc_fetch", "hp3d_gpu_hermitian_unpack_batch", "hp3d_gpu_fp64_peak_probe",
 ]
 
 

@@ -6,6 +6,11 @@
 
 #include <atomic>
 #include <condition_variable>
+#include <cstdint>
+#include <sched.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <cstdarg>
 #include <deque>
 #include <chrono>
@@ -463,6 +468,8 @@ struct MirrorTask { double *a; int n; bool cplx; };
 static void mirror_upper(const MirrorTask &t) {
   const int n = t.n;
   constexpr int T = 16;
+  const bool nt = t.cplx && ((uintptr_t)t.a & 15) == 0;
+  (void)nt;
   // source tiles: rows [R, R+T) x cols [C, C+T) strictly below the TRAP_W block diagonal; destination (C.., R..) = conj transpose
   for (int cb = 0; cb < n; cb += TRAP_W) {
     const int ce = std::min(n, cb + TRAP_W);
@@ -474,6 +481,13 @@ static void mirror_upper(const MirrorTask &t) {
           for (int i = R; i < Re; i++) {           // destination column i, rows C..Ce (contiguous)
             double *dst = t.a + 2 * ((size_t)i * n + C);
             const double *src = t.a + 2 * ((size_t)C * n + i);
+#if defined(__SSE2__)
+            if (nt) {   // streaming stores: the upper triangle is written once and not read here (no read-for-ownership traffic)
+              const __m128d conj = _mm_set_pd(-0.0, 0.0);
+              for (int j = 0; j < Ce - C; j++) _mm_stream_pd(dst + 2 * j, _mm_xor_pd(_mm_loadu_pd(src + 2 * (size_t)j * n), conj));
+              continue;
+            }
+#endif
             for (int j = 0; j < Ce - C; j++) { dst[2 * j] = src[2 * (size_t)j * n]; dst[2 * j + 1] = -src[2 * (size_t)j * n + 1]; }
           }
         } else {
@@ -486,6 +500,9 @@ static void mirror_upper(const MirrorTask &t) {
       }
     }
   }
+#if defined(__SSE2__)
+  if (nt) _mm_sfence();
+#endif
 }
 struct HostPool {
   std::vector<std::thread> th;
@@ -496,9 +513,12 @@ struct HostPool {
   bool stop = false;
   void start() {
     if (!th.empty()) return;
+    // default: the CPUs this process may run on (MPI ranks are usually bound to their share of the node), at most 8, one left
+    // for the submitting thread
     int n = 8;
+    cpu_set_t cs;
+    if (sched_getaffinity(0, sizeof cs, &cs) == 0) n = std::min(8, std::max(1, CPU_COUNT(&cs) - 1));
     if (const char *e = getenv("HP3D_HOST_THREADS")) n = std::max(1, atoi(e));
-    n = std::min<int>(n, std::max(1u, std::thread::hardware_concurrency()));
     for (int i = 0; i < n; i++)
       th.emplace_back([this] {
         for (;;) {
@@ -1324,6 +1344,53 @@ int hp3d_gpu_stc_bwd_batch(int cplx, int nel, int ni, int nb, const void *ASchur
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpy2D(xb, es * sxb, dy, es * nb, es * nb, nel, cudaMemcpyDeviceToHost));
   cudaFree(dA); cudaFree(dB); cudaFree(dx); cudaFree(dy);
+  return HP3D_OK;
+}
+
+// ---- FP64 tensor-pipe probe: the roofline denominator bench.py reports against, measured on the device the run uses
+namespace {
+__global__ void __launch_bounds__(256) dmma_rate_kernel(double *out, int iters, double seed) {
+  // 8 independent m8n8k4 accumulator tiles per warp cover the pipe latency; nothing but DMMA in the loop
+  double acc[8][2], a[8], b[4];
+  for (int i = 0; i < 8; i++) { acc[i][0] = seed * i; acc[i][1] = seed * (i + 1); a[i] = seed + threadIdx.x * 1e-9 * i; }
+  for (int i = 0; i < 4; i++) b[i] = seed * 0.5 + i * 1e-9;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) dmma884(acc[i][0], acc[i][1], a[i], b[i & 3]);
+  }
+  double sum = 0;
+  for (int i = 0; i < 8; i++) sum += acc[i][0] + acc[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = sum;
+}
+}  // namespace
+
+int hp3d_gpu_fp64_peak_probe(double *tflops, double *ms_best) {
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  if (int drc = enter_device()) return drc;
+  if (!tflops) return fail(HP3D_EINVAL, "null argument");
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, g_device));
+  const int grid = prop.multiProcessorCount * 2, iters = 40000;
+  double *out = nullptr;
+  CUDA_TRY(cudaMalloc(&out, sizeof(double) * grid * 256));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  dmma_rate_kernel<<<grid, 256, 0, g_compute>>>(out, 2000, 1.0);
+  float best = 1e30f;
+  for (int r = 0; r < 4; r++) {
+    cudaEventRecord(e0, g_compute);
+    dmma_rate_kernel<<<grid, 256, 0, g_compute>>>(out, iters, 1.0);
+    cudaEventRecord(e1, g_compute);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  CUDA_TRY(cudaGetLastError());
+  *tflops = (double)grid * 8 /*warps*/ * iters * 8.0 /*mma per iteration*/ * (2.0 * 8 * 8 * 4) / (best * 1e-3) / 1e12;
+  if (ms_best) *ms_best = best;
   return HP3D_OK;
 }
 

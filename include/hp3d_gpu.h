@@ -65,13 +65,13 @@ typedef struct hp3d_params {
                             REAL form (A = T A~ T^H, T = diag(i^k): a quarter of the flops of the reference's
                             ZPOTRF/ZTRTRS/ZHERK, same result); 0: always the general complex kernels            */
   int aii_packed;        /* 1: Aii of the Hermitian (DPG) problems returns as its LOWER triangle in LAPACK packed
-                            column-major storage, AP(i + (j-1)(2 ni - j)/2) = A(i,j), i >= j (what ZTRTTP('L') makes of
-                            stc_fwd_herm's ZHERK('L') result, stc.F90:430-460): half the bytes over PCIe; the other
+                            column-major storage, AP(i + (j-1)(2 ni - j)/2) = A(i,j), i >= j (ZTRTTP('L') of the Hermitian
+                            Aii stc_fwd_herm returns, stc.F90:407-414): half the bytes over PCIe; the other
                             triangle is its conjugate mirror (hp3d_gpu_hermitian_unpack_batch).
                             2: the caller still receives the FULL ni x ni block, but only the lower triangle crosses
                             PCIe (as 64-column block trapezoids the copy engine places at their final position, 55 % of
                             the bytes at ni = 600); the upper blocks are mirrored by the library's host threads
-                            (HP3D_HOST_THREADS, default 8) while the device works on the next chunks.
+                            (HP3D_HOST_THREADS; default: the CPUs the process is bound to minus one, at most 8) while the device works on the next chunks.
                             0 (default): the full block crosses PCIe                                              */
 } hp3d_params;
 
@@ -274,6 +274,10 @@ int hp3d_gpu_bench(int plan, int nel, const int *norder, const int *norient_edge
 int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, const int *norient_edge, const int *norient_face,
                      const double *xnod, int xnod_ld, int reps, int max_chunk, int lanes, double *ms_total, double *ms_integ,
                      double *ms_dense, long long *launches);
+
+/* FP64 tensor-pipe (DMMA, mma.sync m8n8k4 f64) issue-rate probe on the current device: the measured roofline denominator
+ * of the dense phase (about 0.1 s; tflops = 2*8*8*4 flops per warp instruction / best of four timed launches). */
+int hp3d_gpu_fp64_peak_probe(double *tflops, double *ms_best);
 
 /* Page-locked host memory for the caller's result arrays (so that the D2H copies of hp3d_gpu_elem_batch are
  * asynchronous DMA transfers that overlap the next chunk's kernels).  Pageable buffers work too, only slower. */
