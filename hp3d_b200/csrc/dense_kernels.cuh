@@ -37,6 +37,14 @@ struct GemmArgs {
   int diag_shift;
   int use_cin;    // 0: C = alpha*S ; 1: C = Cin + alpha*S
   double alpha;
+  // work that is known to be zero or unused is skipped per WARP (each warp owns a 32x32 quadrant of the CTA tile):
+  int rows_valid, cols_valid;  // rows / columns of this launch (from its origin) that carry data, multiples of 32; 0: all.
+                               // Quadrants beyond them are padding: not computed, written as zeros when use_cin == 0
+  int diag_first;  // the first row tile of the launch is a diagonal tile of a Hermitian matrix whose upper triangle is never
+                   // read (Cholesky panel update): its upper-right quadrant is neither computed nor written.  The same holds
+                   // for the diagonal tiles of a lower_only launch (blockIdx.y == blockIdx.x + diag_shift)
+  int tri;         // K == TILE products with a triangular B: 1 lower (B(j,k) = 0 for k > j: quadrants wn == 0 stop at k = 32),
+                   // 2 upper (B(j,k) = 0 for k < j: quadrants wn == 1 start at k = 32)
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
@@ -72,8 +80,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, CPLX ? 2 : 4) gemm_nc_kernel(con
 
   const double *Ag = g.A.re + (long long)e * g.A.batch + (long long)ti * TILE * g.A.ld;
   const double *Bg = g.B.re + (long long)e * g.B.batch + (long long)tj * TILE * g.B.ld;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // quadrant of this warp, rotated from CTA to CTA: a warp sits on the SM sub-partition (warp id mod 4) and each sub-partition has
+  // its own DMMA pipe, so the quadrants that are skipped below (padding, unread triangle) must not always be the same warps --
+  // otherwise two sub-partitions idle while the other two still carry the full load and nothing is gained
+  const int warp = ((tid >> 5) + ti + tj + e) & 3;
   const int wm = warp >> 1, wn = warp & 1, gq = lane >> 2, tq = lane & 3;
+  const bool pad_q = (g.rows_valid && ti * TILE + 32 * wm >= g.rows_valid) || (g.cols_valid && tj * TILE + 32 * wn >= g.cols_valid);
+  const bool diag_q = wm == 0 && wn == 1 && ((g.lower_only && tj == ti + g.diag_shift) || (g.diag_first && ti == 0));
+  const bool act = !pad_q && !diag_q;   // warp-uniform
 
   double cr[4][4][2], ci[4][4][2];
 #pragma unroll
@@ -106,6 +121,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, CPLX ? 2 : 4) gemm_nc_kernel(con
     cp_async_wait<NSTAGE - 2>();
     __syncthreads();
     if (kc + NSTAGE - 1 < nk) load_stage((kc + NSTAGE - 1) % NSTAGE, (kc + NSTAGE - 1) * KC); else cp_async_commit();
+    if (!act || (g.tri == 1 && wn == 0 && kc * KC >= 32) || (g.tri == 2 && wn == 1 && kc * KC < 32)) continue;
     const double *Ar = sm(st, 0, 0) + (32 * wm + gq) * LDS_K + tq;
     const double *Br = sm(st, 1, 0) + (32 * wn + gq) * LDS_K + tq;
     const double *Ai = CPLX ? sm(st, 0, 1) + (32 * wm + gq) * LDS_K + tq : nullptr;
@@ -134,6 +150,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, CPLX ? 2 : 4) gemm_nc_kernel(con
   }
 
   // epilogue: C = [Cin] + alpha*S ; each thread owns (row = 32wm+8m+gq, cols 32wn+8n+2tq, +1)
+  if (diag_q || (pad_q && g.use_cin)) return;   // never read / stays as it is (zero padding)
   const long long crow0 = (long long)ti * TILE, ccol0 = (long long)tj * TILE;
   double *Co = g.Cout.re + (long long)e * g.Cout.batch;
   const double *Cn = g.use_cin ? g.Cin.re + (long long)e * g.Cin.batch : nullptr;

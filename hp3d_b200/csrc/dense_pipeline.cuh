@@ -7,11 +7,14 @@
 // signed permutation back to the reference dof ordering happens in the output kernel (formats.cuh).
 #pragma once
 #include "dense_kernels.cuh"
+#include <algorithm>
 #include <cstdio>
 
 namespace hp3d {
 
 inline int pad64(int n) { return (n + TILE - 1) / TILE * TILE; }
+inline int pad32(int n) { return (n + 31) / 32 * 32; }
+inline int pad16(int n) { return (n + 15) / 16 * 16; }
 
 struct DenseDims {
   bool cplx = true;
@@ -23,12 +26,16 @@ struct DenseDims {
   int nload = 1;       // load rows: the last `nload` padded interface rows
   int n = 0;           // test dofs (rows of the Gram)
   int nb = 0, ni = 0;  // bubble / interface trial dofs
-  int np = 0, nbp = 0, nip = 0;  // padded: np=pad64(n), nbp=pad64(nb), nip=pad64(ni+1); the load sits at interface index nip-1
+  int np = 0, nbp = 0, nip = 0;  // padded LAYOUT extents: np=pad64(n), nbp=pad64(nb), nip=pad64(nil)
+  int nil = 0;                   // interface rows that carry data: the load sits at interface index nil-nload.  pad32(ni+nload) for the
+                                 // Cholesky pipeline (the GEMM skips the 32-row quadrants beyond it), pad64 for the pivoted-LU kernel
   // A batch may mix elements with different n / nb / ni as long as the PADDED extents agree ("dense class"): the kernels
   // below only use np/nbp/nip plus the per-element counts in DenseBuffers::ni_e / nb_e; n, nb, ni here are the class maxima.
   __host__ __device__ int M() const { return nbp + nip; }
   __host__ __device__ int R() const { return np + nbp + nip; }
-  void finish() { np = dpg ? pad64(n) : 0; nbp = pad64(nb); nip = pad64(ni + nload); }
+  __host__ __device__ int Mv() const { return nbp + nil; }        // rows / columns of A that carry data
+  __host__ __device__ int Rv() const { return np + nbp + nil; }   // rows of W that carry data
+  void finish() { np = dpg ? pad64(n) : 0; nbp = pad64(nb); nil = dpg ? pad32(ni + nload) : pad64(ni + nload); nip = pad64(nil); }
   // doubles per element
   __host__ __device__ size_t planes() const { return cplx ? 2 : 1; }
   __host__ __device__ size_t w_plane() const { return (size_t)R() * np; }
@@ -74,7 +81,7 @@ template <bool CPLX> static cudaError_t dense_configure() {
 // If LinvKeep != nullptr the inverted diagonal blocks are stored per step (stride keep_step doubles).
 template <bool CPLX>
 static void chol_trapezoid(double *Mbase, long long plane, long long batch_stride, int ld, int nrow, int ncol, int batch,
-                           double *Linv, double *LinvH, long long linv_batch, long long linv_step, int *info, cudaStream_t st) {
+                           double *Linv, double *LinvH, long long linv_batch, long long linv_step, int *info, cudaStream_t st, int nrow_valid) {
   const int nt_r = nrow / TILE, nt_c = ncol / TILE;
   const long long lp = (long long)TILE * TILE;
   for (int j = 0; j < nt_c; j++) {
@@ -85,6 +92,7 @@ static void chol_trapezoid(double *Mbase, long long plane, long long batch_strid
       g.B = MatRef{Mbase + (long long)j * TILE * ld, plane, batch_stride, ld};
       g.Cin = Dj; g.Cout = Dj;
       g.K = j * TILE; g.lower_only = 0; g.diag_shift = 0; g.use_cin = 1; g.alpha = -1.0;
+      g.rows_valid = nrow_valid - j * TILE; g.diag_first = 1;
       launch_gemm<CPLX>(g, nt_r - j, 1, batch, st);
     }
     MatRef Li{Linv + j * linv_step, lp, linv_batch, TILE}, LiH{LinvH + j * linv_step, lp, linv_batch, TILE};
@@ -95,6 +103,7 @@ static void chol_trapezoid(double *Mbase, long long plane, long long batch_strid
       MatRef Pj{Mbase + (long long)(j + 1) * TILE * ld + (long long)j * TILE, plane, batch_stride, ld};
       g.A = Pj; g.B = Li; g.Cin = Pj; g.Cout = Pj;
       g.K = TILE; g.use_cin = 0; g.alpha = 1.0;
+      g.rows_valid = nrow_valid - (j + 1) * TILE; g.tri = 1;   // Linv is lower triangular
       launch_gemm<CPLX>(g, nt_r - j - 1, 1, batch, st);
     }
   }
@@ -110,13 +119,14 @@ static void dense_phase(const DenseDims &d, const DenseBuffers &b, int batch, cu
   const int M = d.M();
   if (d.dpg) {
     const long long wpl = (long long)d.w_plane();
-    chol_trapezoid<CPLX>(b.W, wpl, P * wpl, d.np, d.R(), d.np, batch, b.Linv, b.LinvH, P * lp, 0, b.info, st);
+    chol_trapezoid<CPLX>(b.W, wpl, P * wpl, d.np, d.R(), d.np, batch, b.Linv, b.LinvH, P * lp, 0, b.info, st, d.Rv());
     // A = B~^H (B~^H)^H  (lower tiles only)
     GemmArgs g{};
     MatRef Bt{b.W + (long long)d.np * d.np, wpl, P * wpl, d.np};
     g.A = Bt; g.B = Bt;
     g.Cout = MatRef{b.Am, (long long)d.a_plane(), P * (long long)d.a_plane(), M}; g.Cin = g.Cout;
-    g.K = d.np; g.lower_only = 1; g.diag_shift = 0; g.use_cin = 0; g.alpha = 1.0;
+    g.K = std::min(d.np, pad16(d.n)); g.lower_only = 1; g.diag_shift = 0; g.use_cin = 0; g.alpha = 1.0;   // columns >= n of B~^H are zero
+    g.rows_valid = d.Mv(); g.cols_valid = d.Mv();
     launch_gemm<CPLX>(g, M / TILE, M / TILE, batch, st);
   }
   if (d.nb == 0 || normal_eq_only) return;
@@ -127,13 +137,14 @@ static void dense_phase(const DenseDims &d, const DenseBuffers &b, int batch, cu
   }
   const int ns = d.nsteps_stc();
   // A_bb = L L^H ; rows below become Y~ = A_ib L^-H (and the load row y_b^H)
-  chol_trapezoid<CPLX>(b.Am, apl, ab, M, M, d.nbp, batch, b.LinvS, b.LinvSH, (long long)ns * P * lp, P * lp, b.info, st);
+  chol_trapezoid<CPLX>(b.Am, apl, ab, M, M, d.nbp, batch, b.LinvS, b.LinvSH, (long long)ns * P * lp, P * lp, b.info, st, d.Mv());
   {  // Schur complement: S = A_ii - Y~ Y~^H (lower tiles)
     GemmArgs g{};
     MatRef Y{b.Am + (long long)d.nbp * M, apl, ab, M};
     MatRef S{b.Am + (long long)d.nbp * M + d.nbp, apl, ab, M};
     g.A = Y; g.B = Y; g.Cin = S; g.Cout = S;
     g.K = d.nbp; g.lower_only = 1; g.use_cin = 1; g.alpha = -1.0;
+    g.rows_valid = d.nil; g.cols_valid = d.nil;
     launch_gemm<CPLX>(g, d.nip / TILE, d.nip / TILE, batch, st);
   }
   if (!want_z) return;   // the Schur factors are not wanted (STORE_STC off): the condensed system is complete
@@ -151,11 +162,13 @@ static void dense_phase(const DenseDims &d, const DenseBuffers &b, int batch, cu
       g.B = MatRef{b.LH + (long long)j * TILE * d.nbp + (long long)(j + 1) * TILE, (long long)d.lh_plane(), P * (long long)d.lh_plane(), d.nbp};
       g.Cin = Zj; g.Cout = Zj;
       g.K = d.nbp - (j + 1) * TILE; g.use_cin = 1; g.alpha = -1.0;
+      g.rows_valid = d.nil;
       launch_gemm<CPLX>(g, d.nip / TILE, 1, batch, st);
     }
     GemmArgs g{};
     g.A = Zj; g.B = MatRef{b.LinvSH + (long long)j * P * lp, lp, (long long)ns * P * lp, TILE};
     g.Cin = Zj; g.Cout = Zj; g.K = TILE; g.use_cin = 0; g.alpha = 1.0;
+    g.rows_valid = d.nil; g.tri = 2;   // B = Linv^H: upper triangular
     launch_gemm<CPLX>(g, d.nip / TILE, 1, batch, st);
   }
 }

@@ -161,7 +161,7 @@ struct ChunkShape {
   void absorb(const SigHost &h) {
     if (d.np == 0 && d.nip == 0) { d = h.dims; gen_stc = h.gen_stc; }
     d.n = std::max(d.n, h.dims.n); d.nb = std::max(d.nb, h.nb); d.ni = std::max(d.ni, h.ni);
-    d.nip = std::max(d.nip, h.dims.nip);   // classes merged across nip (Cholesky path): every element keeps its own row layout (nip_e)
+    d.nip = std::max(d.nip, h.dims.nip); d.nil = std::max(d.nil, h.dims.nil);   // classes merged across nip (Cholesky path): every element keeps its own row layout (nip_e)
     nint_max = std::max(nint_max, h.nint); nH_max = std::max(nH_max, h.nH);
     src_max = std::max(src_max, (size_t)h.nint * (h.cplx ? 6 : 1));
   }
@@ -567,7 +567,7 @@ int dense_debug_run(int nel, int n, int nb, int ni, const void *Gv, const void *
         else if (r == c) Wr[(size_t)r * d.np + c] = 1.0;
       }
     for (size_t c = 0; c < m1; c++) {
-      size_t row = d.np + (c < (size_t)nb ? c : (c < (size_t)nb + ni ? d.nbp + (c - nb) : (size_t)d.nbp + d.nip - 1));
+      size_t row = d.np + (c < (size_t)nb ? c : (c < (size_t)nb + ni ? d.nbp + (c - nb) : (size_t)d.nbp + d.nil - 1));
       for (int k = 0; k < n; k++) {
         T v = Be[(size_t)k + (size_t)n * c];
         Wr[row * d.np + k] = re(v); if (CPLX) Wi[row * d.np + k] = -im(v);

@@ -31,7 +31,7 @@ __global__ void scatter_condensed_kernel(DenseDims d, const double *Am, OutMaps 
   const int *pi = mp.perm_i + (long long)e * mp.perm_stride_i;
   const double *si = mp.sgn_i + (long long)e * mp.sgn_stride_i;
   constexpr int NS = CPLX ? 2 : 1;
-  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, lrow = (mp.nip_e ? mp.nip_e[e] : d.nip) - 1;
+  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, lrow = (mp.nip_e ? mp.nip_e[e] : d.nil) - 1;
   if (r < ni && c < ni && (!packed || r >= c)) {
     int ir = pi[r], ic = pi[c];
     double s = si[r] * si[c];
@@ -62,7 +62,7 @@ __global__ void scatter_schur_kernel(DenseDims d, const double *Am, OutMaps mp, 
   const int *pi = mp.perm_i + (long long)e * mp.perm_stride_i, *pb = mp.perm_b + (long long)e * mp.perm_stride_b;
   const double *si = mp.sgn_i + (long long)e * mp.sgn_stride_i, *sb = mp.sgn_b + (long long)e * mp.sgn_stride_b;
   constexpr int NS = CPLX ? 2 : 1;
-  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, nb = mp.nb_e ? mp.nb_e[e] : d.nb, lrow = (mp.nip_e ? mp.nip_e[e] : d.nip) - 1;
+  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, nb = mp.nb_e ? mp.nb_e[e] : d.nb, lrow = (mp.nip_e ? mp.nip_e[e] : d.nil) - 1;
   if (bq < nb && iq < ni) {
     int ib = pb[bq], ii = pi[iq];
     double s = sb[bq] * si[iq];
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) dpg_residual_kernel(DenseDims d, const do
     double r = 0.0, im = 0.0;
     if (i < nb) { r = xb[((long long)e * sxb + i) * NS]; if (CPLX) im = xb[((long long)e * sxb + i) * NS + 1]; }
     else if (i >= d.nbp && i < d.nbp + ni) { const int k = i - d.nbp; r = xi[((long long)e * sxi + k) * NS]; if (CPLX) im = xi[((long long)e * sxi + k) * NS + 1]; }
-    else if (i == d.nbp + (nip_e ? nip_e[e] : d.nip) - 1) r = -1.0;   // the element's load row
+    else if (i == d.nbp + (nip_e ? nip_e[e] : d.nil) - 1) r = -1.0;   // the element's load row
     vr[i] = r; vi[i] = im;
   }
   __syncthreads();
@@ -193,7 +193,7 @@ __global__ void scatter_condensed_rs_kernel(DenseDims d, const double *Am, OutMa
   const int r = blockIdx.x * 16 + threadIdx.x, c = blockIdx.y * 16 + threadIdx.y;
   const int M = d.M();
   const double *S = Am + (long long)e * (long long)d.a_plane() + (long long)d.nbp * M + d.nbp;
-  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, lrow = (mp.nip_e ? mp.nip_e[e] : d.nip) - 2;
+  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, lrow = (mp.nip_e ? mp.nip_e[e] : d.nil) - 2;
   if (r < ni && c < ni && (!packed || r >= c)) {
     const int a = r >= c ? r : c, b = r >= c ? c : r;
     double re, im;
@@ -216,7 +216,7 @@ __global__ void scatter_schur_rs_kernel(DenseDims d, const double *Am, OutMaps m
   const int bq = blockIdx.x * 16 + threadIdx.x, iq = blockIdx.y * 16 + threadIdx.y;
   const int M = d.M();
   const double *Z = Am + (long long)e * (long long)d.a_plane() + (long long)d.nbp * M;
-  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, nb = mp.nb_e ? mp.nb_e[e] : d.nb, lrow = (mp.nip_e ? mp.nip_e[e] : d.nip) - 2;
+  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, nb = mp.nb_e ? mp.nb_e[e] : d.nb, lrow = (mp.nip_e ? mp.nip_e[e] : d.nil) - 2;
   if (bq < nb && iq < ni) {
     double re, im;
     rs_apply(Z[(long long)iq * M + bq], rs_phase_b(bq), rs_phase_i(iq), re, im);
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(256) dpg_residual_rs_kernel(DenseDims d, const
   __shared__ double red[8];
   const int e = blockIdx.x, M = d.M(), tid = threadIdx.x;
   const double *A = Am + (long long)e * (long long)d.a_plane();
-  const int ni = ni_e[e], nb = nb_e[e], l0 = d.nbp + (nip_e ? nip_e[e] : d.nip) - 2;   // the element's two load rows
+  const int ni = ni_e[e], nb = nb_e[e], l0 = d.nbp + (nip_e ? nip_e[e] : d.nil) - 2;   // the element's two load rows
   double *v1 = sv, *v2 = sv + M;
   for (int i = tid; i < M; i += blockDim.x) {
     double ur = 0.0, ui = 0.0;

@@ -253,7 +253,7 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
     const bool rs = rs_applicable(P);
     D.cplx = !rs; D.rs = rs; D.nload = rs ? 2 : 1; D.dpg = true; D.n = S.ntest; D.nb = S.nb; D.ni = S.ni; D.finish();
     if (sizes_only) return true;
-    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nip - D.nload;   // load row(s): last padded interface rows, independent of ni
+    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nil - D.nload;   // load row(s): last padded interface rows, independent of ni
     const std::complex<double> za = I * P.omega * P.eps, zc = I * P.omega * P.mu;
     const double aF = (P.test_norm == 2) ? 1.0 : P.alpha_norm + std::norm(za);
     const double aG = (P.test_norm == 2) ? 1.0 : P.alpha_norm + std::norm(zc);
@@ -368,7 +368,7 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
     DenseDims &D = S.dims;
     D.cplx = false; D.dpg = true; D.n = nHH; D.nb = S.nb; D.ni = S.ni; D.finish();
     if (sizes_only) return true;
-    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nip - 1;   // load row: last (padded) interface row, independent of ni
+    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nil - 1;   // load row: last (padded) interface row, independent of ni
     const int mapU = add_grid_map(S, hd, -1, ng, [&](int k) { return k < iH ? rowI + k : rowB + (k - iH); });
     {  // Gram (v,q) + (grad v, grad q)
       BlockBuilder b(S, ft, ft, channel(0, 0, 0, 0), no_channel());
@@ -429,7 +429,7 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
       b.finish();
     }
     {
-      BlockBuilder b(S, unit, fu, channel(1, 0, D.nbp + D.nip - 1, 0, -1, mapU), no_channel());
+      BlockBuilder b(S, unit, fu, channel(1, 0, D.nbp + D.nil - 1, 0, -1, mapU), no_channel());
       b.add(-1, -1, F_SRC, 1.0, 1.0, 0.0);
       b.finish();
     }
@@ -465,7 +465,7 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
         b.finish();
       }
     for (int a = 0; a < 3; a++) {  // load as a COLUMN (the LU condensation eliminates rows)
-      BlockBuilder b(S, fe[a], unit, channel(1, 0, 0, D.nbp + D.nip - D.nload, mapE[a]), rsg ? channel(1, 0, 0, D.nbp + D.nip - 1, mapE[a]) : channel(1, 1, 0, D.nbp + D.nip - 1, mapE[a]));
+      BlockBuilder b(S, fe[a], unit, channel(1, 0, 0, D.nbp + D.nil - D.nload, mapE[a]), rsg ? channel(1, 0, 0, D.nbp + D.nil - 1, mapE[a]) : channel(1, 1, 0, D.nbp + D.nil - 1, mapE[a]));
       b.add(-1, -1, F_SRC + 2 * a, 1.0, 1.0, 0.0);
       b.add(-1, -1, F_SRC + 2 * a + 1, 1.0, 0.0, 1.0);
       b.finish();

@@ -211,7 +211,7 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
     const bool rs = rs_applicable(P);   // real-structured dense phase (forms.hpp)
     D.cplx = !rs; D.rs = rs; D.nload = rs ? 2 : 1; D.dpg = true; D.n = S.ntest; D.nb = S.nb; D.ni = S.ni; D.finish();
     if (sizes_only) return true;
-    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nip - D.nload;   // load row(s): last padded interface rows, independent of ni
+    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nil - D.nload;   // load row(s): last padded interface rows, independent of ni
     const std::complex<double> za = I * P.omega * P.eps, zc = I * P.omega * P.mu;
     const double aF = (P.test_norm == 2) ? 1.0 : P.alpha_norm + std::norm(za);
     const double aG = (P.test_norm == 2) ? 1.0 : P.alpha_norm + std::norm(zc);
@@ -322,7 +322,7 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
       b.finish();
     }
     {
-      BlockBuilder b(S, unit.id, fu.id, channel(1, 0, D.nbp + D.nip - 1, 0, -1, mapU), no_channel());
+      BlockBuilder b(S, unit.id, fu.id, channel(1, 0, D.nbp + D.nil - 1, 0, -1, mapU), no_channel());
       b.addp(0, 0, 0, 0, F_SRC, 1.0, 1.0, 0.0);
       b.finish();
     }
@@ -353,7 +353,7 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
       }
     for (int a = 0; a < 2; a++) {
       if (fe[a].nT == 0) continue;
-      BlockBuilder b(S, fe[a].id, unit.id, channel(1, 0, 0, D.nbp + D.nip - D.nload, mapE[a]), rsg ? channel(1, 0, 0, D.nbp + D.nip - 1, mapE[a]) : channel(1, 1, 0, D.nbp + D.nip - 1, mapE[a]));
+      BlockBuilder b(S, fe[a].id, unit.id, channel(1, 0, 0, D.nbp + D.nil - D.nload, mapE[a]), rsg ? channel(1, 0, 0, D.nbp + D.nil - 1, mapE[a]) : channel(1, 1, 0, D.nbp + D.nil - 1, mapE[a]));
       for (int d = 0; d < 3; d++) {
         const CompRef v = pf_val(fe[a].kind, d);
         if (v.tc < 0) continue;
@@ -375,7 +375,7 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
     DenseDims &D = S.dims;
     D.cplx = false; D.dpg = true; D.n = nHH; D.nb = S.nb; D.ni = S.ni; D.finish();
     if (sizes_only) return true;
-    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nip - 1;   // load row: last (padded) interface row, independent of ni
+    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nil - 1;   // load row: last (padded) interface row, independent of ni
     const int mapU = add_pgrid_map(S, hd, 0, fu, [&](int k) { return k < iH ? rowI + k : rowB + (k - iH); });
     {
       BlockBuilder b(S, ft.id, ft.id, channel(0, 0, 0, 0), no_channel());

@@ -750,7 +750,7 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
         memcpy(L.h_xnod + (size_t)i * nx, xnod + (size_t)e * xnod_ld, sizeof(double) * 3 * h.nH);
         if (gp.source == HP3D_SRC_TABLE)
           memcpy(L.h_src + (size_t)i * nsrc, (const double *)source_qp + (size_t)e * source_ld, sizeof(double) * h.nint * (h.cplx ? 6 : 1));
-        L.h_cnt[i] = h.ni; L.h_cnt[lcap + i] = h.nb; L.h_cnt[2 * lcap + i] = h.dims.nip;
+        L.h_cnt[i] = h.ni; L.h_cnt[lcap + i] = h.nb; L.h_cnt[2 * lcap + i] = h.dims.nil;
         if (mode == MODE_CELEM) L.h_cel[i] = e;
         if (!big) {
           memcpy(L.h_xi + NS * sB * i, (const char *)xi + es * sxi * e, es * h.ni);
@@ -1427,7 +1427,7 @@ int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, con
     std::vector<int> hc(3 * n);
     for (size_t i = 0; i < n; i++) {
       memcpy(hx.data() + i * nx, xnod + (size_t)C.el[i] * xnod_ld, sizeof(double) * 3 * C.sig[i]->h.nH);
-      hc[i] = C.sig[i]->h.ni; hc[n + i] = C.sig[i]->h.nb; hc[2 * n + i] = C.sig[i]->h.dims.nip;
+      hc[i] = C.sig[i]->h.ni; hc[n + i] = C.sig[i]->h.nb; hc[2 * n + i] = C.sig[i]->h.dims.nil;
     }
     double *dx; int *dc;
     CUDA_TRY(cudaMalloc(&dx, sizeof(double) * hx.size()));
@@ -1514,7 +1514,7 @@ int hp3d_gpu_integrate_debug_t(int plan, int etype, const int *norder, const int
   const DenseDims &d = h.dims;
   const size_t P = d.planes();
   const size_t need = P * (d.dpg ? d.w_plane() : d.a_plane());
-  if (dims) { dims[0] = d.np; dims[1] = d.nbp; dims[2] = d.nip; dims[3] = d.n; dims[4] = d.nb; dims[5] = d.ni; dims[6] = d.dpg ? d.R() : d.M(); dims[7] = (int)P; }
+  if (dims) { dims[0] = d.np; dims[1] = d.nbp; dims[2] = d.nil;   /* interface rows that carry data: the load rows end at nbp + dims[2] */ dims[3] = d.n; dims[4] = d.nb; dims[5] = d.ni; dims[6] = d.dpg ? d.R() : d.M(); dims[7] = (int)P; }
   if (!W) return HP3D_OK;
   if ((size_t)cap_doubles < need) return fail(HP3D_EINVAL, "integrate_debug: need %zu doubles", need);
   Lane &L = g_lanes.lane[0];

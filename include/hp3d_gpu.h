@@ -359,7 +359,8 @@ int hp3d_gpu_tables_1d(int p, int nq, double *x, double *w, double *H, double *d
 
 /* Test hook: integrate ONE element of a DPG plan and return the dense phase's raw input buffer W
  * (planes x R x np doubles, row-major, see hp3d_b200/csrc/dense_pipeline.cuh) with dims[8] =
- * {np, nbp, nip, n, nb, ni, R, planes}.  For non-DPG plans the buffer is Am (planes x M x M), dims[0] = 0. */
+ * {np, nbp, nip, n, nb, ni, R, planes}; nip = the interface rows that carry data (a multiple of 32; the load rows are the last
+ * of them), R = np + nbp + pad64(nip).  For non-DPG plans the buffer is Am (planes x M x M), dims[0] = 0. */
 int hp3d_gpu_integrate_debug(int plan, const int *norder, const int *norient_edge, const int *norient_face,
                              const double *xnod, const void *source_qp, double *W, long long cap_doubles, int *dims);
 
