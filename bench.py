@@ -276,7 +276,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--elements", type=int, default=256, help="elements per GPU per step")
+    ap.add_argument("--elements", type=int, default=512, help="elements per GPU per step (two lane chunks of half that size: 256-element launches fill the GPU for 10-20 waves)")
     ap.add_argument("--e2e-elements", type=int, default=0, help="elements per GPU per end-to-end step (a subdomain slice; default 1024)")
     ap.add_argument("--complex-kernels", action="store_true", help="force the general complex dense phase (hp3d_params.real_reduction = 0), the reference's ZPOTRF/ZTRTRS/ZHERK sequence")
     ap.add_argument("--p", type=int, default=5)

@@ -37,12 +37,13 @@ struct GemmArgs {
   int diag_shift;
   int use_cin;    // 0: C = alpha*S ; 1: C = Cin + alpha*S
   double alpha;
-  // work that is known to be zero or unused is skipped per WARP (each warp owns a 32x32 quadrant of the CTA tile):
+  // work that is known to be zero or unused is dropped per CTA (see gemm_nc_kernel):
   int rows_valid, cols_valid;  // rows / columns of this launch (from its origin) that carry data, multiples of 32; 0: all.
-                               // Quadrants beyond them are padding: not computed, written as zeros when use_cin == 0
+                               // The 32 rows / columns beyond them in the last tile are padding: not computed, written as zeros
+                               // when use_cin == 0
   int diag_first;  // the first row tile of the launch is a diagonal tile of a Hermitian matrix whose upper triangle is never
-                   // read (Cholesky panel update): its upper-right quadrant is neither computed nor written.  The same holds
-                   // for the diagonal tiles of a lower_only launch (blockIdx.y == blockIdx.x + diag_shift)
+                   // read (Cholesky panel update): only the 8x8 tiles on or below its diagonal are computed and written.  The
+                   // same holds for the diagonal tiles of a lower_only launch (blockIdx.y == blockIdx.x + diag_shift)
   int tri;         // K == TILE products with a triangular B: 1 lower (B(j,k) = 0 for k > j: quadrants wn == 0 stop at k = 32),
                    // 2 upper (B(j,k) = 0 for k < j: quadrants wn == 1 start at k = 32)
 };
@@ -65,7 +66,14 @@ template <bool CPLX> __host__ __device__ constexpr int gemm_stages() { return 2;
 // k-chunk per pipeline stage (32 for the real kernel was measured: 3 CTAs/SM instead of 4, dense 95.3 vs 91.4 ms: worse)
 template <bool CPLX> __host__ __device__ constexpr int gemm_kc() { return 16; }
 
-// One 64x64 output tile per CTA, 4 warps (2x2), each warp a 32x32 sub-tile = 4x4 DMMA tiles.
+// One 64x64 output tile per CTA, 4 warps.  Work that is known to be zero or never read is dropped per CTA (dropping it per
+// warp gains nothing: the warps of a CTA meet at a barrier every k-chunk, so the CTA is as slow as its busiest warp):
+//   FULL      2x2 warps, each a 32x32 quadrant = 4x4 DMMA tiles
+//   half rows / half columns (last tile of a padded-to-32 extent): the valid 32 rows (columns) are split over the warps,
+//             16 per warp: 2x4 (4x2, 2x2) DMMA tiles per warp, half (a quarter of) the work
+//   DIAG      diagonal tile of a Hermitian result of which only the lower triangle is read (Cholesky panel update, HERK,
+//             Schur update): the 36 of 64 DMMA tiles on or below the diagonal; warp w owns the 8-row strips w and 7-w
+//             (w+1 and 8-w tiles: 9 per warp)
 // grid = (row tiles, col tiles, batch)
 template <bool CPLX>
 __global__ void __launch_bounds__(GEMM_THREADS, CPLX ? 2 : 4) gemm_nc_kernel(const GemmArgs g) {
@@ -80,15 +88,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, CPLX ? 2 : 4) gemm_nc_kernel(con
 
   const double *Ag = g.A.re + (long long)e * g.A.batch + (long long)ti * TILE * g.A.ld;
   const double *Bg = g.B.re + (long long)e * g.B.batch + (long long)tj * TILE * g.B.ld;
-  const int tid = threadIdx.x, lane = tid & 31;
-  // quadrant of this warp, rotated from CTA to CTA: a warp sits on the SM sub-partition (warp id mod 4) and each sub-partition has
-  // its own DMMA pipe, so the quadrants that are skipped below (padding, unread triangle) must not always be the same warps --
-  // otherwise two sub-partitions idle while the other two still carry the full load and nothing is gained
-  const int warp = ((tid >> 5) + ti + tj + e) & 3;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp >> 1, wn = warp & 1, gq = lane >> 2, tq = lane & 3;
-  const bool pad_q = (g.rows_valid && ti * TILE + 32 * wm >= g.rows_valid) || (g.cols_valid && tj * TILE + 32 * wn >= g.cols_valid);
-  const bool diag_q = wm == 0 && wn == 1 && ((g.lower_only && tj == ti + g.diag_shift) || (g.diag_first && ti == 0));
-  const bool act = !pad_q && !diag_q;   // warp-uniform
+  // CTA-uniform shape of the work
+  const bool diag = (g.lower_only && tj == ti + g.diag_shift) || (g.diag_first && ti == 0);
+  const bool half_r = !diag && g.rows_valid && ti * TILE + 32 >= g.rows_valid;
+  const bool half_c = !diag && g.cols_valid && tj * TILE + 32 >= g.cols_valid;
+  const int rbase = half_r ? 16 * wm : 32 * wm, cbase = half_c ? 16 * wn : 32 * wn;   // first row / column of the warp (not DIAG)
+  const int mcnt = half_r ? 2 : 4, ncnt = half_c ? 2 : 4;
+  const int sA_ = warp, sB_ = 7 - warp;   // DIAG: the warp's two 8-row strips
 
   double cr[4][4][2], ci[4][4][2];
 #pragma unroll
@@ -110,6 +118,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, CPLX ? 2 : 4) gemm_nc_kernel(con
     }
     cp_async_commit();
   };
+  // one complex (or real) 8x8x4 tile product: c += a * conj(b)
+  auto cmma = [&](double (&xr)[2], double (&xi)[2], double ar, double ai, double br, double bi) {
+    dmma884(xr[0], xr[1], ar, br);
+    if (CPLX) {
+      dmma884(xr[0], xr[1], ai, bi);          // + Ai*Bi   (conj(B) flips the sign of Bi)
+      dmma884(xi[0], xi[1], ai, br);          // + Ai*Br
+      dmma884(xi[0], xi[1], dneg(ar), bi);    // - Ar*Bi
+    }
+  };
 
   // NSTAGE-deep cp.async pipeline, one barrier per k-chunk: at the top of iteration kc the group of chunk kc has landed
   // (NSTAGE-2 younger groups may still be in flight) and every warp has finished chunk kc-1, whose buffer the next load reuses.
@@ -121,54 +138,107 @@ __global__ void __launch_bounds__(GEMM_THREADS, CPLX ? 2 : 4) gemm_nc_kernel(con
     cp_async_wait<NSTAGE - 2>();
     __syncthreads();
     if (kc + NSTAGE - 1 < nk) load_stage((kc + NSTAGE - 1) % NSTAGE, (kc + NSTAGE - 1) * KC); else cp_async_commit();
-    if (!act || (g.tri == 1 && wn == 0 && kc * KC >= 32) || (g.tri == 2 && wn == 1 && kc * KC < 32)) continue;
-    const double *Ar = sm(st, 0, 0) + (32 * wm + gq) * LDS_K + tq;
-    const double *Br = sm(st, 1, 0) + (32 * wn + gq) * LDS_K + tq;
-    const double *Ai = CPLX ? sm(st, 0, 1) + (32 * wm + gq) * LDS_K + tq : nullptr;
-    const double *Bi = CPLX ? sm(st, 1, 1) + (32 * wn + gq) * LDS_K + tq : nullptr;
+    if ((g.tri == 1 && wn == 0 && kc * KC >= 32) || (g.tri == 2 && wn == 1 && kc * KC < 32)) continue;   // triangular B: zero half
+    const double *As0 = sm(st, 0, 0) + gq * LDS_K + tq, *Bs0 = sm(st, 1, 0) + gq * LDS_K + tq;
+    const double *As1 = CPLX ? sm(st, 0, 1) + gq * LDS_K + tq : nullptr, *Bs1 = CPLX ? sm(st, 1, 1) + gq * LDS_K + tq : nullptr;
+    if (diag) {
 #pragma unroll
-    for (int k4 = 0; k4 < KC / 4; k4++) {
-      double ar[4], ai[4], br[4], bi[4];
+      for (int k4 = 0; k4 < KC / 4; k4++) {
+        const double a0r = As0[8 * sA_ * LDS_K + k4 * 4], a1r = As0[8 * sB_ * LDS_K + k4 * 4];
+        const double a0i = CPLX ? As1[8 * sA_ * LDS_K + k4 * 4] : 0.0, a1i = CPLX ? As1[8 * sB_ * LDS_K + k4 * 4] : 0.0;
 #pragma unroll
-      for (int m = 0; m < 4; m++) {
-        ar[m] = Ar[m * 8 * LDS_K + k4 * 4];
-        br[m] = Br[m * 8 * LDS_K + k4 * 4];
-        if (CPLX) { ai[m] = Ai[m * 8 * LDS_K + k4 * 4]; bi[m] = Bi[m * 8 * LDS_K + k4 * 4]; }
-      }
-#pragma unroll
-      for (int m = 0; m < 4; m++)
-#pragma unroll
-        for (int n = 0; n < 4; n++) {
-          dmma884(cr[m][n][0], cr[m][n][1], ar[m], br[n]);
-          if (CPLX) {
-            dmma884(cr[m][n][0], cr[m][n][1], ai[m], bi[n]);   // + Ai*Bi   (conj(B) flips the sign of Bi)
-            dmma884(ci[m][n][0], ci[m][n][1], ai[m], br[n]);   // + Ai*Br
-            dmma884(ci[m][n][0], ci[m][n][1], dneg(ar[m]), bi[n]); // - Ar*Bi
+        for (int n = 0; n < 8; n++) {
+          if (n <= sB_) {
+            const double br = Bs0[8 * n * LDS_K + k4 * 4], bi = CPLX ? Bs1[8 * n * LDS_K + k4 * 4] : 0.0;
+            if (n < 4) { if (n <= sA_) cmma(cr[0][n], ci[0][n], a0r, a0i, br, bi); }
+            if (n < 4) cmma(cr[1][n], ci[1][n], a1r, a1i, br, bi);
+            else cmma(cr[2][n - 4], ci[2][n - 4], a1r, a1i, br, bi);
           }
         }
+      }
+    } else if (mcnt == 4 && ncnt == 4) {
+      const double *Ar = As0 + rbase * LDS_K, *Br = Bs0 + cbase * LDS_K;
+      const double *Ai = CPLX ? As1 + rbase * LDS_K : nullptr, *Bi = CPLX ? Bs1 + cbase * LDS_K : nullptr;
+#pragma unroll
+      for (int k4 = 0; k4 < KC / 4; k4++) {
+        double ar[4], ai[4], br[4], bi[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          ar[m] = Ar[m * 8 * LDS_K + k4 * 4];
+          br[m] = Br[m * 8 * LDS_K + k4 * 4];
+          if (CPLX) { ai[m] = Ai[m * 8 * LDS_K + k4 * 4]; bi[m] = Bi[m * 8 * LDS_K + k4 * 4]; } else { ai[m] = 0.0; bi[m] = 0.0; }
+        }
+#pragma unroll
+        for (int m = 0; m < 4; m++)
+#pragma unroll
+          for (int n = 0; n < 4; n++) cmma(cr[m][n], ci[m][n], ar[m], ai[m], br[n], bi[n]);
+      }
+    } else {   // half tiles: 2 (of 4) DMMA tiles per warp along the halved direction(s)
+      const double *Ar = As0 + rbase * LDS_K, *Br = Bs0 + cbase * LDS_K;
+      const double *Ai = CPLX ? As1 + rbase * LDS_K : nullptr, *Bi = CPLX ? Bs1 + cbase * LDS_K : nullptr;
+#pragma unroll
+      for (int k4 = 0; k4 < KC / 4; k4++) {
+        double ar[4], ai[4], br[4], bi[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          ar[m] = m < mcnt ? Ar[m * 8 * LDS_K + k4 * 4] : 0.0;
+          br[m] = m < ncnt ? Br[m * 8 * LDS_K + k4 * 4] : 0.0;
+          ai[m] = (CPLX && m < mcnt) ? Ai[m * 8 * LDS_K + k4 * 4] : 0.0;
+          bi[m] = (CPLX && m < ncnt) ? Bi[m * 8 * LDS_K + k4 * 4] : 0.0;
+        }
+#pragma unroll
+        for (int m = 0; m < 4; m++)
+#pragma unroll
+          for (int n = 0; n < 4; n++)
+            if (m < mcnt && n < ncnt) cmma(cr[m][n], ci[m][n], ar[m], ai[m], br[n], bi[n]);
+      }
     }
   }
 
-  // epilogue: C = [Cin] + alpha*S ; each thread owns (row = 32wm+8m+gq, cols 32wn+8n+2tq, +1)
-  if (diag_q || (pad_q && g.use_cin)) return;   // never read / stays as it is (zero padding)
+  // epilogue: C = [Cin] + alpha*S ; a thread owns entries (row r, cols c, c+1) of each of its DMMA tiles
   const long long crow0 = (long long)ti * TILE, ccol0 = (long long)tj * TILE;
   double *Co = g.Cout.re + (long long)e * g.Cout.batch;
   const double *Cn = g.use_cin ? g.Cin.re + (long long)e * g.Cin.batch : nullptr;
+  auto store = [&](int rt, int ct, const double (&xr)[2], const double (&xi)[2]) {   // rt, ct: row / column of the 8x8 tile inside the CTA tile
+    const long long r = crow0 + rt + gq, c = ccol0 + ct + 2 * tq;
+    double2 vr = make_double2(g.alpha * xr[0], g.alpha * xr[1]);
+    double2 vi = make_double2(g.alpha * xi[0], g.alpha * xi[1]);
+    if (g.use_cin) {
+      double2 o = *reinterpret_cast<const double2 *>(Cn + r * g.Cin.ld + c);
+      vr.x += o.x; vr.y += o.y;
+      if (CPLX) { double2 oi = *reinterpret_cast<const double2 *>(Cn + g.Cin.im_off + r * g.Cin.ld + c); vi.x += oi.x; vi.y += oi.y; }
+    }
+    *reinterpret_cast<double2 *>(Co + r * g.Cout.ld + c) = vr;
+    if (CPLX) *reinterpret_cast<double2 *>(Co + g.Cout.im_off + r * g.Cout.ld + c) = vi;
+  };
+  if (diag) {
+#pragma unroll
+    for (int n = 0; n < 8; n++) {
+      if (n <= sB_) {
+        if (n < 4) { if (n <= sA_) store(8 * sA_, 8 * n, cr[0][n], ci[0][n]); }
+        if (n < 4) store(8 * sB_, 8 * n, cr[1][n], ci[1][n]);
+        else store(8 * sB_, 8 * n, cr[2][n - 4], ci[2][n - 4]);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int m = 0; m < 4; m++)
 #pragma unroll
-    for (int n = 0; n < 4; n++) {
-      long long r = crow0 + 32 * wm + 8 * m + gq, c = ccol0 + 32 * wn + 8 * n + 2 * tq;
-      double2 vr = make_double2(g.alpha * cr[m][n][0], g.alpha * cr[m][n][1]);
-      double2 vi = make_double2(g.alpha * ci[m][n][0], g.alpha * ci[m][n][1]);
-      if (g.use_cin) {
-        double2 o = *reinterpret_cast<const double2 *>(Cn + r * g.Cin.ld + c);
-        vr.x += o.x; vr.y += o.y;
-        if (CPLX) { double2 oi = *reinterpret_cast<const double2 *>(Cn + g.Cin.im_off + r * g.Cin.ld + c); vi.x += oi.x; vi.y += oi.y; }
+    for (int n = 0; n < 4; n++)
+      if (m < mcnt && n < ncnt) store(rbase + 8 * m, cbase + 8 * n, cr[m][n], ci[m][n]);
+  // the padding half of a half tile is not computed: it stays as it is (zero) when the result is accumulated in place,
+  // and is written as zeros when the launch creates the matrix
+  if (!g.use_cin && (half_r || half_c)) {
+    const double2 z = make_double2(0.0, 0.0);
+    for (int idx = tid; idx < TILE * TILE / 2; idx += GEMM_THREADS) {
+      const int r = idx / (TILE / 2), c = (idx % (TILE / 2)) * 2;
+      if ((half_r && r >= 32) || (half_c && c >= 32)) {
+        *reinterpret_cast<double2 *>(Co + (crow0 + r) * g.Cout.ld + ccol0 + c) = z;
+        if (CPLX) *reinterpret_cast<double2 *>(Co + g.Cout.im_off + (crow0 + r) * g.Cout.ld + ccol0 + c) = z;
       }
-      *reinterpret_cast<double2 *>(Co + r * g.Cout.ld + c) = vr;
-      if (CPLX) *reinterpret_cast<double2 *>(Co + g.Cout.im_off + r * g.Cout.ld + c) = vi;
     }
+  }
 }
 
 // pivots per block and dynamic shared memory of stc_gen_kernel for padded extent M

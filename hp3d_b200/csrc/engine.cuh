@@ -277,7 +277,7 @@ template <int NMAX> static cudaError_t tp2_configure() {
 }
 static void launch_tp3(const Signature &S, const Tp3Args &A, int nel, cudaStream_t st) {
   dim3 grid((unsigned)S.h.work.size(), nel);
-  const int off = (int)S.h.smem_u_off, offF = (int)S.h.smem_f_off, offT1 = (int)S.h.smem_t1_off;
+  const int off = (int)S.h.smem_u_off, offF = (int)S.h.smem_f_off, offT1 = (int)S.h.smem_t1_off, offQ = (int)S.h.smem_q_off;
   if (S.h.etype == 3) {   // prism: (triangle list) x (z table) families
     switch (S.h.nmax) {
       case 4: tp2_kernel<4><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, S.d_ttab, off); break;
@@ -289,10 +289,10 @@ static void launch_tp3(const Signature &S, const Tp3Args &A, int nel, cudaStream
     return;
   }
   switch (S.h.nmax) {
-    case 4: tp3_kernel<4><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, offF, offT1, off); break;
-    case 6: tp3_kernel<6><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, offF, offT1, off); break;
-    case 8: tp3_kernel<8><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, offF, offT1, off); break;
-    default: tp3_kernel<10><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, offF, offT1, off); break;
+    case 4: tp3_kernel<4><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, offF, offT1, off, offQ); break;
+    case 6: tp3_kernel<6><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, offF, offT1, off, offQ); break;
+    case 8: tp3_kernel<8><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, offF, offT1, off, offQ); break;
+    default: tp3_kernel<10><<<grid, S.h.threads, S.h.smem_bytes, st>>>(A, offF, offT1, off, offQ); break;
   }
   g_launches++;
 }
@@ -306,7 +306,7 @@ static void run_integration(const ChunkShape &sh, Lane &L, const GeomParams &gp,
   const DenseDims &d = sh.d;
   const long long P = d.cplx ? 2 : 1;
   cudaMemsetAsync(L.ws.b.info, 0, sizeof(int) * nel, st);
-  if (d.dpg) cudaMemsetAsync(L.ws.b.W, 0, sizeof(double) * P * d.w_plane() * nel, st);
+  if (d.dpg) { dim3 g((d.R() + 15) / 16, (unsigned)(nel * P)); zero_w_kernel<<<g, 256, 0, st>>>(L.ws.b.W, (long long)d.w_plane(), d.R(), d.np); g_launches++; }
   else cudaMemsetAsync(L.ws.b.Am, 0, sizeof(double) * P * d.a_plane() * nel, st);
   size_t wf_off = 0;
   for (const Seg &sg_ : segs) {

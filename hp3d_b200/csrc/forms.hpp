@@ -68,6 +68,7 @@ struct SigHost {
   int nmax = 4, threads = 64;
   size_t smem_u_off = 0, smem_bytes = 0;
   size_t smem_f_off = 0, smem_t1_off = 0;   // hexahedron kernel: weight-field staging and x-contracted terms
+  size_t smem_q_off = 0;                    // hexahedron kernel: y-factor products of the terms, double-buffered
   std::string err;
 };
 
@@ -115,6 +116,8 @@ struct BlockBuilder {
   }
   void finish() {
     if (B.nt == 0) { S.slot.resize(B.s0); return; }
+    // the kernels walk the terms slot by slot
+    std::stable_sort(S.term.begin() + B.t0, S.term.begin() + B.t0 + B.nt, [](const TermDesc &a, const TermDesc &b) { return a.slot < b.slot; });
     const int bi = (int)S.block.size();
     S.block.push_back(B);
     const FamilyDesc &fa = S.fam[B.famA];
@@ -475,24 +478,34 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
     return false;
   }
   // ---- launch geometry of the tp3 kernel
-  int items = 1, nm = 1, ntmax = 1;
-  size_t t1 = 0, u = 0;
+  int items = 1, nm = 1, ntmax = 1, nMmax = 1;
   for (const BlockDesc &B : S.block) {
     const FamilyDesc &fa = S.fam[B.famA], &fb = S.fam[B.famB];
-    t1 = std::max(t1, (size_t)B.nt * fb.n[0] * S.nq[1] * S.nq[2]);
-    u = std::max(u, (size_t)B.ns * fb.n[0] * fb.n[1]);   // x NMAX rows below
-    items = std::max(items, fa.n[2] * fb.n[0] * fb.n[1]);
-    nm = std::max(nm, std::max(fb.n[2], S.nq[2]));
+    items = std::max(items, S.nq[2] * fb.n[0] * fb.n[1]);   // y contraction: one thread per (qz, iB, jB)
+    nm = std::max(nm, std::max(std::max(fa.n[2], fb.n[2]), std::max(S.nq[1], S.nq[2])));
     ntmax = std::max(ntmax, B.nt);
+    if (B.ns > 5) { S.err = "a block of the form has more than 5 z-slots (TP_SMAX)"; return false; }
   }
   S.nmax = nm <= 4 ? 4 : nm <= 6 ? 6 : nm <= 8 ? 8 : 10;
-  S.threads = std::min(384, std::max(64, (items + 31) / 32 * 32));
-  // dynamic smem of tp3_kernel: tables | Z | F [ntmax][fs] | T1 | U [ns][NMAX][nij]  (all offsets even: 16-byte aligned for the TMA bulk copies)
-  u *= S.nmax;
+  size_t t1 = 0, u = 0, q = 0;
+  for (const BlockDesc &B : S.block) {
+    const FamilyDesc &fa = S.fam[B.famA], &fb = S.fam[B.famB];
+    t1 = std::max(t1, (size_t)B.nt * fb.n[0] * S.nq[2] * (S.nmax + 2));   // T1 [t][qz][iB][qy padded to NMAX+2]
+    u = std::max(u, (size_t)B.ns * fb.n[0] * fb.n[1] * S.nmax);          // U [ns][NMAX][nij]
+    q = std::max(q, (size_t)B.nt * fb.n[1] * (S.nmax + 2));              // Q [t][jB][qy padded]
+    nMmax = std::max(nMmax, fa.n[2] * ((S.nmax + 7) / 8));               // m-tiles of the z contraction
+  }
+  // CTA size: one thread per y-contraction item, rounded up to whole warps and then to a multiple of the m-tile count of the
+  // z contraction (every warp owns one m-tile there), at most 448
+  int warps = (std::max(64, items) + 31) / 32;
+  if (nMmax <= 14) warps = std::min(14 / nMmax * nMmax, (warps + nMmax - 1) / nMmax * nMmax);
+  S.threads = 32 * std::max(2, std::min(14, warps));
+  // dynamic smem of tp3_kernel: tables | Z | F [ntmax][fs] | T1 | U | Q [2][...]  (all offsets even: 16-byte aligned for the TMA bulk copies)
   S.smem_f_off = (size_t)12 * TABSZ + (size_t)4 * S.nmax * S.nmax;   // tables | z tables re-laid out [4][NMAX][NMAX]
   S.smem_t1_off = S.smem_f_off + (size_t)ntmax * wf_stride(S.nint);
   S.smem_u_off = S.smem_t1_off + ((t1 + 1) & ~(size_t)1);
-  S.smem_bytes = (S.smem_u_off + u) * sizeof(double);
+  S.smem_q_off = S.smem_u_off + ((u + 1) & ~(size_t)1);
+  S.smem_bytes = (S.smem_q_off + 2 * q) * sizeof(double);
   if (S.smem_bytes > 200 * 1024) { S.err = "integration kernel needs more than 200 KB of shared memory"; return false; }
   return true;
 }

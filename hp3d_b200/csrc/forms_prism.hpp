@@ -429,7 +429,8 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
     const FamilyDesc &fa = S.fam[B.famA], &fb = S.fam[B.famB];
     u = std::max(u, (size_t)B.ns * fb.n[0]);   // x NMAX rows below
     items = std::max(items, std::max(fa.n[2], nqz) * fb.n[0]);
-    nm = std::max(nm, std::max(fb.n[2], nqz));
+    nm = std::max(nm, std::max(std::max(fa.n[2], fb.n[2]), nqz));
+    if (B.ns > 5) { S.err = "a block of the form has more than 5 z-slots (TP_SMAX)"; return false; }
   }
   S.nmax = nm <= 4 ? 4 : nm <= 6 ? 6 : nm <= 8 ? 8 : 10;
   S.threads = std::min(384, std::max(64, (items + 31) / 32 * 32));

@@ -23,6 +23,10 @@
 
 namespace hp3d {
 
+__device__ __forceinline__ void dmma_tile(double &c0, double &c1, double a, double b) {   // 8x8x4 FP64 tensor-core tile product
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
 constexpr int MAXQ = 10;           // points / functions per axis (Gauss table limit of the reference)
 constexpr int TABSZ = MAXQ * MAXQ; // one 1-D table
 enum TabType { T_H = 0, T_DH = 1, T_Q = 2, T_ONE = 3 };
@@ -268,51 +272,117 @@ __device__ __forceinline__ void build_ztab(const double *sTabZ, double *sZ, int 
     sZ[i] = (q < nqz && r * nqz + q < TABSZ) ? sTabZ[type * TABSZ + r * nqz + q] : 0.0;
   }
 }
+// z contraction on the FP64 tensor pipe.  For one (iA,jA) [hexahedron] / tA [prism] and every slot s
+//   D_s[(kA,kB)][ij] = sum_qz (ZA_s[kA][qz] ZB_s[kB][qz]) U_s[qz][ij]
+// is a small matrix product (M = nAz*nBz rows, K = nqz, N = nij columns): DMMA m8n8k4 tiles with the A fragment
+// a = ZA[kA][qz] * ZB[kB][qz] built in registers once per CTA (it depends on the block only: Stage2Frag), the B fragment read
+// from the y-contracted sums U in shared memory, and the two output channels formed from D_s with the slot's coefficients.
+// An m-tile is one kA and eight kB; a warp owns ONE m-tile (the warps sharing an m-tile split its n-tiles; the host sizes the
+// CTA as a multiple of the m-tile count).  Rows kB >= nBz and columns ij >= nij of a tile are computed and dropped.
+constexpr int TP_SMAX = 5;   // slots whose A fragments a thread keeps in registers; forms with more slots per block are refused
+template <int NMAX> struct Stage2Frag {
+  static constexpr int KS = (NMAX + 3) / 4, TB = (NMAX + 7) / 8;
+  double a[TP_SMAX][KS];
+  int mt, part, nsplit;   // m-tile of the warp (-1: none), its share of the n-tiles
+};
 template <int NMAX>
-__device__ __forceinline__ void tp_stage2(const Tp3Args &A, const BlockDesc &B, const double *sZ, const double *sU, int e, int nij, int nBz, int nAz,
-                                          int lA0, int strideA) {
-  const ChannelDesc c0 = B.ch[0], c1 = B.ch[1];
-  for (int it = threadIdx.x; it < nAz * nij; it += blockDim.x) {
-    const int ij = it % nij, kA = it / nij;
-    double acc0[NMAX], acc1[NMAX];
+__device__ __forceinline__ void tp_stage2_prepare(const Tp3Args &A, const BlockDesc &B, const double *sZ, int nAz, Stage2Frag<NMAX> &F) {
+  constexpr int KS = Stage2Frag<NMAX>::KS, TB = Stage2Frag<NMAX>::TB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3, nwarp = blockDim.x >> 5;
+  const int nM = nAz * TB;
+  // warps per m-tile: floor(nwarp / nM), the first (nwarp mod nM) m-tiles get one more; with fewer warps than m-tiles a warp
+  // walks several m-tiles and rebuilds its fragments (tp_stage2 handles that case itself)
+  F.mt = -1; F.part = 0; F.nsplit = 1;
+  if (nM <= nwarp) {
+    const int base = nwarp / nM, extra = nwarp % nM;
+    int w = warp, m = 0;
+    if (w < extra * (base + 1)) { m = w / (base + 1); F.part = w % (base + 1); F.nsplit = base + 1; }
+    else { w -= extra * (base + 1); m = extra + w / base; F.part = w % base; F.nsplit = base; }
+    F.mt = m;
+    const int kA = m / TB, kB = 8 * (m % TB) + gq;
 #pragma unroll
-    for (int k = 0; k < NMAX; k++) { acc0[k] = 0.0; acc1[k] = 0.0; }
-    for (int s = 0; s < B.ns; s++) {
-      const SlotDesc S = A.slot[B.s0 + s];
-      const double *ZA = sZ + (S.zA * NMAX + kA) * NMAX;
-      const double *ZB = sZ + S.zB * NMAX * NMAX;
-      const double *U = sU + (size_t)s * NMAX * nij + ij;
-      double v[NMAX];
+    for (int s = 0; s < TP_SMAX; s++)
 #pragma unroll
-      for (int qz = 0; qz < NMAX; qz++) v[qz] = ZA[qz] * U[qz * nij];
-#pragma unroll
-      for (int kB = 0; kB < NMAX; kB++) {
-        double d = 0.0;
-#pragma unroll
-        for (int qz = 0; qz < NMAX; qz++) d += v[qz] * ZB[kB * NMAX + qz];
-        acc0[kB] += S.c[0] * d;
-        acc1[kB] += S.c[1] * d;
+      for (int ks = 0; ks < KS; ks++) {
+        const int qz = 4 * ks + tq;
+        double v = 0.0;
+        if (s < B.ns && kB < NMAX && qz < NMAX) { const SlotDesc S = A.slot[B.s0 + s]; v = sZ[(S.zA * NMAX + kA) * NMAX + qz] * sZ[(S.zB * NMAX + kB) * NMAX + qz]; }
+        F.a[s][ks] = v;
       }
+  }
+}
+template <int NMAX>
+__device__ __forceinline__ void tp_stage2(const Tp3Args &A, const BlockDesc &B, const double *sZ, const double *sU, const double *sC, int e, int nij,
+                                          int nBz, int nAz, int lA0, int strideA, Stage2Frag<NMAX> &F) {   // sC[2*s + ch]: coefficient of slot s in channel ch
+  constexpr int KS = Stage2Frag<NMAX>::KS, TB = Stage2Frag<NMAX>::TB;
+  const int lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int nM = nAz * TB, nN = (nij + 7) >> 3;
+  const bool own = F.mt >= 0;   // fragments prepared once per CTA
+  const ChannelDesc c0 = B.ch[0], c1 = B.ch[1];
+  const bool has0 = c0.mat >= 0, has1 = c1.mat >= 0;
+  for (int mt = own ? F.mt : warp; mt < nM; mt += (own ? nM : nwarp)) {
+    const int kA = mt / TB, kB = 8 * (mt % TB) + gq;
+    if (!own) {   // fewer warps than m-tiles: rebuild the fragments for this m-tile
+#pragma unroll
+      for (int s = 0; s < TP_SMAX; s++)
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+          const int qz = 4 * ks + tq;
+          double v = 0.0;
+          if (s < B.ns && kB < NMAX && qz < NMAX) { const SlotDesc S = A.slot[B.s0 + s]; v = sZ[(S.zA * NMAX + kA) * NMAX + qz] * sZ[(S.zB * NMAX + kB) * NMAX + qz]; }
+          F.a[s][ks] = v;
+        }
     }
-    // write out
+    // output rows of this m-tile (one kA) in the two channels
     const int lA = lA0 + strideA * kA;
+    double *dst[2]; double sg[2];
 #pragma unroll
     for (int ch = 0; ch < 2; ch++) {
       const ChannelDesc C = ch ? c1 : c0;
-      if (C.mat < 0) continue;
-      long long row; double sg = 1.0;
-      if (C.rowmap >= 0) { int m = A.maps[C.rowmap + lA]; if (m == 0) continue; row = (m < 0 ? -m : m) - 1; if (m < 0) sg = -1.0; }
+      dst[ch] = nullptr; sg[ch] = 1.0;
+      if (C.mat < 0 || kB >= nBz) continue;
+      long long row;
+      if (C.rowmap >= 0) { const int m = A.maps[C.rowmap + lA]; if (m == 0) continue; row = (m < 0 ? -m : m) - 1; if (m < 0) sg[ch] = -1.0; }
       else row = C.row0 + lA;
       const MatTarget M = A.mat[C.mat];
-      double *dst = M.base + (long long)e * M.batch + (long long)C.plane * M.plane + row * M.ld;
+      dst[ch] = M.base + (long long)e * M.batch + (long long)C.plane * M.plane + row * M.ld;
+    }
+    for (int nt = own ? F.part : 0; nt < nN; nt += (own ? F.nsplit : 1)) {
+      const int ij0 = 8 * nt;
+      // B fragment addresses: column ij0+gq (clamped: columns >= nij are dropped at the store), rows qz = 4 ks + tq (clamped: the
+      // A fragment is zero there)
+      const int colb = min(ij0 + gq, nij - 1);
+      const double *Up = sU + colb;
+      int roff[KS];
 #pragma unroll
-      for (int kB = 0; kB < NMAX; kB++) {
-        if (kB < nBz) {
+      for (int ks = 0; ks < KS; ks++) roff[ks] = min(4 * ks + tq, NMAX - 1) * nij;
+      double acc0[2] = {0.0, 0.0}, acc1[2] = {0.0, 0.0};
+#pragma unroll
+      for (int s = 0; s < TP_SMAX; s++) {
+        if (s < B.ns) {
+          double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+          for (int ks = 0; ks < KS; ks++) dmma_tile(d0, d1, F.a[s][ks], Up[roff[ks]]);
+          const double2 k = *reinterpret_cast<const double2 *>(sC + 2 * s);
+          if (has0) { acc0[0] += k.x * d0; acc0[1] += k.x * d1; }
+          if (has1) { acc1[0] += k.y * d0; acc1[1] += k.y * d1; }
+          Up += NMAX * nij;
+        }
+      }
+      // the thread holds (kB, ij0 + 2 tq) and (kB, ij0 + 2 tq + 1) of both channels
+#pragma unroll
+      for (int ch = 0; ch < 2; ch++) {
+        if (!dst[ch]) continue;
+        const ChannelDesc C = ch ? c1 : c0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int ij = ij0 + 2 * tq + h;
+          if (ij >= nij) continue;
           const int lB = ij + nij * kB;
-          long long col; double sc = sg;
-          if (C.colmap >= 0) { int m = A.maps[C.colmap + lB]; if (m == 0) continue; col = (m < 0 ? -m : m) - 1; if (m < 0) sc = -sc; }
+          long long col; double sc = sg[ch];
+          if (C.colmap >= 0) { const int m = A.maps[C.colmap + lB]; if (m == 0) continue; col = (m < 0 ? -m : m) - 1; if (m < 0) sc = -sc; }
           else col = C.col0 + lB;
-          dst[col] = sc * (ch ? acc1[kB] : acc0[kB]);
+          dst[ch][col] = sc * (ch ? acc1[h] : acc0[h]);
         }
       }
     }
@@ -354,10 +424,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 //     contraction with the output column in registers (tp_stage2).
 // dynamic smem: tables 12*TABSZ | F [nt][fs] | T1 [nt][nBx*nqy*nqz] | U [ns][nqz][nBx*nBy]   (offsets from the host, per signature)
 template <int NMAX>
-__global__ void __launch_bounds__(384, 3) tp3_kernel(Tp3Args A, int off_F, int off_T1, int off_U) {
+__global__ void __launch_bounds__(448, 2) tp3_kernel(Tp3Args A, int off_F, int off_T1, int off_U, int off_Q) {
+  constexpr int NQP = NMAX + 2;   // padded qy extent of the T1 / Q rows (even: 16-byte loads; 80-byte row stride at NMAX = 8: conflict-free)
   extern __shared__ __align__(16) double sm[];
   __shared__ __align__(8) unsigned long long mbar;
-  double *sTab = sm, *sZ = sm + 12 * TABSZ, *sF = sm + off_F, *sT1 = sm + off_T1, *sU = sm + off_U;   // sZ: 4*NMAX*NMAX
+  __shared__ int sbeg[TP_SMAX + 1];                 // terms of slot s: [sbeg[s], sbeg[s+1])  (terms are sorted by slot, forms.hpp BlockBuilder::finish)
+  __shared__ __align__(16) double sC[TP_SMAX * 2];  // slot coefficients of the two channels
+  double *sTab = sm, *sZ = sm + 12 * TABSZ, *sF = sm + off_F, *sT1 = sm + off_T1, *sU = sm + off_U, *sQ = sm + off_Q;   // sZ: 4*NMAX*NMAX
   const int e = blockIdx.y, tid = threadIdx.x;
   const WorkItem wi = A.work[blockIdx.x];
   const BlockDesc &B = A.block[wi.block];
@@ -365,7 +438,7 @@ __global__ void __launch_bounds__(384, 3) tp3_kernel(Tp3Args A, int off_F, int o
   const int iA = wi.iA;
   const int nqx = A.nq[0], nqy = A.nq[1], nqz = A.nq[2];
   const int nBx = fb.n[0], nBy = fb.n[1], nBz = fb.n[2], nAy = fa.n[1], nAz = fa.n[2];
-  const int nij = nBx * nBy, t1sz = nBx * nqy * nqz, fs = wf_stride(A.nint);
+  const int nij = nBx * nBy, t1sz = nBx * nqz * NQP, fs = wf_stride(A.nint), qsz = B.nt * nBy * NQP;
   const double *WFe = A.WF + (long long)e * NFIELD * fs;
   if (tid == 0) mbar_init(&mbar, 1);
   __syncthreads();
@@ -373,46 +446,64 @@ __global__ void __launch_bounds__(384, 3) tp3_kernel(Tp3Args A, int off_F, int o
     mbar_expect_tx(&mbar, (unsigned)(B.nt * fs * sizeof(double)));
     for (int t = 0; t < B.nt; t++) tma_bulk_g2s(sF + (size_t)t * fs, WFe + (long long)A.term[B.t0 + t].field * fs, (unsigned)(fs * sizeof(double)), &mbar);
   }
+  if (tid <= B.ns) {   // first term of every slot
+    int b = 0;
+    while (b < B.nt && A.term[B.t0 + b].slot < tid) b++;
+    sbeg[tid] = b;
+    if (tid < B.ns) { sC[2 * tid] = A.slot[B.s0 + tid].c[0]; sC[2 * tid + 1] = A.slot[B.s0 + tid].c[1]; }
+  }
   for (int i = tid; i < 12 * TABSZ; i += blockDim.x) sTab[i] = A.tab[i];
   for (int i = tid; i < B.ns * NMAX * nij; i += blockDim.x) sU[i] = 0.0;   // rows >= nqz stay zero
+  for (int i = tid; i < B.nt * t1sz; i += blockDim.x) sT1[i] = 0.0;        // qy padding stays zero
   __syncthreads();
   build_ztab<NMAX>(sTab + 8 * TABSZ, sZ, nqz);
-  mbar_wait(&mbar, 0);
   auto tabp = [&](int axis, int type) { return sTab + (axis * 4 + type) * TABSZ; };
-  // ---- x contraction of every term (shared by all jA)
-  for (int o = tid; o < B.nt * t1sz; o += blockDim.x) {
-    const int t = o / t1sz, r = o - t * t1sz, iB = r % nBx, qyz = r / nBx;
+  // Q[jA parity][t][jB][qy] = YA_t[jA][qy] * YB_t[jB][qy] (zero for qy >= nqy): the y factors of every term for one jA, double-buffered
+  // (the next jA's table is written while the z contraction of the current one runs)
+  auto build_q = [&](int jA) {
+    double *Q = sQ + (size_t)(jA & 1) * qsz;
+    for (int o = tid; o < qsz; o += blockDim.x) {
+      const int t = o / (nBy * NQP), r = o - t * nBy * NQP, jB = r / NQP, qy = r - jB * NQP;
+      const TermDesc T = A.term[B.t0 + t];
+      Q[o] = qy < nqy ? tabp(1, T.dA == 1 ? T_DH : fa.tab[1])[jA * nqy + qy] * tabp(1, T.dB == 1 ? T_DH : fb.tab[1])[jB * nqy + qy] : 0.0;
+    }
+  };
+  build_q(0);
+  mbar_wait(&mbar, 0);
+  // ---- x contraction of every term (shared by all jA): T1[t][qz][iB][qy]
+  for (int o = tid; o < B.nt * nBx * nqy * nqz; o += blockDim.x) {
+    const int t = o / (nBx * nqy * nqz), r = o - t * nBx * nqy * nqz, iB = r % nBx, qyz = r / nBx, qy = qyz % nqy, qz = qyz / nqy;
     const TermDesc T = A.term[B.t0 + t];
     const double *XA = tabp(0, T.dA == 0 ? T_DH : fa.tab[0]) + iA * nqx;
     const double *XB = tabp(0, T.dB == 0 ? T_DH : fb.tab[0]) + iB * nqx;
     const double *f = sF + (size_t)t * fs + qyz * nqx;
     double sacc = 0.0;
     for (int qx = 0; qx < nqx; qx++) sacc += XA[qx] * XB[qx] * f[qx];
-    sT1[o] = sacc * T.coef;   // [t][qyz][iB]
+    sT1[(size_t)t * t1sz + ((size_t)qz * nBx + iB) * NQP + qy] = sacc * T.coef;
   }
-  __syncthreads();
+  __syncthreads();   // sZ, sT1, Q(0) complete
+  Stage2Frag<NMAX> frag;
+  tp_stage2_prepare<NMAX>(A, B, sZ, nAz, frag);
   for (int jA = 0; jA < nAy; jA++) {
-    // ---- y contraction: U[slot][qz][ij] = sum over the slot's terms
+    // ---- y contraction: U[slot][qz][ij] = sum over the slot's terms and qy of Q[t][jB][qy] * T1[t][qz][iB][qy]
+    const double *Q = sQ + (size_t)(jA & 1) * qsz;
     for (int o = tid; o < nij * nqz; o += blockDim.x) {
       const int ij = o % nij, qz = o / nij, iB = ij % nBx, jB = ij / nBx;
+      const double *q0 = Q + jB * NQP, *t0 = sT1 + ((size_t)qz * nBx + iB) * NQP;
       for (int sl = 0; sl < B.ns; sl++) {
         double acc = 0.0;
-        for (int t = 0; t < B.nt; t++) {
-          const TermDesc T = A.term[B.t0 + t];
-          if (T.slot != sl) continue;
-          const double *YA = tabp(1, T.dA == 1 ? T_DH : fa.tab[1]) + jA * nqy;
-          const double *YB = tabp(1, T.dB == 1 ? T_DH : fb.tab[1]) + jB * nqy;
-          const double *t1 = sT1 + (size_t)t * t1sz + (size_t)qz * nqy * nBx + iB;
-          double sacc = 0.0;
-          for (int qy = 0; qy < nqy; qy++) sacc += YA[qy] * YB[qy] * t1[qy * nBx];
-          acc += sacc;
+        for (int t = sbeg[sl]; t < sbeg[sl + 1]; t++) {
+          const double2 *q = reinterpret_cast<const double2 *>(q0 + t * nBy * NQP), *t1 = reinterpret_cast<const double2 *>(t0 + (size_t)t * t1sz);
+#pragma unroll
+          for (int h = 0; h < NMAX / 2; h++) { const double2 a = q[h], b = t1[h]; acc += a.x * b.x; acc += a.y * b.y; }
         }
         sU[(size_t)sl * NMAX * nij + o] = acc;   // o = qz*nij + ij, qz < nqz
       }
     }
     __syncthreads();
-    // ---- z contraction and output
-    tp_stage2<NMAX>(A, B, sZ, sU, e, nij, nBz, nAz, iA + fa.n[0] * jA, fa.n[0] * fa.n[1]);
+    // ---- z contraction and output (tensor pipe), then the next jA's Q
+    tp_stage2<NMAX>(A, B, sZ, sU, sC, e, nij, nBz, nAz, iA + fa.n[0] * jA, fa.n[0] * fa.n[1], frag);
+    if (jA + 1 < nAy) build_q(jA + 1);
     __syncthreads();
   }
 }
@@ -423,9 +514,10 @@ __global__ void __launch_bounds__(384, 3) tp3_kernel(Tp3Args A, int off_F, int o
 // stage 2: the z contraction of the hexahedron kernel.  Triangle tables live in global memory (L1/L2-resident, read-only).
 // dynamic smem: z tables 4*TABSZ | G [nqt*nqz] | U [ns][nqz][nTB]
 template <int NMAX>
-__global__ void __launch_bounds__(384, 3) tp2_kernel(Tp3Args A, const double *__restrict__ ttab, int smem_u_off) {
+__global__ void __launch_bounds__(384, 2) tp2_kernel(Tp3Args A, const double *__restrict__ ttab, int smem_u_off) {
   extern __shared__ __align__(16) double sm[];
   double *sTabZ = sm, *sZ = sm + 4 * TABSZ, *sG = sZ + 4 * NMAX * NMAX, *sU = sm + smem_u_off;
+  __shared__ __align__(16) double sC[TP_SMAX * 2];   // slot coefficients of the two channels
   const int e = blockIdx.y;
   const WorkItem wi = A.work[blockIdx.x];
   const BlockDesc &B = A.block[wi.block];
@@ -434,6 +526,7 @@ __global__ void __launch_bounds__(384, 3) tp2_kernel(Tp3Args A, const double *__
   const int nqt = A.nq[0], nqz = A.nq[2];
   const int nTA = fa.n[0], nTB = fb.n[0], nBz = fb.n[2], nAz = fa.n[2];
   for (int i = threadIdx.x; i < 4 * TABSZ; i += blockDim.x) sTabZ[i] = A.tab[8 * TABSZ + i];
+  if (threadIdx.x < B.ns) { sC[2 * threadIdx.x] = A.slot[B.s0 + threadIdx.x].c[0]; sC[2 * threadIdx.x + 1] = A.slot[B.s0 + threadIdx.x].c[1]; }
   for (int i = threadIdx.x; i < B.ns * NMAX * nTB; i += blockDim.x) sU[i] = 0.0;
   __syncthreads();
   build_ztab<NMAX>(sTabZ, sZ, nqz);
@@ -457,7 +550,9 @@ __global__ void __launch_bounds__(384, 3) tp2_kernel(Tp3Args A, const double *__
     }
     __syncthreads();
   }
-  tp_stage2<NMAX>(A, B, sZ, sU, e, nTB, nBz, nAz, tA, nTA);
+  Stage2Frag<NMAX> frag;
+  tp_stage2_prepare<NMAX>(A, B, sZ, nAz, frag);
+  tp_stage2<NMAX>(A, B, sZ, sU, sC, e, nTB, nBz, nAz, tA, nTA, frag);
 }
 
 // Element-independent rows of W (trace pairings): W[e][plane 0][crow[r]][0..ncol) = CW[r][0..ncol)
@@ -467,6 +562,20 @@ __global__ void const_rows_kernel(const double *__restrict__ CW, const int *__re
   if (c >= ncol) return;
   const int r = blockIdx.y, e = blockIdx.z;
   M.base[(long long)e * M.batch + (long long)crow[r] * M.ld + c] = CW[(long long)r * ncol + c];
+}
+
+// Zero the part of W the dense phase reads before the integration writes into it (structural zeros of the forms, padding rows
+// and columns): Gram rows r < np up to the end of their diagonal 64-tile, the trial rows r >= np completely.  The upper
+// block-triangle of the Gram (28 % of W at config 3) is never read and is left alone.  grid (R/16, nel * planes), 256 threads.
+__global__ void __launch_bounds__(256) zero_w_kernel(double *W, long long plane, int R, int np) {
+  double *base = W + (long long)blockIdx.y * plane;
+  const int r0 = blockIdx.x * 16;
+  const double2 z = make_double2(0.0, 0.0);
+  for (int r = r0; r < min(R, r0 + 16); r++) {
+    const int w = r < np ? min(np, (r / 64 + 1) * 64) : np;
+    double2 *row = reinterpret_cast<double2 *>(base + (long long)r * np);
+    for (int c = threadIdx.x; c < w / 2; c += 256) row[c] = z;
+  }
 }
 
 // unit diagonal on rows [n0,n1) of the real plane (keeps padded Gram rows regular); grid (ceil((n1-n0)/64), nel)
