@@ -124,7 +124,12 @@ class ElemEngine:
         for k, v in params.items():
             if not hasattr(prm, k):
                 raise TypeError(f"unknown parameter {k}")
-            setattr(prm, k, v)
+            if k == "eps_tensor":   # (3,3) complex, eps_t[i, j]; the struct holds it column-major, (re, im) interleaved
+                t = np.asarray(v, dtype=np.complex128).reshape(3, 3).T.copy().view(np.float64).ravel()
+                for i in range(18):
+                    prm.eps_tensor[i] = t[i]
+            else:
+                setattr(prm, k, v)
         self.kind, self.prm = kind, prm
         self.complex = kind >= MAXW_GAL
         self.dtype = np.complex128 if self.complex else np.float64

@@ -478,6 +478,14 @@ struct Plan {
   }
   GeomParams geom() const {
     GeomParams g; g.kind = fp.kind; g.source = fp.source; g.icomp = fp.icomp; g.omega = fp.omega; g.eps = fp.eps; g.mu = fp.mu; g.sigma = fp.sigma;
+    g.tensor = fp.tensor ? 1 : 0;
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        std::complex<double> m(0.0, 0.0);   // (eps_t eps_t^H)(i,j)
+        for (int c = 0; c < 3; c++) m += fp.epst[i + 3 * c] * std::conj(fp.epst[j + 3 * c]);
+        g.tR[3 * i + j] = m.real(); g.tS[3 * i + j] = m.imag();
+        g.ter[3 * i + j] = fp.epst[i + 3 * j].real(); g.tei[3 * i + j] = fp.epst[i + 3 * j].imag();
+      }
     return g;
   }
   // descriptor arrays keep the brick layout (19/12/6 ints per element); a prism uses the first 15/9/5 entries

@@ -38,6 +38,10 @@ struct FormParams {
   // imaginary, so A = T A~ T^H with A~ = R G~^-1 R^T real: the whole dense phase runs in real arithmetic (a quarter of the
   // flops of the reference's ZPOTRF/ZTRTRS/ZHERK) and the phases come back in the output kernels (formats.cuh).
   bool real_struct = true;
+  // constant permittivity tensor of ultraweak Maxwell (get_permittivity: za = i w eps * eps_t, elem_opt.F90:260-266); entry (i,j) at [i + 3j]
+  bool tensor = false;
+  std::complex<double> epst[9];
+  bool tensor_real() const { for (int i = 0; i < 9; i++) if (epst[i].imag() != 0.0) return false; return true; }
 };
 
 // element_data.F90:106-109 (0-based): edges of face f: [0],[2] run along the face's first axis, [1],[3] along the second
@@ -133,7 +137,7 @@ inline double rs_real(std::complex<double> w, int pr, int pc, bool trial_row) {
   const std::complex<double> z = w * (pr ? -I : std::complex<double>(1, 0)) * (pc ? I : std::complex<double>(1, 0)) * (trial_row ? I : std::complex<double>(1, 0));
   return z.real();
 }
-inline bool rs_applicable(const FormParams &P) { return P.kind == 4 && P.real_struct && P.sigma == 0.0; }
+inline bool rs_applicable(const FormParams &P) { return P.kind == 4 && P.real_struct && P.sigma == 0.0 && (!P.tensor || P.tensor_real()); }
 
 inline int add_family(SigHost &S, int n0, int n1, int n2, int t0, int t1, int t2) {
   FamilyDesc f; f.n[0] = n0; f.n[1] = n1; f.n[2] = n2; f.tab[0] = t0; f.tab[1] = t1; f.tab[2] = t2;
@@ -264,24 +268,46 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
     for (int a = 0; a < 3; a++)
       for (int a2 = 0; a2 <= a; a2++) {
         BlockBuilder b(S, tf[a], tf[a2], channel(0, 0, offE[a], offE[a2]), channel(0, 0, nEE + offE[a], nEE + offE[a2]));
-        b.add(-1, -1, F_D + sym_idx(a, a2), 1.0, aF, aG);
+        if (P.tensor && P.test_norm != 2) {
+          // (za^H F_c, za^H F_r) = w^2 eps^2 F_r^T (eps_t eps_t^H) F_c: the real part R here, the imaginary part S in a block of its own below
+          // FF: alpha D + w^2 eps^2 TD, GG: aG D -- written as aG D (1,1) + [(alpha - aG) D + w^2 eps^2 TD] (1,0) so that the mass terms
+          // share the z-slots (tab,tab,1,1) of the curl-curl terms and (tab,tab,1,0): five slots per block (TP_SMAX)
+          b.add(-1, -1, F_D + sym_idx(a, a2), aG, 1.0, 1.0);
+          b.add(-1, -1, F_D + sym_idx(a, a2), P.alpha_norm - aG, 1.0, 0.0);
+          b.add(-1, -1, F_TD + sym_idx(a, a2), P.omega * P.omega * P.eps * P.eps, 1.0, 0.0);
+        } else
+          b.add(-1, -1, F_D + sym_idx(a, a2), 1.0, aF, aG);
         CurlComp ca[2], cb[2];
         curl_comps(a, ca); curl_comps(a2, cb);
         for (int i = 0; i < 2; i++)
           for (int j = 0; j < 2; j++) b.add(ca[i].dax, cb[j].dax, F_C + sym_idx(ca[i].comp, cb[j].comp), ca[i].sgn * cb[j].sgn, 1.0, 1.0);
         b.finish();
       }
+    // imaginary part of the FF Gram blocks for a complex permittivity tensor: F_r^T (w^2 eps^2 S) F_c, S antisymmetric (zero on a == a2)
+    if (P.tensor && P.test_norm != 2 && !P.tensor_real())
+      for (int a = 1; a < 3; a++)
+        for (int a2 = 0; a2 < a; a2++) {
+          BlockBuilder b(S, tf[a], tf[a2], channel(0, 1, offE[a], offE[a2]), no_channel());
+          b.add(-1, -1, F_TS + (a == 1 ? 0 : a2 + 1), P.omega * P.omega * P.eps * P.eps, 1.0, 0.0);
+          b.finish();
+        }
     // Gram cross block: W[G_j][F_i] = conj(gFG(i,j)) = -conj(za) (F_i, curl G_j) + zc (curl F_i, G_j)   (metric-free: weight w)
+    // permittivity tensor: -(curl G_j)^T za^H F_i = i w eps (curl^ G_j)^T [w (J^T er^T J^-T) - i w (J^T ei^T J^-T)] F^_i: every curl
+    // component b of the row family meets the column family through the fields T1R / T1I (b, a2), also for a == a2
     if (P.test_norm == 1)
       for (int a = 0; a < 3; a++)      // G row family
         for (int a2 = 0; a2 < 3; a2++) {  // F column family
-          if (a == a2) continue;
+          if (a == a2 && !P.tensor) continue;
           BlockBuilder b(S, tf[a], tf[a2], channel(0, 0, nEE + offE[a], offE[a2]), rs ? no_channel() : channel(0, 1, nEE + offE[a], offE[a2]));
           CurlComp cg[2], cf[2];
           curl_comps(a, cg); curl_comps(a2, cf);
           const std::complex<double> m1 = -std::conj(za), m2 = zc;
           for (int i = 0; i < 2; i++) {
-            if (cg[i].comp == a2) b.add(cg[i].dax, -1, F_W, cg[i].sgn, rs ? rs_real(m1, 1, 0, false) : m1.real(), rs ? 0.0 : m1.imag());
+            if (P.tensor) {
+              b.add(cg[i].dax, -1, F_T1R + 3 * cg[i].comp + a2, cg[i].sgn, rs ? rs_real(m1, 1, 0, false) : m1.real(), rs ? 0.0 : m1.imag());
+              const std::complex<double> m1i = m1 * std::complex<double>(0.0, -1.0);
+              if (!P.tensor_real()) b.add(cg[i].dax, -1, F_T1I + 3 * cg[i].comp + a2, cg[i].sgn, m1i.real(), m1i.imag());
+            } else if (cg[i].comp == a2) b.add(cg[i].dax, -1, F_W, cg[i].sgn, rs ? rs_real(m1, 1, 0, false) : m1.real(), rs ? 0.0 : m1.imag());
             if (cf[i].comp == a) b.add(-1, cf[i].dax, F_W, cf[i].sgn, rs ? rs_real(m2, 1, 0, false) : m2.real(), rs ? 0.0 : m2.imag());
           }
           b.finish();
@@ -297,9 +323,12 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
     for (int c = 0; c < 3; c++)
       for (int a = 0; a < 3; a++) {
         {  // B(F_i, E_jc) = -za (E_c, F_i)  ->  W = conj
-          const std::complex<double> m = -std::conj(za);
           BlockBuilder b(S, fq, tf[a], channel(0, 0, 0, offE[a], mapE[c]), rs ? no_channel() : channel(0, 1, 0, offE[a], mapE[c]));
-          b.add(-1, -1, F_WJI + 3 * a + c, 1.0, rs ? rs_real(m, 0, 0, true) : m.real(), rs ? 0.0 : m.imag());
+          for (int d = 0; d < 3; d++) {   // -(za E_c e_c, F) = -sum_d za(d,c) F_d: the identity tensor keeps d = c only
+            const std::complex<double> m = P.tensor ? -std::conj(za * P.epst[d + 3 * c]) : (d == c ? -std::conj(za) : std::complex<double>(0.0, 0.0));
+            if (m == std::complex<double>(0.0, 0.0)) continue;
+            b.add(-1, -1, F_WJI + 3 * a + d, 1.0, rs ? rs_real(m, 0, 0, true) : m.real(), rs ? 0.0 : m.imag());
+          }
           b.finish();
         }
         {  // B(F_i, H_jc) = B(G_i, E_jc) = (H_c, curl F_i)   real

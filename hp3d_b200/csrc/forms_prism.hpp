@@ -195,6 +195,7 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
   if (P.kind == 4) {
     // =============================================================== ultraweak Maxwell
     if (P.test_norm < 1 || P.test_norm > 3) { S.err = "unknown test norm"; return false; }
+    if (P.tensor) { S.err = "a permittivity tensor other than the identity is implemented for hexahedra only"; return false; }
     TriList TV, TS, TQ, TEt, THt;
     const std::vector<PrismDof> ed = prism_dofs_Hcurl(norderi, norie, norif, TV, TS);
     const std::vector<PrismDof> qd = prism_dofs_L2(norder, TQ);

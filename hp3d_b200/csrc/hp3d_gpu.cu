@@ -265,13 +265,18 @@ int hp3d_gpu_finalize(void) {
 int hp3d_gpu_plan(int problem_kind, const hp3d_params *prm) {
   if (!prm) return fail(HP3D_EINVAL, "null params");
   if (problem_kind < HP3D_POIS_GAL || problem_kind > HP3D_MAXW_UW) return fail(HP3D_EINVAL, "unknown problem kind %d", problem_kind);
-  // constant isotropic permittivity only (the reference's default get_permittivity is the identity,
-  // problems/MAXWELL/ULTRAWEAK_DPG/common/commonRoutines.F90:126-150)
+  // get_permittivity (problems/MAXWELL/ULTRAWEAK_DPG/common/commonRoutines.F90:126-150; used at elem_opt.F90:260-266): a CONSTANT
+  // complex 3x3 tensor for ultraweak Maxwell (real tensors keep the real form, complex ones take the general complex kernels);
+  // the other problems of the reference have a scalar permittivity only
+  bool tensor = false;
   for (int j = 0; j < 3; j++)
     for (int i = 0; i < 3; i++) {
       double re = prm->eps_tensor[2 * (i + 3 * j)], im = prm->eps_tensor[2 * (i + 3 * j) + 1];
-      if (re != (i == j ? 1.0 : 0.0) || im != 0.0) return fail(HP3D_EINVAL, "only the identity permittivity tensor is supported (scale with eps)");
+      if (re != (i == j ? 1.0 : 0.0) || im != 0.0) tensor = true;
     }
+  if (tensor && problem_kind != HP3D_MAXW_UW) return fail(HP3D_EINVAL, "a permittivity tensor other than the identity is defined for ultraweak Maxwell only (scale with eps)");
+  if (tensor && prm->source == HP3D_SRC_SIN)
+    return fail(HP3D_EINVAL, "the built-in manufactured source assumes the identity permittivity tensor: pass the source through HP3D_SRC_TABLE");
   if (prm->maxp < 1 || prm->maxp > 9) return fail(HP3D_EINVAL, "maxp out of range");
   if (prm->icomp_exact < 1 || prm->icomp_exact > 3) return fail(HP3D_EINVAL, "icomp_exact out of range");
   Plan *p = new Plan();
@@ -280,6 +285,8 @@ int hp3d_gpu_plan(int problem_kind, const hp3d_params *prm) {
   p->fp.source = prm->source; p->fp.icomp = prm->icomp_exact - 1;
   p->store_schur = prm->store_schur;
   p->fp.real_struct = prm->real_reduction != 0;
+  p->fp.tensor = tensor;
+  for (int i = 0; i < 9; i++) p->fp.epst[i] = std::complex<double>(prm->eps_tensor[2 * i], prm->eps_tensor[2 * i + 1]);
   p->aii_packed = prm->aii_packed;
   if (p->aii_packed < 0 || p->aii_packed > 2) { delete p; return fail(HP3D_EINVAL, "aii_packed must be 0, 1 or 2"); }
   if (p->aii_packed && problem_kind != HP3D_POIS_PDPG && problem_kind != HP3D_MAXW_UW) {

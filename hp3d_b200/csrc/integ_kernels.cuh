@@ -41,7 +41,13 @@ enum Field {
   F_WJD = 23,  // 9: w*dx_c/dxi_b/det at [23+3c+b]
   F_SRC = 32,  // 6: source terms (real problems: [32] = w*det*f ; Maxwell: re/im of w*det*(J^-1 zJ)_a at [32+2a], [33+2a])
   F_X = 38,    // 3: physical coordinates
-  NFIELD = 41
+  // constant permittivity TENSOR eps_t of ultraweak Maxwell (get_permittivity, elem_opt.F90:260-266), only filled when it is not
+  // the identity: with eps_t eps_t^H = R + i S (R symmetric, S antisymmetric) and eps_t = er + i ei
+  F_TD = 41,   // 6: w*det*(J^-1 R J^-T), symmetric (00,11,22,01,02,12)             Gram (za^H F, za^H F), real part
+  F_TS = 47,   // 3: w*det*(J^-1 S J^-T) at (1,0),(2,0),(2,1)                        ... imaginary part
+  F_T1R = 50,  // 9: w*(J^T er^T J^-T)(b,a) at [50+3b+a]                             Gram cross term (curl G, za^H F)
+  F_T1I = 59,  // 9: the same with ei
+  NFIELD = 68
 };
 // weight fields are stored [element][field][fs] with fs = nint rounded up to even: every field starts on a 16-byte boundary,
 // so one field is one TMA bulk copy (cp.async.bulk needs 16-byte aligned addresses and sizes)
@@ -54,6 +60,8 @@ struct GeomParams {
   int source;          // HP3D_SRC_*
   int icomp;           // 0-based component of the manufactured Maxwell solution
   double omega, eps, mu, sigma;
+  int tensor;          // permittivity tensor fields wanted
+  double tR[9], tS[9], ter[9], tei[9];   // R, S, er, ei (see Field), entry (i,j) at [3*i + j]
 };
 
 struct SigTables {               // element-signature tables, device memory
@@ -117,6 +125,23 @@ __device__ __forceinline__ void emit_fields(const GeomParams &gp, int e, int q, 
       F[(F_WJD + 3 * c + a) * fs] = wod * J[c + 3 * a];
     }
   for (int c = 0; c < 3; c++) F[(F_X + c) * fs] = x[c];
+  if (gp.tensor) {
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) {
+        double dd = 0, ss = 0, tr = 0, ti = 0;
+        for (int d = 0; d < 3; d++)
+          for (int d2 = 0; d2 < 3; d2++) {
+            dd += Ji[a + 3 * d] * gp.tR[3 * d + d2] * Ji[b + 3 * d2];
+            ss += Ji[a + 3 * d] * gp.tS[3 * d + d2] * Ji[b + 3 * d2];
+            tr += J[d + 3 * a] * gp.ter[3 * d2 + d] * Ji[b + 3 * d2];   // (J^T er^T J^-T)(a,b)
+            ti += J[d + 3 * a] * gp.tei[3 * d2 + d] * Ji[b + 3 * d2];
+          }
+        if (b >= a) F[(F_TD + sym_idx(a, b)) * fs] = wd * dd;
+        if (a > b) F[(F_TS + (a == 1 ? 0 : b + 1)) * fs] = wd * ss;      // (1,0) -> 0, (2,0) -> 1, (2,1) -> 2
+        F[(F_T1R + 3 * a + b) * fs] = w * tr;
+        F[(F_T1I + 3 * a + b) * fs] = w * ti;
+      }
+  }
   // ---- source term
   double s[6] = {0, 0, 0, 0, 0, 0};
   if (gp.kind == 1 || gp.kind == 2) {  // Poisson: f(x)

@@ -312,3 +312,41 @@ def test_without_schur_factors(oracle, gpu, kind):
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])     # same kernels, same order: bit-identical
         assert not a[2].any() and not a[3].any()                             # the Schur arrays are left untouched
     full.close(); eng.close()
+
+
+@pytest.mark.parametrize("test_norm", [1, 2, 3])
+@pytest.mark.parametrize("tensor,rr", [("real", 1), ("real", 0), ("complex", 1), ("complex", 0)])
+def test_uw_maxwell_permittivity_tensor(oracle, gpu, test_norm, tensor, rr):
+    """get_permittivity other than the identity (elem_opt.F90:260-266: za = i w eps * eps_t, a full 3x3 tensor): the Gram term
+    (za^H F, za^H F), the cross term (curl G, za^H F) and the stiffness -(za E, F) against the oracle's BLAS3 elem_opt with the same
+    tensor.  A real tensor keeps the real form (rr = 1), a complex one takes the general complex kernels whatever rr says."""
+    import ctypes as C
+    oracle.set_maxp(6)
+    oracle.use_blas(True)
+    rng = np.random.default_rng(777 + test_norm)
+    p, nel = 2, 2
+    norder = np.tile(uniform_order(p), (nel, 1))
+    norie = rng.integers(0, 2, (nel, 12)).astype(np.int32); norif = rng.integers(0, 8, (nel, 6)).astype(np.int32)
+    nH = oracle.celndof(norder[0])[0]
+    X = np.stack([hexa_xnod(nH, h=0.5, jitter=0.12, curved=0.01, rng=rng) for e in range(nel)])
+    T = np.eye(3) + 0.3 * rng.standard_normal((3, 3))
+    if tensor == "complex":
+        T = T + 0.2j * rng.standard_normal((3, 3))
+    kw = dict(omega=1.3 * np.pi, eps=1.5, mu=0.8, alpha_norm=0.6, test_norm=test_norm, eps_tensor=T)
+    eng = _engine(4, real_reduction=rr, source=9, **kw)
+    nint = eng.sizes(norder[0])[2]
+    J = rng.standard_normal((nel, nint, 3)) + 1j * rng.standard_normal((nel, nint, 3))
+    res = eng.elem_stc_batch(norder, norie, norif, X, source_qp=J)
+    assert (res["info"] == 0).all()
+    for e in range(nel):
+        tab = np.ascontiguousarray(J[e])
+        prm = _oracle_params(oracle, source=9, source_table=tab.ctypes.data_as(C.c_void_p), **kw)
+        Aii, Bi, AS, BS = eng.unpack(res, e)
+        rA, rB, rAS, rBS = oracle.condensed(4, norder[e], norie[e], norif[e], X[e], prm)
+        assert relerr(Aii, rA) < 1e-12 and relerr(Bi, rB) < 1e-12, (e, relerr(Aii, rA), relerr(Bi, rB))
+        assert relerr(AS, rAS) < 1e-9 and relerr(BS, rBS) < 1e-9
+    eng.close()
+    with pytest.raises(RuntimeError, match="HP3D_SRC_TABLE"):
+        _engine(4, eps_tensor=T)                      # the built-in manufactured source assumes the identity tensor
+    with pytest.raises(RuntimeError, match="ultraweak Maxwell only"):
+        _engine(3, eps_tensor=T, source=9)
