@@ -230,7 +230,27 @@ def bind_to_gpu_numa(gpu_index):
     return None
 
 
-def sub_config(name, kind, p, B, steps, local, rank, world, maxr, peak_tf, hbm_gbs, complex_kernels=False, mesh=None, lanes=2):
+def cpu_rate_mixed(kind, mesh, idx, threads, omega):
+    """Elements/s of the CPU oracle over the elements `idx` of a mixed hexa/prism mesh (one ctypes call per element from a thread
+    pool: the calls release the GIL, so this is the OpenMP-over-elements structure of par_mumps_sc.F90:347)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    O.set_maxp(8)
+    blas = O.use_blas(True, threads=1)
+    prm = O.default_params(omega=omega)
+
+    def one(e):
+        et = int(mesh["etype"][e])
+        nH = O.celndof(mesh["norder"][e], et)[0]
+        O.condensed(kind, mesh["norder"][e], mesh["norient_edge"][e], mesh["norient_face"][e], mesh["xnod"][e, :nH], prm, etype=et)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(one, idx))
+    dt = time.perf_counter() - t0
+    return len(idx) / dt, dt, blas
+
+
+def sub_config(name, kind, p, B, steps, local, rank, world, maxr, peak_tf, hbm_gbs, complex_kernels=False, mesh=None, lanes=2, cpu_sample=0):
     """Device-resident throughput of another BASELINE.json config on this rank's GPU (same timing rules as the headline:
     warm-up, CUDA events on the launching stream inside the library, max over ranks): value, dense TFLOP/s against the measured
     FP64 tensor peak, and the algorithmic output bytes per second against the measured HBM bandwidth."""
@@ -262,7 +282,18 @@ def sub_config(name, kind, p, B, steps, local, rank, world, maxr, peak_tf, hbm_g
     eng.close()
     tf = F / (ms * 1e-3) / 1e12
     gbs = out_bytes / (ms * 1e-3) / 1e9
-    return {"workload": name, "value": world * B / (ms * 1e-3), "unit": "elements/s", "elements_per_gpu_per_step": B, "steps": steps, "ms_per_step": ms,
+    cpu = None
+    if cpu_sample and world == 1:   # the CPU oracle beside it: all host cores, bounded sample of the same workload
+        cores = host_cores()
+        if mesh is None:
+            v, dtc, blas = cpu_reference_rate(kind, p, cpu_sample, cores, omega)
+            what = f"{cpu_sample} elements of the same workload"
+        else:
+            idx = np.random.default_rng(5).choice(B, size=min(cpu_sample, B), replace=False)
+            v, dtc, blas = cpu_rate_mixed(kind, mesh, idx, cores, omega)
+            what = f"{len(idx)} randomly chosen elements of the same mesh"
+        cpu = {"value": v, "unit": "elements/s", "cores": cores, "kind": "port", "sample": f"{what} in {dtc:.1f} s; {cores} threads over elements, single-threaded {'OpenBLAS' if blas else 'built-in loops'} per element"}
+    return {"workload": name, "value": world * B / (ms * 1e-3), "unit": "elements/s", "elements_per_gpu_per_step": B, "steps": steps, "ms_per_step": ms, "cpu_baseline": cpu,
             "gpu_launches_per_step": r["launches"] / steps, "dense_tflops_per_gpu": tf, "frac_fp64_tensor_peak": tf / peak_tf,
             "dense_tflops_on_reference_count": F_ref / (ms * 1e-3) / 1e12,
             "algorithmic_output_gbs_per_gpu": gbs, "frac_hbm": gbs / hbm_gbs,
@@ -460,15 +491,16 @@ def main():
     configs = None
     if not args.no_configs and args.kind == 4 and args.p == 5:
         a = (local, rank, world, maxr, peak_tf, hbm_gbs)
+        cs = (lambda n: 0 if args.no_cpu else n)   # bounded CPU samples (a few seconds each), N = 1 only
         configs = {
             "complex_kernels_uw_maxwell_p5": sub_config("configs[3] through the GENERAL complex dense phase (real_reduction = 0: the reference's ZPOTRF/ZTRTRS/ZHERK sequence, what lossy media use)", 4, 5, 128, 2, *a, complex_kernels=True),
-            "config0_poisson_galerkin_p3": sub_config("configs[0]: Poisson Galerkin, hexa p=3, real FP64 (LU static condensation)", 1, 3, 65536, 2, *a),
-            "config1_poisson_primal_dpg_p4": sub_config("configs[1]: Poisson primal DPG, hexa p=4, dp=1 (Gram + Cholesky condensation)", 2, 4, 8192, 2, *a),
-            "config2_maxwell_galerkin_p5": sub_config("configs[2]: Maxwell H(curl) Galerkin, hexa p=5, complex FP64 (LU static condensation)", 3, 5, 2048, 2, *a),
+            "config0_poisson_galerkin_p3": sub_config("configs[0]: Poisson Galerkin, hexa p=3, real FP64 (LU static condensation)", 1, 3, 65536, 2, *a, cpu_sample=cs(65536)),
+            "config1_poisson_primal_dpg_p4": sub_config("configs[1]: Poisson primal DPG, hexa p=4, dp=1 (Gram + Cholesky condensation)", 2, 4, 8192, 2, *a, cpu_sample=cs(8192)),
+            "config2_maxwell_galerkin_p5": sub_config("configs[2]: Maxwell H(curl) Galerkin, hexa p=5, complex FP64 (LU static condensation)", 3, 5, 2048, 2, *a, cpu_sample=cs(1024)),
         }
         m = synth.hp_mesh(8, pmin=2, pmax=7, jitter=0.1)   # every rank its own copy of the same mesh (weak scaling)
         configs["config4_hp_mixed_p2_7"] = sub_config("configs[4]: hp-refined mixed hexa/prism mesh, p=2..7, ultraweak DPG Maxwell, %d elements (%d prisms) per GPU, one signature per (type, orders, orientations)"
-                                                      % (len(m["etype"]), int((m["etype"] == 3).sum())), 4, 0, 0, 2, *a, mesh=m, lanes=4)
+                                                      % (len(m["etype"]), int((m["etype"] == 3).sum())), 4, 0, 0, 2, *a, mesh=m, lanes=4, cpu_sample=cs(96))
 
     if rank != 0:
         if dist is not None:
