@@ -200,10 +200,31 @@ struct LaneSet {
   int nl = 2;    // lanes currently bound
   double *d_ones = nullptr; int *d_iota = nullptr; int n_iota = 0;   // identity output maps (grown on demand, plain cudaMalloc)
   void layout(const ChunkShape &sh, int batch, Bump &dm, Bump &hm, int nlanes = 2) {
+    for (int i = 0; i < nlanes; i++) layout_lane(lane[i], sh, batch, dm, hm);
+  }
+  // Lane i bound on its own inside partition i of the arena (NLANE equal partitions), whatever the other lanes hold: chunks of
+  // DIFFERENT dense classes run side by side on different lanes without draining each other (hp meshes).  The caller makes
+  // sure the partitions are large enough (ensure_partitions) and orders re-binds by the lane's stream.
+  static int ensure_partitions(size_t dev_bytes_per_lane, size_t host_bytes_per_lane, std::string &err) {
+    const size_t dneed = (dev_bytes_per_lane + 4096) * NLANE, hneed = (host_bytes_per_lane + 4096) * NLANE;
+    return g_arena.ensure(std::max(dneed, g_arena.dcap), std::max(hneed, g_arena.hcap), err);
+  }
+  static void lane_bytes(const ChunkShape &sh, int batch, size_t &dev, size_t &host) {
+    Bump dm(nullptr), hm(nullptr);
+    Lane tmp;
+    layout_lane(tmp, sh, batch, dm, hm);
+    dev = dm.off + 256; host = hm.off + 256;
+  }
+  void bind_lane(int i, const ChunkShape &sh, int batch) {
+    const size_t dpart = (g_arena.dcap / NLANE) & ~(size_t)255, hpart = (g_arena.hcap / NLANE) & ~(size_t)255;
+    Bump dm((char *)g_arena.d + dpart * i), hm((char *)g_arena.h + hpart * i);
+    layout_lane(lane[i], sh, batch, dm, hm);
+    g_arena.owner = nullptr; cap = 0;   // the shared single-shape layout (reserve) is no longer valid
+  }
+  static void layout_lane(Lane &L, const ChunkShape &sh, int batch, Bump &dm, Bump &hm) {
     const size_t NS = sh.ns();
     const DenseDims &d = sh.d;
-    for (int i = 0; i < nlanes; i++) {
-      Lane &L = lane[i];
+    {
       L.ws.bind(d, batch, dm);
       L.ws.b.ni_e = dm.take<int>(batch); L.ws.b.nb_e = dm.take<int>(batch); L.ws.b.nip_e = dm.take<int>(batch);
       L.d_WF = dm.take<double>((size_t)NFIELD * wf_stride(sh.nint_max) * batch);
@@ -250,7 +271,11 @@ struct LaneSet {
     Bump dm(g_arena.d), hm(g_arena.h);
     layout(sh, batch, dm, hm, nlanes);
     nl = nlanes;
-    const int need = std::max(sh.d.ni, sh.d.nb) + 1;
+    if (ensure_iota(std::max(sh.d.ni, sh.d.nb) + 1, err)) return -2;
+    g_arena.owner = this; shape = sh; cap = batch;
+    return 0;
+  }
+  int ensure_iota(int need, std::string &err) {   // identity output maps for at least `need` dofs
     if (need > n_iota) {
       cudaDeviceSynchronize();
       cudaFree(d_ones); cudaFree(d_iota);
@@ -259,7 +284,6 @@ struct LaneSet {
       if (dev_upload(iota, &d_iota, err) || dev_upload(ones, &d_ones, err)) return -2;
       n_iota = need;
     }
-    g_arena.owner = this; shape = sh; cap = batch;
     return 0;
   }
   void release() { cudaFree(d_ones); cudaFree(d_iota); d_ones = nullptr; d_iota = nullptr; n_iota = 0; cap = 0; shape = ChunkShape(); }

@@ -195,7 +195,6 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
   if (P.kind == 4) {
     // =============================================================== ultraweak Maxwell
     if (P.test_norm < 1 || P.test_norm > 3) { S.err = "unknown test norm"; return false; }
-    if (P.tensor) { S.err = "a permittivity tensor other than the identity is implemented for hexahedra only"; return false; }
     TriList TV, TS, TQ, TEt, THt;
     const std::vector<PrismDof> ed = prism_dofs_Hcurl(norderi, norie, norif, TV, TS);
     const std::vector<PrismDof> qd = prism_dofs_L2(norder, TQ);
@@ -219,9 +218,40 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
     for (int a = 0; a < 2; a++)
       for (int a2 = 0; a2 <= a; a2++) {
         BlockBuilder b(S, tf[a].id, tf[a2].id, channel(0, 0, tf[a].off, tf[a2].off), channel(0, 0, nEE + tf[a].off, nEE + tf[a2].off));
-        add_hcurl_pair(b, tf[a].kind, tf[a2].kind, aF, aG, 1.0, 1.0);
+        if (P.tensor && P.test_norm != 2) {
+          // permittivity tensor (forms.hpp): FF = alpha D + w^2 eps^2 TD, GG = aG D, written as aG D (1,1) + [(alpha - aG) D + w^2 eps^2 TD] (1,0)
+          const double kap = P.omega * P.omega * P.eps * P.eps;
+          for (int ca = 0; ca < 3; ca++)
+            for (int cb = 0; cb < 3; cb++) {
+              const CompRef A = pf_val(tf[a].kind, ca), B = pf_val(tf[a2].kind, cb);
+              if (A.tc >= 0 && B.tc >= 0) {
+                b.addp(A.tc, A.zd, B.tc, B.zd, F_D + sym_idx(ca, cb), A.sgn * B.sgn * aG, 1.0, 1.0);
+                b.addp(A.tc, A.zd, B.tc, B.zd, F_D + sym_idx(ca, cb), A.sgn * B.sgn * (P.alpha_norm - aG), 1.0, 0.0);
+                b.addp(A.tc, A.zd, B.tc, B.zd, F_TD + sym_idx(ca, cb), A.sgn * B.sgn * kap, 1.0, 0.0);
+              }
+              const CompRef CA = pf_curl(tf[a].kind, ca), CB = pf_curl(tf[a2].kind, cb);
+              if (CA.tc >= 0 && CB.tc >= 0) b.addp(CA.tc, CA.zd, CB.tc, CB.zd, F_C + sym_idx(ca, cb), CA.sgn * CB.sgn, 1.0, 1.0);
+            }
+        } else
+          add_hcurl_pair(b, tf[a].kind, tf[a2].kind, aF, aG, 1.0, 1.0);
         b.finish();
       }
+    // imaginary part of the FF Gram blocks for a complex permittivity tensor: F_r^T (w^2 eps^2 S) F_c, S antisymmetric
+    if (P.tensor && P.test_norm != 2 && !P.tensor_real())
+      for (int a = 0; a < 2; a++)
+        for (int a2 = 0; a2 <= a; a2++) {
+          BlockBuilder b(S, tf[a].id, tf[a2].id, channel(0, 1, tf[a].off, tf[a2].off), no_channel());
+          const double kap = P.omega * P.omega * P.eps * P.eps;
+          for (int ca = 0; ca < 3; ca++)
+            for (int cb = 0; cb < 3; cb++) {
+              if (ca == cb) continue;
+              const CompRef A = pf_val(tf[a].kind, ca), B = pf_val(tf[a2].kind, cb);
+              if (A.tc < 0 || B.tc < 0) continue;
+              const int hi = std::max(ca, cb), lo = std::min(ca, cb);
+              b.addp(A.tc, A.zd, B.tc, B.zd, F_TS + (hi == 1 ? 0 : lo + 1), A.sgn * B.sgn * kap * (ca > cb ? 1.0 : -1.0), 1.0, 0.0);
+            }
+          b.finish();
+        }
     if (P.test_norm == 1)
       for (int a = 0; a < 2; a++)        // G row family
         for (int a2 = 0; a2 < 2; a2++) { // F column family
@@ -231,7 +261,15 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
           const double m2r = rs ? rs_real(m2, 1, 0, false) : m2.real(), m2i = rs ? 0.0 : m2.imag();
           for (int c = 0; c < 3; c++) {
             const CompRef cg = pf_curl(tf[a].kind, c), vf = pf_val(tf[a2].kind, c);
-            if (cg.tc >= 0 && vf.tc >= 0) b.addp(cg.tc, cg.zd, vf.tc, vf.zd, F_W, cg.sgn * vf.sgn, m1r, m1i);
+            if (P.tensor) {   // -(curl G)^T za^H F through the fields T1R / T1I (curl component c, value component c2), see forms.hpp
+              const std::complex<double> m1t = m1 * std::complex<double>(0.0, -1.0);
+              for (int c2 = 0; c2 < 3; c2++) {
+                const CompRef v2 = pf_val(tf[a2].kind, c2);
+                if (cg.tc < 0 || v2.tc < 0) continue;
+                b.addp(cg.tc, cg.zd, v2.tc, v2.zd, F_T1R + 3 * c + c2, cg.sgn * v2.sgn, m1r, m1i);
+                if (!P.tensor_real()) b.addp(cg.tc, cg.zd, v2.tc, v2.zd, F_T1I + 3 * c + c2, cg.sgn * v2.sgn, m1t.real(), m1t.imag());
+              }
+            } else if (cg.tc >= 0 && vf.tc >= 0) b.addp(cg.tc, cg.zd, vf.tc, vf.zd, F_W, cg.sgn * vf.sgn, m1r, m1i);
             const CompRef vg = pf_val(tf[a].kind, c), cf = pf_curl(tf[a2].kind, c);
             if (vg.tc >= 0 && cf.tc >= 0) b.addp(vg.tc, vg.zd, cf.tc, cf.zd, F_W, vg.sgn * cf.sgn, m2r, m2i);
           }
@@ -247,10 +285,13 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
     for (int c = 0; c < 3; c++)
       for (int a = 0; a < 2; a++) {
         {  // B(F_i, E_jc) = -za (E_c, F_i)
-          const std::complex<double> m = -std::conj(za);
           BlockBuilder b(S, fq.id, tf[a].id, channel(0, 0, 0, tf[a].off, mapE[c]), rs ? no_channel() : channel(0, 1, 0, tf[a].off, mapE[c]));
-          const double mr = rs ? rs_real(m, 0, 0, true) : m.real(), mi = rs ? 0.0 : m.imag();
-          for (int d = 0; d < 3; d++) { const CompRef v = pf_val(tf[a].kind, d); if (v.tc >= 0) b.addp(0, 0, v.tc, v.zd, F_WJI + 3 * d + c, v.sgn, mr, mi); }
+          for (int c2 = 0; c2 < 3; c2++) {   // -(za E_c e_c, F) = -sum_c2 za(c2,c) F_c2: the identity tensor keeps c2 = c only
+            const std::complex<double> m = P.tensor ? -std::conj(za * P.epst[c2 + 3 * c]) : (c2 == c ? -std::conj(za) : std::complex<double>(0.0, 0.0));
+            if (m == std::complex<double>(0.0, 0.0)) continue;
+            const double mr = rs ? rs_real(m, 0, 0, true) : m.real(), mi = rs ? 0.0 : m.imag();
+            for (int d = 0; d < 3; d++) { const CompRef v = pf_val(tf[a].kind, d); if (v.tc >= 0) b.addp(0, 0, v.tc, v.zd, F_WJI + 3 * d + c2, v.sgn, mr, mi); }
+          }
           b.finish();
         }
         {  // B(F_i, H_jc) = B(G_i, E_jc) = (H_c, curl F_i)

@@ -1023,6 +1023,17 @@ int celem_impl(int plan, int nel, const int *etype, const int *norder, const int
   CelemCall cc;
   cc.aoff.resize(nel + 1);
   cc.xptr = xptr; cc.isym = isym_flag;
+  {   // compile the signatures this call meets for the first time CONCURRENTLY before the (serial) validation loop looks them up
+    std::map<std::string, int> first;
+    for (int e = 0; e < nel; e++) {
+      const int et = etype ? etype[e] : HP3D_MDLB;
+      if (et != HP3D_MDLB && et != HP3D_MDLP) return fail(HP3D_EINVAL, "element %d: unknown element type %d", e, et);
+      first.emplace(Plan::key(et, norder + 19 * e, norie + 12 * e, norif + 6 * e), e);
+    }
+    std::vector<std::pair<std::string, int>> missing;
+    for (auto &kv : first) if (!p->find(kv.first)) missing.emplace_back(kv.first, kv.second);
+    if (p->compile_missing(missing, etype, norder, norie, norif, err)) return fail(HP3D_EINVAL, "%s", err.c_str());
+  }
   for (int e = 0; e < nel; e++) {
     if (mptr[e + 1] < mptr[e] || xptr[e + 1] < xptr[e]) return fail(HP3D_EINVAL, "celem_batch: element %d: prefix arrays must be non-decreasing", e);
     Signature *S = p->get(etype ? etype[e] : HP3D_MDLB, norder + 19 * e, norie + 12 * e, norif + 6 * e, false, err);
@@ -1337,20 +1348,34 @@ int hp3d_gpu_stc_bwd_batch(int cplx, int nel, int ni, int nb, const void *ASchur
   std::lock_guard<std::recursive_mutex> lk(g_mu);
   if (int drc = enter_device()) return drc;
   if (nel <= 0 || ni <= 0 || nb <= 0) return fail(HP3D_EINVAL, "bad sizes");
+  if (!ASchur || !BSchur || !xi || !xb) return fail(HP3D_EINVAL, "null argument");
+  if (sAS < (long long)nb * ni || sBS < nb || sxi < ni || sxb < nb) return fail(HP3D_EINVAL, "stc_bwd_batch: a stride is shorter than its block");
   const size_t es = sizeof(double) * (cplx ? 2 : 1);
-  double *dA, *dB, *dx, *dy;
-  // element e of each host array sits at e*stride; copy the used extents as 2-D blocks
-  CUDA_TRY(cudaMalloc(&dA, es * (size_t)nb * ni * nel)); CUDA_TRY(cudaMalloc(&dB, es * (size_t)nb * nel));
-  CUDA_TRY(cudaMalloc(&dx, es * (size_t)ni * nel)); CUDA_TRY(cudaMalloc(&dy, es * (size_t)nb * nel));
-  CUDA_TRY(cudaMemcpy2D(dA, es * nb * ni, ASchur, es * sAS, es * nb * ni, nel, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy2D(dB, es * nb, BSchur, es * sBS, es * nb, nel, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy2D(dx, es * ni, xi, es * sxi, es * ni, nel, cudaMemcpyHostToDevice));
-  dim3 grid((nb + 7) / 8, nel);
-  if (cplx) stc_bwd_kernel<true><<<grid, 256>>>(nullptr, nullptr, ni, nb, dA, (long long)nb * ni, dB, nb, dx, ni, dy, nb);
-  else stc_bwd_kernel<false><<<grid, 256>>>(nullptr, nullptr, ni, nb, dA, (long long)nb * ni, dB, nb, dx, ni, dy, nb);
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpy2D(xb, es * sxb, dy, es * nb, es * nb, nel, cudaMemcpyDeviceToHost));
-  cudaFree(dA); cudaFree(dB); cudaFree(dx); cudaFree(dy);
+  // chunks bounded by the grid limit (65535 elements) and by a quarter of the free device memory; buffers released on every path
+  size_t fr = 0, tot = 0;
+  CUDA_TRY(cudaMemGetInfo(&fr, &tot));
+  const size_t per = es * ((size_t)nb * ni + 2 * (size_t)nb + ni);
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(nel, 65535), (fr / 4) / per));
+  struct Bufs {
+    double *p[4] = {nullptr, nullptr, nullptr, nullptr};
+    ~Bufs() { for (double *q : p) if (q) cudaFree(q); }
+  } b;
+  CUDA_TRY(cudaMalloc(&b.p[0], es * (size_t)nb * ni * chunk)); CUDA_TRY(cudaMalloc(&b.p[1], es * (size_t)nb * chunk));
+  CUDA_TRY(cudaMalloc(&b.p[2], es * (size_t)ni * chunk)); CUDA_TRY(cudaMalloc(&b.p[3], es * (size_t)nb * chunk));
+  for (int c0 = 0; c0 < nel; c0 += chunk) {
+    const int n = std::min(chunk, nel - c0);
+    // element e of each host array sits at e*stride; copy the used extents as 2-D blocks
+    CUDA_TRY(cudaMemcpy2DAsync(b.p[0], es * nb * ni, (const char *)ASchur + es * sAS * c0, es * sAS, es * nb * ni, n, cudaMemcpyHostToDevice, g_compute));
+    CUDA_TRY(cudaMemcpy2DAsync(b.p[1], es * nb, (const char *)BSchur + es * sBS * c0, es * sBS, es * nb, n, cudaMemcpyHostToDevice, g_compute));
+    CUDA_TRY(cudaMemcpy2DAsync(b.p[2], es * ni, (const char *)xi + es * sxi * c0, es * sxi, es * ni, n, cudaMemcpyHostToDevice, g_compute));
+    dim3 grid((nb + 7) / 8, n);
+    if (cplx) stc_bwd_kernel<true><<<grid, 256, 0, g_compute>>>(nullptr, nullptr, ni, nb, b.p[0], (long long)nb * ni, b.p[1], nb, b.p[2], ni, b.p[3], nb);
+    else stc_bwd_kernel<false><<<grid, 256, 0, g_compute>>>(nullptr, nullptr, ni, nb, b.p[0], (long long)nb * ni, b.p[1], nb, b.p[2], ni, b.p[3], nb);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy2DAsync((char *)xb + es * sxb * c0, es * sxb, b.p[3], es * nb, es * nb, n, cudaMemcpyDeviceToHost, g_compute));
+    CUDA_TRY(cudaStreamSynchronize(g_compute));
+  }
   return HP3D_OK;
 }
 
@@ -1420,15 +1445,41 @@ int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, con
   if (int brc = build_classes(p, nel, etype, norder, norie, norif, true, classes, err)) return fail(brc, "%s", err.c_str());
   const GeomParams gp = p->geom();
   // resident inputs per class: geometry dofs (uniform stride 3*nH_max) and the per-element dof counts
-  struct Grp { ClassGroup *C; double *dx; int *dcnt; int n, chunk; };
+  struct Grp { ClassGroup *C; double *dx; int *dcnt; int n, chunk; double work; };
   std::vector<Grp> gs;
-  for (ClassGroup &C : classes) {
+  // Several dense classes (hp meshes): every lane owns a partition of the arena and chunks of DIFFERENT classes run side by side
+  // on different lanes, no drain between classes.  Classes go in order of decreasing work; a class that carries a large share of
+  // the call is still split over the lanes (it would otherwise be the tail on one lane), a small one stays whole: fewer, larger launches.
+  const bool multi = classes.size() > 1 && lanes > 1;
+  double work_total = 0.0;
+  std::vector<double> work(classes.size(), 0.0);
+  for (size_t i = 0; i < classes.size(); i++) {
+    const DenseDims &d = classes[i].shape.d;
+    const double n = d.np, m = d.M();
+    work[i] = (double)classes[i].el.size() * (n * n * n / 3.0 + n * n * m + n * m * m + m * m * m / 3.0 + 1e6);
+    work_total += work[i];
+  }
+  if (multi) {
+    std::vector<size_t> ord(classes.size());
+    for (size_t i = 0; i < ord.size(); i++) ord[i] = i;
+    std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return work[a] > work[b]; });
+    std::vector<ClassGroup> sorted; std::vector<double> w2;
+    for (size_t i : ord) { sorted.push_back(std::move(classes[i])); w2.push_back(work[i]); }
+    classes.swap(sorted); work.swap(w2);
+  }
+  size_t part_dev = 0, part_host = 0;
+  for (size_t ci = 0; ci < classes.size(); ci++) {
+    ClassGroup &C = classes[ci];
     int want = (int)C.el.size();
-    want = (want + lanes - 1) / lanes;
+    if (!multi || work[ci] > work_total / (2.0 * lanes)) want = (want + lanes - 1) / lanes;
     if (max_chunk > 0 && want > max_chunk) want = max_chunk;
-    const int cap = chunk_capacity(C.shape, want, lanes);
+    int cap = chunk_capacity(C.shape, want, lanes);
     if (cap < 1) return fail(HP3D_ENOMEM, "not enough device memory");
-    if (g_lanes.reserve(C.shape, cap, err, lanes)) return fail(HP3D_ENOMEM, "%s", err.c_str());   // grows the arena to the largest class
+    if (multi) {
+      size_t db, hb;
+      LaneSet::lane_bytes(C.shape, cap, db, hb);
+      part_dev = std::max(part_dev, db); part_host = std::max(part_host, hb);
+    } else if (g_lanes.reserve(C.shape, cap, err, lanes)) return fail(HP3D_ENOMEM, "%s", err.c_str());   // grows the arena to the largest class
     const size_t nx = 3 * (size_t)C.shape.nH_max, n = C.el.size();
     std::vector<double> hx(nx * n, 0.0);
     std::vector<int> hc(3 * n);
@@ -1441,7 +1492,12 @@ int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, con
     CUDA_TRY(cudaMemcpy(dx, hx.data(), sizeof(double) * hx.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&dc, sizeof(int) * hc.size()));
     CUDA_TRY(cudaMemcpy(dc, hc.data(), sizeof(int) * hc.size(), cudaMemcpyHostToDevice));
-    gs.push_back(Grp{&C, dx, dc, (int)n, cap});
+    gs.push_back(Grp{&C, dx, dc, (int)n, cap, work[ci]});
+  }
+  if (multi) {
+    int need = 1;
+    for (ClassGroup &C : classes) need = std::max(need, std::max(C.shape.d.ni, C.shape.d.nb) + 1);
+    if (LaneSet::ensure_partitions(part_dev, part_host, err) || g_lanes.ensure_iota(need, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());
   }
   std::vector<StageEvents> evs;
   cudaEvent_t t0, t1, tj, tsw[LaneSet::NLANE];
@@ -1455,7 +1511,7 @@ int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, con
   std::vector<Seg> segs;
   for (int r = 0; r < reps; r++)
     for (Grp &g : gs) {
-      if (gs.size() > 1) {   // another class's buffers occupy the arena: both lanes must drain before they are re-bound
+      if (gs.size() > 1 && !multi) {   // another class's buffers occupy the arena: both lanes must drain before they are re-bound
         for (int i = 0; i < lanes; i++) cudaEventRecord(tsw[i], g_lane_stream[i]);
         for (int i = 0; i < lanes; i++)
           for (int j = 0; j < lanes; j++) if (i != j) cudaStreamWaitEvent(g_lane_stream[i], tsw[j], 0);
@@ -1465,6 +1521,7 @@ int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, con
       const long long nx = 3LL * g.C->shape.nH_max;
       for (int c0 = 0; c0 < g.n; c0 += g.chunk, k++) {
         const int n = std::min(g.n - c0, g.chunk), ln = k % lanes;
+        if (multi) g_lanes.bind_lane(ln, g.C->shape, g.chunk);   // this lane's partition, ordered after the lane's earlier work by its stream
         Lane &L = g_lanes.lane[ln];
         StageEvents ev;
         ev.on = (lanes == 1);

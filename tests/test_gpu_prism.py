@@ -231,3 +231,50 @@ def test_edge_cases(gpu):
     with pytest.raises(RuntimeError, match="DPG"):
         ElemEngine(1).elem_residual_batch(no[None], ne[None], nf[None], X, np.zeros((1, 4)), np.zeros((1, 4)), etype=P)
     eng.close()
+
+
+@pytest.mark.parametrize("test_norm", [1, 2, 3])
+@pytest.mark.parametrize("tensor,rr", [("real", 1), ("complex", 1), ("complex", 0)])
+def test_prism_uw_maxwell_permittivity_tensor(oracle, gpu, test_norm, tensor, rr):
+    """the permittivity tensor of tests/test_gpu_parity.py::test_uw_maxwell_permittivity_tensor on PRISMS (mixed with a brick in the
+    same call): Gram, cross and stiffness terms through the (triangle function) x (z table) families against the oracle"""
+    import ctypes as C
+    from hp3d_b200.api import ElemEngine
+    from tests.test_oracle_prism import prism_signature
+    from tests.util import hexa_xnod, random_signature
+    oracle.set_maxp(6)
+    oracle.use_blas(True)
+    rng = np.random.default_rng(888 + test_norm)
+    B, P = oracle.MDLB, oracle.MDLP
+    items = []
+    for e in range(3):
+        if e == 1:
+            no, ne, nf = random_signature(rng, pmax=2)
+            items.append((B, no, ne, nf, hexa_xnod(oracle.celndof(no, B)[0], h=0.4, jitter=0.1, rng=rng)))
+        else:
+            no, ne, nf = prism_signature(rng, 2, int(rng.integers(1, 3)), uniform=False)
+            items.append((P, no, ne, nf, prism_xnod(oracle.celndof(no, P)[0], rng)))
+    nel = len(items)
+    et = np.array([it[0] for it in items], np.int32)
+    norder = np.stack([it[1] for it in items]); norie = np.stack([it[2] for it in items]); norif = np.stack([it[3] for it in items])
+    X = np.zeros((nel, max(it[4].shape[0] for it in items), 3))
+    for e, it in enumerate(items):
+        X[e, :it[4].shape[0]] = it[4]
+    T = np.eye(3) + 0.3 * rng.standard_normal((3, 3))
+    if tensor == "complex":
+        T = T + 0.2j * rng.standard_normal((3, 3))
+    kw = dict(omega=1.3 * np.pi, eps=1.5, mu=0.8, alpha_norm=0.6, test_norm=test_norm, eps_tensor=T)
+    eng = ElemEngine(4, real_reduction=rr, source=9, maxp=6, **kw)
+    nint = max(eng.sizes(norder[e], int(et[e]))[2] for e in range(nel))
+    J = rng.standard_normal((nel, nint, 3)) + 1j * rng.standard_normal((nel, nint, 3))
+    res = eng.elem_stc_batch(norder, norie, norif, X, source_qp=J, etype=et)
+    assert (res["info"] == 0).all()
+    for e, it in enumerate(items):
+        ni_e = eng.sizes(norder[e], int(et[e]))[2]
+        tab = np.ascontiguousarray(J[e, :ni_e])
+        prm = oracle.default_params(source=9, source_table=tab.ctypes.data_as(C.c_void_p), **kw)
+        Aii, Bi, AS, BS = eng.unpack(res, e)
+        rA, rB, rAS, rBS = oracle.condensed(4, it[1], it[2], it[3], it[4], prm, etype=it[0])
+        assert relerr(Aii, rA) < 1e-12 and relerr(Bi, rB) < 1e-12, (e, it[0], relerr(Aii, rA), relerr(Bi, rB))
+        assert relerr(AS, rAS) < 1e-9 and relerr(BS, rBS) < 1e-9
+    eng.close()
