@@ -1471,7 +1471,8 @@ int hp3d_gpu_bench_t(int plan, int nel, const int *etype, const int *norder, con
   for (size_t ci = 0; ci < classes.size(); ci++) {
     ClassGroup &C = classes[ci];
     int want = (int)C.el.size();
-    if (!multi || work[ci] > work_total / (2.0 * lanes)) want = (want + lanes - 1) / lanes;
+    static const double split_frac = getenv("HP3D_SPLIT_FRAC") ? atof(getenv("HP3D_SPLIT_FRAC")) : 2.0;   // of one lane's share of the call
+    if (!multi || work[ci] > split_frac * work_total / lanes) want = (want + lanes - 1) / lanes;
     if (max_chunk > 0 && want > max_chunk) want = max_chunk;
     int cap = chunk_capacity(C.shape, want, lanes);
     if (cap < 1) return fail(HP3D_ENOMEM, "not enough device memory");
