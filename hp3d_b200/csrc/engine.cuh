@@ -112,30 +112,58 @@ struct Signature {
   double *d_tab = nullptr, *d_wq = nullptr, *d_CW = nullptr, *d_ttab = nullptr;
   int *d_hdof = nullptr, *d_maps = nullptr, *d_crow = nullptr;
   FamilyDesc *d_fam = nullptr; TermDesc *d_term = nullptr; SlotDesc *d_slot = nullptr; BlockDesc *d_block = nullptr; WorkItem *d_work = nullptr;
+  std::shared_ptr<char> slab;   // device allocation shared with the other signatures uploaded by the same call (upload_many)
+  size_t off_[12] = {0};
   ~Signature() { cudaFree(d_blob); }
   int ns() const { return h.cplx ? 2 : 1; }
   size_t src_doubles() const { return (size_t)h.nint * (h.cplx ? 6 : 1); }
+  // the 12 table sections of the signature: (host address, bytes)
+  void sections(const void *src[12], size_t bytes[12]) const {
+    src[0] = h.tab.data(); bytes[0] = sizeof(double) * h.tab.size(); src[1] = h.wq.data(); bytes[1] = sizeof(double) * h.wq.size();
+    src[2] = h.hdof.data(); bytes[2] = sizeof(int) * h.hdof.size(); src[3] = h.maps.data(); bytes[3] = sizeof(int) * h.maps.size();
+    src[4] = h.fam.data(); bytes[4] = sizeof(FamilyDesc) * h.fam.size(); src[5] = h.term.data(); bytes[5] = sizeof(TermDesc) * h.term.size();
+    src[6] = h.slot.data(); bytes[6] = sizeof(SlotDesc) * h.slot.size(); src[7] = h.block.data(); bytes[7] = sizeof(BlockDesc) * h.block.size();
+    src[8] = h.work.data(); bytes[8] = sizeof(WorkItem) * h.work.size(); src[9] = h.crow.data(); bytes[9] = sizeof(int) * h.crow.size();
+    src[10] = h.CW.data(); bytes[10] = sizeof(double) * h.CW.size(); src[11] = h.ttab.data(); bytes[11] = sizeof(double) * h.ttab.size();
+  }
+  // reserve room for the sections behind `off` bytes (256-byte aligned each); returns the new end
+  size_t plan_offsets(size_t off) {
+    const void *src[12]; size_t bytes[12];
+    sections(src, bytes);
+    for (int i = 0; i < 12; i++) { off = (off + 255) & ~(size_t)255; off_[i] = off; off += bytes[i]; }
+    return off;
+  }
+  int copy_sections(char *base, std::string &err) const {   // straight from the host tables (no intermediate blob: the trace-pairing rows CW are tens of MB)
+    const void *src[12]; size_t bytes[12];
+    sections(src, bytes);
+    for (int i = 0; i < 12; i++)
+      if (bytes[i]) HP3D_CK(cudaMemcpy(base + off_[i], src[i], bytes[i], cudaMemcpyHostToDevice));
+    return 0;
+  }
+  void bind(char *base) {   // base = device address of the blob's first byte
+    auto at = [&](size_t off, size_t n) -> char * { return n ? base + off : nullptr; };
+    d_tab = (double *)at(off_[0], h.tab.size()); d_wq = (double *)at(off_[1], h.wq.size()); d_hdof = (int *)at(off_[2], h.hdof.size());
+    d_maps = (int *)at(off_[3], h.maps.size()); d_fam = (FamilyDesc *)at(off_[4], h.fam.size()); d_term = (TermDesc *)at(off_[5], h.term.size());
+    d_slot = (SlotDesc *)at(off_[6], h.slot.size()); d_block = (BlockDesc *)at(off_[7], h.block.size()); d_work = (WorkItem *)at(off_[8], h.work.size());
+    d_crow = (int *)at(off_[9], h.crow.size()); d_CW = (double *)at(off_[10], h.CW.size()); d_ttab = (double *)at(off_[11], h.ttab.size());
+  }
   int upload(std::string &err) {
-    std::vector<char> blob;
-    auto put = [&](const void *src, size_t bytes) -> size_t {   // 256-byte aligned sections
-      const size_t off = (blob.size() + 255) & ~(size_t)255;
-      blob.resize(off + bytes);
-      if (bytes) memcpy(blob.data() + off, src, bytes);
-      return off;
-    };
-    const size_t o_tab = put(h.tab.data(), sizeof(double) * h.tab.size()), o_wq = put(h.wq.data(), sizeof(double) * h.wq.size()),
-                 o_hdof = put(h.hdof.data(), sizeof(int) * h.hdof.size()), o_maps = put(h.maps.data(), sizeof(int) * h.maps.size()),
-                 o_fam = put(h.fam.data(), sizeof(FamilyDesc) * h.fam.size()), o_term = put(h.term.data(), sizeof(TermDesc) * h.term.size()),
-                 o_slot = put(h.slot.data(), sizeof(SlotDesc) * h.slot.size()), o_block = put(h.block.data(), sizeof(BlockDesc) * h.block.size()),
-                 o_work = put(h.work.data(), sizeof(WorkItem) * h.work.size()), o_crow = put(h.crow.data(), sizeof(int) * h.crow.size()),
-                 o_CW = put(h.CW.data(), sizeof(double) * h.CW.size()), o_ttab = put(h.ttab.data(), sizeof(double) * h.ttab.size());
-    HP3D_CK(cudaMalloc((void **)&d_blob, blob.size() + 256));
-    HP3D_CK(cudaMemcpy(d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
-    auto at = [&](size_t off, size_t n) -> char * { return n ? d_blob + off : nullptr; };
-    d_tab = (double *)at(o_tab, h.tab.size()); d_wq = (double *)at(o_wq, h.wq.size()); d_hdof = (int *)at(o_hdof, h.hdof.size());
-    d_maps = (int *)at(o_maps, h.maps.size()); d_fam = (FamilyDesc *)at(o_fam, h.fam.size()); d_term = (TermDesc *)at(o_term, h.term.size());
-    d_slot = (SlotDesc *)at(o_slot, h.slot.size()); d_block = (BlockDesc *)at(o_block, h.block.size()); d_work = (WorkItem *)at(o_work, h.work.size());
-    d_crow = (int *)at(o_crow, h.crow.size()); d_CW = (double *)at(o_CW, h.CW.size()); d_ttab = (double *)at(o_ttab, h.ttab.size());
+    const size_t total = plan_offsets(0);
+    HP3D_CK(cudaMalloc((void **)&d_blob, total + 256));
+    if (copy_sections(d_blob, err)) return -1;
+    bind(d_blob);
+    return 0;
+  }
+  // all tables of the signatures a call meets for the first time in ONE device allocation (an hp mesh brings hundreds of
+  // signatures per call)
+  static int upload_many(const std::vector<Signature *> &sigs, std::string &err) {
+    if (sigs.empty()) return 0;
+    size_t total = 0;
+    for (Signature *S : sigs) total = S->plan_offsets(total);
+    char *base = nullptr;
+    HP3D_CK(cudaMalloc((void **)&base, total + 256));
+    std::shared_ptr<char> slab(base, [](char *q) { cudaFree(q); });
+    for (Signature *S : sigs) { if (S->copy_sections(base, err)) return -1; S->bind(base); S->slab = slab; }
     return 0;
   }
 };

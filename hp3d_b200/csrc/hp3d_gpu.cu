@@ -156,6 +156,11 @@ int build_classes(Plan *p, int nel, const int *etype, const int *norder, const i
               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   }
   const auto t_up0 = std::chrono::steady_clock::now();
+  if (device) {   // tables of all signatures that are not resident yet: one allocation, one copy
+    std::vector<Signature *> fresh;
+    for (auto &g : bysig) { Signature *S = p->find(g.first); if (S && !S->d_tab) fresh.push_back(S); }
+    if (Signature::upload_many(fresh, err)) return HP3D_ENOMEM;
+  }
   for (auto &g : bysig) {
     const int e0 = g.second[0];
     Signature *S = p->get(etype ? etype[e0] : HP3D_MDLB, norder + 19 * e0, norie + 12 * e0, norif + 6 * e0, device, err);
