@@ -344,7 +344,7 @@ __device__ __forceinline__ void tp_stage2(const Tp3Args &A, const BlockDesc &B, 
   const int nM = nAz * TB, nN = (nij + 7) >> 3;
   const bool own = F.mt >= 0;   // fragments prepared once per CTA
   const ChannelDesc c0 = B.ch[0], c1 = B.ch[1];
-  const bool has0 = c0.mat >= 0, has1 = c1.mat >= 0;
+  const bool has1 = c1.mat >= 0;
   for (int mt = own ? F.mt : warp; mt < nM; mt += (own ? nM : nwarp)) {
     const int kA = mt / TB, kB = 8 * (mt % TB) + gq;
     if (!own) {   // fewer warps than m-tiles: rebuild the fragments for this m-tile
@@ -372,15 +372,17 @@ __device__ __forceinline__ void tp_stage2(const Tp3Args &A, const BlockDesc &B, 
       const MatTarget M = A.mat[C.mat];
       dst[ch] = M.base + (long long)e * M.batch + (long long)C.plane * M.plane + row * M.ld;
     }
+    // column of the thread's first entry inside the output row for ij0 = 0 (32-bit arithmetic; the maps, if any, are applied per entry)
+    const int cb0 = nij * kB + 2 * tq;
+    const int cm0 = c0.colmap, cm1 = c1.colmap;
+    int roff[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) roff[ks] = min(4 * ks + tq, NMAX - 1) * nij;   // rows qz = 4 ks + tq (clamped: the A fragment is zero there)
+    const int ustride = NMAX * nij;
     for (int nt = own ? F.part : 0; nt < nN; nt += (own ? F.nsplit : 1)) {
       const int ij0 = 8 * nt;
-      // B fragment addresses: column ij0+gq (clamped: columns >= nij are dropped at the store), rows qz = 4 ks + tq (clamped: the
-      // A fragment is zero there)
-      const int colb = min(ij0 + gq, nij - 1);
-      const double *Up = sU + colb;
-      int roff[KS];
-#pragma unroll
-      for (int ks = 0; ks < KS; ks++) roff[ks] = min(4 * ks + tq, NMAX - 1) * nij;
+      // B fragment: column ij0+gq (clamped: columns >= nij are dropped at the store)
+      const double *Up = sU + min(ij0 + gq, nij - 1);
       double acc0[2] = {0.0, 0.0}, acc1[2] = {0.0, 0.0};
 #pragma unroll
       for (int s = 0; s < TP_SMAX; s++) {
@@ -389,25 +391,30 @@ __device__ __forceinline__ void tp_stage2(const Tp3Args &A, const BlockDesc &B, 
 #pragma unroll
           for (int ks = 0; ks < KS; ks++) dmma_tile(d0, d1, F.a[s][ks], Up[roff[ks]]);
           const double2 k = *reinterpret_cast<const double2 *>(sC + 2 * s);
-          if (has0) { acc0[0] += k.x * d0; acc0[1] += k.x * d1; }
+          acc0[0] += k.x * d0; acc0[1] += k.x * d1;
           if (has1) { acc1[0] += k.y * d0; acc1[1] += k.y * d1; }
-          Up += NMAX * nij;
+          Up += ustride;
         }
       }
       // the thread holds (kB, ij0 + 2 tq) and (kB, ij0 + 2 tq + 1) of both channels
+      const int ij = ij0 + 2 * tq;
+      if (ij >= nij) continue;
+      const bool two = ij + 1 < nij;
 #pragma unroll
       for (int ch = 0; ch < 2; ch++) {
-        if (!dst[ch]) continue;
-        const ChannelDesc C = ch ? c1 : c0;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const int ij = ij0 + 2 * tq + h;
-          if (ij >= nij) continue;
-          const int lB = ij + nij * kB;
-          long long col; double sc = sg[ch];
-          if (C.colmap >= 0) { const int m = A.maps[C.colmap + lB]; if (m == 0) continue; col = (m < 0 ? -m : m) - 1; if (m < 0) sc = -sc; }
-          else col = C.col0 + lB;
-          dst[ch][col] = sc * (ch ? acc1[h] : acc0[h]);
+        double *row = dst[ch];
+        if (!row) continue;
+        const int cm = ch ? cm1 : cm0;
+        const double v0 = sg[ch] * (ch ? acc1[0] : acc0[0]), v1 = sg[ch] * (ch ? acc1[1] : acc0[1]);
+        if (cm < 0) {
+          double *q = row + (ch ? c1.col0 : c0.col0) + cb0 + ij0;
+          q[0] = v0;
+          if (two) q[1] = v1;
+        } else {
+          const int lB = cb0 + ij0;
+          int m = A.maps[cm + lB];
+          if (m != 0) row[(m < 0 ? -m : m) - 1] = m < 0 ? -v0 : v0;
+          if (two) { m = A.maps[cm + lB + 1]; if (m != 0) row[(m < 0 ? -m : m) - 1] = m < 0 ? -v1 : v1; }
         }
       }
     }
@@ -509,20 +516,27 @@ __global__ void __launch_bounds__(448, 2) tp3_kernel(Tp3Args A, int off_F, int o
   __syncthreads();   // sZ, sT1, Q(0) complete
   Stage2Frag<NMAX> frag;
   tp_stage2_prepare<NMAX>(A, B, sZ, nAz, frag);
+  // the y-contraction item of this thread is the same for every jA (the CTA covers all items in one pass whenever it can)
+  const int nitems = nij * nqz;
+  const bool one_pass = nitems <= (int)blockDim.x;
+  int my_q0 = 0, my_t0 = 0;
+  if (one_pass && tid < nitems) { const int ij = tid % nij, qz = tid / nij; my_q0 = (ij / nBx) * NQP; my_t0 = (qz * nBx + ij % nBx) * NQP; }
+  const int qstride = nBy * NQP;
   for (int jA = 0; jA < nAy; jA++) {
     // ---- y contraction: U[slot][qz][ij] = sum over the slot's terms and qy of Q[t][jB][qy] * T1[t][qz][iB][qy]
     const double *Q = sQ + (size_t)(jA & 1) * qsz;
-    for (int o = tid; o < nij * nqz; o += blockDim.x) {
-      const int ij = o % nij, qz = o / nij, iB = ij % nBx, jB = ij / nBx;
-      const double *q0 = Q + jB * NQP, *t0 = sT1 + ((size_t)qz * nBx + iB) * NQP;
+    for (int o = tid; o < nitems; o += blockDim.x) {
+      int q0off = my_q0, t0off = my_t0;
+      if (!one_pass) { const int ij = o % nij, qz = o / nij; q0off = (ij / nBx) * NQP; t0off = (qz * nBx + ij % nBx) * NQP; }
+      const double *q0 = Q + q0off, *t0 = sT1 + t0off;
       for (int sl = 0; sl < B.ns; sl++) {
         double acc = 0.0;
         for (int t = sbeg[sl]; t < sbeg[sl + 1]; t++) {
-          const double2 *q = reinterpret_cast<const double2 *>(q0 + t * nBy * NQP), *t1 = reinterpret_cast<const double2 *>(t0 + (size_t)t * t1sz);
+          const double2 *q = reinterpret_cast<const double2 *>(q0 + t * qstride), *t1 = reinterpret_cast<const double2 *>(t0 + t * t1sz);
 #pragma unroll
           for (int h = 0; h < NMAX / 2; h++) { const double2 a = q[h], b = t1[h]; acc += a.x * b.x; acc += a.y * b.y; }
         }
-        sU[(size_t)sl * NMAX * nij + o] = acc;   // o = qz*nij + ij, qz < nqz
+        sU[sl * NMAX * nij + o] = acc;   // o = qz*nij + ij, qz < nqz
       }
     }
     __syncthreads();
