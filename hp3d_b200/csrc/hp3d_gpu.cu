@@ -700,181 +700,219 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t_begin = now();
   double t_wait = 0.0, t_stage = 0.0;
-  for (ClassGroup &C : classes) {
-    if (rc != HP3D_OK) break;
+  // ---- chunk plan of the whole call.  Every lane owns a partition of the arena (LaneSet::bind_lane) and is bound to the class
+  // of the chunk it runs, so chunks of DIFFERENT dense classes (hp meshes) follow each other on the lanes without draining the
+  // device in between; classes go in order of decreasing work.  A chunk is identified by its global number k: lane k % NL,
+  // output buffer (k / NL) & 1.
+  struct CInfo { ClassGroup *C; int cap; size_t NS, es, nx, nsrc, sA, sB, sS, sT; };
+  struct Rec { int ci; size_t c0; int n; const int *h_info; const double *h_xb, *h_res; bool collected; };
+  std::vector<CInfo> cinfo;
+  std::vector<Rec> recs;
+  {
+    std::vector<size_t> ord(classes.size());
+    for (size_t i = 0; i < ord.size(); i++) ord[i] = i;
+    auto work = [&](const ClassGroup &C) { const double n = C.shape.d.np, m = C.shape.d.M(); return (double)C.el.size() * (n * n * n / 3.0 + n * n * m + n * m * m + m * m * m / 3.0 + 1e6); };
+    std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return work(classes[a]) > work(classes[b]); });
+    size_t part_dev = 0, part_host = 0;
+    int need_iota = 1;
+    for (size_t oi : ord) {
+      ClassGroup &C = classes[oi];
+      const ChunkShape &sh = C.shape;
+      // chunks of up to 64 elements round-robin over the lanes, with a ramped start and a tapered end (chunk_plan)
+      int want = (int)C.el.size();
+      if (g_max_chunk > 0) want = std::min(want, g_max_chunk);
+      else want = std::min(64, std::max(4, (want + NL - 1) / NL));   // small groups are spread over the lanes
+      if (classes.size() > 1 && g_max_chunk <= 0) want = std::min(64, (int)C.el.size());   // several classes: a small class stays whole
+      const int cap = chunk_capacity(sh, want, NL);
+      if (cap < 1) return fail(HP3D_ENOMEM, "not enough device memory for one element");
+      size_t db, hb;
+      LaneSet::lane_bytes(sh, cap, db, hb);
+      part_dev = std::max(part_dev, db); part_host = std::max(part_host, hb);
+      need_iota = std::max(need_iota, std::max(sh.d.ni, sh.d.nb) + 1);
+      CInfo ci;
+      ci.C = &C; ci.cap = cap; ci.NS = sh.ns(); ci.es = sizeof(double) * ci.NS;
+      ci.nx = 3 * (size_t)sh.nH_max; ci.nsrc = sh.src_max;
+      ci.sA = (size_t)sh.d.ni * sh.d.ni; ci.sB = sh.d.ni; ci.sS = (size_t)sh.d.nb * sh.d.ni; ci.sT = sh.d.nb;   // device staging strides
+      const std::vector<size_t> sizes = chunk_plan(C.el.size(), cap, NL, g_max_chunk);
+      size_t c0 = 0;
+      for (size_t n : sizes) { recs.push_back(Rec{(int)cinfo.size(), c0, (int)n, nullptr, nullptr, nullptr, false}); c0 += n; }
+      cinfo.push_back(ci);
+    }
+    if (LaneSet::ensure_partitions(part_dev, part_host, err) || g_lanes.ensure_iota(need_iota, err)) return fail(HP3D_ENOMEM, "%s", err.c_str());
+  }
+  const int nrec = (int)recs.size();
+  int next_mirror = 0;
+  int bound[NL];
+  for (int i = 0; i < NL; i++) bound[i] = -1;
+  auto mirror_chunk = [&](int k) {   // aii_packed = 2: chunk k's trapezoids are on the host; hand its elements to the mirror threads
+    const Rec &R = recs[k];
+    const CInfo &I = cinfo[R.ci];
+    for (size_t i = R.c0; i < R.c0 + R.n; i++)
+      if (I.C->sig[i]->h.ni > TRAP_W) g_pool.push(MirrorTask{(double *)((char *)Aii + I.es * (size_t)sAii * I.C->el[i]), I.C->sig[i]->h.ni, I.NS == 2});
+    next_mirror = k + 1;
+  };
+  auto collect_info = [&](int k) {   // host side of chunk k: wait for its D2H, publish info[] (and the small results)
+    Rec &R = recs[k];
+    if (R.collected) return;
+    R.collected = true;
+    const CInfo &I = cinfo[R.ci];
+    const int slot = (k % NL) * 2 + ((k / NL) & 1);
+    cudaEventSynchronize(evCopy[slot]);
+    if (trap) while (next_mirror <= k) mirror_chunk(next_mirror);   // the copy stream is in order: earlier chunks have landed too
+    for (int i = 0; i < R.n; i++) {
+      const int e = I.C->el[R.c0 + i];
+      if (info) info[e] = R.h_info[i];
+      if (mode == MODE_BWD) memcpy((char *)xb + I.es * sxb * e, R.h_xb + I.NS * (I.sT + 1) * i, I.es * I.C->sig[R.c0 + i]->h.nb);
+      if (mode == MODE_RESID) resid[e] = R.h_res[i];
+    }
+  };
+  for (int k = 0; k < nrec; k++) {
+    Rec &R = recs[k];
+    const CInfo &I = cinfo[R.ci];
+    ClassGroup &C = *I.C;
     const std::vector<int> &el = C.el;
     const ChunkShape &sh = C.shape;
-    // chunk plan: chunks of up to 64 elements round-robin over the lanes, with a ramped start and a tapered end (below)
-    int want = (int)el.size();
-    if (g_max_chunk > 0) want = std::min(want, g_max_chunk);
-    else want = std::min(64, std::max(4, (want + NL - 1) / NL));   // small groups are spread over the lanes
-    const int cap = chunk_capacity(sh, want, NL);
-    if (cap < 1) { rc = fail(HP3D_ENOMEM, "not enough device memory for one element"); break; }
-    if (g_lanes.reserve(sh, cap, err, NL)) { rc = fail(HP3D_ENOMEM, "%s", err.c_str()); break; }
-    const size_t NS = sh.ns(), es = sizeof(double) * NS;
-    const size_t nx = 3 * (size_t)sh.nH_max, nsrc = sh.src_max;
-    const size_t sA = (size_t)sh.d.ni * sh.d.ni, sB = sh.d.ni, sS = (size_t)sh.d.nb * sh.d.ni, sT = sh.d.nb;   // device staging strides
-    const int lcap = g_lanes.cap;
-    std::vector<size_t> cstart;   // chunk k covers el[cstart[k] .. cstart[k+1])
-    {
-      const std::vector<size_t> sizes = chunk_plan(el.size(), cap, NL, g_max_chunk);
-      size_t c0 = 0;
-      for (size_t n : sizes) { cstart.push_back(c0); c0 += n; }
-      cstart.push_back(el.size());
+    const size_t NS = I.NS, es = I.es, nx = I.nx, nsrc = I.nsrc, sA = I.sA, sB = I.sB, sS = I.sS, sT = I.sT, c0 = R.c0;
+    const int n = R.n, ln = k % NL, ob = (k / NL) & 1, slot = ln * 2 + ob, lcap = I.cap;
+    cudaStream_t st = g_lane_stream[ln];
+    const double tw0 = now();
+    if (big) { if (k >= NSLOT) collect_info(k - NSLOT); }   // this slot's previous results are on the host
+    else if (k >= NL) collect_info(k - NL);                 // small results are staged per LANE: drain before the lane is reused
+    if (bound[ln] != R.ci) {
+      // the lane changes class: its buffers move inside its partition, so everything it still has in flight (the other output
+      // buffer's copy) must have landed first; the other lanes keep the device busy meanwhile
+      if (k >= NL) collect_info(k - NL);
+      g_lanes.bind_lane(ln, sh, lcap);
+      bound[ln] = R.ci;
     }
-    int nchunk = 0, next_mirror = 0;
-    auto mirror_chunk = [&](int k) {   // aii_packed = 2: chunk k's trapezoids are on the host; hand its elements to the mirror threads
-      for (size_t i = cstart[k]; i < cstart[k + 1]; i++)
-        if (C.sig[i]->h.ni > TRAP_W) g_pool.push(MirrorTask{(double *)((char *)Aii + es * (size_t)sAii * el[i]), C.sig[i]->h.ni, NS == 2});
-      next_mirror = k + 1;
-    };
-    auto collect_info = [&](int k) {   // host side of chunk k: wait for its D2H, publish info[]
-      const int slot = (k % NL) * 2 + ((k / NL) & 1);
-      cudaEventSynchronize(evCopy[slot]);
-      const size_t pc0 = cstart[k];
-      const int pn = (int)(cstart[k + 1] - pc0);
-      const Lane &PL = g_lanes.lane[k % NL];
-      const int *hi = PL.out[(k / NL) & 1].h_info;
-      if (trap) while (next_mirror <= k) mirror_chunk(next_mirror);   // the copy stream is in order: earlier chunks have landed too
-      for (int i = 0; i < pn; i++) {
-        const int e = el[pc0 + i];
-        if (info) info[e] = hi[i];
-        if (mode == MODE_BWD) memcpy((char *)xb + es * sxb * e, PL.h_xb + NS * (sT + 1) * i, es * C.sig[pc0 + i]->h.nb);
-        if (mode == MODE_RESID) resid[e] = PL.h_res[i];
+    Lane &L = g_lanes.lane[ln];
+    if (k >= NL) cudaEventSynchronize(evH2D[ln]);        // the lane's pinned input staging has been consumed
+    if (trap)   // chunks whose copies have landed meanwhile (chunks complete in order on the copy stream)
+      while (next_mirror < k && cudaEventQuery(evCopy[(next_mirror % NL) * 2 + ((next_mirror / NL) & 1)]) == cudaSuccess) mirror_chunk(next_mirror);
+    const double tw1 = now();
+    t_wait += tw1 - tw0;
+    for (int i = 0; i < n; i++) {
+      const int e = el[c0 + i];
+      const SigHost &h = C.sig[c0 + i]->h;
+      memcpy(L.h_xnod + (size_t)i * nx, xnod + (size_t)e * xnod_ld, sizeof(double) * 3 * h.nH);
+      if (gp.source == HP3D_SRC_TABLE)
+        memcpy(L.h_src + (size_t)i * nsrc, (const double *)source_qp + (size_t)e * source_ld, sizeof(double) * h.nint * (h.cplx ? 6 : 1));
+      L.h_cnt[i] = h.ni; L.h_cnt[lcap + i] = h.nb; L.h_cnt[2 * lcap + i] = h.dims.nil;
+      if (mode == MODE_CELEM) L.h_cel[i] = e;
+      if (!big) {
+        memcpy(L.h_xi + NS * sB * i, (const char *)xi + es * sxi * e, es * h.ni);
+        if (mode == MODE_RESID && h.nb > 0) memcpy(L.h_xb + NS * (sT + 1) * i, (const char *)xb + es * sxb * e, es * h.nb);
       }
-    };
-    for (; nchunk + 1 < (int)cstart.size(); nchunk++) {
-      const size_t c0 = cstart[nchunk];
-      const int n = (int)(cstart[nchunk + 1] - c0), ln = nchunk % NL, ob = (nchunk / NL) & 1, slot = ln * 2 + ob;
-      Lane &L = g_lanes.lane[ln];
-      cudaStream_t st = g_lane_stream[ln];
-      const double tw0 = now();
-      if (big) { if (nchunk >= NSLOT) collect_info(nchunk - NSLOT); }   // this slot's previous results are on the host
-      else if (nchunk >= NL) collect_info(nchunk - NL);       // small results are staged per LANE: drain before the lane is reused
-      if (nchunk >= NL) cudaEventSynchronize(evH2D[ln]);        // the lane's pinned input staging has been consumed
-      if (trap)   // chunks whose copies have landed meanwhile (chunks complete in order on the copy stream)
-        while (next_mirror < nchunk && cudaEventQuery(evCopy[(next_mirror % NL) * 2 + ((next_mirror / NL) & 1)]) == cudaSuccess) mirror_chunk(next_mirror);
-      const double tw1 = now();
-      t_wait += tw1 - tw0;
-      for (int i = 0; i < n; i++) {
-        const int e = el[c0 + i];
-        const SigHost &h = C.sig[c0 + i]->h;
-        memcpy(L.h_xnod + (size_t)i * nx, xnod + (size_t)e * xnod_ld, sizeof(double) * 3 * h.nH);
-        if (gp.source == HP3D_SRC_TABLE)
-          memcpy(L.h_src + (size_t)i * nsrc, (const double *)source_qp + (size_t)e * source_ld, sizeof(double) * h.nint * (h.cplx ? 6 : 1));
-        L.h_cnt[i] = h.ni; L.h_cnt[lcap + i] = h.nb; L.h_cnt[2 * lcap + i] = h.dims.nil;
-        if (mode == MODE_CELEM) L.h_cel[i] = e;
-        if (!big) {
-          memcpy(L.h_xi + NS * sB * i, (const char *)xi + es * sxi * e, es * h.ni);
-          if (mode == MODE_RESID && h.nb > 0) memcpy(L.h_xb + NS * (sT + 1) * i, (const char *)xb + es * sxb * e, es * h.nb);
-        }
-      }
-      t_stage += now() - tw1;
-      cudaMemcpyAsync(L.d_xnod, L.h_xnod, sizeof(double) * nx * n, cudaMemcpyHostToDevice, st);
-      if (gp.source == HP3D_SRC_TABLE) cudaMemcpyAsync(L.d_src, L.h_src, sizeof(double) * nsrc * n, cudaMemcpyHostToDevice, st);
-      cudaMemcpyAsync(L.ws.b.ni_e, L.h_cnt, sizeof(int) * n, cudaMemcpyHostToDevice, st);
-      cudaMemcpyAsync(L.ws.b.nb_e, L.h_cnt + lcap, sizeof(int) * n, cudaMemcpyHostToDevice, st);
-      cudaMemcpyAsync(L.ws.b.nip_e, L.h_cnt + 2 * lcap, sizeof(int) * n, cudaMemcpyHostToDevice, st);
-      if (!big) cudaMemcpyAsync(L.d_xi, L.h_xi, es * sB * n, cudaMemcpyHostToDevice, st);
-      if (mode == MODE_CELEM) cudaMemcpyAsync(L.d_cel, L.h_cel, sizeof(int) * n, cudaMemcpyHostToDevice, st);
-      if (mode == MODE_RESID) cudaMemcpyAsync(L.d_xb, L.h_xb, es * (sT + 1) * n, cudaMemcpyHostToDevice, st);
-      cudaEventRecord(evH2D[ln], st);
-      chunk_segments(C, c0, n, segs);
-      run_chunk(sh, L, ob, gp, segs, n, L.d_xnod, (long long)nx, L.d_src, (long long)nsrc, want_schur, st, nullptr, mode, packed);
-      if (mode == MODE_CELEM) run_celem(sh, L, L.out[ob], *cc, n, st);
-      const Lane::Out &o = L.out[ob];
-      if (cloc && sh.d.nb > 0) {   // Schur factors: device staging -> their slots (same stream; runs of neighbouring slots are merged)
-        for (int i = 0; i < n;) {
-          const ClocStore::Slot &s0 = eslot[el[c0 + i]];
-          if (!s0.AS) { i++; continue; }
-          const size_t ba = (size_t)s0.nb * s0.ni, bb = (size_t)s0.nb;
-          int j = i + 1;
-          if (ba == sS && bb == sT)
-            while (j < n && eslot[el[c0 + j]].AS == s0.AS + NS * ba * (j - i) && eslot[el[c0 + j]].BS == s0.BS + NS * bb * (j - i) &&
-                   eslot[el[c0 + j]].ni == s0.ni && eslot[el[c0 + j]].nb == s0.nb) j++;
-          cudaMemcpyAsync(s0.AS, o.AS + NS * sS * i, es * ba * (j - i), cudaMemcpyDeviceToDevice, st);
-          cudaMemcpyAsync(s0.BS, o.BS + NS * sT * i, es * bb * (j - i), cudaMemcpyDeviceToDevice, st);
-          i = j;
-        }
-      }
-      cudaEventRecord(evCompute[slot], st);
-      cudaStreamWaitEvent(g_copy, evCompute[slot], 0);
-      if (!big) {   // small results: staged through pinned memory, scattered to the caller in collect_info
-        if (mode == MODE_BWD) cudaMemcpyAsync(L.h_xb, L.d_xb, es * (sT + 1) * n, cudaMemcpyDeviceToHost, g_copy);
-        else cudaMemcpyAsync(L.h_res, L.d_res, sizeof(double) * n, cudaMemcpyDeviceToHost, g_copy);
-        cudaMemcpyAsync(o.h_info, o.info, sizeof(int) * n, cudaMemcpyDeviceToHost, g_copy);
-        cudaEventRecord(evCopy[slot], g_copy);
-        continue;
-      }
-      // D2H straight into the caller's arrays; runs of consecutive elements with equal sizes and dense strides are merged
-      if (mode == MODE_CELEM) {   // compressed systems: Zastif / IRN / JCN at the caller's offsets, Zbload at xptr
-        const size_t zmax = sh.nz_max, cmax = sh.nc_max;
-        for (int i = 0; i < n;) {
-          const int e = el[c0 + i];
-          int j = i + 1;   // merge elements that are adjacent in the caller's arrays AND fill their staging slots completely
-          while (j < n && el[c0 + j] == el[c0 + j - 1] + 1 && (size_t)cc->nz(el[c0 + j - 1]) == zmax &&
-                 (size_t)(cc->xptr[el[c0 + j - 1] + 1] - cc->xptr[el[c0 + j - 1]]) == cmax &&
-                 cc->aoff[el[c0 + j]] == cc->aoff[el[c0 + j - 1]] + (long long)zmax) j++;
-          const int el_last = el[c0 + j - 1];
-          const size_t nzr = (size_t)(j - 1 - i) * zmax + (size_t)cc->nz(el_last), ncr = (size_t)(j - 1 - i) * cmax + (size_t)(cc->xptr[el_last + 1] - cc->xptr[el_last]);
-          if (nzr) {
-            cudaMemcpyAsync((char *)cc->zastif + es * cc->aoff[e], o.Z + NS * zmax * i, es * nzr, cudaMemcpyDeviceToHost, g_copy);
-            if (cc->irn) {
-              cudaMemcpyAsync(cc->irn + cc->aoff[e], o.irn + zmax * i, sizeof(int) * nzr, cudaMemcpyDeviceToHost, g_copy);
-              cudaMemcpyAsync(cc->jcn + cc->aoff[e], o.jcn + zmax * i, sizeof(int) * nzr, cudaMemcpyDeviceToHost, g_copy);
-            }
-          }
-          if (ncr) cudaMemcpyAsync((char *)cc->zbload + es * cc->xptr[e], o.zb + NS * cmax * i, es * ncr, cudaMemcpyDeviceToHost, g_copy);
-          i = j;
-        }
-      }
+    }
+    t_stage += now() - tw1;
+    cudaMemcpyAsync(L.d_xnod, L.h_xnod, sizeof(double) * nx * n, cudaMemcpyHostToDevice, st);
+    if (gp.source == HP3D_SRC_TABLE) cudaMemcpyAsync(L.d_src, L.h_src, sizeof(double) * nsrc * n, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(L.ws.b.ni_e, L.h_cnt, sizeof(int) * n, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(L.ws.b.nb_e, L.h_cnt + lcap, sizeof(int) * n, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(L.ws.b.nip_e, L.h_cnt + 2 * lcap, sizeof(int) * n, cudaMemcpyHostToDevice, st);
+    if (!big) cudaMemcpyAsync(L.d_xi, L.h_xi, es * sB * n, cudaMemcpyHostToDevice, st);
+    if (mode == MODE_CELEM) cudaMemcpyAsync(L.d_cel, L.h_cel, sizeof(int) * n, cudaMemcpyHostToDevice, st);
+    if (mode == MODE_RESID) cudaMemcpyAsync(L.d_xb, L.h_xb, es * (sT + 1) * n, cudaMemcpyHostToDevice, st);
+    cudaEventRecord(evH2D[ln], st);
+    chunk_segments(C, c0, n, segs);
+    run_chunk(sh, L, ob, gp, segs, n, L.d_xnod, (long long)nx, L.d_src, (long long)nsrc, want_schur, st, nullptr, mode, packed);
+    if (mode == MODE_CELEM) run_celem(sh, L, L.out[ob], *cc, n, st);
+    const Lane::Out &o = L.out[ob];
+    R.h_info = o.h_info; R.h_xb = L.h_xb; R.h_res = L.h_res;
+    if (cloc && sh.d.nb > 0) {   // Schur factors: device staging -> their slots (same stream; runs of neighbouring slots are merged)
       for (int i = 0; i < n;) {
-        const SigHost &h = C.sig[c0 + i]->h;
+        const ClocStore::Slot &s0 = eslot[el[c0 + i]];
+        if (!s0.AS) { i++; continue; }
+        const size_t ba = (size_t)s0.nb * s0.ni, bb = (size_t)s0.nb;
         int j = i + 1;
-        while (j < n && el[c0 + j] == el[c0 + j - 1] + 1 && C.sig[c0 + j]->h.ni == h.ni && C.sig[c0 + j]->h.nb == h.nb) j++;
-        const int e = el[c0 + i], run = j - i;
-        auto copy = [&](void *dst, long long stride, const double *src, size_t dstride, size_t blk) {
-          if (blk == 0) return;
-          if ((size_t)stride == blk && dstride == blk)
-            cudaMemcpyAsync((char *)dst + es * stride * e, src + NS * dstride * i, es * blk * run, cudaMemcpyDeviceToHost, g_copy);
-          else
-            cudaMemcpy2DAsync((char *)dst + es * stride * e, es * stride, src + NS * dstride * i, es * dstride, es * blk, run, cudaMemcpyDeviceToHost, g_copy);
-        };
-        if (mode == MODE_ELEM) {
-          if (trap && h.ni > TRAP_W) {
-            // block column b of every element of the run in one strided copy when both element strides are whole columns
-            const size_t nn = (size_t)h.ni, pitch = es * nn;
-            const bool whole = sA % nn == 0 && (size_t)sAii % nn == 0;
-            for (int c0 = 0; c0 < h.ni; c0 += TRAP_W) {
-              const size_t w = std::min(TRAP_W, h.ni - c0), rows = nn - c0;
-              if (whole) {
-                cudaMemcpy3DParms q;
-                memset(&q, 0, sizeof q);
-                q.srcPtr = make_cudaPitchedPtr((void *)(o.Aii + NS * sA * i), pitch, pitch, sA / nn);
-                q.dstPtr = make_cudaPitchedPtr((char *)Aii + es * (size_t)sAii * e, pitch, pitch, (size_t)sAii / nn);
-                q.srcPos = make_cudaPos(es * c0, c0, 0); q.dstPos = q.srcPos;
-                q.extent = make_cudaExtent(es * rows, w, run);
-                q.kind = cudaMemcpyDeviceToHost;
-                cudaMemcpy3DAsync(&q, g_copy);
-              } else
-                for (int k = 0; k < run; k++)
-                  cudaMemcpy2DAsync((char *)Aii + es * ((size_t)sAii * (e + k) + (size_t)c0 * nn + c0), pitch,
-                                    o.Aii + NS * (sA * (i + k) + (size_t)c0 * nn + c0), pitch, es * rows, w, cudaMemcpyDeviceToHost, g_copy);
-            }
-          } else
-            copy(Aii, sAii, o.Aii, sA, packed ? (size_t)h.ni * (h.ni + 1) / 2 : (size_t)h.ni * h.ni);
-          copy(Bi, sBi, o.Bi, sB, (size_t)h.ni);
-        }
-        if (to_host_schur) { copy(ASchur, sAS, o.AS, sS, (size_t)h.nb * h.ni); copy(BSchur, sBS, o.BS, sT, (size_t)h.nb); }
+        if (ba == sS && bb == sT)
+          while (j < n && eslot[el[c0 + j]].AS == s0.AS + NS * ba * (j - i) && eslot[el[c0 + j]].BS == s0.BS + NS * bb * (j - i) &&
+                 eslot[el[c0 + j]].ni == s0.ni && eslot[el[c0 + j]].nb == s0.nb) j++;
+        cudaMemcpyAsync(s0.AS, o.AS + NS * sS * i, es * ba * (j - i), cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(s0.BS, o.BS + NS * sT * i, es * bb * (j - i), cudaMemcpyDeviceToDevice, st);
         i = j;
       }
-      cudaMemcpyAsync(o.h_info, o.info, sizeof(int) * n, cudaMemcpyDeviceToHost, g_copy);   // pinned: stays asynchronous
-      cudaEventRecord(evCopy[slot], g_copy);
     }
-    for (int k = std::max(0, nchunk - (big ? NSLOT : NL)); k < nchunk; k++) collect_info(k);
-    for (size_t i = 0; i < el.size(); i++) { const SigHost &h = C.sig[i]->h; if (ni_out) ni_out[el[i]] = h.ni; if (nb_out) nb_out[el[i]] = h.nb; }
+    cudaEventRecord(evCompute[slot], st);
+    cudaStreamWaitEvent(g_copy, evCompute[slot], 0);
+    if (!big) {   // small results: staged through pinned memory, scattered to the caller in collect_info
+      if (mode == MODE_BWD) cudaMemcpyAsync(L.h_xb, L.d_xb, es * (sT + 1) * n, cudaMemcpyDeviceToHost, g_copy);
+      else cudaMemcpyAsync(L.h_res, L.d_res, sizeof(double) * n, cudaMemcpyDeviceToHost, g_copy);
+      cudaMemcpyAsync(o.h_info, o.info, sizeof(int) * n, cudaMemcpyDeviceToHost, g_copy);
+      cudaEventRecord(evCopy[slot], g_copy);
+      continue;
+    }
+    // D2H straight into the caller's arrays; runs of consecutive elements with equal sizes and dense strides are merged
+    if (mode == MODE_CELEM) {   // compressed systems: Zastif / IRN / JCN at the caller's offsets, Zbload at xptr
+      const size_t zmax = sh.nz_max, cmax = sh.nc_max;
+      for (int i = 0; i < n;) {
+        const int e = el[c0 + i];
+        int j = i + 1;   // merge elements that are adjacent in the caller's arrays AND fill their staging slots completely
+        while (j < n && el[c0 + j] == el[c0 + j - 1] + 1 && (size_t)cc->nz(el[c0 + j - 1]) == zmax &&
+               (size_t)(cc->xptr[el[c0 + j - 1] + 1] - cc->xptr[el[c0 + j - 1]]) == cmax &&
+               cc->aoff[el[c0 + j]] == cc->aoff[el[c0 + j - 1]] + (long long)zmax) j++;
+        const int el_last = el[c0 + j - 1];
+        const size_t nzr = (size_t)(j - 1 - i) * zmax + (size_t)cc->nz(el_last), ncr = (size_t)(j - 1 - i) * cmax + (size_t)(cc->xptr[el_last + 1] - cc->xptr[el_last]);
+        if (nzr) {
+          cudaMemcpyAsync((char *)cc->zastif + es * cc->aoff[e], o.Z + NS * zmax * i, es * nzr, cudaMemcpyDeviceToHost, g_copy);
+          if (cc->irn) {
+            cudaMemcpyAsync(cc->irn + cc->aoff[e], o.irn + zmax * i, sizeof(int) * nzr, cudaMemcpyDeviceToHost, g_copy);
+            cudaMemcpyAsync(cc->jcn + cc->aoff[e], o.jcn + zmax * i, sizeof(int) * nzr, cudaMemcpyDeviceToHost, g_copy);
+          }
+        }
+        if (ncr) cudaMemcpyAsync((char *)cc->zbload + es * cc->xptr[e], o.zb + NS * cmax * i, es * ncr, cudaMemcpyDeviceToHost, g_copy);
+        i = j;
+      }
+    }
+    for (int i = 0; i < n;) {
+      const SigHost &h = C.sig[c0 + i]->h;
+      int j = i + 1;
+      while (j < n && el[c0 + j] == el[c0 + j - 1] + 1 && C.sig[c0 + j]->h.ni == h.ni && C.sig[c0 + j]->h.nb == h.nb) j++;
+      const int e = el[c0 + i], run = j - i;
+      auto copy = [&](void *dst, long long stride, const double *src, size_t dstride, size_t blk) {
+        if (blk == 0) return;
+        if ((size_t)stride == blk && dstride == blk)
+          cudaMemcpyAsync((char *)dst + es * stride * e, src + NS * dstride * i, es * blk * run, cudaMemcpyDeviceToHost, g_copy);
+        else
+          cudaMemcpy2DAsync((char *)dst + es * stride * e, es * stride, src + NS * dstride * i, es * dstride, es * blk, run, cudaMemcpyDeviceToHost, g_copy);
+      };
+      if (mode == MODE_ELEM) {
+        if (trap && h.ni > TRAP_W) {
+          // block column b of every element of the run in one strided copy when both element strides are whole columns
+          const size_t nn = (size_t)h.ni, pitch = es * nn;
+          const bool whole = sA % nn == 0 && (size_t)sAii % nn == 0;
+          for (int cb = 0; cb < h.ni; cb += TRAP_W) {
+            const size_t w = std::min(TRAP_W, h.ni - cb), rows = nn - cb;
+            if (whole) {
+              cudaMemcpy3DParms q;
+              memset(&q, 0, sizeof q);
+              q.srcPtr = make_cudaPitchedPtr((void *)(o.Aii + NS * sA * i), pitch, pitch, sA / nn);
+              q.dstPtr = make_cudaPitchedPtr((char *)Aii + es * (size_t)sAii * e, pitch, pitch, (size_t)sAii / nn);
+              q.srcPos = make_cudaPos(es * cb, cb, 0); q.dstPos = q.srcPos;
+              q.extent = make_cudaExtent(es * rows, w, run);
+              q.kind = cudaMemcpyDeviceToHost;
+              cudaMemcpy3DAsync(&q, g_copy);
+            } else
+              for (int kk = 0; kk < run; kk++)
+                cudaMemcpy2DAsync((char *)Aii + es * ((size_t)sAii * (e + kk) + (size_t)cb * nn + cb), pitch,
+                                  o.Aii + NS * (sA * (i + kk) + (size_t)cb * nn + cb), pitch, es * rows, w, cudaMemcpyDeviceToHost, g_copy);
+          }
+        } else
+          copy(Aii, sAii, o.Aii, sA, packed ? (size_t)h.ni * (h.ni + 1) / 2 : (size_t)h.ni * h.ni);
+        copy(Bi, sBi, o.Bi, sB, (size_t)h.ni);
+      }
+      if (to_host_schur) { copy(ASchur, sAS, o.AS, sS, (size_t)h.nb * h.ni); copy(BSchur, sBS, o.BS, sT, (size_t)h.nb); }
+      i = j;
+    }
+    cudaMemcpyAsync(o.h_info, o.info, sizeof(int) * n, cudaMemcpyDeviceToHost, g_copy);   // pinned: stays asynchronous
+    cudaEventRecord(evCopy[slot], g_copy);
+  }
+  for (int k = 0; k < nrec; k++) collect_info(k);
+  for (ClassGroup &C : classes)
+    for (size_t i = 0; i < C.el.size(); i++) { const SigHost &h = C.sig[i]->h; if (ni_out) ni_out[C.el[i]] = h.ni; if (nb_out) nb_out[C.el[i]] = h.nb; }
+  {
     cudaError_t ce = cudaGetLastError();
-    if (ce != cudaSuccess) { rc = fail(HP3D_ENODEV, "CUDA error in elem_batch: %s", cudaGetErrorString(ce)); break; }
+    if (ce != cudaSuccess) rc = fail(HP3D_ENODEV, "CUDA error in elem_batch: %s", cudaGetErrorString(ce));
   }
   const double t_submitted = now();
   if (trap) g_pool.wait();
