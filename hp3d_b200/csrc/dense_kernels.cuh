@@ -260,10 +260,9 @@ __global__ void __launch_bounds__(256) potrf_inv_tile_real_kernel(MatRef D, MatR
   __shared__ double Ls[N * LD];
   __shared__ double vec[2][N];
   __shared__ double rs[N];      // 1 / sqrt(pivot)
-  __shared__ int bad;
+  int bad = 0;   // first non-positive pivot (1-based); every thread sees the same pivots, so a register per thread will do
   const int e = blockIdx.x, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   double *Dg = D.re + (long long)e * D.batch;
-  if (tid == 0) bad = 0;
   double a[4][4];
 #pragma unroll
   for (int i = 0; i < 4; i++)
@@ -284,7 +283,7 @@ __global__ void __launch_bounds__(256) potrf_inv_tile_real_kernel(MatRef D, MatR
       }
       __syncthreads();
       double d = vec[buf][k];
-      if (!(d > 0.0)) { if (tid == 0 && bad == 0) bad = k + 1; d = 1.0; }
+      if (!(d > 0.0)) { if (bad == 0) bad = k + 1; d = 1.0; }
       const double dinv = 1.0 / d;
       if (tid == 0) rs[k] = 1.0 / sqrt(d);
       double cr[4], cc[4];
@@ -377,10 +376,9 @@ __global__ void __launch_bounds__(256) potrf_inv_tile_kernel(MatRef D, MatRef Li
   constexpr int N = TILE, LD = TILE + 1;
   extern __shared__ __align__(16) double smem[];  // 4 planes of N*LD doubles (133 KB: opt-in dynamic smem)
   double *sr = smem, *si = smem + N * LD, *xr = smem + 2 * N * LD, *xi = smem + 3 * N * LD;
-  __shared__ int bad;
+  int bad = 0;   // first non-positive pivot (1-based); every thread sees the same pivots, so a register per thread will do
   const int e = blockIdx.x, tid = threadIdx.x;
   double *Dg = D.re + (long long)e * D.batch;
-  if (tid == 0) bad = 0;
   for (int idx = tid; idx < N * N; idx += blockDim.x) {
     int r = idx / N, c = idx % N;
     sr[r * LD + c] = Dg[(long long)r * D.ld + c];
@@ -390,7 +388,7 @@ __global__ void __launch_bounds__(256) potrf_inv_tile_kernel(MatRef D, MatRef Li
   // right-looking Cholesky on the lower triangle
   for (int k = 0; k < N; k++) {
     double d = sr[k * LD + k];
-    if (!(d > 0.0)) { if (tid == 0 && bad == 0) bad = k + 1; d = 1.0; }
+    if (!(d > 0.0)) { if (bad == 0) bad = k + 1; d = 1.0; }
     double rs = 1.0 / sqrt(d);
     __syncthreads();
     if (tid >= k && tid < N) { // scale column k (entry (tid,k)); the diagonal becomes sqrt(d)
