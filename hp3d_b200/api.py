@@ -336,7 +336,7 @@ class ElemEngine:
         return dict(resid=res, info=info)
 
     def celem_batch(self, norder, norient_edge, norient_face, xnod, cons, isym_flag=2, want_coo=False, want_schur=False,
-                    source_qp=None, etype=None, out=None, packed=None):
+                    source_qp=None, etype=None, out=None, packed=None, cloc=None, iel=None):
         """elem + stc_fwd_wrapper + the rest of celem_systemI (constraints, Dirichlet lift, compression; :543-785) for nel
         elements (hp3d_gpu_celem_batch).  cons: one dict per element with the flat lists of `celem_pack` (cptr, cidx, cval) and
         idbc, zdofd (Nrdofm,), nextract (Nrdofc,) [1-based], optionally lcon (Nrdofc,) global dof numbers.
@@ -371,8 +371,16 @@ class ElemEngine:
         if source_qp is not None:
             source_qp = np.ascontiguousarray(source_qp)
             src_ld = source_qp[0].size * (2 if np.iscomplexobj(source_qp) else 1)
-        f = self.L.hp3d_gpu_celem_batch
         ll = C.c_longlong
+        if cloc is not None:   # Schur factors into the device-resident store (hp3d_gpu_celem_batch_cloc): nothing but the compressed systems returns
+            iel = None if iel is None else np.ascontiguousarray(iel, dtype=np.int64)
+            g = self.L.hp3d_gpu_celem_batch_cloc
+            g.argtypes = ([C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p, ll] + [C.c_void_p] * 9 + [C.c_int] + [C.c_void_p] * 5 + [C.c_void_p] * 3)
+            _lib.check(g(self.plan, int(cloc), nel, _ptr(iel), _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(np.prod(xnod.shape[1:])), _ptr(source_qp), src_ld,
+                         _ptr(mptr), _ptr(cptr), _ptr(cidx), _ptr(cval), _ptr(idbc), _ptr(zdofd), _ptr(xptr), _ptr(nextract), _ptr(lcon), int(isym_flag),
+                         _ptr(aptr), _ptr(zb), _ptr(za), _ptr(irn), _ptr(jcn), _ptr(nio), _ptr(nbo), _ptr(info)))
+            return dict(zbload=zb, zastif=za, xptr=xptr, aptr=aptr, irn=irn, jcn=jcn, ASchur=None, BSchur=None, ni=nio, nb=nbo, info=info)
+        f = self.L.hp3d_gpu_celem_batch
         f.argtypes = ([C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, ll] + [C.c_void_p] * 9 + [C.c_int] + [C.c_void_p] * 5 +
                       [C.c_void_p, ll, C.c_void_p, ll] + [C.c_void_p] * 3)
         _lib.check(f(self.plan, nel, _ptr(et), _ptr(norder), _ptr(noe), _ptr(nof), _ptr(xnod), int(np.prod(xnod.shape[1:])), _ptr(source_qp), src_ld,

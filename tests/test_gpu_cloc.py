@@ -185,3 +185,37 @@ def test_aii_lower_trapezoids_mirrored_on_host(oracle, gpu, kind, rr, uniform):
         assert np.array_equal(res["Aii"][e, :n * n], ref["Aii"][e, :n * n])
         assert np.array_equal(res["Bi"][e, :n], ref["Bi"][e, :n]) and np.array_equal(res["ASchur"][e, :n * nb], ref["ASchur"][e, :n * nb])
     eng.close()
+
+
+@pytest.mark.parametrize("kind", [2, 4])
+def test_celem_batch_with_device_resident_factors(oracle, gpu, kind):
+    """hp3d_gpu_celem_batch_cloc: the compressed systems are bit for bit those of hp3d_gpu_celem_batch, and the factors the fused
+    call files in the store give the same back-substitution as the factors the plain call returns to the host"""
+    from hp3d_b200 import api
+    from tests import celem_util as CU
+    from tests.test_gpu_celem import _batch as celem_batch
+    from tests.util import uniform_order
+    O = oracle
+    O.set_maxp(6)
+    rng = np.random.default_rng(190 + kind)
+    nel, p = 5, 2
+    et, no, noe, nof, X = celem_batch(O, rng, kind, [(O.MDLB, uniform_order(p))] * nel)
+    eng = api.ElemEngine(kind, omega=2 * np.pi if kind == 4 else 1.0)
+    cons = [CU.random_constraints(rng, O, api, kind, no[e], O.MDLB, kind >= 3, frac_con=0.3, frac_dbc=0.2, dof0=1 + 1000 * e) for e in range(nel)]
+    ref = eng.celem_batch(no, noe, nof, X, cons, isym_flag=2, want_coo=True, want_schur=True)
+    cl = eng.cloc_create()
+    iel = np.arange(nel, dtype=np.int64) * 3 + 11
+    res = eng.celem_batch(no, noe, nof, X, cons, isym_flag=2, want_coo=True, cloc=cl, iel=iel)
+    assert (res["info"] == 0).all()
+    for key in ("zbload", "zastif", "irn", "jcn"):
+        assert np.array_equal(res[key], ref[key]), key
+    ni, nb = int(ref["ni"][0]), int(ref["nb"][0])
+    xi = rng.normal(size=(nel, ni)) + (1j * rng.normal(size=(nel, ni)) if kind >= 3 else 0)
+    out = eng.cloc_bwd_batch(cl, xi, iel=iel)
+    for e in range(nel):
+        AS = ref["ASchur"][e][:nb * ni].reshape(ni, nb).T; BS = ref["BSchur"][e][:nb]
+        assert relerr(out["xb"][e, :nb], BS - AS @ xi[e]) < 1e-13
+    with pytest.raises(RuntimeError, match="no such Schur store"):
+        eng.cloc_stats(cl + 17)
+    eng.cloc_destroy(cl)
+    eng.close()
