@@ -1835,6 +1835,63 @@ PbiSig *pbi_signature(int et, const int *norder, const int *norie, const int *no
   }
   return S;
 }
+
+// Compile the signatures a call meets for the first time CONCURRENTLY on the host's cores (as Plan::compile_missing does for the
+// element engine): on an hp mesh nearly every element has its own interpolation signature and one compilation with tables costs
+// milliseconds.  Afterwards pbi_signature() finds the descriptors in the cache; with `tables` the device tables are uploaded here too.
+int pbi_precompile(int nel, const int *etype, const int *norder, const int *norie, const int *norif, int integration, int maxp, bool tables,
+                   int space, std::string &err) {
+  struct Job { std::string key; int e; bool need_desc; std::unique_ptr<PbiSig> S; PbiSigHost full; bool ok_desc = true, ok_full = true; };
+  std::vector<Job> jobs;
+  {
+    std::map<std::string, int> seen;
+    for (int e = 0; e < nel; e++) {
+      const int et = etype ? etype[e] : HP3D_MDLB;
+      std::string key = std::to_string(space) + "/" + std::to_string(integration) + "/" + std::to_string(maxp) + "/" + Plan::key(et, norder + 19 * e, norie + 12 * e, norif + 6 * e);
+      if (!seen.emplace(key, e).second) continue;
+      auto it = g_pbisigs.find(key);
+      const bool need_desc = it == g_pbisigs.end(), need_tab = tables && (need_desc || !it->second->on_device);
+      if (!need_desc && !need_tab) continue;
+      Job j; j.key = std::move(key); j.e = e; j.need_desc = need_desc;
+      jobs.push_back(std::move(j));
+    }
+  }
+  if (jobs.size() < 2) return 0;   // nothing to gain: the serial path handles it
+  std::atomic<size_t> next{0};
+  auto work = [&]() {
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= jobs.size()) break;
+      Job &j = jobs[i];
+      const int e = j.e, et = etype ? etype[e] : HP3D_MDLB;
+      if (j.need_desc) {
+        j.S.reset(new PbiSig());
+        j.ok_desc = compile_pbi_signature(et, norder + 19 * e, norie + 12 * e, norif + 6 * e, integration, maxp, false, j.S->h, space);
+      }
+      if (tables && j.ok_desc) j.ok_full = compile_pbi_signature(et, norder + 19 * e, norie + 12 * e, norif + 6 * e, integration, maxp, true, j.full, space);
+    }
+  };
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = std::max(1u, std::min(nt ? nt : 4u, std::min((unsigned)jobs.size(), 32u)));
+  std::vector<std::thread> th;
+  for (unsigned t = 1; t < nt; t++) th.emplace_back(work);
+  work();
+  for (std::thread &t : th) t.join();
+  for (Job &j : jobs) {
+    if (!j.ok_desc) { err = "element " + std::to_string(j.e) + ": " + j.S->h.err; return -1; }
+    if (!j.ok_full) { err = "element " + std::to_string(j.e) + ": " + j.full.err; return -1; }
+    PbiSig *S = j.need_desc ? g_pbisigs.emplace(j.key, std::move(j.S)).first->second.get() : g_pbisigs.find(j.key)->second.get();
+    if (tables && !S->on_device) {
+      std::vector<PbiNode> nodes(j.full.node, j.full.node + j.full.nnode);
+      if (dev_upload(j.full.wa, &S->d_wa, err) || dev_upload(j.full.tan, &S->d_tan, err) || dev_upload(j.full.grad, &S->d_grad, err) ||
+          dev_upload(j.full.tabE, &S->d_tabE, err) || dev_upload(nodes, &S->d_nodes, err))
+        return -1;
+      S->on_device = true;
+      g_pbi_table_bytes += sizeof(double) * (j.full.wa.size() + j.full.tan.size() + j.full.grad.size() + j.full.tabE.size()) + sizeof(PbiNode) * nodes.size();
+    }
+  }
+  return 0;
+}
 }  // namespace
 
 extern "C" {
@@ -1843,6 +1900,7 @@ int hp3d_gpu_pbi_points(int nel, const int *etype, const int *norder, const int 
                         double *xi, long long xi_ld, int *npts, int *nrdofH, int *nodes) {
   std::lock_guard<std::recursive_mutex> lk(g_mu);
   if (nel < 0 || (nel > 0 && (!norder || !norie || !norif))) return fail(HP3D_EINVAL, "pbi_points: null argument");
+  { std::string perr; if (pbi_precompile(nel, etype, norder, norie, norif, integration, maxp, false, PBI_H1, perr)) return fail(HP3D_EINVAL, "%s", perr.c_str()); }
   for (int e = 0; e < nel; e++) {
     std::string err;
     const PbiSig *S = pbi_signature(etype ? etype[e] : HP3D_MDLB, norder + 19 * e, norie + 12 * e, norif + 6 * e, integration, maxp, false, err);
@@ -1873,6 +1931,7 @@ int hp3d_gpu_pbi_h1_batch(int nel, const int *etype, const int *norder, const in
   if (nel == 0) return HP3D_OK;
   if (int rc = pbi_opt_in_smem()) return rc;
   pbi_trim_table_cache();
+  { std::string perr; if (pbi_precompile(nel, etype, norder, norie, norif, integration, maxp, true, PBI_H1, perr)) return fail(HP3D_EINVAL, "%s", perr.c_str()); }
   // ---- signature groups (elements are addressed in place through an index list: no host-side gather)
   struct Group { PbiSig *S; std::vector<int> el; };
   std::map<const PbiSig *, size_t> where;
@@ -1968,6 +2027,7 @@ static int pbi_vec_points(int space, int nel, const int *etype, const int *norde
                           long long xi_ld, int *npts, int *nrdofE, int *nodes) {
   std::lock_guard<std::recursive_mutex> lk(g_mu);
   if (nel < 0 || (nel > 0 && (!norder || !norie || !norif))) return fail(HP3D_EINVAL, "pbi_hcurl_points: null argument");
+  { std::string perr; if (pbi_precompile(nel, etype, norder, norie, norif, 1, maxp, false, space, perr)) return fail(HP3D_EINVAL, "%s", perr.c_str()); }
   for (int e = 0; e < nel; e++) {
     std::string err;
     const PbiSig *S = pbi_signature(etype ? etype[e] : HP3D_MDLB, norder + 19 * e, norie + 12 * e, norif + 6 * e, 1, maxp, false, err, space);
@@ -1998,6 +2058,7 @@ static int pbi_vec_batch(int space, int nel, const int *etype, const int *norder
   if (nel == 0) return HP3D_OK;
   if (int rc = pbi_opt_in_smem()) return rc;
   pbi_trim_table_cache();
+  { std::string perr; if (pbi_precompile(nel, etype, norder, norie, norif, 1, maxp, true, space, perr)) return fail(HP3D_EINVAL, "%s", perr.c_str()); }
   struct Group { PbiSig *S; std::vector<int> el; };
   std::map<const PbiSig *, size_t> where;
   std::vector<Group> groups;
