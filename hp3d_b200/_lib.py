@@ -16,7 +16,7 @@ class Params(C.Structure):
     _fields_ = [("nord_add", C.c_int), ("maxp", C.c_int), ("test_norm", C.c_int), ("alpha_norm", C.c_double),
                 ("omega", C.c_double), ("eps", C.c_double), ("mu", C.c_double), ("sigma", C.c_double),
                 ("eps_tensor", C.c_double * 18), ("source", C.c_int), ("icomp_exact", C.c_int),
-                ("store_schur", C.c_int), ("real_reduction", C.c_int), ("aii_packed", C.c_int)]
+                ("store_schur", C.c_int), ("real_reduction", C.c_int), ("aii_packed", C.c_int), ("nr_rhs", C.c_int)]
 
 
 # every symbol include/hp3d_gpu.h declares (tests check that the library exports all of them)

@@ -191,8 +191,9 @@ class ElemEngine:
         ni = max((s[0] for s in sz.values()), default=0)
         nb = max((s[1] for s in sz.values()), default=0)
         if out is None:
-            out = dict(Aii=np.zeros((nel, self.aii_len(ni)), self.dtype), Bi=np.zeros((nel, ni), self.dtype),
-                       ASchur=np.zeros((nel, max(nb * ni, 1)), self.dtype), BSchur=np.zeros((nel, max(nb, 1)), self.dtype))
+            nr = max(1, int(self.prm.nr_rhs))   # Bi (ni, NR_RHS), BSchur (nb, NR_RHS) per element, column-major
+            out = dict(Aii=np.zeros((nel, self.aii_len(ni)), self.dtype), Bi=np.zeros((nel, ni * nr), self.dtype),
+                       ASchur=np.zeros((nel, max(nb * ni, 1)), self.dtype), BSchur=np.zeros((nel, max(nb * nr, 1)), self.dtype))
         Aii, Bi, AS, BS = out["Aii"], out["Bi"], out["ASchur"], out["BSchur"]
         nio = np.zeros(nel, np.int32); nbo = np.zeros(nel, np.int32); info = np.zeros(nel, np.int32)
         src_ld = 0
@@ -236,7 +237,7 @@ class ElemEngine:
         norder, noe, nof, xnod, nel, et = self._descr(norder, norient_edge, norient_face, xnod, etype)
         ni = max((self.sizes(norder[e], MDLB if et is None else int(et[e]))[0] for e in range(nel)), default=0) if out is None else 0
         if out is None:
-            out = dict(Aii=np.zeros((nel, self.aii_len(ni)), self.dtype), Bi=np.zeros((nel, ni), self.dtype))
+            out = dict(Aii=np.zeros((nel, self.aii_len(ni)), self.dtype), Bi=np.zeros((nel, ni * max(1, int(self.prm.nr_rhs))), self.dtype))
         Aii, Bi = out["Aii"], out["Bi"]
         iel = None if iel is None else np.ascontiguousarray(iel, dtype=np.int64)
         nio = np.zeros(nel, np.int32); nbo = np.zeros(nel, np.int32); info = np.zeros(nel, np.int32)
@@ -261,7 +262,7 @@ class ElemEngine:
             nb_max = 0
             for e in range(nel):
                 nb_max = max(nb_max, self.cloc_fetch(cloc, e if iel is None else int(iel[e]), sizes_only=True)[1])
-        xb = np.zeros((nel, max(nb_max, 1)), self.dtype)
+        xb = np.zeros((nel, max(nb_max * max(1, int(self.prm.nr_rhs)), 1)), self.dtype)
         nbo = np.zeros(nel, np.int32); info = np.zeros(nel, np.int32)
         f = self.L.hp3d_gpu_cloc_bwd_batch
         ll = C.c_longlong
@@ -282,9 +283,10 @@ class ElemEngine:
             return (ni.value, nb.value)
         if rc == 1:
             return None
-        AS = np.zeros(max(ni.value * nb.value, 1), self.dtype); BS = np.zeros(max(nb.value, 1), self.dtype)
+        nr = max(1, int(self.prm.nr_rhs))
+        AS = np.zeros(max(ni.value * nb.value, 1), self.dtype); BS = np.zeros(max(nb.value * nr, 1), self.dtype)
         _lib.check(f(int(cloc), int(iel), _ptr(AS), _ptr(BS), None, None))
-        return AS[:ni.value * nb.value].reshape(ni.value, nb.value).T, BS[:nb.value]
+        return AS[:ni.value * nb.value].reshape(ni.value, nb.value).T, BS[:nb.value * nr]
 
     def hermitian_unpack(self, AP, ni, out=None, threads=0):
         """Full (nel, ni*ni) column-major Hermitian blocks from packed lower triangles (hp3d_gpu_hermitian_unpack_batch; host only).
@@ -314,7 +316,7 @@ class ElemEngine:
         norder, noe, nof, xnod, nel, et = self._descr(norder, norient_edge, norient_face, xnod, etype)
         xi = np.ascontiguousarray(xi, dtype=self.dtype)
         nb = max(self.sizes(norder[e], MDLB if et is None else int(et[e]))[1] for e in range(nel))
-        xb = np.zeros((nel, max(nb, 1)), self.dtype)
+        xb = np.zeros((nel, max(nb * max(1, int(self.prm.nr_rhs)), 1)), self.dtype)
         nbo = np.zeros(nel, np.int32); info = np.zeros(nel, np.int32)
         f = self.L.hp3d_gpu_elem_bwd_batch
         ll = C.c_longlong

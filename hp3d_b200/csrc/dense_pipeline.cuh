@@ -33,6 +33,7 @@ struct DenseDims {
   // below only use np/nbp/nip plus the per-element counts in DenseBuffers::ni_e / nb_e; n, nb, ni here are the class maxima.
   __host__ __device__ int M() const { return nbp + nip; }
   __host__ __device__ int R() const { return np + nbp + nip; }
+  __host__ __device__ int nrhs() const { return nload / (rs ? 2 : 1); }   // load vectors (NR_RHS); one (complex / real) or two (real form) rows each
   __host__ __device__ int Mv() const { return nbp + nil; }        // rows / columns of A that carry data
   __host__ __device__ int Rv() const { return np + nbp + nil; }   // rows of W that carry data
   void finish() { np = dpg ? pad64(n) : 0; nbp = pad64(nb); nil = dpg ? pad32(ni + nload) : pad64(ni + nload); nip = pad64(nil); }

@@ -191,7 +191,7 @@ struct ChunkShape {
     d.n = std::max(d.n, h.dims.n); d.nb = std::max(d.nb, h.nb); d.ni = std::max(d.ni, h.ni);
     d.nip = std::max(d.nip, h.dims.nip); d.nil = std::max(d.nil, h.dims.nil);   // classes merged across nip (Cholesky path): every element keeps its own row layout (nip_e)
     nint_max = std::max(nint_max, h.nint); nH_max = std::max(nH_max, h.nH);
-    src_max = std::max(src_max, (size_t)h.nint * (h.cplx ? 6 : 1));
+    src_max = std::max(src_max, (size_t)h.nint * (h.cplx ? 6 : 1) * (size_t)std::max(1, h.dims.nrhs()));   // NR_RHS tables per element
   }
   // classes may merge across nip when the condensation is the Cholesky pipeline (the load rows are located per element);
   // the pivoted-LU kernel addresses the load column through the class extent, so its classes keep nip in the key
@@ -252,6 +252,7 @@ struct LaneSet {
   static void layout_lane(Lane &L, const ChunkShape &sh, int batch, Bump &dm, Bump &hm) {
     const size_t NS = sh.ns();
     const DenseDims &d = sh.d;
+    const size_t nr = (size_t)std::max(1, d.nrhs());   // NR_RHS columns of Bi / BSchur / xi / xb
     {
       L.ws.bind(d, batch, dm);
       L.ws.b.ni_e = dm.take<int>(batch); L.ws.b.nb_e = dm.take<int>(batch); L.ws.b.nip_e = dm.take<int>(batch);
@@ -260,9 +261,9 @@ struct LaneSet {
       L.d_src = dm.take<double>(sh.src_max * batch);
       for (int o = 0; o < 2; o++) {
         L.out[o].Aii = dm.take<double>(NS * (size_t)d.ni * d.ni * batch);
-        L.out[o].Bi = dm.take<double>(NS * (size_t)d.ni * batch);
+        L.out[o].Bi = dm.take<double>(NS * (size_t)d.ni * nr * batch);
         L.out[o].AS = dm.take<double>(NS * ((size_t)d.nb * d.ni + 1) * batch);
-        L.out[o].BS = dm.take<double>(NS * ((size_t)d.nb + 1) * batch);
+        L.out[o].BS = dm.take<double>(NS * ((size_t)d.nb * nr + 1) * batch);
         L.out[o].info = dm.take<int>(batch);
         L.out[o].h_info = hm.take<int>(batch);
         L.out[o].Z = dm.take<double>(NS * sh.nz_max * batch);
@@ -274,9 +275,9 @@ struct LaneSet {
       L.h_src = hm.take<double>(sh.src_max * batch);
       L.h_cnt = hm.take<int>(3 * (size_t)batch);
       L.d_cel = dm.take<int>(batch); L.h_cel = hm.take<int>(batch);
-      L.d_xi = dm.take<double>(NS * (size_t)d.ni * batch); L.d_xb = dm.take<double>(NS * ((size_t)d.nb + 1) * batch);
+      L.d_xi = dm.take<double>(NS * (size_t)d.ni * nr * batch); L.d_xb = dm.take<double>(NS * ((size_t)d.nb * nr + 1) * batch);
       L.d_res = dm.take<double>(batch);
-      L.h_xi = hm.take<double>(NS * (size_t)d.ni * batch); L.h_xb = hm.take<double>(NS * ((size_t)d.nb + 1) * batch);
+      L.h_xi = hm.take<double>(NS * (size_t)d.ni * nr * batch); L.h_xb = hm.take<double>(NS * ((size_t)d.nb * nr + 1) * batch);
       L.h_res = hm.take<double>(batch);
     }
   }
@@ -384,7 +385,18 @@ static void run_integration(const ChunkShape &sh, Lane &L, const GeomParams &gp,
     A.mat[0] = MatTarget{d.dpg ? L.ws.b.W + wb * sg_.start : nullptr, wb, (long long)d.w_plane(), d.np};
     A.mat[1] = MatTarget{L.ws.b.Am + ab * sg_.start, ab, (long long)d.a_plane(), d.M()};
     if (d.dpg && d.np > h.dims.n) { dim3 g((d.np - h.dims.n + 63) / 64, sg_.n); unit_diag_kernel<<<g, 64, 0, st>>>(A.mat[0], h.dims.n, d.np); g_launches++; }
+    A.load_only = 0; A.load_shift = 0;
     launch_tp3(S, A, sg_.n, st);
+    // NR_RHS > 1: the q-th load vector comes from the q-th source table of every element: the weight fields are rebuilt with
+    // that source and only the load blocks are integrated again, their rows moved down to the q-th load's rows
+    for (int q = 1; q < d.nrhs(); q++) {
+      const double *srcq = src ? src + (size_t)q * h.nint * (h.cplx ? 6 : 1) : nullptr;
+      if (h.etype == 3) geom_fields_prism_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(sg, gp, sg_.n, xn, xnod_ld, srcq, src_ld, WF, info);
+      else geom_fields_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, st>>>(sg, gp, sg_.n, xn, xnod_ld, srcq, src_ld, WF, info);
+      g_launches++;
+      A.load_only = 1; A.load_shift = q * (d.rs ? 2 : 1);
+      launch_tp3(S, A, sg_.n, st);
+    }
     if (!h.crow.empty()) {
       dim3 g((d.np + 255) / 256, (unsigned)h.crow.size(), sg_.n);
       const_rows_kernel<<<g, 256, 0, st>>>(S.d_CW, S.d_crow, d.np, A.mat[0]);
@@ -447,20 +459,21 @@ static void run_dense_and_scatter(const ChunkShape &sh, Lane &L, const Lane::Out
   if (ev && ev->on) cudaEventRecord(ev->e[2], st);
   OutMaps mp{g_lanes.d_iota, g_lanes.d_iota, g_lanes.d_ones, g_lanes.d_ones, 0, 0, 0, 0, L.ws.b.ni_e, L.ws.b.nb_e, L.ws.b.nip_e};
   dim3 blk(16, 16), g1((d.ni + 15) / 16, (d.ni + 15) / 16, nel);
-  if (RS) scatter_condensed_rs_kernel<<<g1, blk, 0, st>>>(d, L.ws.b.Am, mp, o.Aii, o.Bi, (long long)d.ni * d.ni, (long long)d.ni, packed ? 1 : 0);
-  else scatter_condensed_kernel<CPLX><<<g1, blk, 0, st>>>(d, L.ws.b.Am, mp, o.Aii, o.Bi, (long long)d.ni * d.ni, (long long)d.ni, packed ? 1 : 0);
+  const long long nr = std::max(1, d.nrhs());
+  if (RS) scatter_condensed_rs_kernel<<<g1, blk, 0, st>>>(d, L.ws.b.Am, mp, o.Aii, o.Bi, (long long)d.ni * d.ni, (long long)d.ni * nr, packed ? 1 : 0);
+  else scatter_condensed_kernel<CPLX><<<g1, blk, 0, st>>>(d, L.ws.b.Am, mp, o.Aii, o.Bi, (long long)d.ni * d.ni, (long long)d.ni * nr, packed ? 1 : 0);
   g_launches++;
   if (d.nb > 0 && want_schur) {
     dim3 g2((d.nb + 15) / 16, (d.ni + 15) / 16, nel);
-    if (RS) scatter_schur_rs_kernel<<<g2, blk, 0, st>>>(d, L.ws.b.Am, mp, o.AS, o.BS, (long long)d.nb * d.ni, (long long)d.nb);
-    else scatter_schur_kernel<CPLX><<<g2, blk, 0, st>>>(d, L.ws.b.Am, mp, o.AS, o.BS, (long long)d.nb * d.ni, (long long)d.nb);
+    if (RS) scatter_schur_rs_kernel<<<g2, blk, 0, st>>>(d, L.ws.b.Am, mp, o.AS, o.BS, (long long)d.nb * d.ni, (long long)d.nb * nr);
+    else scatter_schur_kernel<CPLX><<<g2, blk, 0, st>>>(d, L.ws.b.Am, mp, o.AS, o.BS, (long long)d.nb * d.ni, (long long)d.nb * nr);
     g_launches++;
   }
   cudaMemcpyAsync(o.info, L.ws.b.info, sizeof(int) * nel, cudaMemcpyDeviceToDevice, st);
   if (mode == MODE_BWD && d.nb > 0) {
     dim3 gb((d.nb + 7) / 8, nel);
-    stc_bwd_kernel<OUTC><<<gb, 256, 0, st>>>(L.ws.b.ni_e, L.ws.b.nb_e, 0, 0, o.AS, (long long)d.nb * d.ni, o.BS, (long long)d.nb, L.d_xi, (long long)d.ni,
-                                             L.d_xb, (long long)d.nb + 1);
+    stc_bwd_kernel<OUTC><<<gb, 256, 0, st>>>(L.ws.b.ni_e, L.ws.b.nb_e, 0, 0, o.AS, (long long)d.nb * d.ni, o.BS, (long long)d.nb * nr, L.d_xi, (long long)d.ni * nr,
+                                             L.d_xb, (long long)d.nb * nr + 1, (int)nr);
     g_launches++;
   }
 }

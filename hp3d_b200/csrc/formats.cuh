@@ -31,7 +31,7 @@ __global__ void scatter_condensed_kernel(DenseDims d, const double *Am, OutMaps 
   const int *pi = mp.perm_i + (long long)e * mp.perm_stride_i;
   const double *si = mp.sgn_i + (long long)e * mp.sgn_stride_i;
   constexpr int NS = CPLX ? 2 : 1;
-  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, lrow = (mp.nip_e ? mp.nip_e[e] : d.nil) - 1;
+  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, lrow0 = (mp.nip_e ? mp.nip_e[e] : d.nil) - d.nload;   // first load row
   if (r < ni && c < ni && (!packed || r >= c)) {
     int ir = pi[r], ic = pi[c];
     double s = si[r] * si[c];
@@ -45,9 +45,12 @@ __global__ void scatter_condensed_kernel(DenseDims d, const double *Am, OutMaps 
   }
   if (blockIdx.y == 0 && threadIdx.y == 0 && r < ni) {
     int ir = pi[r];
-    double *o = Bi + (long long)e * sB * NS + (long long)r * NS;
-    o[0] = si[r] * S[(long long)lrow * M + ir];
-    if (CPLX) o[1] = -si[r] * S[apl + (long long)lrow * M + ir];   // b_i = conj(load row)
+    for (int q = 0; q < d.nload; q++) {   // Bi(ni, NR_RHS), column q at offset q*ni
+      const int lrow = lrow0 + q;
+      double *o = Bi + (long long)e * sB * NS + ((long long)q * ni + r) * NS;
+      o[0] = si[r] * S[(long long)lrow * M + ir];
+      if (CPLX) o[1] = -si[r] * S[apl + (long long)lrow * M + ir];   // b_i = conj(load row)
+    }
   }
 }
 
@@ -62,7 +65,7 @@ __global__ void scatter_schur_kernel(DenseDims d, const double *Am, OutMaps mp, 
   const int *pi = mp.perm_i + (long long)e * mp.perm_stride_i, *pb = mp.perm_b + (long long)e * mp.perm_stride_b;
   const double *si = mp.sgn_i + (long long)e * mp.sgn_stride_i, *sb = mp.sgn_b + (long long)e * mp.sgn_stride_b;
   constexpr int NS = CPLX ? 2 : 1;
-  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, nb = mp.nb_e ? mp.nb_e[e] : d.nb, lrow = (mp.nip_e ? mp.nip_e[e] : d.nil) - 1;
+  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, nb = mp.nb_e ? mp.nb_e[e] : d.nb, lrow0 = (mp.nip_e ? mp.nip_e[e] : d.nil) - d.nload;
   if (bq < nb && iq < ni) {
     int ib = pb[bq], ii = pi[iq];
     double s = sb[bq] * si[iq];
@@ -72,9 +75,12 @@ __global__ void scatter_schur_kernel(DenseDims d, const double *Am, OutMaps mp, 
   }
   if (blockIdx.y == 0 && threadIdx.y == 0 && bq < nb) {
     int ib = pb[bq];
-    double *o = BS + (long long)e * sBS * NS + (long long)bq * NS;
-    o[0] = sb[bq] * Z[(long long)lrow * M + ib];
-    if (CPLX) o[1] = -sb[bq] * Z[apl + (long long)lrow * M + ib];
+    for (int q = 0; q < d.nload; q++) {   // BSchur(nb, NR_RHS)
+      const int lrow = lrow0 + q;
+      double *o = BS + (long long)e * sBS * NS + ((long long)q * nb + bq) * NS;
+      o[0] = sb[bq] * Z[(long long)lrow * M + ib];
+      if (CPLX) o[1] = -sb[bq] * Z[apl + (long long)lrow * M + ib];
+    }
   }
 }
 
@@ -82,12 +88,14 @@ __global__ void scatter_schur_kernel(DenseDims d, const double *Am, OutMaps mp, 
 // xi / xb in the caller's layout (column-major, interleaved complex), per-element sizes.
 template <bool CPLX>
 __global__ void stc_bwd_kernel(const int *__restrict__ ni_e, const int *__restrict__ nb_e, int ni_u, int nb_u, const double *AS, long long sAS,
-                               const double *BS, long long sBS, const double *xi, long long sxi, double *xb, long long sxb) {
+                               const double *BS, long long sBS, const double *xi, long long sxi, double *xb, long long sxb, int nrhs = 1) {
   constexpr int NS = CPLX ? 2 : 1;
   const int e = blockIdx.y, r = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
   const int ni = ni_e ? ni_e[e] : ni_u, nb = nb_e ? nb_e[e] : nb_u;
   if (r >= nb) return;
-  const double *A = AS + (long long)e * sAS * NS, *x = xi + (long long)e * sxi * NS;
+  const double *A = AS + (long long)e * sAS * NS;
+  for (int q = 0; q < nrhs; q++) {   // xi(ni, NR_RHS), xb(nb, NR_RHS): column q at offset q*ni / q*nb
+  const double *x = xi + ((long long)e * sxi + (long long)q * ni) * NS;
   double sr = 0, si = 0;
   for (int c = lane; c < ni; c += 32) {
     const double *a = A + ((long long)r + (long long)nb * c) * NS;
@@ -96,22 +104,25 @@ __global__ void stc_bwd_kernel(const int *__restrict__ ni_e, const int *__restri
   }
   for (int o = 16; o; o >>= 1) { sr += __shfl_xor_sync(0xffffffffu, sr, o); if (CPLX) si += __shfl_xor_sync(0xffffffffu, si, o); }
   if (lane == 0) {
-    const double *b = BS + (long long)e * sBS * NS + (long long)r * NS;
-    double *o = xb + (long long)e * sxb * NS + (long long)r * NS;
+    const double *b = BS + (long long)e * sBS * NS + ((long long)q * nb + r) * NS;
+    double *o = xb + (long long)e * sxb * NS + ((long long)q * nb + r) * NS;
     o[0] = b[0] - sr;
     if (CPLX) o[1] = b[1] - si;
+  }
   }
 }
 
 // stc_bwd on the device-resident store: element e's factors at AS[e] / BS[e] (one warp per bubble row); grid (ceil(nbmax/8), nel)
 template <bool CPLX>
 __global__ void stc_bwd_ptr_kernel(const double *const *__restrict__ AS, const double *const *__restrict__ BS, const int *__restrict__ ni_e,
-                                   const int *__restrict__ nb_e, const double *xi, long long sxi, double *xb, long long sxb) {
+                                   const int *__restrict__ nb_e, const double *xi, long long sxi, double *xb, long long sxb, int nrhs) {
   constexpr int NS = CPLX ? 2 : 1;
   const int e = blockIdx.y, r = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
   const int ni = ni_e[e], nb = nb_e[e];
   if (r >= nb) return;
-  const double *A = AS[e], *x = xi + (long long)e * sxi * NS;
+  const double *A = AS[e];
+  for (int q = 0; q < nrhs; q++) {
+  const double *x = xi + ((long long)e * sxi + (long long)q * ni) * NS;
   double sr = 0, si = 0;
   for (int c = lane; c < ni; c += 32) {
     const double *a = A + ((long long)r + (long long)nb * c) * NS;
@@ -120,10 +131,11 @@ __global__ void stc_bwd_ptr_kernel(const double *const *__restrict__ AS, const d
   }
   for (int o = 16; o; o >>= 1) { sr += __shfl_xor_sync(0xffffffffu, sr, o); if (CPLX) si += __shfl_xor_sync(0xffffffffu, si, o); }
   if (lane == 0) {
-    const double *b = BS[e] + (long long)r * NS;
-    double *o = xb + (long long)e * sxb * NS + (long long)r * NS;
+    const double *b = BS[e] + ((long long)q * nb + r) * NS;
+    double *o = xb + (long long)e * sxb * NS + ((long long)q * nb + r) * NS;
     o[0] = b[0] - sr;
     if (CPLX) o[1] = b[1] - si;
+  }
   }
 }
 
@@ -193,7 +205,7 @@ __global__ void scatter_condensed_rs_kernel(DenseDims d, const double *Am, OutMa
   const int r = blockIdx.x * 16 + threadIdx.x, c = blockIdx.y * 16 + threadIdx.y;
   const int M = d.M();
   const double *S = Am + (long long)e * (long long)d.a_plane() + (long long)d.nbp * M + d.nbp;
-  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, lrow = (mp.nip_e ? mp.nip_e[e] : d.nil) - 2;
+  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, lrow0 = (mp.nip_e ? mp.nip_e[e] : d.nil) - d.nload;   // first pair of load rows
   if (r < ni && c < ni && (!packed || r >= c)) {
     const int a = r >= c ? r : c, b = r >= c ? c : r;
     double re, im;
@@ -203,10 +215,13 @@ __global__ void scatter_condensed_rs_kernel(DenseDims d, const double *Am, OutMa
     o[0] = re; o[1] = im;
   }
   if (blockIdx.y == 0 && threadIdx.y == 0 && r < ni) {
-    double re, im;
-    rs_load(S[(long long)lrow * M + r], S[(long long)(lrow + 1) * M + r], rs_phase_i(r), re, im);
-    double *o = Bi + (long long)e * sB * 2 + (long long)r * 2;
-    o[0] = re; o[1] = im;
+    for (int q = 0; q < d.nload / 2; q++) {
+      const int lrow = lrow0 + 2 * q;
+      double re, im;
+      rs_load(S[(long long)lrow * M + r], S[(long long)(lrow + 1) * M + r], rs_phase_i(r), re, im);
+      double *o = Bi + (long long)e * sB * 2 + ((long long)q * ni + r) * 2;
+      o[0] = re; o[1] = im;
+    }
   }
 }
 
@@ -216,7 +231,7 @@ __global__ void scatter_schur_rs_kernel(DenseDims d, const double *Am, OutMaps m
   const int bq = blockIdx.x * 16 + threadIdx.x, iq = blockIdx.y * 16 + threadIdx.y;
   const int M = d.M();
   const double *Z = Am + (long long)e * (long long)d.a_plane() + (long long)d.nbp * M;
-  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, nb = mp.nb_e ? mp.nb_e[e] : d.nb, lrow = (mp.nip_e ? mp.nip_e[e] : d.nil) - 2;
+  const int ni = mp.ni_e ? mp.ni_e[e] : d.ni, nb = mp.nb_e ? mp.nb_e[e] : d.nb, lrow0 = (mp.nip_e ? mp.nip_e[e] : d.nil) - d.nload;
   if (bq < nb && iq < ni) {
     double re, im;
     rs_apply(Z[(long long)iq * M + bq], rs_phase_b(bq), rs_phase_i(iq), re, im);
@@ -224,10 +239,13 @@ __global__ void scatter_schur_rs_kernel(DenseDims d, const double *Am, OutMaps m
     o[0] = re; o[1] = im;
   }
   if (blockIdx.y == 0 && threadIdx.y == 0 && bq < nb) {
-    double re, im;
-    rs_load(Z[(long long)lrow * M + bq], Z[(long long)(lrow + 1) * M + bq], rs_phase_b(bq), re, im);
-    double *o = BS + (long long)e * sBS * 2 + (long long)bq * 2;
-    o[0] = re; o[1] = im;
+    for (int q = 0; q < d.nload / 2; q++) {
+      const int lrow = lrow0 + 2 * q;
+      double re, im;
+      rs_load(Z[(long long)lrow * M + bq], Z[(long long)(lrow + 1) * M + bq], rs_phase_b(bq), re, im);
+      double *o = BS + (long long)e * sBS * 2 + ((long long)q * nb + bq) * 2;
+      o[0] = re; o[1] = im;
+    }
   }
 }
 

@@ -39,6 +39,7 @@ struct FormParams {
   // flops of the reference's ZPOTRF/ZTRTRS/ZHERK) and the phases come back in the output kernels (formats.cuh).
   bool real_struct = true;
   // constant permittivity tensor of ultraweak Maxwell (get_permittivity: za = i w eps * eps_t, elem_opt.F90:260-266); entry (i,j) at [i + 3j]
+  int nrhs = 1;   // NR_RHS: load vectors per element (DPG problems; the extra ones come from source tables)
   bool tensor = false;
   std::complex<double> epst[9];
   bool tensor_real() const { for (int i = 0; i < 9; i++) if (epst[i].imag() != 0.0) return false; return true; }
@@ -88,8 +89,9 @@ struct BlockBuilder {
   BlockDesc B;
   BlockBuilder(SigHost &s, int famA, int famB, ChannelDesc c0, ChannelDesc c1) : S(s) {
     B.famA = famA; B.famB = famB; B.t0 = (int)S.term.size(); B.nt = 0; B.s0 = (int)S.slot.size(); B.ns = 0;
-    B.ch[0] = c0; B.ch[1] = c1;
+    B.ch[0] = c0; B.ch[1] = c1; B.is_load = 0;
   }
+  BlockBuilder &load() { B.is_load = 1; return *this; }   // this block is a load vector (NR_RHS > 1 integrates it once per right-hand side)
   // add   coef * (c0, c1) * integral( dA-derivative of A  *  dB-derivative of B  *  field )
   void add(int dA, int dB, int field, double coef, double c0, double c1) {
     if (coef == 0.0 || (c0 == 0.0 && c1 == 0.0)) return;
@@ -258,7 +260,7 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
     S.cplx = true; S.dpg = true; S.ntest = 2 * nEE; S.ni = 2 * nEi; S.nb = 6 * nQ;
     DenseDims &D = S.dims;
     const bool rs = rs_applicable(P);
-    D.cplx = !rs; D.rs = rs; D.nload = rs ? 2 : 1; D.dpg = true; D.n = S.ntest; D.nb = S.nb; D.ni = S.ni; D.finish();
+    D.cplx = !rs; D.rs = rs; D.nload = (rs ? 2 : 1) * P.nrhs; D.dpg = true; D.n = S.ntest; D.nb = S.nb; D.ni = S.ni; D.finish();
     if (sizes_only) return true;
     const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nil - D.nload;   // load row(s): last padded interface rows, independent of ni
     const std::complex<double> za = I * P.omega * P.eps, zc = I * P.omega * P.mu;
@@ -349,6 +351,7 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
     for (int a = 0; a < 3; a++) {
       // real-structured: Re and Im of the stored load row (= conj(l)) go to the two load rows of the single plane
       BlockBuilder b(S, unit, tf[a], channel(0, 0, rowL, offE[a]), rs ? channel(0, 0, rowL + 1, offE[a]) : channel(0, 1, rowL, offE[a]));
+      b.load();
       b.add(-1, -1, F_SRC + 2 * a, 1.0, 1.0, 0.0);
       b.add(-1, -1, F_SRC + 2 * a + 1, 1.0, 0.0, -1.0);
       b.finish();
@@ -398,9 +401,9 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
     const int fu = add_family(S, ng[0], ng[1], ng[2], T_H, T_H, T_H);
     S.cplx = false; S.dpg = true; S.ntest = nHH; S.ni = iH + nVi; S.nb = bH;
     DenseDims &D = S.dims;
-    D.cplx = false; D.dpg = true; D.n = nHH; D.nb = S.nb; D.ni = S.ni; D.finish();
+    D.cplx = false; D.dpg = true; D.nload = P.nrhs; D.n = nHH; D.nb = S.nb; D.ni = S.ni; D.finish();
     if (sizes_only) return true;
-    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nil - 1;   // load row: last (padded) interface row, independent of ni
+    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nil - D.nload;   // load rows: the last padded interface rows, independent of ni
     const int mapU = add_grid_map(S, hd, -1, ng, [&](int k) { return k < iH ? rowI + k : rowB + (k - iH); });
     {  // Gram (v,q) + (grad v, grad q)
       BlockBuilder b(S, ft, ft, channel(0, 0, 0, 0), no_channel());
@@ -415,6 +418,7 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
     }
     {  // load
       BlockBuilder b(S, unit, ft, channel(0, 0, rowL, 0), no_channel());
+      b.load();
       b.add(-1, -1, F_SRC, 1.0, 1.0, 0.0);
       b.finish();
     }

@@ -209,7 +209,7 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
     S.cplx = true; S.dpg = true; S.ntest = 2 * nEE; S.ni = 2 * nEi; S.nb = 6 * nQ;
     DenseDims &D = S.dims;
     const bool rs = rs_applicable(P);   // real-structured dense phase (forms.hpp)
-    D.cplx = !rs; D.rs = rs; D.nload = rs ? 2 : 1; D.dpg = true; D.n = S.ntest; D.nb = S.nb; D.ni = S.ni; D.finish();
+    D.cplx = !rs; D.rs = rs; D.nload = (rs ? 2 : 1) * P.nrhs; D.dpg = true; D.n = S.ntest; D.nb = S.nb; D.ni = S.ni; D.finish();
     if (sizes_only) return true;
     const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nil - D.nload;   // load row(s): last padded interface rows, independent of ni
     const std::complex<double> za = I * P.omega * P.eps, zc = I * P.omega * P.mu;
@@ -310,6 +310,7 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
       }
     for (int a = 0; a < 2; a++) {   // load
       BlockBuilder b(S, unit.id, tf[a].id, channel(0, 0, rowL, tf[a].off), rs ? channel(0, 0, rowL + 1, tf[a].off) : channel(0, 1, rowL, tf[a].off));
+      b.load();
       for (int d = 0; d < 3; d++) {
         const CompRef v = pf_val(tf[a].kind, d);
         if (v.tc < 0) continue;
@@ -415,9 +416,9 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
     const PFam fu = add_pfam(S, PF_SCALAR, TG, pmax[1] + 1, T_H, nqt, tpts);
     S.cplx = false; S.dpg = true; S.ntest = nHH; S.ni = iH + nVi; S.nb = bH;
     DenseDims &D = S.dims;
-    D.cplx = false; D.dpg = true; D.n = nHH; D.nb = S.nb; D.ni = S.ni; D.finish();
+    D.cplx = false; D.dpg = true; D.nload = P.nrhs; D.n = nHH; D.nb = S.nb; D.ni = S.ni; D.finish();
     if (sizes_only) return true;
-    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nil - 1;   // load row: last (padded) interface row, independent of ni
+    const int rowB = D.np, rowI = D.np + D.nbp, rowL = rowI + D.nil - D.nload;   // load rows: the last padded interface rows, independent of ni
     const int mapU = add_pgrid_map(S, hd, 0, fu, [&](int k) { return k < iH ? rowI + k : rowB + (k - iH); });
     {
       BlockBuilder b(S, ft.id, ft.id, channel(0, 0, 0, 0), no_channel());
@@ -432,6 +433,7 @@ inline bool compile_signature_prism(const FormParams &P, const int norder[19], c
     }
     {
       BlockBuilder b(S, unit.id, ft.id, channel(0, 0, rowL, 0), no_channel());
+      b.load();
       b.addp(0, 0, 0, 0, F_SRC, 1.0, 1.0, 0.0);
       b.finish();
     }

@@ -214,7 +214,7 @@ void hp3d_gpu_params_default(hp3d_params *p) {
   p->nord_add = 1; p->maxp = 6; p->test_norm = HP3D_GRAPH_NORM; p->alpha_norm = 1.0;
   p->omega = 1.0; p->eps = 1.0; p->mu = 1.0; p->sigma = 0.0;
   p->eps_tensor[0] = p->eps_tensor[8] = p->eps_tensor[16] = 1.0;
-  p->source = HP3D_SRC_SIN; p->icomp_exact = 1; p->store_schur = 1; p->real_reduction = 1;
+  p->source = HP3D_SRC_SIN; p->icomp_exact = 1; p->store_schur = 1; p->real_reduction = 1; p->nr_rhs = 1;
 }
 
 int hp3d_gpu_init(int device) {
@@ -290,6 +290,14 @@ int hp3d_gpu_plan(int problem_kind, const hp3d_params *prm) {
   p->fp.source = prm->source; p->fp.icomp = prm->icomp_exact - 1;
   p->store_schur = prm->store_schur;
   p->fp.real_struct = prm->real_reduction != 0;
+  p->fp.nrhs = prm->nr_rhs > 0 ? prm->nr_rhs : 1;   // 0 (a zero-initialised struct) means the default
+  if (p->fp.nrhs > 1) {
+    const char *why = nullptr;
+    if (problem_kind != HP3D_POIS_PDPG && problem_kind != HP3D_MAXW_UW) why = "the Cholesky condensation of the DPG problems";
+    else if (prm->source == HP3D_SRC_SIN) why = "sources given through HP3D_SRC_TABLE (the built-in manufactured source is one load)";
+    else if (p->fp.nrhs > 16) why = "at most 16 load vectors";
+    if (why) { const int n = p->fp.nrhs; delete p; return fail(HP3D_EINVAL, "nr_rhs = %d: more than one load vector is implemented for %s", n, why); }
+  }
   p->fp.tensor = tensor;
   for (int i = 0; i < 9; i++) p->fp.epst[i] = std::complex<double>(prm->eps_tensor[2 * i], prm->eps_tensor[2 * i + 1]);
   p->aii_packed = prm->aii_packed;
@@ -449,6 +457,7 @@ namespace {
 struct ClocStore {
   int plan = -1;
   bool cplx = false;
+  int nrhs = 1;   // NR_RHS of the plan: BSchur blocks hold nb x nrhs values
   size_t limit = 0, bytes = 0;
   struct Slot { double *AS, *BS; int ni, nb; };
   struct Spill { int etype; int norder[19], norie[12], norif[6]; std::vector<double> xnod; std::vector<double> src; };
@@ -580,6 +589,8 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
   if (int drc = enter_device()) return drc;
   Plan *p = plan_of(plan);
   if (!p) return fail(HP3D_ENOPLAN, "no such plan %d", plan);
+  const long long nrhs = p->fp.nrhs;
+  if (nrhs > 1 && mode != MODE_ELEM && mode != MODE_BWD) return fail(HP3D_EINVAL, "nr_rhs = %lld: this entry point carries one load vector", nrhs);
   if (nel < 0 || !norder || !norie || !norif || !xnod) return fail(HP3D_EINVAL, "null argument");
   if (mode == MODE_ELEM && (!Aii || !Bi)) return fail(HP3D_EINVAL, "null argument");
   if (mode == MODE_CELEM && !cc) return fail(HP3D_EINVAL, "null argument");
@@ -589,6 +600,7 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
   if (mode == MODE_RESID && p->fp.kind != HP3D_POIS_PDPG && p->fp.kind != HP3D_MAXW_UW) return fail(HP3D_EINVAL, "the element residual is defined for the DPG problems only");
   if (p->fp.source == HP3D_SRC_TABLE && !source_qp) return fail(HP3D_EINVAL, "source == HP3D_SRC_TABLE needs source_qp");
   if (cloc && !big) return fail(HP3D_EINVAL, "the device-resident Schur store is filled by the element / celem calls only");
+
   const bool to_host_schur = big && !cloc && p->store_schur && ASchur && BSchur;
   const bool want_schur = mode == MODE_BWD || to_host_schur || cloc != nullptr;
   const bool packed = mode == MODE_ELEM && p->aii_packed == 1;
@@ -614,15 +626,15 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
     if (mode == MODE_ELEM) {
       const long long need = packed ? ni * (ni + 1) / 2 : ni * ni;
       if (sAii < need) return fail(HP3D_EINVAL, "Aii stride %lld < %lld scalars (%s ni = %lld)", sAii, need, packed ? "packed triangle of" : "ni^2,", ni);
-      if (sBi < ni) return fail(HP3D_EINVAL, "Bi stride %lld < ni = %lld", sBi, ni);
+      if (sBi < ni * nrhs) return fail(HP3D_EINVAL, "Bi stride %lld < ni * nr_rhs = %lld", sBi, ni * nrhs);
     }
     if (to_host_schur && nb > 0) {
       if (sAS < nb * ni) return fail(HP3D_EINVAL, "ASchur stride %lld < nb*ni = %lld", sAS, nb * ni);
-      if (sBS < nb) return fail(HP3D_EINVAL, "BSchur stride %lld < nb = %lld", sBS, nb);
+      if (sBS < nb * nrhs) return fail(HP3D_EINVAL, "BSchur stride %lld < nb * nr_rhs = %lld", sBS, nb * nrhs);
     }
     if (!big) {
-      if (sxi < ni) return fail(HP3D_EINVAL, "xi stride %lld < ni = %lld", sxi, ni);
-      if (xb && sxb < nb) return fail(HP3D_EINVAL, "xb stride %lld < nb = %lld", sxb, nb);
+      if (sxi < ni * nrhs) return fail(HP3D_EINVAL, "xi stride %lld < ni * nr_rhs = %lld", sxi, ni * nrhs);
+      if (xb && sxb < nb * nrhs) return fail(HP3D_EINVAL, "xb stride %lld < nb * nr_rhs = %lld", sxb, nb * nrhs);
       if (mode == MODE_RESID && nb > 0 && !xb) return fail(HP3D_EINVAL, "residual: xb (bubble dofs) is required for elements with bubbles");
     }
     if (mode == MODE_RESID && sizeof(double) * 2 * (size_t)sh.d.M() > (size_t)RESID_SMEM_MAX)
@@ -653,7 +665,7 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
     size_t granted = 0;
     for (; granted < fresh.size(); granted++) {
       const ClocStore::Slot &sl = eslot[fresh[granted]];
-      const size_t a = esz * (size_t)sl.nb * sl.ni, b2 = esz * (size_t)sl.nb;
+      const size_t a = esz * (size_t)sl.nb * sl.ni, b2 = esz * (size_t)sl.nb * (size_t)nrhs;
       if (cloc->bytes + needA + needB + a + b2 + 512 > cloc->limit) break;
       needA += a; needB += b2;
     }
@@ -668,7 +680,7 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
         for (size_t k = 0; k < granted; k++) {
           ClocStore::Slot &sl = eslot[fresh[k]];
           sl.AS = (double *)(slab + oa); sl.BS = (double *)(slab + ob);
-          oa += esz * (size_t)sl.nb * sl.ni; ob += esz * (size_t)sl.nb;
+          oa += esz * (size_t)sl.nb * sl.ni; ob += esz * (size_t)sl.nb * (size_t)nrhs;
           cloc->slots[iel ? iel[fresh[k]] : fresh[k]] = sl;
         }
       }
@@ -732,7 +744,7 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
       CInfo ci;
       ci.C = &C; ci.cap = cap; ci.NS = sh.ns(); ci.es = sizeof(double) * ci.NS;
       ci.nx = 3 * (size_t)sh.nH_max; ci.nsrc = sh.src_max;
-      ci.sA = (size_t)sh.d.ni * sh.d.ni; ci.sB = sh.d.ni; ci.sS = (size_t)sh.d.nb * sh.d.ni; ci.sT = sh.d.nb;   // device staging strides
+      ci.sA = (size_t)sh.d.ni * sh.d.ni; ci.sB = (size_t)sh.d.ni * nrhs; ci.sS = (size_t)sh.d.nb * sh.d.ni; ci.sT = (size_t)sh.d.nb * nrhs;   // device staging strides
       const std::vector<size_t> sizes = chunk_plan(C.el.size(), cap, NL, g_max_chunk);
       size_t c0 = 0;
       for (size_t n : sizes) { recs.push_back(Rec{(int)cinfo.size(), c0, (int)n, nullptr, nullptr, nullptr, false}); c0 += n; }
@@ -762,7 +774,7 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
     for (int i = 0; i < R.n; i++) {
       const int e = I.C->el[R.c0 + i];
       if (info) info[e] = R.h_info[i];
-      if (mode == MODE_BWD) memcpy((char *)xb + I.es * sxb * e, R.h_xb + I.NS * (I.sT + 1) * i, I.es * I.C->sig[R.c0 + i]->h.nb);
+      if (mode == MODE_BWD) memcpy((char *)xb + I.es * sxb * e, R.h_xb + I.NS * (I.sT + 1) * i, I.es * I.C->sig[R.c0 + i]->h.nb * nrhs);
       if (mode == MODE_RESID) resid[e] = R.h_res[i];
     }
   };
@@ -796,11 +808,11 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
       const SigHost &h = C.sig[c0 + i]->h;
       memcpy(L.h_xnod + (size_t)i * nx, xnod + (size_t)e * xnod_ld, sizeof(double) * 3 * h.nH);
       if (gp.source == HP3D_SRC_TABLE)
-        memcpy(L.h_src + (size_t)i * nsrc, (const double *)source_qp + (size_t)e * source_ld, sizeof(double) * h.nint * (h.cplx ? 6 : 1));
+        memcpy(L.h_src + (size_t)i * nsrc, (const double *)source_qp + (size_t)e * source_ld, sizeof(double) * h.nint * (h.cplx ? 6 : 1) * nrhs);
       L.h_cnt[i] = h.ni; L.h_cnt[lcap + i] = h.nb; L.h_cnt[2 * lcap + i] = h.dims.nil;
       if (mode == MODE_CELEM) L.h_cel[i] = e;
       if (!big) {
-        memcpy(L.h_xi + NS * sB * i, (const char *)xi + es * sxi * e, es * h.ni);
+        memcpy(L.h_xi + NS * sB * i, (const char *)xi + es * sxi * e, es * h.ni * nrhs);
         if (mode == MODE_RESID && h.nb > 0) memcpy(L.h_xb + NS * (sT + 1) * i, (const char *)xb + es * sxb * e, es * h.nb);
       }
     }
@@ -823,7 +835,7 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
       for (int i = 0; i < n;) {
         const ClocStore::Slot &s0 = eslot[el[c0 + i]];
         if (!s0.AS) { i++; continue; }
-        const size_t ba = (size_t)s0.nb * s0.ni, bb = (size_t)s0.nb;
+        const size_t ba = (size_t)s0.nb * s0.ni, bb = (size_t)s0.nb * (size_t)nrhs;
         int j = i + 1;
         if (ba == sS && bb == sT)
           while (j < n && eslot[el[c0 + j]].AS == s0.AS + NS * ba * (j - i) && eslot[el[c0 + j]].BS == s0.BS + NS * bb * (j - i) &&
@@ -899,9 +911,9 @@ int batch_impl(int mode, int plan, int nel, const int *etype, const int *norder,
           }
         } else
           copy(Aii, sAii, o.Aii, sA, packed ? (size_t)h.ni * (h.ni + 1) / 2 : (size_t)h.ni * h.ni);
-        copy(Bi, sBi, o.Bi, sB, (size_t)h.ni);
+        copy(Bi, sBi, o.Bi, sB, (size_t)h.ni * nrhs);
       }
-      if (to_host_schur) { copy(ASchur, sAS, o.AS, sS, (size_t)h.nb * h.ni); copy(BSchur, sBS, o.BS, sT, (size_t)h.nb); }
+      if (to_host_schur) { copy(ASchur, sAS, o.AS, sS, (size_t)h.nb * h.ni); copy(BSchur, sBS, o.BS, sT, (size_t)h.nb * nrhs); }
       i = j;
     }
     cudaMemcpyAsync(o.h_info, o.info, sizeof(int) * n, cudaMemcpyDeviceToHost, g_copy);   // pinned: stays asynchronous
@@ -1147,7 +1159,7 @@ int hp3d_gpu_cloc_create(int plan, long long limit_bytes) {
     limit_bytes = (long long)(0.6 * (double)fr);
   }
   ClocStore *c = new ClocStore();
-  c->plan = plan; c->cplx = p->fp.kind >= HP3D_MAXW_GAL; c->limit = (size_t)limit_bytes;
+  c->plan = plan; c->cplx = p->fp.kind >= HP3D_MAXW_GAL; c->nrhs = p->fp.nrhs; c->limit = (size_t)limit_bytes;
   for (size_t i = 0; i < g_clocs.size(); i++)
     if (!g_clocs[i]) { g_clocs[i] = c; return (int)i; }
   g_clocs.push_back(c);
@@ -1216,7 +1228,7 @@ int hp3d_gpu_cloc_fetch(int cloc, long long iel, void *ASchur, void *BSchur, int
   if (nb) *nb = sl.nb;
   for (int i = 0; i < LaneSet::NLANE; i++) cudaStreamSynchronize(g_lane_stream[i]);
   if (ASchur && sl.nb) CUDA_TRY(cudaMemcpy(ASchur, sl.AS, es * (size_t)sl.nb * sl.ni, cudaMemcpyDeviceToHost));
-  if (BSchur && sl.nb) CUDA_TRY(cudaMemcpy(BSchur, sl.BS, es * (size_t)sl.nb, cudaMemcpyDeviceToHost));
+  if (BSchur && sl.nb) CUDA_TRY(cudaMemcpy(BSchur, sl.BS, es * (size_t)sl.nb * c->nrhs, cudaMemcpyDeviceToHost));
   return HP3D_OK;
 }
 
@@ -1228,7 +1240,7 @@ int hp3d_gpu_cloc_bwd_batch(int cloc, int nel, const long long *iel, const void 
   if (!c) return fail(HP3D_EINVAL, "no such Schur store %d", cloc);
   if (nel < 0 || (nel > 0 && (!xi || !xb))) return fail(HP3D_EINVAL, "cloc_bwd: null argument");
   const int NS = c->cplx ? 2 : 1;
-  const size_t es = sizeof(double) * NS;
+  const size_t es = sizeof(double) * NS, nr = (size_t)c->nrhs;   // xi / xb hold nr columns per element (column q at q*ni / q*nb)
   std::vector<int> res, spl;   // caller positions of resident / spilled elements
   int nimax = 0, nbmax = 0;
   for (int e = 0; e < nel; e++) {
@@ -1237,7 +1249,8 @@ int hp3d_gpu_cloc_bwd_batch(int cloc, int nel, const long long *iel, const void 
     if (it != c->slots.end()) {
       res.push_back(e);
       nimax = std::max(nimax, it->second.ni); nbmax = std::max(nbmax, it->second.nb);
-      if (sxi < it->second.ni || sxb < it->second.nb) return fail(HP3D_EINVAL, "cloc_bwd: element %lld needs strides >= (%d, %d)", id, it->second.ni, it->second.nb);
+      if (sxi < (long long)(it->second.ni * nr) || sxb < (long long)(it->second.nb * nr))
+        return fail(HP3D_EINVAL, "cloc_bwd: element %lld needs strides >= (%d, %d) x nr_rhs", id, it->second.ni, it->second.nb);
       if (nb_out) nb_out[e] = it->second.nb;
       if (info) info[e] = 0;
     } else if (c->spilled.count(id)) spl.push_back(e);
@@ -1246,13 +1259,14 @@ int hp3d_gpu_cloc_bwd_batch(int cloc, int nel, const long long *iel, const void 
   for (int i = 0; i < LaneSet::NLANE; i++) cudaStreamSynchronize(g_lane_stream[i]);   // the factors were written on the lane streams
   // resident elements: one warp per bubble row reads its factors in place; chunks bounded by the grid limit and a 256 MB staging budget
   if (!res.empty() && nbmax > 0) {
-    const size_t per = es * ((size_t)nimax + nbmax) + 2 * sizeof(void *) + 2 * sizeof(int);
+    const size_t wi = (size_t)nimax * nr, wb = (size_t)nbmax * nr;   // staging widths per element
+    const size_t per = es * (wi + wb) + 2 * sizeof(void *) + 2 * sizeof(int);
     const int chunk = (int)std::min<size_t>(std::min<size_t>(res.size(), 32768), std::max<size_t>(1, ((size_t)256 << 20) / per));
     struct Bufs {
       void *d = nullptr, *h = nullptr;
       ~Bufs() { if (d) cudaFree(d); if (h) cudaFreeHost(h); }
     } bufs;
-    const size_t oX = 0, oY = oX + es * (size_t)nimax * chunk, oPA = (oY + es * (size_t)nbmax * chunk + 15) & ~(size_t)15,
+    const size_t oX = 0, oY = oX + es * wi * chunk, oPA = (oY + es * wb * chunk + 15) & ~(size_t)15,
                  oPB = oPA + sizeof(void *) * chunk, oNI = oPB + sizeof(void *) * chunk, oNB = oNI + sizeof(int) * chunk, total = oNB + sizeof(int) * chunk;
     if (cudaMalloc(&bufs.d, total) != cudaSuccess || cudaMallocHost(&bufs.h, total) != cudaSuccess) { cudaGetLastError(); return fail(HP3D_ENOMEM, "cloc_bwd: staging buffers"); }
     char *h = (char *)bufs.h, *d = (char *)bufs.d;
@@ -1261,26 +1275,26 @@ int hp3d_gpu_cloc_bwd_batch(int cloc, int nel, const long long *iel, const void 
       for (int i = 0; i < n; i++) {
         const int e = res[c0 + i];
         const ClocStore::Slot &sl = c->slots.find(iel ? iel[e] : e)->second;
-        memcpy(h + oX + es * (size_t)nimax * i, (const char *)xi + es * sxi * e, es * sl.ni);
+        memcpy(h + oX + es * wi * i, (const char *)xi + es * sxi * e, es * sl.ni * nr);
         ((const double **)(h + oPA))[i] = sl.AS; ((const double **)(h + oPB))[i] = sl.BS;
         ((int *)(h + oNI))[i] = sl.ni; ((int *)(h + oNB))[i] = sl.nb;
       }
-      CUDA_TRY(cudaMemcpyAsync(d, h, es * (size_t)nimax * n, cudaMemcpyHostToDevice, g_compute));
+      CUDA_TRY(cudaMemcpyAsync(d, h, es * wi * n, cudaMemcpyHostToDevice, g_compute));
       CUDA_TRY(cudaMemcpyAsync(d + oPA, h + oPA, total - oPA, cudaMemcpyHostToDevice, g_compute));
       dim3 grid((nbmax + 7) / 8, n);
       if (c->cplx)
         stc_bwd_ptr_kernel<true><<<grid, 256, 0, g_compute>>>((const double *const *)(d + oPA), (const double *const *)(d + oPB), (const int *)(d + oNI),
-                                                              (const int *)(d + oNB), (const double *)(d + oX), nimax, (double *)(d + oY), nbmax);
+                                                              (const int *)(d + oNB), (const double *)(d + oX), (long long)wi, (double *)(d + oY), (long long)wb, c->nrhs);
       else
         stc_bwd_ptr_kernel<false><<<grid, 256, 0, g_compute>>>((const double *const *)(d + oPA), (const double *const *)(d + oPB), (const int *)(d + oNI),
-                                                               (const int *)(d + oNB), (const double *)(d + oX), nimax, (double *)(d + oY), nbmax);
+                                                               (const int *)(d + oNB), (const double *)(d + oX), (long long)wi, (double *)(d + oY), (long long)wb, c->nrhs);
       g_launches++;
       CUDA_TRY(cudaGetLastError());
-      CUDA_TRY(cudaMemcpyAsync(h + oY, d + oY, es * (size_t)nbmax * n, cudaMemcpyDeviceToHost, g_compute));
+      CUDA_TRY(cudaMemcpyAsync(h + oY, d + oY, es * wb * n, cudaMemcpyDeviceToHost, g_compute));
       CUDA_TRY(cudaStreamSynchronize(g_compute));
       for (int i = 0; i < n; i++) {
         const int e = res[c0 + i];
-        memcpy((char *)xb + es * sxb * e, h + oY + es * (size_t)nbmax * i, es * ((int *)(h + oNB))[i]);
+        memcpy((char *)xb + es * sxb * e, h + oY + es * wb * i, es * ((int *)(h + oNB))[i] * nr);
       }
     }
   }
@@ -1308,7 +1322,7 @@ int hp3d_gpu_cloc_bwd_batch(int cloc, int nel, const long long *iel, const void 
     if (rc) return rc;
     for (int k = 0; k < m; k++) {
       const int e = spl[k];
-      memcpy((char *)xb + es * sxb * e, &xbs[es * (size_t)sxb * k], es * nbo[k]);
+      memcpy((char *)xb + es * sxb * e, &xbs[es * (size_t)sxb * k], es * nbo[k] * nr);
       if (nb_out) nb_out[e] = nbo[k];
       if (info) info[e] = inf[k];
     }

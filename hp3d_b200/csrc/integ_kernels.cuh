@@ -267,7 +267,7 @@ struct ChannelDesc {
   int row0, col0; // affine target (row = row0 + lA) unless a map is given
   int rowmap, colmap;  // offsets into the map pool or -1.  map entry m: 0 skip, else target = |m|-1, sign = sgn(m)
 };
-struct BlockDesc { int famA, famB, t0, nt, s0, ns; ChannelDesc ch[2]; };
+struct BlockDesc { int famA, famB, t0, nt, s0, ns; ChannelDesc ch[2]; int is_load; };   // is_load: the block integrates a load vector (rows of the unit family)
 struct WorkItem { short block, iA, jA, pad; };
 
 struct MatTarget { double *base; long long batch, plane; int ld; };
@@ -284,6 +284,8 @@ struct Tp3Args {
   int nq[3];
   int nint;
   MatTarget mat[2];
+  int load_only;                // NR_RHS > 1, extra passes: only the load blocks run ...
+  int load_shift;               // ... and their rows move down by this many rows (the q-th load's rows)
 };
 
 // z contraction shared by the hexahedron and prism kernels; thread item = (kA, (iB,jB)), registers over kB.
@@ -369,6 +371,7 @@ __device__ __forceinline__ void tp_stage2(const Tp3Args &A, const BlockDesc &B, 
       long long row;
       if (C.rowmap >= 0) { const int m = A.maps[C.rowmap + lA]; if (m == 0) continue; row = (m < 0 ? -m : m) - 1; if (m < 0) sg[ch] = -1.0; }
       else row = C.row0 + lA;
+      if (B.is_load) row += A.load_shift;
       const MatTarget M = A.mat[C.mat];
       dst[ch] = M.base + (long long)e * M.batch + (long long)C.plane * M.plane + row * M.ld;
     }
@@ -466,6 +469,7 @@ __global__ void __launch_bounds__(448, 2) tp3_kernel(Tp3Args A, int off_F, int o
   const int e = blockIdx.y, tid = threadIdx.x;
   const WorkItem wi = A.work[blockIdx.x];
   const BlockDesc &B = A.block[wi.block];
+  if (A.load_only && !B.is_load) return;   // extra right-hand sides: only the load blocks are integrated again
   const FamilyDesc fa = A.fam[B.famA], fb = A.fam[B.famB];
   const int iA = wi.iA;
   const int nqx = A.nq[0], nqy = A.nq[1], nqz = A.nq[2];
@@ -560,6 +564,7 @@ __global__ void __launch_bounds__(384, 2) tp2_kernel(Tp3Args A, const double *__
   const int e = blockIdx.y;
   const WorkItem wi = A.work[blockIdx.x];
   const BlockDesc &B = A.block[wi.block];
+  if (A.load_only && !B.is_load) return;   // extra right-hand sides: only the load blocks are integrated again
   const FamilyDesc fa = A.fam[B.famA], fb = A.fam[B.famB];
   const int tA = wi.iA;
   const int nqt = A.nq[0], nqz = A.nq[2];

@@ -73,6 +73,12 @@ typedef struct hp3d_params {
                             the bytes at ni = 600); the upper blocks are mirrored by the library's host threads
                             (HP3D_HOST_THREADS; default: the CPUs the process is bound to minus one, at most 8) while the device works on the next chunks.
                             0 (default): the full block crosses PCIe                                              */
+  int nr_rhs;            /* NR_RHS (src/modules/parameters.F90): number of load vectors carried through the condensation
+                            (stc.F90:223-257: Bi(ni,NR_RHS), CLOC%BSchur(nb,NR_RHS)).  1 (default) for every problem of the
+                            reference.  > 1: DPG problems through hp3d_gpu_elem_batch / _elem_batch_cloc / _cloc_bwd_batch /
+                            _stc_bwd_batch only, sources through HP3D_SRC_TABLE: element e holds nr_rhs consecutive
+                            tables (each of the element's own nint points, hp3d_gpu_sig_dims) at source_qp + e*source_ld; Bi, BSchur, xi, xb then hold nr_rhs columns per element
+                            (column q at offset q*ni resp. q*nb of the element's block)                               */
 } hp3d_params;
 
 void hp3d_gpu_params_default(hp3d_params *p);

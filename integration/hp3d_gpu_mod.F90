@@ -20,7 +20,7 @@ module hp3d_gpu
       integer(c_int) :: nord_add, maxp, test_norm
       real(c_double) :: alpha_norm, omega, eps, mu, sigma
       real(c_double) :: eps_tensor(18)
-      integer(c_int) :: source, icomp_exact, store_schur, real_reduction, aii_packed
+      integer(c_int) :: source, icomp_exact, store_schur, real_reduction, aii_packed, nr_rhs
    end type
    type, bind(C) :: hp3d_physics                ! struct hp3d_physics (src/modules/physics.F90: D_TYPE, NR_COMP, ADRES, NR?VAR)
       integer(c_int) :: nphys

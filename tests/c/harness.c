@@ -19,9 +19,9 @@
 static int layout(void) {
   printf("{\"sizeof_params\": %zu, \"params\": {", sizeof(hp3d_params));
 #define F(f) printf("\"%s\": [%zu, %zu], ", #f, offsetof(hp3d_params, f), sizeof(((hp3d_params *)0)->f));
-  F(nord_add) F(maxp) F(test_norm) F(alpha_norm) F(omega) F(eps) F(mu) F(sigma) F(eps_tensor) F(source) F(icomp_exact) F(store_schur) F(real_reduction)
+  F(nord_add) F(maxp) F(test_norm) F(alpha_norm) F(omega) F(eps) F(mu) F(sigma) F(eps_tensor) F(source) F(icomp_exact) F(store_schur) F(real_reduction) F(aii_packed)
 #undef F
-  printf("\"aii_packed\": [%zu, %zu]}, ", offsetof(hp3d_params, aii_packed), sizeof(((hp3d_params *)0)->aii_packed));
+  printf("\"nr_rhs\": [%zu, %zu]}, ", offsetof(hp3d_params, nr_rhs), sizeof(((hp3d_params *)0)->nr_rhs));
   printf("\"sizeof_physics\": %zu, \"physics\": {", sizeof(hp3d_physics));
 #define F(f) printf("\"%s\": [%zu, %zu], ", #f, offsetof(hp3d_physics, f), sizeof(((hp3d_physics *)0)->f));
   F(nphys) F(dtype) F(ncomp) F(adres)
