@@ -21,7 +21,7 @@
 module hp3d_gpu_driver
    use, intrinsic :: iso_c_binding
    use hp3d_gpu
-   use parameters , only: MAXbrickH, NR_RHS, ZERO
+   use parameters , only: MAXbrickH, NR_RHS
    use physics    , only: NR_PHYSA
    use data_structure3D, only: NODES, NRELES_SUBD, ELEM_SUBD          ! src/modules/data_structure3D.F90:26,420-432
    use assembly   , only: ALOC, BLOC
@@ -57,6 +57,7 @@ contains
       call hp3d_gpu_check(hp3d_gpu_init(int(mod(RANK, Ngpu), c_int)), 'hp3d_gpu_setup: init')
       Prm%store_schur = 1          ! STORE_STC: the factors are formed; they stay on the device (cloc) unless fetched
       Prm%aii_packed  = 0          ! full Aii blocks (1: packed lower triangle, 2: half over PCIe + host mirror by the library)
+      Prm%nr_rhs      = int(NR_RHS, c_int)   ! > 1: DPG problems with HP3D_SRC_TABLE sources (one table per load)
       GPU_PLAN = hp3d_gpu_plan(Kind, Prm)
       if (GPU_PLAN .lt. 0) call hp3d_gpu_check(GPU_PLAN, 'hp3d_gpu_setup: plan')
       GPU_CLOC = hp3d_gpu_cloc_create(GPU_PLAN, 0_c_long_long)     ! 0: up to 60 % of the free device memory; the rest spills to recompute
@@ -98,7 +99,7 @@ contains
          call hp3d_gpu_check(hp3d_gpu_sizes_t(GPU_PLAN, g_etype(iel), g_norder(:,iel), ni, nb, nint, nrdofH), 'sizes')
          ni_max = max(ni_max, int(ni))
       enddo
-      sAii = int(ni_max, c_long_long)**2; sBi = int(ni_max, c_long_long)
+      sAii = int(ni_max, c_long_long)**2; sBi = int(ni_max, c_long_long)*NR_RHS      ! Bi(ni,NR_RHS) per element
       es = 8_c_long_long; if (GPU_KIND .ge. HP3D_MAXW_GAL) es = 16_c_long_long
       if (c_associated(p_Aii)) then; call hp3d_gpu_host_free(p_Aii); call hp3d_gpu_host_free(p_Bi); endif
       nbytes = es*sAii*NRELES_SUBD; p_Aii = hp3d_gpu_host_alloc(max(nbytes, 8_c_long_long))
@@ -131,7 +132,7 @@ contains
    subroutine hp3d_gpu_scatter_to_aloc(Iel)
       integer, intent(in) :: Iel
       integer :: nrdofi(NR_PHYSA), nrdofb(NR_PHYSA)
-      integer :: i, j, ii, ji, ki, kj, ni, r, c
+      integer :: i, j, ii, ji, ki, kj, ni, r, c, q
 !
       call stc_get_nrdof(ELEM_SUBD(Iel), nrdofi, nrdofb)
       ni = sum(nrdofi(1:NR_PHYSA))
@@ -159,12 +160,14 @@ contains
             ki = ki + ii
          enddo
          if (ji .gt. 0) then
-            BLOC(j)%array(1:ji,1:NR_RHS) = ZERO
-            if (GPU_KIND .ge. HP3D_MAXW_GAL) then
-               BLOC(j)%array(1:ji,1) = z_Bi(kj+1:kj+ji, Iel)
-            else
-               BLOC(j)%array(1:ji,1) = r_Bi(kj+1:kj+ji, Iel)
-            endif
+!        ...Bi(ni,NR_RHS), column-major with leading dimension ni: load q of dof kj+r at (q-1)*ni + kj + r
+            do q = 1,NR_RHS
+               if (GPU_KIND .ge. HP3D_MAXW_GAL) then
+                  BLOC(j)%array(1:ji,q) = z_Bi((q-1)*ni+kj+1:(q-1)*ni+kj+ji, Iel)
+               else
+                  BLOC(j)%array(1:ji,q) = r_Bi((q-1)*ni+kj+1:(q-1)*ni+kj+ji, Iel)
+               endif
+            enddo
          endif
          kj = kj + ji
       enddo
@@ -172,7 +175,8 @@ contains
 !
 !-----------------------------------------------------------------------------------------------------------------------
 !  stc_bwd for the whole subdomain (stc_bwd_wrapper, stc.F90:529-677): Xi(1:ni,iel) = interface solution of element iel in the
-!  row order of Aii (what solout gathers, src/solver/frontal/interf/solout.F90), Xb(1:nb,iel) = BSchur - ASchur * xi.
+!  row order of Aii (what solout gathers, src/solver/frontal/interf/solout.F90), Xb(1:nb,iel) = BSchur - ASchur * xi
+!  (NR_RHS > 1: NR_RHS columns per element, column q at offset (q-1)*ni resp. (q-1)*nb; Ldxi >= ni*NR_RHS, Ldxb >= nb*NR_RHS).
 !  Elements whose factors did not fit into the store were spilled at condensation time and are recomputed here -- same result.
    subroutine hp3d_gpu_stc_bwd_subdomain(Xi, Ldxi, Xb, Ldxb, Ierr)
       integer, intent(in)  :: Ldxi, Ldxb
