@@ -306,7 +306,8 @@ __device__ __forceinline__ void build_ztab(const double *sTabZ, double *sZ, int 
 // from the y-contracted sums U in shared memory, and the two output channels formed from D_s with the slot's coefficients.
 // An m-tile is one kA and eight kB; a warp owns ONE m-tile (the warps sharing an m-tile split its n-tiles; the host sizes the
 // CTA as a multiple of the m-tile count).  Rows kB >= nBz and columns ij >= nij of a tile are computed and dropped.
-constexpr int TP_SMAX = 5;   // slots whose A fragments a thread keeps in registers; forms with more slots per block are refused
+constexpr int TP_SMAX = 5;
+constexpr int TP_TMAX = 16;  // terms of a block kept in shared memory (more: read from global memory)   // slots whose A fragments a thread keeps in registers; forms with more slots per block are refused
 template <int NMAX> struct Stage2Frag {
   static constexpr int KS = (NMAX + 3) / 4, TB = (NMAX + 7) / 8;
   double a[TP_SMAX][KS];
@@ -468,8 +469,16 @@ __global__ void __launch_bounds__(448, 2) tp3_kernel(Tp3Args A, int off_F, int o
   double *sTab = sm, *sZ = sm + 12 * TABSZ, *sF = sm + off_F, *sT1 = sm + off_T1, *sU = sm + off_U, *sQ = sm + off_Q;   // sZ: 4*NMAX*NMAX
   const int e = blockIdx.y, tid = threadIdx.x;
   const WorkItem wi = A.work[blockIdx.x];
-  const BlockDesc &B = A.block[wi.block];
-  if (A.load_only && !B.is_load) return;   // extra right-hand sides: only the load blocks are integrated again
+  // the block and its terms are read all over the kernel: shared-memory copies (global reads would be re-issued after every
+  // global store of the output, which the compiler must assume to alias them)
+  __shared__ BlockDesc sBlk;
+  __shared__ TermDesc sTerm[TP_TMAX];
+  if (tid == 0) sBlk = A.block[wi.block];
+  __syncthreads();
+  const BlockDesc &B = sBlk;
+  if (A.load_only && !B.is_load) return;   // extra right-hand sides: only the load blocks are integrated again (CTA-uniform)
+  for (int t = tid; t < B.nt && t < TP_TMAX; t += blockDim.x) sTerm[t] = A.term[B.t0 + t];
+  const TermDesc *term = B.nt <= TP_TMAX ? sTerm : A.term + B.t0;
   const FamilyDesc fa = A.fam[B.famA], fb = A.fam[B.famB];
   const int iA = wi.iA;
   const int nqx = A.nq[0], nqy = A.nq[1], nqz = A.nq[2];
@@ -484,7 +493,7 @@ __global__ void __launch_bounds__(448, 2) tp3_kernel(Tp3Args A, int off_F, int o
   }
   if (tid <= B.ns) {   // first term of every slot
     int b = 0;
-    while (b < B.nt && A.term[B.t0 + b].slot < tid) b++;
+    while (b < B.nt && A.term[B.t0 + b].slot < tid) b++;   // (global copy: sTerm is not complete before the next barrier)
     sbeg[tid] = b;
     if (tid < B.ns) { sC[2 * tid] = A.slot[B.s0 + tid].c[0]; sC[2 * tid + 1] = A.slot[B.s0 + tid].c[1]; }
   }
@@ -500,7 +509,7 @@ __global__ void __launch_bounds__(448, 2) tp3_kernel(Tp3Args A, int off_F, int o
     double *Q = sQ + (size_t)(jA & 1) * qsz;
     for (int o = tid; o < qsz; o += blockDim.x) {
       const int t = o / (nBy * NQP), r = o - t * nBy * NQP, jB = r / NQP, qy = r - jB * NQP;
-      const TermDesc T = A.term[B.t0 + t];
+      const TermDesc T = term[t];
       Q[o] = qy < nqy ? tabp(1, T.dA == 1 ? T_DH : fa.tab[1])[jA * nqy + qy] * tabp(1, T.dB == 1 ? T_DH : fb.tab[1])[jB * nqy + qy] : 0.0;
     }
   };
@@ -509,7 +518,7 @@ __global__ void __launch_bounds__(448, 2) tp3_kernel(Tp3Args A, int off_F, int o
   // ---- x contraction of every term (shared by all jA): T1[t][qz][iB][qy]
   for (int o = tid; o < B.nt * nBx * nqy * nqz; o += blockDim.x) {
     const int t = o / (nBx * nqy * nqz), r = o - t * nBx * nqy * nqz, iB = r % nBx, qyz = r / nBx, qy = qyz % nqy, qz = qyz / nqy;
-    const TermDesc T = A.term[B.t0 + t];
+    const TermDesc T = term[t];
     const double *XA = tabp(0, T.dA == 0 ? T_DH : fa.tab[0]) + iA * nqx;
     const double *XB = tabp(0, T.dB == 0 ? T_DH : fb.tab[0]) + iB * nqx;
     const double *f = sF + (size_t)t * fs + qyz * nqx;
@@ -563,8 +572,11 @@ __global__ void __launch_bounds__(384, 2) tp2_kernel(Tp3Args A, const double *__
   __shared__ __align__(16) double sC[TP_SMAX * 2];   // slot coefficients of the two channels
   const int e = blockIdx.y;
   const WorkItem wi = A.work[blockIdx.x];
-  const BlockDesc &B = A.block[wi.block];
-  if (A.load_only && !B.is_load) return;   // extra right-hand sides: only the load blocks are integrated again
+  __shared__ BlockDesc sBlk;
+  if (threadIdx.x == 0) sBlk = A.block[wi.block];
+  __syncthreads();
+  const BlockDesc &B = sBlk;
+  if (A.load_only && !B.is_load) return;   // extra right-hand sides: only the load blocks are integrated again (CTA-uniform)
   const FamilyDesc fa = A.fam[B.famA], fb = A.fam[B.famB];
   const int tA = wi.iA;
   const int nqt = A.nq[0], nqz = A.nq[2];
