@@ -280,6 +280,28 @@ def sub_config(name, kind, p, B, steps, local, rank, world, maxr, peak_tf, hbm_g
     r = eng.bench(norder, noe, nof, xnod, reps=steps, lanes=lanes, etype=et)
     ms = maxr(r["ms_total"]) / steps
     eng.close()
+    e2e = None
+    if mesh is not None:   # the same mesh end to end: host descriptors in, condensed systems (packed Hermitian Aii, Bi) out, Schur factors resident in HBM
+        from hp3d_b200.api import pinned_empty
+        eng_e = ElemEngine(kind, device=local, omega=omega, maxp=8, real_reduction=0 if complex_kernels else 1, aii_packed=1)
+        ni_max = max(d["ni"] for d in dims)
+        bufs = [pinned_empty((B, ni_max * (ni_max + 1) // 2), eng_e.dtype), pinned_empty((B, ni_max), eng_e.dtype)]
+        out = dict(Aii=bufs[0].a, Bi=bufs[1].a)
+        cl = eng_e.cloc_create()
+        for _ in range(2):
+            eng_e.elem_stc_batch_cloc(cl, norder, noe, nof, xnod, etype=et, out=out)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            re_ = eng_e.elem_stc_batch_cloc(cl, norder, noe, nof, xnod, etype=et, out=out)
+        te = maxr(time.perf_counter() - t0)
+        assert (re_["info"] == 0).all()
+        e2e = {"value": world * B * steps / te, "unit": "elements/s",
+               "d2h_bytes_per_step": int(sum(es * (d["ni"] * (d["ni"] + 1) // 2 + d["ni"]) + 4 for d in dims)),
+               "call": "hp3d_gpu_elem_batch_cloc (aii_packed = 1), pinned host arrays, Schur factors resident in HBM"}
+        eng_e.cloc_destroy(cl)
+        eng_e.close()
+        for b in bufs:
+            b.free()
     tf = F / (ms * 1e-3) / 1e12
     gbs = out_bytes / (ms * 1e-3) / 1e9
     cpu = None
@@ -293,7 +315,7 @@ def sub_config(name, kind, p, B, steps, local, rank, world, maxr, peak_tf, hbm_g
             v, dtc, blas = cpu_rate_mixed(kind, mesh, idx, cores, omega)
             what = f"{len(idx)} randomly chosen elements of the same mesh"
         cpu = {"value": v, "unit": "elements/s", "cores": cores, "kind": "port", "sample": f"{what} in {dtc:.1f} s; {cores} threads over elements, single-threaded {'OpenBLAS' if blas else 'built-in loops'} per element"}
-    return {"workload": name, "value": world * B / (ms * 1e-3), "unit": "elements/s", "elements_per_gpu_per_step": B, "steps": steps, "ms_per_step": ms, "cpu_baseline": cpu,
+    return {"workload": name, "value": world * B / (ms * 1e-3), "unit": "elements/s", "elements_per_gpu_per_step": B, "steps": steps, "ms_per_step": ms, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches_per_step": r["launches"] / steps, "dense_tflops_per_gpu": tf, "frac_fp64_tensor_peak": tf / peak_tf,
             "dense_tflops_on_reference_count": F_ref / (ms * 1e-3) / 1e12,
             "algorithmic_output_gbs_per_gpu": gbs, "frac_hbm": gbs / hbm_gbs,
