@@ -169,7 +169,7 @@ int build_classes(Plan *p, int nel, const int *etype, const int *norder, const i
   }
   if (getenv("HP3D_TRACE"))
     fprintf(stderr, "[hp3d] signature lookup + upload: %.1f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_up0).count());
-  size_t MERGE_TARGET = 32;   // elements (sweep on the 576-element hp mesh: 1 -> 881, 8 -> 1128, 16 -> 1261, 32 -> 1306, 64 -> 1268 elements/s)
+  size_t MERGE_TARGET = 16;   // elements (576-element hp mesh, round-2 scheduler with per-lane class binding: 8 -> 1495, 16 -> 1503, 32 -> 1476, 64 -> 1410, 128 -> 1374 elements/s; round 1: 32)
   if (const char *mt = getenv("HP3D_MERGE_TARGET")) MERGE_TARGET = (size_t)atoi(mt);
   for (auto &b : base) {
     std::vector<SigGroup> &v = b.second;
