@@ -14,6 +14,7 @@
 // group the reference's own order is kept (stc gather order, src/modules/stc.F90:226-261), so the output maps
 // are identities and orientation signs are applied here, at integration time.
 #pragma once
+#include <cstdlib>
 #include "dense_pipeline.cuh"
 #include "hexa_space.hpp"
 #include "integ_kernels.cuh"
@@ -532,6 +533,7 @@ inline bool compile_signature(const FormParams &P, const int norder[19], const i
   // z contraction (every warp owns one m-tile there), at most 448
   int warps = (std::max(64, items) + 31) / 32;
   if (nMmax <= 14) warps = std::min(14 / nMmax * nMmax, (warps + nMmax - 1) / nMmax * nMmax);
+  if (const char *w = getenv("HP3D_TP3_WARPS")) warps = atoi(w);   // experiment hook
   S.threads = 32 * std::max(2, std::min(14, warps));
   // dynamic smem of tp3_kernel: tables | Z | F [ntmax][fs] | T1 | U | Q [2][...]  (all offsets even: 16-byte aligned for the TMA bulk copies)
   S.smem_f_off = (size_t)12 * TABSZ + (size_t)4 * S.nmax * S.nmax;   // tables | z tables re-laid out [4][NMAX][NMAX]
